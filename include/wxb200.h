@@ -1,0 +1,169 @@
+/*
+ * wxb200.h — C-ABI of the B200-native WhisperX hot path (libwxb200.so).
+ *
+ * The reference (sooth/whisperx-mlx) has no FFI: its plugin boundary is the duck-typed
+ * Python backend interface (whisperx/backends/base.py:8-57, whisperx/asr.py:67-87) and the
+ * module-level aligner functions (whisperx/alignment.py:113,387,447,500).  This header is the
+ * C-ABI that sits directly under our Python mirror of that interface; every entry point names
+ * the reference function whose numeric core it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross the boundary.
+ *   - pointers named *_dev are device pointers on the ctx's GPU, *_host are host pointers.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*, NULL = legacy
+ *     default stream) unless stated otherwise; buffers are caller-owned and must stay alive
+ *     until the stream reaches the call.
+ *   - return value 0 = ok, negative = error; wxb_last_error() gives the message.  Nothing
+ *     throws across the ABI.  There is no CPU fallback: without a usable sm_100 GPU
+ *     wxb_create() fails.
+ *   - a wxb_ctx is bound to one device and is NOT thread-safe (one ctx per process per GPU).
+ */
+#ifndef WXB200_H
+#define WXB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WXB_ABI_VERSION 1
+
+typedef struct wxb_ctx wxb_ctx;
+
+enum {
+  WXB_OK = 0,
+  WXB_ERR_INVALID = -1,   /* bad argument */
+  WXB_ERR_CUDA = -2,      /* CUDA runtime / driver error */
+  WXB_ERR_UNSUPPORTED = -3, /* device is not sm_100 or a shape is outside the kernel's range */
+  WXB_ERR_STATE = -4      /* call made in the wrong order (e.g. encode before set_model) */
+};
+
+/* ------------------------------------------------------------------------------------------
+ * Context
+ * ---------------------------------------------------------------------------------------- */
+int wxb_abi_version(void);
+/* Create a context on CUDA device `device`.  Fails with WXB_ERR_UNSUPPORTED if the device's
+ * compute capability is not 10.x. */
+int wxb_create(int device, wxb_ctx** out);
+void wxb_destroy(wxb_ctx* ctx);
+/* Library-owned string, valid until the next call on ctx.  ctx may be NULL (global slot used
+ * by wxb_create failures). */
+const char* wxb_last_error(const wxb_ctx* ctx);
+/* Number of kernel launches issued by this ctx since creation (bench.py's gpu_launches). */
+int64_t wxb_launch_count(const wxb_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  log-mel frontend — replaces whisperx/audio.py:112-159 log_mel_spectrogram
+ *     (reflect-padded STFT n_fft=400 hop=160 periodic Hann, |X|^2, mel filterbank,
+ *      log10(max(.,1e-10)), max(., per-chunk max - 8), (.+4)/4).
+ *
+ * audio_dev      f32, all chunks back to back
+ * chunk_off_host int64[n_chunks]  first sample of each chunk inside audio_dev
+ * chunk_len_host int32[n_chunks]  valid samples of each chunk (<= n_samples_padded)
+ * n_samples_padded  every chunk is treated as zero-padded on the right to this many samples
+ *                   before the STFT (audio.py:147-148 `padding`); >= 400.
+ *                   n_frames = n_samples_padded / 160 (floor; the reference drops the last frame).
+ * filters_dev    f32 [n_mels, 201] (assets/mel_filters.npz), n_mels in {80,128} (any <= 128 ok)
+ * mel_out_dev    f32 [n_chunks, n_mels, n_frames]   (reference layout, audio.py:159)
+ * The max used by the clamp is PER CHUNK (the reference is called once per chunk).
+ * ---------------------------------------------------------------------------------------- */
+int wxb_logmel(wxb_ctx* ctx, const float* audio_dev, const int64_t* chunk_off_host,
+               const int32_t* chunk_len_host, int n_chunks, int n_samples_padded, int n_mels,
+               const float* filters_dev, float* mel_out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4  CTC forced alignment — replaces whisperx/alignment.py:387-404 get_trellis,
+ *     :407-437 get_wildcard_emission, :447-481 backtrack, :500-579 backtrack_beam(beam_width=2)
+ *
+ * emis_dev   f32 [sum T, V] log-probabilities (already log_softmax'ed, alignment.py:258),
+ *            segments back to back
+ * t_off_host int32[n_seg+1]   frame offsets of each segment inside emis_dev
+ * tok_dev    int32[sum N]     token ids per segment back to back, -1 = wildcard
+ * n_off_host int32[n_seg+1]   token offsets
+ * mode       WXB_CTC_BACKTRACK (alignment.py:447) or WXB_CTC_BEAM2 (alignment.py:500, width 2)
+ * trellis_dev   optional f32 buffer of sum(T_i*N_i) elements receiving every segment's trellis
+ *               (row-major [T_i, N_i], back to back, offsets = prefix sums of T_i*N_i);
+ *               NULL = use the ctx workspace.
+ * path_tok_dev  int32[sum T]  token_index of the path point at each frame
+ * path_lp_dev   f32[sum T]    log-prob of that point (exact emission value; score = exp(lp))
+ * path_prob_dev f32[sum T]    expf(lp) computed on the device (may differ from torch's exp by
+ *                             an ulp; indices and lp are bit-exact)
+ * status_dev    int32[n_seg]  0 ok, 1 = "backtrack failed" (alignment.py:271 / assert :451)
+ * ---------------------------------------------------------------------------------------- */
+enum { WXB_CTC_BACKTRACK = 0, WXB_CTC_BEAM2 = 1, WXB_CTC_TRELLIS_ONLY = 2 };
+
+int wxb_ctc_align(wxb_ctx* ctx, const float* emis_dev, const int32_t* t_off_host,
+                  const int32_t* tok_dev, const int32_t* n_off_host, int n_seg, int V, int blank,
+                  int mode, float* trellis_dev, int32_t* path_tok_dev, float* path_lp_dev,
+                  float* path_prob_dev, int32_t* status_dev, void* stream);
+
+/* In-place log_softmax over the last dim of f32 [rows, V] (alignment.py:258), one warp per row
+ * with a warp-shuffle logsumexp.  Provided so emissions can stay on the device. */
+int wxb_log_softmax_rows(wxb_ctx* ctx, float* x_dev, int64_t rows, int V, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2/K3  Whisper model — replaces the mlx_whisper model the reference delegates to
+ *     (call sites: whisperx/backends/mlx_lightning.py:163-196, mlx_whisper_batch_decoder.py:
+ *      37-100 logits, :267-303 update, :317-384 main loop).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t n_mels;        /* 80 | 128 */
+  int32_t n_audio_ctx;   /* 1500 */
+  int32_t n_audio_state; /* d */
+  int32_t n_audio_head;
+  int32_t n_audio_layer;
+  int32_t n_vocab;
+  int32_t n_text_ctx;    /* 448 */
+  int32_t n_text_state;
+  int32_t n_text_head;
+  int32_t n_text_layer;
+} wxb_dims;
+
+/* Weight table: `names[i]` identifies tensor i (OpenAI-Whisper parameter names, e.g.
+ * "encoder.blocks.0.attn.query.weight"); ptrs_dev[i] is a device pointer to a contiguous
+ * tensor of the documented dtype (bf16 matrices, f32 biases / LN / positional tables; see
+ * DESIGN.md).  The library BORROWS the pointers: the caller keeps the tensors alive until
+ * wxb_destroy or the next wxb_set_model. */
+int wxb_set_model(wxb_ctx* ctx, const wxb_dims* dims, const char* const* names,
+                  const void* const* ptrs_dev, int n_tensors);
+
+/* Encoder: mel f32 [B, n_mels, 3000] (output layout of wxb_logmel) -> enc_out bf16 [B,1500,d]. */
+int wxb_encode(wxb_ctx* ctx, const float* mel_dev, int B, void* enc_out_dev, void* stream);
+
+typedef struct {
+  int32_t eot;             /* end-of-transcript token id */
+  int32_t no_speech;       /* <|nospeech|> id, or -1 */
+  int32_t sample_len;      /* max sampled tokens (reference: n_text_ctx // 2 = 224) */
+  int32_t suppress_blank;  /* 1: at the first sampled position suppress blank_token and eot */
+  int32_t blank_token;     /* id of encode(" ") (only used when suppress_blank) */
+  int32_t n_suppress;      /* length of suppress_dev */
+  const int32_t* suppress_dev; /* device int32 ids set to -inf every step */
+  int32_t check_every;     /* host polls "all rows hit EOT" every this many steps (0 = 16) */
+} wxb_decode_opts;
+
+/* Batched greedy KV-cache decode.  enc_out bf16 [B,1500,d]; prompt_host int32[prompt_len]
+ * (same prompt for every row, mlx_whisper_batch_decoder.py:406-407).  Outputs (device):
+ * tokens_out int32 [B, sample_len] sampled tokens (EOT-padded), n_tokens int32[B] tokens before
+ * the first EOT, sum_logprob f32[B], no_speech_prob f32[B] (softmax prob of no_speech at the
+ * SOT position, unfiltered).  This call synchronises `stream` internally when polling. */
+int wxb_decode_greedy(wxb_ctx* ctx, const void* enc_out_dev, int B, const int32_t* prompt_host,
+                      int prompt_len, const wxb_decode_opts* opts, int32_t* tokens_out_dev,
+                      int32_t* n_tokens_dev, float* sum_logprob_dev, float* no_speech_prob_dev,
+                      void* stream);
+
+/* Teacher-forced logits for parity tests: runs the decoder over tokens_host int32 [B, n_tok]
+ * and writes the f32 logits of every position to logits_out_dev [B, n_tok, n_vocab]. */
+int wxb_decoder_logits(wxb_ctx* ctx, const void* enc_out_dev, int B, const int32_t* tokens_host,
+                       int n_tok, float* logits_out_dev, void* stream);
+
+/* Stand-alone bf16 GEMM used by the encoder (exposed for parity tests and roofline timing):
+ * D[M,N] = A[M,K] * W[N,K]^T (+bias[N]) (GELU) ; A,W bf16 row-major, D bf16 or f32.
+ * flags: bit0 = GELU, bit1 = output f32. */
+int wxb_gemm_bf16(wxb_ctx* ctx, const void* A_dev, const void* W_dev, const float* bias_dev,
+                  void* D_dev, int M, int N, int K, int flags, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WXB200_H */

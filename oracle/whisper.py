@@ -1,0 +1,177 @@
+"""
+ORACLE — test infrastructure only.  Never imported by the product path (whisperx-mlx_b200/);
+only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it.
+
+Torch-CPU fp32 restatement of the Whisper model and of the reference's batched greedy loop.
+
+The model arithmetic is NOT in /root/reference: the reference delegates it to the un-vendored
+third-party package `mlx-whisper` (pyproject.toml:13, git branch pin `whisperx-optimizations`,
+no commit hash; on top of mlx>=0.26.0).  This file restates the published OpenAI Whisper
+architecture (the one mlx_whisper ports) and is cross-checked in tests/test_oracle_cpu.py against
+transformers 5.5.0 `WhisperModel` (modeling_whisper.py:541-648 encoder, :650-798 decoder) built
+from an explicit WhisperConfig.  PARITY UNPINNED for this piece: the reference's own tests hold no
+known-answer vectors for mel twin / encoder / decoder; parity is anchored on the
+reference's call sites and in-tree loop:
+    /root/reference/mlx_whisper_batch_decoder.py:267-303  BatchGreedyDecoder.update
+    /root/reference/mlx_whisper_batch_decoder.py:317-384  BatchDecodingTask._main_loop_batch
+    /root/reference/mlx_whisper_batch_decoder.py:386-468  run (EOT trimming, avg_logprob)
+    /root/reference/whisperx/backends/mlx_lightning.py:187-196  DecodingOptions(temperature=0)
+"""
+import math
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn.functional as F
+
+
+def sinusoids(length: int, channels: int, max_timescale: float = 10000.0) -> torch.Tensor:
+    """OpenAI Whisper encoder positions (HF modeling_whisper.py:55-62)."""
+    assert channels % 2 == 0
+    log_inc = math.log(max_timescale) / (channels // 2 - 1)
+    inv = torch.exp(-log_inc * torch.arange(channels // 2, dtype=torch.float32))
+    t = torch.arange(length, dtype=torch.float32)[:, None] * inv[None, :]
+    return torch.cat([t.sin(), t.cos()], dim=1)
+
+
+def _ln(x, w, b):
+    return F.layer_norm(x, (x.shape[-1],), w, b, 1e-5)
+
+
+def _mha(q, k, v, n_head, causal_offset: Optional[int] = None):
+    """q [B,Tq,d], k/v [B,Tk,d]; softmax(q k^T / sqrt(dh)) v.  causal_offset = absolute position of
+    q[0] for causal masking over absolute key positions (None = no mask)."""
+    B, Tq, d = q.shape
+    Tk = k.shape[1]
+    dh = d // n_head
+    qh = q.view(B, Tq, n_head, dh).transpose(1, 2)
+    kh = k.view(B, Tk, n_head, dh).transpose(1, 2)
+    vh = v.view(B, Tk, n_head, dh).transpose(1, 2)
+    s = (qh @ kh.transpose(-1, -2)) * (dh ** -0.5)
+    if causal_offset is not None:
+        qi = torch.arange(Tq)[:, None] + causal_offset
+        ki = torch.arange(Tk)[None, :]
+        s = s.masked_fill(ki > qi, float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    return (p @ vh).transpose(1, 2).reshape(B, Tq, d)
+
+
+def _lin(x, w: Dict[str, torch.Tensor], name: str):
+    return F.linear(x, w[name + ".weight"], w.get(name + ".bias"))
+
+
+def encoder_forward(w: Dict[str, torch.Tensor], dims, mel: torch.Tensor, return_layers: bool = False):
+    """mel f32 [B, n_mels, 3000] -> [B, 1500, d].  conv1 k3 p1, conv2 k3 s2 p1, GELU(erf) after each,
+    + sinusoid positions, pre-LN blocks, ln_post."""
+    x = F.gelu(F.conv1d(mel, w["encoder.conv1.weight"], w["encoder.conv1.bias"], padding=1))
+    x = F.gelu(F.conv1d(x, w["encoder.conv2.weight"], w["encoder.conv2.bias"], stride=2, padding=1))
+    x = x.permute(0, 2, 1) + w["encoder.positional_embedding"][None]
+    layers = [x]
+    for i in range(dims["n_audio_layer"]):
+        p = f"encoder.blocks.{i}"
+        h = _ln(x, w[p + ".attn_ln.weight"], w[p + ".attn_ln.bias"])
+        a = _mha(_lin(h, w, p + ".attn.query"), _lin(h, w, p + ".attn.key"), _lin(h, w, p + ".attn.value"),
+                 dims["n_audio_head"])
+        x = x + _lin(a, w, p + ".attn.out")
+        h = _ln(x, w[p + ".mlp_ln.weight"], w[p + ".mlp_ln.bias"])
+        x = x + _lin(F.gelu(_lin(h, w, p + ".mlp.0")), w, p + ".mlp.2")
+        layers.append(x)
+    x = _ln(x, w["encoder.ln_post.weight"], w["encoder.ln_post.bias"])
+    return (x, layers) if return_layers else x
+
+
+class DecoderCache:
+    """Self-attention K/V grow by one position per call; cross K/V are computed once."""
+
+    def __init__(self, w, dims, enc_out: torch.Tensor):
+        self.self_k: List[Optional[torch.Tensor]] = [None] * dims["n_text_layer"]
+        self.self_v: List[Optional[torch.Tensor]] = [None] * dims["n_text_layer"]
+        self.cross_k, self.cross_v = [], []
+        for i in range(dims["n_text_layer"]):
+            p = f"decoder.blocks.{i}.cross_attn"
+            self.cross_k.append(_lin(enc_out, w, p + ".key"))
+            self.cross_v.append(_lin(enc_out, w, p + ".value"))
+        self.pos = 0
+
+
+def decoder_forward(w, dims, tokens: torch.Tensor, cache: DecoderCache) -> torch.Tensor:
+    """tokens int64 [B, n] appended at positions cache.pos.. ; returns f32 logits [B, n, V]
+    (tied output head, HF modeling_whisper.py:971)."""
+    B, n = tokens.shape
+    pos0 = cache.pos
+    x = w["decoder.token_embedding.weight"][tokens] + w["decoder.positional_embedding"][pos0:pos0 + n][None]
+    for i in range(dims["n_text_layer"]):
+        p = f"decoder.blocks.{i}"
+        h = _ln(x, w[p + ".attn_ln.weight"], w[p + ".attn_ln.bias"])
+        k_new, v_new = _lin(h, w, p + ".attn.key"), _lin(h, w, p + ".attn.value")
+        cache.self_k[i] = k_new if cache.self_k[i] is None else torch.cat([cache.self_k[i], k_new], 1)
+        cache.self_v[i] = v_new if cache.self_v[i] is None else torch.cat([cache.self_v[i], v_new], 1)
+        a = _mha(_lin(h, w, p + ".attn.query"), cache.self_k[i], cache.self_v[i], dims["n_text_head"],
+                 causal_offset=pos0)
+        x = x + _lin(a, w, p + ".attn.out")
+        h = _ln(x, w[p + ".cross_attn_ln.weight"], w[p + ".cross_attn_ln.bias"])
+        a = _mha(_lin(h, w, p + ".cross_attn.query"), cache.cross_k[i], cache.cross_v[i], dims["n_text_head"])
+        x = x + _lin(a, w, p + ".cross_attn.out")
+        h = _ln(x, w[p + ".mlp_ln.weight"], w[p + ".mlp_ln.bias"])
+        x = x + _lin(F.gelu(_lin(h, w, p + ".mlp.0")), w, p + ".mlp.2")
+    cache.pos += n
+    x = _ln(x, w["decoder.ln.weight"], w["decoder.ln.bias"])
+    return (x @ w["decoder.token_embedding.weight"].t()).float()
+
+
+def greedy_decode(w, dims, enc_out: torch.Tensor, prompt: List[int], eot: int, no_speech: int = -1,
+                  sample_len: int = 224, suppress_blank: bool = False, blank_token: int = 220,
+                  suppress_tokens=(), return_logits: bool = False):
+    """Batched greedy loop, mlx_whisper_batch_decoder.py:317-384 + :267-303, with the SuppressBlank /
+    SuppressTokens filters (timestamp rules are not applied: without_timestamps prompt).
+
+    Returns dict(tokens=[B][...] up to first EOT, sum_logprob[B], avg_logprob[B], no_speech_prob[B],
+    all_tokens int64 [B, n_sampled], step_logits (optional, filtered f32 logits per step)).
+    no_speech_prob follows upstream Whisper (softmax at the SOT position, unfiltered); the in-tree
+    batch loop takes it from the filtered last-prompt logits (:347-352) - see DESIGN.md."""
+    B = enc_out.shape[0]
+    cache = DecoderCache(w, dims, enc_out)
+    toks = torch.tensor(prompt, dtype=torch.long)[None].expand(B, -1).contiguous()
+    logits_all = decoder_forward(w, dims, toks, cache)
+    if no_speech >= 0:
+        no_speech_prob = torch.softmax(logits_all[:, 0].float(), -1)[:, no_speech]
+    else:
+        no_speech_prob = torch.full((B,), float("nan"))
+    logits = logits_all[:, -1].clone()
+    sum_lp = torch.zeros(B)
+    last = toks[:, -1]
+    sampled, step_logits = [], []
+    suppress = torch.tensor(list(suppress_tokens), dtype=torch.long)
+    n_ctx = dims["n_text_ctx"]
+    for i in range(sample_len):
+        if i == 0 and suppress_blank:
+            logits[:, blank_token] = -float("inf")
+            logits[:, eot] = -float("inf")
+        if len(suppress):
+            logits[:, suppress] = -float("inf")
+        if return_logits:
+            step_logits.append(logits.clone())
+        nxt = logits.argmax(-1)
+        lp = logits - torch.logsumexp(logits, -1, keepdim=True)
+        sum_lp = sum_lp + lp[torch.arange(B), nxt] * (last != eot)
+        nxt = torch.where(last == eot, torch.full_like(nxt, eot), nxt)
+        sampled.append(nxt)
+        last = nxt
+        if bool((last == eot).all()):
+            break
+        if len(prompt) + len(sampled) > n_ctx:
+            break
+        if i + 1 < sample_len:
+            logits = decoder_forward(w, dims, nxt[:, None], cache)[:, -1].clone()
+    all_tokens = torch.stack(sampled, 1)
+    out_tokens = []
+    for b in range(B):
+        row = all_tokens[b].tolist()
+        if eot in row:
+            row = row[:row.index(eot)]
+        out_tokens.append(row)
+    avg = [float(s) / (len(t) + 1) for s, t in zip(sum_lp.tolist(), out_tokens)]
+    res = dict(tokens=out_tokens, sum_logprob=sum_lp, avg_logprob=avg, no_speech_prob=no_speech_prob,
+               all_tokens=all_tokens)
+    if return_logits:
+        res["step_logits"] = step_logits
+    return res

@@ -1,0 +1,98 @@
+"""Host-side logic of the product path that needs no GPU: chunk merging, padding, run-length merge,
+and the char/word/sentence assembly of align() (fed with oracle paths), against the reference's
+golden align() output."""
+import json
+import os
+
+import numpy as np
+import torch
+
+from fake_ctc_model import FakeCTCModel, METADATA, synthetic_speech
+from oracle import ctc as octc
+
+
+def test_merge_chunks_rule():
+    from whisperx.vads import SegmentX, Vad
+    segs = [SegmentX(0.0, 10.0), SegmentX(11.0, 25.0), SegmentX(26.0, 40.0), SegmentX(41.0, 50.0), SegmentX(90.0, 95.0)]
+    out = Vad.merge_chunks(segs, 30, onset=0.5, offset=0.363)
+    assert [(c["start"], c["end"]) for c in out] == [(0.0, 25.0), (26.0, 50.0), (90.0, 95.0)]
+    assert out[0]["segments"] == [(0.0, 10.0), (11.0, 25.0)]
+    one = Vad.merge_chunks([SegmentX(3.0, 50.0)], 30)  # a single over-long region is kept whole
+    assert [(c["start"], c["end"]) for c in one] == [(3.0, 50.0)]
+
+
+def test_pad_or_trim():
+    from whisperx.audio import N_SAMPLES, pad_or_trim
+    a = np.arange(10, dtype=np.float32)
+    assert pad_or_trim(a, 4).tolist() == [0, 1, 2, 3]
+    assert pad_or_trim(a, 12).tolist() == list(range(10)) + [0, 0]
+    t = torch.arange(6.0).view(2, 3)
+    assert pad_or_trim(t, 5, axis=1).shape == (2, 5) and pad_or_trim(t, 2, axis=1).tolist() == [[0, 1], [3, 4]]
+    assert pad_or_trim(np.zeros(5, np.float32)).shape == (N_SAMPLES,)
+
+
+def test_synthetic_cuts():
+    from whisperx.vads import synthetic_vad_cuts
+    u = synthetic_vad_cuts(1800.0)
+    assert len(u) == 60 and u[-1]["end"] == 1800.0
+    r = synthetic_vad_cuts(1800.0, mode="ragged")
+    assert r[0]["start"] == 0.0 and r[-1]["end"] == 1800.0 and all(c["end"] - c["start"] <= 30.0 + 1e-6 for c in r)
+
+
+def _oracle_align(transcript, audio, return_chars):
+    """align() with the numeric core swapped for the numpy oracle — exercises exactly the host code
+    the product runs around kernel K4."""
+    import whisperx.alignment as wa
+
+    audio_t = torch.from_numpy(audio)[None]
+    model = FakeCTCModel()
+    out = []
+    for seg in transcript:
+        prep = wa._prepare_segment(seg["text"], METADATA["dictionary"], True)
+        plain = {"start": seg["start"], "end": seg["end"], "text": seg["text"], "words": [],
+                 "chars": [] if return_chars else None}
+        if not prep["clean_char"] or seg["start"] >= audio_t.shape[1] / 16000:
+            out.append(plain)
+            continue
+        text_clean = "".join(prep["clean_char"])
+        tokens = [METADATA["dictionary"].get(c, -1) for c in text_clean]
+        wave = audio_t[:, int(seg["start"] * 16000):int(seg["end"] * 16000)]
+        if wave.shape[-1] < 400:
+            wave = torch.nn.functional.pad(wave, (0, 400 - wave.shape[-1]))
+        em = torch.log_softmax(model(wave)[0], -1)[0].numpy()
+        tr = octc.get_trellis(em, tokens, 0)
+        path = octc.backtrack_beam(tr, em, tokens, 0, beam_width=2)
+        if path is None:
+            out.append(plain)
+            continue
+        pts = [wa.Point(p.token_index, p.time_index, p.score) for p in path]
+        cs = wa.merge_repeats(pts, text_clean)
+        ratio = (seg["end"] - seg["start"]) * 1 / (tr.shape[0] - 1)
+        out += wa._assemble(seg["text"], prep, cs, ratio, seg["start"], True, "nearest", return_chars)
+    return out
+
+
+def _close(a, b, path=""):
+    if isinstance(a, dict):
+        assert set(a) == set(b), (path, set(a) ^ set(b))
+        for k in a:
+            _close(a[k], b[k], f"{path}.{k}")
+    elif isinstance(a, (list, tuple)):
+        assert len(a) == len(b), path
+        for i, (x, y) in enumerate(zip(a, b)):
+            _close(x, y, f"{path}[{i}]")
+    elif isinstance(a, (float, np.floating)) or isinstance(b, (float, np.floating)):
+        if a is None or b is None:
+            assert a is None and b is None, path
+        else:
+            assert abs(float(a) - float(b)) <= 1.001e-3, (path, a, b)
+    else:
+        assert a == b, (path, a, b)
+
+
+def test_align_host_assembly_matches_reference_golden(golden_dir):
+    g = json.load(open(os.path.join(golden_dir, "align_golden.json")))
+    audio = synthetic_speech(g["audio_seconds"], seed=g["audio_seed"])
+    for tag, chars in (("words", False), ("chars", True)):
+        got = json.loads(json.dumps(_oracle_align(g["transcript"], audio, chars), default=float))
+        _close(got, g["result"][tag]["segments"], tag)

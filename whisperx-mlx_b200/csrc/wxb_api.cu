@@ -1,0 +1,96 @@
+// wxb_api.cu — context lifetime, error slot, workspace management (C-ABI in include/wxb200.h).
+#include "wxb_common.cuh"
+#include <stdarg.h>
+#include <string.h>
+
+static std::string g_global_err;
+
+int wxb_fail(wxb_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx)
+    ctx->err = buf;
+  else
+    g_global_err = buf;
+  return code;
+}
+
+int wxb_reserve(wxb_ctx* ctx, wxb_buf& b, size_t bytes) {
+  if (bytes <= b.cap) return WXB_OK;
+  if (b.p) {
+    // buffers may still be in use by queued work: a blocking free is the safe choice here
+    cudaError_t e = cudaFree(b.p);
+    if (e != cudaSuccess) return wxb_fail(ctx, WXB_ERR_CUDA, "cudaFree: %s", cudaGetErrorString(e));
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  size_t want = bytes + bytes / 4 + 256;
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess)
+    return wxb_fail(ctx, WXB_ERR_CUDA, "cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
+  b.cap = want;
+  return WXB_OK;
+}
+
+void* wxb_named(wxb_ctx* ctx, const char* name, size_t bytes, bool zero_on_alloc) {
+  wxb_buf& b = ctx->named[name];
+  if (bytes <= b.cap) return b.p;
+  size_t old = b.cap;
+  if (wxb_reserve(ctx, b, bytes) != WXB_OK) return nullptr;
+  if (zero_on_alloc && b.cap != old) cudaMemset(b.p, 0, b.cap);
+  return b.p;
+}
+
+extern "C" {
+
+int wxb_abi_version(void) { return WXB_ABI_VERSION; }
+
+int wxb_create(int device, wxb_ctx** out) {
+  if (!out) return wxb_fail(nullptr, WXB_ERR_INVALID, "wxb_create: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return wxb_fail(nullptr, WXB_ERR_CUDA, "wxb_create: no CUDA device (%s); there is no CPU fallback",
+                    e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n)
+    return wxb_fail(nullptr, WXB_ERR_INVALID, "wxb_create: device %d out of range [0,%d)", device, n);
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess)
+    return wxb_fail(nullptr, WXB_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return wxb_fail(nullptr, WXB_ERR_UNSUPPORTED,
+                    "wxb_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                    device, prop.major, prop.minor);
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return wxb_fail(nullptr, WXB_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  wxb_ctx* c = new wxb_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  *out = c;
+  return WXB_OK;
+}
+
+void wxb_destroy(wxb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  wxb_model_free(ctx);
+  wxb_buf* bufs[] = {&ctx->ws_ctc_trellis, &ctx->ws_ctc_hist, &ctx->ws_ctc_meta, &ctx->ws_mel_max,
+                     &ctx->ws_mel_band};
+  for (wxb_buf* b : bufs)
+    if (b->p) cudaFree(b->p);
+  for (auto& kv : ctx->named)
+    if (kv.second.p) cudaFree(kv.second.p);
+  delete ctx;
+}
+
+const char* wxb_last_error(const wxb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_global_err.c_str(); }
+
+int64_t wxb_launch_count(const wxb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

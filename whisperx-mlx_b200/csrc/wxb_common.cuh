@@ -1,0 +1,80 @@
+// wxb_common.cuh — context, error plumbing and small device helpers shared by all kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <map>
+#include "../../include/wxb200.h"
+
+struct wxb_buf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct wxb_model;    // defined in wxb_model.cuh
+struct wxb_dec_state;
+
+struct wxb_ctx {
+  int device = 0;
+  int sm_count = 148;
+  std::string err;
+  int64_t launches = 0;
+  // growable device workspaces (never shrunk; freed in wxb_destroy)
+  wxb_buf ws_ctc_trellis, ws_ctc_hist, ws_ctc_meta, ws_mel_max, ws_mel_band;
+  std::map<std::string, wxb_buf> named;  // model-side activations / caches keyed by name
+  wxb_model* model = nullptr;
+  void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled (driver entry point), lazily resolved
+  bool lm_tables_ready = false;  // log-mel window/twiddle tables uploaded to this device
+};
+
+int wxb_fail(wxb_ctx* ctx, int code, const char* fmt, ...);
+int wxb_reserve(wxb_ctx* ctx, wxb_buf& b, size_t bytes);
+void* wxb_named(wxb_ctx* ctx, const char* name, size_t bytes, bool zero_on_alloc = false);
+void wxb_model_free(wxb_ctx* ctx);  // wxb_model.cu
+
+#define WXB_CUDA(ctx, expr)                                                              \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess)                                                               \
+      return wxb_fail((ctx), WXB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,               \
+                      cudaGetErrorString(_e), __FILE__, __LINE__);                       \
+  } while (0)
+
+#define WXB_LAUNCH_CHECK(ctx)                                                            \
+  do {                                                                                   \
+    (ctx)->launches++;                                                                   \
+    cudaError_t _e = cudaGetLastError();                                                 \
+    if (_e != cudaSuccess)                                                               \
+      return wxb_fail((ctx), WXB_ERR_CUDA, "kernel launch failed: %s (%s:%d)",           \
+                      cudaGetErrorString(_e), __FILE__, __LINE__);                       \
+  } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// torch.maximum semantics: NaN if either operand is NaN
+__device__ __forceinline__ float nanmax(float a, float b) {
+  return (a != a) ? a : ((b != b) ? b : fmaxf(a, b));
+}
+// total-order float max through integer atomics (works for mixed signs; init with -inf)
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  if (v >= 0.f)
+    atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else
+    atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+#endif

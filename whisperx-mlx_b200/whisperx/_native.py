@@ -1,0 +1,264 @@
+"""
+ctypes binding of libwxb200.so (include/wxb200.h) + a thin per-GPU context object.
+
+PyTorch is used only to own device memory and streams; every numeric call below goes through the
+C-ABI.  There is no CPU fallback: if the library is missing or no sm_100 GPU is present, the
+constructors raise.
+"""
+import ctypes as C
+import os
+import threading
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "lib", "libwxb200.so")
+_lib = None
+_lib_lock = threading.Lock()
+
+CTC_BACKTRACK, CTC_BEAM2, CTC_TRELLIS_ONLY = 0, 1, 2
+
+
+class WxbError(RuntimeError):
+    pass
+
+
+class Dims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "n_mels", "n_audio_ctx", "n_audio_state", "n_audio_head", "n_audio_layer",
+        "n_vocab", "n_text_ctx", "n_text_state", "n_text_head", "n_text_layer")]
+
+
+class DecodeOpts(C.Structure):
+    _fields_ = [("eot", C.c_int32), ("no_speech", C.c_int32), ("sample_len", C.c_int32),
+                ("suppress_blank", C.c_int32), ("blank_token", C.c_int32), ("n_suppress", C.c_int32),
+                ("suppress_dev", C.c_void_p), ("check_every", C.c_int32)]
+
+
+def load_library(path: Optional[str] = None):
+    """dlopen libwxb200.so and declare every prototype of include/wxb200.h."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None and path is None:
+            return _lib
+        p = path or os.environ.get("WXB200_LIB", _LIB_PATH)
+        if not os.path.exists(p):
+            raise WxbError(
+                f"libwxb200.so not found at {p}: build it with `python __graft_entry__.py` "
+                "(make -C whisperx-mlx_b200/csrc). There is no CPU fallback.")
+        lib = C.CDLL(p)
+        vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+        lib.wxb_abi_version.restype = i32
+        lib.wxb_abi_version.argtypes = []
+        lib.wxb_create.restype = i32
+        lib.wxb_create.argtypes = [i32, C.POINTER(vp)]
+        lib.wxb_destroy.restype = None
+        lib.wxb_destroy.argtypes = [vp]
+        lib.wxb_last_error.restype = C.c_char_p
+        lib.wxb_last_error.argtypes = [vp]
+        lib.wxb_launch_count.restype = i64
+        lib.wxb_launch_count.argtypes = [vp]
+        lib.wxb_logmel.restype = i32
+        lib.wxb_logmel.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp]
+        lib.wxb_ctc_align.restype = i32
+        lib.wxb_ctc_align.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+        lib.wxb_log_softmax_rows.restype = i32
+        lib.wxb_log_softmax_rows.argtypes = [vp, vp, i64, i32, vp]
+        lib.wxb_set_model.restype = i32
+        lib.wxb_set_model.argtypes = [vp, C.POINTER(Dims), C.POINTER(C.c_char_p), C.POINTER(vp), i32]
+        lib.wxb_encode.restype = i32
+        lib.wxb_encode.argtypes = [vp, vp, i32, vp, vp]
+        lib.wxb_decode_greedy.restype = i32
+        lib.wxb_decode_greedy.argtypes = [vp, vp, i32, vp, i32, C.POINTER(DecodeOpts), vp, vp, vp, vp, vp]
+        lib.wxb_decoder_logits.restype = i32
+        lib.wxb_decoder_logits.argtypes = [vp, vp, i32, vp, i32, vp, vp]
+        lib.wxb_gemm_bf16.restype = i32
+        lib.wxb_gemm_bf16.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
+        if lib.wxb_abi_version() != 1:
+            raise WxbError("libwxb200.so ABI version mismatch")
+        if path is None:
+            _lib = lib
+        return lib
+
+
+EXPORTED_SYMBOLS = (
+    "wxb_abi_version", "wxb_create", "wxb_destroy", "wxb_last_error", "wxb_launch_count", "wxb_logmel",
+    "wxb_ctc_align", "wxb_log_softmax_rows", "wxb_set_model", "wxb_encode", "wxb_decode_greedy",
+    "wxb_decoder_logits", "wxb_gemm_bf16")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _np_ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One wxb_ctx per (process, GPU).  Not thread-safe (mirrors the C contract)."""
+
+    def __init__(self, device_index: int = 0):
+        if not torch.cuda.is_available():
+            raise WxbError("whisperx b200 backend needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = load_library()
+        self.device_index = int(device_index)
+        self.device = torch.device("cuda", self.device_index)
+        torch.cuda.set_device(self.device)
+        torch.zeros(1, device=self.device)  # make sure the primary context exists
+        h = C.c_void_p()
+        rc = self.lib.wxb_create(self.device_index, C.byref(h))
+        if rc != 0:
+            raise WxbError(self.lib.wxb_last_error(None).decode())
+        self.h = h
+        self._keep: Dict[str, object] = {}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.wxb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---------------------------------------------------------------- helpers
+    def _check(self, rc: int):
+        if rc != 0:
+            raise WxbError(f"[wxb {rc}] " + self.lib.wxb_last_error(self.h).decode())
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.wxb_launch_count(self.h))
+
+    # ---------------------------------------------------------------- K1
+    def logmel(self, audio_dev: torch.Tensor, chunk_off: np.ndarray, chunk_len: np.ndarray,
+               n_samples_padded: int, n_mels: int, filters_dev: torch.Tensor,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """audio_dev f32 cuda [total]; returns f32 cuda [n_chunks, n_mels, n_samples_padded//160]."""
+        assert audio_dev.is_cuda and audio_dev.dtype == torch.float32 and audio_dev.is_contiguous()
+        assert filters_dev.is_cuda and filters_dev.dtype == torch.float32 and filters_dev.is_contiguous()
+        off = np.ascontiguousarray(chunk_off, dtype=np.int64)
+        ln = np.ascontiguousarray(chunk_len, dtype=np.int32)
+        n = len(off)
+        if n and int((off + ln).max()) > audio_dev.numel():
+            raise ValueError("chunk exceeds the audio buffer")
+        n_frames = n_samples_padded // 160
+        if out is None:
+            out = torch.empty((n, n_mels, n_frames), dtype=torch.float32, device=self.device)
+        assert out.is_contiguous() and out.dtype == torch.float32 and out.numel() == n * n_mels * n_frames
+        self._check(self.lib.wxb_logmel(self.h, _ptr(audio_dev), _np_ptr(off), _np_ptr(ln), n, n_samples_padded,
+                                        n_mels, _ptr(filters_dev), _ptr(out), self._stream()))
+        return out
+
+    # ---------------------------------------------------------------- K4
+    def ctc_align(self, emis_dev: torch.Tensor, t_off: np.ndarray, tok_dev: torch.Tensor, n_off: np.ndarray,
+                  blank: int, mode: int, want_trellis: bool = False):
+        """emis_dev f32 cuda [sumT, V] log-probs.  Returns dict of cuda tensors."""
+        assert emis_dev.is_cuda and emis_dev.dtype == torch.float32 and emis_dev.is_contiguous() and emis_dev.dim() == 2
+        assert tok_dev.is_cuda and tok_dev.dtype == torch.int32 and tok_dev.is_contiguous()
+        t_off = np.ascontiguousarray(t_off, dtype=np.int32)
+        n_off = np.ascontiguousarray(n_off, dtype=np.int32)
+        n_seg = len(t_off) - 1
+        sumT, V = emis_dev.shape
+        assert int(t_off[-1]) == sumT and int(n_off[-1]) == tok_dev.numel()
+        dev = self.device
+        path_tok = torch.full((max(sumT, 1),), -1, dtype=torch.int32, device=dev)
+        path_lp = torch.zeros((max(sumT, 1),), dtype=torch.float32, device=dev)
+        path_prob = torch.zeros((max(sumT, 1),), dtype=torch.float32, device=dev)
+        status = torch.full((max(n_seg, 1),), -1, dtype=torch.int32, device=dev)
+        trellis = None
+        if want_trellis:
+            T = np.diff(t_off).astype(np.int64)
+            N = np.diff(n_off).astype(np.int64)
+            trellis = torch.empty((max(int((T * N).sum()), 1),), dtype=torch.float32, device=dev)
+        self._check(self.lib.wxb_ctc_align(self.h, _ptr(emis_dev), _np_ptr(t_off), _ptr(tok_dev), _np_ptr(n_off),
+                                           n_seg, V, int(blank), int(mode), _ptr(trellis), _ptr(path_tok),
+                                           _ptr(path_lp), _ptr(path_prob), _ptr(status), self._stream()))
+        return dict(path_tok=path_tok[:sumT], path_lp=path_lp[:sumT], path_prob=path_prob[:sumT],
+                    status=status[:n_seg], trellis=trellis)
+
+    def log_softmax_rows_(self, x: torch.Tensor) -> torch.Tensor:
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        V = x.shape[-1]
+        self._check(self.lib.wxb_log_softmax_rows(self.h, _ptr(x), x.numel() // V, V, self._stream()))
+        return x
+
+    # ---------------------------------------------------------------- K2 / K3
+    def set_model(self, dims: dict, tensors: Dict[str, torch.Tensor]):
+        d = Dims(**{k: int(dims[k]) for k, _ in Dims._fields_})
+        names = list(tensors.keys())
+        for k in names:
+            t = tensors[k]
+            assert t.is_cuda and t.is_contiguous(), k
+        arr_n = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        arr_p = (C.c_void_p * len(names))(*[tensors[n].data_ptr() for n in names])
+        self._keep["model"] = tensors  # the library borrows the pointers
+        self._keep["dims"] = dict(dims)
+        self._check(self.lib.wxb_set_model(self.h, C.byref(d), arr_n, arr_p, len(names)))
+
+    def encode(self, mel_dev: torch.Tensor) -> torch.Tensor:
+        """mel f32 cuda [B, n_mels, 3000] -> bf16 cuda [B, 1500, d]."""
+        dims = self._keep["dims"]
+        assert mel_dev.is_cuda and mel_dev.dtype == torch.float32 and mel_dev.is_contiguous()
+        B = mel_dev.shape[0]
+        out = torch.empty((B, dims["n_audio_ctx"], dims["n_audio_state"]), dtype=torch.bfloat16, device=self.device)
+        self._check(self.lib.wxb_encode(self.h, _ptr(mel_dev), B, _ptr(out), self._stream()))
+        return out
+
+    def decode_greedy(self, enc_out: torch.Tensor, prompt, eot: int, no_speech: int = -1, sample_len: int = 224,
+                      suppress_blank: bool = False, blank_token: int = 220, suppress_tokens=(),
+                      check_every: int = 16):
+        assert enc_out.is_cuda and enc_out.dtype == torch.bfloat16 and enc_out.is_contiguous()
+        B = enc_out.shape[0]
+        dev = self.device
+        prompt_np = np.ascontiguousarray(prompt, dtype=np.int32)
+        sup = torch.tensor(list(suppress_tokens), dtype=torch.int32, device=dev) if len(suppress_tokens) else None
+        opts = DecodeOpts(eot=eot, no_speech=no_speech, sample_len=sample_len, suppress_blank=int(suppress_blank),
+                          blank_token=blank_token, n_suppress=0 if sup is None else sup.numel(),
+                          suppress_dev=None if sup is None else sup.data_ptr(), check_every=check_every)
+        tokens = torch.full((B, sample_len), eot, dtype=torch.int32, device=dev)
+        n_tok = torch.zeros((B,), dtype=torch.int32, device=dev)
+        sum_lp = torch.zeros((B,), dtype=torch.float32, device=dev)
+        nsp = torch.zeros((B,), dtype=torch.float32, device=dev)
+        self._check(self.lib.wxb_decode_greedy(self.h, _ptr(enc_out), B, _np_ptr(prompt_np), len(prompt_np),
+                                               C.byref(opts), _ptr(tokens), _ptr(n_tok), _ptr(sum_lp), _ptr(nsp),
+                                               self._stream()))
+        return dict(tokens=tokens, n_tokens=n_tok, sum_logprob=sum_lp, no_speech_prob=nsp)
+
+    def decoder_logits(self, enc_out: torch.Tensor, tokens: np.ndarray) -> torch.Tensor:
+        dims = self._keep["dims"]
+        tokens = np.ascontiguousarray(tokens, dtype=np.int32)
+        B, n = tokens.shape
+        out = torch.empty((B, n, dims["n_vocab"]), dtype=torch.float32, device=self.device)
+        self._check(self.lib.wxb_decoder_logits(self.h, _ptr(enc_out), B, _np_ptr(tokens), n, _ptr(out), self._stream()))
+        return out
+
+    def gemm_bf16(self, A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None, gelu: bool = False,
+                  out_f32: bool = False) -> torch.Tensor:
+        assert A.dtype == torch.bfloat16 and W.dtype == torch.bfloat16 and A.is_contiguous() and W.is_contiguous()
+        M, K = A.shape
+        N, K2 = W.shape
+        assert K == K2
+        D = torch.empty((M, N), dtype=torch.float32 if out_f32 else torch.bfloat16, device=self.device)
+        flags = (1 if gelu else 0) | (2 if out_f32 else 0)
+        self._check(self.lib.wxb_gemm_bf16(self.h, _ptr(A), _ptr(W), _ptr(bias), _ptr(D), M, N, K, flags, self._stream()))
+        return D
+
+
+_contexts: Dict[int, Context] = {}
+
+
+def get_context(device_index: int = 0) -> Context:
+    """Process-wide context per GPU (the backend, audio.log_mel_spectrogram and align() share it)."""
+    ctx = _contexts.get(device_index)
+    if ctx is None:
+        ctx = Context(device_index)
+        _contexts[device_index] = ctx
+    return ctx

@@ -1,0 +1,431 @@
+"""
+Forced alignment for the B200 backend — same public functions as the reference's
+whisperx/alignment.py (load_align_model :77, align :113, get_trellis :387, backtrack :447,
+backtrack_beam :500, merge_repeats :597), with the numeric core (log-softmax'ed emissions ->
+trellis -> backtrack / beam-2) executed by kernel K4 (csrc/wxb_ctc.cu) for ALL segments of a
+transcript in one launch, one warp per segment.
+
+Host work that stays in Python: text normalisation, wildcard marking, run-length
+merge of the frame path, pandas word / sentence aggregation — written so the resulting dicts
+equal the reference's value for value.
+"""
+import math
+from dataclasses import dataclass
+from typing import Iterable, List, Optional, Union
+
+import numpy as np
+import pandas as pd
+import torch
+
+from .audio import SAMPLE_RATE, load_audio
+from .types import AlignedTranscriptionResult, SingleAlignedSegment, SingleSegment, SingleWordSegment
+from .utils import LANGUAGES_WITHOUT_SPACES, interpolate_nans
+
+PUNKT_ABBREVIATIONS = ["dr", "vs", "mr", "mrs", "prof"]
+
+# language -> default CTC model (reference tables, alignment.py:31-74; data, not logic)
+DEFAULT_ALIGN_MODELS_TORCH = {
+    "en": "WAV2VEC2_ASR_BASE_960H", "fr": "VOXPOPULI_ASR_BASE_10K_FR", "de": "VOXPOPULI_ASR_BASE_10K_DE",
+    "es": "VOXPOPULI_ASR_BASE_10K_ES", "it": "VOXPOPULI_ASR_BASE_10K_IT",
+}
+DEFAULT_ALIGN_MODELS_HF = {
+    "ja": "jonatasgrosman/wav2vec2-large-xlsr-53-japanese", "zh": "jonatasgrosman/wav2vec2-large-xlsr-53-chinese-zh-cn",
+    "nl": "jonatasgrosman/wav2vec2-large-xlsr-53-dutch", "uk": "Yehor/wav2vec2-xls-r-300m-uk-with-small-lm",
+    "pt": "jonatasgrosman/wav2vec2-large-xlsr-53-portuguese", "ar": "jonatasgrosman/wav2vec2-large-xlsr-53-arabic",
+    "cs": "comodoro/wav2vec2-xls-r-300m-cs-250", "ru": "jonatasgrosman/wav2vec2-large-xlsr-53-russian",
+    "pl": "jonatasgrosman/wav2vec2-large-xlsr-53-polish", "hu": "jonatasgrosman/wav2vec2-large-xlsr-53-hungarian",
+    "fi": "jonatasgrosman/wav2vec2-large-xlsr-53-finnish", "fa": "jonatasgrosman/wav2vec2-large-xlsr-53-persian",
+    "el": "jonatasgrosman/wav2vec2-large-xlsr-53-greek", "tr": "mpoyraz/wav2vec2-xls-r-300m-cv7-turkish",
+    "da": "saattrupdan/wav2vec2-xls-r-300m-ftspeech", "he": "imvladikon/wav2vec2-xls-r-300m-hebrew",
+    "vi": "nguyenvulebinh/wav2vec2-base-vi", "ko": "kresnik/wav2vec2-large-xlsr-korean",
+    "ur": "kingabzpro/wav2vec2-large-xls-r-300m-Urdu", "te": "anuragshas/wav2vec2-large-xlsr-53-telugu",
+    "hi": "theainerd/Wav2Vec2-large-xlsr-hindi", "ca": "softcatala/wav2vec2-large-xlsr-catala",
+    "ml": "gvs/wav2vec2-large-xlsr-malayalam", "no": "NbAiLab/nb-wav2vec2-1b-bokmaal-v2",
+    "nn": "NbAiLab/nb-wav2vec2-1b-nynorsk", "sk": "comodoro/wav2vec2-xls-r-300m-sk-cv8",
+    "sl": "anton-l/wav2vec2-large-xlsr-53-slovenian", "hr": "classla/wav2vec2-xls-r-parlaspeech-hr",
+    "ro": "gigant/romanian-wav2vec2", "eu": "stefan-it/wav2vec2-large-xlsr-53-basque",
+    "gl": "ifrz/wav2vec2-large-xlsr-galician", "ka": "xsway/wav2vec2-large-xlsr-georgian",
+    "lv": "jimregan/wav2vec2-large-xlsr-latvian-cv", "tl": "Khalsuu/filipino-wav2vec2-l-xls-r-300m-official",
+}
+
+
+# ------------------------------------------------------------------------------------------------
+# model loading (library code: torchaudio / transformers provide the CTC acoustic model)
+# ------------------------------------------------------------------------------------------------
+def load_align_model(language_code: str, device: str, model_name: Optional[str] = None, model_dir=None):
+    """Same contract as alignment.py:77-110: returns (model, {"language","dictionary","type"})."""
+    import torchaudio
+
+    if model_name is None:
+        model_name = DEFAULT_ALIGN_MODELS_TORCH.get(language_code) or DEFAULT_ALIGN_MODELS_HF.get(language_code)
+        if model_name is None:
+            print(f"There is no default alignment model set for this language ({language_code}). "
+                  "Please find a wav2vec2.0 model finetuned on this language in https://huggingface.co/models, "
+                  "then pass the model name in --align_model [MODEL_NAME]")
+            raise ValueError(f"No default align-model for language: {language_code}")
+
+    if model_name in torchaudio.pipelines.__all__:
+        kind = "torchaudio"
+        bundle = getattr(torchaudio.pipelines, model_name)
+        model = bundle.get_model(dl_kwargs={"model_dir": model_dir}).to(device)
+        dictionary = {label.lower(): idx for idx, label in enumerate(bundle.get_labels())}
+    else:
+        from transformers import Wav2Vec2ForCTC, Wav2Vec2Processor
+        try:
+            processor = Wav2Vec2Processor.from_pretrained(model_name, cache_dir=model_dir)
+            model = Wav2Vec2ForCTC.from_pretrained(model_name, cache_dir=model_dir)
+        except Exception as e:
+            print(e)
+            print("Error loading model from huggingface, check https://huggingface.co/models for finetuned wav2vec2.0 models")
+            raise ValueError(f'The chosen align_model "{model_name}" could not be found in huggingface '
+                             "(https://huggingface.co/models) or torchaudio (https://pytorch.org/audio/stable/pipelines.html#id14)")
+        kind = "huggingface"
+        model = model.to(device)
+        dictionary = {tok.lower(): idx for tok, idx in processor.tokenizer.get_vocab().items()}
+    return model, {"language": language_code, "dictionary": dictionary, "type": kind}
+
+
+# ------------------------------------------------------------------------------------------------
+# kernel-level seams with the reference's signatures
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class Point:
+    token_index: int
+    time_index: int
+    score: float
+
+
+@dataclass
+class Segment:
+    label: str
+    start: int
+    end: int
+    score: float
+
+    def __repr__(self):
+        return f"{self.label}\t({self.score:4.2f}): [{self.start:5d}, {self.end:5d})"
+
+    @property
+    def length(self):
+        return self.end - self.start
+
+
+def _ctx_for(device=None):
+    from ._native import get_context
+    if device is None:
+        idx = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    else:
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("the b200 aligner runs on the GPU only (no CPU fallback)")
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    return get_context(idx)
+
+
+def _as_emission(ctx, emission) -> torch.Tensor:
+    e = emission if torch.is_tensor(emission) else torch.as_tensor(np.asarray(emission))
+    return e.to(ctx.device, dtype=torch.float32).contiguous()
+
+
+def _tokens_dev(ctx, tokens) -> torch.Tensor:
+    return torch.as_tensor(np.asarray(list(tokens), dtype=np.int32)).to(ctx.device)
+
+
+def get_trellis(emission, tokens, blank_id=0):
+    """alignment.py:387-404 on the GPU: returns f32 cuda tensor [T, N]."""
+    from ._native import CTC_TRELLIS_ONLY
+    ctx = _ctx_for(emission.device if torch.is_tensor(emission) and emission.is_cuda else None)
+    e = _as_emission(ctx, emission)
+    T, N = e.shape[0], len(tokens)
+    res = ctx.ctc_align(e, np.array([0, T]), _tokens_dev(ctx, tokens), np.array([0, N]), blank_id,
+                        CTC_TRELLIS_ONLY, want_trellis=True)
+    return res["trellis"][:T * N].view(T, N)
+
+
+def _points_from(res, T: int, t0: int = 0) -> List[Point]:
+    tok = res["path_tok"][t0:t0 + T].cpu().numpy()
+    lp = res["path_lp"][t0:t0 + T].cpu()
+    prob = torch.exp(lp).numpy()  # host exp on the exact log-probs: same rounding as the reference's .exp()
+    return [Point(int(tok[t]), t, float(prob[t])) for t in range(T)]
+
+
+def _run_single(emission, tokens, blank_id, mode):
+    ctx = _ctx_for(emission.device if torch.is_tensor(emission) and emission.is_cuda else None)
+    e = _as_emission(ctx, emission)
+    T, N = e.shape[0], len(tokens)
+    res = ctx.ctc_align(e, np.array([0, T]), _tokens_dev(ctx, tokens), np.array([0, N]), blank_id, mode)
+    return res, T
+
+
+def backtrack(trellis, emission, tokens, blank_id=0):
+    """alignment.py:447-481.  `trellis` is accepted for signature compatibility; the kernel
+    recomputes it from (emission, tokens) on the device, bit-identically."""
+    from ._native import CTC_BACKTRACK
+    res, T = _run_single(emission, tokens, blank_id, CTC_BACKTRACK)
+    if int(res["status"][0]) != 0:
+        raise AssertionError("backtrack: ran out of frames before reaching the first token (t > 0 violated)")
+    return _points_from(res, T)
+
+
+def backtrack_beam(trellis, emission, tokens, blank_id=0, beam_width=5):
+    """alignment.py:500-579.  The device kernel implements the width the reference's align() uses
+    (beam_width=2, alignment.py:269); other widths are not on the hot path."""
+    from ._native import CTC_BEAM2
+    if beam_width != 2:
+        raise NotImplementedError("the b200 aligner implements backtrack_beam for beam_width=2 (what align() uses)")
+    res, T = _run_single(emission, tokens, blank_id, CTC_BEAM2)
+    if int(res["status"][0]) != 0:
+        return None
+    return _points_from(res, T)
+
+
+def merge_repeats(path: List[Point], transcript: str) -> List[Segment]:
+    """Run-length encode the frame path by token index (alignment.py:597-613)."""
+    out: List[Segment] = []
+    n = len(path)
+    lo = 0
+    while lo < n:
+        hi = lo
+        while hi < n and path[hi].token_index == path[lo].token_index:
+            hi += 1
+        mean_score = sum(path[k].score for k in range(lo, hi)) / (hi - lo)
+        out.append(Segment(transcript[path[lo].token_index], path[lo].time_index, path[hi - 1].time_index + 1, mean_score))
+        lo = hi
+    return out
+
+
+def merge_words(segments, separator="|"):
+    """alignment.py:615-629 (unused by align(); kept for API completeness)."""
+    words, lo, hi = [], 0, 0
+    while lo < len(segments):
+        if hi >= len(segments) or segments[hi].label == separator:
+            if lo != hi:
+                group = segments[lo:hi]
+                total = sum(s.length for s in group)
+                words.append(Segment("".join(s.label for s in group), group[0].start, group[-1].end,
+                                     sum(s.score * s.length for s in group) / total))
+            lo = hi = hi + 1
+        else:
+            hi += 1
+    return words
+
+
+# ------------------------------------------------------------------------------------------------
+# align()
+# ------------------------------------------------------------------------------------------------
+def _sentence_spans(text: str):
+    """Punkt sentence spans with the reference's abbreviation list (alignment.py:190-194).  nltk is an
+    optional dependency here: without it the whole text is one sentence (documented in DESIGN.md)."""
+    try:
+        from nltk.tokenize.punkt import PunktParameters, PunktSentenceTokenizer
+    except ImportError:
+        return [(0, len(text))]
+    params = PunktParameters()
+    params.abbrev_types = set(PUNKT_ABBREVIATIONS)
+    return list(PunktSentenceTokenizer(params).span_tokenize(text))
+
+
+def _prepare_segment(text: str, dictionary: dict, spaced: bool):
+    """Character cleaning of one transcript segment (alignment.py:151-201)."""
+    lead = len(text) - len(text.lstrip())
+    trail = len(text) - len(text.rstrip())
+    last_kept = len(text) - trail - 1
+    clean_char, clean_cdx = [], []
+    for cdx, ch in enumerate(text):
+        if cdx < lead or cdx > last_kept:
+            continue
+        c = ch.lower()
+        if spaced:
+            c = c.replace(" ", "|")
+        clean_char.append(c if c in dictionary else "*")
+        clean_cdx.append(cdx)
+    words = text.split(" ") if spaced else text
+    return {"clean_char": clean_char, "clean_cdx": clean_cdx, "clean_wdx": list(range(len(words))),
+            "sentence_spans": _sentence_spans(text)}
+
+
+def _emissions_for(model, model_type: str, wave: torch.Tensor, lengths, device):
+    with torch.inference_mode():
+        if model_type == "torchaudio":
+            logits, _ = model(wave.to(device), lengths=lengths)
+        elif model_type == "huggingface":
+            logits = model(wave.to(device)).logits
+        else:
+            raise NotImplementedError(f"Align model of type {model_type} not supported.")
+    return logits[0]
+
+
+def align(
+    transcript: Iterable[SingleSegment],
+    model: torch.nn.Module,
+    align_model_metadata: dict,
+    audio: Union[str, np.ndarray, torch.Tensor],
+    device: str,
+    interpolate_method: str = "nearest",
+    return_char_alignments: bool = False,
+    print_progress: bool = False,
+    combined_progress: bool = False,
+) -> AlignedTranscriptionResult:
+    """Drop-in for alignment.py:113-380.  Emissions of every alignable segment are gathered on the
+    GPU, log-softmax'ed and aligned by ONE K4 launch (beam-2, as the reference), then the host
+    builds the same char / word / sentence dicts."""
+    from ._native import CTC_BEAM2
+
+    if not torch.is_tensor(audio):
+        if isinstance(audio, str):
+            audio = load_audio(audio)
+        audio = torch.from_numpy(audio)
+    if audio.dim() == 1:
+        audio = audio.unsqueeze(0)
+    max_duration = audio.shape[1] / SAMPLE_RATE
+
+    dictionary = align_model_metadata["dictionary"]
+    lang = align_model_metadata["language"]
+    model_type = align_model_metadata["type"]
+    spaced = lang not in LANGUAGES_WITHOUT_SPACES
+    ctx = _ctx_for(device)
+
+    transcript = list(transcript)
+    total = len(transcript)
+    prepared = []
+    for sdx, seg in enumerate(transcript):
+        if print_progress:
+            base = ((sdx + 1) / total) * 100
+            print(f"Progress: {(50 + base / 2) if combined_progress else base:.2f}%...")
+        prepared.append(_prepare_segment(seg["text"], dictionary, spaced))
+
+    blank_id = 0
+    for ch, code in dictionary.items():
+        if ch == "[pad]" or ch == "<pad>":
+            blank_id = code
+
+    # ---- pass 1: emissions of every alignable segment, kept on the device ------------------
+    jobs = []  # (sdx, text_clean, tokens, T)
+    emis_parts, tok_parts = [], []
+    skip_reason = {}
+    for sdx, seg in enumerate(transcript):
+        t1, t2 = seg["start"], seg["end"]
+        if len(prepared[sdx]["clean_char"]) == 0:
+            skip_reason[sdx] = "no characters in this segment found in model dictionary, resorting to original..."
+            continue
+        if t1 >= max_duration:
+            skip_reason[sdx] = "original start time longer than audio duration, skipping..."
+            continue
+        text_clean = "".join(prepared[sdx]["clean_char"])
+        tokens = [dictionary.get(c, -1) for c in text_clean]
+        f1, f2 = int(t1 * SAMPLE_RATE), int(t2 * SAMPLE_RATE)
+        wave = audio[:, f1:f2]
+        lengths = None
+        if wave.shape[-1] < 400:  # minimum wav2vec2 input (alignment.py:243-249)
+            lengths = torch.as_tensor([wave.shape[-1]]).to(device)
+            wave = torch.nn.functional.pad(wave, (0, 400 - wave.shape[-1]))
+        logits = _emissions_for(model, model_type, wave, lengths, device)
+        logits = logits.to(ctx.device, dtype=torch.float32)
+        emis_parts.append(logits)
+        tok_parts.append(np.asarray(tokens, dtype=np.int32))
+        jobs.append((sdx, text_clean, tokens, logits.shape[0], wave.size(0)))
+
+    results = {}
+    if jobs:
+        emis = torch.cat(emis_parts, 0).contiguous()
+        ctx.log_softmax_rows_(emis)  # alignment.py:258
+        t_off = np.concatenate([[0], np.cumsum([j[3] for j in jobs])]).astype(np.int32)
+        n_off = np.concatenate([[0], np.cumsum([len(t) for t in tok_parts])]).astype(np.int32)
+        tok_dev = torch.from_numpy(np.concatenate(tok_parts)).to(ctx.device)
+        res = ctx.ctc_align(emis, t_off, tok_dev, n_off, blank_id, CTC_BEAM2)
+        status = res["status"].cpu().numpy()
+        path_tok = res["path_tok"].cpu().numpy()
+        path_prob = torch.exp(res["path_lp"].cpu()).numpy()
+        for k, job in enumerate(jobs):
+            a, b = int(t_off[k]), int(t_off[k + 1])
+            results[job[0]] = (int(status[k]), path_tok[a:b], path_prob[a:b], job)
+
+    # ---- pass 2: host assembly --------------------------------------------------------------
+    aligned_segments: List[SingleAlignedSegment] = []
+    for sdx, seg in enumerate(transcript):
+        t1, t2, text = seg["start"], seg["end"], seg["text"]
+        plain: SingleAlignedSegment = {"start": t1, "end": t2, "text": text, "words": [], "chars": None}
+        if return_char_alignments:
+            plain["chars"] = []
+        if sdx in skip_reason:
+            print(f'Failed to align segment ("{text}"): {skip_reason[sdx]}')
+            aligned_segments.append(plain)
+            continue
+        status, ptok, pprob, job = results[sdx]
+        if status != 0:
+            print(f'Failed to align segment ("{text}"): backtrack failed, resorting to original...')
+            aligned_segments.append(plain)
+            continue
+        _, text_clean, _tokens, T, n_channels = job
+        path = [Point(int(ptok[t]), t, float(pprob[t])) for t in range(T)]
+        char_segments = merge_repeats(path, text_clean)
+        ratio = (t2 - t1) * n_channels / (T - 1)
+        aligned_segments += _assemble(text, prepared[sdx], char_segments, ratio, t1, spaced,
+                                      interpolate_method, return_char_alignments)
+
+    word_segments: List[SingleWordSegment] = []
+    for seg in aligned_segments:
+        word_segments += seg["words"]
+    return {"segments": aligned_segments, "word_segments": word_segments}
+
+
+def _assemble(text, prep, char_segments, ratio, t1, spaced, interpolate_method, return_char_alignments):
+    """Char -> word -> sentence aggregation (alignment.py:281-373), same pandas primitives so the
+    float results (min / max / mean, NaN handling, groupby ordering) are the reference's."""
+    pos_of = {cdx: k for k, cdx in enumerate(prep["clean_cdx"])}
+    rows = []
+    widx = 0
+    for cdx, ch in enumerate(text):
+        start = end = score = None
+        k = pos_of.get(cdx)
+        if k is not None:
+            cs = char_segments[k]
+            start = round(cs.start * ratio + t1, 3)
+            end = round(cs.end * ratio + t1, 3)
+            score = round(cs.score, 3)
+        rows.append({"char": ch, "start": start, "end": end, "score": score, "word-idx": widx})
+        if not spaced:
+            widx += 1
+        elif cdx == len(text) - 1 or text[cdx + 1] == " ":
+            widx += 1
+    chars = pd.DataFrame(rows)
+    chars["sentence-idx"] = None
+
+    sentences = []
+    for sidx, (s0, s1) in enumerate(prep["sentence_spans"]):
+        sel = (chars.index >= s0) & (chars.index <= s1)
+        cur = chars.loc[sel]
+        chars.loc[sel, "sentence-idx"] = sidx
+        non_space = cur[cur["char"] != " "]
+        words = []
+        for w in cur["word-idx"].unique():
+            wc = cur.loc[cur["word-idx"] == w]
+            wtext = "".join(wc["char"].tolist()).strip()
+            if len(wtext) == 0:
+                continue
+            wc = wc[wc["char"] != " "]
+            w_start, w_end = wc["start"].min(), wc["end"].max()
+            w_score = round(wc["score"].mean(), 3)
+            entry = {"word": wtext}
+            if not np.isnan(w_start):
+                entry["start"] = w_start
+            if not np.isnan(w_end):
+                entry["end"] = w_end
+            if not np.isnan(w_score):
+                entry["score"] = w_score
+            words.append(entry)
+        sent = {"text": text[s0:s1], "start": cur["start"].min(), "end": non_space["end"].max(), "words": words}
+        if return_char_alignments:
+            cc = cur[["char", "start", "end", "score"]].copy()
+            cc.fillna(-1, inplace=True)
+            sent["chars"] = [{k: v for k, v in rec.items() if v != -1} for rec in cc.to_dict("records")]
+        sentences.append(sent)
+
+    df = pd.DataFrame(sentences)
+    df["start"] = interpolate_nans(df["start"], method=interpolate_method)
+    df["end"] = interpolate_nans(df["end"], method=interpolate_method)
+    agg = {"text": " ".join if spaced else "".join, "words": "sum"}
+    if return_char_alignments:
+        agg["chars"] = "sum"
+    df = df.groupby(["start", "end"], as_index=False).agg(agg)
+    return df.to_dict("records")
