@@ -1,4 +1,391 @@
-#include "wxb_common.cuh"
-extern "C" int wxb_encode(wxb_ctx* ctx, const float*, int, void*, void*) {
-  return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "wxb_encode: not built yet");
+// wxb_encoder.cu — K2: the Whisper audio encoder (conv stem, 2 x GELU, sinusoid positions,
+// pre-LN transformer blocks, ln_post).  Architecture: OpenAI Whisper AudioEncoder as ported by
+// mlx_whisper (the reference's dependency; container oracle transformers/models/whisper/
+// modeling_whisper.py:541-648).
+//
+// Data layout in HBM (B chunks, T = 1500 positions, d = n_audio_state):
+//   melT  bf16 [B*3002 + 2, n_mels]  frame-major mel with one zero frame before and after each chunk,
+//                                    so row r of the conv1 im2col matrix is the 3*n_mels contiguous
+//                                    elements starting at r*n_mels (a TMA view with OVERLAPPING rows)
+//   h1    bf16 [B*3002 + 2, d]       GELU(conv1), same padding; conv2 (stride 2) im2col row q is the
+//                                    3*d contiguous elements starting at q*2*d
+//   x     f32  [B*T, d]              residual stream
+//   xn    bf16 [B*T, d]              LayerNorm output (GEMM A operand)
+//   qkv   bf16 [B*T, 3d]             fused Q|K|V projection
+//   att   bf16 [B*T, d]              attention output
+//   hid   bf16 [B*T, 4d]             GELU(fc1)
+// All GEMMs run on wxb_gemm.cu (tcgen05/TMEM/TMA) with bias / GELU / residual / positional add fused
+// into the epilogue.
+#include "wxb_gemm.cuh"
+#include "wxb_model.cuh"
+#include <math.h>
+
+namespace {
+
+constexpr int T_AUDIO = 1500;
+constexpr int T_MEL = 3000;
+constexpr int G1 = 3002;  // padded frames per chunk (melT / h1)
+
+// ---------------------------------------------------------------------------------------------
+// mel f32 [B, n_mels, 3000] -> melT bf16 rows (b*3002 + 1 + frame), via a 32x32 smem transpose
+// ---------------------------------------------------------------------------------------------
+__global__ void mel_transpose_kernel(const float* __restrict__ mel, __nv_bfloat16* __restrict__ melT, int n_mels) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int f0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  const float* src = mel + (size_t)b * n_mels * T_MEL;
+  for (int i = ty; i < 32; i += 8) {
+    const int m = m0 + i, f = f0 + tx;
+    tile[i][tx] = (m < n_mels && f < T_MEL) ? src[(size_t)m * T_MEL + f] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int f = f0 + i, m = m0 + tx;
+    if (f < T_MEL && m < n_mels) melT[((size_t)b * G1 + 1 + f) * n_mels + m] = __float2bfloat16_rn(tile[tx][i]);
+  }
+}
+
+// zero the padding rows (row 0 and 3001 of each chunk, plus the 2 tail rows) of a [B*3002+2, width] bf16 buffer
+__global__ void zero_pad_rows_kernel(__nv_bfloat16* __restrict__ buf, int B, int width) {
+  const int row_id = blockIdx.x;  // 0 .. 2B+1
+  long long row;
+  if (row_id < 2 * B) row = (long long)(row_id >> 1) * G1 + ((row_id & 1) ? (G1 - 1) : 0);
+  else row = (long long)B * G1 + (row_id - 2 * B);
+  __nv_bfloat16* p = buf + row * width;
+  for (int i = threadIdx.x; i < width; i += blockDim.x) p[i] = __float2bfloat16_rn(0.f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm (eps 1e-5): f32 [rows, d] -> bf16 [rows, d]; one warp per row, row kept in registers
+// ---------------------------------------------------------------------------------------------
+template <int MAXV>  // MAXV float4 per lane: d <= 128 * MAXV
+__global__ void __launch_bounds__(256)
+layernorm_bf16_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                      __nv_bfloat16* __restrict__ y, long long rows, int d) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * d);
+  const int nv = d >> 2;
+  float4 v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nv) {
+      v[i] = xr[idx];
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+  }
+  const float mean = warp_sum(s) / d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nv) {
+      const float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+      q += a * a + bb * bb + c * c + e * e;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / d + 1e-5f);
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+  uint2* yr = reinterpret_cast<uint2*>(y + row * d);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nv) {
+      const float4 ww = __ldg(w4 + idx), bb = __ldg(b4 + idx);
+      __nv_bfloat162 lo = __floats2bfloat162_rn((v[i].x - mean) * rstd * ww.x + bb.x, (v[i].y - mean) * rstd * ww.y + bb.y);
+      __nv_bfloat162 hi = __floats2bfloat162_rn((v[i].z - mean) * rstd * ww.z + bb.z, (v[i].w - mean) * rstd * ww.w + bb.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      yr[idx] = pk;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Non-causal multi-head attention over T = 1500 positions, head_dim 64 (v1: flash-style online
+// softmax on mma.sync m16n8k16 bf16; 128 query rows per CTA, 64-key tiles double-buffered with
+// cp.async, XOR-swizzled shared memory for conflict-free ldmatrix).
+// ---------------------------------------------------------------------------------------------
+constexpr int ATT_BQ = 128, ATT_BK = 64, ATT_THREADS = 256;
+
+__device__ __forceinline__ void ldsm_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(uint32_t smem, const void* gmem, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// tile of [rows][64] bf16, 128 B per row, 16-byte chunk c of row r stored at chunk c ^ (r & 7)
+__device__ __forceinline__ uint32_t sw_off(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
+
+// load `rows` x 64 bf16 starting at global row `g0` (row stride ld elements) into a swizzled tile;
+// rows >= g_end are zero-filled
+__device__ __forceinline__ void load_tile_async(uint32_t smem_base, const __nv_bfloat16* gbase, long long ld, int g0,
+                                                int g_end, int rows, int tid) {
+  for (int idx = tid; idx < rows * 8; idx += ATT_THREADS) {
+    const int r = idx >> 3, c = idx & 7;
+    const int gr = g0 + r;
+    const bool ok = gr < g_end;
+    const __nv_bfloat16* src = gbase + (long long)(ok ? gr : (g_end - 1)) * ld + c * 8;
+    cp_async16(smem_base + sw_off(r, c), src, ok ? 16 : 0);
+  }
+}
+
+__global__ void __launch_bounds__(ATT_THREADS)
+attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T, int d, float scale_log2) {
+  extern __shared__ __align__(128) uint8_t att_smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int q0 = blockIdx.x * ATT_BQ, h = blockIdx.y, b = blockIdx.z;
+  const long long ld = 3LL * d;
+  const __nv_bfloat16* qb = qkv + (long long)b * T * ld + h * 64;
+  const __nv_bfloat16* kb = qb + d;
+  const __nv_bfloat16* vb = qb + 2 * d;
+  const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(att_smem);
+  const uint32_t sK = sQ + ATT_BQ * 128;            // 2 buffers of 64 x 128 B
+  const uint32_t sV = sK + 2 * ATT_BK * 128;        // 2 buffers
+  const int nkt = (T + ATT_BK - 1) / ATT_BK;
+
+  load_tile_async(sQ, qb, ld, q0, T, ATT_BQ, tid);
+  load_tile_async(sK, kb, ld, 0, T, ATT_BK, tid);
+  load_tile_async(sV, vb, ld, 0, T, ATT_BK, tid);
+  asm volatile("cp.async.commit_group;");
+
+  uint32_t qf[4][4];
+  float o[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
+
+  for (int kt = 0; kt < nkt; ++kt) {
+    asm volatile("cp.async.wait_group 0;");
+    __syncthreads();
+    if (kt + 1 < nkt) {
+      const int nb = (kt + 1) & 1;
+      load_tile_async(sK + nb * ATT_BK * 128, kb, ld, (kt + 1) * ATT_BK, T, ATT_BK, tid);
+      load_tile_async(sV + nb * ATT_BK * 128, vb, ld, (kt + 1) * ATT_BK, T, ATT_BK, tid);
+      asm volatile("cp.async.commit_group;");
+    }
+    if (kt == 0) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const int m = lane >> 3;
+        const int row = warp * 16 + (m & 1) * 8 + (lane & 7);
+        ldsm_x4(qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], sQ + sw_off(row, ks * 2 + (m >> 1)));
+      }
+    }
+    const uint32_t cK = sK + (kt & 1) * ATT_BK * 128, cV = sV + (kt & 1) * ATT_BK * 128;
+    float s[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      uint32_t bf[8];
+      const int krow = nt * 8 + (lane & 7);
+      const int m = lane >> 3;
+      ldsm_x4(bf[0], bf[1], bf[2], bf[3], cK + sw_off(krow, m));
+      ldsm_x4(bf[4], bf[5], bf[6], bf[7], cK + sw_off(krow, 4 + m));
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) mma_16816(s[nt], qf[ks], bf[2 * ks], bf[2 * ks + 1]);
+    }
+    // mask keys beyond T (only the last tile)
+    const int kbase = kt * ATT_BK;
+    if (kbase + ATT_BK > T) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int k0 = kbase + nt * 8 + 2 * t4;
+        if (k0 >= T) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+        if (k0 + 1 >= T) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+      }
+    }
+    float mx_lo = -INFINITY, mx_hi = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      mx_lo = fmaxf(mx_lo, fmaxf(s[nt][0], s[nt][1]));
+      mx_hi = fmaxf(mx_hi, fmaxf(s[nt][2], s[nt][3]));
+    }
+    mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1));
+    mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
+    mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
+    mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
+    const float mn_lo = fmaxf(m_lo, mx_lo), mn_hi = fmaxf(m_hi, mx_hi);
+    const float a_lo = exp2f((m_lo - mn_lo) * scale_log2), a_hi = exp2f((m_hi - mn_hi) * scale_log2);
+    m_lo = mn_lo; m_hi = mn_hi;
+    const float off_lo = mn_lo * scale_log2, off_hi = mn_hi * scale_log2;
+    float sum_lo = 0.f, sum_hi = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = exp2f(s[nt][0] * scale_log2 - off_lo);
+      s[nt][1] = exp2f(s[nt][1] * scale_log2 - off_lo);
+      s[nt][2] = exp2f(s[nt][2] * scale_log2 - off_hi);
+      s[nt][3] = exp2f(s[nt][3] * scale_log2 - off_hi);
+      sum_lo += s[nt][0] + s[nt][1];
+      sum_hi += s[nt][2] + s[nt][3];
+    }
+    l_lo = l_lo * a_lo + sum_lo;
+    l_hi = l_hi * a_hi + sum_hi;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { o[i][0] *= a_lo; o[i][1] *= a_lo; o[i][2] *= a_hi; o[i][3] *= a_hi; }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t pa[4];
+      pa[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+      pa[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+      pa[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      pa[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        const int m = lane >> 3;
+        const int vrow = kk * 16 + (m & 1) * 8 + (lane & 7);
+        uint32_t v0, v1, v2, v3;
+        ldsm_x4_t(v0, v1, v2, v3, cV + sw_off(vrow, 2 * dp + (m >> 1)));
+        mma_16816(o[2 * dp], pa, v0, v1);
+        mma_16816(o[2 * dp + 1], pa, v2, v3);
+      }
+    }
+  }
+  // row sums live spread over the 4 lanes of a quad
+  l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1);
+  l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+  l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1);
+  l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+  const float inv_lo = 1.f / l_lo, inv_hi = 1.f / l_hi;
+  const int r_lo = q0 + warp * 16 + g, r_hi = r_lo + 8;
+  __nv_bfloat16* ob = out + (long long)b * T * d + h * 64;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const int col = nt * 8 + 2 * t4;
+    if (r_lo < T) *reinterpret_cast<uint32_t*>(ob + (long long)r_lo * d + col) = pack_bf16(o[nt][0] * inv_lo, o[nt][1] * inv_lo);
+    if (r_hi < T) *reinterpret_cast<uint32_t*>(ob + (long long)r_hi * d + col) = pack_bf16(o[nt][2] * inv_hi, o[nt][3] * inv_hi);
+  }
+}
+
+int launch_layernorm(wxb_ctx* ctx, const float* x, const float* w, const float* b, __nv_bfloat16* y, long long rows, int d,
+                     cudaStream_t st) {
+  if (d % 4 || d > 128 * 10) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "layernorm: d=%d", d);
+  const unsigned grid = (unsigned)ceil_div64(rows, 8);
+  if (d <= 512) layernorm_bf16_kernel<4><<<grid, 256, 0, st>>>(x, w, b, y, rows, d);
+  else layernorm_bf16_kernel<10><<<grid, 256, 0, st>>>(x, w, b, y, rows, d);
+  WXB_LAUNCH_CHECK(ctx);
+  return WXB_OK;
+}
+
+}  // namespace
+
+// exported to wxb_decoder.cu
+int wxb_launch_layernorm(wxb_ctx* ctx, const float* x, const float* w, const float* b, __nv_bfloat16* y, long long rows,
+                         int d, cudaStream_t st) {
+  return launch_layernorm(ctx, x, w, b, y, rows, d, st);
+}
+
+int wxb_encode_impl(wxb_ctx* ctx, const float* mel_dev, int B, __nv_bfloat16* enc_out, cudaStream_t st) {
+  if (!ctx->model) return wxb_fail(ctx, WXB_ERR_STATE, "wxb_encode: no model set");
+  const wxb_dims& D = ctx->model->dims;
+  const int d = D.n_audio_state, nm = D.n_mels, H = D.n_audio_head;
+  const long long M = (long long)B * T_AUDIO;
+  const long long rows1 = (long long)B * G1 + 2;
+  __nv_bfloat16* melT = (__nv_bfloat16*)wxb_named(ctx, "enc.melT", rows1 * nm * 2);
+  __nv_bfloat16* h1 = (__nv_bfloat16*)wxb_named(ctx, "enc.h1", rows1 * d * 2);
+  float* x = (float*)wxb_named(ctx, "enc.x", M * d * 4);
+  __nv_bfloat16* xn = (__nv_bfloat16*)wxb_named(ctx, "enc.xn", M * d * 2);
+  __nv_bfloat16* qkv = (__nv_bfloat16*)wxb_named(ctx, "enc.qkv", M * 3 * d * 2);
+  __nv_bfloat16* att = (__nv_bfloat16*)wxb_named(ctx, "enc.att", M * d * 2);
+  __nv_bfloat16* hid = (__nv_bfloat16*)wxb_named(ctx, "enc.hid", M * 4 * d * 2);
+  if (!melT || !h1 || !x || !xn || !qkv || !att || !hid) return WXB_ERR_CUDA;
+
+  const __nv_bfloat16* c1w = (const __nv_bfloat16*)wxb_weight(ctx, "enc.conv1.w");
+  const float* c1b = (const float*)wxb_weight(ctx, "enc.conv1.b");
+  const __nv_bfloat16* c2w = (const __nv_bfloat16*)wxb_weight(ctx, "enc.conv2.w");
+  const float* c2b = (const float*)wxb_weight(ctx, "enc.conv2.b");
+  const float* pos = (const float*)wxb_weight(ctx, "enc.pos");
+  const float* lnp_w = (const float*)wxb_weight(ctx, "enc.ln_post.w");
+  const float* lnp_b = (const float*)wxb_weight(ctx, "enc.ln_post.b");
+  if (!c1w || !c1b || !c2w || !c2b || !pos || !lnp_w || !lnp_b) return WXB_ERR_STATE;
+
+  // --- mel -> frame-major bf16 with zero frames around each chunk
+  zero_pad_rows_kernel<<<2 * B + 2, 128, 0, st>>>(melT, B, nm);
+  WXB_LAUNCH_CHECK(ctx);
+  zero_pad_rows_kernel<<<2 * B + 2, 128, 0, st>>>(h1, B, d);
+  WXB_LAUNCH_CHECK(ctx);
+  mel_transpose_kernel<<<dim3(ceil_div(T_MEL, 32), ceil_div(nm, 32), B), dim3(32, 8), 0, st>>>(mel_dev, melT, nm);
+  WXB_LAUNCH_CHECK(ctx);
+  int rc;
+  {  // conv1 (k3, s1, p1) + GELU as one GEMM over overlapping rows
+    GemmArgs a;
+    a.A = melT; a.lda = nm; a.M = B * G1; a.W = c1w; a.N = d; a.K = 3 * nm;
+    a.bias = c1b; a.gelu = 1; a.out = h1; a.out_f32 = 0; a.ldo = d;
+    a.g_in = G1; a.g_valid = T_MEL; a.g_out = G1; a.out_off = 1;
+    if ((rc = wxb_gemm_launch(ctx, a, st)) != WXB_OK) return rc;
+  }
+  {  // conv2 (k3, s2, p1) + GELU + positional embedding -> residual stream
+    GemmArgs a;
+    a.A = h1; a.lda = 2LL * d; a.M = B * (T_AUDIO + 1); a.W = c2w; a.N = d; a.K = 3 * d;
+    a.bias = c2b; a.gelu = 1; a.residual = pos; a.res_mode = 2; a.ldr = d;
+    a.out = x; a.out_f32 = 1; a.ldo = d;
+    a.g_in = T_AUDIO + 1; a.g_valid = T_AUDIO; a.g_out = T_AUDIO; a.out_off = 0;
+    if ((rc = wxb_gemm_launch(ctx, a, st)) != WXB_OK) return rc;
+  }
+  const float scale_log2 = (1.0f / sqrtf(64.f)) * 1.44269504088896341f;
+  const int att_smem = ATT_BQ * 128 + 4 * ATT_BK * 128;
+  for (int l = 0; l < D.n_audio_layer; ++l) {
+    EncLayerW w;
+    if ((rc = wxb_enc_layer(ctx, l, &w)) != WXB_OK) return rc;
+    if ((rc = launch_layernorm(ctx, x, w.ln1_w, w.ln1_b, xn, M, d, st)) != WXB_OK) return rc;
+    {
+      GemmArgs a;
+      a.A = xn; a.lda = d; a.M = (int)M; a.W = w.qkv_w; a.N = 3 * d; a.K = d; a.bias = w.qkv_b;
+      a.out = qkv; a.ldo = 3 * d;
+      if ((rc = wxb_gemm_launch(ctx, a, st)) != WXB_OK) return rc;
+    }
+    attention_kernel<<<dim3(ceil_div(T_AUDIO, ATT_BQ), H, B), ATT_THREADS, att_smem, st>>>(qkv, att, T_AUDIO, d, scale_log2);
+    WXB_LAUNCH_CHECK(ctx);
+    {
+      GemmArgs a;
+      a.A = att; a.lda = d; a.M = (int)M; a.W = w.out_w; a.N = d; a.K = d; a.bias = w.out_b;
+      a.residual = x; a.res_mode = 1; a.ldr = d; a.out = x; a.out_f32 = 1; a.ldo = d;
+      if ((rc = wxb_gemm_launch(ctx, a, st)) != WXB_OK) return rc;
+    }
+    if ((rc = launch_layernorm(ctx, x, w.ln2_w, w.ln2_b, xn, M, d, st)) != WXB_OK) return rc;
+    {
+      GemmArgs a;
+      a.A = xn; a.lda = d; a.M = (int)M; a.W = w.fc1_w; a.N = 4 * d; a.K = d; a.bias = w.fc1_b; a.gelu = 1;
+      a.out = hid; a.ldo = 4 * d;
+      if ((rc = wxb_gemm_launch(ctx, a, st)) != WXB_OK) return rc;
+    }
+    {
+      GemmArgs a;
+      a.A = hid; a.lda = 4 * d; a.M = (int)M; a.W = w.fc2_w; a.N = d; a.K = 4 * d; a.bias = w.fc2_b;
+      a.residual = x; a.res_mode = 1; a.ldr = d; a.out = x; a.out_f32 = 1; a.ldo = d;
+      if ((rc = wxb_gemm_launch(ctx, a, st)) != WXB_OK) return rc;
+    }
+  }
+  return launch_layernorm(ctx, x, lnp_w, lnp_b, enc_out, M, d, st);
+}
+
+extern "C" int wxb_encode(wxb_ctx* ctx, const float* mel_dev, int B, void* enc_out_dev, void* stream) {
+  if (!ctx) return WXB_ERR_INVALID;
+  if (!mel_dev || !enc_out_dev || B <= 0) return wxb_fail(ctx, WXB_ERR_INVALID, "wxb_encode: bad argument");
+  WXB_CUDA(ctx, cudaSetDevice(ctx->device));
+  static bool attr = false;
+  if (!attr) {
+    WXB_CUDA(ctx, cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BQ * 128 + 4 * ATT_BK * 128));
+    attr = true;
+  }
+  return wxb_encode_impl(ctx, mel_dev, B, (__nv_bfloat16*)enc_out_dev, (cudaStream_t)stream);
 }

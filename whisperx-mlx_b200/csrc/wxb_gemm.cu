@@ -1,4 +1,382 @@
-#include "wxb_common.cuh"
-extern "C" int wxb_gemm_bf16(wxb_ctx* ctx, const void*, const void*, const float*, void*, int, int, int, int, void*) {
-  return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "wxb_gemm_bf16: not built yet");
+// wxb_gemm.cu — K2 building block: persistent, warp-specialised bf16 GEMM on the 5th-gen tensor
+// cores.  D[M,N] = A[M,K] * W[N,K]^T, fp32 accumulation in TMEM, fused epilogue.
+//
+//   warp 0      TMA producer: cp.async.bulk.tensor 2D loads of a 128 x 64 A box and a BN x 64 W box
+//               (128-byte swizzle) into a STAGES-deep shared-memory ring, mbarrier complete_tx.
+//   warp 1      MMA issuer: one lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16)
+//               four times per stage; tcgen05.commit releases the stage / publishes the accumulator.
+//   warp 2      TMEM allocator (2 x BN columns: double-buffered accumulator so the epilogue of
+//               tile i overlaps the main loop of tile i+1).
+//   warps 4-7   epilogue: tcgen05.ld (32 lanes x 32 columns per instruction) -> bias, GELU(erf),
+//               residual / positional add, row remap (conv stem) -> bf16 or f32 global stores.
+// Grid = min(#tiles, #SMs); tiles are walked m-fastest so concurrently running CTAs share W tiles.
+#include "wxb_gemm.cuh"
+#include <cuda.h>
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NTHREADS = 256;
+
+struct GemmParams {
+  int M, N, K;
+  int num_m_tiles, num_n_tiles, num_k_blocks;
+  const float* bias;
+  const float* residual;
+  int res_mode;
+  long long ldr;
+  int gelu;
+  void* out;
+  int out_f32;
+  long long ldo;
+  int g_in, g_valid, g_out, out_off;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (=1),
+// descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  const uint32_t lo = ((smem_addr >> 4) & 0x3FFFu) | (1u << 16);
+  const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+  return (uint64_t)lo | ((uint64_t)hi << 32);
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+template <int BN, int STAGES>
+struct SmemLayout {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 8 * (2 * STAGES + 4) + 16 + 1024;  // + alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using L = SmemLayout<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar + a, 1);
+      mbar_init(tempty_bar + a, 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % p.num_m_tiles, n_blk = tile / p.num_m_tiles;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(empty_bar + stage, phase ^ 1);
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          mbar_arrive_expect_tx(full_bar + stage, L::STAGE_BYTES);
+          tma_load_2d(sa, &tmA, full_bar + stage, kb * BK, m_blk * BM);
+          tma_load_2d(sb, &tmB, full_bar + stage, kb * BK, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      // instruction descriptor: D=f32 (bit 4), A=bf16 (bit 7), B=bf16 (bit 10), K-major A and B,
+      // N>>3 at bit 17, M>>4 at bit 24
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar + acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(full_bar + stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint64_t adesc = make_sw128_desc(sa);
+          const uint64_t bdesc = make_sw128_desc(sa + L::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+            tc_mma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          }
+          tc_commit(empty_bar + stage);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(tfull_bar + acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int ew = warp - 4;  // == warp % 4: TMEM lane quarter this warp may read
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % p.num_m_tiles, n_blk = tile / p.num_m_tiles;
+      mbar_wait(tfull_bar + acc, acc_phase);
+      tc_fence_after();
+      const int r = m_blk * BM + ew * 32 + lane;  // GEMM row of this thread
+      bool row_ok = r < p.M;
+      long long out_row = r;
+      int t_in_group = r;
+      if (p.g_in > 0) {
+        const int g = r / p.g_in;
+        t_in_group = r - g * p.g_in;
+        row_ok = row_ok && (t_in_group < p.g_valid);
+        out_row = (long long)g * p.g_out + t_in_group + p.out_off;
+      }
+      const float* res_row = nullptr;
+      if (p.res_mode == 1) res_row = p.residual + out_row * p.ldr;
+      else if (p.res_mode == 2) res_row = p.residual + (long long)t_in_group * p.ldr;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + c * 32);
+        tc_ld_32x32(taddr, v);
+        tc_wait_ld();
+        const int n0 = n_blk * BN + c * 32;
+        if (row_ok && n0 < p.N) {
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          const bool full = (n0 + 32 <= p.N);
+          if (p.bias) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (full || n0 + i < p.N) f[i] += __ldg(p.bias + n0 + i);
+          }
+          if (p.gelu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+          }
+          if (res_row) {
+            if (full) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 rr = *reinterpret_cast<const float4*>(res_row + n0 + i);
+                f[i] += rr.x; f[i + 1] += rr.y; f[i + 2] += rr.z; f[i + 3] += rr.w;
+              }
+            } else {
+              for (int i = 0; i < 32; ++i)
+                if (n0 + i < p.N) f[i] += res_row[n0 + i];
+            }
+          }
+          if (p.out_f32) {
+            float* o = reinterpret_cast<float*>(p.out) + out_row * p.ldo + n0;
+            if (full) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+            } else {
+              for (int i = 0; i < 32; ++i)
+                if (n0 + i < p.N) o[i] = f[i];
+            }
+          } else {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldo + n0;
+            if (full) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                uint4 pk;
+                __nv_bfloat162 b0 = __floats2bfloat162_rn(f[i], f[i + 1]);
+                __nv_bfloat162 b1 = __floats2bfloat162_rn(f[i + 2], f[i + 3]);
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(f[i + 4], f[i + 5]);
+                __nv_bfloat162 b3 = __floats2bfloat162_rn(f[i + 6], f[i + 7]);
+                pk.x = *reinterpret_cast<uint32_t*>(&b0);
+                pk.y = *reinterpret_cast<uint32_t*>(&b1);
+                pk.z = *reinterpret_cast<uint32_t*>(&b2);
+                pk.w = *reinterpret_cast<uint32_t*>(&b3);
+                *reinterpret_cast<uint4*>(o + i) = pk;
+              }
+            } else {
+              for (int i = 0; i < 32; ++i)
+                if (n0 + i < p.N) o[i] = __float2bfloat16_rn(f[i]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  // ------------------------------------------------------------------ teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_tmap(wxb_ctx* ctx, CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
+              uint32_t box_inner, uint32_t box_rows) {
+  if (!ctx->encode_tiled) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn)
+      return wxb_fail(ctx, WXB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    ctx->encode_tiled = fn;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (row_stride_bytes & 15))
+    return wxb_fail(ctx, WXB_ERR_INVALID, "TMA operand must be 16-byte aligned (base %p, row stride %llu B)", base,
+                    (unsigned long long)row_stride_bytes);
+  cuuint64_t gdim[2] = {inner, rows};
+  cuuint64_t gstride[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = ((EncodeTiledFn)ctx->encode_tiled)(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride,
+                                                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return wxb_fail(ctx, WXB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) inner=%llu rows=%llu stride=%llu", (int)r,
+                    (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)row_stride_bytes);
+  return WXB_OK;
+}
+
+template <int BN, int STAGES>
+int launch_cfg(wxb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
+  using L = SmemLayout<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    WXB_CUDA(ctx, cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_set = true;
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
+  gemm_tc_kernel<BN, STAGES><<<grid, NTHREADS, L::TOTAL, st>>>(tmA, tmB, p);
+  WXB_LAUNCH_CHECK(ctx);
+  return WXB_OK;
+}
+
+}  // namespace
+
+int wxb_gemm_launch(wxb_ctx* ctx, const GemmArgs& a, cudaStream_t st) {
+  if (!a.A || !a.W || !a.out || a.M <= 0 || a.N <= 0 || a.K <= 0)
+    return wxb_fail(ctx, WXB_ERR_INVALID, "gemm: bad argument (M=%d N=%d K=%d)", a.M, a.N, a.K);
+  if (a.K % 8 != 0) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "gemm: K=%d must be a multiple of 8", a.K);
+  // tile width: 256 where it divides N (or N is large), else 128
+  const int BN = (a.N % 256 == 0 || a.N >= 2048) ? 256 : 128;
+  GemmParams p;
+  p.M = a.M; p.N = a.N; p.K = a.K;
+  p.num_m_tiles = ceil_div(a.M, BM);
+  p.num_n_tiles = ceil_div(a.N, BN);
+  p.num_k_blocks = ceil_div(a.K, BK);
+  p.bias = a.bias; p.residual = a.residual; p.res_mode = a.residual ? a.res_mode : 0; p.ldr = a.ldr;
+  p.gelu = a.gelu; p.out = a.out; p.out_f32 = a.out_f32; p.ldo = a.ldo ? a.ldo : a.N;
+  p.g_in = a.g_in; p.g_valid = a.g_valid; p.g_out = a.g_out; p.out_off = a.out_off;
+  CUtensorMap tmA, tmB;
+  int rc;
+  const long long lda = a.lda ? a.lda : a.K;
+  if ((rc = make_tmap(ctx, &tmA, a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)lda * 2, BK, BM)) != WXB_OK) return rc;
+  if ((rc = make_tmap(ctx, &tmB, a.W, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.K * 2, BK, BN)) != WXB_OK) return rc;
+  if (BN == 256) return launch_cfg<256, 4>(ctx, tmA, tmB, p, st);
+  return launch_cfg<128, 6>(ctx, tmA, tmB, p, st);
+}
+
+extern "C" int wxb_gemm_bf16(wxb_ctx* ctx, const void* A_dev, const void* W_dev, const float* bias_dev, void* D_dev,
+                             int M, int N, int K, int flags, void* stream) {
+  if (!ctx) return WXB_ERR_INVALID;
+  WXB_CUDA(ctx, cudaSetDevice(ctx->device));
+  GemmArgs a;
+  a.A = (const __nv_bfloat16*)A_dev; a.lda = K; a.M = M;
+  a.W = (const __nv_bfloat16*)W_dev; a.N = N; a.K = K;
+  a.bias = bias_dev; a.gelu = flags & 1; a.out = D_dev; a.out_f32 = (flags >> 1) & 1; a.ldo = N;
+  return wxb_gemm_launch(ctx, a, (cudaStream_t)stream);
 }

@@ -139,3 +139,154 @@ def round_to_bf16(w: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         else:
             out[k] = v.float()
     return out
+
+
+def to_kernel_layout(w: Dict[str, torch.Tensor], dims: Dict[str, int], device) -> Dict[str, torch.Tensor]:
+    """OpenAI-named fp32 weights -> the device tensors wxb_set_model consumes (csrc/wxb_model.cu):
+    bf16 [N, K] matrices (Q|K|V fused, conv kernels flattened tap-major for the implicit-im2col GEMM,
+    cross K|V fused), f32 biases / LayerNorm parameters / positional tables."""
+    bf, f32 = torch.bfloat16, torch.float32
+    out: Dict[str, torch.Tensor] = {}
+
+    def put(name, t, dtype):
+        out[name] = t.to(device=device, dtype=dtype).contiguous()
+
+    def conv_flat(k):  # [co, ci, 3] -> [co, 3*ci] with column index tap*ci + channel
+        return k.permute(0, 2, 1).reshape(k.shape[0], -1)
+
+    put("enc.conv1.w", conv_flat(w["encoder.conv1.weight"]), bf)
+    put("enc.conv1.b", w["encoder.conv1.bias"], f32)
+    put("enc.conv2.w", conv_flat(w["encoder.conv2.weight"]), bf)
+    put("enc.conv2.b", w["encoder.conv2.bias"], f32)
+    put("enc.pos", w["encoder.positional_embedding"], f32)
+
+    def fused_qkv(p, width):
+        wq, wk, wv = w[p + ".query.weight"], w[p + ".key.weight"], w[p + ".value.weight"]
+        bq, bv = w[p + ".query.bias"], w[p + ".value.bias"]
+        return torch.cat([wq, wk, wv], 0), torch.cat([bq, torch.zeros(width), bv], 0)
+
+    for i in range(dims["n_audio_layer"]):
+        s, d = f"encoder.blocks.{i}", f"enc.{i}"
+        width = dims["n_audio_state"]
+        put(d + ".ln1.w", w[s + ".attn_ln.weight"], f32); put(d + ".ln1.b", w[s + ".attn_ln.bias"], f32)
+        qw, qb = fused_qkv(s + ".attn", width)
+        put(d + ".qkv.w", qw, bf); put(d + ".qkv.b", qb, f32)
+        put(d + ".out.w", w[s + ".attn.out.weight"], bf); put(d + ".out.b", w[s + ".attn.out.bias"], f32)
+        put(d + ".ln2.w", w[s + ".mlp_ln.weight"], f32); put(d + ".ln2.b", w[s + ".mlp_ln.bias"], f32)
+        put(d + ".fc1.w", w[s + ".mlp.0.weight"], bf); put(d + ".fc1.b", w[s + ".mlp.0.bias"], f32)
+        put(d + ".fc2.w", w[s + ".mlp.2.weight"], bf); put(d + ".fc2.b", w[s + ".mlp.2.bias"], f32)
+    put("enc.ln_post.w", w["encoder.ln_post.weight"], f32); put("enc.ln_post.b", w["encoder.ln_post.bias"], f32)
+
+    put("dec.emb", w["decoder.token_embedding.weight"], bf)
+    put("dec.pos", w["decoder.positional_embedding"].to(bf).float(), f32)
+    width = dims["n_text_state"]
+    for i in range(dims["n_text_layer"]):
+        s, d = f"decoder.blocks.{i}", f"dec.{i}"
+        put(d + ".ln1.w", w[s + ".attn_ln.weight"], f32); put(d + ".ln1.b", w[s + ".attn_ln.bias"], f32)
+        qw, qb = fused_qkv(s + ".attn", width)
+        put(d + ".qkv.w", qw, bf); put(d + ".qkv.b", qb, f32)
+        put(d + ".out.w", w[s + ".attn.out.weight"], bf); put(d + ".out.b", w[s + ".attn.out.bias"], f32)
+        put(d + ".ln2.w", w[s + ".cross_attn_ln.weight"], f32); put(d + ".ln2.b", w[s + ".cross_attn_ln.bias"], f32)
+        put(d + ".cq.w", w[s + ".cross_attn.query.weight"], bf); put(d + ".cq.b", w[s + ".cross_attn.query.bias"], f32)
+        put(d + ".ckv.w", torch.cat([w[s + ".cross_attn.key.weight"], w[s + ".cross_attn.value.weight"]], 0), bf)
+        put(d + ".ckv.b", torch.cat([torch.zeros(width), w[s + ".cross_attn.value.bias"]], 0), f32)
+        put(d + ".cout.w", w[s + ".cross_attn.out.weight"], bf); put(d + ".cout.b", w[s + ".cross_attn.out.bias"], f32)
+        put(d + ".ln3.w", w[s + ".mlp_ln.weight"], f32); put(d + ".ln3.b", w[s + ".mlp_ln.bias"], f32)
+        put(d + ".fc1.w", w[s + ".mlp.0.weight"], bf); put(d + ".fc1.b", w[s + ".mlp.0.bias"], f32)
+        put(d + ".fc2.w", w[s + ".mlp.2.weight"], bf); put(d + ".fc2.b", w[s + ".mlp.2.bias"], f32)
+    put("dec.ln.w", w["decoder.ln.weight"], f32); put("dec.ln.b", w["decoder.ln.bias"], f32)
+    return out
+
+
+def random_kernel_weights_on_device(dims: Dict[str, int], device, seed: int = 0, std: float = 0.02):
+    """Large models: draw the random-init weights directly on the GPU in kernel layout (avoids a
+    multi-GB CPU generate + copy).  Same tensor set as to_kernel_layout(init_random_weights(...))."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    bf, f32 = torch.bfloat16, torch.float32
+    out: Dict[str, torch.Tensor] = {}
+
+    def mat(name, *shape, dtype=bf, s=std):
+        out[name] = (torch.randn(*shape, generator=g, device=device, dtype=f32) * s).to(dtype)
+
+    def ln(name, width):
+        out[name + ".w"] = 1.0 + torch.randn(width, generator=g, device=device) * 0.1
+        mat(name + ".b", width, dtype=f32)
+
+    d, nm = dims["n_audio_state"], dims["n_mels"]
+    mat("enc.conv1.w", d, 3 * nm); mat("enc.conv1.b", d, dtype=f32)
+    mat("enc.conv2.w", d, 3 * d); mat("enc.conv2.b", d, dtype=f32)
+    out["enc.pos"] = _sinusoids(dims["n_audio_ctx"], d).to(device)
+
+    def block(p, width, cross):
+        ln(p + ".ln1", width)
+        mat(p + ".qkv.w", 3 * width, width); mat(p + ".qkv.b", 3 * width, dtype=f32)
+        out[p + ".qkv.b"][width:2 * width] = 0
+        mat(p + ".out.w", width, width); mat(p + ".out.b", width, dtype=f32)
+        ln(p + ".ln2", width)
+        if cross:
+            mat(p + ".cq.w", width, width); mat(p + ".cq.b", width, dtype=f32)
+            mat(p + ".ckv.w", 2 * width, width); mat(p + ".ckv.b", 2 * width, dtype=f32)
+            out[p + ".ckv.b"][:width] = 0
+            mat(p + ".cout.w", width, width); mat(p + ".cout.b", width, dtype=f32)
+            ln(p + ".ln3", width)
+        mat(p + ".fc1.w", 4 * width, width); mat(p + ".fc1.b", 4 * width, dtype=f32)
+        mat(p + ".fc2.w", width, 4 * width); mat(p + ".fc2.b", width, dtype=f32)
+
+    for i in range(dims["n_audio_layer"]):
+        block(f"enc.{i}", d, False)
+    ln("enc.ln_post", d)
+    t = dims["n_text_state"]
+    mat("dec.emb", dims["n_vocab"], t)
+    out["dec.pos"] = (torch.randn(dims["n_text_ctx"], t, generator=g, device=device) * std).to(bf).float()
+    for i in range(dims["n_text_layer"]):
+        block(f"dec.{i}", t, True)
+    ln("dec.ln", t)
+    return out
+
+
+def kernel_layout_to_openai_fp32(k: Dict[str, torch.Tensor], dims: Dict[str, int]) -> Dict[str, torch.Tensor]:
+    """Inverse of to_kernel_layout (fp32, CPU): lets the oracle run on exactly the (bf16-rounded)
+    numbers the kernels hold, whichever way the model was initialised."""
+    w: Dict[str, torch.Tensor] = {}
+    c = lambda n: k[n].detach().float().cpu()  # noqa: E731
+    nm, d = dims["n_mels"], dims["n_audio_state"]
+    w["encoder.conv1.weight"] = c("enc.conv1.w").view(d, 3, nm).permute(0, 2, 1).contiguous()
+    w["encoder.conv1.bias"] = c("enc.conv1.b")
+    w["encoder.conv2.weight"] = c("enc.conv2.w").view(d, 3, d).permute(0, 2, 1).contiguous()
+    w["encoder.conv2.bias"] = c("enc.conv2.b")
+    w["encoder.positional_embedding"] = c("enc.pos")
+
+    def unfuse(src, dst, width):
+        qw, qb = c(src + ".qkv.w"), c(src + ".qkv.b")
+        w[dst + ".query.weight"], w[dst + ".key.weight"], w[dst + ".value.weight"] = qw[:width], qw[width:2 * width], qw[2 * width:]
+        w[dst + ".query.bias"], w[dst + ".value.bias"] = qb[:width], qb[2 * width:]
+        w[dst + ".out.weight"], w[dst + ".out.bias"] = c(src + ".out.w"), c(src + ".out.b")
+
+    def mlp(src, dst):
+        w[dst + ".0.weight"], w[dst + ".0.bias"] = c(src + ".fc1.w"), c(src + ".fc1.b")
+        w[dst + ".2.weight"], w[dst + ".2.bias"] = c(src + ".fc2.w"), c(src + ".fc2.b")
+
+    for i in range(dims["n_audio_layer"]):
+        s, o = f"enc.{i}", f"encoder.blocks.{i}"
+        w[o + ".attn_ln.weight"], w[o + ".attn_ln.bias"] = c(s + ".ln1.w"), c(s + ".ln1.b")
+        unfuse(s, o + ".attn", d)
+        w[o + ".mlp_ln.weight"], w[o + ".mlp_ln.bias"] = c(s + ".ln2.w"), c(s + ".ln2.b")
+        mlp(s, o + ".mlp")
+    w["encoder.ln_post.weight"], w["encoder.ln_post.bias"] = c("enc.ln_post.w"), c("enc.ln_post.b")
+    t = dims["n_text_state"]
+    w["decoder.token_embedding.weight"] = c("dec.emb")
+    w["decoder.positional_embedding"] = c("dec.pos")
+    for i in range(dims["n_text_layer"]):
+        s, o = f"dec.{i}", f"decoder.blocks.{i}"
+        w[o + ".attn_ln.weight"], w[o + ".attn_ln.bias"] = c(s + ".ln1.w"), c(s + ".ln1.b")
+        unfuse(s, o + ".attn", t)
+        w[o + ".cross_attn_ln.weight"], w[o + ".cross_attn_ln.bias"] = c(s + ".ln2.w"), c(s + ".ln2.b")
+        ckw, ckb = c(s + ".ckv.w"), c(s + ".ckv.b")
+        w[o + ".cross_attn.query.weight"], w[o + ".cross_attn.query.bias"] = c(s + ".cq.w"), c(s + ".cq.b")
+        w[o + ".cross_attn.key.weight"], w[o + ".cross_attn.value.weight"] = ckw[:t], ckw[t:]
+        w[o + ".cross_attn.value.bias"] = ckb[t:]
+        w[o + ".cross_attn.out.weight"], w[o + ".cross_attn.out.bias"] = c(s + ".cout.w"), c(s + ".cout.b")
+        w[o + ".mlp_ln.weight"], w[o + ".mlp_ln.bias"] = c(s + ".ln3.w"), c(s + ".ln3.b")
+        mlp(s, o + ".mlp")
+    w["decoder.ln.weight"], w["decoder.ln.bias"] = c("dec.ln.w"), c("dec.ln.b")
+    return w
