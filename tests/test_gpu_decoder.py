@@ -1,0 +1,150 @@
+"""GPU parity for K3 (batched greedy KV-cache decoder) against the torch-CPU oracle.
+
+Token-ID parity on random-init weights is ill-posed (top-2 logit margins of 1e-4..3e-3
+against bf16 noise), so three complementary gates are used:
+  1. teacher-forced per-position logits within a stated tolerance;
+  2. free-running greedy with MARGIN-AWARE accounting: every step where the kernel's token differs
+     from the oracle's argmax must be a near-tie (oracle margin below the measured logit error bound);
+  3. free-running greedy on weights engineered for large margins + a scripted EOT: token ids,
+     lengths and EOT latching must be IDENTICAL, sum_logprob within tolerance.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _dims(name):
+    from whisperx.backends import b200_weights as bw
+    if name == "mini":
+        return dict(n_mels=80, n_audio_ctx=1500, n_audio_state=128, n_audio_head=2, n_audio_layer=1,
+                    n_vocab=1000, n_text_ctx=448, n_text_state=128, n_text_head=2, n_text_layer=2)
+    return bw.dims_for(name)
+
+
+def _setup(ctx, name, B, std=0.05, seed=5, mutate=None):
+    from oracle import whisper as ow
+    from whisperx.backends import b200_weights as bw
+    dims = _dims(name)
+    w = bw.init_random_weights(dims, seed=seed, std=std)
+    if mutate is not None:
+        mutate(w, dims)
+    kw = bw.to_kernel_layout(w, dims, "cuda")
+    ctx.set_model(dims, kw)
+    w_ref = bw.kernel_layout_to_openai_fp32(kw, dims)
+    g = torch.Generator().manual_seed(seed + 100)
+    mel = torch.randn(B, dims["n_mels"], 3000, generator=g) * 0.5
+    enc = ctx.encode(mel.cuda())          # bf16: both sides decode from the SAME encoder output
+    return dims, w_ref, enc, ow
+
+
+@pytest.mark.parametrize("name,B", [("mini", 3), ("tiny", 2), ("mini", 19)])
+def test_teacher_forced_logits(wxb_ctx, name, B):
+    dims, w_ref, enc, ow = _setup(wxb_ctx, name, B)
+    n_tok = 6
+    toks = np.random.RandomState(0).randint(0, dims["n_vocab"], size=(B, n_tok)).astype(np.int32)
+    got = wxb_ctx.decoder_logits(enc, toks).float().cpu()
+    with torch.no_grad():
+        cache = ow.DecoderCache(w_ref, dims, enc.float().cpu())
+        ref = ow.decoder_forward(w_ref, dims, torch.from_numpy(toks).long(), cache)
+    err = (got - ref).abs()
+    sigma = float(ref.std())
+    print(f"[{name} B={B}] logits max-abs err {float(err.max()):.4f}, mean {float(err.mean()):.5f}, logit std {sigma:.3f}")
+    assert float(err.max()) <= 0.05 * max(sigma, 1.0) + 0.02, float(err.max())
+    assert float(err.mean()) <= 0.006 * max(sigma, 1.0) + 0.002
+
+
+@pytest.mark.parametrize("name,B,opts", [("mini", 5, {}), ("tiny", 3, {"suppress_blank": True, "suppress_tokens": (7, 50257, 11)})])
+def test_greedy_margin_aware(wxb_ctx, name, B, opts):
+    dims, w_ref, enc, ow = _setup(wxb_ctx, name, B)
+    V = dims["n_vocab"]
+    eot = 50257 if V > 50000 else 3
+    no_speech = 50362 if V > 50000 else 5
+    prompt = [50258, 50259, 50359, 50363] if V > 50000 else [1, 2, 4]
+    sample_len = 20
+    sup = tuple(t for t in opts.get("suppress_tokens", ()) if t < V)
+    # SuppressTokens must not contain eot in a real run; here it checks the mask plumbing only
+    r = wxb_ctx.decode_greedy(enc, prompt, eot, no_speech=no_speech, sample_len=sample_len,
+                              suppress_blank=opts.get("suppress_blank", False), blank_token=220 if V > 220 else 9,
+                              suppress_tokens=sup, check_every=4)
+    got = r["tokens"].cpu().numpy()
+    # oracle teacher-forced on the kernel's tokens, filtered logits per step
+    with torch.no_grad():
+        cache = ow.DecoderCache(w_ref, dims, enc.float().cpu())
+        logits = ow.decoder_forward(w_ref, dims, torch.tensor(prompt)[None].expand(B, -1).contiguous(), cache)
+        nsp_ref = torch.softmax(logits[:, 0], -1)[:, no_speech]
+        cur = logits[:, -1].clone()
+        n_tie, n_exact, sum_lp = 0, 0, torch.zeros(B)
+        alive = torch.ones(B, dtype=torch.bool)
+        for i in range(sample_len):
+            if i == 0 and opts.get("suppress_blank", False):
+                cur[:, 220 if V > 220 else 9] = -float("inf")
+                cur[:, eot] = -float("inf")
+            if sup:
+                cur[:, list(sup)] = -float("inf")
+            lp = cur - torch.logsumexp(cur, -1, keepdim=True)
+            top2 = torch.topk(cur, 2, -1)
+            for b in range(B):
+                tok = int(got[b, i])
+                if not alive[b]:
+                    assert tok == eot  # once EOT always EOT
+                    continue
+                assert np.isfinite(float(cur[b, tok])), f"suppressed token {tok} sampled"
+                if tok == int(top2.indices[b, 0]):
+                    n_exact += 1
+                else:
+                    margin = float(top2.values[b, 0] - cur[b, tok])
+                    assert margin < 0.05, f"row {b} step {i}: kernel token {tok} loses by {margin:.4f} (not a near-tie)"
+                    n_tie += 1
+                sum_lp[b] += lp[b, tok]
+                if tok == eot:
+                    alive[b] = False
+            cur = ow.decoder_forward(w_ref, dims, torch.from_numpy(got[:, i:i + 1]).long(), cache)[:, -1].clone()
+    print(f"[{name}] greedy steps exact {n_exact}, near-tie divergences {n_tie}")
+    assert torch.allclose(r["no_speech_prob"].cpu(), nsp_ref, rtol=0.05, atol=1e-6)
+    assert torch.allclose(r["sum_logprob"].cpu(), sum_lp, rtol=2e-3, atol=0.05)
+    n_tok = r["n_tokens"].cpu().numpy()
+    for b in range(B):
+        row = got[b].tolist()
+        assert n_tok[b] == (row.index(eot) if eot in row else sample_len)
+
+
+def _script(eot_step, first_tok=1000, stride=7):
+    """Engineer large argmax margins: the learned positional embedding dominates the residual stream
+    and the (tied) embedding of the scripted token of each position is aligned with it."""
+    def mutate(w, dims):
+        d, n_ctx = dims["n_text_state"], dims["n_text_ctx"]
+        g = torch.Generator().manual_seed(99)
+        pos = torch.randn(n_ctx, d, generator=g)
+        w["decoder.positional_embedding"] = pos
+        emb = w["decoder.token_embedding.weight"]
+        for p in range(n_ctx):
+            tok = 50257 if p == eot_step else first_tok + stride * p
+            emb[tok] = 0.05 * pos[p]
+    return mutate
+
+
+@pytest.mark.parametrize("B", [4, 17])
+def test_greedy_scripted_tokens_identical(wxb_ctx, B):
+    prompt = [50258, 50259, 50359, 50363]
+    eot, eot_pos = 50257, 3 + 9          # EOT is the 10th sampled token
+    dims, w_ref, enc, ow = _setup(wxb_ctx, "tiny", B, std=0.02, mutate=_script(eot_pos))
+    r = wxb_ctx.decode_greedy(enc, prompt, eot, no_speech=50362, sample_len=40, check_every=4)
+    with torch.no_grad():
+        ref = ow.greedy_decode(w_ref, dims, enc.float().cpu(), prompt, eot, no_speech=50362, sample_len=40)
+    got = r["tokens"].cpu().numpy()
+    n_tok = r["n_tokens"].cpu().numpy()
+    identical = 0
+    for b in range(B):
+        ref_row = ref["tokens"][b]
+        assert len(ref_row) == 9 and ref_row == [1000 + 7 * (3 + i) for i in range(9)]
+        same = got[b, :n_tok[b]].tolist() == ref_row
+        identical += int(same)
+        if not same:
+            print(f"DIVERGENCE row {b}: kernel {got[b, :n_tok[b]].tolist()} vs oracle {ref_row}")
+        assert (got[b, n_tok[b]:] == eot).all()
+    print(f"scripted greedy: {identical}/{B} segments identical")
+    assert identical == B
+    assert torch.allclose(r["sum_logprob"].cpu(), ref["sum_logprob"], rtol=1e-2, atol=1e-3)
+    assert torch.allclose(r["no_speech_prob"].cpu(), ref["no_speech_prob"], rtol=0.05, atol=1e-7)

@@ -1,7 +1,883 @@
-#include "wxb_common.cuh"
-extern "C" int wxb_decode_greedy(wxb_ctx* ctx, const void*, int, const int32_t*, int, const wxb_decode_opts*, int32_t*, int32_t*, float*, float*, void*) {
-  return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "wxb_decode_greedy: not built yet");
+// wxb_decoder.cu — K3: batched greedy KV-cache decoder (Whisper TextDecoder) for VAD-cut chunks.
+//
+// Behavioural spec: the reference's in-tree batched loop
+//   /root/reference/mlx_whisper_batch_decoder.py:317-384 (_main_loop_batch), :267-303 (update),
+//   :386-468 (run: EOT trimming, avg_logprob), filters per SURVEY A.3 (SuppressBlank, SuppressTokens).
+//
+// One decode step is bandwidth-bound (weights once per step + cross-KV once per sequence), so every
+// kernel here is built around streaming HBM:
+//   dec_gemv_kernel    y[b,n] = sum_k act[b,k] W[n,k]: mma.sync m16n8k16 with the BATCH as the M tile
+//                      (<=16 rows, padded) and 8 weight rows as the N tile; weights are read straight
+//                      from HBM into MMA B-fragments with 16-byte loads (a K-permutation shared by the
+//                      A and B fragments makes natural row-major weights fragment-ready, no repack, no
+//                      shared-memory staging); the first weight loads are issued BEFORE the
+//                      programmatic-dependent-launch wait so they overlap the previous kernel's tail.
+//                      LayerNorm of the residual stream is fused into the activation staging, and
+//                      bias / GELU / residual add / QKV scatter into the KV cache into the epilogue.
+//   dec_attn_kernel    one CTA per (split, head, sequence): 8 lanes per key (16-byte loads, 128 B per
+//                      key row = fully coalesced), scores -> softmax -> P.V in fp32, split-KV partials
+//                      merged by the last-arriving CTA (self-cleaning ticket).
+//   dec_sample_kernel  logit filters + argmax (first max) + logsumexp + bookkeeping, one CTA per row.
+// The per-step launch sequence is captured once in a CUDA graph (position read from device memory).
+//
+// HBM layout (L decoder layers, B sequences, H heads, d = 64 H):
+//   self K/V  bf16 [L][2][B][H][448][64]      cross K/V bf16 [L][2][B][H][1500][64]
+//   x f32 [B,d] residual; q f32 [B,d]; att f32 [B,d]; hid bf16 [B,4d]; logits f32 [B,V]
+#include "wxb_gemm.cuh"
+#include "wxb_model.cuh"
+#include <math.h>
+#include <stdlib.h>
+
+int wxb_launch_layernorm(wxb_ctx* ctx, const float* x, const float* w, const float* b, __nv_bfloat16* y, long long rows,
+                         int d, cudaStream_t st);
+
+namespace {
+
+constexpr int T_AUDIO = 1500;
+constexpr int GV_THREADS = 256;
+constexpr int GV_U = 5;  // 64-wide K chunks per register group
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+__device__ __forceinline__ void mma_16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-extern "C" int wxb_decoder_logits(wxb_ctx* ctx, const void*, int, const int32_t*, int, float*, void*) {
-  return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "wxb_decoder_logits: not built yet");
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+enum { IN_LN = 0, IN_F32 = 1, IN_BF16 = 2 };
+enum { EPI_F32 = 0, EPI_RESID = 1, EPI_GELU_BF16 = 2, EPI_QKV = 3 };
+
+struct GemvParams {
+  int B, N, K, kw;  // kw = warps that split K for one 8-row group (8 % kw == 0)
+  int in_mode;
+  const void* in;
+  long long ld_in;
+  const float *ln_w, *ln_b;
+  const __nv_bfloat16* W;
+  const float* bias;
+  int epi;
+  void* out;
+  long long ldo;
+  // EPI_QKV
+  float* q_out;
+  __nv_bfloat16 *kcache, *vcache;  // [B][H][tmax][64] of this layer
+  const int* d_pos;
+  int H, tmax;
+};
+
+// Weight chunk c of this lane: two 16-byte loads at k = 64c + 8t and 64c + 32 + 8t of row (n0 + g).
+__device__ __forceinline__ void gv_load(uint4* w, const __nv_bfloat16* wrow, int c_first, int c_end) {
+#pragma unroll
+  for (int u = 0; u < GV_U; ++u) {
+    const int c = c_first + u;
+    if (c < c_end) {
+      w[2 * u] = ldg_nc_v4(wrow + (size_t)c * 64);
+      w[2 * u + 1] = ldg_nc_v4(wrow + (size_t)c * 64 + 32);
+    }
+  }
+}
+__device__ __forceinline__ void gv_compute(float* acc, const uint4* w, const unsigned char* act_lo, const unsigned char* act_hi,
+                                           int c_first, int c_end) {
+#pragma unroll
+  for (int u = 0; u < GV_U; ++u) {
+    const int c = c_first + u;
+    if (c < c_end) {
+      const uint4 al0 = *reinterpret_cast<const uint4*>(act_lo + c * 128);
+      const uint4 ah0 = *reinterpret_cast<const uint4*>(act_hi + c * 128);
+      const uint4 al1 = *reinterpret_cast<const uint4*>(act_lo + c * 128 + 64);
+      const uint4 ah1 = *reinterpret_cast<const uint4*>(act_hi + c * 128 + 64);
+      const uint4 w0 = w[2 * u], w1 = w[2 * u + 1];
+      mma_16816(acc, al0.x, ah0.x, al0.y, ah0.y, w0.x, w0.y);
+      mma_16816(acc, al0.z, ah0.z, al0.w, ah0.w, w0.z, w0.w);
+      mma_16816(acc, al1.x, ah1.x, al1.y, ah1.y, w1.x, w1.y);
+      mma_16816(acc, al1.z, ah1.z, al1.w, ah1.w, w1.z, w1.w);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(GV_THREADS)
+dec_gemv_kernel(const GemvParams p) {
+  extern __shared__ __align__(16) unsigned char gv_smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int kw = p.kw, rg_per_cta = 8 / kw;
+  const int rg = warp / kw, ks = warp - rg * kw;
+  const int n0 = (blockIdx.x * rg_per_cta + rg) * 8;
+  const int b0 = blockIdx.y * 16;
+  const int chunks = p.K / 64 / kw;
+  const int c_begin = ks * chunks, c_end = c_begin + chunks;
+  const size_t row_bytes = (size_t)(p.K + 32) * 2;  // +64 B: rows g and g+1 land on different bank halves
+  float* red = reinterpret_cast<float*>(gv_smem + 16 * row_bytes);
+
+  const bool warp_active = n0 < p.N;
+  int nrow = n0 + g;
+  if (nrow >= p.N) nrow = p.N - 1;
+  const __nv_bfloat16* wrow = p.W + (size_t)nrow * p.K + 8 * t;
+  uint4 wa[2 * GV_U], wb[2 * GV_U];
+  if (warp_active) gv_load(wa, wrow, c_begin, c_end);  // independent of the previous kernel: issue before the PDL wait
+  pdl_wait();
+
+  // ---- stage the activation tile (16 batch rows x K) as bf16 ----
+  if (p.in_mode == IN_LN) {
+    const float* x = reinterpret_cast<const float*>(p.in);
+    for (int r = warp; r < 16; r += 8) {
+      const int b = b0 + r;
+      unsigned char* dst = gv_smem + r * row_bytes;
+      const int nv = p.K >> 2;
+      if (b < p.B) {
+        const float4* xr = reinterpret_cast<const float4*>(x + (size_t)b * p.ld_in);
+        float4 v[10];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+          const int idx = lane + 32 * i;
+          if (idx < nv) { v[i] = xr[idx]; s += v[i].x + v[i].y + v[i].z + v[i].w; }
+        }
+        const float mean = warp_sum(s) / p.K;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+          const int idx = lane + 32 * i;
+          if (idx < nv) {
+            const float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+            q += a * a + bb * bb + c * c + e * e;
+          }
+        }
+        const float rstd = rsqrtf(warp_sum(q) / p.K + 1e-5f);
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+          const int idx = lane + 32 * i;
+          if (idx < nv) {
+            const float4 ww = __ldg(reinterpret_cast<const float4*>(p.ln_w) + idx);
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.ln_b) + idx);
+            uint2 pk;
+            pk.x = pack_bf16((v[i].x - mean) * rstd * ww.x + bb.x, (v[i].y - mean) * rstd * ww.y + bb.y);
+            pk.y = pack_bf16((v[i].z - mean) * rstd * ww.z + bb.z, (v[i].w - mean) * rstd * ww.w + bb.w);
+            *reinterpret_cast<uint2*>(dst + idx * 8) = pk;
+          }
+        }
+      } else {
+        for (int idx = lane; idx < nv; idx += 32) *reinterpret_cast<uint2*>(dst + idx * 8) = make_uint2(0u, 0u);
+      }
+    }
+  } else if (p.in_mode == IN_F32) {
+    const float* x = reinterpret_cast<const float*>(p.in);
+    const int nv = p.K >> 2;
+    for (int idx = tid; idx < 16 * nv; idx += GV_THREADS) {
+      const int r = idx / nv, c = idx - r * nv;
+      const int b = b0 + r;
+      uint2 pk = make_uint2(0u, 0u);
+      if (b < p.B) {
+        const float4 v = *reinterpret_cast<const float4*>(x + (size_t)b * p.ld_in + c * 4);
+        pk.x = pack_bf16(v.x, v.y);
+        pk.y = pack_bf16(v.z, v.w);
+      }
+      *reinterpret_cast<uint2*>(gv_smem + r * row_bytes + c * 8) = pk;
+    }
+  } else {
+    const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(p.in);
+    const int nv = p.K >> 3;
+    for (int idx = tid; idx < 16 * nv; idx += GV_THREADS) {
+      const int r = idx / nv, c = idx - r * nv;
+      const int b = b0 + r;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (b < p.B) v = *reinterpret_cast<const uint4*>(x + (size_t)b * p.ld_in + c * 8);
+      *reinterpret_cast<uint4*>(gv_smem + r * row_bytes + c * 16) = v;
+    }
+  }
+  __syncthreads();
+  pdl_launch();
+
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (warp_active) {
+    const unsigned char* act_lo = gv_smem + g * row_bytes + 16 * t;
+    const unsigned char* act_hi = act_lo + 8 * row_bytes;
+    for (int c = c_begin; c < c_end; c += 2 * GV_U) {
+      if (c + GV_U < c_end) gv_load(wb, wrow, c + GV_U, c_end);
+      gv_compute(acc, wa, act_lo, act_hi, c, c_end);
+      if (c + 2 * GV_U < c_end) gv_load(wa, wrow, c + 2 * GV_U, c_end);
+      if (c + GV_U < c_end) gv_compute(acc, wb, act_lo, act_hi, c + GV_U, c_end);
+    }
+  }
+  // ---- reduce the kw K-slices of each row group, then the epilogue ----
+  if (kw > 1) {
+    *reinterpret_cast<float4*>(red + (warp * 32 + lane) * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    __syncthreads();
+    if (ks != 0) return;
+    for (int s = 1; s < kw; ++s) {
+      const float4 o = *reinterpret_cast<const float4*>(red + ((warp + s) * 32 + lane) * 4);
+      acc[0] += o.x; acc[1] += o.y; acc[2] += o.z; acc[3] += o.w;
+    }
+  }
+  if (!warp_active) return;
+  int pos = 0;
+  if (p.epi == EPI_QKV) pos = *p.d_pos;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int b = b0 + g + (i >> 1) * 8;
+    const int n = n0 + 2 * t + (i & 1);
+    if (b >= p.B || n >= p.N) continue;
+    float v = acc[i] + (p.bias ? __ldg(p.bias + n) : 0.f);
+    if (p.epi == EPI_F32) {
+      reinterpret_cast<float*>(p.out)[(size_t)b * p.ldo + n] = v;
+    } else if (p.epi == EPI_RESID) {
+      float* o = reinterpret_cast<float*>(p.out) + (size_t)b * p.ldo + n;
+      *o = *o + v;
+    } else if (p.epi == EPI_GELU_BF16) {
+      reinterpret_cast<__nv_bfloat16*>(p.out)[(size_t)b * p.ldo + n] = __float2bfloat16_rn(gelu_erf(v));
+    } else {
+      const int d = p.N / 3;
+      if (n < d) {
+        p.q_out[(size_t)b * d + n] = v;
+      } else {
+        const int nn = (n < 2 * d) ? (n - d) : (n - 2 * d);
+        __nv_bfloat16* cache = (n < 2 * d) ? p.kcache : p.vcache;
+        const int h = nn >> 6, j = nn & 63;
+        cache[(((size_t)b * p.H + h) * p.tmax + pos) * 64 + j] = __float2bfloat16_rn(v);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// decode attention: q f32 [B,d] against K/V bf16 [B][H][tkv][64]
+// ---------------------------------------------------------------------------------------------
+constexpr int DA_THREADS = 256;
+
+struct AttnParams {
+  const float* q;               // [B, d]
+  const __nv_bfloat16 *K, *V;   // [B][H][tkv][64]
+  int tkv;                      // allocated keys per (b,h)
+  int n_keys;                   // used when d_pos == nullptr
+  const int* d_pos;             // if set: n_keys = *d_pos + 1 (self-attention)
+  int splits, H, d;
+  float scale;
+  float* out;                   // [B, d]
+  float* part;                  // [B][H][splits][66]  (m, l, o[64])
+  int* ticket;                  // [B*H], zero-initialised, self-cleaning
+};
+
+__global__ void __launch_bounds__(DA_THREADS)
+dec_attn_kernel(const AttnParams p) {
+  extern __shared__ __align__(16) float da_smem[];
+  float* sc = da_smem;                       // [per] scores
+  float* sq = sc + ((p.tkv + p.splits - 1) / p.splits + 32);  // [64] q
+  float* sred = sq + 64;                     // [8*64 + 16]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int slot = lane >> 3, c8 = lane & 7;  // 4 keys per warp iteration, 8 lanes x 8 dims per key
+  const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  pdl_wait();
+  const int n_keys = p.d_pos ? (*p.d_pos + 1) : p.n_keys;
+  const int per = (n_keys + p.splits - 1) / p.splits;
+  const int k0 = split * per;
+  const int k1 = min(n_keys, k0 + per);
+  const size_t slab = ((size_t)b * p.H + h) * p.tkv * 64;
+  const __nv_bfloat16* Kb = p.K + slab;
+  const __nv_bfloat16* Vb = p.V + slab;
+  if (tid < 64) sq[tid] = p.q[(size_t)b * p.d + h * 64 + tid] * p.scale;
+  __syncthreads();
+  pdl_launch();
+  float qr[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) qr[j] = sq[c8 * 8 + j];
+
+  // ---- scores ----
+  float lmax = -INFINITY;
+  for (int kb = k0 + warp * 4; kb < k1; kb += 32 * 4) {
+    uint4 kv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int key = kb + u * 32 + slot;
+      if (key < k1) kv[u] = ldg_nc_v4(Kb + (size_t)key * 64 + c8 * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int key = kb + u * 32 + slot;
+      float s = 0.f;
+      if (key < k1) {
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&kv[u]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(h2[j]);
+          s = fmaf(qr[2 * j], f.x, s);
+          s = fmaf(qr[2 * j + 1], f.y, s);
+        }
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      if (key < k1) {
+        if (c8 == 0) sc[key - k0] = s;
+        lmax = fmaxf(lmax, s);
+      }
+    }
+  }
+  lmax = warp_max(lmax);
+  if (lane == 0) sred[warp] = lmax;
+  __syncthreads();
+  float m = sred[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) m = fmaxf(m, sred[w]);
+  __syncthreads();
+  // ---- softmax numerators + P.V ----
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  float lsum = 0.f;
+  for (int kb = k0 + warp * 4; kb < k1; kb += 32 * 4) {
+    uint4 vv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int key = kb + u * 32 + slot;
+      if (key < k1) vv[u] = ldg_nc_v4(Vb + (size_t)key * 64 + c8 * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int key = kb + u * 32 + slot;
+      if (key < k1) {
+        const float pr = __expf(sc[key - k0] - m);
+        if (c8 == 0) lsum += pr;
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&vv[u]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(h2[j]);
+          acc[2 * j] = fmaf(pr, f.x, acc[2 * j]);
+          acc[2 * j + 1] = fmaf(pr, f.y, acc[2 * j + 1]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
+    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+  }
+  lsum = warp_sum(lsum);
+  if (slot == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sred[16 + warp * 64 + c8 * 8 + j] = acc[j];
+  }
+  if (lane == 0) sred[8 + warp] = lsum;
+  __syncthreads();
+  float o = 0.f, l = 0.f;
+  if (tid < 64) {
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { o += sred[16 + w * 64 + tid]; l += sred[8 + w]; }
+  }
+  if (p.splits == 1) {
+    if (tid < 64) p.out[(size_t)b * p.d + h * 64 + tid] = o / l;
+    return;
+  }
+  // ---- split-KV: publish the partial, the last CTA of this (b,h) merges ----
+  float* part = p.part + (((size_t)b * p.H + h) * p.splits) * 66;
+  if (tid < 64) {
+    part[split * 66 + 2 + tid] = o;
+    if (tid == 0) { part[split * 66] = m; part[split * 66 + 1] = l; }
+  }
+  __threadfence();
+  __syncthreads();
+  __shared__ int s_last;
+  if (tid == 0) {
+    const int prev = atomicAdd(p.ticket + b * p.H + h, 1);
+    s_last = (prev == p.splits - 1);
+    if (s_last) p.ticket[b * p.H + h] = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (tid < 64) {
+    float M = -INFINITY;
+    for (int s = 0; s < p.splits; ++s) M = fmaxf(M, __ldcg(part + s * 66));
+    float L = 0.f, O = 0.f;
+    for (int s = 0; s < p.splits; ++s) {
+      const float w = __expf(__ldcg(part + s * 66) - M);
+      L += w * __ldcg(part + s * 66 + 1);
+      O += w * __ldcg(part + s * 66 + 2 + tid);
+    }
+    p.out[(size_t)b * p.d + h * 64 + tid] = O / L;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// token embedding + learned position; sampling; bookkeeping
+// ---------------------------------------------------------------------------------------------
+// x[b,:] = emb[tok[b*stride + col]] + pos_emb[pos], col = pos = *d_pos
+__global__ void dec_embed_kernel(const int* __restrict__ tok, int stride, const int* __restrict__ d_pos,
+                                 const __nv_bfloat16* __restrict__ emb, const float* __restrict__ pos_emb,
+                                 float* __restrict__ x, int d, int n_vocab) {
+  pdl_wait();
+  const int b = blockIdx.x;
+  const int pos = *d_pos;
+  int token = tok[(size_t)b * stride + pos];
+  token = min(max(token, 0), n_vocab - 1);
+  for (int i = threadIdx.x; i < d; i += blockDim.x)
+    x[(size_t)b * d + i] = __bfloat162float(emb[(size_t)token * d + i]) + pos_emb[(size_t)pos * d + i];
+}
+
+__global__ void dec_advance_kernel(int* d_pos) {
+  pdl_wait();
+  if (threadIdx.x == 0) *d_pos += 1;
+}
+
+// softmax probability of `token` per row (no_speech_prob at the SOT position, unfiltered)
+__global__ void dec_token_prob_kernel(const float* __restrict__ logits, int V, int token, float* __restrict__ out) {
+  __shared__ float red[32];
+  pdl_wait();
+  const float* x = logits + (size_t)blockIdx.x * V;
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) m = fmaxf(m, x[i]);
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = red[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
+  __syncthreads();
+  float s = 0.f;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) s += expf(x[i] - m);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    out[blockIdx.x] = expf(x[token] - m) / t;
+  }
+}
+
+struct SampleParams {
+  float* logits;  // [B, V] (filters are applied in place)
+  int V;
+  int* tokens;    // [B, stride]: prompt + sampled tokens; this step writes column pos + 1
+  int stride;
+  int* d_pos;
+  int prompt_len;
+  int eot, suppress_blank, blank_token, n_suppress;
+  const int* suppress;
+  float* sum_logprob;  // [B]
+  int* done;           // [B] 1 once the row has emitted EOT
+};
+
+// mlx_whisper_batch_decoder.py:267-303 for one row: filters, argmax, logprob accounting, EOT latch.
+__global__ void __launch_bounds__(1024)
+dec_sample_kernel(const SampleParams p) {
+  __shared__ float s_val[32];
+  __shared__ int s_idx[32];
+  pdl_wait();
+  const int b = blockIdx.x, tid = threadIdx.x;
+  float* x = p.logits + (size_t)b * p.V;
+  const int pos = *p.d_pos;
+  for (int i = tid; i < p.n_suppress; i += blockDim.x) {
+    const int id = p.suppress[i];
+    if (id >= 0 && id < p.V) x[id] = -INFINITY;
+  }
+  if (p.suppress_blank && pos == p.prompt_len - 1 && tid == 0) {
+    if (p.blank_token >= 0 && p.blank_token < p.V) x[p.blank_token] = -INFINITY;
+    x[p.eot] = -INFINITY;
+  }
+  __syncthreads();
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = tid; i < p.V; i += blockDim.x) {
+    const float v = x[i];
+    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if ((tid & 31) == 0) { s_val[tid >> 5] = best; s_idx[tid >> 5] = bi; }
+  __syncthreads();
+  best = s_val[0]; bi = s_idx[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+    if (s_val[w] > best || (s_val[w] == best && s_idx[w] < bi)) { best = s_val[w]; bi = s_idx[w]; }
+  __syncthreads();
+  float s = 0.f;
+  for (int i = tid; i < p.V; i += blockDim.x) s += expf(x[i] - best);
+  s = warp_sum(s);
+  if ((tid & 31) == 0) s_val[tid >> 5] = s;
+  __syncthreads();
+  if (tid == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_val[w];
+    const float logprob = -logf(tot);  // x[bi] - (best + log(sum)) with x[bi] == best
+    int* row = p.tokens + (size_t)b * p.stride;
+    const int last = row[pos];
+    const bool was_eot = (last == p.eot) && (pos >= p.prompt_len);  // prompt tokens never latch
+    if (!was_eot) p.sum_logprob[b] += logprob;
+    const int next = was_eot ? p.eot : bi;
+    row[pos + 1] = next;
+    if (next == p.eot) p.done[b] = 1;
+  }
+  if (b == 0 && tid == 0) {
+    // every row of this step has read d_pos before any block can be this far? No: blocks are
+    // independent, so the position is advanced by dec_advance_kernel in the next launch.
+  }
+}
+
+// n_tokens[b] = sampled tokens before the first EOT; tokens_out[b, i] = sampled token i (EOT padded)
+__global__ void dec_finalize_kernel(const int* __restrict__ tokens, int stride, int prompt_len, int n_sampled, int sample_len,
+                                    int eot, int* __restrict__ tokens_out, int* __restrict__ n_tokens) {
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) {
+    int n = n_sampled;
+    for (int i = 0; i < n_sampled; ++i)
+      if (tokens[(size_t)b * stride + prompt_len + i] == eot) { n = i; break; }
+    n_tokens[b] = n;
+  }
+  for (int i = threadIdx.x; i < sample_len; i += blockDim.x)
+    tokens_out[(size_t)b * sample_len + i] = (i < n_sampled) ? tokens[(size_t)b * stride + prompt_len + i] : eot;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct DecBuffers {
+  float *x, *q, *att, *logits, *part, *sum_lp;
+  __nv_bfloat16 *hid, *self_kv, *cross_kv;
+  int *ticket, *d_pos, *tokens, *done;
+  int B, tok_stride;
+};
+
+bool use_pdl() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WXB_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+template <typename... KArgs, typename... Args>
+int launch_k(wxb_ctx* ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl() ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+  ctx->launches++;
+  if (e != cudaSuccess) return wxb_fail(ctx, WXB_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  return WXB_OK;
+}
+
+int pick_kw(int K) {
+  for (int kw = 8; kw >= 1; kw >>= 1)
+    if (K % (64 * kw) == 0) return kw;
+  return 0;
+}
+
+int launch_gemv(wxb_ctx* ctx, GemvParams p, cudaStream_t st) {
+  p.kw = pick_kw(p.K);
+  if (p.kw == 0) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "gemv: K=%d must be a multiple of 64", p.K);
+  if (p.in_mode == IN_LN && p.K > 1280) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "gemv: fused LayerNorm needs K <= 1280");
+  const int rg = 8 / p.kw;
+  const size_t smem = (size_t)16 * (p.K + 32) * 2 + 8 * 128 * 4;  // opt-in size set in alloc_buffers()
+  dim3 grid(ceil_div(ceil_div(p.N, 8), rg), ceil_div(p.B, 16));
+  return launch_k(ctx, dec_gemv_kernel, grid, dim3(GV_THREADS), smem, st, p);
+}
+
+int launch_attn(wxb_ctx* ctx, AttnParams p, int B, cudaStream_t st) {
+  const size_t smem = (size_t)((p.tkv + p.splits - 1) / p.splits + 32 + 64 + 8 * 64 + 16) * 4;
+  return launch_k(ctx, dec_attn_kernel, dim3(p.splits, p.H, B), dim3(DA_THREADS), smem, st, p);
+}
+
+int alloc_buffers(wxb_ctx* ctx, int B, int tok_stride, DecBuffers* o) {
+  const wxb_dims& D = ctx->model->dims;
+  const int d = D.n_text_state, L = D.n_text_layer, H = D.n_text_head, V = D.n_vocab;
+  o->B = B;
+  o->tok_stride = tok_stride;
+  {  // largest dynamic shared memory any decoder kernel asks for (fc2: K = 4d); set outside graph capture
+    const size_t gv_smem = (size_t)16 * (4 * d + 32) * 2 + 8 * 128 * 4;
+    if (gv_smem > 227 * 1024) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: d=%d too wide for the GEMV activation tile", d);
+    WXB_CUDA(ctx, cudaFuncSetAttribute(dec_gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gv_smem));
+  }
+  o->x = (float*)wxb_named(ctx, "dec.x", (size_t)B * d * 4);
+  o->q = (float*)wxb_named(ctx, "dec.q", (size_t)B * d * 4);
+  o->att = (float*)wxb_named(ctx, "dec.att", (size_t)B * d * 4);
+  o->hid = (__nv_bfloat16*)wxb_named(ctx, "dec.hid", (size_t)B * 4 * d * 2);
+  o->logits = (float*)wxb_named(ctx, "dec.logits", (size_t)B * V * 4);
+  o->part = (float*)wxb_named(ctx, "dec.part", (size_t)B * H * 8 * 66 * 4);
+  o->sum_lp = (float*)wxb_named(ctx, "dec.sum_lp", (size_t)B * 4);
+  o->self_kv = (__nv_bfloat16*)wxb_named(ctx, "dec.self_kv", (size_t)L * 2 * B * H * D.n_text_ctx * 64 * 2);
+  o->cross_kv = (__nv_bfloat16*)wxb_named(ctx, "dec.cross_kv", (size_t)L * 2 * B * H * T_AUDIO * 64 * 2);
+  o->ticket = (int*)wxb_named(ctx, "dec.ticket", (size_t)B * H * 4 + 64, true);
+  o->d_pos = (int*)wxb_named(ctx, "dec.pos", 64);
+  o->tokens = (int*)wxb_named(ctx, "dec.tokens", (size_t)B * tok_stride * 4);
+  o->done = (int*)wxb_named(ctx, "dec.done", (size_t)B * 4);
+  if (!o->x || !o->q || !o->att || !o->hid || !o->logits || !o->part || !o->sum_lp || !o->self_kv || !o->cross_kv ||
+      !o->ticket || !o->d_pos || !o->tokens || !o->done)
+    return WXB_ERR_CUDA;
+  return WXB_OK;
+}
+
+// cross K/V of every decoder layer from the encoder output (tcgen05 GEMM, head-major scatter)
+int cross_kv_precompute(wxb_ctx* ctx, const __nv_bfloat16* enc_out, const DecBuffers& buf, cudaStream_t st) {
+  const wxb_dims& D = ctx->model->dims;
+  const int d = D.n_text_state, H = D.n_text_head, B = buf.B;
+  for (int l = 0; l < D.n_text_layer; ++l) {
+    DecLayerW w;
+    int rc = wxb_dec_layer(ctx, l, &w);
+    if (rc != WXB_OK) return rc;
+    GemmArgs a;
+    a.A = enc_out; a.lda = D.n_audio_state; a.M = B * T_AUDIO; a.W = w.ckv_w; a.N = 2 * d; a.K = D.n_audio_state;
+    a.bias = w.ckv_b;
+    a.out = buf.cross_kv + (size_t)l * 2 * B * H * T_AUDIO * 64;
+    a.ldo = 2 * d; a.kv_mode = 1; a.kv_B = B; a.kv_H = H; a.kv_T = T_AUDIO;
+    if ((rc = wxb_gemm_launch(ctx, a, st)) != WXB_OK) return rc;
+  }
+  return WXB_OK;
+}
+
+// One decoder step at position *d_pos over buf.tokens[:, pos]; logits (optional) to logits_out with row stride ldl.
+int decoder_step(wxb_ctx* ctx, const DecBuffers& buf, float* logits_out, long long ldl, cudaStream_t st) {
+  const wxb_dims& D = ctx->model->dims;
+  const int d = D.n_text_state, H = D.n_text_head, B = buf.B, L = D.n_text_layer, TX = D.n_text_ctx;
+  const __nv_bfloat16* emb = (const __nv_bfloat16*)wxb_weight(ctx, "dec.emb");
+  const float* pos_emb = (const float*)wxb_weight(ctx, "dec.pos");
+  const float* lnf_w = (const float*)wxb_weight(ctx, "dec.ln.w");
+  const float* lnf_b = (const float*)wxb_weight(ctx, "dec.ln.b");
+  if (!emb || !pos_emb || !lnf_w || !lnf_b) return WXB_ERR_STATE;
+  int rc;
+  if ((rc = launch_k(ctx, dec_embed_kernel, dim3(B), dim3(256), 0, st, (const int*)buf.tokens, buf.tok_stride,
+                     (const int*)buf.d_pos, emb, pos_emb, buf.x, d, D.n_vocab)) != WXB_OK)
+    return rc;
+  const float scale = 1.0f / sqrtf(64.f);
+  const int cross_splits = (B * H >= 4 * ctx->sm_count) ? 1 : ((B * H >= 2 * ctx->sm_count) ? 2 : 4);
+  for (int l = 0; l < L; ++l) {
+    DecLayerW w;
+    if ((rc = wxb_dec_layer(ctx, l, &w)) != WXB_OK) return rc;
+    __nv_bfloat16* sk = buf.self_kv + (size_t)l * 2 * B * H * TX * 64;
+    __nv_bfloat16* sv = sk + (size_t)B * H * TX * 64;
+    const __nv_bfloat16* ck = buf.cross_kv + (size_t)l * 2 * B * H * T_AUDIO * 64;
+    const __nv_bfloat16* cv = ck + (size_t)B * H * T_AUDIO * 64;
+    GemvParams g = {};
+    g.B = B;
+    // 1. LN1 + fused QKV, K/V appended to the self cache at pos
+    g.N = 3 * d; g.K = d; g.in_mode = IN_LN; g.in = buf.x; g.ld_in = d; g.ln_w = w.ln1_w; g.ln_b = w.ln1_b;
+    g.W = w.qkv_w; g.bias = w.qkv_b; g.epi = EPI_QKV; g.q_out = buf.q; g.kcache = sk; g.vcache = sv;
+    g.d_pos = buf.d_pos; g.H = H; g.tmax = TX;
+    if ((rc = launch_gemv(ctx, g, st)) != WXB_OK) return rc;
+    // 2. causal self-attention over pos+1 cached positions
+    AttnParams a = {};
+    a.q = buf.q; a.K = sk; a.V = sv; a.tkv = TX; a.d_pos = buf.d_pos; a.splits = 1; a.H = H; a.d = d; a.scale = scale;
+    a.out = buf.att; a.part = buf.part; a.ticket = buf.ticket;
+    if ((rc = launch_attn(ctx, a, B, st)) != WXB_OK) return rc;
+    // 3. out projection + residual
+    g = GemvParams{};
+    g.B = B; g.N = d; g.K = d; g.in_mode = IN_F32; g.in = buf.att; g.ld_in = d; g.W = w.out_w; g.bias = w.out_b;
+    g.epi = EPI_RESID; g.out = buf.x; g.ldo = d;
+    if ((rc = launch_gemv(ctx, g, st)) != WXB_OK) return rc;
+    // 4. LN2 + cross query
+    g = GemvParams{};
+    g.B = B; g.N = d; g.K = d; g.in_mode = IN_LN; g.in = buf.x; g.ld_in = d; g.ln_w = w.ln2_w; g.ln_b = w.ln2_b;
+    g.W = w.cq_w; g.bias = w.cq_b; g.epi = EPI_F32; g.out = buf.q; g.ldo = d;
+    if ((rc = launch_gemv(ctx, g, st)) != WXB_OK) return rc;
+    // 5. cross-attention over the 1500 encoder positions
+    a = AttnParams{};
+    a.q = buf.q; a.K = ck; a.V = cv; a.tkv = T_AUDIO; a.n_keys = T_AUDIO; a.d_pos = nullptr; a.splits = cross_splits;
+    a.H = H; a.d = d; a.scale = scale; a.out = buf.att; a.part = buf.part; a.ticket = buf.ticket;
+    if ((rc = launch_attn(ctx, a, B, st)) != WXB_OK) return rc;
+    // 6. cross out projection + residual
+    g = GemvParams{};
+    g.B = B; g.N = d; g.K = d; g.in_mode = IN_F32; g.in = buf.att; g.ld_in = d; g.W = w.cout_w; g.bias = w.cout_b;
+    g.epi = EPI_RESID; g.out = buf.x; g.ldo = d;
+    if ((rc = launch_gemv(ctx, g, st)) != WXB_OK) return rc;
+    // 7. LN3 + fc1 + GELU
+    g = GemvParams{};
+    g.B = B; g.N = 4 * d; g.K = d; g.in_mode = IN_LN; g.in = buf.x; g.ld_in = d; g.ln_w = w.ln3_w; g.ln_b = w.ln3_b;
+    g.W = w.fc1_w; g.bias = w.fc1_b; g.epi = EPI_GELU_BF16; g.out = buf.hid; g.ldo = 4 * d;
+    if ((rc = launch_gemv(ctx, g, st)) != WXB_OK) return rc;
+    // 8. fc2 + residual
+    g = GemvParams{};
+    g.B = B; g.N = d; g.K = 4 * d; g.in_mode = IN_BF16; g.in = buf.hid; g.ld_in = 4 * d; g.W = w.fc2_w; g.bias = w.fc2_b;
+    g.epi = EPI_RESID; g.out = buf.x; g.ldo = d;
+    if ((rc = launch_gemv(ctx, g, st)) != WXB_OK) return rc;
+  }
+  if (logits_out) {
+    GemvParams g = {};
+    g.B = B; g.N = D.n_vocab; g.K = d; g.in_mode = IN_LN; g.in = buf.x; g.ld_in = d; g.ln_w = lnf_w; g.ln_b = lnf_b;
+    g.W = emb; g.bias = nullptr; g.epi = EPI_F32; g.out = logits_out; g.ldo = ldl;
+    if ((rc = launch_gemv(ctx, g, st)) != WXB_OK) return rc;
+  }
+  return WXB_OK;
+}
+
+struct StepGraph {
+  cudaGraphExec_t exec = nullptr;
+  // identity of what was captured
+  const void* model = nullptr;
+  int B = 0, tok_stride = 0, mode = 0;
+  void* key_ptrs[4] = {nullptr, nullptr, nullptr, nullptr};
+  SampleParams sp = {};
+};
+StepGraph g_graphs[3];  // 0: prefill (no logits), 1: prefill + logits (no sampling), 2: logits + sample
+
+bool use_graph() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WXB_GRAPH");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+int enqueue_step(wxb_ctx* ctx, const DecBuffers& buf, int mode, const SampleParams& sp, cudaStream_t st) {
+  int rc;
+  if ((rc = decoder_step(ctx, buf, mode >= 1 ? buf.logits : nullptr, ctx->model->dims.n_vocab, st)) != WXB_OK) return rc;
+  if (mode == 2) {
+    if ((rc = launch_k(ctx, dec_sample_kernel, dim3(buf.B), dim3(1024), 0, st, sp)) != WXB_OK) return rc;
+  }
+  return launch_k(ctx, dec_advance_kernel, dim3(1), dim3(32), 0, st, buf.d_pos);
+}
+
+// Run one step of `mode`, through a cached CUDA graph when enabled.
+int run_step(wxb_ctx* ctx, const DecBuffers& buf, int mode, const SampleParams& sp, cudaStream_t st) {
+  if (!use_graph()) return enqueue_step(ctx, buf, mode, sp, st);
+  StepGraph& G = g_graphs[mode];
+  const bool same = G.exec && G.model == (const void*)ctx->model && G.B == buf.B && G.tok_stride == buf.tok_stride &&
+                    G.key_ptrs[0] == buf.x && G.key_ptrs[1] == buf.self_kv && G.key_ptrs[2] == buf.cross_kv &&
+                    G.key_ptrs[3] == buf.tokens && memcmp(&G.sp, &sp, sizeof(sp)) == 0;
+  if (!same) {
+    if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+    const int64_t launches_before = ctx->launches;
+    cudaGraph_t graph = nullptr;
+    WXB_CUDA(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_step(ctx, buf, mode, sp, st);
+    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    ctx->launches = launches_before;
+    if (rc != WXB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return wxb_fail(ctx, WXB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&G.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { G.exec = nullptr; return wxb_fail(ctx, WXB_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e)); }
+    G.model = ctx->model; G.B = buf.B; G.tok_stride = buf.tok_stride; G.mode = mode;
+    G.key_ptrs[0] = buf.x; G.key_ptrs[1] = buf.self_kv; G.key_ptrs[2] = buf.cross_kv; G.key_ptrs[3] = buf.tokens;
+    G.sp = sp;
+  }
+  WXB_CUDA(ctx, cudaGraphLaunch(G.exec, st));
+  const int L = ctx->model->dims.n_text_layer;
+  ctx->launches += 1 + 8 * L + (mode >= 1 ? 1 : 0) + (mode == 2 ? 1 : 0) + 1;
+  return WXB_OK;
+}
+
+}  // namespace
+
+void wxb_decoder_reset_graphs() {
+  for (auto& G : g_graphs)
+    if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+}
+
+extern "C" int wxb_decode_greedy(wxb_ctx* ctx, const void* enc_out_dev, int B, const int32_t* prompt_host, int prompt_len,
+                                 const wxb_decode_opts* opts, int32_t* tokens_out_dev, int32_t* n_tokens_dev,
+                                 float* sum_logprob_dev, float* no_speech_prob_dev, void* stream) {
+  if (!ctx) return WXB_ERR_INVALID;
+  if (!ctx->model) return wxb_fail(ctx, WXB_ERR_STATE, "wxb_decode_greedy: no model set");
+  if (!enc_out_dev || B <= 0 || !prompt_host || prompt_len <= 0 || !opts || !tokens_out_dev || !n_tokens_dev || !sum_logprob_dev)
+    return wxb_fail(ctx, WXB_ERR_INVALID, "wxb_decode_greedy: bad argument");
+  const wxb_dims& D = ctx->model->dims;
+  const int sample_len = opts->sample_len;
+  if (sample_len <= 0 || prompt_len + sample_len > D.n_text_ctx)
+    return wxb_fail(ctx, WXB_ERR_INVALID, "wxb_decode_greedy: prompt_len %d + sample_len %d exceeds n_text_ctx %d", prompt_len,
+                    sample_len, D.n_text_ctx);
+  if (opts->eot < 0 || opts->eot >= D.n_vocab) return wxb_fail(ctx, WXB_ERR_INVALID, "wxb_decode_greedy: eot out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  WXB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int stride = D.n_text_ctx + 1;
+  DecBuffers buf;
+  int rc;
+  if ((rc = alloc_buffers(ctx, B, stride, &buf)) != WXB_OK) return rc;
+  // tokens[b, :prompt_len] = prompt; state reset
+  std::vector<int> init((size_t)B * stride, opts->eot);
+  for (int b = 0; b < B; ++b)
+    for (int i = 0; i < prompt_len; ++i) init[(size_t)b * stride + i] = prompt_host[i];
+  WXB_CUDA(ctx, cudaMemcpyAsync(buf.tokens, init.data(), init.size() * 4, cudaMemcpyHostToDevice, st));
+  WXB_CUDA(ctx, cudaMemsetAsync(buf.d_pos, 0, 4, st));
+  WXB_CUDA(ctx, cudaMemsetAsync(buf.done, 0, (size_t)B * 4, st));
+  WXB_CUDA(ctx, cudaMemsetAsync(buf.sum_lp, 0, (size_t)B * 4, st));
+  WXB_CUDA(ctx, cudaStreamSynchronize(st));  // `init` is pageable host memory
+  if ((rc = cross_kv_precompute(ctx, (const __nv_bfloat16*)enc_out_dev, buf, st)) != WXB_OK) return rc;
+
+  SampleParams sp = {};
+  sp.logits = buf.logits; sp.V = D.n_vocab; sp.tokens = buf.tokens; sp.stride = stride; sp.d_pos = buf.d_pos;
+  sp.prompt_len = prompt_len; sp.eot = opts->eot; sp.suppress_blank = opts->suppress_blank; sp.blank_token = opts->blank_token;
+  sp.n_suppress = opts->n_suppress; sp.suppress = opts->suppress_dev; sp.sum_logprob = buf.sum_lp; sp.done = buf.done;
+
+  // prompt positions 0 .. prompt_len-2 (forced tokens); logits only at position 0 for no_speech_prob
+  for (int pos = 0; pos < prompt_len - 1; ++pos) {
+    const bool want_nsp = (pos == 0 && opts->no_speech >= 0 && no_speech_prob_dev);
+    if ((rc = run_step(ctx, buf, want_nsp ? 1 : 0, sp, st)) != WXB_OK) return rc;
+    if (want_nsp) {
+      dec_token_prob_kernel<<<B, 1024, 0, st>>>(buf.logits, D.n_vocab, opts->no_speech, no_speech_prob_dev);
+      WXB_LAUNCH_CHECK(ctx);
+    }
+  }
+  const bool nsp_at_last = (prompt_len == 1 && opts->no_speech >= 0 && no_speech_prob_dev);
+  const int check_every = opts->check_every > 0 ? opts->check_every : 16;
+  std::vector<int> done_host(B);
+  int n_sampled = 0;
+  for (int i = 0; i < sample_len; ++i) {
+    if (i == 0 && nsp_at_last) {
+      // single-token prompt: the SOT position is also the first sampling position
+      if ((rc = decoder_step(ctx, buf, buf.logits, D.n_vocab, st)) != WXB_OK) return rc;
+      dec_token_prob_kernel<<<B, 1024, 0, st>>>(buf.logits, D.n_vocab, opts->no_speech, no_speech_prob_dev);
+      WXB_LAUNCH_CHECK(ctx);
+      if ((rc = launch_k(ctx, dec_sample_kernel, dim3(B), dim3(1024), 0, st, sp)) != WXB_OK) return rc;
+      if ((rc = launch_k(ctx, dec_advance_kernel, dim3(1), dim3(32), 0, st, buf.d_pos)) != WXB_OK) return rc;
+    } else {
+      if ((rc = run_step(ctx, buf, 2, sp, st)) != WXB_OK) return rc;
+    }
+    n_sampled = i + 1;
+    if ((i + 1) % check_every == 0 && i + 1 < sample_len) {
+      WXB_CUDA(ctx, cudaMemcpyAsync(done_host.data(), buf.done, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+      WXB_CUDA(ctx, cudaStreamSynchronize(st));
+      bool all = true;
+      for (int b = 0; b < B; ++b) all = all && done_host[b];
+      if (all) break;  // mlx_whisper_batch_decoder.py:357
+    }
+  }
+  dec_finalize_kernel<<<B, 256, 0, st>>>(buf.tokens, stride, prompt_len, n_sampled, sample_len, opts->eot, tokens_out_dev, n_tokens_dev);
+  WXB_LAUNCH_CHECK(ctx);
+  WXB_CUDA(ctx, cudaMemcpyAsync(sum_logprob_dev, buf.sum_lp, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+  return WXB_OK;
+}
+
+extern "C" int wxb_decoder_logits(wxb_ctx* ctx, const void* enc_out_dev, int B, const int32_t* tokens_host, int n_tok,
+                                  float* logits_out_dev, void* stream) {
+  if (!ctx) return WXB_ERR_INVALID;
+  if (!ctx->model) return wxb_fail(ctx, WXB_ERR_STATE, "wxb_decoder_logits: no model set");
+  const wxb_dims& D = ctx->model->dims;
+  if (!enc_out_dev || B <= 0 || !tokens_host || n_tok <= 0 || n_tok > D.n_text_ctx || !logits_out_dev)
+    return wxb_fail(ctx, WXB_ERR_INVALID, "wxb_decoder_logits: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  WXB_CUDA(ctx, cudaSetDevice(ctx->device));
+  DecBuffers buf;
+  int rc;
+  if ((rc = alloc_buffers(ctx, B, n_tok, &buf)) != WXB_OK) return rc;
+  WXB_CUDA(ctx, cudaMemcpyAsync(buf.tokens, tokens_host, (size_t)B * n_tok * 4, cudaMemcpyHostToDevice, st));
+  WXB_CUDA(ctx, cudaMemsetAsync(buf.d_pos, 0, 4, st));
+  if ((rc = cross_kv_precompute(ctx, (const __nv_bfloat16*)enc_out_dev, buf, st)) != WXB_OK) return rc;
+  for (int pos = 0; pos < n_tok; ++pos) {
+    if ((rc = decoder_step(ctx, buf, logits_out_dev + (size_t)pos * D.n_vocab, (long long)n_tok * D.n_vocab, st)) != WXB_OK) return rc;
+    if ((rc = launch_k(ctx, dec_advance_kernel, dim3(1), dim3(32), 0, st, buf.d_pos)) != WXB_OK) return rc;
+  }
+  return WXB_OK;
 }

@@ -32,6 +32,7 @@ struct GemmParams {
   int out_f32;
   long long ldo;
   int g_in, g_valid, g_out, out_off;
+  int kv_mode, kv_B, kv_H, kv_T;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -264,6 +265,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           } else {
             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldo + n0;
+            if (p.kv_mode) {
+              const int dm = p.N >> 1;
+              const int kv = n0 / dm, rem = n0 - kv * dm;
+              const int hh = rem >> 6, j0 = rem & 63;
+              const int bb = r / p.kv_T, tt = r - bb * p.kv_T;
+              o = reinterpret_cast<__nv_bfloat16*>(p.out) +
+                  ((((long long)kv * p.kv_B + bb) * p.kv_H + hh) * p.kv_T + tt) * 64 + j0;
+            }
             if (full) {
 #pragma unroll
               for (int i = 0; i < 32; i += 8) {
@@ -361,6 +370,8 @@ int wxb_gemm_launch(wxb_ctx* ctx, const GemmArgs& a, cudaStream_t st) {
   p.bias = a.bias; p.residual = a.residual; p.res_mode = a.residual ? a.res_mode : 0; p.ldr = a.ldr;
   p.gelu = a.gelu; p.out = a.out; p.out_f32 = a.out_f32; p.ldo = a.ldo ? a.ldo : a.N;
   p.g_in = a.g_in; p.g_valid = a.g_valid; p.g_out = a.g_out; p.out_off = a.out_off;
+  p.kv_mode = a.kv_mode; p.kv_B = a.kv_B; p.kv_H = a.kv_H; p.kv_T = a.kv_T;
+  if (a.kv_mode && (a.out_f32 || (a.N % 128) != 0)) return wxb_fail(ctx, WXB_ERR_INVALID, "gemm: kv_mode needs bf16 output and N %% 128 == 0");
   CUtensorMap tmA, tmB;
   int rc;
   const long long lda = a.lda ? a.lda : a.K;

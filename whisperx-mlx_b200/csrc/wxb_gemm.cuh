@@ -24,6 +24,9 @@ struct GemmArgs {
   // row remap: GEMM row r -> group g = r / g_in, t = r % g_in; rows with t >= g_valid are dropped;
   // output row = g * g_out + t + out_off.  Defaults = identity.
   int g_in = 0, g_valid = 0, g_out = 0, out_off = 0;
+  // kv_mode (cross-attention K|V projection): N = 2*d, bf16 output scattered head-major:
+  //   out[((kv*kv_B + b)*kv_H + h)*kv_T + t][j]  with r = b*kv_T + t, n = kv*d + h*64 + j
+  int kv_mode = 0, kv_B = 0, kv_H = 0, kv_T = 0;
 };
 
 int wxb_gemm_launch(wxb_ctx* ctx, const GemmArgs& a, cudaStream_t st);
