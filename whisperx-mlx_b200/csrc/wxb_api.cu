@@ -80,6 +80,7 @@ void wxb_destroy(wxb_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   wxb_model_free(ctx);
+  if (ctx->cap_stream) cudaStreamDestroy((cudaStream_t)ctx->cap_stream);
   wxb_buf* bufs[] = {&ctx->ws_ctc_trellis, &ctx->ws_ctc_hist, &ctx->ws_ctc_meta, &ctx->ws_mel_max,
                      &ctx->ws_mel_band};
   for (wxb_buf* b : bufs)

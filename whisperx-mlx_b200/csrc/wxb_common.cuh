@@ -27,6 +27,7 @@ struct wxb_ctx {
   std::map<std::string, wxb_buf> named;  // model-side activations / caches keyed by name
   wxb_model* model = nullptr;
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled (driver entry point), lazily resolved
+  void* cap_stream = nullptr;    // private non-blocking stream used only to CAPTURE decoder step graphs
   bool lm_tables_ready = false;  // log-mel window/twiddle tables uploaded to this device
 };
 

@@ -760,9 +760,17 @@ int run_step(wxb_ctx* ctx, const DecBuffers& buf, int mode, const SampleParams& 
     if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
     const int64_t launches_before = ctx->launches;
     cudaGraph_t graph = nullptr;
-    WXB_CUDA(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    int rc = enqueue_step(ctx, buf, mode, sp, st);
-    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    // capture on a private stream (the caller's stream may be the legacy default stream, which
+    // cannot be captured); the instantiated graph is then launched on the caller's stream
+    if (!ctx->cap_stream) {
+      cudaStream_t cs;
+      WXB_CUDA(ctx, cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+      ctx->cap_stream = cs;
+    }
+    cudaStream_t cs = (cudaStream_t)ctx->cap_stream;
+    WXB_CUDA(ctx, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_step(ctx, buf, mode, sp, cs);
+    cudaError_t e = cudaStreamEndCapture(cs, &graph);
     ctx->launches = launches_before;
     if (rc != WXB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (e != cudaSuccess) return wxb_fail(ctx, WXB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));

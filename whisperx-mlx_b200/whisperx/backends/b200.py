@@ -1,0 +1,201 @@
+"""
+B200WhisperBackend — the new entry in whisperx/backends: log-mel -> encoder -> batched greedy
+KV-cache decode on hand-written sm_100a kernels (libwxb200.so), behind the reference's backend
+interface (whisperx/backends/base.py:8-57) and the duck-typed `transcribe_batch` fast path
+(whisperx/asr.py:67-87; shape per whisperx/backends/mlx_lightning.py:82-119).
+
+Segment convention: upstream-WhisperX style — `without_timestamps` prompt, one
+segment per VAD chunk: {"text", "start": round(chunk.start, 3), "end": round(chunk.end, 3)} plus
+"tokens", "avg_logprob", "no_speech_prob".  Empty text drops the segment (mlx_lightning.py:199-200).
+"""
+import os
+import warnings
+from typing import Any, Dict, List, Optional, Union
+
+import numpy as np
+import torch
+
+from ..audio import N_SAMPLES, SAMPLE_RATE, load_audio, mel_filters
+from ..tokenizer import LANGUAGE_CODES, Tokenizer
+from ..types import TranscriptionResult
+from . import b200_weights as bw
+from .base import WhisperBackend
+
+
+class B200WhisperBackend(WhisperBackend):
+    def __init__(self, model: str, device: str = "cuda", device_index: int = 0, compute_type: str = "bfloat16",
+                 download_root: Optional[str] = None, local_files_only: bool = False, threads: int = 4,
+                 asr_options: Optional[dict] = None, language: Optional[str] = None, task: str = "transcribe",
+                 weights: Optional[Union[str, Dict[str, torch.Tensor]]] = None, seed: int = 0,
+                 tokenizer: Optional[Tokenizer] = None, **kwargs):
+        from .._native import get_context
+        if str(device).startswith("cpu"):
+            raise RuntimeError("the b200 backend runs on CUDA sm_100a only; there is no CPU fallback")
+        self.model_name = bw.canonical_name(model)
+        self.dims = bw.dims_for(self.model_name)
+        self.ctx = get_context(device_index)
+        self.device = self.ctx.device
+        self.compute_type = "bfloat16"  # kernels compute in bf16 with fp32 accumulation whatever was asked
+        self.language = language
+        self.task = task or "transcribe"
+        self.options = dict(suppress_blank=True, suppress_tokens=[], sample_len=self.dims["n_text_ctx"] // 2,
+                            without_timestamps=True)
+        if asr_options:
+            for k in ("suppress_blank", "suppress_tokens", "sample_len", "without_timestamps"):
+                if k in asr_options and asr_options[k] is not None:
+                    self.options[k] = asr_options[k]
+        if self.options["suppress_tokens"] == [-1]:
+            self.options["suppress_tokens"] = []  # "-1" = tokenizer's non-speech set: needs a real vocabulary
+        self.specials = bw.special_tokens(self.dims)
+        self.tokenizer = tokenizer or Tokenizer(self.specials, self.dims["n_vocab"])
+        self.kernel_weights = self._load_weights(weights, seed)
+        self.ctx.set_model(self.dims, self.kernel_weights)
+        self._filters = mel_filters(self.device, self.dims["n_mels"])
+        self.align_model = kwargs.get("align_model")  # optional (model, metadata) for _align_words
+        self.last_stats: Dict[str, Any] = {}
+
+    # ------------------------------------------------------------------ weights
+    def _load_weights(self, weights, seed):
+        if weights is None:
+            warnings.warn(f"no checkpoint given for '{self.model_name}': using seeded random-init weights "
+                          "(pass weights=<state dict or path> for a trained model)")
+            return bw.random_kernel_weights_on_device(self.dims, self.device, seed=seed)
+        if isinstance(weights, str):
+            sd = torch.load(weights, map_location="cpu")
+            weights = sd.get("model_state_dict", sd)
+        if any(k.startswith("model.encoder.") for k in weights):
+            weights = bw.from_hf_state_dict(weights)
+        if "enc.conv1.w" in weights:  # already in kernel layout
+            return {k: v.to(self.device).contiguous() for k, v in weights.items()}
+        return bw.to_kernel_layout(weights, self.dims, self.device)
+
+    # ------------------------------------------------------------------ interface properties
+    @property
+    def supported_languages(self) -> List[str]:
+        return list(LANGUAGE_CODES[: self.tokenizer.num_languages]) if self.is_multilingual else ["en"]
+
+    @property
+    def is_multilingual(self) -> bool:
+        return self.dims["n_vocab"] >= 51865
+
+    # ------------------------------------------------------------------ device-resident hot path
+    def upload_chunks(self, chunks: List[np.ndarray]):
+        """Pinned staging + one H2D copy.  Returns (audio_dev, offsets, lengths)."""
+        lens = np.array([min(len(c), N_SAMPLES) for c in chunks], dtype=np.int32)
+        offs = np.zeros(len(chunks), dtype=np.int64)
+        if len(chunks) > 1:
+            offs[1:] = np.cumsum(lens[:-1])
+        total = int(lens.sum())
+        host = torch.empty(max(total, 1), dtype=torch.float32).pin_memory()
+        hv = host.numpy()
+        for c, o, l in zip(chunks, offs, lens):
+            hv[o:o + l] = np.asarray(c[:l], dtype=np.float32)
+        return host.to(self.device, non_blocking=True), offs, lens
+
+    def transcribe_device(self, audio_dev: torch.Tensor, offs: np.ndarray, lens: np.ndarray, batch_size: int,
+                          language: str, task: str):
+        """mel -> encode -> greedy decode for chunks already resident in HBM.  Returns device tensors
+        (tokens [n, sample_len], n_tokens, sum_logprob, no_speech_prob)."""
+        prompt = self.tokenizer.prompt(language, task, self.options["without_timestamps"])
+        n = len(offs)
+        out = {"tokens": [], "n_tokens": [], "sum_logprob": [], "no_speech_prob": []}
+        for i in range(0, n, batch_size):
+            j = min(n, i + batch_size)
+            mel = self.ctx.logmel(audio_dev, offs[i:j], lens[i:j], N_SAMPLES, self.dims["n_mels"], self._filters)
+            enc = self.ctx.encode(mel)
+            r = self.ctx.decode_greedy(enc, prompt, self.specials["eot"], no_speech=self.specials["no_speech"],
+                                       sample_len=int(self.options["sample_len"]),
+                                       suppress_blank=bool(self.options["suppress_blank"]),
+                                       blank_token=self.specials["blank"],
+                                       suppress_tokens=tuple(self.options["suppress_tokens"]))
+            for k in out:
+                out[k].append(r[k])
+        return {k: torch.cat(v, 0) for k, v in out.items()}
+
+    # ------------------------------------------------------------------ public API
+    def transcribe_batch(self, segments: List[Dict[str, Any]], batch_size: int = 8, align_words: bool = False,
+                         print_progress: bool = False, combined_progress: bool = False, verbose: bool = False,
+                         language: Optional[str] = None, task: Optional[str] = None, **kwargs) -> Dict[str, Any]:
+        segs = [s for s in segments if s.get("audio") is not None and len(s["audio"]) > 0]
+        language = language or self.language
+        if language is None:
+            language = self.detect_language(segs[0]["audio"]) if segs else "en"
+        task = task or self.task
+        result_segments: List[Dict[str, Any]] = []
+        if segs:
+            audio_dev, offs, lens = self.upload_chunks([s["audio"] for s in segs])
+            r = self.transcribe_device(audio_dev, offs, lens, max(1, int(batch_size or 8)), language, task)
+            tokens = r["tokens"].cpu().numpy()          # D2H of the step's result
+            n_tok = r["n_tokens"].cpu().numpy()
+            sum_lp = r["sum_logprob"].cpu().numpy()
+            nsp = r["no_speech_prob"].cpu().numpy()
+            for k, seg in enumerate(segs):
+                ids = tokens[k, : n_tok[k]].tolist()
+                text = self.tokenizer.decode(ids).strip()
+                if print_progress:
+                    base = ((k + 1) / len(segs)) * 100
+                    print(f"Progress: {(base / 2) if combined_progress else base:.2f}%...")
+                if not text:
+                    continue
+                item = {"text": text, "start": round(float(seg["start"]), 3), "end": round(float(seg["end"]), 3),
+                        "tokens": ids, "avg_logprob": float(sum_lp[k]) / (len(ids) + 1), "no_speech_prob": float(nsp[k])}
+                if verbose:
+                    print(f"[{item['start']:.3f} --> {item['end']:.3f}] {text}")
+                result_segments.append(item)
+        result = {"segments": result_segments, "language": language or "en"}
+        if align_words and result_segments:
+            result = self._align_words(result, segments)
+        return result
+
+    def transcribe(self, audio: Union[str, np.ndarray], batch_size: Optional[int] = None, num_workers: int = 0,
+                   language: Optional[str] = None, task: Optional[str] = None, chunk_size: int = 30,
+                   print_progress: bool = False, combined_progress: bool = False, verbose: bool = False,
+                   align_words: bool = False, **kwargs) -> TranscriptionResult:
+        """Whole-audio entry point: cut into back-to-back <= chunk_size windows (the Lightning seek
+        loop, mlx_lightning.py:174-216, without the per-window Python overhead) and batch them."""
+        if isinstance(audio, str):
+            audio = load_audio(audio)
+        audio = np.asarray(audio, dtype=np.float32)
+        win = int(min(chunk_size, 30) * SAMPLE_RATE)
+        segments = []
+        for s in range(0, max(len(audio), 1), win):
+            e = min(len(audio), s + win)
+            if e > s:
+                segments.append({"start": s / SAMPLE_RATE, "end": e / SAMPLE_RATE, "audio": audio[s:e]})
+        return self.transcribe_batch(segments, batch_size=batch_size or 8, align_words=align_words,
+                                     print_progress=print_progress, combined_progress=combined_progress, verbose=verbose,
+                                     language=language, task=task)
+
+    def detect_language(self, audio: np.ndarray) -> str:
+        """Language-id step: one decoder position on [sot]; argmax over the language tokens."""
+        if not self.is_multilingual:
+            return "en"
+        audio = np.asarray(audio, dtype=np.float32)[:N_SAMPLES]
+        audio_dev, offs, lens = self.upload_chunks([audio])
+        mel = self.ctx.logmel(audio_dev, offs, lens, N_SAMPLES, self.dims["n_mels"], self._filters)
+        enc = self.ctx.encode(mel)
+        logits = self.ctx.decoder_logits(enc, np.array([[self.specials["sot"]]], dtype=np.int32))[0, 0]
+        lo = self.specials["sot"] + 1
+        lang_tok = int(torch.argmax(logits[lo: lo + self.tokenizer.num_languages]).item()) + lo
+        return self.tokenizer.language_of(lang_tok)
+
+    # presence of this attribute makes the pipeline translate word_timestamps=True into
+    # align_words=True (asr.py:50-52,76-78)
+    def _align_words(self, result: Dict[str, Any], segments: List[Dict[str, Any]]) -> Dict[str, Any]:
+        from ..alignment import align
+        if self.align_model is None:
+            raise RuntimeError("word alignment needs an alignment model: pass align_model=(model, metadata) to load_model "
+                               "(whisperx.load_align_model needs network access for the default checkpoints)")
+        model, meta = self.align_model
+        segs = [s for s in segments if s.get("audio") is not None]
+        if not segs:
+            return result
+        # stitch the chunk audio back onto one timeline for align()
+        end = max(int(round(s["end"] * SAMPLE_RATE)) for s in segs)
+        audio = np.zeros(end, dtype=np.float32)
+        for s in segs:
+            a = int(s["start"] * SAMPLE_RATE)
+            audio[a:a + len(s["audio"])] = s["audio"][: max(0, end - a)]
+        aligned = align(result["segments"], model, meta, audio, str(self.device))
+        aligned["language"] = result["language"]
+        return aligned
