@@ -152,6 +152,11 @@ int wxb_decode_greedy(wxb_ctx* ctx, const void* enc_out_dev, int B, const int32_
                       int32_t* n_tokens_dev, float* sum_logprob_dev, float* no_speech_prob_dev,
                       void* stream);
 
+/* Device-side timing of the wxb_decode_greedy calls made since the last reset (CUDA events recorded
+ * on the caller's stream; this call synchronises on them): total milliseconds spent in the cross-KV
+ * projection GEMMs, in the per-token step loop, and the number of decoder steps run. */
+int wxb_decode_stats(wxb_ctx* ctx, double* cross_kv_ms, double* steps_ms, int64_t* n_steps, int reset);
+
 /* Teacher-forced logits for parity tests: runs the decoder over tokens_host int32 [B, n_tok]
  * and writes the f32 logits of every position to logits_out_dev [B, n_tok, n_vocab]. */
 int wxb_decoder_logits(wxb_ctx* ctx, const void* enc_out_dev, int B, const int32_t* tokens_host,

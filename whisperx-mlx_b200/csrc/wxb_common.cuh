@@ -17,6 +17,11 @@ struct wxb_buf {
 struct wxb_model;    // defined in wxb_model.cuh
 struct wxb_dec_state;
 
+struct wxb_dec_timing {
+  cudaEvent_t e0, e1, e2;
+  int steps;
+};
+
 struct wxb_ctx {
   int device = 0;
   int sm_count = 148;
@@ -27,6 +32,7 @@ struct wxb_ctx {
   std::map<std::string, wxb_buf> named;  // model-side activations / caches keyed by name
   wxb_model* model = nullptr;
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled (driver entry point), lazily resolved
+  std::vector<wxb_dec_timing> dec_timings;  // one entry per wxb_decode_greedy call since the last reset
   void* cap_stream = nullptr;    // private non-blocking stream used only to CAPTURE decoder step graphs
   bool lm_tables_ready = false;  // log-mel window/twiddle tables uploaded to this device
 };

@@ -822,7 +822,13 @@ extern "C" int wxb_decode_greedy(wxb_ctx* ctx, const void* enc_out_dev, int B, c
   WXB_CUDA(ctx, cudaMemsetAsync(buf.done, 0, (size_t)B * 4, st));
   WXB_CUDA(ctx, cudaMemsetAsync(buf.sum_lp, 0, (size_t)B * 4, st));
   WXB_CUDA(ctx, cudaStreamSynchronize(st));  // `init` is pageable host memory
+  wxb_dec_timing tm;
+  WXB_CUDA(ctx, cudaEventCreate(&tm.e0));
+  WXB_CUDA(ctx, cudaEventCreate(&tm.e1));
+  WXB_CUDA(ctx, cudaEventCreate(&tm.e2));
+  WXB_CUDA(ctx, cudaEventRecord(tm.e0, st));
   if ((rc = cross_kv_precompute(ctx, (const __nv_bfloat16*)enc_out_dev, buf, st)) != WXB_OK) return rc;
+  WXB_CUDA(ctx, cudaEventRecord(tm.e1, st));
 
   SampleParams sp = {};
   sp.logits = buf.logits; sp.V = D.n_vocab; sp.tokens = buf.tokens; sp.stride = stride; sp.d_pos = buf.d_pos;
@@ -862,9 +868,33 @@ extern "C" int wxb_decode_greedy(wxb_ctx* ctx, const void* enc_out_dev, int B, c
       if (all) break;  // mlx_whisper_batch_decoder.py:357
     }
   }
+  WXB_CUDA(ctx, cudaEventRecord(tm.e2, st));
+  tm.steps = prompt_len - 1 + n_sampled;
+  ctx->dec_timings.push_back(tm);
   dec_finalize_kernel<<<B, 256, 0, st>>>(buf.tokens, stride, prompt_len, n_sampled, sample_len, opts->eot, tokens_out_dev, n_tokens_dev);
   WXB_LAUNCH_CHECK(ctx);
   WXB_CUDA(ctx, cudaMemcpyAsync(sum_logprob_dev, buf.sum_lp, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+  return WXB_OK;
+}
+
+extern "C" int wxb_decode_stats(wxb_ctx* ctx, double* cross_kv_ms, double* steps_ms, int64_t* n_steps, int reset) {
+  if (!ctx) return WXB_ERR_INVALID;
+  double a = 0, b = 0;
+  int64_t n = 0;
+  for (auto& t : ctx->dec_timings) {
+    WXB_CUDA(ctx, cudaEventSynchronize(t.e2));
+    float x = 0.f, y = 0.f;
+    WXB_CUDA(ctx, cudaEventElapsedTime(&x, t.e0, t.e1));
+    WXB_CUDA(ctx, cudaEventElapsedTime(&y, t.e1, t.e2));
+    a += x; b += y; n += t.steps;
+  }
+  if (cross_kv_ms) *cross_kv_ms = a;
+  if (steps_ms) *steps_ms = b;
+  if (n_steps) *n_steps = n;
+  if (reset) {
+    for (auto& t : ctx->dec_timings) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); cudaEventDestroy(t.e2); }
+    ctx->dec_timings.clear();
+  }
   return WXB_OK;
 }
 

@@ -71,6 +71,8 @@ def load_library(path: Optional[str] = None):
         lib.wxb_encode.argtypes = [vp, vp, i32, vp, vp]
         lib.wxb_decode_greedy.restype = i32
         lib.wxb_decode_greedy.argtypes = [vp, vp, i32, vp, i32, C.POINTER(DecodeOpts), vp, vp, vp, vp, vp]
+        lib.wxb_decode_stats.restype = i32
+        lib.wxb_decode_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64), i32]
         lib.wxb_decoder_logits.restype = i32
         lib.wxb_decoder_logits.argtypes = [vp, vp, i32, vp, i32, vp, vp]
         lib.wxb_gemm_bf16.restype = i32
@@ -85,7 +87,7 @@ def load_library(path: Optional[str] = None):
 EXPORTED_SYMBOLS = (
     "wxb_abi_version", "wxb_create", "wxb_destroy", "wxb_last_error", "wxb_launch_count", "wxb_logmel",
     "wxb_ctc_align", "wxb_log_softmax_rows", "wxb_set_model", "wxb_encode", "wxb_decode_greedy",
-    "wxb_decoder_logits", "wxb_gemm_bf16")
+    "wxb_decoder_logits", "wxb_gemm_bf16", "wxb_decode_stats")
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -231,6 +233,12 @@ class Context:
                                                C.byref(opts), _ptr(tokens), _ptr(n_tok), _ptr(sum_lp), _ptr(nsp),
                                                self._stream()))
         return dict(tokens=tokens, n_tokens=n_tok, sum_logprob=sum_lp, no_speech_prob=nsp)
+
+    def decode_stats(self, reset: bool = True):
+        """(cross_kv_ms, steps_ms, n_steps) summed over the decode_greedy calls since the last reset."""
+        a, b, n = C.c_double(), C.c_double(), C.c_int64()
+        self._check(self.lib.wxb_decode_stats(self.h, C.byref(a), C.byref(b), C.byref(n), int(reset)))
+        return a.value, b.value, n.value
 
     def decoder_logits(self, enc_out: torch.Tensor, tokens: np.ndarray) -> torch.Tensor:
         dims = self._keep["dims"]

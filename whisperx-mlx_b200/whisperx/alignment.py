@@ -429,3 +429,29 @@ def _assemble(text, prep, char_segments, ratio, t1, spaced, interpolate_method, 
         agg["chars"] = "sum"
     df = df.groupby(["start", "end"], as_index=False).agg(agg)
     return df.to_dict("records")
+
+
+def align_from_emissions(emission_logits: List[np.ndarray], token_lists: List[List[int]], blank_id: int = 0,
+                         device_index: int = 0, beam: bool = True):
+    """Numeric core of align() for callers that already hold the CTC model's output (host arrays):
+    pinned H2D copy -> log_softmax (alignment.py:258) -> K4 trellis + beam-2 / backtrack for all
+    segments in one launch -> D2H.  Returns per segment (status, token_index[T], prob[T])."""
+    from ._native import CTC_BACKTRACK, CTC_BEAM2, get_context
+    ctx = get_context(device_index)
+    T = [int(e.shape[0]) for e in emission_logits]
+    V = int(emission_logits[0].shape[1])
+    host = torch.empty((sum(T), V), dtype=torch.float32).pin_memory()
+    off = 0
+    for e in emission_logits:
+        host[off:off + e.shape[0]] = torch.from_numpy(np.ascontiguousarray(e, dtype=np.float32))
+        off += e.shape[0]
+    emis = host.to(ctx.device, non_blocking=True)
+    ctx.log_softmax_rows_(emis)
+    t_off = np.concatenate([[0], np.cumsum(T)]).astype(np.int32)
+    n_off = np.concatenate([[0], np.cumsum([len(t) for t in token_lists])]).astype(np.int32)
+    tok = torch.from_numpy(np.concatenate([np.asarray(t, dtype=np.int32) for t in token_lists])).pin_memory()
+    res = ctx.ctc_align(emis, t_off, tok.to(ctx.device, non_blocking=True), n_off, blank_id, CTC_BEAM2 if beam else CTC_BACKTRACK)
+    status = res["status"].cpu().numpy()
+    ptok = res["path_tok"].cpu().numpy()
+    prob = torch.exp(res["path_lp"].cpu()).numpy()
+    return [(int(status[k]), ptok[t_off[k]:t_off[k + 1]], prob[t_off[k]:t_off[k + 1]]) for k in range(len(T))]
