@@ -160,6 +160,7 @@ def main():
     ap.add_argument("--minutes", type=float, default=30.0)
     ap.add_argument("--batch-size", type=int, default=16)
     ap.add_argument("--cpu-chunks", type=int, default=1)
+    ap.add_argument("--sample-len", type=int, default=0, help="override the number of sampled positions (profiling only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -199,6 +200,8 @@ def main():
     n_off = np.concatenate([[0], np.cumsum([len(t) for t in toks])]).astype(np.int32)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     prompt = be.tokenizer.prompt("en", "transcribe", True)
+    if args.sample_len > 0:
+        be.options["sample_len"] = args.sample_len
     sample_len = int(be.options["sample_len"])
 
     stage_ev = {k: [] for k in ("mel", "encoder", "decode", "ctc")}
