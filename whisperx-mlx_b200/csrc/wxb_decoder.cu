@@ -269,23 +269,51 @@ struct AttnParams {
   int* ticket;                  // [B*H], zero-initialised, self-cleaning
 };
 
+// Single pass over the keys with an online softmax per 8-lane key slot: every lane owns 8 of the 64
+// dims of its slot's keys; K and V rows of 4 keys per slot are requested together and one iteration
+// ahead (<= 16 x 16 B in flight per lane); the 32 slot states of the CTA are merged through shared
+// memory at the end.  static_kv (cross-attention): K/V do not depend on the previous kernel, so the
+// first loads are issued before the programmatic-dependent-launch wait.
+__device__ __forceinline__ void da_load(uint4* kv, uint4* vv, const __nv_bfloat16* Kb, const __nv_bfloat16* Vb, int kb, int slot,
+                                        int c8, int k1) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int key = kb + u * 32 + slot;
+    if (key < k1) {
+      kv[u] = ldg_nc_v4(Kb + (size_t)key * 64 + c8 * 8);
+      vv[u] = ldg_nc_v4(Vb + (size_t)key * 64 + c8 * 8);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(DA_THREADS)
 dec_attn_kernel(const AttnParams p) {
   extern __shared__ __align__(16) float da_smem[];
-  float* sc = da_smem;                       // [per] scores
-  float* sq = sc + ((p.tkv + p.splits - 1) / p.splits + 32);  // [64] q
-  float* sred = sq + 64;                     // [8*64 + 16]
+  float* sq = da_smem;            // [64] scaled q
+  float* sst = sq + 64;           // [32 slots][66]: m, l, acc[64]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int slot = lane >> 3, c8 = lane & 7;  // 4 keys per warp iteration, 8 lanes x 8 dims per key
+  const int slot = lane >> 3, c8 = lane & 7;
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  pdl_wait();
-  const int n_keys = p.d_pos ? (*p.d_pos + 1) : p.n_keys;
-  const int per = (n_keys + p.splits - 1) / p.splits;
-  const int k0 = split * per;
-  const int k1 = min(n_keys, k0 + per);
   const size_t slab = ((size_t)b * p.H + h) * p.tkv * 64;
   const __nv_bfloat16* Kb = p.K + slab;
   const __nv_bfloat16* Vb = p.V + slab;
+  uint4 kA[4], vA[4], kB[4], vB[4];
+  int n_keys = p.n_keys, per = 0, k0 = 0, k1 = 0;
+  const bool static_kv = (p.d_pos == nullptr);
+  if (static_kv) {
+    per = (n_keys + p.splits - 1) / p.splits;
+    k0 = split * per;
+    k1 = min(n_keys, k0 + per);
+    da_load(kA, vA, Kb, Vb, k0 + warp * 4, slot, c8, k1);
+  }
+  pdl_wait();
+  if (!static_kv) {
+    n_keys = *p.d_pos + 1;
+    per = (n_keys + p.splits - 1) / p.splits;
+    k0 = split * per;
+    k1 = min(n_keys, k0 + per);
+    da_load(kA, vA, Kb, Vb, k0 + warp * 4, slot, c8, k1);
+  }
   if (tid < 64) sq[tid] = p.q[(size_t)b * p.d + h * 64 + tid] * p.scale;
   __syncthreads();
   pdl_launch();
@@ -293,62 +321,43 @@ dec_attn_kernel(const AttnParams p) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) qr[j] = sq[c8 * 8 + j];
 
-  // ---- scores ----
-  float lmax = -INFINITY;
-  for (int kb = k0 + warp * 4; kb < k1; kb += 32 * 4) {
-    uint4 kv[4];
+  float m = -INFINITY, l = 0.f, acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+
+  auto consume = [&](const uint4* kv, const uint4* vv, int kb) {
+    float sc4[4];
+    float mx = -INFINITY;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int key = kb + u * 32 + slot;
-      if (key < k1) kv[u] = ldg_nc_v4(Kb + (size_t)key * 64 + c8 * 8);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int key = kb + u * 32 + slot;
-      float s = 0.f;
+      float sdot = 0.f;
       if (key < k1) {
         const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&kv[u]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 f = __bfloat1622float2(h2[j]);
-          s = fmaf(qr[2 * j], f.x, s);
-          s = fmaf(qr[2 * j + 1], f.y, s);
+          sdot = fmaf(qr[2 * j], f.x, sdot);
+          sdot = fmaf(qr[2 * j + 1], f.y, sdot);
         }
       }
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      s += __shfl_xor_sync(0xffffffffu, s, 4);
-      if (key < k1) {
-        if (c8 == 0) sc[key - k0] = s;
-        lmax = fmaxf(lmax, s);
-      }
+      sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+      sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+      sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
+      sc4[u] = (key < k1) ? sdot : -INFINITY;
+      mx = fmaxf(mx, sc4[u]);
     }
-  }
-  lmax = warp_max(lmax);
-  if (lane == 0) sred[warp] = lmax;
-  __syncthreads();
-  float m = sred[0];
+    if (mx > -INFINITY) {  // uniform within the 8-lane slot
+      const float mn = fmaxf(m, mx);
+      const float alpha = __expf(m - mn);  // m = -inf -> 0
+      m = mn;
+      l *= alpha;
 #pragma unroll
-  for (int w = 1; w < 8; ++w) m = fmaxf(m, sred[w]);
-  __syncthreads();
-  // ---- softmax numerators + P.V ----
-  float acc[8];
+      for (int j = 0; j < 8; ++j) acc[j] *= alpha;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  float lsum = 0.f;
-  for (int kb = k0 + warp * 4; kb < k1; kb += 32 * 4) {
-    uint4 vv[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int key = kb + u * 32 + slot;
-      if (key < k1) vv[u] = ldg_nc_v4(Vb + (size_t)key * 64 + c8 * 8);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int key = kb + u * 32 + slot;
-      if (key < k1) {
-        const float pr = __expf(sc[key - k0] - m);
-        if (c8 == 0) lsum += pr;
+      for (int u = 0; u < 4; ++u) {
+        const float pr = __expf(sc4[u] - mn);  // -inf -> 0
+        l += pr;
         const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&vv[u]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -358,33 +367,52 @@ dec_attn_kernel(const AttnParams p) {
         }
       }
     }
-  }
+  };
+  // masked-out V registers may hold garbage (never loaded): zero them so 0 * garbage cannot make NaN
+  auto clear = [&](uint4* vv, int kb) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
-    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+    for (int u = 0; u < 4; ++u)
+      if (kb + u * 32 + slot >= k1) vv[u] = make_uint4(0u, 0u, 0u, 0u);
+  };
+  for (int kb = k0 + warp * 4; kb < k1; kb += 2 * 128) {
+    if (kb + 128 < k1) da_load(kB, vB, Kb, Vb, kb + 128, slot, c8, k1);
+    clear(vA, kb);
+    consume(kA, vA, kb);
+    if (kb + 256 < k1) da_load(kA, vA, Kb, Vb, kb + 256, slot, c8, k1);
+    if (kb + 128 < k1) {
+      clear(vB, kb + 128);
+      consume(kB, vB, kb + 128);
+    }
   }
-  lsum = warp_sum(lsum);
-  if (slot == 0) {
+  // ---- merge the 32 slot states ----
+  {
+    float* st = sst + (warp * 4 + slot) * 66;
+    if (c8 == 0) { st[0] = m; st[1] = l; }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) sred[16 + warp * 64 + c8 * 8 + j] = acc[j];
+    for (int j = 0; j < 8; ++j) st[2 + c8 * 8 + j] = acc[j];
   }
-  if (lane == 0) sred[8 + warp] = lsum;
   __syncthreads();
-  float o = 0.f, l = 0.f;
+  float o = 0.f, L = 0.f, M = -INFINITY;
   if (tid < 64) {
-#pragma unroll
-    for (int w = 0; w < 8; ++w) { o += sred[16 + w * 64 + tid]; l += sred[8 + w]; }
+#pragma unroll 4
+    for (int i = 0; i < 32; ++i) M = fmaxf(M, sst[i * 66]);
+    if (M > -INFINITY) {
+      for (int i = 0; i < 32; ++i) {
+        const float w = __expf(sst[i * 66] - M);
+        L += w * sst[i * 66 + 1];
+        o += w * sst[i * 66 + 2 + tid];
+      }
+    }
   }
   if (p.splits == 1) {
-    if (tid < 64) p.out[(size_t)b * p.d + h * 64 + tid] = o / l;
+    if (tid < 64) p.out[(size_t)b * p.d + h * 64 + tid] = o / L;
     return;
   }
   // ---- split-KV: publish the partial, the last CTA of this (b,h) merges ----
   float* part = p.part + (((size_t)b * p.H + h) * p.splits) * 66;
   if (tid < 64) {
     part[split * 66 + 2 + tid] = o;
-    if (tid == 0) { part[split * 66] = m; part[split * 66 + 1] = l; }
+    if (tid == 0) { part[split * 66] = M; part[split * 66 + 1] = L; }
   }
   __threadfence();
   __syncthreads();
@@ -398,15 +426,15 @@ dec_attn_kernel(const AttnParams p) {
   if (!s_last) return;
   __threadfence();
   if (tid < 64) {
-    float M = -INFINITY;
-    for (int s = 0; s < p.splits; ++s) M = fmaxf(M, __ldcg(part + s * 66));
-    float L = 0.f, O = 0.f;
-    for (int s = 0; s < p.splits; ++s) {
-      const float w = __expf(__ldcg(part + s * 66) - M);
-      L += w * __ldcg(part + s * 66 + 1);
-      O += w * __ldcg(part + s * 66 + 2 + tid);
+    float MM = -INFINITY;
+    for (int s2 = 0; s2 < p.splits; ++s2) MM = fmaxf(MM, __ldcg(part + s2 * 66));
+    float LL = 0.f, OO = 0.f;
+    for (int s2 = 0; s2 < p.splits; ++s2) {
+      const float w = __expf(__ldcg(part + s2 * 66) - MM);
+      LL += w * __ldcg(part + s2 * 66 + 1);
+      OO += w * __ldcg(part + s2 * 66 + 2 + tid);
     }
-    p.out[(size_t)b * p.d + h * 64 + tid] = O / L;
+    p.out[(size_t)b * p.d + h * 64 + tid] = OO / LL;
   }
 }
 
@@ -596,7 +624,7 @@ int launch_gemv(wxb_ctx* ctx, GemvParams p, cudaStream_t st) {
 }
 
 int launch_attn(wxb_ctx* ctx, AttnParams p, int B, cudaStream_t st) {
-  const size_t smem = (size_t)((p.tkv + p.splits - 1) / p.splits + 32 + 64 + 8 * 64 + 16) * 4;
+  const size_t smem = (size_t)(64 + 32 * 66) * 4;
   return launch_k(ctx, dec_attn_kernel, dim3(p.splits, p.H, B), dim3(DA_THREADS), smem, st, p);
 }
 
