@@ -56,15 +56,20 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-enum { IN_LN = 0, IN_F32 = 1, IN_BF16 = 2 };
+enum { IN_LN = 0, IN_BF16 = 2 };
 enum { EPI_F32 = 0, EPI_RESID = 1, EPI_GELU_BF16 = 2, EPI_QKV = 3 };
 
+constexpr int GV_ROWS = 64;  // weight rows per CTA (8 warps x 8 rows)
+
 struct GemvParams {
-  int B, N, K, kw;  // kw = warps that split K for one 8-row group (8 % kw == 0)
+  int B, N, K;
+  int ks;         // split-K factor across CTAs (gridDim.y); K / ks is a multiple of 64
   int in_mode;
-  const void* in;
+  const void* in;  // IN_LN: residual stream f32 [B, K];  IN_BF16: bf16 [B, K]
   long long ld_in;
   const float *ln_w, *ln_b;
+  const float* stats_in;  // IN_LN: [n_stat_blocks][B][2] partial (sum, sum of squares) of each row of `in`
+  int n_stat_blocks;
   const __nv_bfloat16* W;
   const float* bias;
   int epi;
@@ -75,9 +80,14 @@ struct GemvParams {
   __nv_bfloat16 *kcache, *vcache;  // [B][H][tmax][64] of this layer
   const int* d_pos;
   int H, tmax;
+  // split-K partials [ks][Bp][Npad] and per-row-block tickets (zero-initialised, self-cleaning)
+  float* part;
+  int* ticket;
+  // EPI_RESID: per-row-block (sum, sum of squares) of the updated residual rows, [N/64][B][2]
+  float* stats_out;
 };
 
-// Weight chunk c of this lane: two 16-byte loads at k = 64c + 8t and 64c + 32 + 8t of row (n0 + g).
+// Weight chunk c (64 K-columns) of this lane: two 16-byte loads at k = 64c + 8t and 64c + 32 + 8t of row (n0 + g).
 __device__ __forceinline__ void gv_load(uint4* w, const __nv_bfloat16* wrow, int c_first, int c_end) {
 #pragma unroll
   for (int u = 0; u < GV_U; ++u) {
@@ -107,145 +117,195 @@ __device__ __forceinline__ void gv_compute(float* acc, const uint4* w, const uns
   }
 }
 
+// Skinny GEMM y[B, N] = act[B, K] W[N, K]^T for B <= 64.  CTA = 64 weight rows x one K-slice; warp w owns
+// rows 8w..8w+7 and keeps its weight fragments in registers while looping over the (<= 4) 16-row batch
+// tiles, whose activations sit in shared memory.  gridDim.y K-slices are combined deterministically: every
+// slice publishes fp32 partials and the last-arriving CTA of a row block sums them in slice order and runs
+// the epilogue (bias / GELU / residual + LayerNorm statistics / QKV scatter into the KV cache).
 __global__ void __launch_bounds__(GV_THREADS)
 dec_gemv_kernel(const GemvParams p) {
   extern __shared__ __align__(16) unsigned char gv_smem[];
+  __shared__ float s_mean[64], s_rstd[64];
+  __shared__ int s_last;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int kw = p.kw, rg_per_cta = 8 / kw;
-  const int rg = warp / kw, ks = warp - rg * kw;
-  const int n0 = (blockIdx.x * rg_per_cta + rg) * 8;
-  const int b0 = blockIdx.y * 16;
-  const int chunks = p.K / 64 / kw;
-  const int c_begin = ks * chunks, c_end = c_begin + chunks;
-  const size_t row_bytes = (size_t)(p.K + 32) * 2;  // +64 B: rows g and g+1 land on different bank halves
-  float* red = reinterpret_cast<float*>(gv_smem + 16 * row_bytes);
+  const int Bp = (p.B + 15) & ~15;
+  const int MT = Bp >> 4;
+  const int kslice = p.K / p.ks;
+  const int k_begin = blockIdx.y * kslice;
+  const int chunks = kslice >> 6;
+  const int nblk0 = blockIdx.x * GV_ROWS;
+  const int n0 = nblk0 + warp * 8;
+  const size_t row_bytes = (size_t)(kslice + 32) * 2;  // +64 B: rows g and g+1 land on different bank halves
+  float* s_ln = reinterpret_cast<float*>(gv_smem + (size_t)Bp * row_bytes);  // [2][kslice] LN weight / bias slice
 
-  const bool warp_active = n0 < p.N;
   int nrow = n0 + g;
   if (nrow >= p.N) nrow = p.N - 1;
-  const __nv_bfloat16* wrow = p.W + (size_t)nrow * p.K + 8 * t;
+  const __nv_bfloat16* wrow = p.W + (size_t)nrow * p.K + k_begin + 8 * t;
   uint4 wa[2 * GV_U], wb[2 * GV_U];
-  if (warp_active) gv_load(wa, wrow, c_begin, c_end);  // independent of the previous kernel: issue before the PDL wait
+  // everything up to the wait is independent of the previous kernel: weights + LayerNorm parameters
+  gv_load(wa, wrow, 0, chunks);
+  if (p.in_mode == IN_LN) {
+    for (int i = tid; i < kslice; i += GV_THREADS) {
+      s_ln[i] = __ldg(p.ln_w + k_begin + i);
+      s_ln[kslice + i] = __ldg(p.ln_b + k_begin + i);
+    }
+  }
   pdl_wait();
 
-  // ---- stage the activation tile (16 batch rows x K) as bf16 ----
+  // ---- stage the activation tile (Bp batch rows x K-slice) as bf16 ----
   if (p.in_mode == IN_LN) {
-    const float* x = reinterpret_cast<const float*>(p.in);
-    for (int r = warp; r < 16; r += 8) {
-      const int b = b0 + r;
-      unsigned char* dst = gv_smem + r * row_bytes;
-      const int nv = p.K >> 2;
-      if (b < p.B) {
-        const float4* xr = reinterpret_cast<const float4*>(x + (size_t)b * p.ld_in);
-        float4 v[10];
-        float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < 10; ++i) {
-          const int idx = lane + 32 * i;
-          if (idx < nv) { v[i] = xr[idx]; s += v[i].x + v[i].y + v[i].z + v[i].w; }
+    if (tid < Bp) {
+      float mean = 0.f, rstd = 0.f;
+      if (tid < p.B) {
+        float S = 0.f, Q = 0.f;
+        for (int i = 0; i < p.n_stat_blocks; ++i) {
+          const float2 st = *reinterpret_cast<const float2*>(p.stats_in + ((size_t)i * p.B + tid) * 2);
+          S += st.x;
+          Q += st.y;
         }
-        const float mean = warp_sum(s) / p.K;
-        float q = 0.f;
-#pragma unroll
-        for (int i = 0; i < 10; ++i) {
-          const int idx = lane + 32 * i;
-          if (idx < nv) {
-            const float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
-            q += a * a + bb * bb + c * c + e * e;
-          }
-        }
-        const float rstd = rsqrtf(warp_sum(q) / p.K + 1e-5f);
-#pragma unroll
-        for (int i = 0; i < 10; ++i) {
-          const int idx = lane + 32 * i;
-          if (idx < nv) {
-            const float4 ww = __ldg(reinterpret_cast<const float4*>(p.ln_w) + idx);
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.ln_b) + idx);
-            uint2 pk;
-            pk.x = pack_bf16((v[i].x - mean) * rstd * ww.x + bb.x, (v[i].y - mean) * rstd * ww.y + bb.y);
-            pk.y = pack_bf16((v[i].z - mean) * rstd * ww.z + bb.z, (v[i].w - mean) * rstd * ww.w + bb.w);
-            *reinterpret_cast<uint2*>(dst + idx * 8) = pk;
-          }
-        }
-      } else {
-        for (int idx = lane; idx < nv; idx += 32) *reinterpret_cast<uint2*>(dst + idx * 8) = make_uint2(0u, 0u);
+        mean = S / p.K;
+        rstd = rsqrtf(fmaxf(Q / p.K - mean * mean, 0.f) + 1e-5f);
       }
+      s_mean[tid] = mean;
+      s_rstd[tid] = rstd;
     }
-  } else if (p.in_mode == IN_F32) {
+    __syncthreads();
     const float* x = reinterpret_cast<const float*>(p.in);
-    const int nv = p.K >> 2;
-    for (int idx = tid; idx < 16 * nv; idx += GV_THREADS) {
+    const int nv = kslice >> 2;
+    for (int idx = tid; idx < Bp * nv; idx += GV_THREADS) {
       const int r = idx / nv, c = idx - r * nv;
-      const int b = b0 + r;
       uint2 pk = make_uint2(0u, 0u);
-      if (b < p.B) {
-        const float4 v = *reinterpret_cast<const float4*>(x + (size_t)b * p.ld_in + c * 4);
-        pk.x = pack_bf16(v.x, v.y);
-        pk.y = pack_bf16(v.z, v.w);
+      if (r < p.B) {
+        const float4 v = *reinterpret_cast<const float4*>(x + (size_t)r * p.ld_in + k_begin + c * 4);
+        const float4 ww = *reinterpret_cast<const float4*>(s_ln + c * 4);
+        const float4 bb = *reinterpret_cast<const float4*>(s_ln + kslice + c * 4);
+        const float mean = s_mean[r], rstd = s_rstd[r];
+        pk.x = pack_bf16((v.x - mean) * rstd * ww.x + bb.x, (v.y - mean) * rstd * ww.y + bb.y);
+        pk.y = pack_bf16((v.z - mean) * rstd * ww.z + bb.z, (v.w - mean) * rstd * ww.w + bb.w);
       }
       *reinterpret_cast<uint2*>(gv_smem + r * row_bytes + c * 8) = pk;
     }
   } else {
     const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(p.in);
-    const int nv = p.K >> 3;
-    for (int idx = tid; idx < 16 * nv; idx += GV_THREADS) {
+    const int nv = kslice >> 3;
+    for (int idx = tid; idx < Bp * nv; idx += GV_THREADS) {
       const int r = idx / nv, c = idx - r * nv;
-      const int b = b0 + r;
       uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (b < p.B) v = *reinterpret_cast<const uint4*>(x + (size_t)b * p.ld_in + c * 8);
+      if (r < p.B) v = *reinterpret_cast<const uint4*>(x + (size_t)r * p.ld_in + k_begin + c * 8);
       *reinterpret_cast<uint4*>(gv_smem + r * row_bytes + c * 16) = v;
     }
   }
   __syncthreads();
   pdl_launch();
 
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  if (warp_active) {
+  float acc[4][4];
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt) acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0.f;
+  {
     const unsigned char* act_lo = gv_smem + g * row_bytes + 16 * t;
     const unsigned char* act_hi = act_lo + 8 * row_bytes;
-    for (int c = c_begin; c < c_end; c += 2 * GV_U) {
-      if (c + GV_U < c_end) gv_load(wb, wrow, c + GV_U, c_end);
-      gv_compute(acc, wa, act_lo, act_hi, c, c_end);
-      if (c + 2 * GV_U < c_end) gv_load(wa, wrow, c + 2 * GV_U, c_end);
-      if (c + GV_U < c_end) gv_compute(acc, wb, act_lo, act_hi, c + GV_U, c_end);
+    for (int c = 0; c < chunks; c += 2 * GV_U) {
+      if (c + GV_U < chunks) gv_load(wb, wrow, c + GV_U, chunks);
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+        if (mt < MT) gv_compute(acc[mt], wa, act_lo + mt * 16 * row_bytes, act_hi + mt * 16 * row_bytes, c, chunks);
+      if (c + 2 * GV_U < chunks) gv_load(wa, wrow, c + 2 * GV_U, chunks);
+      if (c + GV_U < chunks) {
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+          if (mt < MT) gv_compute(acc[mt], wb, act_lo + mt * 16 * row_bytes, act_hi + mt * 16 * row_bytes, c + GV_U, chunks);
+      }
     }
   }
-  // ---- reduce the kw K-slices of each row group, then the epilogue ----
-  if (kw > 1) {
-    *reinterpret_cast<float4*>(red + (warp * 32 + lane) * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  // ---- hand the 64-column output tile to the finisher: shared memory (ks == 1) or global partials ----
+  const int Npad = gridDim.x * GV_ROWS;
+  float* s_out = reinterpret_cast<float*>(gv_smem);  // [Bp][66] overlays the activation tile
+  if (p.ks == 1) {
+    __syncthreads();  // everyone is done reading the activation tile
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+      if (mt < MT) {
+        const int col = warp * 8 + 2 * t;
+        *reinterpret_cast<float2*>(s_out + (mt * 16 + g) * 66 + col) = make_float2(acc[mt][0], acc[mt][1]);
+        *reinterpret_cast<float2*>(s_out + (mt * 16 + g + 8) * 66 + col) = make_float2(acc[mt][2], acc[mt][3]);
+      }
     __syncthreads();
-    if (ks != 0) return;
-    for (int s = 1; s < kw; ++s) {
-      const float4 o = *reinterpret_cast<const float4*>(red + ((warp + s) * 32 + lane) * 4);
-      acc[0] += o.x; acc[1] += o.y; acc[2] += o.z; acc[3] += o.w;
+  } else {
+    float* mine = p.part + (size_t)blockIdx.y * Bp * Npad;
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+      if (mt < MT) {
+        const int col = n0 + 2 * t;
+        __stcg(reinterpret_cast<float2*>(mine + (size_t)(mt * 16 + g) * Npad + col), make_float2(acc[mt][0], acc[mt][1]));
+        __stcg(reinterpret_cast<float2*>(mine + (size_t)(mt * 16 + g + 8) * Npad + col), make_float2(acc[mt][2], acc[mt][3]));
+      }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const int prev = atomicAdd(p.ticket + blockIdx.x, 1);
+      s_last = (prev == p.ks - 1);
+      if (s_last) p.ticket[blockIdx.x] = 0;
     }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
   }
-  if (!warp_active) return;
+  // ---- finisher: warp w handles batch rows w, w+8, ...; lane handles columns 2*lane, 2*lane+1 of the block ----
   int pos = 0;
   if (p.epi == EPI_QKV) pos = *p.d_pos;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int b = b0 + g + (i >> 1) * 8;
-    const int n = n0 + 2 * t + (i & 1);
-    if (b >= p.B || n >= p.N) continue;
-    float v = acc[i] + (p.bias ? __ldg(p.bias + n) : 0.f);
+  const int n = nblk0 + 2 * lane;
+  const bool ok0 = n < p.N, ok1 = n + 1 < p.N;
+  const float b0 = (p.bias && ok0) ? __ldg(p.bias + n) : 0.f;
+  const float b1 = (p.bias && ok1) ? __ldg(p.bias + n + 1) : 0.f;
+  for (int b = warp; b < p.B; b += 8) {
+    float v0, v1;
+    if (p.ks == 1) {
+      const float2 v = *reinterpret_cast<const float2*>(s_out + b * 66 + 2 * lane);
+      v0 = v.x; v1 = v.y;
+    } else {
+      v0 = 0.f; v1 = 0.f;
+      for (int s2 = 0; s2 < p.ks; ++s2) {
+        const float2 v = __ldcg(reinterpret_cast<const float2*>(p.part + ((size_t)s2 * Bp + b) * Npad + n));
+        v0 += v.x; v1 += v.y;
+      }
+    }
+    v0 += b0; v1 += b1;
     if (p.epi == EPI_F32) {
-      reinterpret_cast<float*>(p.out)[(size_t)b * p.ldo + n] = v;
+      float* o = reinterpret_cast<float*>(p.out) + (size_t)b * p.ldo + n;
+      if (ok0) o[0] = v0;
+      if (ok1) o[1] = v1;
     } else if (p.epi == EPI_RESID) {
       float* o = reinterpret_cast<float*>(p.out) + (size_t)b * p.ldo + n;
-      *o = *o + v;
+      float S = 0.f, Q = 0.f;
+      if (ok1) {
+        float2 cur = *reinterpret_cast<float2*>(o);
+        cur.x += v0; cur.y += v1;
+        *reinterpret_cast<float2*>(o) = cur;
+        S = cur.x + cur.y; Q = cur.x * cur.x + cur.y * cur.y;
+      } else if (ok0) {
+        const float cur = o[0] + v0;
+        o[0] = cur;
+        S = cur; Q = cur * cur;
+      }
+      S = warp_sum(S);
+      Q = warp_sum(Q);
+      if (lane == 0 && p.stats_out) *reinterpret_cast<float2*>(p.stats_out + ((size_t)blockIdx.x * p.B + b) * 2) = make_float2(S, Q);
     } else if (p.epi == EPI_GELU_BF16) {
-      reinterpret_cast<__nv_bfloat16*>(p.out)[(size_t)b * p.ldo + n] = __float2bfloat16_rn(gelu_erf(v));
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)b * p.ldo + n;
+      if (ok1) *reinterpret_cast<uint32_t*>(o) = pack_bf16(gelu_erf(v0), gelu_erf(v1));
+      else if (ok0) o[0] = __float2bfloat16_rn(gelu_erf(v0));
     } else {
-      const int d = p.N / 3;
-      if (n < d) {
-        p.q_out[(size_t)b * d + n] = v;
-      } else {
-        const int nn = (n < 2 * d) ? (n - d) : (n - 2 * d);
-        __nv_bfloat16* cache = (n < 2 * d) ? p.kcache : p.vcache;
-        const int h = nn >> 6, j = nn & 63;
-        cache[(((size_t)b * p.H + h) * p.tmax + pos) * 64 + j] = __float2bfloat16_rn(v);
+      const int d = p.N / 3;  // n and n+1 share a 64-wide head block (n even)
+      if (ok0) {
+        if (n < d) {
+          *reinterpret_cast<float2*>(p.q_out + (size_t)b * d + n) = make_float2(v0, v1);
+        } else {
+          const int nn = (n < 2 * d) ? (n - d) : (n - 2 * d);
+          __nv_bfloat16* cache = (n < 2 * d) ? p.kcache : p.vcache;
+          const int h = nn >> 6, j = nn & 63;
+          *reinterpret_cast<uint32_t*>(cache + (((size_t)b * p.H + h) * p.tmax + pos) * 64 + j) = pack_bf16(v0, v1);
+        }
       }
     }
   }
@@ -264,7 +324,7 @@ struct AttnParams {
   const int* d_pos;             // if set: n_keys = *d_pos + 1 (self-attention)
   int splits, H, d;
   float scale;
-  float* out;                   // [B, d]
+  __nv_bfloat16* out;           // [B, d] bf16 (feeds the out-projection GEMV)
   float* part;                  // [B][H][splits][66]  (m, l, o[64])
   int* ticket;                  // [B*H], zero-initialised, self-cleaning
 };
@@ -405,7 +465,7 @@ dec_attn_kernel(const AttnParams p) {
     }
   }
   if (p.splits == 1) {
-    if (tid < 64) p.out[(size_t)b * p.d + h * 64 + tid] = o / L;
+    if (tid < 64) p.out[(size_t)b * p.d + h * 64 + tid] = __float2bfloat16_rn(o / L);
     return;
   }
   // ---- split-KV: publish the partial, the last CTA of this (b,h) merges ----
@@ -434,24 +494,33 @@ dec_attn_kernel(const AttnParams p) {
       LL += w * __ldcg(part + s2 * 66 + 1);
       OO += w * __ldcg(part + s2 * 66 + 2 + tid);
     }
-    p.out[(size_t)b * p.d + h * 64 + tid] = OO / LL;
+    p.out[(size_t)b * p.d + h * 64 + tid] = __float2bfloat16_rn(OO / LL);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // token embedding + learned position; sampling; bookkeeping
 // ---------------------------------------------------------------------------------------------
-// x[b,:] = emb[tok[b*stride + col]] + pos_emb[pos], col = pos = *d_pos
-__global__ void dec_embed_kernel(const int* __restrict__ tok, int stride, const int* __restrict__ d_pos,
-                                 const __nv_bfloat16* __restrict__ emb, const float* __restrict__ pos_emb,
-                                 float* __restrict__ x, int d, int n_vocab) {
+// x[b,:] = emb[tok[b*stride + pos]] + pos_emb[pos], pos = *d_pos; also the per-64-column (sum, sum of
+// squares) of the new row, which the first LayerNorm-fused GEMV of the step consumes.
+__global__ void __launch_bounds__(256)
+dec_embed_kernel(const int* __restrict__ tok, int stride, const int* __restrict__ d_pos,
+                 const __nv_bfloat16* __restrict__ emb, const float* __restrict__ pos_emb,
+                 float* __restrict__ x, float* __restrict__ stats, int d, int n_vocab, int B) {
   pdl_wait();
-  const int b = blockIdx.x;
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pos = *d_pos;
   int token = tok[(size_t)b * stride + pos];
   token = min(max(token, 0), n_vocab - 1);
-  for (int i = threadIdx.x; i < d; i += blockDim.x)
-    x[(size_t)b * d + i] = __bfloat162float(emb[(size_t)token * d + i]) + pos_emb[(size_t)pos * d + i];
+  for (int blk = warp; blk < d / 64; blk += 8) {
+    const int i = blk * 64 + 2 * lane;
+    const __nv_bfloat162 e = *reinterpret_cast<const __nv_bfloat162*>(emb + (size_t)token * d + i);
+    const float2 pe = *reinterpret_cast<const float2*>(pos_emb + (size_t)pos * d + i);
+    const float v0 = __low2float(e) + pe.x, v1 = __high2float(e) + pe.y;
+    *reinterpret_cast<float2*>(x + (size_t)b * d + i) = make_float2(v0, v1);
+    const float S = warp_sum(v0 + v1), Q = warp_sum(v0 * v0 + v1 * v1);
+    if (lane == 0) *reinterpret_cast<float2*>(stats + ((size_t)blk * B + b) * 2) = make_float2(S, Q);
+  }
 }
 
 __global__ void dec_advance_kernel(int* d_pos) {
@@ -574,10 +643,11 @@ __global__ void dec_finalize_kernel(const int* __restrict__ tokens, int stride, 
 // host side
 // ---------------------------------------------------------------------------------------------
 struct DecBuffers {
-  float *x, *q, *att, *logits, *part, *sum_lp;
-  __nv_bfloat16 *hid, *self_kv, *cross_kv;
-  int *ticket, *d_pos, *tokens, *done;
+  float *x, *q, *logits, *part, *sum_lp, *stats, *gv_part;
+  __nv_bfloat16 *att, *hid, *self_kv, *cross_kv;
+  int *ticket, *gv_ticket, *d_pos, *tokens, *done;
   int B, tok_stride;
+  size_t gv_part_floats;
 };
 
 bool use_pdl() {
@@ -607,20 +677,40 @@ int launch_k(wxb_ctx* ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t
   return WXB_OK;
 }
 
-int pick_kw(int K) {
-  for (int kw = 8; kw >= 1; kw >>= 1)
-    if (K % (64 * kw) == 0) return kw;
-  return 0;
+constexpr size_t GV_SMEM_MAX = 200 * 1024;
+
+size_t gemv_smem(int Bp, int kslice, int in_mode) {
+  const size_t act = (size_t)Bp * (kslice + 32) * 2 + (in_mode == IN_LN ? (size_t)2 * kslice * 4 : 0);
+  const size_t outt = (size_t)Bp * 66 * 4;
+  return act > outt ? act : outt;
 }
 
-int launch_gemv(wxb_ctx* ctx, GemvParams p, cudaStream_t st) {
-  p.kw = pick_kw(p.K);
-  if (p.kw == 0) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "gemv: K=%d must be a multiple of 64", p.K);
-  if (p.in_mode == IN_LN && p.K > 1280) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "gemv: fused LayerNorm needs K <= 1280");
-  const int rg = 8 / p.kw;
-  const size_t smem = (size_t)16 * (p.K + 32) * 2 + 8 * 128 * 4;  // opt-in size set in alloc_buffers()
-  dim3 grid(ceil_div(ceil_div(p.N, 8), rg), ceil_div(p.B, 16));
-  return launch_k(ctx, dec_gemv_kernel, grid, dim3(GV_THREADS), smem, st, p);
+// split-K factor: the smallest divisor of K/64 that yields at least one CTA per SM and fits shared memory
+int pick_ks(wxb_ctx* ctx, int Bp, int N, int K, int in_mode) {
+  const int row_blocks = ceil_div(N, GV_ROWS), kc = K / 64;
+  int best = 0;
+  for (int ks = 1; ks <= kc; ++ks) {
+    if (kc % ks) continue;
+    if (gemv_smem(Bp, K / ks, in_mode) > GV_SMEM_MAX) continue;
+    best = ks;
+    if (row_blocks * ks >= ctx->sm_count) break;
+  }
+  return best;
+}
+
+int launch_gemv(wxb_ctx* ctx, GemvParams p, const DecBuffers& buf, cudaStream_t st) {
+  if (p.K % 64) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "gemv: K=%d must be a multiple of 64", p.K);
+  if (p.B > 64) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "gemv: batch %d > 64", p.B);
+  const int Bp = (p.B + 15) & ~15;
+  p.ks = pick_ks(ctx, Bp, p.N, p.K, p.in_mode);
+  if (p.ks == 0) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "gemv: no K split of K=%d fits shared memory", p.K);
+  const int row_blocks = ceil_div(p.N, GV_ROWS);
+  if (p.ks > 1 && (size_t)p.ks * Bp * row_blocks * GV_ROWS > buf.gv_part_floats)
+    return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "gemv: split-K workspace too small (N=%d K=%d ks=%d)", p.N, p.K, p.ks);
+  p.part = buf.gv_part;
+  p.ticket = buf.gv_ticket;
+  const size_t smem = gemv_smem(Bp, p.K / p.ks, p.in_mode);
+  return launch_k(ctx, dec_gemv_kernel, dim3(row_blocks, p.ks), dim3(GV_THREADS), smem, st, p);
 }
 
 int launch_attn(wxb_ctx* ctx, AttnParams p, int B, cudaStream_t st) {
@@ -633,14 +723,16 @@ int alloc_buffers(wxb_ctx* ctx, int B, int tok_stride, DecBuffers* o) {
   const int d = D.n_text_state, L = D.n_text_layer, H = D.n_text_head, V = D.n_vocab;
   o->B = B;
   o->tok_stride = tok_stride;
-  {  // largest dynamic shared memory any decoder kernel asks for (fc2: K = 4d); set outside graph capture
-    const size_t gv_smem = (size_t)16 * (4 * d + 32) * 2 + 8 * 128 * 4;
-    if (gv_smem > 227 * 1024) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: d=%d too wide for the GEMV activation tile", d);
-    WXB_CUDA(ctx, cudaFuncSetAttribute(dec_gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gv_smem));
-  }
+  if (B > 64) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: batch %d > 64 sequences per call", B);
+  // opt in to the largest dynamic shared memory the GEMV may ask for; set outside graph capture
+  WXB_CUDA(ctx, cudaFuncSetAttribute(dec_gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GV_SMEM_MAX));
   o->x = (float*)wxb_named(ctx, "dec.x", (size_t)B * d * 4);
   o->q = (float*)wxb_named(ctx, "dec.q", (size_t)B * d * 4);
-  o->att = (float*)wxb_named(ctx, "dec.att", (size_t)B * d * 4);
+  o->att = (__nv_bfloat16*)wxb_named(ctx, "dec.att", (size_t)B * d * 2);
+  o->stats = (float*)wxb_named(ctx, "dec.stats", (size_t)(d / 64) * B * 2 * 4);
+  o->gv_part_floats = (size_t)4 << 20;  // 16 MB of fp32 split-K partials
+  o->gv_part = (float*)wxb_named(ctx, "dec.gv_part", o->gv_part_floats * 4);
+  o->gv_ticket = (int*)wxb_named(ctx, "dec.gv_ticket", (size_t)(ceil_div(V, GV_ROWS) + 64) * 4, true);
   o->hid = (__nv_bfloat16*)wxb_named(ctx, "dec.hid", (size_t)B * 4 * d * 2);
   o->logits = (float*)wxb_named(ctx, "dec.logits", (size_t)B * V * 4);
   o->part = (float*)wxb_named(ctx, "dec.part", (size_t)B * H * 8 * 66 * 4);
@@ -652,7 +744,7 @@ int alloc_buffers(wxb_ctx* ctx, int B, int tok_stride, DecBuffers* o) {
   o->tokens = (int*)wxb_named(ctx, "dec.tokens", (size_t)B * tok_stride * 4);
   o->done = (int*)wxb_named(ctx, "dec.done", (size_t)B * 4);
   if (!o->x || !o->q || !o->att || !o->hid || !o->logits || !o->part || !o->sum_lp || !o->self_kv || !o->cross_kv ||
-      !o->ticket || !o->d_pos || !o->tokens || !o->done)
+      !o->ticket || !o->d_pos || !o->tokens || !o->done || !o->stats || !o->gv_part || !o->gv_ticket)
     return WXB_ERR_CUDA;
   return WXB_OK;
 }
@@ -686,7 +778,7 @@ int decoder_step(wxb_ctx* ctx, const DecBuffers& buf, float* logits_out, long lo
   if (!emb || !pos_emb || !lnf_w || !lnf_b) return WXB_ERR_STATE;
   int rc;
   if ((rc = launch_k(ctx, dec_embed_kernel, dim3(B), dim3(256), 0, st, (const int*)buf.tokens, buf.tok_stride,
-                     (const int*)buf.d_pos, emb, pos_emb, buf.x, d, D.n_vocab)) != WXB_OK)
+                     (const int*)buf.d_pos, emb, pos_emb, buf.x, buf.stats, d, D.n_vocab, B)) != WXB_OK)
     return rc;
   const float scale = 1.0f / sqrtf(64.f);
   const int cross_splits = (B * H >= 4 * ctx->sm_count) ? 1 : ((B * H >= 2 * ctx->sm_count) ? 2 : 4);
@@ -701,9 +793,10 @@ int decoder_step(wxb_ctx* ctx, const DecBuffers& buf, float* logits_out, long lo
     g.B = B;
     // 1. LN1 + fused QKV, K/V appended to the self cache at pos
     g.N = 3 * d; g.K = d; g.in_mode = IN_LN; g.in = buf.x; g.ld_in = d; g.ln_w = w.ln1_w; g.ln_b = w.ln1_b;
+    g.stats_in = buf.stats; g.n_stat_blocks = d / 64;
     g.W = w.qkv_w; g.bias = w.qkv_b; g.epi = EPI_QKV; g.q_out = buf.q; g.kcache = sk; g.vcache = sv;
     g.d_pos = buf.d_pos; g.H = H; g.tmax = TX;
-    if ((rc = launch_gemv(ctx, g, st)) != WXB_OK) return rc;
+    if ((rc = launch_gemv(ctx, g, buf, st)) != WXB_OK) return rc;
     // 2. causal self-attention over pos+1 cached positions
     AttnParams a = {};
     a.q = buf.q; a.K = sk; a.V = sv; a.tkv = TX; a.d_pos = buf.d_pos; a.splits = 1; a.H = H; a.d = d; a.scale = scale;
@@ -711,14 +804,15 @@ int decoder_step(wxb_ctx* ctx, const DecBuffers& buf, float* logits_out, long lo
     if ((rc = launch_attn(ctx, a, B, st)) != WXB_OK) return rc;
     // 3. out projection + residual
     g = GemvParams{};
-    g.B = B; g.N = d; g.K = d; g.in_mode = IN_F32; g.in = buf.att; g.ld_in = d; g.W = w.out_w; g.bias = w.out_b;
-    g.epi = EPI_RESID; g.out = buf.x; g.ldo = d;
-    if ((rc = launch_gemv(ctx, g, st)) != WXB_OK) return rc;
+    g.B = B; g.N = d; g.K = d; g.in_mode = IN_BF16; g.in = buf.att; g.ld_in = d; g.W = w.out_w; g.bias = w.out_b;
+    g.epi = EPI_RESID; g.out = buf.x; g.ldo = d; g.stats_out = buf.stats;
+    if ((rc = launch_gemv(ctx, g, buf, st)) != WXB_OK) return rc;
     // 4. LN2 + cross query
     g = GemvParams{};
     g.B = B; g.N = d; g.K = d; g.in_mode = IN_LN; g.in = buf.x; g.ld_in = d; g.ln_w = w.ln2_w; g.ln_b = w.ln2_b;
+    g.stats_in = buf.stats; g.n_stat_blocks = d / 64;
     g.W = w.cq_w; g.bias = w.cq_b; g.epi = EPI_F32; g.out = buf.q; g.ldo = d;
-    if ((rc = launch_gemv(ctx, g, st)) != WXB_OK) return rc;
+    if ((rc = launch_gemv(ctx, g, buf, st)) != WXB_OK) return rc;
     // 5. cross-attention over the 1500 encoder positions
     a = AttnParams{};
     a.q = buf.q; a.K = ck; a.V = cv; a.tkv = T_AUDIO; a.n_keys = T_AUDIO; a.d_pos = nullptr; a.splits = cross_splits;
@@ -726,25 +820,27 @@ int decoder_step(wxb_ctx* ctx, const DecBuffers& buf, float* logits_out, long lo
     if ((rc = launch_attn(ctx, a, B, st)) != WXB_OK) return rc;
     // 6. cross out projection + residual
     g = GemvParams{};
-    g.B = B; g.N = d; g.K = d; g.in_mode = IN_F32; g.in = buf.att; g.ld_in = d; g.W = w.cout_w; g.bias = w.cout_b;
-    g.epi = EPI_RESID; g.out = buf.x; g.ldo = d;
-    if ((rc = launch_gemv(ctx, g, st)) != WXB_OK) return rc;
+    g.B = B; g.N = d; g.K = d; g.in_mode = IN_BF16; g.in = buf.att; g.ld_in = d; g.W = w.cout_w; g.bias = w.cout_b;
+    g.epi = EPI_RESID; g.out = buf.x; g.ldo = d; g.stats_out = buf.stats;
+    if ((rc = launch_gemv(ctx, g, buf, st)) != WXB_OK) return rc;
     // 7. LN3 + fc1 + GELU
     g = GemvParams{};
     g.B = B; g.N = 4 * d; g.K = d; g.in_mode = IN_LN; g.in = buf.x; g.ld_in = d; g.ln_w = w.ln3_w; g.ln_b = w.ln3_b;
+    g.stats_in = buf.stats; g.n_stat_blocks = d / 64;
     g.W = w.fc1_w; g.bias = w.fc1_b; g.epi = EPI_GELU_BF16; g.out = buf.hid; g.ldo = 4 * d;
-    if ((rc = launch_gemv(ctx, g, st)) != WXB_OK) return rc;
+    if ((rc = launch_gemv(ctx, g, buf, st)) != WXB_OK) return rc;
     // 8. fc2 + residual
     g = GemvParams{};
     g.B = B; g.N = d; g.K = 4 * d; g.in_mode = IN_BF16; g.in = buf.hid; g.ld_in = 4 * d; g.W = w.fc2_w; g.bias = w.fc2_b;
-    g.epi = EPI_RESID; g.out = buf.x; g.ldo = d;
-    if ((rc = launch_gemv(ctx, g, st)) != WXB_OK) return rc;
+    g.epi = EPI_RESID; g.out = buf.x; g.ldo = d; g.stats_out = buf.stats;
+    if ((rc = launch_gemv(ctx, g, buf, st)) != WXB_OK) return rc;
   }
   if (logits_out) {
     GemvParams g = {};
     g.B = B; g.N = D.n_vocab; g.K = d; g.in_mode = IN_LN; g.in = buf.x; g.ld_in = d; g.ln_w = lnf_w; g.ln_b = lnf_b;
+    g.stats_in = buf.stats; g.n_stat_blocks = d / 64;
     g.W = emb; g.bias = nullptr; g.epi = EPI_F32; g.out = logits_out; g.ldo = ldl;
-    if ((rc = launch_gemv(ctx, g, st)) != WXB_OK) return rc;
+    if ((rc = launch_gemv(ctx, g, buf, st)) != WXB_OK) return rc;
   }
   return WXB_OK;
 }
