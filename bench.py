@@ -313,7 +313,7 @@ def main():
     enc_flops = flops_encoder(dims) * n_chunks
     ckv_flops = 2 * 1500 * dims["n_text_state"] * dims["n_audio_state"] * 2 * dims["n_text_layer"] * n_chunks
     mel_bytes = n_chunks * (4 * 480000 + dims["n_mels"] * 3000 * 4)
-    roofline = {"bound": "hbm", "kernel": f"decode step (CUDA graph of {1 + 8 * dims['n_text_layer'] + 3} kernels: dec_gemv / dec_attn / sample)",
+    roofline = {"bound": "hbm", "kernel": f"decode step (CUDA graph of {1 + 11 * dims['n_text_layer'] + 4} kernels: dec_gemv / dec_attn / sample)",
                 "achieved": achieved, "peak": P["hbm_gbs"], "unit": "GB/s", "frac": achieved / P["hbm_gbs"], "traffic": None,
                 "peak_source": P["source"], "bytes_per_launch": bytes_step, "ms_per_launch": dec_ms_per_step,
                 "weight_reads_per_step": groups,

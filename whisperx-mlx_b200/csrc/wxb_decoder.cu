@@ -35,7 +35,7 @@ namespace {
 
 constexpr int T_AUDIO = 1500;
 constexpr int GV_THREADS = 256;
-constexpr int GV_U = 5;  // 64-wide K chunks per register group
+constexpr int GV_U = 4;  // 64-wide K chunks per register group
 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -56,20 +56,16 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-enum { IN_LN = 0, IN_BF16 = 2 };
 enum { EPI_F32 = 0, EPI_RESID = 1, EPI_GELU_BF16 = 2, EPI_QKV = 3 };
 
-constexpr int GV_ROWS = 64;  // weight rows per CTA (8 warps x 8 rows)
+constexpr int GV_ROWS = 64;    // weight rows per CTA (8 warps x 8 rows)
+constexpr int GV_KS_MAX = 20;  // largest split-K factor the finisher unrolls
 
 struct GemvParams {
   int B, N, K;
-  int ks;         // split-K factor across CTAs (gridDim.y); K / ks is a multiple of 64
-  int in_mode;
-  const void* in;  // IN_LN: residual stream f32 [B, K];  IN_BF16: bf16 [B, K]
+  int ks;                      // split-K factor across CTAs (gridDim.y); K / ks is a multiple of 64
+  const __nv_bfloat16* in;     // activations bf16 [B, K]
   long long ld_in;
-  const float *ln_w, *ln_b;
-  const float* stats_in;  // IN_LN: [n_stat_blocks][B][2] partial (sum, sum of squares) of each row of `in`
-  int n_stat_blocks;
   const __nv_bfloat16* W;
   const float* bias;
   int epi;
@@ -83,8 +79,6 @@ struct GemvParams {
   // split-K partials [ks][Bp][Npad] and per-row-block tickets (zero-initialised, self-cleaning)
   float* part;
   int* ticket;
-  // EPI_RESID: per-row-block (sum, sum of squares) of the updated residual rows, [N/64][B][2]
-  float* stats_out;
 };
 
 // Weight chunk c (64 K-columns) of this lane: two 16-byte loads at k = 64c + 8t and 64c + 32 + 8t of row (n0 + g).
@@ -117,15 +111,65 @@ __device__ __forceinline__ void gv_compute(float* acc, const uint4* w, const uns
   }
 }
 
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+
+// LayerNorm (eps 1e-5) of the residual stream rows: f32 [B, d] -> bf16 [B, d], one warp per row (d <= 1280)
+__global__ void __launch_bounds__(256)
+dec_ln_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+              __nv_bfloat16* __restrict__ y, int B, int d) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int nv = d >> 2;
+  float4 ww[10], bb[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {  // parameters do not depend on the previous kernel
+    const int idx = lane + 32 * i;
+    if (idx < nv) { ww[i] = __ldg(reinterpret_cast<const float4*>(w) + idx); bb[i] = __ldg(reinterpret_cast<const float4*>(bias) + idx); }
+  }
+  pdl_wait();
+  pdl_launch();
+  if (row >= B) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * d);
+  float4 v[10];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nv) { v[i] = xr[idx]; s += v[i].x + v[i].y + v[i].z + v[i].w; }
+  }
+  const float mean = warp_sum(s) / d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nv) {
+      const float a = v[i].x - mean, b2 = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+      q += a * a + b2 * b2 + c * c + e * e;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / d + 1e-5f);
+  uint2* yr = reinterpret_cast<uint2*>(y + (size_t)row * d);
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nv) {
+      uint2 pk;
+      pk.x = pack_bf16((v[i].x - mean) * rstd * ww[i].x + bb[i].x, (v[i].y - mean) * rstd * ww[i].y + bb[i].y);
+      pk.y = pack_bf16((v[i].z - mean) * rstd * ww[i].z + bb[i].z, (v[i].w - mean) * rstd * ww[i].w + bb[i].w);
+      yr[idx] = pk;
+    }
+  }
+}
+
 // Skinny GEMM y[B, N] = act[B, K] W[N, K]^T for B <= 64.  CTA = 64 weight rows x one K-slice; warp w owns
 // rows 8w..8w+7 and keeps its weight fragments in registers while looping over the (<= 4) 16-row batch
-// tiles, whose activations sit in shared memory.  gridDim.y K-slices are combined deterministically: every
-// slice publishes fp32 partials and the last-arriving CTA of a row block sums them in slice order and runs
-// the epilogue (bias / GELU / residual + LayerNorm statistics / QKV scatter into the KV cache).
-__global__ void __launch_bounds__(GV_THREADS)
+// tiles, whose activations are cp.async'ed into shared memory.  gridDim.y K-slices are combined
+// deterministically: every slice publishes fp32 partials and the last-arriving CTA of a row block sums
+// them in slice order and runs the epilogue (bias / GELU / residual / QKV scatter into the KV cache).
+__global__ void __launch_bounds__(GV_THREADS, 2)
 dec_gemv_kernel(const GemvParams p) {
   extern __shared__ __align__(16) unsigned char gv_smem[];
-  __shared__ float s_mean[64], s_rstd[64];
   __shared__ int s_last;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -137,64 +181,24 @@ dec_gemv_kernel(const GemvParams p) {
   const int nblk0 = blockIdx.x * GV_ROWS;
   const int n0 = nblk0 + warp * 8;
   const size_t row_bytes = (size_t)(kslice + 32) * 2;  // +64 B: rows g and g+1 land on different bank halves
-  float* s_ln = reinterpret_cast<float*>(gv_smem + (size_t)Bp * row_bytes);  // [2][kslice] LN weight / bias slice
 
   int nrow = n0 + g;
   if (nrow >= p.N) nrow = p.N - 1;
   const __nv_bfloat16* wrow = p.W + (size_t)nrow * p.K + k_begin + 8 * t;
   uint4 wa[2 * GV_U], wb[2 * GV_U];
-  // everything up to the wait is independent of the previous kernel: weights + LayerNorm parameters
-  gv_load(wa, wrow, 0, chunks);
-  if (p.in_mode == IN_LN) {
-    for (int i = tid; i < kslice; i += GV_THREADS) {
-      s_ln[i] = __ldg(p.ln_w + k_begin + i);
-      s_ln[kslice + i] = __ldg(p.ln_b + k_begin + i);
-    }
-  }
+  gv_load(wa, wrow, 0, chunks);  // weights do not depend on the previous kernel: request them before the wait
   pdl_wait();
 
-  // ---- stage the activation tile (Bp batch rows x K-slice) as bf16 ----
-  if (p.in_mode == IN_LN) {
-    if (tid < Bp) {
-      float mean = 0.f, rstd = 0.f;
-      if (tid < p.B) {
-        float S = 0.f, Q = 0.f;
-        for (int i = 0; i < p.n_stat_blocks; ++i) {
-          const float2 st = *reinterpret_cast<const float2*>(p.stats_in + ((size_t)i * p.B + tid) * 2);
-          S += st.x;
-          Q += st.y;
-        }
-        mean = S / p.K;
-        rstd = rsqrtf(fmaxf(Q / p.K - mean * mean, 0.f) + 1e-5f);
-      }
-      s_mean[tid] = mean;
-      s_rstd[tid] = rstd;
-    }
-    __syncthreads();
-    const float* x = reinterpret_cast<const float*>(p.in);
-    const int nv = kslice >> 2;
-    for (int idx = tid; idx < Bp * nv; idx += GV_THREADS) {
-      const int r = idx / nv, c = idx - r * nv;
-      uint2 pk = make_uint2(0u, 0u);
-      if (r < p.B) {
-        const float4 v = *reinterpret_cast<const float4*>(x + (size_t)r * p.ld_in + k_begin + c * 4);
-        const float4 ww = *reinterpret_cast<const float4*>(s_ln + c * 4);
-        const float4 bb = *reinterpret_cast<const float4*>(s_ln + kslice + c * 4);
-        const float mean = s_mean[r], rstd = s_rstd[r];
-        pk.x = pack_bf16((v.x - mean) * rstd * ww.x + bb.x, (v.y - mean) * rstd * ww.y + bb.y);
-        pk.y = pack_bf16((v.z - mean) * rstd * ww.z + bb.z, (v.w - mean) * rstd * ww.w + bb.w);
-      }
-      *reinterpret_cast<uint2*>(gv_smem + r * row_bytes + c * 8) = pk;
-    }
-  } else {
-    const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(p.in);
+  // ---- stage the activation tile (B batch rows x K-slice, bf16) with 16-byte async copies ----
+  {
     const int nv = kslice >> 3;
     for (int idx = tid; idx < Bp * nv; idx += GV_THREADS) {
       const int r = idx / nv, c = idx - r * nv;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (r < p.B) v = *reinterpret_cast<const uint4*>(x + (size_t)r * p.ld_in + k_begin + c * 8);
-      *reinterpret_cast<uint4*>(gv_smem + r * row_bytes + c * 16) = v;
+      unsigned char* dst = gv_smem + r * row_bytes + c * 16;
+      if (r < p.B) cp_async16(dst, p.in + (size_t)r * p.ld_in + k_begin + c * 8);
+      else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
     }
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
   }
   __syncthreads();
   pdl_launch();
@@ -264,11 +268,14 @@ dec_gemv_kernel(const GemvParams p) {
       const float2 v = *reinterpret_cast<const float2*>(s_out + b * 66 + 2 * lane);
       v0 = v.x; v1 = v.y;
     } else {
+      float2 pv[GV_KS_MAX];
+#pragma unroll
+      for (int s2 = 0; s2 < GV_KS_MAX; ++s2)  // all loads first (one L2 round trip), then a fixed-order sum
+        if (s2 < p.ks) pv[s2] = __ldcg(reinterpret_cast<const float2*>(p.part + ((size_t)s2 * Bp + b) * Npad + n));
       v0 = 0.f; v1 = 0.f;
-      for (int s2 = 0; s2 < p.ks; ++s2) {
-        const float2 v = __ldcg(reinterpret_cast<const float2*>(p.part + ((size_t)s2 * Bp + b) * Npad + n));
-        v0 += v.x; v1 += v.y;
-      }
+#pragma unroll
+      for (int s2 = 0; s2 < GV_KS_MAX; ++s2)
+        if (s2 < p.ks) { v0 += pv[s2].x; v1 += pv[s2].y; }
     }
     v0 += b0; v1 += b1;
     if (p.epi == EPI_F32) {
@@ -277,20 +284,13 @@ dec_gemv_kernel(const GemvParams p) {
       if (ok1) o[1] = v1;
     } else if (p.epi == EPI_RESID) {
       float* o = reinterpret_cast<float*>(p.out) + (size_t)b * p.ldo + n;
-      float S = 0.f, Q = 0.f;
       if (ok1) {
         float2 cur = *reinterpret_cast<float2*>(o);
         cur.x += v0; cur.y += v1;
         *reinterpret_cast<float2*>(o) = cur;
-        S = cur.x + cur.y; Q = cur.x * cur.x + cur.y * cur.y;
       } else if (ok0) {
-        const float cur = o[0] + v0;
-        o[0] = cur;
-        S = cur; Q = cur * cur;
+        o[0] += v0;
       }
-      S = warp_sum(S);
-      Q = warp_sum(Q);
-      if (lane == 0 && p.stats_out) *reinterpret_cast<float2*>(p.stats_out + ((size_t)blockIdx.x * p.B + b) * 2) = make_float2(S, Q);
     } else if (p.epi == EPI_GELU_BF16) {
       __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)b * p.ldo + n;
       if (ok1) *reinterpret_cast<uint32_t*>(o) = pack_bf16(gelu_erf(v0), gelu_erf(v1));
@@ -501,25 +501,21 @@ dec_attn_kernel(const AttnParams p) {
 // ---------------------------------------------------------------------------------------------
 // token embedding + learned position; sampling; bookkeeping
 // ---------------------------------------------------------------------------------------------
-// x[b,:] = emb[tok[b*stride + pos]] + pos_emb[pos], pos = *d_pos; also the per-64-column (sum, sum of
-// squares) of the new row, which the first LayerNorm-fused GEMV of the step consumes.
+// x[b,:] = emb[tok[b*stride + pos]] + pos_emb[pos], pos = *d_pos
 __global__ void __launch_bounds__(256)
 dec_embed_kernel(const int* __restrict__ tok, int stride, const int* __restrict__ d_pos,
                  const __nv_bfloat16* __restrict__ emb, const float* __restrict__ pos_emb,
-                 float* __restrict__ x, float* __restrict__ stats, int d, int n_vocab, int B) {
+                 float* __restrict__ x, int d, int n_vocab) {
   pdl_wait();
-  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch();
+  const int b = blockIdx.x;
   const int pos = *d_pos;
   int token = tok[(size_t)b * stride + pos];
   token = min(max(token, 0), n_vocab - 1);
-  for (int blk = warp; blk < d / 64; blk += 8) {
-    const int i = blk * 64 + 2 * lane;
+  for (int i = 2 * threadIdx.x; i < d; i += 2 * blockDim.x) {
     const __nv_bfloat162 e = *reinterpret_cast<const __nv_bfloat162*>(emb + (size_t)token * d + i);
     const float2 pe = *reinterpret_cast<const float2*>(pos_emb + (size_t)pos * d + i);
-    const float v0 = __low2float(e) + pe.x, v1 = __high2float(e) + pe.y;
-    *reinterpret_cast<float2*>(x + (size_t)b * d + i) = make_float2(v0, v1);
-    const float S = warp_sum(v0 + v1), Q = warp_sum(v0 * v0 + v1 * v1);
-    if (lane == 0) *reinterpret_cast<float2*>(stats + ((size_t)blk * B + b) * 2) = make_float2(S, Q);
+    *reinterpret_cast<float2*>(x + (size_t)b * d + i) = make_float2(__low2float(e) + pe.x, __high2float(e) + pe.y);
   }
 }
 
@@ -643,8 +639,8 @@ __global__ void dec_finalize_kernel(const int* __restrict__ tokens, int stride, 
 // host side
 // ---------------------------------------------------------------------------------------------
 struct DecBuffers {
-  float *x, *q, *logits, *part, *sum_lp, *stats, *gv_part;
-  __nv_bfloat16 *att, *hid, *self_kv, *cross_kv;
+  float *x, *q, *logits, *part, *sum_lp, *gv_part;
+  __nv_bfloat16 *att, *xn, *hid, *self_kv, *cross_kv;
   int *ticket, *gv_ticket, *d_pos, *tokens, *done;
   int B, tok_stride;
   size_t gv_part_floats;
@@ -679,21 +675,23 @@ int launch_k(wxb_ctx* ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t
 
 constexpr size_t GV_SMEM_MAX = 200 * 1024;
 
-size_t gemv_smem(int Bp, int kslice, int in_mode) {
-  const size_t act = (size_t)Bp * (kslice + 32) * 2 + (in_mode == IN_LN ? (size_t)2 * kslice * 4 : 0);
+size_t gemv_smem(int Bp, int kslice) {
+  const size_t act = (size_t)Bp * (kslice + 32) * 2;
   const size_t outt = (size_t)Bp * 66 * 4;
   return act > outt ? act : outt;
 }
 
-// split-K factor: the smallest divisor of K/64 that yields at least one CTA per SM and fits shared memory
-int pick_ks(wxb_ctx* ctx, int Bp, int N, int K, int in_mode) {
+// split-K factor: the smallest divisor of K/64 that yields at least one CTA per SM, keeps two CTAs per SM
+// resident (<= ~100 KB of shared memory) and stays within what the finisher unrolls
+int pick_ks(wxb_ctx* ctx, int Bp, int N, int K) {
   const int row_blocks = ceil_div(N, GV_ROWS), kc = K / 64;
   int best = 0;
-  for (int ks = 1; ks <= kc; ++ks) {
+  for (int ks = 1; ks <= kc && ks <= GV_KS_MAX; ++ks) {
     if (kc % ks) continue;
-    if (gemv_smem(Bp, K / ks, in_mode) > GV_SMEM_MAX) continue;
+    const size_t sm = gemv_smem(Bp, K / ks);
+    if (sm > GV_SMEM_MAX) continue;
     best = ks;
-    if (row_blocks * ks >= ctx->sm_count) break;
+    if (row_blocks * ks >= ctx->sm_count && sm <= 100 * 1024) break;
   }
   return best;
 }
@@ -702,15 +700,19 @@ int launch_gemv(wxb_ctx* ctx, GemvParams p, const DecBuffers& buf, cudaStream_t 
   if (p.K % 64) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "gemv: K=%d must be a multiple of 64", p.K);
   if (p.B > 64) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "gemv: batch %d > 64", p.B);
   const int Bp = (p.B + 15) & ~15;
-  p.ks = pick_ks(ctx, Bp, p.N, p.K, p.in_mode);
+  p.ks = pick_ks(ctx, Bp, p.N, p.K);
   if (p.ks == 0) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "gemv: no K split of K=%d fits shared memory", p.K);
   const int row_blocks = ceil_div(p.N, GV_ROWS);
   if (p.ks > 1 && (size_t)p.ks * Bp * row_blocks * GV_ROWS > buf.gv_part_floats)
     return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "gemv: split-K workspace too small (N=%d K=%d ks=%d)", p.N, p.K, p.ks);
   p.part = buf.gv_part;
   p.ticket = buf.gv_ticket;
-  const size_t smem = gemv_smem(Bp, p.K / p.ks, p.in_mode);
-  return launch_k(ctx, dec_gemv_kernel, dim3(row_blocks, p.ks), dim3(GV_THREADS), smem, st, p);
+  return launch_k(ctx, dec_gemv_kernel, dim3(row_blocks, p.ks), dim3(GV_THREADS), gemv_smem(Bp, p.K / p.ks), st, p);
+}
+
+int launch_ln(wxb_ctx* ctx, const float* x, const float* w, const float* b, __nv_bfloat16* y, int B, int d, cudaStream_t st) {
+  if (d % 4 || d > 1280) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder layernorm: d=%d", d);
+  return launch_k(ctx, dec_ln_kernel, dim3(ceil_div(B, 8)), dim3(256), 0, st, x, w, b, y, B, d);
 }
 
 int launch_attn(wxb_ctx* ctx, AttnParams p, int B, cudaStream_t st) {
@@ -729,7 +731,7 @@ int alloc_buffers(wxb_ctx* ctx, int B, int tok_stride, DecBuffers* o) {
   o->x = (float*)wxb_named(ctx, "dec.x", (size_t)B * d * 4);
   o->q = (float*)wxb_named(ctx, "dec.q", (size_t)B * d * 4);
   o->att = (__nv_bfloat16*)wxb_named(ctx, "dec.att", (size_t)B * d * 2);
-  o->stats = (float*)wxb_named(ctx, "dec.stats", (size_t)(d / 64) * B * 2 * 4);
+  o->xn = (__nv_bfloat16*)wxb_named(ctx, "dec.xn", (size_t)B * d * 2);
   o->gv_part_floats = (size_t)4 << 20;  // 16 MB of fp32 split-K partials
   o->gv_part = (float*)wxb_named(ctx, "dec.gv_part", o->gv_part_floats * 4);
   o->gv_ticket = (int*)wxb_named(ctx, "dec.gv_ticket", (size_t)(ceil_div(V, GV_ROWS) + 64) * 4, true);
@@ -744,7 +746,7 @@ int alloc_buffers(wxb_ctx* ctx, int B, int tok_stride, DecBuffers* o) {
   o->tokens = (int*)wxb_named(ctx, "dec.tokens", (size_t)B * tok_stride * 4);
   o->done = (int*)wxb_named(ctx, "dec.done", (size_t)B * 4);
   if (!o->x || !o->q || !o->att || !o->hid || !o->logits || !o->part || !o->sum_lp || !o->self_kv || !o->cross_kv ||
-      !o->ticket || !o->d_pos || !o->tokens || !o->done || !o->stats || !o->gv_part || !o->gv_ticket)
+      !o->ticket || !o->d_pos || !o->tokens || !o->done || !o->xn || !o->gv_part || !o->gv_ticket)
     return WXB_ERR_CUDA;
   return WXB_OK;
 }
@@ -778,7 +780,7 @@ int decoder_step(wxb_ctx* ctx, const DecBuffers& buf, float* logits_out, long lo
   if (!emb || !pos_emb || !lnf_w || !lnf_b) return WXB_ERR_STATE;
   int rc;
   if ((rc = launch_k(ctx, dec_embed_kernel, dim3(B), dim3(256), 0, st, (const int*)buf.tokens, buf.tok_stride,
-                     (const int*)buf.d_pos, emb, pos_emb, buf.x, buf.stats, d, D.n_vocab, B)) != WXB_OK)
+                     (const int*)buf.d_pos, emb, pos_emb, buf.x, d, D.n_vocab)) != WXB_OK)
     return rc;
   const float scale = 1.0f / sqrtf(64.f);
   const int cross_splits = (B * H >= 4 * ctx->sm_count) ? 1 : ((B * H >= 2 * ctx->sm_count) ? 2 : 4);
@@ -792,8 +794,8 @@ int decoder_step(wxb_ctx* ctx, const DecBuffers& buf, float* logits_out, long lo
     GemvParams g = {};
     g.B = B;
     // 1. LN1 + fused QKV, K/V appended to the self cache at pos
-    g.N = 3 * d; g.K = d; g.in_mode = IN_LN; g.in = buf.x; g.ld_in = d; g.ln_w = w.ln1_w; g.ln_b = w.ln1_b;
-    g.stats_in = buf.stats; g.n_stat_blocks = d / 64;
+    if ((rc = launch_ln(ctx, buf.x, w.ln1_w, w.ln1_b, buf.xn, B, d, st)) != WXB_OK) return rc;
+    g.N = 3 * d; g.K = d; g.in = buf.xn; g.ld_in = d;
     g.W = w.qkv_w; g.bias = w.qkv_b; g.epi = EPI_QKV; g.q_out = buf.q; g.kcache = sk; g.vcache = sv;
     g.d_pos = buf.d_pos; g.H = H; g.tmax = TX;
     if ((rc = launch_gemv(ctx, g, buf, st)) != WXB_OK) return rc;
@@ -804,13 +806,13 @@ int decoder_step(wxb_ctx* ctx, const DecBuffers& buf, float* logits_out, long lo
     if ((rc = launch_attn(ctx, a, B, st)) != WXB_OK) return rc;
     // 3. out projection + residual
     g = GemvParams{};
-    g.B = B; g.N = d; g.K = d; g.in_mode = IN_BF16; g.in = buf.att; g.ld_in = d; g.W = w.out_w; g.bias = w.out_b;
-    g.epi = EPI_RESID; g.out = buf.x; g.ldo = d; g.stats_out = buf.stats;
+    g.B = B; g.N = d; g.K = d; g.in = buf.att; g.ld_in = d; g.W = w.out_w; g.bias = w.out_b;
+    g.epi = EPI_RESID; g.out = buf.x; g.ldo = d;
     if ((rc = launch_gemv(ctx, g, buf, st)) != WXB_OK) return rc;
     // 4. LN2 + cross query
     g = GemvParams{};
-    g.B = B; g.N = d; g.K = d; g.in_mode = IN_LN; g.in = buf.x; g.ld_in = d; g.ln_w = w.ln2_w; g.ln_b = w.ln2_b;
-    g.stats_in = buf.stats; g.n_stat_blocks = d / 64;
+    if ((rc = launch_ln(ctx, buf.x, w.ln2_w, w.ln2_b, buf.xn, B, d, st)) != WXB_OK) return rc;
+    g.B = B; g.N = d; g.K = d; g.in = buf.xn; g.ld_in = d;
     g.W = w.cq_w; g.bias = w.cq_b; g.epi = EPI_F32; g.out = buf.q; g.ldo = d;
     if ((rc = launch_gemv(ctx, g, buf, st)) != WXB_OK) return rc;
     // 5. cross-attention over the 1500 encoder positions
@@ -820,25 +822,25 @@ int decoder_step(wxb_ctx* ctx, const DecBuffers& buf, float* logits_out, long lo
     if ((rc = launch_attn(ctx, a, B, st)) != WXB_OK) return rc;
     // 6. cross out projection + residual
     g = GemvParams{};
-    g.B = B; g.N = d; g.K = d; g.in_mode = IN_BF16; g.in = buf.att; g.ld_in = d; g.W = w.cout_w; g.bias = w.cout_b;
-    g.epi = EPI_RESID; g.out = buf.x; g.ldo = d; g.stats_out = buf.stats;
+    g.B = B; g.N = d; g.K = d; g.in = buf.att; g.ld_in = d; g.W = w.cout_w; g.bias = w.cout_b;
+    g.epi = EPI_RESID; g.out = buf.x; g.ldo = d;
     if ((rc = launch_gemv(ctx, g, buf, st)) != WXB_OK) return rc;
     // 7. LN3 + fc1 + GELU
     g = GemvParams{};
-    g.B = B; g.N = 4 * d; g.K = d; g.in_mode = IN_LN; g.in = buf.x; g.ld_in = d; g.ln_w = w.ln3_w; g.ln_b = w.ln3_b;
-    g.stats_in = buf.stats; g.n_stat_blocks = d / 64;
+    if ((rc = launch_ln(ctx, buf.x, w.ln3_w, w.ln3_b, buf.xn, B, d, st)) != WXB_OK) return rc;
+    g.B = B; g.N = 4 * d; g.K = d; g.in = buf.xn; g.ld_in = d;
     g.W = w.fc1_w; g.bias = w.fc1_b; g.epi = EPI_GELU_BF16; g.out = buf.hid; g.ldo = 4 * d;
     if ((rc = launch_gemv(ctx, g, buf, st)) != WXB_OK) return rc;
     // 8. fc2 + residual
     g = GemvParams{};
-    g.B = B; g.N = d; g.K = 4 * d; g.in_mode = IN_BF16; g.in = buf.hid; g.ld_in = 4 * d; g.W = w.fc2_w; g.bias = w.fc2_b;
-    g.epi = EPI_RESID; g.out = buf.x; g.ldo = d; g.stats_out = buf.stats;
+    g.B = B; g.N = d; g.K = 4 * d; g.in = buf.hid; g.ld_in = 4 * d; g.W = w.fc2_w; g.bias = w.fc2_b;
+    g.epi = EPI_RESID; g.out = buf.x; g.ldo = d;
     if ((rc = launch_gemv(ctx, g, buf, st)) != WXB_OK) return rc;
   }
   if (logits_out) {
     GemvParams g = {};
-    g.B = B; g.N = D.n_vocab; g.K = d; g.in_mode = IN_LN; g.in = buf.x; g.ld_in = d; g.ln_w = lnf_w; g.ln_b = lnf_b;
-    g.stats_in = buf.stats; g.n_stat_blocks = d / 64;
+    if ((rc = launch_ln(ctx, buf.x, lnf_w, lnf_b, buf.xn, B, d, st)) != WXB_OK) return rc;
+    g.B = B; g.N = D.n_vocab; g.K = d; g.in = buf.xn; g.ld_in = d;
     g.W = emb; g.bias = nullptr; g.epi = EPI_F32; g.out = logits_out; g.ldo = ldl;
     if ((rc = launch_gemv(ctx, g, buf, st)) != WXB_OK) return rc;
   }
@@ -907,7 +909,7 @@ int run_step(wxb_ctx* ctx, const DecBuffers& buf, int mode, const SampleParams& 
   }
   WXB_CUDA(ctx, cudaGraphLaunch(G.exec, st));
   const int L = ctx->model->dims.n_text_layer;
-  ctx->launches += 1 + 8 * L + (mode >= 1 ? 1 : 0) + (mode == 2 ? 1 : 0) + 1;
+  ctx->launches += 1 + 11 * L + (mode >= 1 ? 2 : 0) + (mode == 2 ? 1 : 0) + 1;
   return WXB_OK;
 }
 

@@ -19,6 +19,7 @@
 #include "wxb_gemm.cuh"
 #include "wxb_model.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -288,6 +289,18 @@ int launch_layernorm(wxb_ctx* ctx, const float* x, const float* w, const float* 
 
 }  // namespace
 
+int wxb_attention_tc(wxb_ctx* ctx, const __nv_bfloat16* qkv, __nv_bfloat16* vT, __nv_bfloat16* out, int B, int T, int d, int H,
+                     cudaStream_t st);  // wxb_attn.cu
+
+static bool use_tc_attention() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WXB_ATTN");
+    v = (e && e[0] == 'm') ? 0 : 1;  // WXB_ATTN=mma selects the mma.sync kernel (A/B and debugging)
+  }
+  return v == 1;
+}
+
 // exported to wxb_decoder.cu
 int wxb_launch_layernorm(wxb_ctx* ctx, const float* x, const float* w, const float* b, __nv_bfloat16* y, long long rows,
                          int d, cudaStream_t st) {
@@ -307,7 +320,8 @@ int wxb_encode_impl(wxb_ctx* ctx, const float* mel_dev, int B, __nv_bfloat16* en
   __nv_bfloat16* qkv = (__nv_bfloat16*)wxb_named(ctx, "enc.qkv", M * 3 * d * 2);
   __nv_bfloat16* att = (__nv_bfloat16*)wxb_named(ctx, "enc.att", M * d * 2);
   __nv_bfloat16* hid = (__nv_bfloat16*)wxb_named(ctx, "enc.hid", M * 4 * d * 2);
-  if (!melT || !h1 || !x || !xn || !qkv || !att || !hid) return WXB_ERR_CUDA;
+  __nv_bfloat16* vT = (__nv_bfloat16*)wxb_named(ctx, "enc.vT", (size_t)B * H * 64 * 1504 * 2);
+  if (!melT || !h1 || !x || !xn || !qkv || !att || !hid || !vT) return WXB_ERR_CUDA;
 
   const __nv_bfloat16* c1w = (const __nv_bfloat16*)wxb_weight(ctx, "enc.conv1.w");
   const float* c1b = (const float*)wxb_weight(ctx, "enc.conv1.b");
@@ -353,8 +367,12 @@ int wxb_encode_impl(wxb_ctx* ctx, const float* mel_dev, int B, __nv_bfloat16* en
       a.out = qkv; a.ldo = 3 * d;
       if ((rc = wxb_gemm_launch(ctx, a, st)) != WXB_OK) return rc;
     }
-    attention_kernel<<<dim3(ceil_div(T_AUDIO, ATT_BQ), H, B), ATT_THREADS, att_smem, st>>>(qkv, att, T_AUDIO, d, scale_log2);
-    WXB_LAUNCH_CHECK(ctx);
+    if (use_tc_attention()) {
+      if ((rc = wxb_attention_tc(ctx, qkv, vT, att, B, T_AUDIO, d, H, st)) != WXB_OK) return rc;
+    } else {
+      attention_kernel<<<dim3(ceil_div(T_AUDIO, ATT_BQ), H, B), ATT_THREADS, att_smem, st>>>(qkv, att, T_AUDIO, d, scale_log2);
+      WXB_LAUNCH_CHECK(ctx);
+    }
     {
       GemmArgs a;
       a.A = att; a.lda = d; a.M = (int)M; a.W = w.out_w; a.N = d; a.K = d; a.bias = w.out_b;

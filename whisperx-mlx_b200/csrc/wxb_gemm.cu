@@ -251,8 +251,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_tmap(wxb_ctx* ctx, CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
-              uint32_t box_inner, uint32_t box_rows) {
+}  // namespace
+
+int wxb_make_tmap_bf16(wxb_ctx* ctx, CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
+                       uint32_t box_inner, uint32_t box_rows) {
   if (!ctx->encode_tiled) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult q;
@@ -276,6 +278,8 @@ int make_tmap(wxb_ctx* ctx, CUtensorMap* tm, const void* base, uint64_t inner, u
                     (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)row_stride_bytes);
   return WXB_OK;
 }
+
+namespace {
 
 template <int BN, int STAGES>
 int launch_cfg(wxb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
@@ -313,8 +317,8 @@ int wxb_gemm_launch(wxb_ctx* ctx, const GemmArgs& a, cudaStream_t st) {
   CUtensorMap tmA, tmB;
   int rc;
   const long long lda = a.lda ? a.lda : a.K;
-  if ((rc = make_tmap(ctx, &tmA, a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)lda * 2, BK, BM)) != WXB_OK) return rc;
-  if ((rc = make_tmap(ctx, &tmB, a.W, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.K * 2, BK, BN)) != WXB_OK) return rc;
+  if ((rc = wxb_make_tmap_bf16(ctx, &tmA, a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)lda * 2, BK, BM)) != WXB_OK) return rc;
+  if ((rc = wxb_make_tmap_bf16(ctx, &tmB, a.W, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.K * 2, BK, BN)) != WXB_OK) return rc;
   if (BN == 256) return launch_cfg<256, 4>(ctx, tmA, tmB, p, st);
   return launch_cfg<128, 6>(ctx, tmA, tmB, p, st);
 }
