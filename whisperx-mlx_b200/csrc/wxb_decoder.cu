@@ -691,7 +691,7 @@ int pick_ks(wxb_ctx* ctx, int Bp, int N, int K) {
     const size_t sm = gemv_smem(Bp, K / ks);
     if (sm > GV_SMEM_MAX) continue;
     best = ks;
-    if (row_blocks * ks >= ctx->sm_count && sm <= 100 * 1024) break;
+    if (row_blocks * ks >= ctx->sm_count && (sm <= 100 * 1024 || row_blocks >= 2 * ctx->sm_count)) break;
   }
   return best;
 }
