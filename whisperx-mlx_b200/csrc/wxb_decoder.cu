@@ -27,6 +27,8 @@
 #include "wxb_model.cuh"
 #include <math.h>
 #include <stdlib.h>
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 int wxb_launch_layernorm(wxb_ctx* ctx, const float* x, const float* w, const float* b, __nv_bfloat16* y, long long rows,
                          int d, cudaStream_t st);
@@ -59,7 +61,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 enum { EPI_F32 = 0, EPI_RESID = 1, EPI_GELU_BF16 = 2, EPI_QKV = 3 };
 
 constexpr int GV_ROWS = 64;    // weight rows per CTA (8 warps x 8 rows)
-constexpr int GV_KS_MAX = 20;  // largest split-K factor the finisher unrolls
+constexpr int GV_KS_MAX = 8;   // split-K CTAs of a row block form one thread-block cluster (portable limit 8)
 
 struct GemvParams {
   int B, N, K;
@@ -76,9 +78,6 @@ struct GemvParams {
   __nv_bfloat16 *kcache, *vcache;  // [B][H][tmax][64] of this layer
   const int* d_pos;
   int H, tmax;
-  // split-K partials [ks][Bp][Npad] and per-row-block tickets (zero-initialised, self-cleaning)
-  float* part;
-  int* ticket;
 };
 
 // Weight chunk c (64 K-columns) of this lane: two 16-byte loads at k = 64c + 8t and 64c + 32 + 8t of row (n0 + g).
@@ -170,7 +169,6 @@ dec_ln_kernel(const float* __restrict__ x, const float* __restrict__ w, const fl
 __global__ void __launch_bounds__(GV_THREADS, 2)
 dec_gemv_kernel(const GemvParams p) {
   extern __shared__ __align__(16) unsigned char gv_smem[];
-  __shared__ int s_last;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int Bp = (p.B + 15) & ~15;
@@ -222,62 +220,46 @@ dec_gemv_kernel(const GemvParams p) {
       }
     }
   }
-  // ---- hand the 64-column output tile to the finisher: shared memory (ks == 1) or global partials ----
-  const int Npad = gridDim.x * GV_ROWS;
+  // ---- every K-slice CTA parks its 64-column fp32 tile in its own shared memory; the ks CTAs of a row block
+  //      form a thread-block cluster and each of them finishes a slice of the batch rows, summing the ks
+  //      tiles in rank order through distributed shared memory (deterministic, no global partials) ----
   float* s_out = reinterpret_cast<float*>(gv_smem);  // [Bp][66] overlays the activation tile
-  if (p.ks == 1) {
-    __syncthreads();  // everyone is done reading the activation tile
+  __syncthreads();  // everyone is done reading the activation tile
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
-      if (mt < MT) {
-        const int col = warp * 8 + 2 * t;
-        *reinterpret_cast<float2*>(s_out + (mt * 16 + g) * 66 + col) = make_float2(acc[mt][0], acc[mt][1]);
-        *reinterpret_cast<float2*>(s_out + (mt * 16 + g + 8) * 66 + col) = make_float2(acc[mt][2], acc[mt][3]);
-      }
-    __syncthreads();
-  } else {
-    float* mine = p.part + (size_t)blockIdx.y * Bp * Npad;
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
-      if (mt < MT) {
-        const int col = n0 + 2 * t;
-        __stcg(reinterpret_cast<float2*>(mine + (size_t)(mt * 16 + g) * Npad + col), make_float2(acc[mt][0], acc[mt][1]));
-        __stcg(reinterpret_cast<float2*>(mine + (size_t)(mt * 16 + g + 8) * Npad + col), make_float2(acc[mt][2], acc[mt][3]));
-      }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-      const int prev = atomicAdd(p.ticket + blockIdx.x, 1);
-      s_last = (prev == p.ks - 1);
-      if (s_last) p.ticket[blockIdx.x] = 0;
+  for (int mt = 0; mt < 4; ++mt)
+    if (mt < MT) {
+      const int col = warp * 8 + 2 * t;
+      *reinterpret_cast<float2*>(s_out + (mt * 16 + g) * 66 + col) = make_float2(acc[mt][0], acc[mt][1]);
+      *reinterpret_cast<float2*>(s_out + (mt * 16 + g + 8) * 66 + col) = make_float2(acc[mt][2], acc[mt][3]);
     }
+  cg::cluster_group cluster = cg::this_cluster();
+  int rank = 0;
+  if (p.ks > 1) {
+    cluster.sync();
+    rank = (int)cluster.block_rank();
+  } else {
     __syncthreads();
-    if (!s_last) return;
-    __threadfence();
   }
-  // ---- finisher: warp w handles batch rows w, w+8, ...; lane handles columns 2*lane, 2*lane+1 of the block ----
+  const float* tiles[8];
+#pragma unroll
+  for (int s2 = 0; s2 < 8; ++s2) tiles[s2] = (p.ks > 1 && s2 < p.ks) ? cluster.map_shared_rank(s_out, s2) : s_out;
   int pos = 0;
   if (p.epi == EPI_QKV) pos = *p.d_pos;
   const int n = nblk0 + 2 * lane;
   const bool ok0 = n < p.N, ok1 = n + 1 < p.N;
   const float b0 = (p.bias && ok0) ? __ldg(p.bias + n) : 0.f;
   const float b1 = (p.bias && ok1) ? __ldg(p.bias + n + 1) : 0.f;
-  for (int b = warp; b < p.B; b += 8) {
-    float v0, v1;
-    if (p.ks == 1) {
-      const float2 v = *reinterpret_cast<const float2*>(s_out + b * 66 + 2 * lane);
-      v0 = v.x; v1 = v.y;
-    } else {
-      float2 pv[GV_KS_MAX];
+  const int rows_per = (p.B + p.ks - 1) / p.ks;
+  const int row_end = min(p.B, (rank + 1) * rows_per);
+  for (int b = rank * rows_per + warp; b < row_end; b += 8) {
+    float2 pv[8];
 #pragma unroll
-      for (int s2 = 0; s2 < GV_KS_MAX; ++s2)  // all loads first (one L2 round trip), then a fixed-order sum
-        if (s2 < p.ks) pv[s2] = __ldcg(reinterpret_cast<const float2*>(p.part + ((size_t)s2 * Bp + b) * Npad + n));
-      v0 = 0.f; v1 = 0.f;
+    for (int s2 = 0; s2 < 8; ++s2)
+      if (s2 < p.ks) pv[s2] = *reinterpret_cast<const float2*>(tiles[s2] + b * 66 + 2 * lane);
+    float v0 = b0, v1 = b1;
 #pragma unroll
-      for (int s2 = 0; s2 < GV_KS_MAX; ++s2)
-        if (s2 < p.ks) { v0 += pv[s2].x; v1 += pv[s2].y; }
-    }
-    v0 += b0; v1 += b1;
+    for (int s2 = 0; s2 < 8; ++s2)
+      if (s2 < p.ks) { v0 += pv[s2].x; v1 += pv[s2].y; }
     if (p.epi == EPI_F32) {
       float* o = reinterpret_cast<float*>(p.out) + (size_t)b * p.ldo + n;
       if (ok0) o[0] = v0;
@@ -309,6 +291,7 @@ dec_gemv_kernel(const GemvParams p) {
       }
     }
   }
+  if (p.ks > 1) cluster.sync();  // peers may still be reading this CTA's tile
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -655,6 +638,8 @@ bool use_pdl() {
   return v == 1;
 }
 
+int g_cluster_y = 1;  // cluster dimension (y) of the next launch_k call
+
 template <typename... KArgs, typename... Args>
 int launch_k(wxb_ctx* ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg = {};
@@ -662,11 +647,23 @@ int launch_k(wxb_ctx* ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (use_pdl()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (g_cluster_y > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1;
+    attr[na].val.clusterDim.y = g_cluster_y;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+    g_cluster_y = 1;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = use_pdl() ? 1 : 0;
+  cfg.numAttrs = na;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
   ctx->launches++;
   if (e != cudaSuccess) return wxb_fail(ctx, WXB_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
@@ -681,13 +678,13 @@ size_t gemv_smem(int Bp, int kslice) {
   return act > outt ? act : outt;
 }
 
-// split-K factor: the smallest divisor of K/64 that yields at least one CTA per SM, keeps two CTAs per SM
-// resident (<= ~100 KB of shared memory) and stays within what the finisher unrolls
+// split-K factor = cluster size in {1,2,4,8}: the smallest that yields about one CTA per SM while the
+// activation tile stays <= ~100 KB (two CTAs per SM); very wide N (logits) never splits.
 int pick_ks(wxb_ctx* ctx, int Bp, int N, int K) {
   const int row_blocks = ceil_div(N, GV_ROWS), kc = K / 64;
   int best = 0;
-  for (int ks = 1; ks <= kc && ks <= GV_KS_MAX; ++ks) {
-    if (kc % ks) continue;
+  for (int ks = 1; ks <= GV_KS_MAX; ks *= 2) {
+    if (kc % ks) break;
     const size_t sm = gemv_smem(Bp, K / ks);
     if (sm > GV_SMEM_MAX) continue;
     best = ks;
@@ -697,17 +694,14 @@ int pick_ks(wxb_ctx* ctx, int Bp, int N, int K) {
 }
 
 int launch_gemv(wxb_ctx* ctx, GemvParams p, const DecBuffers& buf, cudaStream_t st) {
+  (void)buf;
   if (p.K % 64) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "gemv: K=%d must be a multiple of 64", p.K);
   if (p.B > 64) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "gemv: batch %d > 64", p.B);
   const int Bp = (p.B + 15) & ~15;
   p.ks = pick_ks(ctx, Bp, p.N, p.K);
   if (p.ks == 0) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "gemv: no K split of K=%d fits shared memory", p.K);
-  const int row_blocks = ceil_div(p.N, GV_ROWS);
-  if (p.ks > 1 && (size_t)p.ks * Bp * row_blocks * GV_ROWS > buf.gv_part_floats)
-    return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "gemv: split-K workspace too small (N=%d K=%d ks=%d)", p.N, p.K, p.ks);
-  p.part = buf.gv_part;
-  p.ticket = buf.gv_ticket;
-  return launch_k(ctx, dec_gemv_kernel, dim3(row_blocks, p.ks), dim3(GV_THREADS), gemv_smem(Bp, p.K / p.ks), st, p);
+  g_cluster_y = p.ks;
+  return launch_k(ctx, dec_gemv_kernel, dim3(ceil_div(p.N, GV_ROWS), p.ks), dim3(GV_THREADS), gemv_smem(Bp, p.K / p.ks), st, p);
 }
 
 int launch_ln(wxb_ctx* ctx, const float* x, const float* w, const float* b, __nv_bfloat16* y, int B, int d, cudaStream_t st) {

@@ -296,7 +296,7 @@ static bool use_tc_attention() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("WXB_ATTN");
-    v = (e && e[0] == 'm') ? 0 : 1;  // WXB_ATTN=mma selects the mma.sync kernel (A/B and debugging)
+    v = (e && e[0] == 't') ? 1 : 0;  // WXB_ATTN=tc selects the tcgen05 kernel (correct, not yet faster: see DESIGN.md)
   }
   return v == 1;
 }
