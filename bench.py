@@ -158,7 +158,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="large-v3")
     ap.add_argument("--minutes", type=float, default=30.0)
-    ap.add_argument("--batch-size", type=int, default=16)
+    ap.add_argument("--batch-size", type=int, default=60)
     ap.add_argument("--cpu-chunks", type=int, default=1)
     ap.add_argument("--sample-len", type=int, default=0, help="override the number of sampled positions (profiling only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
