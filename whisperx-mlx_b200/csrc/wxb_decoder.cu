@@ -714,7 +714,9 @@ int launch_attn(wxb_ctx* ctx, AttnParams p, int B, cudaStream_t st) {
   return launch_k(ctx, dec_attn_kernel, dim3(p.splits, p.H, B), dim3(DA_THREADS), smem, st, p);
 }
 
-int alloc_buffers(wxb_ctx* ctx, int B, int tok_stride, DecBuffers* o) {
+int alloc_buffers(wxb_ctx* ctx, int B, int tok_stride, int group, DecBuffers* o) {
+  const std::string sfx = group ? (".g" + std::to_string(group)) : std::string();
+  auto nm = [&](const char* base) { return std::string(base) + sfx; };
   const wxb_dims& D = ctx->model->dims;
   const int d = D.n_text_state, L = D.n_text_layer, H = D.n_text_head, V = D.n_vocab;
   o->B = B;
@@ -722,23 +724,23 @@ int alloc_buffers(wxb_ctx* ctx, int B, int tok_stride, DecBuffers* o) {
   if (B > 64) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: batch %d > 64 sequences per call", B);
   // opt in to the largest dynamic shared memory the GEMV may ask for; set outside graph capture
   WXB_CUDA(ctx, cudaFuncSetAttribute(dec_gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GV_SMEM_MAX));
-  o->x = (float*)wxb_named(ctx, "dec.x", (size_t)B * d * 4);
-  o->q = (float*)wxb_named(ctx, "dec.q", (size_t)B * d * 4);
-  o->att = (__nv_bfloat16*)wxb_named(ctx, "dec.att", (size_t)B * d * 2);
-  o->xn = (__nv_bfloat16*)wxb_named(ctx, "dec.xn", (size_t)B * d * 2);
+  o->x = (float*)wxb_named(ctx, nm("dec.x").c_str(), (size_t)B * d * 4);
+  o->q = (float*)wxb_named(ctx, nm("dec.q").c_str(), (size_t)B * d * 4);
+  o->att = (__nv_bfloat16*)wxb_named(ctx, nm("dec.att").c_str(), (size_t)B * d * 2);
+  o->xn = (__nv_bfloat16*)wxb_named(ctx, nm("dec.xn").c_str(), (size_t)B * d * 2);
   o->gv_part_floats = (size_t)4 << 20;  // 16 MB of fp32 split-K partials
-  o->gv_part = (float*)wxb_named(ctx, "dec.gv_part", o->gv_part_floats * 4);
-  o->gv_ticket = (int*)wxb_named(ctx, "dec.gv_ticket", (size_t)(ceil_div(V, GV_ROWS) + 64) * 4, true);
-  o->hid = (__nv_bfloat16*)wxb_named(ctx, "dec.hid", (size_t)B * 4 * d * 2);
-  o->logits = (float*)wxb_named(ctx, "dec.logits", (size_t)B * V * 4);
-  o->part = (float*)wxb_named(ctx, "dec.part", (size_t)B * H * 8 * 66 * 4);
-  o->sum_lp = (float*)wxb_named(ctx, "dec.sum_lp", (size_t)B * 4);
-  o->self_kv = (__nv_bfloat16*)wxb_named(ctx, "dec.self_kv", (size_t)L * 2 * B * H * D.n_text_ctx * 64 * 2);
-  o->cross_kv = (__nv_bfloat16*)wxb_named(ctx, "dec.cross_kv", (size_t)L * 2 * B * H * T_AUDIO * 64 * 2);
-  o->ticket = (int*)wxb_named(ctx, "dec.ticket", (size_t)B * H * 4 + 64, true);
-  o->d_pos = (int*)wxb_named(ctx, "dec.pos", 64);
-  o->tokens = (int*)wxb_named(ctx, "dec.tokens", (size_t)B * tok_stride * 4);
-  o->done = (int*)wxb_named(ctx, "dec.done", (size_t)B * 4);
+  o->gv_part = (float*)wxb_named(ctx, nm("dec.gv_part").c_str(), o->gv_part_floats * 4);
+  o->gv_ticket = (int*)wxb_named(ctx, nm("dec.gv_ticket").c_str(), (size_t)(ceil_div(V, GV_ROWS) + 64) * 4, true);
+  o->hid = (__nv_bfloat16*)wxb_named(ctx, nm("dec.hid").c_str(), (size_t)B * 4 * d * 2);
+  o->logits = (float*)wxb_named(ctx, nm("dec.logits").c_str(), (size_t)B * V * 4);
+  o->part = (float*)wxb_named(ctx, nm("dec.part").c_str(), (size_t)B * H * 8 * 66 * 4);
+  o->sum_lp = (float*)wxb_named(ctx, nm("dec.sum_lp").c_str(), (size_t)B * 4);
+  o->self_kv = (__nv_bfloat16*)wxb_named(ctx, nm("dec.self_kv").c_str(), (size_t)L * 2 * B * H * D.n_text_ctx * 64 * 2);
+  o->cross_kv = (__nv_bfloat16*)wxb_named(ctx, nm("dec.cross_kv").c_str(), (size_t)L * 2 * B * H * T_AUDIO * 64 * 2);
+  o->ticket = (int*)wxb_named(ctx, nm("dec.ticket").c_str(), (size_t)B * H * 4 + 64, true);
+  o->d_pos = (int*)wxb_named(ctx, nm("dec.pos").c_str(), 64);
+  o->tokens = (int*)wxb_named(ctx, nm("dec.tokens").c_str(), (size_t)B * tok_stride * 4);
+  o->done = (int*)wxb_named(ctx, nm("dec.done").c_str(), (size_t)B * 4);
   if (!o->x || !o->q || !o->att || !o->hid || !o->logits || !o->part || !o->sum_lp || !o->self_kv || !o->cross_kv ||
       !o->ticket || !o->d_pos || !o->tokens || !o->done || !o->xn || !o->gv_part || !o->gv_ticket)
     return WXB_ERR_CUDA;
@@ -849,7 +851,7 @@ struct StepGraph {
   void* key_ptrs[4] = {nullptr, nullptr, nullptr, nullptr};
   SampleParams sp = {};
 };
-StepGraph g_graphs[3];  // 0: prefill (no logits), 1: prefill + logits (no sampling), 2: logits + sample
+StepGraph g_graphs[2][3];  // [batch group][0: prefill (no logits), 1: prefill + logits (no sampling), 2: logits + sample]
 
 bool use_graph() {
   static int v = -1;
@@ -870,9 +872,9 @@ int enqueue_step(wxb_ctx* ctx, const DecBuffers& buf, int mode, const SamplePara
 }
 
 // Run one step of `mode`, through a cached CUDA graph when enabled.
-int run_step(wxb_ctx* ctx, const DecBuffers& buf, int mode, const SampleParams& sp, cudaStream_t st) {
+int run_step(wxb_ctx* ctx, const DecBuffers& buf, int mode, const SampleParams& sp, cudaStream_t st, int group) {
   if (!use_graph()) return enqueue_step(ctx, buf, mode, sp, st);
-  StepGraph& G = g_graphs[mode];
+  StepGraph& G = g_graphs[group][mode];
   const bool same = G.exec && G.model == (const void*)ctx->model && G.B == buf.B && G.tok_stride == buf.tok_stride &&
                     G.key_ptrs[0] == buf.x && G.key_ptrs[1] == buf.self_kv && G.key_ptrs[2] == buf.cross_kv &&
                     G.key_ptrs[3] == buf.tokens && memcmp(&G.sp, &sp, sizeof(sp)) == 0;
@@ -910,8 +912,9 @@ int run_step(wxb_ctx* ctx, const DecBuffers& buf, int mode, const SampleParams& 
 }  // namespace
 
 void wxb_decoder_reset_graphs() {
-  for (auto& G : g_graphs)
-    if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+  for (auto& row : g_graphs)
+    for (auto& G : row)
+      if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
 }
 
 extern "C" int wxb_decode_greedy(wxb_ctx* ctx, const void* enc_out_dev, int B, const int32_t* prompt_host, int prompt_len,
@@ -930,38 +933,77 @@ extern "C" int wxb_decode_greedy(wxb_ctx* ctx, const void* enc_out_dev, int B, c
   cudaStream_t st = (cudaStream_t)stream;
   WXB_CUDA(ctx, cudaSetDevice(ctx->device));
   const int stride = D.n_text_ctx + 1;
-  DecBuffers buf;
   int rc;
-  if ((rc = alloc_buffers(ctx, B, stride, &buf)) != WXB_OK) return rc;
-  // tokens[b, :prompt_len] = prompt; state reset
-  std::vector<int> init((size_t)B * stride, opts->eot);
-  for (int b = 0; b < B; ++b)
-    for (int i = 0; i < prompt_len; ++i) init[(size_t)b * stride + i] = prompt_host[i];
-  WXB_CUDA(ctx, cudaMemcpyAsync(buf.tokens, init.data(), init.size() * 4, cudaMemcpyHostToDevice, st));
-  WXB_CUDA(ctx, cudaMemsetAsync(buf.d_pos, 0, 4, st));
-  WXB_CUDA(ctx, cudaMemsetAsync(buf.done, 0, (size_t)B * 4, st));
-  WXB_CUDA(ctx, cudaMemsetAsync(buf.sum_lp, 0, (size_t)B * 4, st));
-  WXB_CUDA(ctx, cudaStreamSynchronize(st));  // `init` is pageable host memory
+  // Batch groups: with >= 32 sequences the batch is decoded as two independent halves on two private
+  // streams (own buffers, own step graphs), so one half's bandwidth-bound cross-attention overlaps the
+  // other half's latency-bound GEMV chain; the second reader of a weight matrix hits L2.
+  int ng = (B >= 32) ? 2 : 1;
+  if (const char* e = getenv("WXB_DEC_GROUPS")) ng = (atoi(e) >= 2 && B >= 2) ? 2 : 1;
+  if (B > 64 * ng) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "wxb_decode_greedy: at most %d sequences per call", 64 * ng);
+  cudaStream_t sg[2] = {st, st};
+  if (ng == 2) {
+    for (int g = 0; g < 2; ++g) {
+      if (!ctx->dec_streams[g]) {
+        cudaStream_t s2;
+        WXB_CUDA(ctx, cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+        ctx->dec_streams[g] = s2;
+      }
+      sg[g] = (cudaStream_t)ctx->dec_streams[g];
+    }
+    if (!ctx->dec_events[0])
+      for (int i = 0; i < 3; ++i) {
+        cudaEvent_t ev;
+        WXB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ctx->dec_events[i] = ev;
+      }
+  }
+  int g0[3] = {0, (ng == 2) ? (B + 1) / 2 : B, B};
+  if (ng == 1) g0[2] = B;
+  DecBuffers buf[2];
+  SampleParams sp[2];
+  for (int g = 0; g < ng; ++g) {
+    const int Bg = g0[g + 1] - g0[g];
+    if ((rc = alloc_buffers(ctx, Bg, stride, g, &buf[g])) != WXB_OK) return rc;
+  }
   wxb_dec_timing tm;
   WXB_CUDA(ctx, cudaEventCreate(&tm.e0));
   WXB_CUDA(ctx, cudaEventCreate(&tm.e1));
   WXB_CUDA(ctx, cudaEventCreate(&tm.e2));
   WXB_CUDA(ctx, cudaEventRecord(tm.e0, st));
-  if ((rc = cross_kv_precompute(ctx, (const __nv_bfloat16*)enc_out_dev, buf, st)) != WXB_OK) return rc;
-  WXB_CUDA(ctx, cudaEventRecord(tm.e1, st));
-
-  SampleParams sp = {};
-  sp.logits = buf.logits; sp.V = D.n_vocab; sp.tokens = buf.tokens; sp.stride = stride; sp.d_pos = buf.d_pos;
-  sp.prompt_len = prompt_len; sp.eot = opts->eot; sp.suppress_blank = opts->suppress_blank; sp.blank_token = opts->blank_token;
-  sp.n_suppress = opts->n_suppress; sp.suppress = opts->suppress_dev; sp.sum_logprob = buf.sum_lp; sp.done = buf.done;
+  if (ng == 2) {
+    WXB_CUDA(ctx, cudaEventRecord((cudaEvent_t)ctx->dec_events[0], st));
+    for (int g = 0; g < 2; ++g) WXB_CUDA(ctx, cudaStreamWaitEvent(sg[g], (cudaEvent_t)ctx->dec_events[0], 0));
+  }
+  std::vector<int> init((size_t)B * stride, opts->eot);
+  for (int b = 0; b < B; ++b)
+    for (int i = 0; i < prompt_len; ++i) init[(size_t)b * stride + i] = prompt_host[i];
+  const size_t enc_row = (size_t)T_AUDIO * D.n_audio_state;
+  for (int g = 0; g < ng; ++g) {
+    const int Bg = buf[g].B;
+    // tokens[b, :prompt_len] = prompt; state reset
+    WXB_CUDA(ctx, cudaMemcpyAsync(buf[g].tokens, init.data() + (size_t)g0[g] * stride, (size_t)Bg * stride * 4, cudaMemcpyHostToDevice, sg[g]));
+    WXB_CUDA(ctx, cudaMemsetAsync(buf[g].d_pos, 0, 4, sg[g]));
+    WXB_CUDA(ctx, cudaMemsetAsync(buf[g].done, 0, (size_t)Bg * 4, sg[g]));
+    WXB_CUDA(ctx, cudaMemsetAsync(buf[g].sum_lp, 0, (size_t)Bg * 4, sg[g]));
+    if ((rc = cross_kv_precompute(ctx, (const __nv_bfloat16*)enc_out_dev + (size_t)g0[g] * enc_row, buf[g], sg[g])) != WXB_OK) return rc;
+    SampleParams& s1 = sp[g];
+    s1 = SampleParams{};
+    s1.logits = buf[g].logits; s1.V = D.n_vocab; s1.tokens = buf[g].tokens; s1.stride = stride; s1.d_pos = buf[g].d_pos;
+    s1.prompt_len = prompt_len; s1.eot = opts->eot; s1.suppress_blank = opts->suppress_blank; s1.blank_token = opts->blank_token;
+    s1.n_suppress = opts->n_suppress; s1.suppress = opts->suppress_dev; s1.sum_logprob = buf[g].sum_lp; s1.done = buf[g].done;
+  }
+  for (int g = 0; g < ng; ++g) WXB_CUDA(ctx, cudaStreamSynchronize(sg[g]));  // `init` is pageable host memory
+  WXB_CUDA(ctx, cudaEventRecord(tm.e1, sg[0]));
 
   // prompt positions 0 .. prompt_len-2 (forced tokens); logits only at position 0 for no_speech_prob
   for (int pos = 0; pos < prompt_len - 1; ++pos) {
     const bool want_nsp = (pos == 0 && opts->no_speech >= 0 && no_speech_prob_dev);
-    if ((rc = run_step(ctx, buf, want_nsp ? 1 : 0, sp, st)) != WXB_OK) return rc;
-    if (want_nsp) {
-      dec_token_prob_kernel<<<B, 1024, 0, st>>>(buf.logits, D.n_vocab, opts->no_speech, no_speech_prob_dev);
-      WXB_LAUNCH_CHECK(ctx);
+    for (int g = 0; g < ng; ++g) {
+      if ((rc = run_step(ctx, buf[g], want_nsp ? 1 : 0, sp[g], sg[g], g)) != WXB_OK) return rc;
+      if (want_nsp) {
+        dec_token_prob_kernel<<<buf[g].B, 1024, 0, sg[g]>>>(buf[g].logits, D.n_vocab, opts->no_speech, no_speech_prob_dev + g0[g]);
+        WXB_LAUNCH_CHECK(ctx);
+      }
     }
   }
   const bool nsp_at_last = (prompt_len == 1 && opts->no_speech >= 0 && no_speech_prob_dev);
@@ -969,31 +1011,41 @@ extern "C" int wxb_decode_greedy(wxb_ctx* ctx, const void* enc_out_dev, int B, c
   std::vector<int> done_host(B);
   int n_sampled = 0;
   for (int i = 0; i < sample_len; ++i) {
-    if (i == 0 && nsp_at_last) {
-      // single-token prompt: the SOT position is also the first sampling position
-      if ((rc = decoder_step(ctx, buf, buf.logits, D.n_vocab, st)) != WXB_OK) return rc;
-      dec_token_prob_kernel<<<B, 1024, 0, st>>>(buf.logits, D.n_vocab, opts->no_speech, no_speech_prob_dev);
-      WXB_LAUNCH_CHECK(ctx);
-      if ((rc = launch_k(ctx, dec_sample_kernel, dim3(B), dim3(1024), 0, st, sp)) != WXB_OK) return rc;
-      if ((rc = launch_k(ctx, dec_advance_kernel, dim3(1), dim3(32), 0, st, buf.d_pos)) != WXB_OK) return rc;
-    } else {
-      if ((rc = run_step(ctx, buf, 2, sp, st)) != WXB_OK) return rc;
+    for (int g = 0; g < ng; ++g) {
+      if (i == 0 && nsp_at_last) {
+        // single-token prompt: the SOT position is also the first sampling position
+        if ((rc = decoder_step(ctx, buf[g], buf[g].logits, D.n_vocab, sg[g])) != WXB_OK) return rc;
+        dec_token_prob_kernel<<<buf[g].B, 1024, 0, sg[g]>>>(buf[g].logits, D.n_vocab, opts->no_speech, no_speech_prob_dev + g0[g]);
+        WXB_LAUNCH_CHECK(ctx);
+        if ((rc = launch_k(ctx, dec_sample_kernel, dim3(buf[g].B), dim3(1024), 0, sg[g], sp[g])) != WXB_OK) return rc;
+        if ((rc = launch_k(ctx, dec_advance_kernel, dim3(1), dim3(32), 0, sg[g], buf[g].d_pos)) != WXB_OK) return rc;
+      } else {
+        if ((rc = run_step(ctx, buf[g], 2, sp[g], sg[g], g)) != WXB_OK) return rc;
+      }
     }
     n_sampled = i + 1;
     if ((i + 1) % check_every == 0 && i + 1 < sample_len) {
-      WXB_CUDA(ctx, cudaMemcpyAsync(done_host.data(), buf.done, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-      WXB_CUDA(ctx, cudaStreamSynchronize(st));
+      for (int g = 0; g < ng; ++g)
+        WXB_CUDA(ctx, cudaMemcpyAsync(done_host.data() + g0[g], buf[g].done, (size_t)buf[g].B * 4, cudaMemcpyDeviceToHost, sg[g]));
+      for (int g = 0; g < ng; ++g) WXB_CUDA(ctx, cudaStreamSynchronize(sg[g]));
       bool all = true;
       for (int b = 0; b < B; ++b) all = all && done_host[b];
       if (all) break;  // mlx_whisper_batch_decoder.py:357
     }
   }
+  for (int g = 0; g < ng; ++g) {
+    dec_finalize_kernel<<<buf[g].B, 256, 0, sg[g]>>>(buf[g].tokens, stride, prompt_len, n_sampled, sample_len, opts->eot,
+                                                   tokens_out_dev + (size_t)g0[g] * sample_len, n_tokens_dev + g0[g]);
+    WXB_LAUNCH_CHECK(ctx);
+    WXB_CUDA(ctx, cudaMemcpyAsync(sum_logprob_dev + g0[g], buf[g].sum_lp, (size_t)buf[g].B * 4, cudaMemcpyDeviceToDevice, sg[g]));
+    if (ng == 2) {
+      WXB_CUDA(ctx, cudaEventRecord((cudaEvent_t)ctx->dec_events[1 + g], sg[g]));
+      WXB_CUDA(ctx, cudaStreamWaitEvent(st, (cudaEvent_t)ctx->dec_events[1 + g], 0));
+    }
+  }
   WXB_CUDA(ctx, cudaEventRecord(tm.e2, st));
   tm.steps = prompt_len - 1 + n_sampled;
   ctx->dec_timings.push_back(tm);
-  dec_finalize_kernel<<<B, 256, 0, st>>>(buf.tokens, stride, prompt_len, n_sampled, sample_len, opts->eot, tokens_out_dev, n_tokens_dev);
-  WXB_LAUNCH_CHECK(ctx);
-  WXB_CUDA(ctx, cudaMemcpyAsync(sum_logprob_dev, buf.sum_lp, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
   return WXB_OK;
 }
 
@@ -1029,7 +1081,7 @@ extern "C" int wxb_decoder_logits(wxb_ctx* ctx, const void* enc_out_dev, int B, 
   WXB_CUDA(ctx, cudaSetDevice(ctx->device));
   DecBuffers buf;
   int rc;
-  if ((rc = alloc_buffers(ctx, B, n_tok, &buf)) != WXB_OK) return rc;
+  if ((rc = alloc_buffers(ctx, B, n_tok, 0, &buf)) != WXB_OK) return rc;
   WXB_CUDA(ctx, cudaMemcpyAsync(buf.tokens, tokens_host, (size_t)B * n_tok * 4, cudaMemcpyHostToDevice, st));
   WXB_CUDA(ctx, cudaMemsetAsync(buf.d_pos, 0, 4, st));
   if ((rc = cross_kv_precompute(ctx, (const __nv_bfloat16*)enc_out_dev, buf, st)) != WXB_OK) return rc;
