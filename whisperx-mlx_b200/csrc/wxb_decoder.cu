@@ -305,7 +305,7 @@ struct AttnParams {
   int tkv;                      // allocated keys per (b,h)
   int n_keys;                   // used when d_pos == nullptr
   const int* d_pos;             // if set: n_keys = *d_pos + 1 (self-attention)
-  int splits, H, d;
+  int splits, H, d, B;
   float scale;
   __nv_bfloat16* out;           // [B, d] bf16 (feeds the out-projection GEMV)
   float* part;                  // [B][H][splits][66]  (m, l, o[64])
@@ -334,22 +334,28 @@ dec_attn_kernel(const AttnParams p) {
   extern __shared__ __align__(16) float da_smem[];
   float* sq = da_smem;            // [64] scaled q
   float* sst = sq + 64;           // [32 slots][66]: m, l, acc[64]
+  __shared__ int s_last;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int slot = lane >> 3, c8 = lane & 7;
-  const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const bool static_kv = (p.d_pos == nullptr);
+  const int n_units = p.splits * p.H * p.B;
+  bool first = true;
+  // persistent over work units (split, head, sequence): the cross-attention launch uses one CTA per SM so
+  // that the other batch group's GEMV chain can co-reside and overlap with this HBM stream
+  for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+  const int split = unit % p.splits, h = (unit / p.splits) % p.H, b = unit / (p.splits * p.H);
   const size_t slab = ((size_t)b * p.H + h) * p.tkv * 64;
   const __nv_bfloat16* Kb = p.K + slab;
   const __nv_bfloat16* Vb = p.V + slab;
   uint4 kA[4], vA[4], kB[4], vB[4];
   int n_keys = p.n_keys, per = 0, k0 = 0, k1 = 0;
-  const bool static_kv = (p.d_pos == nullptr);
   if (static_kv) {
     per = (n_keys + p.splits - 1) / p.splits;
     k0 = split * per;
     k1 = min(n_keys, k0 + per);
     da_load(kA, vA, Kb, Vb, k0 + warp * 4, slot, c8, k1);
   }
-  pdl_wait();
+  if (first) pdl_wait();
   if (!static_kv) {
     n_keys = *p.d_pos + 1;
     per = (n_keys + p.splits - 1) / p.splits;
@@ -359,7 +365,8 @@ dec_attn_kernel(const AttnParams p) {
   }
   if (tid < 64) sq[tid] = p.q[(size_t)b * p.d + h * 64 + tid] * p.scale;
   __syncthreads();
-  pdl_launch();
+  if (first) pdl_launch();
+  first = false;
   float qr[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) qr[j] = sq[c8 * 8 + j];
@@ -449,36 +456,38 @@ dec_attn_kernel(const AttnParams p) {
   }
   if (p.splits == 1) {
     if (tid < 64) p.out[(size_t)b * p.d + h * 64 + tid] = __float2bfloat16_rn(o / L);
-    return;
-  }
-  // ---- split-KV: publish the partial, the last CTA of this (b,h) merges ----
-  float* part = p.part + (((size_t)b * p.H + h) * p.splits) * 66;
-  if (tid < 64) {
-    part[split * 66 + 2 + tid] = o;
-    if (tid == 0) { part[split * 66] = M; part[split * 66 + 1] = L; }
-  }
-  __threadfence();
-  __syncthreads();
-  __shared__ int s_last;
-  if (tid == 0) {
-    const int prev = atomicAdd(p.ticket + b * p.H + h, 1);
-    s_last = (prev == p.splits - 1);
-    if (s_last) p.ticket[b * p.H + h] = 0;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  if (tid < 64) {
-    float MM = -INFINITY;
-    for (int s2 = 0; s2 < p.splits; ++s2) MM = fmaxf(MM, __ldcg(part + s2 * 66));
-    float LL = 0.f, OO = 0.f;
-    for (int s2 = 0; s2 < p.splits; ++s2) {
-      const float w = __expf(__ldcg(part + s2 * 66) - MM);
-      LL += w * __ldcg(part + s2 * 66 + 1);
-      OO += w * __ldcg(part + s2 * 66 + 2 + tid);
+  } else {
+    // ---- split-KV: publish the partial, the last CTA of this (b,h) merges ----
+    float* part = p.part + (((size_t)b * p.H + h) * p.splits) * 66;
+    if (tid < 64) {
+      part[split * 66 + 2 + tid] = o;
+      if (tid == 0) { part[split * 66] = M; part[split * 66 + 1] = L; }
     }
-    p.out[(size_t)b * p.d + h * 64 + tid] = __float2bfloat16_rn(OO / LL);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const int prev = atomicAdd(p.ticket + b * p.H + h, 1);
+      s_last = (prev == p.splits - 1);
+      if (s_last) p.ticket[b * p.H + h] = 0;
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      if (tid < 64) {
+        float MM = -INFINITY;
+        for (int s2 = 0; s2 < p.splits; ++s2) MM = fmaxf(MM, __ldcg(part + s2 * 66));
+        float LL = 0.f, OO = 0.f;
+        for (int s2 = 0; s2 < p.splits; ++s2) {
+          const float w = __expf(__ldcg(part + s2 * 66) - MM);
+          LL += w * __ldcg(part + s2 * 66 + 1);
+          OO += w * __ldcg(part + s2 * 66 + 2 + tid);
+        }
+        p.out[(size_t)b * p.d + h * 64 + tid] = __float2bfloat16_rn(OO / LL);
+      }
+    }
   }
+  __syncthreads();  // sq / sst are reused by the next unit
+  }  // unit loop
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -629,6 +638,16 @@ struct DecBuffers {
   size_t gv_part_floats;
 };
 
+// profiling aid only (results become meaningless): WXB_DEC_SKIP bitmask 1 = cross-attention, 2 = GEMV + LN, 4 = self-attention
+int dec_skip_mask() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WXB_DEC_SKIP");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 bool use_pdl() {
   static int v = -1;
   if (v < 0) {
@@ -638,7 +657,8 @@ bool use_pdl() {
   return v == 1;
 }
 
-int g_cluster_y = 1;  // cluster dimension (y) of the next launch_k call
+int g_cluster_y = 1;   // cluster dimension (y) of the next launch_k call
+int g_low_prio = 0;    // 1: the next launch_k call is the bandwidth stream (cross-attention) -> lowest priority
 
 template <typename... KArgs, typename... Args>
 int launch_k(wxb_ctx* ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
@@ -647,8 +667,14 @@ int launch_k(wxb_ctx* ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[3];
   int na = 0;
+  {  // chain kernels outrank the cross-attention stream of the other batch group
+    attr[na].id = cudaLaunchAttributePriority;
+    attr[na].val.priority = g_low_prio ? 0 : -1;
+    ++na;
+    g_low_prio = 0;
+  }
   if (use_pdl()) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
@@ -695,6 +721,7 @@ int pick_ks(wxb_ctx* ctx, int Bp, int N, int K) {
 
 int launch_gemv(wxb_ctx* ctx, GemvParams p, const DecBuffers& buf, cudaStream_t st) {
   (void)buf;
+  if (dec_skip_mask() & 2) return WXB_OK;
   if (p.K % 64) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "gemv: K=%d must be a multiple of 64", p.K);
   if (p.B > 64) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "gemv: batch %d > 64", p.B);
   const int Bp = (p.B + 15) & ~15;
@@ -705,13 +732,22 @@ int launch_gemv(wxb_ctx* ctx, GemvParams p, const DecBuffers& buf, cudaStream_t 
 }
 
 int launch_ln(wxb_ctx* ctx, const float* x, const float* w, const float* b, __nv_bfloat16* y, int B, int d, cudaStream_t st) {
+  if (dec_skip_mask() & 2) return WXB_OK;
   if (d % 4 || d > 1280) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder layernorm: d=%d", d);
   return launch_k(ctx, dec_ln_kernel, dim3(ceil_div(B, 8)), dim3(256), 0, st, x, w, b, y, B, d);
 }
 
 int launch_attn(wxb_ctx* ctx, AttnParams p, int B, cudaStream_t st) {
+  if (dec_skip_mask() & (p.d_pos ? 4 : 1)) return WXB_OK;
   const size_t smem = (size_t)(64 + 32 * 66) * 4;
-  return launch_k(ctx, dec_attn_kernel, dim3(p.splits, p.H, B), dim3(DA_THREADS), smem, st, p);
+  p.B = B;
+  const int n_units = p.splits * p.H * B;
+  int grid = n_units;
+  if (!p.d_pos) {  // cross-attention: persistent, one CTA per SM, lowest priority
+    grid = n_units < ctx->sm_count ? n_units : ctx->sm_count;
+    g_low_prio = 1;
+  }
+  return launch_k(ctx, dec_attn_kernel, dim3(grid), dim3(DA_THREADS), smem, st, p);
 }
 
 int alloc_buffers(wxb_ctx* ctx, int B, int tok_stride, int group, DecBuffers* o) {
@@ -779,7 +815,7 @@ int decoder_step(wxb_ctx* ctx, const DecBuffers& buf, float* logits_out, long lo
                      (const int*)buf.d_pos, emb, pos_emb, buf.x, d, D.n_vocab)) != WXB_OK)
     return rc;
   const float scale = 1.0f / sqrtf(64.f);
-  const int cross_splits = (B * H >= 4 * ctx->sm_count) ? 1 : ((B * H >= 2 * ctx->sm_count) ? 2 : 4);
+  const int cross_splits = (B * H >= 8 * ctx->sm_count) ? 1 : ((B * H >= 4 * ctx->sm_count) ? 2 : 4);
   for (int l = 0; l < L; ++l) {
     DecLayerW w;
     if ((rc = wxb_dec_layer(ctx, l, &w)) != WXB_OK) return rc;
