@@ -490,6 +490,111 @@ dec_attn_kernel(const AttnParams p) {
   }  // unit loop
 }
 
+// Causal self-attention over the <= 448 cached positions: one WARP per (sequence, head), no shared memory,
+// no block barriers.  Same lane layout as dec_attn_kernel (4 key slots x 8 lanes x 8 dims); the 4 slot
+// states are merged with shuffles at the end.
+__global__ void __launch_bounds__(256)
+dec_self_attn_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ K, const __nv_bfloat16* __restrict__ V,
+                     const int* __restrict__ d_pos, int tkv, int H, int d, int n_bh, float scale, __nv_bfloat16* __restrict__ out) {
+  pdl_wait();
+  pdl_launch();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.x * 8 + warp;
+  if (bh >= n_bh) return;
+  const int b = bh / H, h = bh - b * H;
+  const int slot = lane >> 3, c8 = lane & 7;
+  const int n_keys = *d_pos + 1;
+  const __nv_bfloat16* Kb = K + (size_t)bh * tkv * 64;
+  const __nv_bfloat16* Vb = V + (size_t)bh * tkv * 64;
+  float qr[8];
+  {
+    const float4 a = *reinterpret_cast<const float4*>(q + (size_t)b * d + h * 64 + c8 * 8);
+    const float4 c = *reinterpret_cast<const float4*>(q + (size_t)b * d + h * 64 + c8 * 8 + 4);
+    qr[0] = a.x * scale; qr[1] = a.y * scale; qr[2] = a.z * scale; qr[3] = a.w * scale;
+    qr[4] = c.x * scale; qr[5] = c.y * scale; qr[6] = c.z * scale; qr[7] = c.w * scale;
+  }
+  float m = -INFINITY, l = 0.f, acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int kb = 0; kb < n_keys; kb += 16) {
+    uint4 kv[4], vv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int key = kb + u * 4 + slot;
+      vv[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (key < n_keys) {
+        kv[u] = *reinterpret_cast<const uint4*>(Kb + (size_t)key * 64 + c8 * 8);
+        vv[u] = *reinterpret_cast<const uint4*>(Vb + (size_t)key * 64 + c8 * 8);
+      }
+    }
+    float sc4[4], mx = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int key = kb + u * 4 + slot;
+      float sdot = 0.f;
+      if (key < n_keys) {
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&kv[u]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(h2[j]);
+          sdot = fmaf(qr[2 * j], f.x, sdot);
+          sdot = fmaf(qr[2 * j + 1], f.y, sdot);
+        }
+      }
+      sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+      sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+      sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
+      sc4[u] = (key < n_keys) ? sdot : -INFINITY;
+      mx = fmaxf(mx, sc4[u]);
+    }
+    if (mx > -INFINITY) {
+      const float mn = fmaxf(m, mx);
+      const float alpha = __expf(m - mn);
+      m = mn;
+      l *= alpha;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] *= alpha;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float pr = __expf(sc4[u] - mn);
+        l += pr;
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&vv[u]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(h2[j]);
+          acc[2 * j] = fmaf(pr, f.x, acc[2 * j]);
+          acc[2 * j + 1] = fmaf(pr, f.y, acc[2 * j + 1]);
+        }
+      }
+    }
+  }
+  // merge the 4 slot states (lanes differing in bits 3 and 4)
+#pragma unroll
+  for (int o = 8; o <= 16; o <<= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+    const float l2 = __shfl_xor_sync(0xffffffffu, l, o);
+    const float mn = fmaxf(m, m2);
+    const float w1 = (m > -INFINITY) ? __expf(m - mn) : 0.f;
+    const float w2 = (m2 > -INFINITY) ? __expf(m2 - mn) : 0.f;
+    l = l * w1 + l2 * w2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float a2 = __shfl_xor_sync(0xffffffffu, acc[j], o);
+      acc[j] = acc[j] * w1 + a2 * w2;
+    }
+    m = mn;
+  }
+  if (slot == 0) {
+    const float inv = 1.f / l;
+    uint4 pk;
+    pk.x = pack_bf16(acc[0] * inv, acc[1] * inv);
+    pk.y = pack_bf16(acc[2] * inv, acc[3] * inv);
+    pk.z = pack_bf16(acc[4] * inv, acc[5] * inv);
+    pk.w = pack_bf16(acc[6] * inv, acc[7] * inv);
+    *reinterpret_cast<uint4*>(out + (size_t)b * d + h * 64 + c8 * 8) = pk;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // token embedding + learned position; sampling; bookkeeping
 // ---------------------------------------------------------------------------------------------
@@ -671,7 +776,9 @@ int launch_k(wxb_ctx* ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t
   int na = 0;
   {  // chain kernels outrank the cross-attention stream of the other batch group
     attr[na].id = cudaLaunchAttributePriority;
-    attr[na].val.priority = g_low_prio ? 0 : -1;
+    static int use_prio = -1;
+    if (use_prio < 0) { const char* e = getenv("WXB_PRIO"); use_prio = e ? atoi(e) : 1; }
+    attr[na].val.priority = (g_low_prio || !use_prio) ? 0 : -1;
     ++na;
     g_low_prio = 0;
   }
@@ -743,8 +850,10 @@ int launch_attn(wxb_ctx* ctx, AttnParams p, int B, cudaStream_t st) {
   p.B = B;
   const int n_units = p.splits * p.H * B;
   int grid = n_units;
-  if (!p.d_pos) {  // cross-attention: persistent, one CTA per SM, lowest priority
-    grid = n_units < ctx->sm_count ? n_units : ctx->sm_count;
+  if (!p.d_pos) {  // cross-attention = the bandwidth stream: lowest priority so the other group's chain kernels slip in
+    static int persist = -1;
+    if (persist < 0) { const char* e = getenv("WXB_ATTN_PERSIST"); persist = e ? atoi(e) : 0; }
+    if (persist > 0) grid = n_units < persist * ctx->sm_count ? n_units : persist * ctx->sm_count;
     g_low_prio = 1;
   }
   return launch_k(ctx, dec_attn_kernel, dim3(grid), dim3(DA_THREADS), smem, st, p);
@@ -815,7 +924,7 @@ int decoder_step(wxb_ctx* ctx, const DecBuffers& buf, float* logits_out, long lo
                      (const int*)buf.d_pos, emb, pos_emb, buf.x, d, D.n_vocab)) != WXB_OK)
     return rc;
   const float scale = 1.0f / sqrtf(64.f);
-  const int cross_splits = (B * H >= 8 * ctx->sm_count) ? 1 : ((B * H >= 4 * ctx->sm_count) ? 2 : 4);
+  const int cross_splits = (B * H >= 4 * ctx->sm_count) ? 1 : ((B * H >= 2 * ctx->sm_count) ? 2 : 4);
   for (int l = 0; l < L; ++l) {
     DecLayerW w;
     if ((rc = wxb_dec_layer(ctx, l, &w)) != WXB_OK) return rc;
@@ -831,11 +940,13 @@ int decoder_step(wxb_ctx* ctx, const DecBuffers& buf, float* logits_out, long lo
     g.W = w.qkv_w; g.bias = w.qkv_b; g.epi = EPI_QKV; g.q_out = buf.q; g.kcache = sk; g.vcache = sv;
     g.d_pos = buf.d_pos; g.H = H; g.tmax = TX;
     if ((rc = launch_gemv(ctx, g, buf, st)) != WXB_OK) return rc;
-    // 2. causal self-attention over pos+1 cached positions
+    // 2. causal self-attention over pos+1 cached positions (one warp per (b, h))
+    if (!(dec_skip_mask() & 4)) {
+      if ((rc = launch_k(ctx, dec_self_attn_kernel, dim3(ceil_div(B * H, 8)), dim3(256), 0, st, (const float*)buf.q,
+                         (const __nv_bfloat16*)sk, (const __nv_bfloat16*)sv, (const int*)buf.d_pos, TX, H, d, B * H, scale, buf.att)) != WXB_OK)
+        return rc;
+    }
     AttnParams a = {};
-    a.q = buf.q; a.K = sk; a.V = sv; a.tkv = TX; a.d_pos = buf.d_pos; a.splits = 1; a.H = H; a.d = d; a.scale = scale;
-    a.out = buf.att; a.part = buf.part; a.ticket = buf.ticket;
-    if ((rc = launch_attn(ctx, a, B, st)) != WXB_OK) return rc;
     // 3. out projection + residual
     g = GemvParams{};
     g.B = B; g.N = d; g.K = d; g.in = buf.att; g.ld_in = d; g.W = w.out_w; g.bias = w.out_b;
