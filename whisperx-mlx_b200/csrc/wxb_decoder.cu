@@ -4,717 +4,1038 @@
 //   /root/reference/mlx_whisper_batch_decoder.py:317-384 (_main_loop_batch), :267-303 (update),
 //   :386-468 (run: EOT trimming, avg_logprob), filters per SURVEY A.3 (SuppressBlank, SuppressTokens).
 //
-// One decode step is bandwidth-bound (weights once per step + cross-KV once per sequence), so every
-// kernel here is built around streaming HBM:
-//   dec_gemv_kernel    y[b,n] = sum_k act[b,k] W[n,k]: mma.sync m16n8k16 with the BATCH as the M tile
-//                      (<=16 rows, padded) and 8 weight rows as the N tile; weights are read straight
-//                      from HBM into MMA B-fragments with 16-byte loads (a K-permutation shared by the
-//                      A and B fragments makes natural row-major weights fragment-ready, no repack, no
-//                      shared-memory staging); the first weight loads are issued BEFORE the
-//                      programmatic-dependent-launch wait so they overlap the previous kernel's tail.
-//                      LayerNorm of the residual stream is fused into the activation staging, and
-//                      bias / GELU / residual add / QKV scatter into the KV cache into the epilogue.
-//   dec_attn_kernel    one CTA per (split, head, sequence): 8 lanes per key (16-byte loads, 128 B per
-//                      key row = fully coalesced), scores -> softmax -> P.V in fp32, split-KV partials
-//                      merged by the last-arriving CTA (self-cleaning ticket).
-//   dec_sample_kernel  logit filters + argmax (first max) + logsumexp + bookkeeping, one CTA per row.
-// The per-step launch sequence is captured once in a CUDA graph (position read from device memory).
+// One decode step streams ~17 GB at large-v3 / batch 60 (weights once, cross-KV once per sequence) through
+// ~350 dependent small operators.  Launch/dependency latency, not bandwidth, dominated a kernel-per-operator
+// design (measured: 8.7 us per dependent kernel, chain 3.1 ms + attention 2.9 ms per step, not overlapping),
+// so the whole step is ONE persistent cooperative kernel: one CTA per SM, operators are phases separated by
+// a grid barrier (one L2 atomic + acquire poll, ~0.5 us):
+//
+//   per layer   LN1 | QKV | self-attention | out | LN2 | cq | cross-attention | cout | LN3 | fc1 | fc2
+//   then        final LN | logits | no_speech_prob + filters + argmax + logsumexp + EOT latch
+//
+//   GEMV phases   y[b,n] = sum_k act[b,k] W[n,k]: mma.sync m16n8k16 with the BATCH as the M tile and 8 weight
+//                 rows as the N tile.  A K-permutation shared by the A and B fragments lets natural row-major
+//                 weights go from HBM straight into B fragments with 16-byte loads (no repack); up to 16 such
+//                 loads per lane are in flight (two register batches).  A CTA tile is (64*nb weight rows) x
+//                 (K / gk slice); its activation slice is cp.async'ed into shared memory.  Split-K tiles write
+//                 fp32 partials [gk][B][N]; the CONSUMER phase sums them in slice order (deterministic) together
+//                 with bias / residual / LayerNorm / q-scaling / KV-cache append, so no reduction phase exists.
+//   attention     8 lanes x 16 B per key row (128 B, fully coalesced), online softmax per 8-lane key slot,
+//                 K/V rows of the next keys requested one iteration ahead.  Cross-attention gives every CTA
+//                 the same number of whole (sequence, head) slabs; the remainder slabs are cut into pieces
+//                 whose partial states are merged by the last-arriving CTA (self-cleaning ticket).
 //
 // HBM layout (L decoder layers, B sequences, H heads, d = 64 H):
 //   self K/V  bf16 [L][2][B][H][448][64]      cross K/V bf16 [L][2][B][H][1500][64]
-//   x f32 [B,d] residual; q f32 [B,d]; att f32 [B,d]; hid bf16 [B,4d]; logits f32 [B,V]
+//   x f32 [B,d] residual; xn/att bf16 [B,d]; hid bf16 [B,4d]; part f32 [gk][B][N]; logits f32 [B,V]
 #include "wxb_gemm.cuh"
 #include "wxb_model.cuh"
+#include "wxb_tc.cuh"
 #include <math.h>
 #include <stdlib.h>
-#include <cooperative_groups.h>
-namespace cg = cooperative_groups;
+#include <string.h>
 
-int wxb_launch_layernorm(wxb_ctx* ctx, const float* x, const float* w, const float* b, __nv_bfloat16* y, long long rows,
-                         int d, cudaStream_t st);
+int wxb_make_tmap_bf16(wxb_ctx* ctx, CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
+                       uint32_t box_inner, uint32_t box_rows);  // wxb_gemm.cu
 
 namespace {
 
+using namespace wxbtc;
+
 constexpr int T_AUDIO = 1500;
-constexpr int GV_THREADS = 256;
-constexpr int GV_U = 4;  // 64-wide K chunks per register group
+constexpr int MK_THREADS = 256;
+constexpr int MK_WARPS = MK_THREADS / 32;
+constexpr int LN_V4 = 2;    // LayerNorm phase: float4 groups per thread, d <= 4 * 2 * 256
+constexpr int GK_MAX = 10;  // largest split-K factor a GEMV plan may use
+constexpr int MAX_LAYERS = 32;
+static_assert(GK_MAX + 1 <= 11, "q staging rows");
+constexpr int PROF_XA = (1 << 16) - 32;  // profile buffer: cross-attention cycle counters live behind the timestamps
 
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// ---- shared-memory plan of the persistent kernel (dynamic, 1024-byte aligned base) -------------------------
+// One region is time-shared by the two TMA rings (GEMV phases and cross-attention never overlap):
+//   GEMV ring   GV_NST stages x (A: 128 weight rows x 64 k bf16 = 16 KB | B: Bp batch rows x 64 k), 128-byte swizzle
+//   KV ring     XA_NST stages x (K: 128 keys x 64 dims bf16 = 16 KB | V: 16 KB), linear
+// followed by the attention scratch (scaled q + 32 slot states).
+constexpr int GV_ROWS = 128;                 // weight rows per tile = UMMA M
+constexpr int GV_BK = 64;                    // k per stage (one 128-byte swizzle row)
+constexpr int GV_A_BYTES = GV_ROWS * GV_BK * 2;
+constexpr int GV_NST = 6;
+constexpr int XA_KEYS = 128;
+constexpr int XA_HALF = XA_KEYS * 128;       // bytes of K (or V) per stage
+constexpr int XA_NST = 6;
+constexpr int RING_BYTES = XA_NST * 2 * XA_HALF;  // 192 KB >= GV_NST * (16 KB + 8 KB)
+constexpr int SST_BYTES = 4352;                          // [2 item parities][8 warps][66] floats, padded
+constexpr int QST_ROW = 64 * 4;                           // one q-sized row of fp32
+constexpr int QST_WARP = 11 * QST_ROW;                    // per warp: bias row + up to GK_MAX split-K partial rows
+constexpr int SCRATCH_BYTES = SST_BYTES + 8 * QST_WARP;   // attention scratch behind the ring
+constexpr size_t MK_SMEM = RING_BYTES + SCRATCH_BYTES + 1024;
+static_assert(GV_NST * (GV_A_BYTES + 64 * GV_BK * 2) <= RING_BYTES, "GEMV ring must fit the shared region");
 
-__device__ __forceinline__ void mma_16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
-  uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-  return r;
-}
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-enum { EPI_F32 = 0, EPI_RESID = 1, EPI_GELU_BF16 = 2, EPI_QKV = 3 };
-
-constexpr int GV_ROWS = 64;    // weight rows per CTA (8 warps x 8 rows)
-constexpr int GV_KS_MAX = 8;   // split-K CTAs of a row block form one thread-block cluster (portable limit 8)
-
-struct GemvParams {
-  int B, N, K;
-  int ks;                      // split-K factor across CTAs (gridDim.y); K / ks is a multiple of 64
-  const __nv_bfloat16* in;     // activations bf16 [B, K]
-  long long ld_in;
-  const __nv_bfloat16* W;
-  const float* bias;
-  int epi;
-  void* out;
-  long long ldo;
-  // EPI_QKV
-  float* q_out;
-  __nv_bfloat16 *kcache, *vcache;  // [B][H][tmax][64] of this layer
-  const int* d_pos;
-  int H, tmax;
-};
-
-// Weight chunk c (64 K-columns) of this lane: two 16-byte loads at k = 64c + 8t and 64c + 32 + 8t of row (n0 + g).
-__device__ __forceinline__ void gv_load(uint4* w, const __nv_bfloat16* wrow, int c_first, int c_end) {
-#pragma unroll
-  for (int u = 0; u < GV_U; ++u) {
-    const int c = c_first + u;
-    if (c < c_end) {
-      w[2 * u] = ldg_nc_v4(wrow + (size_t)c * 64);
-      w[2 * u + 1] = ldg_nc_v4(wrow + (size_t)c * 64 + 32);
-    }
-  }
-}
-__device__ __forceinline__ void gv_compute(float* acc, const uint4* w, const unsigned char* act_lo, const unsigned char* act_hi,
-                                           int c_first, int c_end) {
-#pragma unroll
-  for (int u = 0; u < GV_U; ++u) {
-    const int c = c_first + u;
-    if (c < c_end) {
-      const uint4 al0 = *reinterpret_cast<const uint4*>(act_lo + c * 128);
-      const uint4 ah0 = *reinterpret_cast<const uint4*>(act_hi + c * 128);
-      const uint4 al1 = *reinterpret_cast<const uint4*>(act_lo + c * 128 + 64);
-      const uint4 ah1 = *reinterpret_cast<const uint4*>(act_hi + c * 128 + 64);
-      const uint4 w0 = w[2 * u], w1 = w[2 * u + 1];
-      mma_16816(acc, al0.x, ah0.x, al0.y, ah0.y, w0.x, w0.y);
-      mma_16816(acc, al0.z, ah0.z, al0.w, ah0.w, w0.z, w0.w);
-      mma_16816(acc, al1.x, ah1.x, al1.y, ah1.y, w1.x, w1.y);
-      mma_16816(acc, al1.z, ah1.z, al1.w, ah1.w, w1.z, w1.w);
-    }
-  }
-}
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
-}
-
-// LayerNorm (eps 1e-5) of the residual stream rows: f32 [B, d] -> bf16 [B, d], one warp per row (d <= 1280)
-__global__ void __launch_bounds__(256)
-dec_ln_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-              __nv_bfloat16* __restrict__ y, int B, int d) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  const int nv = d >> 2;
-  float4 ww[10], bb[10];
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {  // parameters do not depend on the previous kernel
-    const int idx = lane + 32 * i;
-    if (idx < nv) { ww[i] = __ldg(reinterpret_cast<const float4*>(w) + idx); bb[i] = __ldg(reinterpret_cast<const float4*>(bias) + idx); }
-  }
-  pdl_wait();
-  pdl_launch();
-  if (row >= B) return;
-  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * d);
-  float4 v[10];
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    const int idx = lane + 32 * i;
-    if (idx < nv) { v[i] = xr[idx]; s += v[i].x + v[i].y + v[i].z + v[i].w; }
-  }
-  const float mean = warp_sum(s) / d;
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    const int idx = lane + 32 * i;
-    if (idx < nv) {
-      const float a = v[i].x - mean, b2 = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
-      q += a * a + b2 * b2 + c * c + e * e;
-    }
-  }
-  const float rstd = rsqrtf(warp_sum(q) / d + 1e-5f);
-  uint2* yr = reinterpret_cast<uint2*>(y + (size_t)row * d);
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    const int idx = lane + 32 * i;
-    if (idx < nv) {
-      uint2 pk;
-      pk.x = pack_bf16((v[i].x - mean) * rstd * ww[i].x + bb[i].x, (v[i].y - mean) * rstd * ww[i].y + bb[i].y);
-      pk.y = pack_bf16((v[i].z - mean) * rstd * ww[i].z + bb[i].z, (v[i].w - mean) * rstd * ww[i].w + bb[i].w);
-      yr[idx] = pk;
-    }
-  }
-}
-
-// Skinny GEMM y[B, N] = act[B, K] W[N, K]^T for B <= 64.  CTA = 64 weight rows x one K-slice; warp w owns
-// rows 8w..8w+7 and keeps its weight fragments in registers while looping over the (<= 4) 16-row batch
-// tiles, whose activations are cp.async'ed into shared memory.  gridDim.y K-slices are combined
-// deterministically: every slice publishes fp32 partials and the last-arriving CTA of a row block sums
-// them in slice order and runs the epilogue (bias / GELU / residual / QKV scatter into the KV cache).
-__global__ void __launch_bounds__(GV_THREADS, 2)
-dec_gemv_kernel(const GemvParams p) {
-  extern __shared__ __align__(16) unsigned char gv_smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int g = lane >> 2, t = lane & 3;
-  const int Bp = (p.B + 15) & ~15;
-  const int MT = Bp >> 4;
-  const int kslice = p.K / p.ks;
-  const int k_begin = blockIdx.y * kslice;
-  const int chunks = kslice >> 6;
-  const int nblk0 = blockIdx.x * GV_ROWS;
-  const int n0 = nblk0 + warp * 8;
-  const size_t row_bytes = (size_t)(kslice + 32) * 2;  // +64 B: rows g and g+1 land on different bank halves
-
-  int nrow = n0 + g;
-  if (nrow >= p.N) nrow = p.N - 1;
-  const __nv_bfloat16* wrow = p.W + (size_t)nrow * p.K + k_begin + 8 * t;
-  uint4 wa[2 * GV_U], wb[2 * GV_U];
-  gv_load(wa, wrow, 0, chunks);  // weights do not depend on the previous kernel: request them before the wait
-  pdl_wait();
-
-  // ---- stage the activation tile (B batch rows x K-slice, bf16) with 16-byte async copies ----
-  {
-    const int nv = kslice >> 3;
-    for (int idx = tid; idx < Bp * nv; idx += GV_THREADS) {
-      const int r = idx / nv, c = idx - r * nv;
-      unsigned char* dst = gv_smem + r * row_bytes + c * 16;
-      if (r < p.B) cp_async16(dst, p.in + (size_t)r * p.ld_in + k_begin + c * 8);
-      else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
-    }
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-  }
-  __syncthreads();
-  pdl_launch();
-
-  float acc[4][4];
-#pragma unroll
-  for (int mt = 0; mt < 4; ++mt) acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0.f;
-  {
-    const unsigned char* act_lo = gv_smem + g * row_bytes + 16 * t;
-    const unsigned char* act_hi = act_lo + 8 * row_bytes;
-    for (int c = 0; c < chunks; c += 2 * GV_U) {
-      if (c + GV_U < chunks) gv_load(wb, wrow, c + GV_U, chunks);
-#pragma unroll
-      for (int mt = 0; mt < 4; ++mt)
-        if (mt < MT) gv_compute(acc[mt], wa, act_lo + mt * 16 * row_bytes, act_hi + mt * 16 * row_bytes, c, chunks);
-      if (c + 2 * GV_U < chunks) gv_load(wa, wrow, c + 2 * GV_U, chunks);
-      if (c + GV_U < chunks) {
-#pragma unroll
-        for (int mt = 0; mt < 4; ++mt)
-          if (mt < MT) gv_compute(acc[mt], wb, act_lo + mt * 16 * row_bytes, act_hi + mt * 16 * row_bytes, c + GV_U, chunks);
-      }
-    }
-  }
-  // ---- every K-slice CTA parks its 64-column fp32 tile in its own shared memory; the ks CTAs of a row block
-  //      form a thread-block cluster and each of them finishes a slice of the batch rows, summing the ks
-  //      tiles in rank order through distributed shared memory (deterministic, no global partials) ----
-  float* s_out = reinterpret_cast<float*>(gv_smem);  // [Bp][66] overlays the activation tile
-  __syncthreads();  // everyone is done reading the activation tile
-#pragma unroll
-  for (int mt = 0; mt < 4; ++mt)
-    if (mt < MT) {
-      const int col = warp * 8 + 2 * t;
-      *reinterpret_cast<float2*>(s_out + (mt * 16 + g) * 66 + col) = make_float2(acc[mt][0], acc[mt][1]);
-      *reinterpret_cast<float2*>(s_out + (mt * 16 + g + 8) * 66 + col) = make_float2(acc[mt][2], acc[mt][3]);
-    }
-  cg::cluster_group cluster = cg::this_cluster();
-  int rank = 0;
-  if (p.ks > 1) {
-    cluster.sync();
-    rank = (int)cluster.block_rank();
-  } else {
-    __syncthreads();
-  }
-  const float* tiles[8];
-#pragma unroll
-  for (int s2 = 0; s2 < 8; ++s2) tiles[s2] = (p.ks > 1 && s2 < p.ks) ? cluster.map_shared_rank(s_out, s2) : s_out;
-  int pos = 0;
-  if (p.epi == EPI_QKV) pos = *p.d_pos;
-  const int n = nblk0 + 2 * lane;
-  const bool ok0 = n < p.N, ok1 = n + 1 < p.N;
-  const float b0 = (p.bias && ok0) ? __ldg(p.bias + n) : 0.f;
-  const float b1 = (p.bias && ok1) ? __ldg(p.bias + n + 1) : 0.f;
-  const int rows_per = (p.B + p.ks - 1) / p.ks;
-  const int row_end = min(p.B, (rank + 1) * rows_per);
-  for (int b = rank * rows_per + warp; b < row_end; b += 8) {
-    float2 pv[8];
-#pragma unroll
-    for (int s2 = 0; s2 < 8; ++s2)
-      if (s2 < p.ks) pv[s2] = *reinterpret_cast<const float2*>(tiles[s2] + b * 66 + 2 * lane);
-    float v0 = b0, v1 = b1;
-#pragma unroll
-    for (int s2 = 0; s2 < 8; ++s2)
-      if (s2 < p.ks) { v0 += pv[s2].x; v1 += pv[s2].y; }
-    if (p.epi == EPI_F32) {
-      float* o = reinterpret_cast<float*>(p.out) + (size_t)b * p.ldo + n;
-      if (ok0) o[0] = v0;
-      if (ok1) o[1] = v1;
-    } else if (p.epi == EPI_RESID) {
-      float* o = reinterpret_cast<float*>(p.out) + (size_t)b * p.ldo + n;
-      if (ok1) {
-        float2 cur = *reinterpret_cast<float2*>(o);
-        cur.x += v0; cur.y += v1;
-        *reinterpret_cast<float2*>(o) = cur;
-      } else if (ok0) {
-        o[0] += v0;
-      }
-    } else if (p.epi == EPI_GELU_BF16) {
-      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)b * p.ldo + n;
-      if (ok1) *reinterpret_cast<uint32_t*>(o) = pack_bf16(gelu_erf(v0), gelu_erf(v1));
-      else if (ok0) o[0] = __float2bfloat16_rn(gelu_erf(v0));
-    } else {
-      const int d = p.N / 3;  // n and n+1 share a 64-wide head block (n even)
-      if (ok0) {
-        if (n < d) {
-          *reinterpret_cast<float2*>(p.q_out + (size_t)b * d + n) = make_float2(v0, v1);
-        } else {
-          const int nn = (n < 2 * d) ? (n - d) : (n - 2 * d);
-          __nv_bfloat16* cache = (n < 2 * d) ? p.kcache : p.vcache;
-          const int h = nn >> 6, j = nn & 63;
-          *reinterpret_cast<uint32_t*>(cache + (((size_t)b * p.H + h) * p.tmax + pos) * 64 + j) = pack_bf16(v0, v1);
-        }
-      }
-    }
-  }
-  if (p.ks > 1) cluster.sync();  // peers may still be reading this CTA's tile
-}
-
-// ---------------------------------------------------------------------------------------------
-// decode attention: q f32 [B,d] against K/V bf16 [B][H][tkv][64]
-// ---------------------------------------------------------------------------------------------
-constexpr int DA_THREADS = 256;
-
-struct AttnParams {
-  const float* q;               // [B, d]
-  const __nv_bfloat16 *K, *V;   // [B][H][tkv][64]
-  int tkv;                      // allocated keys per (b,h)
-  int n_keys;                   // used when d_pos == nullptr
-  const int* d_pos;             // if set: n_keys = *d_pos + 1 (self-attention)
-  int splits, H, d, B;
-  float scale;
-  __nv_bfloat16* out;           // [B, d] bf16 (feeds the out-projection GEMV)
-  float* part;                  // [B][H][splits][66]  (m, l, o[64])
-  int* ticket;                  // [B*H], zero-initialised, self-cleaning
-};
-
-// Single pass over the keys with an online softmax per 8-lane key slot: every lane owns 8 of the 64
-// dims of its slot's keys; K and V rows of 4 keys per slot are requested together and one iteration
-// ahead (<= 16 x 16 B in flight per lane); the 32 slot states of the CTA are merged through shared
-// memory at the end.  static_kv (cross-attention): K/V do not depend on the previous kernel, so the
-// first loads are issued before the programmatic-dependent-launch wait.
-__device__ __forceinline__ void da_load(uint4* kv, uint4* vv, const __nv_bfloat16* Kb, const __nv_bfloat16* Vb, int kb, int slot,
-                                        int c8, int k1) {
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int key = kb + u * 32 + slot;
-    if (key < k1) {
-      kv[u] = ldg_nc_v4(Kb + (size_t)key * 64 + c8 * 8);
-      vv[u] = ldg_nc_v4(Vb + (size_t)key * 64 + c8 * 8);
-    }
-  }
-}
-
-__global__ void __launch_bounds__(DA_THREADS)
-dec_attn_kernel(const AttnParams p) {
-  extern __shared__ __align__(16) float da_smem[];
-  float* sq = da_smem;            // [64] scaled q
-  float* sst = sq + 64;           // [32 slots][66]: m, l, acc[64]
-  __shared__ int s_last;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int slot = lane >> 3, c8 = lane & 7;
-  const bool static_kv = (p.d_pos == nullptr);
-  const int n_units = p.splits * p.H * p.B;
-  bool first = true;
-  // persistent over work units (split, head, sequence): the cross-attention launch uses one CTA per SM so
-  // that the other batch group's GEMV chain can co-reside and overlap with this HBM stream
-  for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-  const int split = unit % p.splits, h = (unit / p.splits) % p.H, b = unit / (p.splits * p.H);
-  const size_t slab = ((size_t)b * p.H + h) * p.tkv * 64;
-  const __nv_bfloat16* Kb = p.K + slab;
-  const __nv_bfloat16* Vb = p.V + slab;
-  uint4 kA[4], vA[4], kB[4], vB[4];
-  int n_keys = p.n_keys, per = 0, k0 = 0, k1 = 0;
-  if (static_kv) {
-    per = (n_keys + p.splits - 1) / p.splits;
-    k0 = split * per;
-    k1 = min(n_keys, k0 + per);
-    da_load(kA, vA, Kb, Vb, k0 + warp * 4, slot, c8, k1);
-  }
-  if (first) pdl_wait();
-  if (!static_kv) {
-    n_keys = *p.d_pos + 1;
-    per = (n_keys + p.splits - 1) / p.splits;
-    k0 = split * per;
-    k1 = min(n_keys, k0 + per);
-    da_load(kA, vA, Kb, Vb, k0 + warp * 4, slot, c8, k1);
-  }
-  if (tid < 64) sq[tid] = p.q[(size_t)b * p.d + h * 64 + tid] * p.scale;
-  __syncthreads();
-  if (first) pdl_launch();
-  first = false;
-  float qr[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) qr[j] = sq[c8 * 8 + j];
-
-  float m = -INFINITY, l = 0.f, acc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-
-  auto consume = [&](const uint4* kv, const uint4* vv, int kb) {
-    float sc4[4];
-    float mx = -INFINITY;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int key = kb + u * 32 + slot;
-      float sdot = 0.f;
-      if (key < k1) {
-        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&kv[u]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = __bfloat1622float2(h2[j]);
-          sdot = fmaf(qr[2 * j], f.x, sdot);
-          sdot = fmaf(qr[2 * j + 1], f.y, sdot);
-        }
-      }
-      sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
-      sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
-      sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
-      sc4[u] = (key < k1) ? sdot : -INFINITY;
-      mx = fmaxf(mx, sc4[u]);
-    }
-    if (mx > -INFINITY) {  // uniform within the 8-lane slot
-      const float mn = fmaxf(m, mx);
-      const float alpha = __expf(m - mn);  // m = -inf -> 0
-      m = mn;
-      l *= alpha;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] *= alpha;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float pr = __expf(sc4[u] - mn);  // -inf -> 0
-        l += pr;
-        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&vv[u]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = __bfloat1622float2(h2[j]);
-          acc[2 * j] = fmaf(pr, f.x, acc[2 * j]);
-          acc[2 * j + 1] = fmaf(pr, f.y, acc[2 * j + 1]);
-        }
-      }
-    }
-  };
-  // masked-out V registers may hold garbage (never loaded): zero them so 0 * garbage cannot make NaN
-  auto clear = [&](uint4* vv, int kb) {
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (kb + u * 32 + slot >= k1) vv[u] = make_uint4(0u, 0u, 0u, 0u);
-  };
-  for (int kb = k0 + warp * 4; kb < k1; kb += 2 * 128) {
-    if (kb + 128 < k1) da_load(kB, vB, Kb, Vb, kb + 128, slot, c8, k1);
-    clear(vA, kb);
-    consume(kA, vA, kb);
-    if (kb + 256 < k1) da_load(kA, vA, Kb, Vb, kb + 256, slot, c8, k1);
-    if (kb + 128 < k1) {
-      clear(vB, kb + 128);
-      consume(kB, vB, kb + 128);
-    }
-  }
-  // ---- merge the 32 slot states ----
-  {
-    float* st = sst + (warp * 4 + slot) * 66;
-    if (c8 == 0) { st[0] = m; st[1] = l; }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) st[2 + c8 * 8 + j] = acc[j];
-  }
-  __syncthreads();
-  float o = 0.f, L = 0.f, M = -INFINITY;
-  if (tid < 64) {
-#pragma unroll 4
-    for (int i = 0; i < 32; ++i) M = fmaxf(M, sst[i * 66]);
-    if (M > -INFINITY) {
-      for (int i = 0; i < 32; ++i) {
-        const float w = __expf(sst[i * 66] - M);
-        L += w * sst[i * 66 + 1];
-        o += w * sst[i * 66 + 2 + tid];
-      }
-    }
-  }
-  if (p.splits == 1) {
-    if (tid < 64) p.out[(size_t)b * p.d + h * 64 + tid] = __float2bfloat16_rn(o / L);
-  } else {
-    // ---- split-KV: publish the partial, the last CTA of this (b,h) merges ----
-    float* part = p.part + (((size_t)b * p.H + h) * p.splits) * 66;
-    if (tid < 64) {
-      part[split * 66 + 2 + tid] = o;
-      if (tid == 0) { part[split * 66] = M; part[split * 66 + 1] = L; }
-    }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-      const int prev = atomicAdd(p.ticket + b * p.H + h, 1);
-      s_last = (prev == p.splits - 1);
-      if (s_last) p.ticket[b * p.H + h] = 0;
-    }
-    __syncthreads();
-    if (s_last) {
-      __threadfence();
-      if (tid < 64) {
-        float MM = -INFINITY;
-        for (int s2 = 0; s2 < p.splits; ++s2) MM = fmaxf(MM, __ldcg(part + s2 * 66));
-        float LL = 0.f, OO = 0.f;
-        for (int s2 = 0; s2 < p.splits; ++s2) {
-          const float w = __expf(__ldcg(part + s2 * 66) - MM);
-          LL += w * __ldcg(part + s2 * 66 + 1);
-          OO += w * __ldcg(part + s2 * 66 + 2 + tid);
-        }
-        p.out[(size_t)b * p.d + h * 64 + tid] = __float2bfloat16_rn(OO / LL);
-      }
-    }
-  }
-  __syncthreads();  // sq / sst are reused by the next unit
-  }  // unit loop
-}
-
-// Causal self-attention over the <= 448 cached positions: one WARP per (sequence, head), no shared memory,
-// no block barriers.  Same lane layout as dec_attn_kernel (4 key slots x 8 lanes x 8 dims); the 4 slot
-// states are merged with shuffles at the end.
-__global__ void __launch_bounds__(256)
-dec_self_attn_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ K, const __nv_bfloat16* __restrict__ V,
-                     const int* __restrict__ d_pos, int tkv, int H, int d, int n_bh, float scale, __nv_bfloat16* __restrict__ out) {
-  pdl_wait();
-  pdl_launch();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int bh = blockIdx.x * 8 + warp;
-  if (bh >= n_bh) return;
-  const int b = bh / H, h = bh - b * H;
-  const int slot = lane >> 3, c8 = lane & 7;
-  const int n_keys = *d_pos + 1;
-  const __nv_bfloat16* Kb = K + (size_t)bh * tkv * 64;
-  const __nv_bfloat16* Vb = V + (size_t)bh * tkv * 64;
-  float qr[8];
-  {
-    const float4 a = *reinterpret_cast<const float4*>(q + (size_t)b * d + h * 64 + c8 * 8);
-    const float4 c = *reinterpret_cast<const float4*>(q + (size_t)b * d + h * 64 + c8 * 8 + 4);
-    qr[0] = a.x * scale; qr[1] = a.y * scale; qr[2] = a.z * scale; qr[3] = a.w * scale;
-    qr[4] = c.x * scale; qr[5] = c.y * scale; qr[6] = c.z * scale; qr[7] = c.w * scale;
-  }
-  float m = -INFINITY, l = 0.f, acc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  for (int kb = 0; kb < n_keys; kb += 16) {
-    uint4 kv[4], vv[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int key = kb + u * 4 + slot;
-      vv[u] = make_uint4(0u, 0u, 0u, 0u);
-      if (key < n_keys) {
-        kv[u] = *reinterpret_cast<const uint4*>(Kb + (size_t)key * 64 + c8 * 8);
-        vv[u] = *reinterpret_cast<const uint4*>(Vb + (size_t)key * 64 + c8 * 8);
-      }
-    }
-    float sc4[4], mx = -INFINITY;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int key = kb + u * 4 + slot;
-      float sdot = 0.f;
-      if (key < n_keys) {
-        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&kv[u]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = __bfloat1622float2(h2[j]);
-          sdot = fmaf(qr[2 * j], f.x, sdot);
-          sdot = fmaf(qr[2 * j + 1], f.y, sdot);
-        }
-      }
-      sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
-      sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
-      sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
-      sc4[u] = (key < n_keys) ? sdot : -INFINITY;
-      mx = fmaxf(mx, sc4[u]);
-    }
-    if (mx > -INFINITY) {
-      const float mn = fmaxf(m, mx);
-      const float alpha = __expf(m - mn);
-      m = mn;
-      l *= alpha;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] *= alpha;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float pr = __expf(sc4[u] - mn);
-        l += pr;
-        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&vv[u]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = __bfloat1622float2(h2[j]);
-          acc[2 * j] = fmaf(pr, f.x, acc[2 * j]);
-          acc[2 * j + 1] = fmaf(pr, f.y, acc[2 * j + 1]);
-        }
-      }
-    }
-  }
-  // merge the 4 slot states (lanes differing in bits 3 and 4)
-#pragma unroll
-  for (int o = 8; o <= 16; o <<= 1) {
-    const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
-    const float l2 = __shfl_xor_sync(0xffffffffu, l, o);
-    const float mn = fmaxf(m, m2);
-    const float w1 = (m > -INFINITY) ? __expf(m - mn) : 0.f;
-    const float w2 = (m2 > -INFINITY) ? __expf(m2 - mn) : 0.f;
-    l = l * w1 + l2 * w2;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float a2 = __shfl_xor_sync(0xffffffffu, acc[j], o);
-      acc[j] = acc[j] * w1 + a2 * w2;
-    }
-    m = mn;
-  }
-  if (slot == 0) {
-    const float inv = 1.f / l;
-    uint4 pk;
-    pk.x = pack_bf16(acc[0] * inv, acc[1] * inv);
-    pk.y = pack_bf16(acc[2] * inv, acc[3] * inv);
-    pk.z = pack_bf16(acc[4] * inv, acc[5] * inv);
-    pk.w = pack_bf16(acc[6] * inv, acc[7] * inv);
-    *reinterpret_cast<uint4*>(out + (size_t)b * d + h * 64 + c8 * 8) = pk;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// token embedding + learned position; sampling; bookkeeping
-// ---------------------------------------------------------------------------------------------
-// x[b,:] = emb[tok[b*stride + pos]] + pos_emb[pos], pos = *d_pos
-__global__ void __launch_bounds__(256)
-dec_embed_kernel(const int* __restrict__ tok, int stride, const int* __restrict__ d_pos,
-                 const __nv_bfloat16* __restrict__ emb, const float* __restrict__ pos_emb,
-                 float* __restrict__ x, int d, int n_vocab) {
-  pdl_wait();
-  pdl_launch();
-  const int b = blockIdx.x;
-  const int pos = *d_pos;
-  int token = tok[(size_t)b * stride + pos];
-  token = min(max(token, 0), n_vocab - 1);
-  for (int i = 2 * threadIdx.x; i < d; i += 2 * blockDim.x) {
-    const __nv_bfloat162 e = *reinterpret_cast<const __nv_bfloat162*>(emb + (size_t)token * d + i);
-    const float2 pe = *reinterpret_cast<const float2*>(pos_emb + (size_t)pos * d + i);
-    *reinterpret_cast<float2*>(x + (size_t)b * d + i) = make_float2(__low2float(e) + pe.x, __high2float(e) + pe.y);
-  }
-}
-
-__global__ void dec_advance_kernel(int* d_pos) {
-  pdl_wait();
-  if (threadIdx.x == 0) *d_pos += 1;
-}
-
-// softmax probability of `token` per row (no_speech_prob at the SOT position, unfiltered)
-__global__ void dec_token_prob_kernel(const float* __restrict__ logits, int V, int token, float* __restrict__ out) {
-  __shared__ float red[32];
-  pdl_wait();
-  const float* x = logits + (size_t)blockIdx.x * V;
-  float m = -INFINITY;
-  for (int i = threadIdx.x; i < V; i += blockDim.x) m = fmaxf(m, x[i]);
-  m = warp_max(m);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-  __syncthreads();
-  m = red[0];
-  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
-  __syncthreads();
-  float s = 0.f;
-  for (int i = threadIdx.x; i < V; i += blockDim.x) s += expf(x[i] - m);
-  s = warp_sum(s);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+// Grid barrier of the cooperative launch: monotone arrival counter (zeroed by the host before the launch).
+// Arrival is a release-add (orders this CTA's earlier writes, made visible to thread 0 by the block barrier),
+// the wait an acquire-poll.  The proxy fences order the generic-proxy global writes of a phase with the TMA
+// (async-proxy) reads of the next one.  With `prof` set, CTA 0 records the global timer at every barrier exit.
+__device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& target, unsigned long long* prof, int& prof_n) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-    out[blockIdx.x] = expf(x[token] - m) / t;
+    target += gridDim.x;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+    unsigned v;
+    do {
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+    } while ((int)(v - target) < 0);
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    fence_proxy_async_all();  // thread 0 is also the TMA producer of the next phase
+    if (prof && blockIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      prof[prof_n] = t;
+    }
   }
+  ++prof_n;
+  __syncthreads();
 }
+
+enum { EPI_PART = 0, EPI_GELU_BF16 = 1, EPI_LOGITS = 2 };
+
+// plan of one GEMV phase: CTA tile = 128 weight rows x (K / gk) columns; tiles = ceil(N / 128) * gk
+struct MkGemv {
+  int N, K, gk, tiles;
+};
 
 struct SampleParams {
   float* logits;  // [B, V] (filters are applied in place)
   int V;
-  int* tokens;    // [B, stride]: prompt + sampled tokens; this step writes column pos + 1
+  int* tokens;    // [B, stride]: prompt + sampled tokens; a step at position pos writes column pos + 1
   int stride;
-  int* d_pos;
   int prompt_len;
   int eot, suppress_blank, blank_token, n_suppress;
   const int* suppress;
   float* sum_logprob;  // [B]
   int* done;           // [B] 1 once the row has emitted EOT
+  float* nsp_out;      // if set: softmax prob of nsp_token from the UNFILTERED logits of this step
+  int nsp_token;
 };
 
-// mlx_whisper_batch_decoder.py:267-303 for one row: filters, argmax, logprob accounting, EOT latch.
-__global__ void __launch_bounds__(1024)
-dec_sample_kernel(const SampleParams p) {
-  __shared__ float s_val[32];
-  __shared__ int s_idx[32];
-  pdl_wait();
-  const int b = blockIdx.x, tid = threadIdx.x;
-  float* x = p.logits + (size_t)b * p.V;
-  const int pos = *p.d_pos;
-  for (int i = tid; i < p.n_suppress; i += blockDim.x) {
-    const int id = p.suppress[i];
-    if (id >= 0 && id < p.V) x[id] = -INFINITY;
-  }
-  if (p.suppress_blank && pos == p.prompt_len - 1 && tid == 0) {
-    if (p.blank_token >= 0 && p.blank_token < p.V) x[p.blank_token] = -INFINITY;
-    x[p.eot] = -INFINITY;
-  }
+// tensor-map table (device array): per layer {qkv, out, cq, cout, fc1, fc2} weight maps, then emb, xn, att, hid, cross K/V
+enum { TM_QKV = 0, TM_OUT = 1, TM_CQ = 2, TM_COUT = 3, TM_FC1 = 4, TM_FC2 = 5, TM_PER_LAYER = 6 };
+
+struct MkParams {
+  int B, d, H, L, V, TX;
+  int mode;     // 0: no logits (forced prompt token); 1: logits; 2: logits + sampling
+  int n_steps;  // consecutive positions decoded by this launch (> 1 only in mode 2)
+  int skip;     // profiling aid (WXB_DEC_SKIP): 1 cross-attention, 2 GEMV, 4 self-attention, 8 LayerNorm, 16 cross math, 32 cross merge
+  const DecLayerW* layers;  // device array [L]
+  const CUtensorMap* maps;  // device array [6 L + 5]
+  const __nv_bfloat16* emb;
+  const float *pos_emb, *lnf_w, *lnf_b;
+  int* tokens;
+  int tok_stride;
+  int* d_pos;
+  float* x;
+  __nv_bfloat16 *xn, *att, *hid;
+  float* part;
+  __nv_bfloat16* self_kv;
+  const __nv_bfloat16* cross_kv;
+  float* logits;
+  long long ldl;
+  float* apart;  // cross-attention piece states [pieces][66]
+  int* ticket;   // [<= gridDim] zero-initialised, self-cleaning
+  unsigned* bar;
+  unsigned long long* prof;  // optional: barrier-exit timestamps of CTA 0 (WXB_DEC_PROF)
+  MkGemv g_qkv, g_dd, g_fc1, g_fc2, g_logits;
+  SampleParams sp;
+  float scale;
+};
+
+// mbarriers + ring cursors of the persistent kernel.  The cursors are advanced identically by every thread
+// (all loop bounds are CTA-uniform), so each thread holds its own consistent copy.
+struct MkSync {
+  uint64_t* gv_full;   // [GV_NST] TMA -> MMA
+  uint64_t* gv_empty;  // [GV_NST] MMA (tcgen05.commit) -> TMA
+  uint64_t* acc_full;  // [1]      MMA -> epilogue
+  uint64_t* xa_full;   // [XA_NST] bulk copies -> attention warps
+  uint64_t* xa_empty;  // [XA_NST] 8 warp arrivals -> producer
+  uint64_t* st_full;   // [2]      8 warp states of an item deposited -> merging warp
+  uint64_t* st_free;   // [2]      merging warp -> writers of the item after next
+  uint32_t gv_count;   // GEMV stages issued so far (slot = count % GV_NST, parity = (count / GV_NST) & 1)
+  uint32_t acc_count;  // accumulator hand-offs so far
+  uint32_t xa_count;   // KV stages issued so far
+  uint32_t xa_items;   // cross-attention work items finished so far
+  uint32_t tmem;       // TMEM base address (64 fp32 columns x 128 lanes)
+};
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
   __syncthreads();
-  float best = -INFINITY;
-  int bi = 0x7fffffff;
-  for (int i = tid; i < p.V; i += blockDim.x) {
-    const float v = x[i];
-    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-  }
-  if ((tid & 31) == 0) { s_val[tid >> 5] = best; s_idx[tid >> 5] = bi; }
-  __syncthreads();
-  best = s_val[0]; bi = s_idx[0];
-  for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
-    if (s_val[w] > best || (s_val[w] == best && s_idx[w] < bi)) { best = s_val[w]; bi = s_idx[w]; }
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
   float s = 0.f;
-  for (int i = tid; i < p.V; i += blockDim.x) s += expf(x[i] - best);
-  s = warp_sum(s);
-  if ((tid & 31) == 0) s_val[tid >> 5] = s;
+#pragma unroll
+  for (int w = 0; w < MK_WARPS; ++w) s += red[w];
+  return s;
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+  v = warp_max(v);
   __syncthreads();
-  if (tid == 0) {
-    float tot = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_val[w];
-    const float logprob = -logf(tot);  // x[bi] - (best + log(sum)) with x[bi] == best
-    int* row = p.tokens + (size_t)b * p.stride;
-    const int last = row[pos];
-    const bool was_eot = (last == p.eot) && (pos >= p.prompt_len);  // prompt tokens never latch
-    if (!was_eot) p.sum_logprob[b] += logprob;
-    const int next = was_eot ? p.eot : bi;
-    row[pos + 1] = next;
-    if (next == p.eot) p.done[b] = 1;
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = red[0];
+#pragma unroll
+  for (int w = 1; w < MK_WARPS; ++w) s = fmaxf(s, red[w]);
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm phase (one CTA per sequence row).  The residual row is first brought up to date:
+//   from_embed: x = emb[token] + pos_emb[pos]
+//   else:       x += bias + sum over the gk split-K partials of the previous GEMV (slice order)
+// then xn = LN(x) in bf16 (two-pass variance, eps 1e-5).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ln_phase(const MkParams& p, bool from_embed, int gk, const float* __restrict__ prev_bias,
+                                         const float* __restrict__ lw, const float* __restrict__ lb, int pos, float* red) {
+  const int tid = threadIdx.x, d = p.d, nv = d >> 2;
+  for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+    float4 v[LN_V4];
+    float s = 0.f;
+    int token = 0;
+    if (from_embed) {
+      token = __ldcg(p.tokens + (size_t)b * p.tok_stride + pos);
+      token = min(max(token, 0), p.V - 1);
+    }
+#pragma unroll
+    for (int i = 0; i < LN_V4; ++i) {
+      const int c4 = tid + MK_THREADS * i;
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c4 < nv) {
+        if (from_embed) {
+          const uint2 e = __ldg(reinterpret_cast<const uint2*>(p.emb + (size_t)token * d) + c4);
+          const float4 pe = __ldg(reinterpret_cast<const float4*>(p.pos_emb + (size_t)pos * d) + c4);
+          const float2 e0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&e.x));
+          const float2 e1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&e.y));
+          v[i] = make_float4(e0.x + pe.x, e0.y + pe.y, e1.x + pe.z, e1.y + pe.w);
+        } else {
+          // all loads of this element group are independent: one L2 round trip, then a fixed-order sum
+          float4 a = __ldcg(reinterpret_cast<const float4*>(p.x + (size_t)b * d) + c4);
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(prev_bias) + c4);
+          a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
+#pragma unroll
+          for (int k0 = 0; k0 < GK_MAX; k0 += 8) {
+            if (k0 < gk) {
+              float4 pp[8];
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks)
+                if (k0 + ks < gk) pp[ks] = __ldcg(reinterpret_cast<const float4*>(p.part + ((size_t)(k0 + ks) * p.B + b) * d) + c4);
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks)
+                if (k0 + ks < gk) { a.x += pp[ks].x; a.y += pp[ks].y; a.z += pp[ks].z; a.w += pp[ks].w; }
+            }
+          }
+          v[i] = a;
+        }
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+    }
+    float4 ww[LN_V4], wb[LN_V4];  // requested before the reductions so their latency is hidden
+#pragma unroll
+    for (int i = 0; i < LN_V4; ++i) {
+      const int c4 = tid + MK_THREADS * i;
+      if (c4 < nv) { ww[i] = __ldg(reinterpret_cast<const float4*>(lw) + c4); wb[i] = __ldg(reinterpret_cast<const float4*>(lb) + c4); }
+    }
+    const float mean = block_sum(s, red) / d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_V4; ++i) {
+      const int c4 = tid + MK_THREADS * i;
+      if (c4 < nv) {
+        const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
+        q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+      }
+    }
+    const float rstd = rsqrtf(block_sum(q, red) / d + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < LN_V4; ++i) {
+      const int c4 = tid + MK_THREADS * i;
+      if (c4 < nv) {
+        reinterpret_cast<float4*>(p.x + (size_t)b * d)[c4] = v[i];
+        uint2 pk;
+        pk.x = pack_bf16((v[i].x - mean) * rstd * ww[i].x + wb[i].x, (v[i].y - mean) * rstd * ww[i].y + wb[i].y);
+        pk.y = pack_bf16((v[i].z - mean) * rstd * ww[i].z + wb[i].z, (v[i].w - mean) * rstd * ww[i].w + wb[i].w);
+        reinterpret_cast<uint2*>(p.xn + (size_t)b * d)[c4] = pk;
+      }
+    }
   }
-  if (b == 0 && tid == 0) {
-    // every row of this step has read d_pos before any block can be this far? No: blocks are
-    // independent, so the position is advanced by dec_advance_kernel in the next launch.
+}
+
+// ---------------------------------------------------------------------------------------------
+// GEMV phase on the 5th-gen tensor cores: D[128 weight rows, Bp batch rows] = W_tile[128, Ks] act[Bp, Ks]^T.
+// The WEIGHTS are the M operand (UMMA M = 128), the batch the N operand (UMMA N = Bp = 16 MT), so a weight
+// element crosses HBM -> L2 -> shared memory (TMA, 128-byte swizzle) -> tensor core exactly once and never
+// touches a register; fp32 accumulation in TMEM.  Thread 0 is the TMA producer, lane 0 of warp 1 issues
+// tcgen05.mma, all 8 warps read the accumulator back (tcgen05.ld, lane = weight row) for the epilogue.
+// Split-K tiles write fp32 partials [ks][B][N]; their consumer phase performs the reduction.
+// ---------------------------------------------------------------------------------------------
+template <int MT>
+__device__ __forceinline__ void gemv_phase(const MkParams& p, const MkGemv& g, const CUtensorMap* wmap, const CUtensorMap* amap,
+                                           const float* __restrict__ bias, const int epi, uint8_t* ring, MkSync& sy) {
+  constexpr int Bp = 16 * MT;
+  constexpr int B_BYTES = Bp * GV_BK * 2;
+  constexpr int STAGE = GV_A_BYTES + B_BYTES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int B = p.B;
+  const int Ks = g.K / g.gk, nkb = Ks / GV_BK;
+  for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x) {
+    const int ks = tile % g.gk, rb = tile / g.gk;
+    const int k0 = ks * Ks, row0 = rb * GV_ROWS;
+    if (warp == 0 && lane == 0) {
+      // ---- TMA producer: the whole K-slice is requested as fast as ring slots free up ----
+      uint32_t c = sy.gv_count;
+      for (int kb = 0; kb < nkb; ++kb, ++c) {
+        const uint32_t slot = c % GV_NST, par = (c / GV_NST) & 1;
+        mbar_wait(sy.gv_empty + slot, par ^ 1);
+        uint8_t* sa = ring + slot * STAGE;
+        mbar_arrive_expect_tx(sy.gv_full + slot, STAGE);
+        tma_load_2d(sa, wmap, sy.gv_full + slot, k0 + kb * GV_BK, row0);
+        tma_load_2d(sa + GV_A_BYTES, amap, sy.gv_full + slot, k0 + kb * GV_BK, 0);
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ---- MMA issuer ----
+      const uint32_t idesc = make_idesc_bf16(GV_ROWS, Bp);
+      uint32_t c = sy.gv_count;
+      for (int kb = 0; kb < nkb; ++kb, ++c) {
+        const uint32_t slot = c % GV_NST, par = (c / GV_NST) & 1;
+        mbar_wait(sy.gv_full + slot, par);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(ring + slot * STAGE);
+        const uint64_t adesc = make_sw128_desc(sa);
+        const uint64_t bdesc = make_sw128_desc(sa + GV_A_BYTES);
+#pragma unroll
+        for (int k = 0; k < GV_BK / 16; ++k)  // +32 bytes along K inside the swizzle row = +2 in the address field
+          tc_mma_bf16(sy.tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+        tc_commit(sy.gv_empty + slot);
+      }
+      tc_commit(sy.acc_full);
+    }
+    sy.gv_count += nkb;
+    __syncwarp();
+    mbar_wait(sy.acc_full, sy.acc_count & 1);
+    sy.acc_count++;
+    tc_fence_after();
+    // ---- epilogue: warp w reads TMEM lanes 32 (w & 3) .. +31 (weight rows), 16-column groups j = w >> 2, + 2, .. ----
+    const int n = row0 + (warp & 3) * 32 + lane;
+    for (int j = warp >> 2; j < MT; j += 2) {
+      uint32_t v[16];
+      tc_ld_32x32_x16(sy.tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(j * 16), v);
+      tc_wait_ld();
+      if (n < g.N) {
+        if (epi == EPI_PART) {
+          float* o = p.part + ((size_t)ks * B + j * 16) * g.N + n;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (j * 16 + i < B) o[(size_t)i * g.N] = __uint_as_float(v[i]);
+        } else if (epi == EPI_GELU_BF16) {
+          const float bn = __ldg(bias + n);
+          __nv_bfloat16* o = p.hid + (size_t)(j * 16) * g.N + n;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (j * 16 + i < B) o[(size_t)i * g.N] = __float2bfloat16_rn(gelu_erf(__uint_as_float(v[i]) + bn));
+        } else {
+          float* o = p.logits + (size_t)(j * 16) * p.ldl + n;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (j * 16 + i < B) o[(size_t)i * p.ldl] = __uint_as_float(v[i]);
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // the next tile's first MMA overwrites the accumulator
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// attention pieces.  Lane layout: slot = lane >> 3 (4 key slots per warp), c8 = lane & 7 owns dims 8 c8 .. 8 c8 + 7.
+// One call consumes 4 keys per slot: key(u) = kb + u * KSTRIDE + slot, masked by key < k1.
+// ---------------------------------------------------------------------------------------------
+template <int KSTRIDE>
+__device__ __forceinline__ void att_consume(const uint4* kv, uint4* vv, int kb, int slot, int k1, const float* qr, float& m,
+                                            float& l, float* acc) {
+  float sc4[4];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int key = kb + u * KSTRIDE + slot;
+    float sdot = 0.f;
+    if (key < k1) {
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&kv[u]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(h2[j]);
+        sdot = fmaf(qr[2 * j], f.x, sdot);
+        sdot = fmaf(qr[2 * j + 1], f.y, sdot);
+      }
+    } else {
+      vv[u] = make_uint4(0u, 0u, 0u, 0u);  // never loaded: 0 * garbage must not make NaN
+    }
+    sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+    sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+    sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
+    sc4[u] = (key < k1) ? sdot : -INFINITY;
+    mx = fmaxf(mx, sc4[u]);
+  }
+  if (mx > -INFINITY) {  // uniform within the 8-lane slot
+    const float mn = fmaxf(m, mx);
+    const float alpha = __expf(m - mn);  // m = -inf -> 0
+    m = mn;
+    l *= alpha;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] *= alpha;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float pr = __expf(sc4[u] - mn);  // -inf -> 0
+      l += pr;
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&vv[u]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(h2[j]);
+        acc[2 * j] = fmaf(pr, f.x, acc[2 * j]);
+        acc[2 * j + 1] = fmaf(pr, f.y, acc[2 * j + 1]);
+      }
+    }
+  }
+}
+
+// Causal self-attention, one warp per (sequence, head).  The warp first finishes the QKV GEMV for its head
+// (sum of split-K partials + bias), appends the new K/V row to the cache, and attends over the pos cached rows
+// plus the new one (taken from registers, rounded to bf16 like its cached copy).
+__device__ __forceinline__ void self_attn_phase(const MkParams& p, int l, const float* __restrict__ qkv_b, int pos) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, slot = lane >> 3, c8 = lane & 7;
+  const int d = p.d, H = p.H, B = p.B, TX = p.TX, gk = p.g_qkv.gk, N3 = 3 * d;
+  __nv_bfloat16* sk = p.self_kv + (size_t)l * 2 * B * H * TX * 64;
+  __nv_bfloat16* sv = sk + (size_t)B * H * TX * 64;
+  for (int u0 = blockIdx.x * MK_WARPS + warp; u0 < B * H; u0 += gridDim.x * MK_WARPS) {
+    const int b = u0 / H, h = u0 - b * H;
+    const int col = h * 64 + c8 * 8;
+    float q8[8], k8[8], v8[8];
+    {
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(qkv_b + col)), a1 = __ldg(reinterpret_cast<const float4*>(qkv_b + col + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(qkv_b + d + col)), b1 = __ldg(reinterpret_cast<const float4*>(qkv_b + d + col + 4));
+      const float4 c0 = __ldg(reinterpret_cast<const float4*>(qkv_b + 2 * d + col)), c1 = __ldg(reinterpret_cast<const float4*>(qkv_b + 2 * d + col + 4));
+      q8[0] = a0.x; q8[1] = a0.y; q8[2] = a0.z; q8[3] = a0.w; q8[4] = a1.x; q8[5] = a1.y; q8[6] = a1.z; q8[7] = a1.w;
+      k8[0] = b0.x; k8[1] = b0.y; k8[2] = b0.z; k8[3] = b0.w; k8[4] = b1.x; k8[5] = b1.y; k8[6] = b1.z; k8[7] = b1.w;
+      v8[0] = c0.x; v8[1] = c0.y; v8[2] = c0.z; v8[3] = c0.w; v8[4] = c1.x; v8[5] = c1.y; v8[6] = c1.z; v8[7] = c1.w;
+    }
+    for (int ks0 = 0; ks0 < gk; ks0 += 4) {
+      // slot s fetches slice ks0 + s (6 independent 16-byte loads), then the 4 slots are summed by shuffles:
+      // one L2 round trip per 4 slices and a fixed summation order
+      float t[24];
+#pragma unroll
+      for (int j = 0; j < 24; ++j) t[j] = 0.f;
+      if (ks0 + slot < gk) {
+        const float* base = p.part + ((size_t)(ks0 + slot) * B + b) * N3 + col;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const float4 a0 = __ldcg(reinterpret_cast<const float4*>(base + j * d));
+          const float4 a1 = __ldcg(reinterpret_cast<const float4*>(base + j * d + 4));
+          t[8 * j + 0] = a0.x; t[8 * j + 1] = a0.y; t[8 * j + 2] = a0.z; t[8 * j + 3] = a0.w;
+          t[8 * j + 4] = a1.x; t[8 * j + 5] = a1.y; t[8 * j + 6] = a1.z; t[8 * j + 7] = a1.w;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 24; ++j) {
+        t[j] += __shfl_xor_sync(0xffffffffu, t[j], 8);
+        t[j] += __shfl_xor_sync(0xffffffffu, t[j], 16);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { q8[j] += t[j]; k8[j] += t[8 + j]; v8[j] += t[16 + j]; }
+    }
+    uint4 kq, vq;
+    kq.x = pack_bf16(k8[0], k8[1]); kq.y = pack_bf16(k8[2], k8[3]); kq.z = pack_bf16(k8[4], k8[5]); kq.w = pack_bf16(k8[6], k8[7]);
+    vq.x = pack_bf16(v8[0], v8[1]); vq.y = pack_bf16(v8[2], v8[3]); vq.z = pack_bf16(v8[4], v8[5]); vq.w = pack_bf16(v8[6], v8[7]);
+    const size_t slab = ((size_t)b * H + h) * TX * 64;
+    if (slot == 0) {
+      *reinterpret_cast<uint4*>(sk + slab + (size_t)pos * 64 + c8 * 8) = kq;
+      *reinterpret_cast<uint4*>(sv + slab + (size_t)pos * 64 + c8 * 8) = vq;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q8[j] *= p.scale;
+    // new key (slot 0 only)
+    float m = -INFINITY, lsum = 0.f, acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    {
+      const __nv_bfloat162* kh = reinterpret_cast<const __nv_bfloat162*>(&kq);
+      const __nv_bfloat162* vh = reinterpret_cast<const __nv_bfloat162*>(&vq);
+      float sdot = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(kh[j]);
+        sdot = fmaf(q8[2 * j], f.x, sdot);
+        sdot = fmaf(q8[2 * j + 1], f.y, sdot);
+      }
+      sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+      sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+      sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
+      if (slot == 0) {
+        m = sdot;
+        lsum = 1.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(vh[j]);
+          acc[2 * j] = f.x;
+          acc[2 * j + 1] = f.y;
+        }
+      }
+    }
+    // cached keys 0 .. pos-1 (written by earlier steps): 16 keys per iteration, next iteration's rows in flight
+    const __nv_bfloat16* Kb = sk + slab;
+    const __nv_bfloat16* Vb = sv + slab;
+    const int n = pos;
+    uint4 kA[4], vA[4], kB[4], vB[4];
+    auto sload = [&](uint4* kv, uint4* vv, int kb) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int key = kb + u * 4 + slot;
+        if (key < n) {
+          kv[u] = __ldcg(reinterpret_cast<const uint4*>(Kb + (size_t)key * 64 + c8 * 8));
+          vv[u] = __ldcg(reinterpret_cast<const uint4*>(Vb + (size_t)key * 64 + c8 * 8));
+        }
+      }
+    };
+    if (n > 0) sload(kA, vA, 0);
+    for (int kb = 0; kb < n; kb += 32) {
+      if (kb + 16 < n) sload(kB, vB, kb + 16);
+      att_consume<4>(kA, vA, kb, slot, n, q8, m, lsum, acc);
+      if (kb + 32 < n) sload(kA, vA, kb + 32);
+      if (kb + 16 < n) att_consume<4>(kB, vB, kb + 16, slot, n, q8, m, lsum, acc);
+    }
+    // merge the 4 slot states (lanes differing in bits 3 and 4)
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+      const float l2 = __shfl_xor_sync(0xffffffffu, lsum, o);
+      const float mn = fmaxf(m, m2);
+      const float w1 = (m > -INFINITY) ? __expf(m - mn) : 0.f;
+      const float w2 = (m2 > -INFINITY) ? __expf(m2 - mn) : 0.f;
+      lsum = lsum * w1 + l2 * w2;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float a2 = __shfl_xor_sync(0xffffffffu, acc[j], o);
+        acc[j] = acc[j] * w1 + a2 * w2;
+      }
+      m = mn;
+    }
+    if (slot == 0) {
+      const float inv = 1.f / lsum;
+      uint4 pk;
+      pk.x = pack_bf16(acc[0] * inv, acc[1] * inv);
+      pk.y = pack_bf16(acc[2] * inv, acc[3] * inv);
+      pk.z = pack_bf16(acc[4] * inv, acc[5] * inv);
+      pk.w = pack_bf16(acc[6] * inv, acc[7] * inv);
+      *reinterpret_cast<uint4*>(p.att + (size_t)b * d + col) = pk;
+    }
+  }
+}
+
+// Cross-attention over the 1500 encoder positions.  n_slabs = B * H (sequence, head) slabs of 192 KB K + 192 KB V.
+// Every CTA streams floor(n_slabs / G) whole slabs; the n_slabs % G remaining slabs are cut into pieces so that
+// the tail is spread over all CTAs as well.  K/V do not depend on q, so thread 0 keeps XA_NST stages of 128 keys
+// (16 KB K + 16 KB V, 2-D TMA boxes with the 128-byte swizzle, completing on an mbarrier) in flight ACROSS work
+// items: the HBM stream never drains while a slab's states are merged or the next q is assembled.
+//
+// Math on the (otherwise idle) legacy tensor pipe, one query per head: warp w owns keys 16 w .. 16 w + 15 of a stage.
+//   S = K q      mma.m16n8k16: A = K rows (ldmatrix), B column 0 = bf16 hi part of the scaled q, column 1 = its
+//                bf16 lo part (q - hi), so S = c0 + c1 carries ~16 mantissa bits of q; columns 2-7 are zero.
+//   softmax      online over 16-key blocks (scores replicated per quad, max by shuffles over the quads).
+//   O += V^T p   mma.m16n8k16: A = V^T (ldmatrix.trans, 16 dims x 16 keys), B column 0 / 1 = hi / lo part of p.
+struct XaItem {
+  int slab, k0, k1, piece, lj;
+};
+__device__ __forceinline__ XaItem xa_item(int it, int qw, int G, int P, int plen) {
+  XaItem x;
+  if (it < qw) {
+    x.slab = it * G + blockIdx.x; x.k0 = 0; x.k1 = T_AUDIO; x.piece = -1; x.lj = 0;
+  } else {
+    const int pc = (it - qw) * G + blockIdx.x;
+    x.lj = pc / P; x.piece = pc - x.lj * P;
+    x.slab = qw * G + x.lj; x.k0 = x.piece * plen; x.k1 = min(T_AUDIO, x.k0 + plen);
+  }
+  return x;
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t* r, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t* r, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// bf16 hi / lo split of two floats, packed for an MMA B fragment: sel 0 -> (hi(x), hi(y)), 1 -> (lo(x), lo(y)), else 0.
+// Branch-free (sel differs between the lanes of a warp).
+__device__ __forceinline__ uint32_t split_pack(float x, float y, int sel) {
+  const uint32_t hi = pack_bf16(x, y);  // x in the low half
+  const float hx = __uint_as_float(hi << 16), hy = __uint_as_float(hi & 0xffff0000u);
+  const uint32_t lo = pack_bf16(x - hx, y - hy);
+  return sel == 0 ? hi : (sel == 1 ? lo : 0u);
+}
+
+// One online-softmax update over NS consecutive stages (NS x 16 keys of this warp): the QK products of all
+// blocks are issued back to back (two accumulators per block), one max reduction serves all blocks, and the PV
+// products follow, so the long HMMA / shuffle latencies overlap across blocks instead of adding up per stage.
+template <int NS>
+__device__ __forceinline__ void xa_block(const uint32_t (*ka)[4][4], const uint32_t (*va)[4][4], const uint32_t (*qb)[2],
+                                         int key0, int k1, int lane, int g, int t, float& m, float& lsum, float (*o)[4]) {
+  float s[NS][2];
+#pragma unroll
+  for (int n = 0; n < NS; ++n) {
+    float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+    mma_16816(c0, ka[n][0], qb[0][0], qb[0][1]);
+    mma_16816(c1, ka[n][1], qb[1][0], qb[1][1]);
+    mma_16816(c0, ka[n][2], qb[2][0], qb[2][1]);
+    mma_16816(c1, ka[n][3], qb[3][0], qb[3][1]);
+    s[n][0] = __shfl_sync(0xffffffffu, (c0[0] + c0[1]) + (c1[0] + c1[1]), lane & ~3);
+    s[n][1] = __shfl_sync(0xffffffffu, (c0[2] + c0[3]) + (c1[2] + c1[3]), lane & ~3);
+    if (key0 + n * XA_KEYS >= k1) s[n][0] = -INFINITY;
+    if (key0 + n * XA_KEYS + 8 >= k1) s[n][1] = -INFINITY;
+  }
+  float mx = fmaxf(s[0][0], s[0][1]);
+#pragma unroll
+  for (int n = 1; n < NS; ++n) mx = fmaxf(mx, fmaxf(s[n][0], s[n][1]));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+  const float mn = fmaxf(m, mx);
+  if (mn == -INFINITY) return;  // every key of the blocks is outside the range (warp-uniform)
+  if (mn > m) {                 // warp-uniform
+    const float alpha = __expf(m - mn);  // m = -inf -> 0
+    lsum *= alpha;
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) { o[mt][0] *= alpha; o[mt][1] *= alpha; o[mt][2] *= alpha; o[mt][3] *= alpha; }
+    m = mn;
+  }
+#pragma unroll
+  for (int n = 0; n < NS; ++n) {
+    const float p0 = __expf(s[n][0] - m), p1 = __expf(s[n][1] - m);  // -inf -> 0
+    lsum += p0 + p1;  // per-quad partial sum (identical in the 4 lanes of a quad)
+    // B fragment of p: lane (g, t) needs keys 2t, 2t+1 (b0) and 2t+8, 2t+9 (b1): quads 2t and 2t+1
+    const float x0 = __shfl_sync(0xffffffffu, p0, 8 * t), x1 = __shfl_sync(0xffffffffu, p0, 8 * t + 4);
+    const float y0 = __shfl_sync(0xffffffffu, p1, 8 * t), y1 = __shfl_sync(0xffffffffu, p1, 8 * t + 4);
+    const uint32_t pb0 = split_pack(x0, x1, g), pb1 = split_pack(y0, y1, g);
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) mma_16816(o[mt], va[n][mt], pb0, pb1);
+  }
+}
+
+// The 8 warps never meet at a block barrier inside the phase: each warp assembles q for itself (and prefetches
+// the next item's), deposits its (m, l, O) state of a finished item in a double-buffered shared-memory slot and
+// moves straight on; warp (item % 8) merges the 8 states once all have arrived (mbarrier) and writes the output.
+__device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const float* __restrict__ cq_b, uint8_t* ring,
+                                                 float* scratch, MkSync& sy) {
+  float* sst = scratch;  // [2 item parities][8 warps][66]: m, l, O[64]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int B = p.B, H = p.H, d = p.d, G = gridDim.x, gk = p.g_dd.gk;
+  const CUtensorMap* kvmap = p.maps + (size_t)p.L * TM_PER_LAYER + 4;
+  const int n_slabs = B * H, qw = n_slabs / G, r = n_slabs - qw * G;
+  const int krow0 = (l * 2) * n_slabs * T_AUDIO, vrow0 = (l * 2 + 1) * n_slabs * T_AUDIO;  // rows of the [rows, 64] K/V tensor
+  int P = 0, plen = T_AUDIO;
+  if (r > 0) {
+    const int want = (G + r - 1) / r;
+    plen = (T_AUDIO + want - 1) / want;
+    P = (T_AUDIO + plen - 1) / plen;
+  }
+  const int n_items = qw + ((r > 0 && (int)blockIdx.x < r * P) ? ((r * P - 1 - (int)blockIdx.x) / G + 1) : 0);
+  // producer cursor (thread 0 only): next (item, stage-in-item) to request
+  int pit = 0, pst = 0;
+  uint32_t issued = sy.xa_count;
+  uint32_t consumed = sy.xa_count;
+  // thread 0: request stages until XA_NST are in flight or the work list is exhausted.  Opportunistic: a slot still
+  // held by a lagging warp ends the call (retried at the next one) unless fewer than `need` stages past `consumed`
+  // have been requested, i.e. this warp itself is about to wait for them.
+  auto top_up = [&](uint32_t need) {
+    while (pit < n_items && issued - consumed < (uint32_t)XA_NST) {
+      const XaItem x = xa_item(pit, qw, G, P, plen);
+      const int kk = x.k0 + pst * XA_KEYS;
+      const uint32_t sl = issued % XA_NST, par = (issued / XA_NST) & 1;
+      // never block the producer's own consumer warp: if a lagging warp still holds the slot, retry at the next call
+      if (!mbar_test(sy.xa_empty + sl, par ^ 1)) {
+        if (issued - consumed >= need) break;
+        mbar_wait(sy.xa_empty + sl, par ^ 1);
+      }
+      uint8_t* dst = ring + (size_t)sl * 2 * XA_HALF;
+      // full 128-row boxes: rows past the slab (or past the tensor: zero-filled) are masked by the consumer
+      mbar_arrive_expect_tx(sy.xa_full + sl, 2 * XA_HALF);
+      tma_load_2d(dst, kvmap, sy.xa_full + sl, 0, krow0 + x.slab * T_AUDIO + kk);
+      tma_load_2d(dst + XA_HALF, kvmap, sy.xa_full + sl, 0, vrow0 + x.slab * T_AUDIO + kk);
+      ++issued;
+      if (kk + XA_KEYS >= x.k1) { ++pit; pst = 0; } else { ++pst; }
+    }
+  };
+  if (tid == 0) top_up(0);
+  // ldmatrix lane addressing inside a 128-row x 128-byte swizzled tile (chunk' = chunk ^ (row & 7)); this warp's rows 16 w ..
+  const int rowA = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, chA = lane >> 4;         // K (non-transposed): chunk 2 j + chA
+  const int rowV = warp * 16 + (lane & 7) + ((lane >> 4) & 1) * 8, chV = (lane >> 3) & 1;   // V (transposed): chunk 2 mt + chV
+  const int sw = lane & 7;
+  // scaled q of an item = bias + split-K partials of the cq GEMV (slice order).  The rows of the NEXT item are
+  // copied asynchronously (cp.async, no registers held) into this warp's staging rows at the start of an item and
+  // summed when that item begins; every warp assembles q for itself, so no block barrier is involved.
+  float* qst = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(scratch) + SST_BYTES + warp * QST_WARP);
+  auto issue_q = [&](int it) {
+    const XaItem x = xa_item(it, qw, G, P, plen);
+    const int b = x.slab / H, h = x.slab - b * H;
+    const int half = lane >> 4, l16 = lane & 15;  // 16 lanes x 16 B = one 64-float row; two rows per pass
+    for (int r0 = 0; r0 <= gk; r0 += 2) {
+      const int row = r0 + half;  // row gk = bias, rows 0 .. gk-1 = partials
+      if (row <= gk) {
+        const float* src = (row == gk) ? (cq_b + h * 64) : (p.part + ((size_t)row * B + b) * d + h * 64);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(qst + row * 64 + l16 * 4)), "l"(src + l16 * 4));
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  auto finish_q = [&](float& q0, float& q1) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    float a0 = qst[gk * 64 + lane], a1 = qst[gk * 64 + lane + 32];
+    for (int ks = 0; ks < gk; ++ks) { a0 += qst[ks * 64 + lane]; a1 += qst[ks * 64 + lane + 32]; }
+    __syncwarp();  // all lanes have read the rows before the next issue_q overwrites them
+    q0 = a0 * p.scale;
+    q1 = a1 * p.scale;
+  };
+  if (n_items > 0) issue_q(0);
+  // WXB_DEC_PROF: cycle split of the stage loop as seen by warp 1 (and thread 0's producer work) of CTA 0
+  const bool pw = p.prof && blockIdx.x == 0;
+  long long c_wait = 0, c_math = 0, c_top = 0, c_item = 0, c_pre = 0, tA = 0, tB = 0, tP = 0;
+  const long long t_phase0 = pw ? clock64() : 0;
+  for (int it = 0; it < n_items; ++it) {
+    if (pw) tP = clock64();
+    const XaItem x = xa_item(it, qw, G, P, plen);
+    const int b = x.slab / H, h = x.slab - b * H;
+    // B fragments of q: lane (g, t) holds elements 16 j + 2 t + {0, 1} and + {8, 9}; column g = 0 hi part, g = 1 lo part
+    uint32_t qb[4][2];
+    float qn0, qn1;
+    finish_q(qn0, qn1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float src = (j < 2) ? qn0 : qn1;
+      const int e = (16 * j + 2 * t) & 31;
+      const float v0 = __shfl_sync(0xffffffffu, src, e), v1 = __shfl_sync(0xffffffffu, src, e + 1);
+      const float v8 = __shfl_sync(0xffffffffu, src, e + 8), v9 = __shfl_sync(0xffffffffu, src, e + 9);
+      qb[j][0] = split_pack(v0, v1, g);
+      qb[j][1] = split_pack(v8, v9, g);
+    }
+    if (it + 1 < n_items) issue_q(it + 1);  // in flight during this item's stream
+    float m = -INFINITY, lsum = 0.f, o[4][4];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) o[mt][0] = o[mt][1] = o[mt][2] = o[mt][3] = 0.f;
+    if (pw) c_pre += clock64() - tP;
+    for (int kk = x.k0; kk < x.k1;) {
+      const int ns = (kk + XA_KEYS < x.k1) ? 2 : 1;  // stages handled by this iteration
+      uint32_t ka[2][4][4], va[2][4][4];
+      if (tid == 0) top_up((uint32_t)ns);  // the stages about to be awaited are certainly on their way
+      if (pw) tA = clock64();
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        if (n < ns) {
+          const uint32_t sl = (consumed + n) % XA_NST, par = ((consumed + n) / XA_NST) & 1;
+          mbar_wait(sy.xa_full + sl, par);
+          const uint32_t kbase = smem_u32(ring + (size_t)sl * 2 * XA_HALF), vbase = kbase + XA_HALF;
+          // all fragments go to registers first, so the slot is released (and refilled) before the math
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ldsm_x4(ka[n][j], kbase + rowA * 128 + (((2 * j + chA) ^ sw) << 4));
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) ldsm_x4_t(va[n][mt], vbase + rowV * 128 + (((2 * mt + chV) ^ sw) << 4));
+          __syncwarp();
+          if (lane == 0) mbar_arrive(sy.xa_empty + sl);  // this warp is done reading the stage
+        }
+      }
+      consumed += ns;
+      if (pw) { tB = clock64(); c_wait += tB - tA; }
+      if (tid == 0) top_up(0);
+      if (pw) { tA = clock64(); c_top += tA - tB; }
+      const int key0 = kk + warp * 16 + g;  // this quad's keys in the first stage: key0 and key0 + 8
+      if (!(p.skip & 16)) {
+        if (ns == 2) xa_block<2>(ka, va, qb, key0, x.k1, lane, g, t, m, lsum, o);
+        else xa_block<1>(ka, va, qb, key0, x.k1, lane, g, t, m, lsum, o);
+      }
+      if (pw) { tB = clock64(); c_math += tB - tA; }
+      if (tid == 0) top_up(0);
+      kk += ns * XA_KEYS;
+    }
+    if (pw) tA = clock64();
+    // ---- deposit this warp's state; warp (item % 8) merges the 8 states and writes the output ----
+    const uint32_t gi = sy.xa_items + (uint32_t)it;  // items since kernel start: parity and phase of the state slot
+    const uint32_t ipar = gi & 1, iph = (gi >> 1) & 1;
+    lsum += __shfl_xor_sync(0xffffffffu, lsum, 4);
+    lsum += __shfl_xor_sync(0xffffffffu, lsum, 8);
+    lsum += __shfl_xor_sync(0xffffffffu, lsum, 16);
+    mbar_wait(sy.st_free + ipar, iph ^ 1);  // the merge of item gi - 2 has released this slot
+    {
+      float* st = sst + (ipar * MK_WARPS + warp) * 66;
+      if (lane == 0) { st[0] = m; st[1] = lsum; }
+      if (t == 0) {
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+          st[2 + 16 * mt + g] = o[mt][0] + o[mt][1];
+          st[2 + 16 * mt + g + 8] = o[mt][2] + o[mt][3];
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(sy.st_full + ipar);
+    if (warp == (int)(gi % MK_WARPS) && !(p.skip & 32)) {
+      mbar_wait(sy.st_full + ipar, iph);
+      const float* st = sst + (size_t)ipar * MK_WARPS * 66;
+      float M = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < MK_WARPS; ++i) M = fmaxf(M, st[i * 66]);
+      float Ls = 0.f, o0 = 0.f, o1 = 0.f;  // dims lane and lane + 32
+#pragma unroll
+      for (int i = 0; i < MK_WARPS; ++i) {
+        const float w = __expf(st[i * 66] - M);
+        Ls += w * st[i * 66 + 1];
+        o0 += w * st[i * 66 + 2 + lane];
+        o1 += w * st[i * 66 + 2 + lane + 32];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sy.st_free + ipar);
+      __nv_bfloat16* out = p.att + (size_t)b * d + h * 64;
+      if (x.piece < 0) {
+        out[lane] = __float2bfloat16_rn(o0 / Ls);
+        out[lane + 32] = __float2bfloat16_rn(o1 / Ls);
+      } else {
+        // ---- piece of a remainder slab: publish the state, the last-arriving piece merges all of them ----
+        float* part = p.apart + (size_t)x.lj * P * 66;
+        part[x.piece * 66 + 2 + lane] = o0;
+        part[x.piece * 66 + 2 + lane + 32] = o1;
+        if (lane == 0) { part[x.piece * 66] = M; part[x.piece * 66 + 1] = Ls; }
+        __threadfence();
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) {
+          const int prev = atomicAdd(p.ticket + x.lj, 1);
+          last = (prev == P - 1);
+          if (last) p.ticket[x.lj] = 0;
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+          __threadfence();
+          float MM = -INFINITY;
+          for (int s2 = 0; s2 < P; ++s2) MM = fmaxf(MM, __ldcg(part + s2 * 66));
+          float LL = 0.f, O0 = 0.f, O1 = 0.f;
+          for (int s2 = 0; s2 < P; ++s2) {
+            const float w = __expf(__ldcg(part + s2 * 66) - MM);
+            LL += w * __ldcg(part + s2 * 66 + 1);
+            O0 += w * __ldcg(part + s2 * 66 + 2 + lane);
+            O1 += w * __ldcg(part + s2 * 66 + 2 + lane + 32);
+          }
+          out[lane] = __float2bfloat16_rn(O0 / LL);
+          out[lane + 32] = __float2bfloat16_rn(O1 / LL);
+        }
+      }
+    } else if (warp == (int)(gi % MK_WARPS)) {
+      mbar_wait(sy.st_full + ipar, iph);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sy.st_free + ipar);
+    }
+    if (pw) c_item += clock64() - tA;
+  }
+  if (pw && lane == 0 && warp <= 1) {  // slots: warp 0 (with the producer) then warp 1
+    unsigned long long* dst = p.prof + PROF_XA + warp * 8;
+    dst[0] += (unsigned long long)c_wait; dst[1] += (unsigned long long)c_pre; dst[6] += (unsigned long long)(clock64() - t_phase0); dst[2] += (unsigned long long)c_top;
+    dst[3] += (unsigned long long)c_math; dst[4] += (unsigned long long)c_item; dst[5] += 1;
+  }
+  // every thread advances the uniform cursors by this CTA's work list
+  {
+    uint32_t n_st = (uint32_t)qw * ((T_AUDIO + XA_KEYS - 1) / XA_KEYS);
+    for (int it = qw; it < n_items; ++it) {
+      const XaItem x = xa_item(it, qw, G, P, plen);
+      n_st += (uint32_t)((x.k1 - x.k0 + XA_KEYS - 1) / XA_KEYS);
+    }
+    sy.xa_count += n_st;
+    sy.xa_items += (uint32_t)n_items;
+  }
+}
+
+// mlx_whisper_batch_decoder.py:267-303 for one row per CTA: (no_speech_prob from the unfiltered logits,)
+// filters, argmax (first max), logprob accounting, EOT latch.  Row loops keep 8 independent loads in flight.
+__device__ __forceinline__ void sample_phase(const SampleParams& p, int B, int pos, bool do_sample, float* red, int* red_i) {
+  const int tid = threadIdx.x;
+  constexpr int U = 8;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    float* x = p.logits + (size_t)b * p.V;
+    if (p.nsp_out) {
+      float m = -INFINITY;
+      for (int i0 = tid; i0 < p.V; i0 += MK_THREADS * U) {
+        float t[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) { const int i = i0 + MK_THREADS * j; t[j] = i < p.V ? __ldcg(x + i) : -INFINITY; }
+#pragma unroll
+        for (int j = 0; j < U; ++j) m = fmaxf(m, t[j]);
+      }
+      m = block_max(m, red);
+      float s = 0.f;
+      for (int i0 = tid; i0 < p.V; i0 += MK_THREADS * U) {
+        float t[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) { const int i = i0 + MK_THREADS * j; t[j] = i < p.V ? __ldcg(x + i) : -INFINITY; }
+#pragma unroll
+        for (int j = 0; j < U; ++j) s += expf(t[j] - m);
+      }
+      s = block_sum(s, red);
+      if (tid == 0) p.nsp_out[b] = expf(__ldcg(x + p.nsp_token) - m) / s;
+    }
+    if (!do_sample) continue;
+    __syncthreads();
+    for (int i = tid; i < p.n_suppress; i += MK_THREADS) {
+      const int id = p.suppress[i];
+      if (id >= 0 && id < p.V) x[id] = -INFINITY;
+    }
+    if (p.suppress_blank && pos == p.prompt_len - 1 && tid == 0) {
+      if (p.blank_token >= 0 && p.blank_token < p.V) x[p.blank_token] = -INFINITY;
+      x[p.eot] = -INFINITY;
+    }
+    __syncthreads();
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i0 = tid; i0 < p.V; i0 += MK_THREADS * U) {
+      float t[U];
+#pragma unroll
+      for (int j = 0; j < U; ++j) { const int i = i0 + MK_THREADS * j; t[j] = i < p.V ? __ldcg(x + i) : -INFINITY; }
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const int i = i0 + MK_THREADS * j;  // increasing within the thread: strict > keeps the first maximum
+        if (i < p.V && (t[j] > best || bi == 0x7fffffff)) { best = t[j]; bi = i; }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    __syncthreads();
+    if ((tid & 31) == 0) { red[tid >> 5] = best; red_i[tid >> 5] = bi; }
+    __syncthreads();
+    best = red[0]; bi = red_i[0];
+#pragma unroll
+    for (int w = 1; w < MK_WARPS; ++w)
+      if (red[w] > best || (red[w] == best && red_i[w] < bi)) { best = red[w]; bi = red_i[w]; }
+    float s = 0.f;
+    for (int i0 = tid; i0 < p.V; i0 += MK_THREADS * U) {
+      float t[U];
+#pragma unroll
+      for (int j = 0; j < U; ++j) { const int i = i0 + MK_THREADS * j; t[j] = i < p.V ? __ldcg(x + i) : -INFINITY; }
+#pragma unroll
+      for (int j = 0; j < U; ++j) s += expf(t[j] - best);
+    }
+    s = block_sum(s, red);
+    if (tid == 0) {
+      const float logprob = -logf(s);  // x[bi] - (best + log(sum)) with x[bi] == best
+      int* row = p.tokens + (size_t)b * p.stride;
+      const int last = __ldcg(row + pos);
+      const bool was_eot = (last == p.eot) && (pos >= p.prompt_len);  // prompt tokens never latch
+      if (!was_eot) p.sum_logprob[b] += logprob;
+      const int next = was_eot ? p.eot : bi;
+      row[pos + 1] = next;
+      if (next == p.eot) p.done[b] = 1;
+    }
+    __syncthreads();
+  }
+}
+
+// phase kinds of the step schedule: 11 per layer, then final LN | logits | sampling
+enum { PH_LN = 0, PH_GEMV = 1, PH_SELF = 2, PH_CROSS = 3, PH_SAMPLE = 4 };
+
+template <int MT>
+__global__ void __launch_bounds__(MK_THREADS, 1) dec_step_kernel(const __grid_constant__ MkParams p) {
+  extern __shared__ uint8_t mk_smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(mk_smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* scratch = reinterpret_cast<float*>(ring + RING_BYTES);
+  __shared__ float red[MK_WARPS];
+  __shared__ int red_i[MK_WARPS];
+  __shared__ __align__(8) uint64_t bars[2 * GV_NST + 1 + 2 * XA_NST + 4];
+  __shared__ uint32_t tmem_slot;
+  __shared__ DecLayerW s_layers[MAX_LAYERS];  // pointer table of every layer: no dependent global load per phase
+  for (int i = threadIdx.x; i < p.L * (int)(sizeof(DecLayerW) / 8); i += MK_THREADS)
+    reinterpret_cast<unsigned long long*>(s_layers)[i] = reinterpret_cast<const unsigned long long*>(p.layers)[i];
+  const int warp = threadIdx.x >> 5;
+  MkSync sy;
+  sy.gv_full = bars; sy.gv_empty = bars + GV_NST; sy.acc_full = bars + 2 * GV_NST;
+  sy.xa_full = bars + 2 * GV_NST + 1; sy.xa_empty = sy.xa_full + XA_NST;
+  sy.st_full = sy.xa_empty + XA_NST; sy.st_free = sy.st_full + 2;
+  sy.gv_count = 0; sy.acc_count = 0; sy.xa_count = 0; sy.xa_items = 0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < GV_NST; ++i) { mbar_init(sy.gv_full + i, 1); mbar_init(sy.gv_empty + i, 1); }
+    mbar_init(sy.acc_full, 1);
+    for (int i = 0; i < XA_NST; ++i) { mbar_init(sy.xa_full + i, 1); mbar_init(sy.xa_empty + i, MK_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(sy.st_full + i, MK_WARPS); mbar_init(sy.st_free + i, 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) tmem_alloc(&tmem_slot, 64);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  sy.tmem = tmem_slot;
+
+  unsigned bar_target = 0;
+  int prof_n = 0;
+  const int pos0 = *p.d_pos;  // written only after the last barrier of this launch
+  const int tail = (p.mode >= 1 ? 2 : 0) + ((p.mode == 2 || p.sp.nsp_out) ? 1 : 0);
+  const int n_ph = 11 * p.L + tail;
+  for (int s = 0; s < p.n_steps; ++s) {
+    const int pos = pos0 + s;
+    for (int ph = 0; ph < n_ph; ++ph) {
+      int l = ph / 11, k = ph - 11 * l;
+      if (l >= p.L) { k = 11 + (ph - 11 * p.L); l = p.L - 1; }
+      const DecLayerW& w = s_layers[l];
+      // k: 0 LN1 | 1 QKV | 2 self-attention | 3 out | 4 LN2 | 5 cq | 6 cross-attention | 7 cout | 8 LN3 | 9 fc1 | 10 fc2
+      //    11 final LN | 12 logits | 13 (no_speech_prob,) filters + sampling
+      const int kind = (k == 0 || k == 4 || k == 8 || k == 11) ? PH_LN : (k == 2) ? PH_SELF : (k == 6) ? PH_CROSS : (k == 13) ? PH_SAMPLE : PH_GEMV;
+      if (kind == PH_LN) {
+        if (!(p.skip & 8)) {
+          // the LayerNorm phase first folds the previous GEMV's split-K partials (+ bias) into the residual row
+          const bool from_embed = (k == 0 && l == 0);
+          const int gk = (k == 0 || k == 11) ? p.g_fc2.gk : p.g_dd.gk;
+          const float* pb = (k == 0) ? (l > 0 ? s_layers[l - 1].fc2_b : nullptr) : (k == 4) ? w.out_b : (k == 8) ? w.cout_b : w.fc2_b;
+          const float* lw = (k == 0) ? w.ln1_w : (k == 4) ? w.ln2_w : (k == 8) ? w.ln3_w : p.lnf_w;
+          const float* lb = (k == 0) ? w.ln1_b : (k == 4) ? w.ln2_b : (k == 8) ? w.ln3_b : p.lnf_b;
+          ln_phase(p, from_embed, gk, pb, lw, lb, pos, red);
+        }
+      } else if (kind == PH_GEMV) {
+        if (!(p.skip & 2)) {
+          const CUtensorMap* lm = p.maps + (size_t)l * TM_PER_LAYER;
+          const CUtensorMap* am = p.maps + (size_t)p.L * TM_PER_LAYER;  // emb, xn, att, hid
+          const MkGemv& g = (k == 1) ? p.g_qkv : (k == 9) ? p.g_fc1 : (k == 10) ? p.g_fc2 : (k == 12) ? p.g_logits : p.g_dd;
+          const CUtensorMap* wm = (k == 1) ? lm + TM_QKV : (k == 3) ? lm + TM_OUT : (k == 5) ? lm + TM_CQ : (k == 7) ? lm + TM_COUT
+                                  : (k == 9) ? lm + TM_FC1 : (k == 10) ? lm + TM_FC2 : am;
+          const CUtensorMap* xm = (k == 3 || k == 7) ? am + 2 : (k == 10) ? am + 3 : am + 1;
+          const int epi = (k == 9) ? EPI_GELU_BF16 : (k == 12) ? EPI_LOGITS : EPI_PART;
+          gemv_phase<MT>(p, g, wm, xm, w.fc1_b, epi, ring, sy);
+        }
+      } else if (kind == PH_SELF) {
+        if (!(p.skip & 4)) self_attn_phase(p, l, w.qkv_b, pos);
+      } else if (kind == PH_CROSS) {
+        if (!(p.skip & 1)) cross_attn_phase(p, l, w.cq_b, ring, scratch, sy);
+      } else {
+        sample_phase(p.sp, p.B, pos, p.mode == 2, red, red_i);
+      }
+      if (ph + 1 < n_ph || s + 1 < p.n_steps) grid_sync(p.bar, bar_target, p.prof, prof_n);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *p.d_pos = pos0 + p.n_steps;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(sy.tmem, 64);
   }
 }
 
@@ -735,15 +1056,20 @@ __global__ void dec_finalize_kernel(const int* __restrict__ tokens, int stride, 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+constexpr int MAX_GROUP = 64;           // sequences per persistent kernel (4 m16 tiles)
+constexpr size_t PART_FLOATS = (size_t)4 << 20;  // 16 MB of fp32 split-K partials per group
+
 struct DecBuffers {
-  float *x, *q, *logits, *part, *sum_lp, *gv_part;
+  float *x, *logits, *part, *apart, *sum_lp;
   __nv_bfloat16 *att, *xn, *hid, *self_kv, *cross_kv;
-  int *ticket, *gv_ticket, *d_pos, *tokens, *done;
+  int *ticket, *d_pos, *tokens, *done;
+  unsigned* bar;
+  const DecLayerW* layers;
+  const CUtensorMap* maps;
   int B, tok_stride;
-  size_t gv_part_floats;
 };
 
-// profiling aid only (results become meaningless): WXB_DEC_SKIP bitmask 1 = cross-attention, 2 = GEMV + LN, 4 = self-attention
+// profiling aid only (results become meaningless): WXB_DEC_SKIP bitmask, see MkParams::skip
 int dec_skip_mask() {
   static int v = -1;
   if (v < 0) {
@@ -753,111 +1079,49 @@ int dec_skip_mask() {
   return v;
 }
 
-bool use_pdl() {
+// WXB_DEC_PROF=1: CTA 0 of the step kernel records the global timer at every grid barrier; after a decode the
+// per-phase averages of the last launch are printed to stderr (tracing aid, no effect on results).
+bool dec_prof_enabled() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("WXB_PDL");
-    v = (e && e[0] == '0') ? 0 : 1;
+    const char* e = getenv("WXB_DEC_PROF");
+    v = (e && e[0] == '1') ? 1 : 0;
   }
   return v == 1;
 }
+constexpr size_t PROF_SLOTS = 1 << 16;
+struct ProfLast { int mode = 0, n_steps = 0, L = 0; bool nsp = false; unsigned long long* dev = nullptr; } g_prof_last;
 
-int g_cluster_y = 1;   // cluster dimension (y) of the next launch_k call
-int g_low_prio = 0;    // 1: the next launch_k call is the bandwidth stream (cross-attention) -> lowest priority
+const void* g_layers_model = nullptr;  // the model whose DecLayerW table is resident in "dec.layers"
 
-template <typename... KArgs, typename... Args>
-int launch_k(wxb_ctx* ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[3];
-  int na = 0;
-  {  // chain kernels outrank the cross-attention stream of the other batch group
-    attr[na].id = cudaLaunchAttributePriority;
-    static int use_prio = -1;
-    if (use_prio < 0) { const char* e = getenv("WXB_PRIO"); use_prio = e ? atoi(e) : 1; }
-    attr[na].val.priority = (g_low_prio || !use_prio) ? 0 : -1;
-    ++na;
-    g_low_prio = 0;
-  }
-  if (use_pdl()) {
-    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[na].val.programmaticStreamSerializationAllowed = 1;
-    ++na;
-  }
-  if (g_cluster_y > 1) {
-    attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = 1;
-    attr[na].val.clusterDim.y = g_cluster_y;
-    attr[na].val.clusterDim.z = 1;
-    ++na;
-    g_cluster_y = 1;
-  }
-  cfg.attrs = attr;
-  cfg.numAttrs = na;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
-  ctx->launches++;
-  if (e != cudaSuccess) return wxb_fail(ctx, WXB_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
-  return WXB_OK;
-}
-
-constexpr size_t GV_SMEM_MAX = 200 * 1024;
-
-size_t gemv_smem(int Bp, int kslice) {
-  const size_t act = (size_t)Bp * (kslice + 32) * 2;
-  const size_t outt = (size_t)Bp * 66 * 4;
-  return act > outt ? act : outt;
-}
-
-// split-K factor = cluster size in {1,2,4,8}: the smallest that yields about one CTA per SM while the
-// activation tile stays <= ~100 KB (two CTAs per SM); very wide N (logits) never splits.
-int pick_ks(wxb_ctx* ctx, int Bp, int N, int K) {
-  const int row_blocks = ceil_div(N, GV_ROWS), kc = K / 64;
-  int best = 0;
-  for (int ks = 1; ks <= GV_KS_MAX; ks *= 2) {
-    if (kc % ks) break;
-    const size_t sm = gemv_smem(Bp, K / ks);
-    if (sm > GV_SMEM_MAX) continue;
-    best = ks;
-    if (row_blocks * ks >= ctx->sm_count && (sm <= 100 * 1024 || row_blocks >= 2 * ctx->sm_count)) break;
+// Pick the split-K factor for y[B, N] = act[B, K] W[N, K]^T on G CTAs (tiles of 128 weight rows x K / gk).
+// Cost model in microseconds: a CTA pulls its weight tile at ~60 KB/us and its activation slice from L2 at
+// ~80 KB/us, every wave of tiles pays ~1 us of pipeline latency, and split-K partials are written once and
+// read once through L2 (~10 MB/us chip-wide).
+MkGemv plan_gemv(int N, int K, int B, int Bp, int G, bool full_k) {
+  MkGemv best = {N, K, 0, 0};
+  double best_cost = 1e30;
+  for (int gk = 1; gk <= K / GV_BK && gk <= GK_MAX; ++gk) {
+    if (full_k && gk > 1) break;
+    if (K % gk) continue;
+    const int Ks = K / gk;
+    if (Ks % GV_BK) continue;
+    if ((size_t)gk * B * N > PART_FLOATS) continue;
+    const int tiles = ceil_div(N, GV_ROWS) * gk;
+    const int waves = ceil_div(tiles, G);
+    const double cost = waves * ((double)GV_ROWS * Ks * 2 / 60e3 + (double)Bp * Ks * 2 / 80e3 + 1.0) +
+                        (gk > 1 ? 2.0 * gk * Bp * (double)N * 4 / 10e6 + 0.05 * gk : 0.0);
+    if (cost < best_cost) { best_cost = cost; best.gk = gk; best.tiles = tiles; }
   }
   return best;
 }
 
-int launch_gemv(wxb_ctx* ctx, GemvParams p, const DecBuffers& buf, cudaStream_t st) {
-  (void)buf;
-  if (dec_skip_mask() & 2) return WXB_OK;
-  if (p.K % 64) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "gemv: K=%d must be a multiple of 64", p.K);
-  if (p.B > 64) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "gemv: batch %d > 64", p.B);
-  const int Bp = (p.B + 15) & ~15;
-  p.ks = pick_ks(ctx, Bp, p.N, p.K);
-  if (p.ks == 0) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "gemv: no K split of K=%d fits shared memory", p.K);
-  g_cluster_y = p.ks;
-  return launch_k(ctx, dec_gemv_kernel, dim3(ceil_div(p.N, GV_ROWS), p.ks), dim3(GV_THREADS), gemv_smem(Bp, p.K / p.ks), st, p);
-}
-
-int launch_ln(wxb_ctx* ctx, const float* x, const float* w, const float* b, __nv_bfloat16* y, int B, int d, cudaStream_t st) {
-  if (dec_skip_mask() & 2) return WXB_OK;
-  if (d % 4 || d > 1280) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder layernorm: d=%d", d);
-  return launch_k(ctx, dec_ln_kernel, dim3(ceil_div(B, 8)), dim3(256), 0, st, x, w, b, y, B, d);
-}
-
-int launch_attn(wxb_ctx* ctx, AttnParams p, int B, cudaStream_t st) {
-  if (dec_skip_mask() & (p.d_pos ? 4 : 1)) return WXB_OK;
-  const size_t smem = (size_t)(64 + 32 * 66) * 4;
-  p.B = B;
-  const int n_units = p.splits * p.H * B;
-  int grid = n_units;
-  if (!p.d_pos) {  // cross-attention = the bandwidth stream: lowest priority so the other group's chain kernels slip in
-    static int persist = -1;
-    if (persist < 0) { const char* e = getenv("WXB_ATTN_PERSIST"); persist = e ? atoi(e) : 0; }
-    if (persist > 0) grid = n_units < persist * ctx->sm_count ? n_units : persist * ctx->sm_count;
-    g_low_prio = 1;
-  }
-  return launch_k(ctx, dec_attn_kernel, dim3(grid), dim3(DA_THREADS), smem, st, p);
-}
+// identity of the tensor-map table resident in "dec.maps<group>"
+struct MapsKey {
+  const void* model = nullptr;
+  const void *xn = nullptr, *att = nullptr, *hid = nullptr, *ckv = nullptr;
+  int B = 0;
+} g_maps_key[2];
 
 int alloc_buffers(wxb_ctx* ctx, int B, int tok_stride, int group, DecBuffers* o) {
   const std::string sfx = group ? (".g" + std::to_string(group)) : std::string();
@@ -866,29 +1130,73 @@ int alloc_buffers(wxb_ctx* ctx, int B, int tok_stride, int group, DecBuffers* o)
   const int d = D.n_text_state, L = D.n_text_layer, H = D.n_text_head, V = D.n_vocab;
   o->B = B;
   o->tok_stride = tok_stride;
-  if (B > 64) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: batch %d > 64 sequences per call", B);
-  // opt in to the largest dynamic shared memory the GEMV may ask for; set outside graph capture
-  WXB_CUDA(ctx, cudaFuncSetAttribute(dec_gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GV_SMEM_MAX));
+  if (B > MAX_GROUP) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: batch %d > %d sequences per group", B, MAX_GROUP);
+  if (L > MAX_LAYERS) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: %d layers > %d", L, MAX_LAYERS);
+  if (d > 4 * LN_V4 * MK_THREADS || d % 64)
+    return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: n_text_state=%d unsupported (multiple of 64, <= %d)", d, 4 * LN_V4 * MK_THREADS);
   o->x = (float*)wxb_named(ctx, nm("dec.x").c_str(), (size_t)B * d * 4);
-  o->q = (float*)wxb_named(ctx, nm("dec.q").c_str(), (size_t)B * d * 4);
   o->att = (__nv_bfloat16*)wxb_named(ctx, nm("dec.att").c_str(), (size_t)B * d * 2);
   o->xn = (__nv_bfloat16*)wxb_named(ctx, nm("dec.xn").c_str(), (size_t)B * d * 2);
-  o->gv_part_floats = (size_t)4 << 20;  // 16 MB of fp32 split-K partials
-  o->gv_part = (float*)wxb_named(ctx, nm("dec.gv_part").c_str(), o->gv_part_floats * 4);
-  o->gv_ticket = (int*)wxb_named(ctx, nm("dec.gv_ticket").c_str(), (size_t)(ceil_div(V, GV_ROWS) + 64) * 4, true);
+  o->part = (float*)wxb_named(ctx, nm("dec.part").c_str(), PART_FLOATS * 4);
   o->hid = (__nv_bfloat16*)wxb_named(ctx, nm("dec.hid").c_str(), (size_t)B * 4 * d * 2);
   o->logits = (float*)wxb_named(ctx, nm("dec.logits").c_str(), (size_t)B * V * 4);
-  o->part = (float*)wxb_named(ctx, nm("dec.part").c_str(), (size_t)B * H * 8 * 66 * 4);
+  o->apart = (float*)wxb_named(ctx, nm("dec.apart").c_str(), (size_t)2 * 1024 * 66 * 4);
   o->sum_lp = (float*)wxb_named(ctx, nm("dec.sum_lp").c_str(), (size_t)B * 4);
   o->self_kv = (__nv_bfloat16*)wxb_named(ctx, nm("dec.self_kv").c_str(), (size_t)L * 2 * B * H * D.n_text_ctx * 64 * 2);
   o->cross_kv = (__nv_bfloat16*)wxb_named(ctx, nm("dec.cross_kv").c_str(), (size_t)L * 2 * B * H * T_AUDIO * 64 * 2);
-  o->ticket = (int*)wxb_named(ctx, nm("dec.ticket").c_str(), (size_t)B * H * 4 + 64, true);
+  o->ticket = (int*)wxb_named(ctx, nm("dec.ticket").c_str(), (size_t)1024 * 4, true);
   o->d_pos = (int*)wxb_named(ctx, nm("dec.pos").c_str(), 64);
+  o->bar = (unsigned*)wxb_named(ctx, nm("dec.bar").c_str(), 64, true);
   o->tokens = (int*)wxb_named(ctx, nm("dec.tokens").c_str(), (size_t)B * tok_stride * 4);
   o->done = (int*)wxb_named(ctx, nm("dec.done").c_str(), (size_t)B * 4);
-  if (!o->x || !o->q || !o->att || !o->hid || !o->logits || !o->part || !o->sum_lp || !o->self_kv || !o->cross_kv ||
-      !o->ticket || !o->d_pos || !o->tokens || !o->done || !o->xn || !o->gv_part || !o->gv_ticket)
+  DecLayerW* layers = (DecLayerW*)wxb_named(ctx, "dec.layers", (size_t)L * sizeof(DecLayerW));
+  if (!o->x || !o->att || !o->hid || !o->logits || !o->part || !o->apart || !o->sum_lp || !o->self_kv || !o->cross_kv ||
+      !o->ticket || !o->d_pos || !o->bar || !o->tokens || !o->done || !o->xn || !layers)
     return WXB_ERR_CUDA;
+  if (g_layers_model != (const void*)ctx->model) {
+    std::vector<DecLayerW> h(L);
+    for (int l = 0; l < L; ++l) {
+      int rc = wxb_dec_layer(ctx, l, &h[l]);
+      if (rc != WXB_OK) return rc;
+    }
+    WXB_CUDA(ctx, cudaMemcpy(layers, h.data(), (size_t)L * sizeof(DecLayerW), cudaMemcpyHostToDevice));
+    g_layers_model = ctx->model;
+  }
+  o->layers = layers;
+  // tensor maps (128-byte swizzle, 64-element boxes): weights [N, K] in 128-row boxes, activations [B, K] in one
+  // Bp-row box whose rows >= B are zero-filled by the TMA unit
+  const size_t n_maps = (size_t)TM_PER_LAYER * L + 5;
+  CUtensorMap* maps = (CUtensorMap*)wxb_named(ctx, nm("dec.maps").c_str(), n_maps * sizeof(CUtensorMap));
+  if (!maps) return WXB_ERR_CUDA;
+  MapsKey& key = g_maps_key[group ? 1 : 0];
+  if (key.model != (const void*)ctx->model || key.xn != o->xn || key.att != o->att || key.hid != o->hid || key.ckv != o->cross_kv || key.B != B) {
+    std::vector<CUtensorMap> h(n_maps);
+    const int Bp = (B + 15) & ~15;
+    int rc;
+    for (int l = 0; l < L; ++l) {
+      DecLayerW w;
+      if ((rc = wxb_dec_layer(ctx, l, &w)) != WXB_OK) return rc;
+      const struct { const __nv_bfloat16* p; int N, K; } ws[TM_PER_LAYER] = {
+          {w.qkv_w, 3 * d, d}, {w.out_w, d, d}, {w.cq_w, d, d}, {w.cout_w, d, d}, {w.fc1_w, 4 * d, d}, {w.fc2_w, d, 4 * d}};
+      for (int i = 0; i < TM_PER_LAYER; ++i)
+        if ((rc = wxb_make_tmap_bf16(ctx, &h[(size_t)l * TM_PER_LAYER + i], ws[i].p, (uint64_t)ws[i].K, (uint64_t)ws[i].N,
+                                     (uint64_t)ws[i].K * 2, GV_BK, GV_ROWS)) != WXB_OK)
+          return rc;
+    }
+    const void* emb = wxb_weight(ctx, "dec.emb");
+    if (!emb) return WXB_ERR_STATE;
+    CUtensorMap* am = &h[(size_t)TM_PER_LAYER * L];
+    if ((rc = wxb_make_tmap_bf16(ctx, am + 0, emb, (uint64_t)d, (uint64_t)V, (uint64_t)d * 2, GV_BK, GV_ROWS)) != WXB_OK) return rc;
+    if ((rc = wxb_make_tmap_bf16(ctx, am + 1, o->xn, (uint64_t)d, (uint64_t)B, (uint64_t)d * 2, GV_BK, Bp)) != WXB_OK) return rc;
+    if ((rc = wxb_make_tmap_bf16(ctx, am + 2, o->att, (uint64_t)d, (uint64_t)B, (uint64_t)d * 2, GV_BK, Bp)) != WXB_OK) return rc;
+    if ((rc = wxb_make_tmap_bf16(ctx, am + 3, o->hid, (uint64_t)4 * d, (uint64_t)B, (uint64_t)4 * d * 2, GV_BK, Bp)) != WXB_OK) return rc;
+    // cross K/V of all layers as one [rows, 64] tensor read in 128-key boxes
+    if ((rc = wxb_make_tmap_bf16(ctx, am + 4, o->cross_kv, 64, (uint64_t)L * 2 * B * H * T_AUDIO, 128, 64, XA_KEYS)) != WXB_OK) return rc;
+    WXB_CUDA(ctx, cudaDeviceSynchronize());  // a previous decode may still be reading the old table
+    WXB_CUDA(ctx, cudaMemcpy(maps, h.data(), n_maps * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    key.model = ctx->model; key.xn = o->xn; key.att = o->att; key.hid = o->hid; key.ckv = o->cross_kv; key.B = B;
+  }
+  o->maps = maps;
   return WXB_OK;
 }
 
@@ -910,158 +1218,113 @@ int cross_kv_precompute(wxb_ctx* ctx, const __nv_bfloat16* enc_out, const DecBuf
   return WXB_OK;
 }
 
-// One decoder step at position *d_pos over buf.tokens[:, pos]; logits (optional) to logits_out with row stride ldl.
-int decoder_step(wxb_ctx* ctx, const DecBuffers& buf, float* logits_out, long long ldl, cudaStream_t st) {
+// Launch the persistent step kernel: n_steps consecutive positions starting at *d_pos.
+int launch_steps(wxb_ctx* ctx, const DecBuffers& buf, int mode, int n_steps, const SampleParams& sp, float* logits_out,
+                 long long ldl, cudaStream_t st) {
   const wxb_dims& D = ctx->model->dims;
-  const int d = D.n_text_state, H = D.n_text_head, B = buf.B, L = D.n_text_layer, TX = D.n_text_ctx;
-  const __nv_bfloat16* emb = (const __nv_bfloat16*)wxb_weight(ctx, "dec.emb");
-  const float* pos_emb = (const float*)wxb_weight(ctx, "dec.pos");
-  const float* lnf_w = (const float*)wxb_weight(ctx, "dec.ln.w");
-  const float* lnf_b = (const float*)wxb_weight(ctx, "dec.ln.b");
-  if (!emb || !pos_emb || !lnf_w || !lnf_b) return WXB_ERR_STATE;
-  int rc;
-  if ((rc = launch_k(ctx, dec_embed_kernel, dim3(B), dim3(256), 0, st, (const int*)buf.tokens, buf.tok_stride,
-                     (const int*)buf.d_pos, emb, pos_emb, buf.x, d, D.n_vocab)) != WXB_OK)
-    return rc;
-  const float scale = 1.0f / sqrtf(64.f);
-  const int cross_splits = (B * H >= 4 * ctx->sm_count) ? 1 : ((B * H >= 2 * ctx->sm_count) ? 2 : 4);
-  for (int l = 0; l < L; ++l) {
-    DecLayerW w;
-    if ((rc = wxb_dec_layer(ctx, l, &w)) != WXB_OK) return rc;
-    __nv_bfloat16* sk = buf.self_kv + (size_t)l * 2 * B * H * TX * 64;
-    __nv_bfloat16* sv = sk + (size_t)B * H * TX * 64;
-    const __nv_bfloat16* ck = buf.cross_kv + (size_t)l * 2 * B * H * T_AUDIO * 64;
-    const __nv_bfloat16* cv = ck + (size_t)B * H * T_AUDIO * 64;
-    GemvParams g = {};
-    g.B = B;
-    // 1. LN1 + fused QKV, K/V appended to the self cache at pos
-    if ((rc = launch_ln(ctx, buf.x, w.ln1_w, w.ln1_b, buf.xn, B, d, st)) != WXB_OK) return rc;
-    g.N = 3 * d; g.K = d; g.in = buf.xn; g.ld_in = d;
-    g.W = w.qkv_w; g.bias = w.qkv_b; g.epi = EPI_QKV; g.q_out = buf.q; g.kcache = sk; g.vcache = sv;
-    g.d_pos = buf.d_pos; g.H = H; g.tmax = TX;
-    if ((rc = launch_gemv(ctx, g, buf, st)) != WXB_OK) return rc;
-    // 2. causal self-attention over pos+1 cached positions (one warp per (b, h))
-    if (!(dec_skip_mask() & 4)) {
-      if ((rc = launch_k(ctx, dec_self_attn_kernel, dim3(ceil_div(B * H, 8)), dim3(256), 0, st, (const float*)buf.q,
-                         (const __nv_bfloat16*)sk, (const __nv_bfloat16*)sv, (const int*)buf.d_pos, TX, H, d, B * H, scale, buf.att)) != WXB_OK)
-        return rc;
-    }
-    AttnParams a = {};
-    // 3. out projection + residual
-    g = GemvParams{};
-    g.B = B; g.N = d; g.K = d; g.in = buf.att; g.ld_in = d; g.W = w.out_w; g.bias = w.out_b;
-    g.epi = EPI_RESID; g.out = buf.x; g.ldo = d;
-    if ((rc = launch_gemv(ctx, g, buf, st)) != WXB_OK) return rc;
-    // 4. LN2 + cross query
-    g = GemvParams{};
-    if ((rc = launch_ln(ctx, buf.x, w.ln2_w, w.ln2_b, buf.xn, B, d, st)) != WXB_OK) return rc;
-    g.B = B; g.N = d; g.K = d; g.in = buf.xn; g.ld_in = d;
-    g.W = w.cq_w; g.bias = w.cq_b; g.epi = EPI_F32; g.out = buf.q; g.ldo = d;
-    if ((rc = launch_gemv(ctx, g, buf, st)) != WXB_OK) return rc;
-    // 5. cross-attention over the 1500 encoder positions
-    a = AttnParams{};
-    a.q = buf.q; a.K = ck; a.V = cv; a.tkv = T_AUDIO; a.n_keys = T_AUDIO; a.d_pos = nullptr; a.splits = cross_splits;
-    a.H = H; a.d = d; a.scale = scale; a.out = buf.att; a.part = buf.part; a.ticket = buf.ticket;
-    if ((rc = launch_attn(ctx, a, B, st)) != WXB_OK) return rc;
-    // 6. cross out projection + residual
-    g = GemvParams{};
-    g.B = B; g.N = d; g.K = d; g.in = buf.att; g.ld_in = d; g.W = w.cout_w; g.bias = w.cout_b;
-    g.epi = EPI_RESID; g.out = buf.x; g.ldo = d;
-    if ((rc = launch_gemv(ctx, g, buf, st)) != WXB_OK) return rc;
-    // 7. LN3 + fc1 + GELU
-    g = GemvParams{};
-    if ((rc = launch_ln(ctx, buf.x, w.ln3_w, w.ln3_b, buf.xn, B, d, st)) != WXB_OK) return rc;
-    g.B = B; g.N = 4 * d; g.K = d; g.in = buf.xn; g.ld_in = d;
-    g.W = w.fc1_w; g.bias = w.fc1_b; g.epi = EPI_GELU_BF16; g.out = buf.hid; g.ldo = 4 * d;
-    if ((rc = launch_gemv(ctx, g, buf, st)) != WXB_OK) return rc;
-    // 8. fc2 + residual
-    g = GemvParams{};
-    g.B = B; g.N = d; g.K = 4 * d; g.in = buf.hid; g.ld_in = 4 * d; g.W = w.fc2_w; g.bias = w.fc2_b;
-    g.epi = EPI_RESID; g.out = buf.x; g.ldo = d;
-    if ((rc = launch_gemv(ctx, g, buf, st)) != WXB_OK) return rc;
+  const int d = D.n_text_state, B = buf.B;
+  const int Bp = (B + 15) & ~15, MT = Bp / 16;
+  const int G = ctx->sm_count;
+  MkParams p = {};
+  p.B = B; p.d = d; p.H = D.n_text_head; p.L = D.n_text_layer; p.V = D.n_vocab; p.TX = D.n_text_ctx;
+  p.mode = mode; p.n_steps = n_steps; p.skip = dec_skip_mask();
+  p.layers = buf.layers; p.maps = buf.maps;
+  p.emb = (const __nv_bfloat16*)wxb_weight(ctx, "dec.emb");
+  p.pos_emb = (const float*)wxb_weight(ctx, "dec.pos");
+  p.lnf_w = (const float*)wxb_weight(ctx, "dec.ln.w");
+  p.lnf_b = (const float*)wxb_weight(ctx, "dec.ln.b");
+  if (!p.emb || !p.pos_emb || !p.lnf_w || !p.lnf_b) return WXB_ERR_STATE;
+  p.tokens = buf.tokens; p.tok_stride = buf.tok_stride; p.d_pos = buf.d_pos;
+  p.x = buf.x; p.xn = buf.xn; p.att = buf.att; p.hid = buf.hid; p.part = buf.part;
+  p.self_kv = buf.self_kv; p.cross_kv = buf.cross_kv;
+  p.logits = logits_out; p.ldl = ldl;
+  p.apart = buf.apart; p.ticket = buf.ticket; p.bar = buf.bar;
+  if (dec_prof_enabled()) {
+    p.prof = (unsigned long long*)wxb_named(ctx, "dec.prof", PROF_SLOTS * 8);
+    if ((size_t)n_steps * (11 * p.L + 4) > (size_t)PROF_XA) p.prof = nullptr;
+    if (p.prof) WXB_CUDA(ctx, cudaMemsetAsync(p.prof + PROF_XA, 0, 32 * 8, st));
+    g_prof_last.mode = mode; g_prof_last.n_steps = n_steps; g_prof_last.L = p.L; g_prof_last.nsp = sp.nsp_out != nullptr;
+    g_prof_last.dev = p.prof;
   }
-  if (logits_out) {
-    GemvParams g = {};
-    if ((rc = launch_ln(ctx, buf.x, lnf_w, lnf_b, buf.xn, B, d, st)) != WXB_OK) return rc;
-    g.B = B; g.N = D.n_vocab; g.K = d; g.in = buf.xn; g.ld_in = d;
-    g.W = emb; g.bias = nullptr; g.epi = EPI_F32; g.out = logits_out; g.ldo = ldl;
-    if ((rc = launch_gemv(ctx, g, buf, st)) != WXB_OK) return rc;
+  p.g_qkv = plan_gemv(3 * d, d, B, Bp, G, false);
+  p.g_dd = plan_gemv(d, d, B, Bp, G, false);
+  p.g_fc1 = plan_gemv(4 * d, d, B, Bp, G, true);
+  p.g_fc2 = plan_gemv(d, 4 * d, B, Bp, G, false);
+  p.g_logits = plan_gemv(D.n_vocab, d, B, Bp, G, true);
+  if (!p.g_qkv.gk || !p.g_dd.gk || !p.g_fc1.gk || !p.g_fc2.gk || !p.g_logits.gk)
+    return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: no GEMV tiling fits (d=%d, batch %d)", d, B);
+  p.sp = sp;
+  p.scale = 1.0f / sqrtf(64.f);
+  const size_t smem = MK_SMEM;
+  void (*kern)(const MkParams) = MT == 1 ? dec_step_kernel<1> : MT == 2 ? dec_step_kernel<2> : MT == 3 ? dec_step_kernel<3> : dec_step_kernel<4>;
+  static bool attr_set[5] = {false, false, false, false, false};
+  if (!attr_set[MT]) {
+    WXB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MK_SMEM));
+    int per_sm = 0;
+    WXB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MK_THREADS, MK_SMEM));
+    if (per_sm < 1) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: persistent step kernel does not fit an SM");
+    attr_set[MT] = true;
   }
+  WXB_CUDA(ctx, cudaMemsetAsync(buf.bar, 0, 4, st));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(G);
+  cfg.blockDim = dim3(MK_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident: the grid barrier cannot deadlock
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+  ctx->launches++;
+  if (e != cudaSuccess) return wxb_fail(ctx, WXB_ERR_CUDA, "decoder step launch failed: %s", cudaGetErrorString(e));
   return WXB_OK;
 }
 
-struct StepGraph {
-  cudaGraphExec_t exec = nullptr;
-  // identity of what was captured
-  const void* model = nullptr;
-  int B = 0, tok_stride = 0, mode = 0;
-  void* key_ptrs[4] = {nullptr, nullptr, nullptr, nullptr};
-  SampleParams sp = {};
-};
-StepGraph g_graphs[2][3];  // [batch group][0: prefill (no logits), 1: prefill + logits (no sampling), 2: logits + sample]
-
-bool use_graph() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("WXB_GRAPH");
-    v = (e && e[0] == '0') ? 0 : 1;
-  }
-  return v == 1;
-}
-
-int enqueue_step(wxb_ctx* ctx, const DecBuffers& buf, int mode, const SampleParams& sp, cudaStream_t st) {
-  int rc;
-  if ((rc = decoder_step(ctx, buf, mode >= 1 ? buf.logits : nullptr, ctx->model->dims.n_vocab, st)) != WXB_OK) return rc;
-  if (mode == 2) {
-    if ((rc = launch_k(ctx, dec_sample_kernel, dim3(buf.B), dim3(1024), 0, st, sp)) != WXB_OK) return rc;
-  }
-  return launch_k(ctx, dec_advance_kernel, dim3(1), dim3(32), 0, st, buf.d_pos);
-}
-
-// Run one step of `mode`, through a cached CUDA graph when enabled.
-int run_step(wxb_ctx* ctx, const DecBuffers& buf, int mode, const SampleParams& sp, cudaStream_t st, int group) {
-  if (!use_graph()) return enqueue_step(ctx, buf, mode, sp, st);
-  StepGraph& G = g_graphs[group][mode];
-  const bool same = G.exec && G.model == (const void*)ctx->model && G.B == buf.B && G.tok_stride == buf.tok_stride &&
-                    G.key_ptrs[0] == buf.x && G.key_ptrs[1] == buf.self_kv && G.key_ptrs[2] == buf.cross_kv &&
-                    G.key_ptrs[3] == buf.tokens && memcmp(&G.sp, &sp, sizeof(sp)) == 0;
-  if (!same) {
-    if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
-    const int64_t launches_before = ctx->launches;
-    cudaGraph_t graph = nullptr;
-    // capture on a private stream (the caller's stream may be the legacy default stream, which
-    // cannot be captured); the instantiated graph is then launched on the caller's stream
-    if (!ctx->cap_stream) {
-      cudaStream_t cs;
-      WXB_CUDA(ctx, cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-      ctx->cap_stream = cs;
+int dump_prof(wxb_ctx* ctx) {
+  const ProfLast& P = g_prof_last;
+  if (!P.dev) return WXB_OK;
+  WXB_CUDA(ctx, cudaDeviceSynchronize());
+  const int tail = (P.mode >= 1 ? 2 : 0) + ((P.mode == 2 || P.nsp) ? 1 : 0);
+  const int per_step = 11 * P.L + tail;  // phases = barriers per step (the last phase of the launch has none)
+  const int n = per_step * P.n_steps - 1;
+  std::vector<unsigned long long> t(n);
+  WXB_CUDA(ctx, cudaMemcpy(t.data(), P.dev, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  static const char* names[11] = {"ln1", "qkv", "self", "out", "ln2", "cq", "cross", "cout", "ln3", "fc1", "fc2"};
+  double sum[16] = {0};
+  long cnt[16] = {0};
+  for (int s = 0; s < P.n_steps; ++s)
+    for (int i = 0; i < per_step; ++i) {
+      const int k = s * per_step + i;
+      if (k == 0 || k >= n) continue;
+      const double us = (double)(t[k] - t[k - 1]) * 1e-3;
+      const int slot = i < 11 * P.L ? i % 11 : 11 + (i - 11 * P.L);  // 11 lnf, 12 logits, 13 sample (barrier after it = step end)
+      sum[slot] += us; cnt[slot]++;
     }
-    cudaStream_t cs = (cudaStream_t)ctx->cap_stream;
-    WXB_CUDA(ctx, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-    int rc = enqueue_step(ctx, buf, mode, sp, cs);
-    cudaError_t e = cudaStreamEndCapture(cs, &graph);
-    ctx->launches = launches_before;
-    if (rc != WXB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
-    if (e != cudaSuccess) return wxb_fail(ctx, WXB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
-    e = cudaGraphInstantiate(&G.exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (e != cudaSuccess) { G.exec = nullptr; return wxb_fail(ctx, WXB_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e)); }
-    G.model = ctx->model; G.B = buf.B; G.tok_stride = buf.tok_stride; G.mode = mode;
-    G.key_ptrs[0] = buf.x; G.key_ptrs[1] = buf.self_kv; G.key_ptrs[2] = buf.cross_kv; G.key_ptrs[3] = buf.tokens;
-    G.sp = sp;
-  }
-  WXB_CUDA(ctx, cudaGraphLaunch(G.exec, st));
-  const int L = ctx->model->dims.n_text_layer;
-  ctx->launches += 1 + 11 * L + (mode >= 1 ? 2 : 0) + (mode == 2 ? 1 : 0) + 1;
+  fprintf(stderr, "[wxb dec prof] mode %d, %d steps/launch, per-phase mean us (phase + its barrier):", P.mode, P.n_steps);
+  double layer = 0;
+  for (int i = 0; i < 11; ++i) { if (cnt[i]) { fprintf(stderr, " %s %.2f", names[i], sum[i] / cnt[i]); layer += sum[i] / cnt[i]; } }
+  fprintf(stderr, " | layer %.2f |", layer);
+  static const char* tn[4] = {"lnf", "logits", "sample", "x"};
+  for (int i = 11; i < 15; ++i) if (cnt[i]) fprintf(stderr, " %s %.2f", tn[i - 11], sum[i] / cnt[i]);
+  fprintf(stderr, " | step %.1f us\n", (double)(t[n - 1] - t[0]) * 1e-3 / P.n_steps);
+  unsigned long long xa[16];
+  WXB_CUDA(ctx, cudaMemcpy(xa, P.dev + PROF_XA, sizeof(xa), cudaMemcpyDeviceToHost));
+  for (int w = 0; w < 2; ++w)
+    if (xa[8 * w + 5])
+      fprintf(stderr, "[wxb dec prof] cross-attention warp %d of CTA 0, kcycles per phase: wait+ldmatrix %.1f item-start %.1f producer %.1f math %.1f item-end %.1f | in phase %.1f\n",
+              w, xa[8 * w] * 1e-3 / xa[8 * w + 5], xa[8 * w + 1] * 1e-3 / xa[8 * w + 5], xa[8 * w + 2] * 1e-3 / xa[8 * w + 5],
+              xa[8 * w + 3] * 1e-3 / xa[8 * w + 5], xa[8 * w + 4] * 1e-3 / xa[8 * w + 5], xa[8 * w + 6] * 1e-3 / xa[8 * w + 5]);
   return WXB_OK;
 }
 
 }  // namespace
 
 void wxb_decoder_reset_graphs() {
-  for (auto& row : g_graphs)
-    for (auto& G : row)
-      if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+  g_layers_model = nullptr;
+  g_maps_key[0] = MapsKey();
+  g_maps_key[1] = MapsKey();
 }
 
 extern "C" int wxb_decode_greedy(wxb_ctx* ctx, const void* enc_out_dev, int B, const int32_t* prompt_host, int prompt_len,
@@ -1077,16 +1340,15 @@ extern "C" int wxb_decode_greedy(wxb_ctx* ctx, const void* enc_out_dev, int B, c
     return wxb_fail(ctx, WXB_ERR_INVALID, "wxb_decode_greedy: prompt_len %d + sample_len %d exceeds n_text_ctx %d", prompt_len,
                     sample_len, D.n_text_ctx);
   if (opts->eot < 0 || opts->eot >= D.n_vocab) return wxb_fail(ctx, WXB_ERR_INVALID, "wxb_decode_greedy: eot out of range");
+  if (opts->no_speech >= D.n_vocab) return wxb_fail(ctx, WXB_ERR_INVALID, "wxb_decode_greedy: no_speech out of range");
   cudaStream_t st = (cudaStream_t)stream;
   WXB_CUDA(ctx, cudaSetDevice(ctx->device));
   const int stride = D.n_text_ctx + 1;
   int rc;
-  // Batch groups: with >= 32 sequences the batch is decoded as two independent halves on two private
-  // streams (own buffers, own step graphs), so one half's bandwidth-bound cross-attention overlaps the
-  // other half's latency-bound GEMV chain; the second reader of a weight matrix hits L2.
-  int ng = (B >= 32) ? 2 : 1;
-  if (const char* e = getenv("WXB_DEC_GROUPS")) ng = (atoi(e) >= 2 && B >= 2) ? 2 : 1;
-  if (B > 64 * ng) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "wxb_decode_greedy: at most %d sequences per call", 64 * ng);
+  // Batch groups: one persistent kernel decodes up to 64 sequences; larger batches are two groups on two
+  // private streams (own buffers).
+  const int ng = (B > MAX_GROUP) ? 2 : 1;
+  if (B > MAX_GROUP * ng) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "wxb_decode_greedy: at most %d sequences per call", MAX_GROUP * 2);
   cudaStream_t sg[2] = {st, st};
   if (ng == 2) {
     for (int g = 0; g < 2; ++g) {
@@ -1104,8 +1366,7 @@ extern "C" int wxb_decode_greedy(wxb_ctx* ctx, const void* enc_out_dev, int B, c
         ctx->dec_events[i] = ev;
       }
   }
-  int g0[3] = {0, (ng == 2) ? (B + 1) / 2 : B, B};
-  if (ng == 1) g0[2] = B;
+  const int g0[3] = {0, (ng == 2) ? (B + 1) / 2 : B, B};
   DecBuffers buf[2];
   SampleParams sp[2];
   for (int g = 0; g < ng; ++g) {
@@ -1135,43 +1396,38 @@ extern "C" int wxb_decode_greedy(wxb_ctx* ctx, const void* enc_out_dev, int B, c
     if ((rc = cross_kv_precompute(ctx, (const __nv_bfloat16*)enc_out_dev + (size_t)g0[g] * enc_row, buf[g], sg[g])) != WXB_OK) return rc;
     SampleParams& s1 = sp[g];
     s1 = SampleParams{};
-    s1.logits = buf[g].logits; s1.V = D.n_vocab; s1.tokens = buf[g].tokens; s1.stride = stride; s1.d_pos = buf[g].d_pos;
+    s1.logits = buf[g].logits; s1.V = D.n_vocab; s1.tokens = buf[g].tokens; s1.stride = stride;
     s1.prompt_len = prompt_len; s1.eot = opts->eot; s1.suppress_blank = opts->suppress_blank; s1.blank_token = opts->blank_token;
     s1.n_suppress = opts->n_suppress; s1.suppress = opts->suppress_dev; s1.sum_logprob = buf[g].sum_lp; s1.done = buf[g].done;
+    s1.nsp_out = nullptr; s1.nsp_token = opts->no_speech;
   }
   for (int g = 0; g < ng; ++g) WXB_CUDA(ctx, cudaStreamSynchronize(sg[g]));  // `init` is pageable host memory
   WXB_CUDA(ctx, cudaEventRecord(tm.e1, sg[0]));
 
+  const bool want_nsp = (opts->no_speech >= 0 && no_speech_prob_dev);
   // prompt positions 0 .. prompt_len-2 (forced tokens); logits only at position 0 for no_speech_prob
   for (int pos = 0; pos < prompt_len - 1; ++pos) {
-    const bool want_nsp = (pos == 0 && opts->no_speech >= 0 && no_speech_prob_dev);
     for (int g = 0; g < ng; ++g) {
-      if ((rc = run_step(ctx, buf[g], want_nsp ? 1 : 0, sp[g], sg[g], g)) != WXB_OK) return rc;
-      if (want_nsp) {
-        dec_token_prob_kernel<<<buf[g].B, 1024, 0, sg[g]>>>(buf[g].logits, D.n_vocab, opts->no_speech, no_speech_prob_dev + g0[g]);
-        WXB_LAUNCH_CHECK(ctx);
-      }
+      SampleParams s1 = sp[g];
+      const bool nsp = (pos == 0 && want_nsp);
+      if (nsp) s1.nsp_out = no_speech_prob_dev + g0[g];
+      if ((rc = launch_steps(ctx, buf[g], nsp ? 1 : 0, 1, s1, buf[g].logits, D.n_vocab, sg[g])) != WXB_OK) return rc;
     }
   }
-  const bool nsp_at_last = (prompt_len == 1 && opts->no_speech >= 0 && no_speech_prob_dev);
   const int check_every = opts->check_every > 0 ? opts->check_every : 16;
   std::vector<int> done_host(B);
   int n_sampled = 0;
-  for (int i = 0; i < sample_len; ++i) {
+  while (n_sampled < sample_len) {
+    // a single-token prompt makes the SOT position the first sampling position: that step also emits no_speech_prob
+    const bool nsp_now = (n_sampled == 0 && prompt_len == 1 && want_nsp);
+    const int n = nsp_now ? 1 : std::min(check_every, sample_len - n_sampled);
     for (int g = 0; g < ng; ++g) {
-      if (i == 0 && nsp_at_last) {
-        // single-token prompt: the SOT position is also the first sampling position
-        if ((rc = decoder_step(ctx, buf[g], buf[g].logits, D.n_vocab, sg[g])) != WXB_OK) return rc;
-        dec_token_prob_kernel<<<buf[g].B, 1024, 0, sg[g]>>>(buf[g].logits, D.n_vocab, opts->no_speech, no_speech_prob_dev + g0[g]);
-        WXB_LAUNCH_CHECK(ctx);
-        if ((rc = launch_k(ctx, dec_sample_kernel, dim3(buf[g].B), dim3(1024), 0, sg[g], sp[g])) != WXB_OK) return rc;
-        if ((rc = launch_k(ctx, dec_advance_kernel, dim3(1), dim3(32), 0, sg[g], buf[g].d_pos)) != WXB_OK) return rc;
-      } else {
-        if ((rc = run_step(ctx, buf[g], 2, sp[g], sg[g], g)) != WXB_OK) return rc;
-      }
+      SampleParams s1 = sp[g];
+      if (nsp_now) s1.nsp_out = no_speech_prob_dev + g0[g];
+      if ((rc = launch_steps(ctx, buf[g], 2, n, s1, buf[g].logits, D.n_vocab, sg[g])) != WXB_OK) return rc;
     }
-    n_sampled = i + 1;
-    if ((i + 1) % check_every == 0 && i + 1 < sample_len) {
+    n_sampled += n;
+    if (n_sampled < sample_len && !nsp_now) {
       for (int g = 0; g < ng; ++g)
         WXB_CUDA(ctx, cudaMemcpyAsync(done_host.data() + g0[g], buf[g].done, (size_t)buf[g].B * 4, cudaMemcpyDeviceToHost, sg[g]));
       for (int g = 0; g < ng; ++g) WXB_CUDA(ctx, cudaStreamSynchronize(sg[g]));
@@ -1193,6 +1449,7 @@ extern "C" int wxb_decode_greedy(wxb_ctx* ctx, const void* enc_out_dev, int B, c
   WXB_CUDA(ctx, cudaEventRecord(tm.e2, st));
   tm.steps = prompt_len - 1 + n_sampled;
   ctx->dec_timings.push_back(tm);
+  if (dec_prof_enabled()) return dump_prof(ctx);
   return WXB_OK;
 }
 
@@ -1232,9 +1489,8 @@ extern "C" int wxb_decoder_logits(wxb_ctx* ctx, const void* enc_out_dev, int B, 
   WXB_CUDA(ctx, cudaMemcpyAsync(buf.tokens, tokens_host, (size_t)B * n_tok * 4, cudaMemcpyHostToDevice, st));
   WXB_CUDA(ctx, cudaMemsetAsync(buf.d_pos, 0, 4, st));
   if ((rc = cross_kv_precompute(ctx, (const __nv_bfloat16*)enc_out_dev, buf, st)) != WXB_OK) return rc;
-  for (int pos = 0; pos < n_tok; ++pos) {
-    if ((rc = decoder_step(ctx, buf, logits_out_dev + (size_t)pos * D.n_vocab, (long long)n_tok * D.n_vocab, st)) != WXB_OK) return rc;
-    if ((rc = launch_k(ctx, dec_advance_kernel, dim3(1), dim3(32), 0, st, buf.d_pos)) != WXB_OK) return rc;
-  }
+  SampleParams sp = {};
+  for (int pos = 0; pos < n_tok; ++pos)
+    if ((rc = launch_steps(ctx, buf, 1, 1, sp, logits_out_dev + (size_t)pos * D.n_vocab, (long long)n_tok * D.n_vocab, st)) != WXB_OK) return rc;
   return WXB_OK;
 }
