@@ -48,28 +48,36 @@ constexpr int MK_WARPS = MK_THREADS / 32;
 constexpr int LN_V4 = 2;    // LayerNorm phase: float4 groups per thread, d <= 4 * 2 * 256
 constexpr int GK_MAX = 10;  // largest split-K factor a GEMV plan may use
 constexpr int MAX_LAYERS = 32;
-static_assert(GK_MAX + 1 <= 11, "q staging rows");
 constexpr int PROF_XA = (1 << 16) - 32;  // profile buffer: cross-attention cycle counters live behind the timestamps
 
 // ---- shared-memory plan of the persistent kernel (dynamic, 1024-byte aligned base) -------------------------
-// One region is time-shared by the two TMA rings (GEMV phases and cross-attention never overlap):
+// One region is time-shared by the two TMA rings (GEMV phases and cross-attention never overlap inside a CTA):
 //   GEMV ring   GV_NST stages x (A: 128 weight rows x 64 k bf16 = 16 KB | B: Bp batch rows x 64 k), 128-byte swizzle
-//   KV ring     XA_NST stages x (K: 128 keys x 64 dims bf16 = 16 KB | V: 16 KB), linear
-// followed by the attention scratch (scaled q + 32 slot states).
+//   KV ring     XA_NST stages x (K: 112 keys x 64 dims bf16 = 14 KB | V: 14 KB), 128-byte swizzle
+// followed by the attention scratch (warp states of two items, raw q rows of two items).
+// OCC = CTAs per SM = independent sequence groups decoded side by side (see dec_step_kernel): the ring depth shrinks
+// with OCC so that OCC CTAs fit one SM; shallow rings are backed by TMA prefetches into L2.
 constexpr int GV_ROWS = 128;                 // weight rows per tile = UMMA M
 constexpr int GV_BK = 64;                    // k per stage (one 128-byte swizzle row)
 constexpr int GV_A_BYTES = GV_ROWS * GV_BK * 2;
-constexpr int GV_NST = 6;
-constexpr int XA_KEYS = 128;
+constexpr int XA_CW = 7;                     // cross-attention consumer warps (hardware warps 1 .. 7); warp 0 produces
+constexpr int XA_KEYS = 16 * XA_CW;          // keys per stage: one m16 tile per consumer warp
 constexpr int XA_HALF = XA_KEYS * 128;       // bytes of K (or V) per stage
-constexpr int XA_NST = 6;
-constexpr int RING_BYTES = XA_NST * 2 * XA_HALF;  // 192 KB >= GV_NST * (16 KB + 8 KB)
-constexpr int SST_BYTES = 4352;                          // [2 item parities][8 warps][66] floats, padded
-constexpr int QST_ROW = 64 * 4;                           // one q-sized row of fp32
-constexpr int QST_WARP = 11 * QST_ROW;                    // per warp: bias row + up to GK_MAX split-K partial rows
-constexpr int SCRATCH_BYTES = SST_BYTES + 8 * QST_WARP;   // attention scratch behind the ring
-constexpr size_t MK_SMEM = RING_BYTES + SCRATCH_BYTES + 1024;
-static_assert(GV_NST * (GV_A_BYTES + 64 * GV_BK * 2) <= RING_BYTES, "GEMV ring must fit the shared region");
+constexpr int XA_TAIL = 48;                  // rows of the short TMA box used when <= 48 keys of an item remain
+constexpr int SST_BYTES = 3712;                           // [2 item parities][7 warps][66] floats, padded
+constexpr int QRAW_ROWS = GK_MAX + 1;                     // bias row + up to GK_MAX split-K partial rows of q
+constexpr int QRAW_BYTES = 2 * QRAW_ROWS * 64 * 4;        // two items in flight
+constexpr int SCRATCH_BYTES = SST_BYTES + QRAW_BYTES;     // attention scratch behind the ring
+template <int OCC>
+struct MkCfg {
+  static constexpr int XA_NST = OCC == 1 ? 6 : OCC == 2 ? 3 : 2;
+  static constexpr int GV_NST = OCC == 1 ? 6 : OCC == 2 ? 4 : 2;
+  static constexpr int MT_MAX = OCC == 1 ? 4 : 2;         // m16 batch tiles per group
+  static constexpr int RING_BYTES = XA_NST * 2 * XA_HALF;
+  static constexpr size_t SMEM = RING_BYTES + SCRATCH_BYTES + 1024;
+  static_assert(GV_NST * (GV_A_BYTES + 16 * MT_MAX * GV_BK * 2) <= RING_BYTES, "GEMV ring must fit the shared region");
+};
+constexpr int MAX_OCC = 3;
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -81,18 +89,20 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // Arrival is a release-add (orders this CTA's earlier writes, made visible to thread 0 by the block barrier),
 // the wait an acquire-poll.  The proxy fences order the generic-proxy global writes of a phase with the TMA
 // (async-proxy) reads of the next one.  With `prof` set, CTA 0 records the global timer at every barrier exit.
-__device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& target, unsigned long long* prof, int& prof_n) {
+__device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& target, int nc, int cta, unsigned long long* prof, int& prof_n) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    target += gridDim.x;
+    target += (unsigned)nc;
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
     unsigned v;
+    unsigned spins = 0;
     do {
       asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+      if (++spins > (1u << 26)) __trap();  // ~30 s: a CTA of the group is missing; fail the launch instead of hanging the GPU
     } while ((int)(v - target) < 0);
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
     fence_proxy_async_all();  // thread 0 is also the TMA producer of the next phase
-    if (prof && blockIdx.x == 0) {
+    if (prof && cta == 0) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       prof[prof_n] = t;
@@ -130,6 +140,7 @@ struct MkParams {
   int B, d, H, L, V, TX;
   int mode;     // 0: no logits (forced prompt token); 1: logits; 2: logits + sampling
   int n_steps;  // consecutive positions decoded by this launch (> 1 only in mode 2)
+  int xa_pf;    // L2 prefetch distance of the cross-attention K/V stream in stages (0 = off)
   int skip;     // profiling aid (WXB_DEC_SKIP): 1 cross-attention, 2 GEMV, 4 self-attention, 8 LayerNorm, 16 cross math, 32 cross merge
   const DecLayerW* layers;  // device array [L]
   const CUtensorMap* maps;  // device array [6 L + 5]
@@ -146,7 +157,7 @@ struct MkParams {
   float* logits;
   long long ldl;
   float* apart;  // cross-attention piece states [pieces][66]
-  int* ticket;   // [<= gridDim] zero-initialised, self-cleaning
+  int* ticket;   // [<= CTAs of the group] zero-initialised, self-cleaning
   unsigned* bar;
   unsigned long long* prof;  // optional: barrier-exit timestamps of CTA 0 (WXB_DEC_PROF)
   MkGemv g_qkv, g_dd, g_fc1, g_fc2, g_logits;
@@ -154,21 +165,42 @@ struct MkParams {
   float scale;
 };
 
-// mbarriers + ring cursors of the persistent kernel.  The cursors are advanced identically by every thread
-// (all loop bounds are CTA-uniform), so each thread holds its own consistent copy.
+// One launch decodes up to MAX_OCC independent sequence groups: the grid holds n_groups x nc CTAs, exactly
+// n_groups per SM (the shared-memory footprint allows no more), and every SM hosts one CTA of every group.
+// While one group streams its cross-attention K/V, the latency-bound GEMV / LayerNorm chain of the others runs
+// underneath on the same SMs; groups never synchronise with each other (own buffers, own grid barrier).
+struct MkLaunch {
+  int n_groups, nc;
+  unsigned* sm_slots;  // [256] zero-initialised per launch: arrival order of the CTAs of one SM
+  unsigned* grp_ctas;  // [MAX_OCC] zero-initialised per launch: CTAs that joined each group so far
+  MkParams g[MAX_OCC];
+};
+
+// mbarriers + ring cursors of the persistent kernel.  The barriers live in one shared array (fixed slots sized for
+// the deepest rings) addressed as `bars + 8 * slot`, so the whole synchronisation state costs one register plus the
+// cursors.  The cursors are advanced identically by every thread (all loop bounds are CTA-uniform), so each thread
+// holds its own consistent copy.
+enum {
+  MB_GV_FULL = 0,    // [6] TMA -> MMA
+  MB_GV_EMPTY = 6,   // [6] MMA (tcgen05.commit / 8 warp arrivals) -> TMA
+  MB_ACC_FULL = 12,  // [1] MMA -> epilogue
+  MB_XA_FULL = 13,   // [6] TMA -> attention warps
+  MB_XA_EMPTY = 19,  // [6] 7 consumer-warp arrivals -> producer
+  MB_ST_FULL = 25,   // [2] 7 warp states of an item deposited -> merging warp
+  MB_ST_FREE = 27,   // [2] merging warp -> writers of the item after next
+  MB_Q_FULL = 29,    // [2] raw q rows of an item landed (cp.async arrive-on of the 32 producer lanes)
+  MB_Q_FREE = 31,    // [2] 7 consumer warps have built their q fragments
+  MB_COUNT = 33
+};
 struct MkSync {
-  uint64_t* gv_full;   // [GV_NST] TMA -> MMA
-  uint64_t* gv_empty;  // [GV_NST] MMA (tcgen05.commit) -> TMA
-  uint64_t* acc_full;  // [1]      MMA -> epilogue
-  uint64_t* xa_full;   // [XA_NST] bulk copies -> attention warps
-  uint64_t* xa_empty;  // [XA_NST] 8 warp arrivals -> producer
-  uint64_t* st_full;   // [2]      8 warp states of an item deposited -> merging warp
-  uint64_t* st_free;   // [2]      merging warp -> writers of the item after next
+  uint32_t bars;       // shared-memory address of the barrier array
   uint32_t gv_count;   // GEMV stages issued so far (slot = count % GV_NST, parity = (count / GV_NST) & 1)
   uint32_t acc_count;  // accumulator hand-offs so far
   uint32_t xa_count;   // KV stages issued so far
   uint32_t xa_items;   // cross-attention work items finished so far
   uint32_t tmem;       // TMEM base address (64 fp32 columns x 128 lanes)
+  int cta, nc;         // this CTA's index within its group, CTAs per group
+  __device__ __forceinline__ uint32_t mb(int slot) const { return bars + 8u * (uint32_t)slot; }
 };
 
 __device__ __forceinline__ float block_sum(float v, float* red) {
@@ -199,9 +231,10 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 // then xn = LN(x) in bf16 (two-pass variance, eps 1e-5).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void ln_phase(const MkParams& p, bool from_embed, int gk, const float* __restrict__ prev_bias,
-                                         const float* __restrict__ lw, const float* __restrict__ lb, int pos, float* red) {
+                                         const float* __restrict__ lw, const float* __restrict__ lb, int pos, float* red,
+                                         const MkSync& sy) {
   const int tid = threadIdx.x, d = p.d, nv = d >> 2;
-  for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+  for (int b = sy.cta; b < p.B; b += sy.nc) {
     float4 v[LN_V4];
     float s = 0.f;
     int token = 0;
@@ -273,6 +306,18 @@ __device__ __forceinline__ void ln_phase(const MkParams& p, bool from_embed, int
   }
 }
 
+__device__ __forceinline__ void ldsm_x4(uint32_t* r, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t* r, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 // ---------------------------------------------------------------------------------------------
 // GEMV phase on the 5th-gen tensor cores: D[128 weight rows, Bp batch rows] = W_tile[128, Ks] act[Bp, Ks]^T.
 // The WEIGHTS are the M operand (UMMA M = 128), the batch the N operand (UMMA N = Bp = 16 MT), so a weight
@@ -281,7 +326,7 @@ __device__ __forceinline__ void ln_phase(const MkParams& p, bool from_embed, int
 // tcgen05.mma, all 8 warps read the accumulator back (tcgen05.ld, lane = weight row) for the epilogue.
 // Split-K tiles write fp32 partials [ks][B][N]; their consumer phase performs the reduction.
 // ---------------------------------------------------------------------------------------------
-template <int MT>
+template <int MT, int GV_NST>
 __device__ __forceinline__ void gemv_phase(const MkParams& p, const MkGemv& g, const CUtensorMap* wmap, const CUtensorMap* amap,
                                            const float* __restrict__ bias, const int epi, uint8_t* ring, MkSync& sy) {
   constexpr int Bp = 16 * MT;
@@ -290,7 +335,7 @@ __device__ __forceinline__ void gemv_phase(const MkParams& p, const MkGemv& g, c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int B = p.B;
   const int Ks = g.K / g.gk, nkb = Ks / GV_BK;
-  for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x) {
+  for (int tile = sy.cta; tile < g.tiles; tile += sy.nc) {
     const int ks = tile % g.gk, rb = tile / g.gk;
     const int k0 = ks * Ks, row0 = rb * GV_ROWS;
     if (warp == 0 && lane == 0) {
@@ -298,11 +343,11 @@ __device__ __forceinline__ void gemv_phase(const MkParams& p, const MkGemv& g, c
       uint32_t c = sy.gv_count;
       for (int kb = 0; kb < nkb; ++kb, ++c) {
         const uint32_t slot = c % GV_NST, par = (c / GV_NST) & 1;
-        mbar_wait(sy.gv_empty + slot, par ^ 1);
+        mbar_wait(sy.mb(MB_GV_EMPTY + slot), par ^ 1);
         uint8_t* sa = ring + slot * STAGE;
-        mbar_arrive_expect_tx(sy.gv_full + slot, STAGE);
-        tma_load_2d(sa, wmap, sy.gv_full + slot, k0 + kb * GV_BK, row0);
-        tma_load_2d(sa + GV_A_BYTES, amap, sy.gv_full + slot, k0 + kb * GV_BK, 0);
+        mbar_arrive_expect_tx(sy.mb(MB_GV_FULL + slot), STAGE);
+        tma_load_2d(sa, wmap, sy.mb(MB_GV_FULL + slot), k0 + kb * GV_BK, row0);
+        tma_load_2d(sa + GV_A_BYTES, amap, sy.mb(MB_GV_FULL + slot), k0 + kb * GV_BK, 0);
       }
     } else if (warp == 1 && lane == 0) {
       // ---- MMA issuer ----
@@ -310,7 +355,7 @@ __device__ __forceinline__ void gemv_phase(const MkParams& p, const MkGemv& g, c
       uint32_t c = sy.gv_count;
       for (int kb = 0; kb < nkb; ++kb, ++c) {
         const uint32_t slot = c % GV_NST, par = (c / GV_NST) & 1;
-        mbar_wait(sy.gv_full + slot, par);
+        mbar_wait(sy.mb(MB_GV_FULL + slot), par);
         tc_fence_after();
         const uint32_t sa = smem_u32(ring + slot * STAGE);
         const uint64_t adesc = make_sw128_desc(sa);
@@ -318,13 +363,13 @@ __device__ __forceinline__ void gemv_phase(const MkParams& p, const MkGemv& g, c
 #pragma unroll
         for (int k = 0; k < GV_BK / 16; ++k)  // +32 bytes along K inside the swizzle row = +2 in the address field
           tc_mma_bf16(sy.tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-        tc_commit(sy.gv_empty + slot);
+        tc_commit(sy.mb(MB_GV_EMPTY + slot));
       }
-      tc_commit(sy.acc_full);
+      tc_commit(sy.mb(MB_ACC_FULL));
     }
     sy.gv_count += nkb;
     __syncwarp();
-    mbar_wait(sy.acc_full, sy.acc_count & 1);
+    mbar_wait(sy.mb(MB_ACC_FULL), sy.acc_count & 1);
     sy.acc_count++;
     tc_fence_after();
     // ---- epilogue: warp w reads TMEM lanes 32 (w & 3) .. +31 (weight rows), 16-column groups j = w >> 2, + 2, .. ----
@@ -355,6 +400,91 @@ __device__ __forceinline__ void gemv_phase(const MkParams& p, const MkGemv& g, c
     }
     tc_fence_before();
     __syncthreads();  // the next tile's first MMA overwrites the accumulator
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GEMV phase on the legacy tensor pipe (mma.sync), used when several CTAs share an SM: a kernel that allocates
+// tensor memory is limited to one CTA per SM by the driver, and at batch <= 32 the phase is bound by the weight
+// stream and its latency, not by the MMA rate.  Same tiles, same TMA ring and swizzle as the tcgen05 variant:
+// warp w owns weight rows 16 w .. 16 w + 15 of the tile (A fragments by ldmatrix), all warps read the whole
+// activation slice (B fragments by ldmatrix, two 8-row batch tiles per instruction), fp32 accumulators in
+// registers.  Lane 0 of warp 0 refills a ring slot as soon as all 8 warps have released it.
+// ---------------------------------------------------------------------------------------------
+template <int MT, int GV_NST>
+__device__ __forceinline__ void gemv_phase_mma(const MkParams& p, const MkGemv& g, const CUtensorMap* wmap, const CUtensorMap* amap,
+                                               const float* __restrict__ bias, const int epi, uint8_t* ring, MkSync& sy) {
+  constexpr int Bp = 16 * MT;
+  constexpr int B_BYTES = Bp * GV_BK * 2;
+  constexpr int STAGE = GV_A_BYTES + B_BYTES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
+  const int B = p.B;
+  const int Ks = g.K / g.gk, nkb = Ks / GV_BK;
+  const bool producer = (warp == 0 && lane == 0);
+  // ldmatrix lane addressing (128-byte swizzle: chunk' = chunk ^ (row & 7))
+  const int rowA = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, chA = lane >> 4;  // weights: chunk 2 kq + chA
+  const int rowB = (lane & 7) + (lane >> 4) * 8, chB = (lane >> 3) & 1;              // batch rows 16 j2 + rowB: chunk 2 kq + chB
+  const int sw = lane & 7;
+  for (int tile = sy.cta; tile < g.tiles; tile += sy.nc) {
+    const int ks = tile % g.gk, rb = tile / g.gk;
+    const int k0 = ks * Ks, row0 = rb * GV_ROWS;
+    auto issue = [&](int kb) {
+      const uint32_t c = sy.gv_count + (uint32_t)kb;
+      const uint32_t slot = c % GV_NST, par = (c / GV_NST) & 1;
+      mbar_wait(sy.mb(MB_GV_EMPTY + slot), par ^ 1);
+      uint8_t* sa = ring + slot * STAGE;
+      mbar_arrive_expect_tx(sy.mb(MB_GV_FULL + slot), STAGE);
+      tma_load_2d(sa, wmap, sy.mb(MB_GV_FULL + slot), k0 + kb * GV_BK, row0);
+      tma_load_2d(sa + GV_A_BYTES, amap, sy.mb(MB_GV_FULL + slot), k0 + kb * GV_BK, 0);
+    };
+    if (producer)
+      for (int kb = 0; kb < nkb && kb < GV_NST; ++kb) issue(kb);
+    float acc[2 * MT][4];
+#pragma unroll
+    for (int j = 0; j < 2 * MT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const uint32_t c = sy.gv_count + (uint32_t)kb;
+      const uint32_t slot = c % GV_NST, par = (c / GV_NST) & 1;
+      mbar_wait(sy.mb(MB_GV_FULL + slot), par);
+      const uint32_t abase = smem_u32(ring + slot * STAGE), bbase = abase + GV_A_BYTES;
+#pragma unroll
+      for (int kq = 0; kq < GV_BK / 16; ++kq) {
+        uint32_t a[4];
+        ldsm_x4(a, abase + rowA * 128 + (((2 * kq + chA) ^ sw) << 4));
+#pragma unroll
+        for (int j2 = 0; j2 < MT; ++j2) {
+          uint32_t b[4];  // {b0, b1} of batch tile 2 j2, {b0, b1} of batch tile 2 j2 + 1
+          ldsm_x4(b, bbase + (16 * j2 + rowB) * 128 + (((2 * kq + chB) ^ sw) << 4));
+          mma_16816(acc[2 * j2], a, b[0], b[1]);
+          mma_16816(acc[2 * j2 + 1], a, b[2], b[3]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sy.mb(MB_GV_EMPTY + slot));
+      if (producer && kb + GV_NST < nkb) issue(kb + GV_NST);
+    }
+    sy.gv_count += nkb;
+    // ---- epilogue: lane (gq, t) holds weight rows n0 = row0 + 16 w + gq and n0 + 8, batch columns 8 j + 2 t, + 1 ----
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int n = row0 + warp * 16 + gq + 8 * hh;
+      if (n < g.N) {
+        const float bn = (epi == EPI_GELU_BF16) ? __ldg(bias + n) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 2 * MT; ++j) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int b = 8 * j + 2 * t + e;
+            const float v = acc[j][2 * hh + e];
+            if (b < B) {
+              if (epi == EPI_PART) p.part[((size_t)ks * B + b) * g.N + n] = v;
+              else if (epi == EPI_GELU_BF16) p.hid[(size_t)b * g.N + n] = __float2bfloat16_rn(gelu_erf(v + bn));
+              else p.logits[(size_t)b * p.ldl + n] = v;
+            }
+          }
+        }
+      }
+    }
   }
 }
 
@@ -413,12 +543,12 @@ __device__ __forceinline__ void att_consume(const uint4* kv, uint4* vv, int kb, 
 // Causal self-attention, one warp per (sequence, head).  The warp first finishes the QKV GEMV for its head
 // (sum of split-K partials + bias), appends the new K/V row to the cache, and attends over the pos cached rows
 // plus the new one (taken from registers, rounded to bf16 like its cached copy).
-__device__ __forceinline__ void self_attn_phase(const MkParams& p, int l, const float* __restrict__ qkv_b, int pos) {
+__device__ __forceinline__ void self_attn_phase(const MkParams& p, int l, const float* __restrict__ qkv_b, int pos, const MkSync& sy) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, slot = lane >> 3, c8 = lane & 7;
   const int d = p.d, H = p.H, B = p.B, TX = p.TX, gk = p.g_qkv.gk, N3 = 3 * d;
   __nv_bfloat16* sk = p.self_kv + (size_t)l * 2 * B * H * TX * 64;
   __nv_bfloat16* sv = sk + (size_t)B * H * TX * 64;
-  for (int u0 = blockIdx.x * MK_WARPS + warp; u0 < B * H; u0 += gridDim.x * MK_WARPS) {
+  for (int u0 = sy.cta * MK_WARPS + warp; u0 < B * H; u0 += sy.nc * MK_WARPS) {
     const int b = u0 / H, h = u0 - b * H;
     const int col = h * 64 + c8 * 8;
     float q8[8], k8[8], v8[8];
@@ -544,11 +674,13 @@ __device__ __forceinline__ void self_attn_phase(const MkParams& p, int l, const 
 
 // Cross-attention over the 1500 encoder positions.  n_slabs = B * H (sequence, head) slabs of 192 KB K + 192 KB V.
 // Every CTA streams floor(n_slabs / G) whole slabs; the n_slabs % G remaining slabs are cut into pieces so that
-// the tail is spread over all CTAs as well.  K/V do not depend on q, so thread 0 keeps XA_NST stages of 128 keys
-// (16 KB K + 16 KB V, 2-D TMA boxes with the 128-byte swizzle, completing on an mbarrier) in flight ACROSS work
-// items: the HBM stream never drains while a slab's states are merged or the next q is assembled.
+// the tail is spread over all CTAs as well.  Warp 0 is a dedicated producer: K/V do not depend on q, so it keeps
+// XA_NST stages of 112 keys (14 KB K + 14 KB V, 2-D TMA boxes with the 128-byte swizzle, L2 evict-first, completing
+// on an mbarrier) in flight ACROSS work items and, for shallow rings, pulls the stages behind them into L2 with
+// TMA prefetches; it also stages the raw q rows of upcoming items with cp.async.  The HBM stream never drains
+// while a slab's states are merged or the next q is assembled.
 //
-// Math on the (otherwise idle) legacy tensor pipe, one query per head: warp w owns keys 16 w .. 16 w + 15 of a stage.
+// Math on the (otherwise idle) legacy tensor pipe, one query per head: consumer warp w owns keys 16 w .. 16 w + 15 of a stage.
 //   S = K q      mma.m16n8k16: A = K rows (ldmatrix), B column 0 = bf16 hi part of the scaled q, column 1 = its
 //                bf16 lo part (q - hi), so S = c0 + c1 carries ~16 mantissa bits of q; columns 2-7 are zero.
 //   softmax      online over 16-key blocks (scores replicated per quad, max by shuffles over the quads).
@@ -556,27 +688,16 @@ __device__ __forceinline__ void self_attn_phase(const MkParams& p, int l, const 
 struct XaItem {
   int slab, k0, k1, piece, lj;
 };
-__device__ __forceinline__ XaItem xa_item(int it, int qw, int G, int P, int plen) {
+__device__ __forceinline__ XaItem xa_item(int it, int cta, int qw, int G, int P, int plen) {
   XaItem x;
   if (it < qw) {
-    x.slab = it * G + blockIdx.x; x.k0 = 0; x.k1 = T_AUDIO; x.piece = -1; x.lj = 0;
+    x.slab = it * G + cta; x.k0 = 0; x.k1 = T_AUDIO; x.piece = -1; x.lj = 0;
   } else {
-    const int pc = (it - qw) * G + blockIdx.x;
+    const int pc = (it - qw) * G + cta;
     x.lj = pc / P; x.piece = pc - x.lj * P;
     x.slab = qw * G + x.lj; x.k0 = x.piece * plen; x.k1 = min(T_AUDIO, x.k0 + plen);
   }
   return x;
-}
-__device__ __forceinline__ void ldsm_x4(uint32_t* r, uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x4_t(uint32_t* r, uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ __forceinline__ void mma_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 // bf16 hi / lo split of two floats, packed for an MMA B fragment: sel 0 -> (hi(x), hi(y)), 1 -> (lo(x), lo(y)), else 0.
 // Branch-free (sel differs between the lanes of a warp).
@@ -634,15 +755,25 @@ __device__ __forceinline__ void xa_block(const uint32_t (*ka)[4][4], const uint3
   }
 }
 
-// The 8 warps never meet at a block barrier inside the phase: each warp assembles q for itself (and prefetches
-// the next item's), deposits its (m, l, O) state of a finished item in a double-buffered shared-memory slot and
-// moves straight on; warp (item % 8) merges the 8 states once all have arrived (mbarrier) and writes the output.
+// The warps never meet at a block barrier inside the phase: the producer warp stages the raw q rows (bias + split-K
+// partials of the cq GEMV) of the next items, every consumer warp sums them for itself, deposits its (m, l, O) state of
+// a finished item in a double-buffered shared-memory slot and moves straight on; consumer warp (item % 7) merges the
+// 7 states once all have arrived (mbarrier) and writes the output.
+template <int XA_NST>
 __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const float* __restrict__ cq_b, uint8_t* ring,
                                                  float* scratch, MkSync& sy) {
-  float* sst = scratch;  // [2 item parities][8 warps][66]: m, l, O[64]
+  constexpr uint32_t STAGE = 2 * XA_HALF;
+  float* sst = scratch;                                                                          // [2 item parities][7 warps][66]: m, l, O[64]
+  float* qraw = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(scratch) + SST_BYTES);      // [2 item parities][QRAW_ROWS][64]
+  const float scale = p.scale;
+  const int skip = p.skip, xa_pf = p.xa_pf;
+  const float* __restrict__ part_q = p.part;
+  __nv_bfloat16* __restrict__ att = p.att;
+  float* __restrict__ apart = p.apart;
+  int* __restrict__ ticket = p.ticket;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int B = p.B, H = p.H, d = p.d, G = gridDim.x, gk = p.g_dd.gk;
-  const CUtensorMap* kvmap = p.maps + (size_t)p.L * TM_PER_LAYER + 4;
+  const int B = p.B, H = p.H, d = p.d, G = sy.nc, cta = sy.cta, gk = p.g_dd.gk;
+  const CUtensorMap* kvmap = p.maps + (size_t)p.L * TM_PER_LAYER + 4;  // 112-key boxes; kvmap + 1: 48-key boxes
   const int n_slabs = B * H, qw = n_slabs / G, r = n_slabs - qw * G;
   const int krow0 = (l * 2) * n_slabs * T_AUDIO, vrow0 = (l * 2 + 1) * n_slabs * T_AUDIO;  // rows of the [rows, 64] K/V tensor
   int P = 0, plen = T_AUDIO;
@@ -651,212 +782,198 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
     plen = (T_AUDIO + want - 1) / want;
     P = (T_AUDIO + plen - 1) / plen;
   }
-  const int n_items = qw + ((r > 0 && (int)blockIdx.x < r * P) ? ((r * P - 1 - (int)blockIdx.x) / G + 1) : 0);
-  // producer cursor (thread 0 only): next (item, stage-in-item) to request
-  int pit = 0, pst = 0;
-  uint32_t issued = sy.xa_count;
-  uint32_t consumed = sy.xa_count;
-  // thread 0: request stages until XA_NST are in flight or the work list is exhausted.  Opportunistic: a slot still
-  // held by a lagging warp ends the call (retried at the next one) unless fewer than `need` stages past `consumed`
-  // have been requested, i.e. this warp itself is about to wait for them.
-  auto top_up = [&](uint32_t need) {
-    while (pit < n_items && issued - consumed < (uint32_t)XA_NST) {
-      const XaItem x = xa_item(pit, qw, G, P, plen);
-      const int kk = x.k0 + pst * XA_KEYS;
-      const uint32_t sl = issued % XA_NST, par = (issued / XA_NST) & 1;
-      // never block the producer's own consumer warp: if a lagging warp still holds the slot, retry at the next call
-      if (!mbar_test(sy.xa_empty + sl, par ^ 1)) {
-        if (issued - consumed >= need) break;
-        mbar_wait(sy.xa_empty + sl, par ^ 1);
+  const int n_items = qw + ((r > 0 && cta < r * P) ? ((r * P - 1 - cta) / G + 1) : 0);
+  if (warp == 0) {
+    // ------------------------------- producer warp -------------------------------
+    int it = 0, kk = 0, pit = 0, pkk = 0, ahead = 0;  // load cursor, L2-prefetch cursor, distance between them in stages
+    XaItem x = {}, px = {};
+    if (n_items > 0) { x = xa_item(0, cta, qw, G, P, plen); kk = x.k0; px = x; pkk = kk; }
+    uint32_t issued = sy.xa_count;
+    while (it < n_items) {
+      if (xa_pf > 0) {
+        while (pit < n_items && ahead <= xa_pf) {
+          if (ahead >= XA_NST && lane == 0) {
+            const CUtensorMap* m = (px.k1 - pkk <= XA_TAIL) ? kvmap + 1 : kvmap;
+            tma_prefetch_2d(m, 0, krow0 + px.slab * T_AUDIO + pkk);
+            tma_prefetch_2d(m, 0, vrow0 + px.slab * T_AUDIO + pkk);
+          }
+          ++ahead;
+          pkk += XA_KEYS;
+          if (pkk >= px.k1) {
+            ++pit;
+            if (pit < n_items) { px = xa_item(pit, cta, qw, G, P, plen); pkk = px.k0; }
+          }
+        }
       }
-      uint8_t* dst = ring + (size_t)sl * 2 * XA_HALF;
-      // full 128-row boxes: rows past the slab (or past the tensor: zero-filled) are masked by the consumer
-      mbar_arrive_expect_tx(sy.xa_full + sl, 2 * XA_HALF);
-      tma_load_2d(dst, kvmap, sy.xa_full + sl, 0, krow0 + x.slab * T_AUDIO + kk);
-      tma_load_2d(dst + XA_HALF, kvmap, sy.xa_full + sl, 0, vrow0 + x.slab * T_AUDIO + kk);
+      if (kk == x.k0) {
+        // first stage of an item: its raw q rows (row gk = bias, rows 0 .. gk-1 = split-K partials), 2 rows per pass
+        const uint32_t gi = sy.xa_items + (uint32_t)it, qpar = gi & 1;
+        mbar_wait(sy.mb(MB_Q_FREE + qpar), ((gi >> 1) & 1) ^ 1);  // the consumers have used the rows of item gi - 2
+        float* dst = qraw + qpar * (QRAW_ROWS * 64);
+        const int b = x.slab / H, h = x.slab - b * H;
+        const int half = lane >> 4, l16 = lane & 15;
+        for (int r0 = 0; r0 <= gk; r0 += 2) {
+          const int row = r0 + half;
+          if (row <= gk) {
+            const float* src = (row == gk) ? (cq_b + h * 64) : (part_q + ((size_t)row * B + b) * d + h * 64);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + row * 64 + l16 * 4)), "l"(src + l16 * 4) : "memory");
+          }
+        }
+        cp_async_mbar_arrive(sy.mb(MB_Q_FULL + qpar));
+      }
+      if (lane == 0) {
+        const uint32_t sl = issued % XA_NST, par = (issued / XA_NST) & 1;
+        mbar_wait(sy.mb(MB_XA_EMPTY + sl), par ^ 1);
+        const bool tail = (x.k1 - kk <= XA_TAIL);  // keys past the item (or the tensor: zero-filled) are masked by the consumer
+        const CUtensorMap* m = tail ? kvmap + 1 : kvmap;
+        uint8_t* dst = ring + (size_t)sl * STAGE;
+        mbar_arrive_expect_tx(sy.mb(MB_XA_FULL + sl), tail ? 2 * XA_TAIL * 128 : STAGE);
+        tma_load_2d_hint(dst, m, sy.mb(MB_XA_FULL + sl), 0, krow0 + x.slab * T_AUDIO + kk, L2_EVICT_FIRST);
+        tma_load_2d_hint(dst + XA_HALF, m, sy.mb(MB_XA_FULL + sl), 0, vrow0 + x.slab * T_AUDIO + kk, L2_EVICT_FIRST);
+      }
+      __syncwarp();
       ++issued;
-      if (kk + XA_KEYS >= x.k1) { ++pit; pst = 0; } else { ++pst; }
-    }
-  };
-  if (tid == 0) top_up(0);
-  // ldmatrix lane addressing inside a 128-row x 128-byte swizzled tile (chunk' = chunk ^ (row & 7)); this warp's rows 16 w ..
-  const int rowA = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, chA = lane >> 4;         // K (non-transposed): chunk 2 j + chA
-  const int rowV = warp * 16 + (lane & 7) + ((lane >> 4) & 1) * 8, chV = (lane >> 3) & 1;   // V (transposed): chunk 2 mt + chV
-  const int sw = lane & 7;
-  // scaled q of an item = bias + split-K partials of the cq GEMV (slice order).  The rows of the NEXT item are
-  // copied asynchronously (cp.async, no registers held) into this warp's staging rows at the start of an item and
-  // summed when that item begins; every warp assembles q for itself, so no block barrier is involved.
-  float* qst = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(scratch) + SST_BYTES + warp * QST_WARP);
-  auto issue_q = [&](int it) {
-    const XaItem x = xa_item(it, qw, G, P, plen);
-    const int b = x.slab / H, h = x.slab - b * H;
-    const int half = lane >> 4, l16 = lane & 15;  // 16 lanes x 16 B = one 64-float row; two rows per pass
-    for (int r0 = 0; r0 <= gk; r0 += 2) {
-      const int row = r0 + half;  // row gk = bias, rows 0 .. gk-1 = partials
-      if (row <= gk) {
-        const float* src = (row == gk) ? (cq_b + h * 64) : (p.part + ((size_t)row * B + b) * d + h * 64);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(qst + row * 64 + l16 * 4)), "l"(src + l16 * 4));
+      --ahead;
+      kk += XA_KEYS;
+      if (kk >= x.k1) {
+        ++it;
+        if (it < n_items) { x = xa_item(it, cta, qw, G, P, plen); kk = x.k0; }
       }
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  auto finish_q = [&](float& q0, float& q1) {
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncwarp();
-    float a0 = qst[gk * 64 + lane], a1 = qst[gk * 64 + lane + 32];
-    for (int ks = 0; ks < gk; ++ks) { a0 += qst[ks * 64 + lane]; a1 += qst[ks * 64 + lane + 32]; }
-    __syncwarp();  // all lanes have read the rows before the next issue_q overwrites them
-    q0 = a0 * p.scale;
-    q1 = a1 * p.scale;
-  };
-  if (n_items > 0) issue_q(0);
-  // WXB_DEC_PROF: cycle split of the stage loop as seen by warp 1 (and thread 0's producer work) of CTA 0
-  const bool pw = p.prof && blockIdx.x == 0;
-  long long c_wait = 0, c_math = 0, c_top = 0, c_item = 0, c_pre = 0, tA = 0, tB = 0, tP = 0;
-  const long long t_phase0 = pw ? clock64() : 0;
-  for (int it = 0; it < n_items; ++it) {
-    if (pw) tP = clock64();
-    const XaItem x = xa_item(it, qw, G, P, plen);
-    const int b = x.slab / H, h = x.slab - b * H;
-    // B fragments of q: lane (g, t) holds elements 16 j + 2 t + {0, 1} and + {8, 9}; column g = 0 hi part, g = 1 lo part
-    uint32_t qb[4][2];
-    float qn0, qn1;
-    finish_q(qn0, qn1);
+  } else {
+    // ------------------------------- consumer warps -------------------------------
+    const int cw = warp - 1;
+    // ldmatrix lane addressing inside a 112-row x 128-byte swizzled tile (chunk' = chunk ^ (row & 7)); this warp's rows 16 cw ..
+    const int rowA = cw * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, chA = lane >> 4;         // K (non-transposed): chunk 2 j + chA
+    const int rowV = cw * 16 + (lane & 7) + ((lane >> 4) & 1) * 8, chV = (lane >> 3) & 1;   // V (transposed): chunk 2 mt + chV
+    const int sw = lane & 7;
+    uint32_t consumed = sy.xa_count;
+    for (int it = 0; it < n_items; ++it) {
+      const XaItem x = xa_item(it, cta, qw, G, P, plen);
+      const int b = x.slab / H, h = x.slab - b * H;
+      const uint32_t gi = sy.xa_items + (uint32_t)it;  // items since kernel start: parity and phase of the double-buffered slots
+      const uint32_t ipar = gi & 1, iph = (gi >> 1) & 1;
+      // scaled q = (bias + split-K partials in slice order) * scale; lane holds dims lane and lane + 32
+      mbar_wait(sy.mb(MB_Q_FULL + ipar), iph);
+      float qn0, qn1;
+      {
+        const float* qr = qraw + ipar * (QRAW_ROWS * 64);
+        float a0 = qr[gk * 64 + lane], a1 = qr[gk * 64 + lane + 32];
+        for (int ks = 0; ks < gk; ++ks) { a0 += qr[ks * 64 + lane]; a1 += qr[ks * 64 + lane + 32]; }
+        qn0 = a0 * scale;
+        qn1 = a1 * scale;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sy.mb(MB_Q_FREE + ipar));
+      // B fragments of q: lane (g, t) holds elements 16 j + 2 t + {0, 1} and + {8, 9}; column g = 0 hi part, g = 1 lo part
+      uint32_t qb[4][2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float src = (j < 2) ? qn0 : qn1;
-      const int e = (16 * j + 2 * t) & 31;
-      const float v0 = __shfl_sync(0xffffffffu, src, e), v1 = __shfl_sync(0xffffffffu, src, e + 1);
-      const float v8 = __shfl_sync(0xffffffffu, src, e + 8), v9 = __shfl_sync(0xffffffffu, src, e + 9);
-      qb[j][0] = split_pack(v0, v1, g);
-      qb[j][1] = split_pack(v8, v9, g);
-    }
-    if (it + 1 < n_items) issue_q(it + 1);  // in flight during this item's stream
-    float m = -INFINITY, lsum = 0.f, o[4][4];
+      for (int j = 0; j < 4; ++j) {
+        const float src = (j < 2) ? qn0 : qn1;
+        const int e = (16 * j + 2 * t) & 31;
+        const float v0 = __shfl_sync(0xffffffffu, src, e), v1 = __shfl_sync(0xffffffffu, src, e + 1);
+        const float v8 = __shfl_sync(0xffffffffu, src, e + 8), v9 = __shfl_sync(0xffffffffu, src, e + 9);
+        qb[j][0] = split_pack(v0, v1, g);
+        qb[j][1] = split_pack(v8, v9, g);
+      }
+      float m = -INFINITY, lsum = 0.f, o[4][4];
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt) o[mt][0] = o[mt][1] = o[mt][2] = o[mt][3] = 0.f;
-    if (pw) c_pre += clock64() - tP;
-    for (int kk = x.k0; kk < x.k1;) {
-      const int ns = (kk + XA_KEYS < x.k1) ? 2 : 1;  // stages handled by this iteration
-      uint32_t ka[2][4][4], va[2][4][4];
-      if (tid == 0) top_up((uint32_t)ns);  // the stages about to be awaited are certainly on their way
-      if (pw) tA = clock64();
-#pragma unroll
-      for (int n = 0; n < 2; ++n) {
-        if (n < ns) {
-          const uint32_t sl = (consumed + n) % XA_NST, par = ((consumed + n) / XA_NST) & 1;
-          mbar_wait(sy.xa_full + sl, par);
-          const uint32_t kbase = smem_u32(ring + (size_t)sl * 2 * XA_HALF), vbase = kbase + XA_HALF;
+      for (int mt = 0; mt < 4; ++mt) o[mt][0] = o[mt][1] = o[mt][2] = o[mt][3] = 0.f;
+      for (int kk = x.k0; kk < x.k1; kk += XA_KEYS) {
+        const uint32_t sl = consumed % XA_NST, par = (consumed / XA_NST) & 1;
+        const bool act = kk + cw * 16 < x.k1;  // warp-uniform: this warp's 16 keys hold at least one key of the item
+        uint32_t ka[1][4][4], va[1][4][4];
+        mbar_wait(sy.mb(MB_XA_FULL + sl), par);
+        if (act) {
+          const uint32_t kbase = smem_u32(ring + (size_t)sl * STAGE), vbase = kbase + XA_HALF;
           // all fragments go to registers first, so the slot is released (and refilled) before the math
 #pragma unroll
-          for (int j = 0; j < 4; ++j) ldsm_x4(ka[n][j], kbase + rowA * 128 + (((2 * j + chA) ^ sw) << 4));
+          for (int j = 0; j < 4; ++j) ldsm_x4(ka[0][j], kbase + rowA * 128 + (((2 * j + chA) ^ sw) << 4));
 #pragma unroll
-          for (int mt = 0; mt < 4; ++mt) ldsm_x4_t(va[n][mt], vbase + rowV * 128 + (((2 * mt + chV) ^ sw) << 4));
-          __syncwarp();
-          if (lane == 0) mbar_arrive(sy.xa_empty + sl);  // this warp is done reading the stage
+          for (int mt = 0; mt < 4; ++mt) ldsm_x4_t(va[0][mt], vbase + rowV * 128 + (((2 * mt + chV) ^ sw) << 4));
         }
-      }
-      consumed += ns;
-      if (pw) { tB = clock64(); c_wait += tB - tA; }
-      if (tid == 0) top_up(0);
-      if (pw) { tA = clock64(); c_top += tA - tB; }
-      const int key0 = kk + warp * 16 + g;  // this quad's keys in the first stage: key0 and key0 + 8
-      if (!(p.skip & 16)) {
-        if (ns == 2) xa_block<2>(ka, va, qb, key0, x.k1, lane, g, t, m, lsum, o);
-        else xa_block<1>(ka, va, qb, key0, x.k1, lane, g, t, m, lsum, o);
-      }
-      if (pw) { tB = clock64(); c_math += tB - tA; }
-      if (tid == 0) top_up(0);
-      kk += ns * XA_KEYS;
-    }
-    if (pw) tA = clock64();
-    // ---- deposit this warp's state; warp (item % 8) merges the 8 states and writes the output ----
-    const uint32_t gi = sy.xa_items + (uint32_t)it;  // items since kernel start: parity and phase of the state slot
-    const uint32_t ipar = gi & 1, iph = (gi >> 1) & 1;
-    lsum += __shfl_xor_sync(0xffffffffu, lsum, 4);
-    lsum += __shfl_xor_sync(0xffffffffu, lsum, 8);
-    lsum += __shfl_xor_sync(0xffffffffu, lsum, 16);
-    mbar_wait(sy.st_free + ipar, iph ^ 1);  // the merge of item gi - 2 has released this slot
-    {
-      float* st = sst + (ipar * MK_WARPS + warp) * 66;
-      if (lane == 0) { st[0] = m; st[1] = lsum; }
-      if (t == 0) {
-#pragma unroll
-        for (int mt = 0; mt < 4; ++mt) {
-          st[2 + 16 * mt + g] = o[mt][0] + o[mt][1];
-          st[2 + 16 * mt + g + 8] = o[mt][2] + o[mt][3];
-        }
-      }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(sy.st_full + ipar);
-    if (warp == (int)(gi % MK_WARPS) && !(p.skip & 32)) {
-      mbar_wait(sy.st_full + ipar, iph);
-      const float* st = sst + (size_t)ipar * MK_WARPS * 66;
-      float M = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < MK_WARPS; ++i) M = fmaxf(M, st[i * 66]);
-      float Ls = 0.f, o0 = 0.f, o1 = 0.f;  // dims lane and lane + 32
-#pragma unroll
-      for (int i = 0; i < MK_WARPS; ++i) {
-        const float w = __expf(st[i * 66] - M);
-        Ls += w * st[i * 66 + 1];
-        o0 += w * st[i * 66 + 2 + lane];
-        o1 += w * st[i * 66 + 2 + lane + 32];
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(sy.st_free + ipar);
-      __nv_bfloat16* out = p.att + (size_t)b * d + h * 64;
-      if (x.piece < 0) {
-        out[lane] = __float2bfloat16_rn(o0 / Ls);
-        out[lane + 32] = __float2bfloat16_rn(o1 / Ls);
-      } else {
-        // ---- piece of a remainder slab: publish the state, the last-arriving piece merges all of them ----
-        float* part = p.apart + (size_t)x.lj * P * 66;
-        part[x.piece * 66 + 2 + lane] = o0;
-        part[x.piece * 66 + 2 + lane + 32] = o1;
-        if (lane == 0) { part[x.piece * 66] = M; part[x.piece * 66 + 1] = Ls; }
-        __threadfence();
         __syncwarp();
-        int last = 0;
-        if (lane == 0) {
-          const int prev = atomicAdd(p.ticket + x.lj, 1);
-          last = (prev == P - 1);
-          if (last) p.ticket[x.lj] = 0;
-        }
-        last = __shfl_sync(0xffffffffu, last, 0);
-        if (last) {
-          __threadfence();
-          float MM = -INFINITY;
-          for (int s2 = 0; s2 < P; ++s2) MM = fmaxf(MM, __ldcg(part + s2 * 66));
-          float LL = 0.f, O0 = 0.f, O1 = 0.f;
-          for (int s2 = 0; s2 < P; ++s2) {
-            const float w = __expf(__ldcg(part + s2 * 66) - MM);
-            LL += w * __ldcg(part + s2 * 66 + 1);
-            O0 += w * __ldcg(part + s2 * 66 + 2 + lane);
-            O1 += w * __ldcg(part + s2 * 66 + 2 + lane + 32);
+        if (lane == 0) mbar_arrive(sy.mb(MB_XA_EMPTY + sl));  // this warp is done reading the stage
+        ++consumed;
+        if (act && !(skip & 16)) xa_block<1>(ka, va, qb, kk + cw * 16 + g, x.k1, lane, g, t, m, lsum, o);
+      }
+      // ---- deposit this warp's state; consumer warp (item % 7) merges the 7 states and writes the output ----
+      lsum += __shfl_xor_sync(0xffffffffu, lsum, 4);
+      lsum += __shfl_xor_sync(0xffffffffu, lsum, 8);
+      lsum += __shfl_xor_sync(0xffffffffu, lsum, 16);
+      mbar_wait(sy.mb(MB_ST_FREE + ipar), iph ^ 1);  // the merge of item gi - 2 has released this slot
+      {
+        float* st = sst + (ipar * XA_CW + cw) * 66;
+        if (lane == 0) { st[0] = m; st[1] = lsum; }
+        if (t == 0) {
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) {
+            st[2 + 16 * mt + g] = o[mt][0] + o[mt][1];
+            st[2 + 16 * mt + g + 8] = o[mt][2] + o[mt][3];
           }
-          out[lane] = __float2bfloat16_rn(O0 / LL);
-          out[lane + 32] = __float2bfloat16_rn(O1 / LL);
         }
       }
-    } else if (warp == (int)(gi % MK_WARPS)) {
-      mbar_wait(sy.st_full + ipar, iph);
       __syncwarp();
-      if (lane == 0) mbar_arrive(sy.st_free + ipar);
+      if (lane == 0) mbar_arrive(sy.mb(MB_ST_FULL + ipar));
+      if (cw == (int)(gi % XA_CW)) {
+        mbar_wait(sy.mb(MB_ST_FULL + ipar), iph);
+        const float* st = sst + (size_t)ipar * XA_CW * 66;
+        float M = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < XA_CW; ++i) M = fmaxf(M, st[i * 66]);
+        float Ls = 0.f, o0 = 0.f, o1 = 0.f;  // dims lane and lane + 32
+#pragma unroll
+        for (int i = 0; i < XA_CW; ++i) {
+          const float w = __expf(st[i * 66] - M);  // a warp that saw no key of the item: m = -inf -> 0
+          Ls += w * st[i * 66 + 1];
+          o0 += w * st[i * 66 + 2 + lane];
+          o1 += w * st[i * 66 + 2 + lane + 32];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sy.mb(MB_ST_FREE + ipar));
+        __nv_bfloat16* out = att + (size_t)b * d + h * 64;
+        if (skip & 32) {
+        } else if (x.piece < 0) {
+          out[lane] = __float2bfloat16_rn(o0 / Ls);
+          out[lane + 32] = __float2bfloat16_rn(o1 / Ls);
+        } else {
+          // ---- piece of a remainder slab: publish the state, the last-arriving piece merges all of them ----
+          float* part = apart + (size_t)x.lj * P * 66;
+          part[x.piece * 66 + 2 + lane] = o0;
+          part[x.piece * 66 + 2 + lane + 32] = o1;
+          if (lane == 0) { part[x.piece * 66] = M; part[x.piece * 66 + 1] = Ls; }
+          __threadfence();
+          __syncwarp();
+          int last = 0;
+          if (lane == 0) {
+            const int prev = atomicAdd(ticket + x.lj, 1);
+            last = (prev == P - 1);
+            if (last) ticket[x.lj] = 0;
+          }
+          last = __shfl_sync(0xffffffffu, last, 0);
+          if (last) {
+            __threadfence();
+            float MM = -INFINITY;
+            for (int s2 = 0; s2 < P; ++s2) MM = fmaxf(MM, __ldcg(part + s2 * 66));
+            float LL = 0.f, O0 = 0.f, O1 = 0.f;
+            for (int s2 = 0; s2 < P; ++s2) {
+              const float w = __expf(__ldcg(part + s2 * 66) - MM);
+              LL += w * __ldcg(part + s2 * 66 + 1);
+              O0 += w * __ldcg(part + s2 * 66 + 2 + lane);
+              O1 += w * __ldcg(part + s2 * 66 + 2 + lane + 32);
+            }
+            out[lane] = __float2bfloat16_rn(O0 / LL);
+            out[lane + 32] = __float2bfloat16_rn(O1 / LL);
+          }
+        }
+      }
     }
-    if (pw) c_item += clock64() - tA;
-  }
-  if (pw && lane == 0 && warp <= 1) {  // slots: warp 0 (with the producer) then warp 1
-    unsigned long long* dst = p.prof + PROF_XA + warp * 8;
-    dst[0] += (unsigned long long)c_wait; dst[1] += (unsigned long long)c_pre; dst[6] += (unsigned long long)(clock64() - t_phase0); dst[2] += (unsigned long long)c_top;
-    dst[3] += (unsigned long long)c_math; dst[4] += (unsigned long long)c_item; dst[5] += 1;
   }
   // every thread advances the uniform cursors by this CTA's work list
   {
     uint32_t n_st = (uint32_t)qw * ((T_AUDIO + XA_KEYS - 1) / XA_KEYS);
     for (int it = qw; it < n_items; ++it) {
-      const XaItem x = xa_item(it, qw, G, P, plen);
+      const XaItem x = xa_item(it, cta, qw, G, P, plen);
       n_st += (uint32_t)((x.k1 - x.k0 + XA_KEYS - 1) / XA_KEYS);
     }
     sy.xa_count += n_st;
@@ -866,10 +983,10 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
 
 // mlx_whisper_batch_decoder.py:267-303 for one row per CTA: (no_speech_prob from the unfiltered logits,)
 // filters, argmax (first max), logprob accounting, EOT latch.  Row loops keep 8 independent loads in flight.
-__device__ __forceinline__ void sample_phase(const SampleParams& p, int B, int pos, bool do_sample, float* red, int* red_i) {
+__device__ __forceinline__ void sample_phase(const SampleParams& p, int B, int pos, bool do_sample, float* red, int* red_i, const MkSync& sy) {
   const int tid = threadIdx.x;
   constexpr int U = 8;
-  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+  for (int b = sy.cta; b < B; b += sy.nc) {
     float* x = p.logits + (size_t)b * p.V;
     if (p.nsp_out) {
       float m = -INFINITY;
@@ -954,36 +1071,49 @@ __device__ __forceinline__ void sample_phase(const SampleParams& p, int B, int p
 // phase kinds of the step schedule: 11 per layer, then final LN | logits | sampling
 enum { PH_LN = 0, PH_GEMV = 1, PH_SELF = 2, PH_CROSS = 3, PH_SAMPLE = 4 };
 
-template <int MT>
-__global__ void __launch_bounds__(MK_THREADS, 1) dec_step_kernel(const __grid_constant__ MkParams p) {
+// The step loop of one CTA.  `p` must be a compile-time-indexed member of the kernel parameter, so that every p.field
+// is a constant-bank operand: behind a run-time group index the compiler loads the fields instead and hoists dozens
+// of them into registers across the whole phase loop.
+template <int MT, int OCC>
+__device__ __forceinline__ void dec_step_body(const MkParams& p, const int cta, const int nc) {
+  using C = MkCfg<OCC>;
+  constexpr int GV_NST = C::GV_NST, XA_NST = C::XA_NST;
   extern __shared__ uint8_t mk_smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(mk_smem_raw) + 1023) & ~(uintptr_t)1023);
-  float* scratch = reinterpret_cast<float*>(ring + RING_BYTES);
+  float* scratch = reinterpret_cast<float*>(ring + C::RING_BYTES);
   __shared__ float red[MK_WARPS];
   __shared__ int red_i[MK_WARPS];
-  __shared__ __align__(8) uint64_t bars[2 * GV_NST + 1 + 2 * XA_NST + 4];
+  __shared__ __align__(8) uint64_t bars[MB_COUNT];
   __shared__ uint32_t tmem_slot;
   __shared__ DecLayerW s_layers[MAX_LAYERS];  // pointer table of every layer: no dependent global load per phase
   for (int i = threadIdx.x; i < p.L * (int)(sizeof(DecLayerW) / 8); i += MK_THREADS)
     reinterpret_cast<unsigned long long*>(s_layers)[i] = reinterpret_cast<const unsigned long long*>(p.layers)[i];
   const int warp = threadIdx.x >> 5;
   MkSync sy;
-  sy.gv_full = bars; sy.gv_empty = bars + GV_NST; sy.acc_full = bars + 2 * GV_NST;
-  sy.xa_full = bars + 2 * GV_NST + 1; sy.xa_empty = sy.xa_full + XA_NST;
-  sy.st_full = sy.xa_empty + XA_NST; sy.st_free = sy.st_full + 2;
+  sy.cta = cta; sy.nc = nc;
+  sy.bars = smem_u32(bars);
   sy.gv_count = 0; sy.acc_count = 0; sy.xa_count = 0; sy.xa_items = 0;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < GV_NST; ++i) { mbar_init(sy.gv_full + i, 1); mbar_init(sy.gv_empty + i, 1); }
-    mbar_init(sy.acc_full, 1);
-    for (int i = 0; i < XA_NST; ++i) { mbar_init(sy.xa_full + i, 1); mbar_init(sy.xa_empty + i, MK_WARPS); }
-    for (int i = 0; i < 2; ++i) { mbar_init(sy.st_full + i, MK_WARPS); mbar_init(sy.st_free + i, 1); }
+    for (int i = 0; i < GV_NST; ++i) { mbar_init(sy.mb(MB_GV_FULL + i), 1); mbar_init(sy.mb(MB_GV_EMPTY + i), OCC == 1 ? 1 : MK_WARPS); }
+    mbar_init(sy.mb(MB_ACC_FULL), 1);
+    for (int i = 0; i < XA_NST; ++i) { mbar_init(sy.mb(MB_XA_FULL + i), 1); mbar_init(sy.mb(MB_XA_EMPTY + i), XA_CW); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(sy.mb(MB_ST_FULL + i), XA_CW); mbar_init(sy.mb(MB_ST_FREE + i), 1);
+      mbar_init(sy.mb(MB_Q_FULL + i), 32); mbar_init(sy.mb(MB_Q_FREE + i), XA_CW);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) tmem_alloc(&tmem_slot, 64);
-  tc_fence_before();
+  if constexpr (OCC == 1) {  // tensor memory only where the tcgen05 GEMV runs (it pins the kernel to one CTA per SM)
+    if (warp == 2) tmem_alloc(&tmem_slot, 64);
+    tc_fence_before();
+  }
   __syncthreads();
-  tc_fence_after();
-  sy.tmem = tmem_slot;
+  if constexpr (OCC == 1) {
+    tc_fence_after();
+    sy.tmem = tmem_slot;
+  } else {
+    sy.tmem = 0;
+  }
 
   unsigned bar_target = 0;
   int prof_n = 0;
@@ -1007,7 +1137,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) dec_step_kernel(const __grid_co
           const float* pb = (k == 0) ? (l > 0 ? s_layers[l - 1].fc2_b : nullptr) : (k == 4) ? w.out_b : (k == 8) ? w.cout_b : w.fc2_b;
           const float* lw = (k == 0) ? w.ln1_w : (k == 4) ? w.ln2_w : (k == 8) ? w.ln3_w : p.lnf_w;
           const float* lb = (k == 0) ? w.ln1_b : (k == 4) ? w.ln2_b : (k == 8) ? w.ln3_b : p.lnf_b;
-          ln_phase(p, from_embed, gk, pb, lw, lb, pos, red);
+          ln_phase(p, from_embed, gk, pb, lw, lb, pos, red, sy);
         }
       } else if (kind == PH_GEMV) {
         if (!(p.skip & 2)) {
@@ -1018,25 +1148,55 @@ __global__ void __launch_bounds__(MK_THREADS, 1) dec_step_kernel(const __grid_co
                                   : (k == 9) ? lm + TM_FC1 : (k == 10) ? lm + TM_FC2 : am;
           const CUtensorMap* xm = (k == 3 || k == 7) ? am + 2 : (k == 10) ? am + 3 : am + 1;
           const int epi = (k == 9) ? EPI_GELU_BF16 : (k == 12) ? EPI_LOGITS : EPI_PART;
-          gemv_phase<MT>(p, g, wm, xm, w.fc1_b, epi, ring, sy);
+          if constexpr (OCC == 1) gemv_phase<MT, GV_NST>(p, g, wm, xm, w.fc1_b, epi, ring, sy);
+          else gemv_phase_mma<MT, GV_NST>(p, g, wm, xm, w.fc1_b, epi, ring, sy);
         }
       } else if (kind == PH_SELF) {
-        if (!(p.skip & 4)) self_attn_phase(p, l, w.qkv_b, pos);
+        if (!(p.skip & 4)) self_attn_phase(p, l, w.qkv_b, pos, sy);
       } else if (kind == PH_CROSS) {
-        if (!(p.skip & 1)) cross_attn_phase(p, l, w.cq_b, ring, scratch, sy);
+        if (!(p.skip & 1)) cross_attn_phase<XA_NST>(p, l, w.cq_b, ring, scratch, sy);
       } else {
-        sample_phase(p.sp, p.B, pos, p.mode == 2, red, red_i);
+        sample_phase(p.sp, p.B, pos, p.mode == 2, red, red_i, sy);
       }
-      if (ph + 1 < n_ph || s + 1 < p.n_steps) grid_sync(p.bar, bar_target, p.prof, prof_n);
+      if (ph + 1 < n_ph || s + 1 < p.n_steps) grid_sync(p.bar, bar_target, sy.nc, sy.cta, p.prof, prof_n);
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) *p.d_pos = pos0 + p.n_steps;
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc(sy.tmem, 64);
+  if (sy.cta == 0 && threadIdx.x == 0) *p.d_pos = pos0 + p.n_steps;
+  if constexpr (OCC == 1) {
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+      tc_fence_after();
+      tmem_dealloc(sy.tmem, 64);
+    }
   }
+}
+
+template <int MT, int OCC>
+__global__ void __launch_bounds__(MK_THREADS, OCC) dec_step_kernel(const __grid_constant__ MkLaunch L) {
+  __shared__ int s_seat[2];
+  // ---- seat: which sequence group this CTA serves, and its index there.  CTAs of one SM take the groups in
+  // arrival order, so every SM hosts one CTA of every group; a full group passes the CTA on to the next one.
+  if (threadIdx.x == 0) {
+    int grp = 0, cta = blockIdx.x;
+    if (L.n_groups > 1) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      grp = (int)(atomicAdd(L.sm_slots + (smid & 255u), 1u) % (unsigned)L.n_groups);
+      for (;;) {
+        cta = (int)atomicAdd(L.grp_ctas + grp, 1u);
+        if (cta < L.nc) break;
+        grp = (grp + 1) % L.n_groups;
+      }
+    }
+    s_seat[0] = grp;
+    s_seat[1] = cta;
+  }
+  __syncthreads();
+  const int grp = s_seat[0], cta = s_seat[1];
+  if (OCC == 1 || grp == 0) dec_step_body<MT, OCC>(L.g[0], cta, L.nc);
+  else if (OCC == 2 || grp == 1) dec_step_body<MT, OCC>(L.g[1], cta, L.nc);
+  else dec_step_body<MT, OCC>(L.g[2], cta, L.nc);
 }
 
 // n_tokens[b] = sampled tokens before the first EOT; tokens_out[b, i] = sampled token i (EOT padded)
@@ -1056,7 +1216,7 @@ __global__ void dec_finalize_kernel(const int* __restrict__ tokens, int stride, 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-constexpr int MAX_GROUP = 64;           // sequences per persistent kernel (4 m16 tiles)
+constexpr int MAX_GROUP = 64;           // sequences per group when the launch holds one group (4 m16 tiles)
 constexpr size_t PART_FLOATS = (size_t)4 << 20;  // 16 MB of fp32 split-K partials per group
 
 struct DecBuffers {
@@ -1068,6 +1228,16 @@ struct DecBuffers {
   const CUtensorMap* maps;
   int B, tok_stride;
 };
+
+// tuning aid: WXB_XA_PF overrides the L2 prefetch distance of the cross-attention stream
+int dec_xa_prefetch(int ng) {
+  static int v = -2;
+  if (v == -2) {
+    const char* e = getenv("WXB_XA_PF");
+    v = e ? atoi(e) : -1;
+  }
+  return v >= 0 ? v : 0;
+}
 
 // profiling aid only (results become meaningless): WXB_DEC_SKIP bitmask, see MkParams::skip
 int dec_skip_mask() {
@@ -1121,7 +1291,7 @@ struct MapsKey {
   const void* model = nullptr;
   const void *xn = nullptr, *att = nullptr, *hid = nullptr, *ckv = nullptr;
   int B = 0;
-} g_maps_key[2];
+} g_maps_key[MAX_OCC];
 
 int alloc_buffers(wxb_ctx* ctx, int B, int tok_stride, int group, DecBuffers* o) {
   const std::string sfx = group ? (".g" + std::to_string(group)) : std::string();
@@ -1146,7 +1316,9 @@ int alloc_buffers(wxb_ctx* ctx, int B, int tok_stride, int group, DecBuffers* o)
   o->cross_kv = (__nv_bfloat16*)wxb_named(ctx, nm("dec.cross_kv").c_str(), (size_t)L * 2 * B * H * T_AUDIO * 64 * 2);
   o->ticket = (int*)wxb_named(ctx, nm("dec.ticket").c_str(), (size_t)1024 * 4, true);
   o->d_pos = (int*)wxb_named(ctx, nm("dec.pos").c_str(), 64);
-  o->bar = (unsigned*)wxb_named(ctx, nm("dec.bar").c_str(), 64, true);
+  // launch-scoped counters shared by the groups: [256] CTAs seated per SM | [4] CTAs seated per group | [4] grid barriers
+  unsigned* sync = (unsigned*)wxb_named(ctx, "dec.sync", (256 + 8) * 4, true);
+  o->bar = sync ? sync + 256 + 4 + group : nullptr;
   o->tokens = (int*)wxb_named(ctx, nm("dec.tokens").c_str(), (size_t)B * tok_stride * 4);
   o->done = (int*)wxb_named(ctx, nm("dec.done").c_str(), (size_t)B * 4);
   DecLayerW* layers = (DecLayerW*)wxb_named(ctx, "dec.layers", (size_t)L * sizeof(DecLayerW));
@@ -1165,10 +1337,10 @@ int alloc_buffers(wxb_ctx* ctx, int B, int tok_stride, int group, DecBuffers* o)
   o->layers = layers;
   // tensor maps (128-byte swizzle, 64-element boxes): weights [N, K] in 128-row boxes, activations [B, K] in one
   // Bp-row box whose rows >= B are zero-filled by the TMA unit
-  const size_t n_maps = (size_t)TM_PER_LAYER * L + 5;
+  const size_t n_maps = (size_t)TM_PER_LAYER * L + 6;
   CUtensorMap* maps = (CUtensorMap*)wxb_named(ctx, nm("dec.maps").c_str(), n_maps * sizeof(CUtensorMap));
   if (!maps) return WXB_ERR_CUDA;
-  MapsKey& key = g_maps_key[group ? 1 : 0];
+  MapsKey& key = g_maps_key[group];
   if (key.model != (const void*)ctx->model || key.xn != o->xn || key.att != o->att || key.hid != o->hid || key.ckv != o->cross_kv || key.B != B) {
     std::vector<CUtensorMap> h(n_maps);
     const int Bp = (B + 15) & ~15;
@@ -1190,8 +1362,9 @@ int alloc_buffers(wxb_ctx* ctx, int B, int tok_stride, int group, DecBuffers* o)
     if ((rc = wxb_make_tmap_bf16(ctx, am + 1, o->xn, (uint64_t)d, (uint64_t)B, (uint64_t)d * 2, GV_BK, Bp)) != WXB_OK) return rc;
     if ((rc = wxb_make_tmap_bf16(ctx, am + 2, o->att, (uint64_t)d, (uint64_t)B, (uint64_t)d * 2, GV_BK, Bp)) != WXB_OK) return rc;
     if ((rc = wxb_make_tmap_bf16(ctx, am + 3, o->hid, (uint64_t)4 * d, (uint64_t)B, (uint64_t)4 * d * 2, GV_BK, Bp)) != WXB_OK) return rc;
-    // cross K/V of all layers as one [rows, 64] tensor read in 128-key boxes
+    // cross K/V of all layers as one [rows, 64] tensor read in 112-key boxes (48-key boxes at the end of an item)
     if ((rc = wxb_make_tmap_bf16(ctx, am + 4, o->cross_kv, 64, (uint64_t)L * 2 * B * H * T_AUDIO, 128, 64, XA_KEYS)) != WXB_OK) return rc;
+    if ((rc = wxb_make_tmap_bf16(ctx, am + 5, o->cross_kv, 64, (uint64_t)L * 2 * B * H * T_AUDIO, 128, 64, XA_TAIL)) != WXB_OK) return rc;
     WXB_CUDA(ctx, cudaDeviceSynchronize());  // a previous decode may still be reading the old table
     WXB_CUDA(ctx, cudaMemcpy(maps, h.data(), n_maps * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
     key.model = ctx->model; key.xn = o->xn; key.att = o->att; key.hid = o->hid; key.ckv = o->cross_kv; key.B = B;
@@ -1218,68 +1391,120 @@ int cross_kv_precompute(wxb_ctx* ctx, const __nv_bfloat16* enc_out, const DecBuf
   return WXB_OK;
 }
 
-// Launch the persistent step kernel: n_steps consecutive positions starting at *d_pos.
-int launch_steps(wxb_ctx* ctx, const DecBuffers& buf, int mode, int n_steps, const SampleParams& sp, float* logits_out,
-                 long long ldl, cudaStream_t st) {
-  const wxb_dims& D = ctx->model->dims;
-  const int d = D.n_text_state, B = buf.B;
-  const int Bp = (B + 15) & ~15, MT = Bp / 16;
-  const int G = ctx->sm_count;
-  MkParams p = {};
-  p.B = B; p.d = d; p.H = D.n_text_head; p.L = D.n_text_layer; p.V = D.n_vocab; p.TX = D.n_text_ctx;
-  p.mode = mode; p.n_steps = n_steps; p.skip = dec_skip_mask();
-  p.layers = buf.layers; p.maps = buf.maps;
-  p.emb = (const __nv_bfloat16*)wxb_weight(ctx, "dec.emb");
-  p.pos_emb = (const float*)wxb_weight(ctx, "dec.pos");
-  p.lnf_w = (const float*)wxb_weight(ctx, "dec.ln.w");
-  p.lnf_b = (const float*)wxb_weight(ctx, "dec.ln.b");
-  if (!p.emb || !p.pos_emb || !p.lnf_w || !p.lnf_b) return WXB_ERR_STATE;
-  p.tokens = buf.tokens; p.tok_stride = buf.tok_stride; p.d_pos = buf.d_pos;
-  p.x = buf.x; p.xn = buf.xn; p.att = buf.att; p.hid = buf.hid; p.part = buf.part;
-  p.self_kv = buf.self_kv; p.cross_kv = buf.cross_kv;
-  p.logits = logits_out; p.ldl = ldl;
-  p.apart = buf.apart; p.ticket = buf.ticket; p.bar = buf.bar;
-  if (dec_prof_enabled()) {
-    p.prof = (unsigned long long*)wxb_named(ctx, "dec.prof", PROF_SLOTS * 8);
-    if ((size_t)n_steps * (11 * p.L + 4) > (size_t)PROF_XA) p.prof = nullptr;
-    if (p.prof) WXB_CUDA(ctx, cudaMemsetAsync(p.prof + PROF_XA, 0, 32 * 8, st));
-    g_prof_last.mode = mode; g_prof_last.n_steps = n_steps; g_prof_last.L = p.L; g_prof_last.nsp = sp.nsp_out != nullptr;
-    g_prof_last.dev = p.prof;
-  }
-  p.g_qkv = plan_gemv(3 * d, d, B, Bp, G, false);
-  p.g_dd = plan_gemv(d, d, B, Bp, G, false);
-  p.g_fc1 = plan_gemv(4 * d, d, B, Bp, G, true);
-  p.g_fc2 = plan_gemv(d, 4 * d, B, Bp, G, false);
-  p.g_logits = plan_gemv(D.n_vocab, d, B, Bp, G, true);
-  if (!p.g_qkv.gk || !p.g_dd.gk || !p.g_fc1.gk || !p.g_fc2.gk || !p.g_logits.gk)
-    return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: no GEMV tiling fits (d=%d, batch %d)", d, B);
-  p.sp = sp;
-  p.scale = 1.0f / sqrtf(64.f);
-  const size_t smem = MK_SMEM;
-  void (*kern)(const MkParams) = MT == 1 ? dec_step_kernel<1> : MT == 2 ? dec_step_kernel<2> : MT == 3 ? dec_step_kernel<3> : dec_step_kernel<4>;
-  static bool attr_set[5] = {false, false, false, false, false};
-  if (!attr_set[MT]) {
-    WXB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MK_SMEM));
+template <int MT, int OCC>
+int launch_instance(wxb_ctx* ctx, const MkLaunch& L, cudaStream_t st) {
+  auto kern = dec_step_kernel<MT, OCC>;
+  constexpr size_t smem = MkCfg<OCC>::SMEM;
+  static bool attr_set = false;
+  if (!attr_set) {
+    WXB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WXB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 0;
-    WXB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MK_THREADS, MK_SMEM));
-    if (per_sm < 1) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: persistent step kernel does not fit an SM");
-    attr_set[MT] = true;
+    WXB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MK_THREADS, smem));
+    // exactly OCC CTAs per SM: fewer and the grid is not co-resident, more and an SM could host two CTAs of one group
+    if (per_sm != OCC) {
+      cudaFuncAttributes fa = {};
+      cudaFuncGetAttributes(&fa, kern);
+      int sm_smem = 0, occ_half = 0;
+      cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, ctx->device);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_half, kern, MK_THREADS, smem / 2);
+      return wxb_fail(ctx, WXB_ERR_UNSUPPORTED,
+                      "decoder: step kernel occupancy %d CTAs/SM, expected %d (regs %d, static smem %zu, dynamic %zu, max dynamic %d, "
+                      "local %zu, SM smem %d, occupancy at half the dynamic smem %d)",
+                      per_sm, OCC, fa.numRegs, fa.sharedSizeBytes, smem, fa.maxDynamicSharedSizeBytes, fa.localSizeBytes, sm_smem, occ_half);
+    }
+    attr_set = true;
   }
-  WXB_CUDA(ctx, cudaMemsetAsync(buf.bar, 0, 4, st));
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(G);
+  cfg.gridDim = dim3(L.nc * L.n_groups);
   cfg.blockDim = dim3(MK_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident: the grid barrier cannot deadlock
+  attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident: the grid barriers cannot deadlock
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, L);
   ctx->launches++;
   if (e != cudaSuccess) return wxb_fail(ctx, WXB_ERR_CUDA, "decoder step launch failed: %s", cudaGetErrorString(e));
   return WXB_OK;
+}
+
+// Launch the persistent step kernel: n_steps consecutive positions starting at *d_pos, for ng sequence groups at once.
+int launch_steps(wxb_ctx* ctx, const DecBuffers* bufs, int ng, int mode, int n_steps, const SampleParams* sps,
+                 float* const* logits_out, long long ldl, cudaStream_t st) {
+  const wxb_dims& D = ctx->model->dims;
+  const int d = D.n_text_state;
+  const int G = ctx->sm_count;
+  MkLaunch L = {};
+  L.n_groups = ng;
+  L.nc = G;
+  unsigned* sync = (unsigned*)wxb_named(ctx, "dec.sync", (256 + 8) * 4, true);
+  if (!sync) return WXB_ERR_CUDA;
+  L.sm_slots = sync;
+  L.grp_ctas = sync + 256;
+  int MT = 1;
+  for (int g = 0; g < ng; ++g) {
+    const DecBuffers& buf = bufs[g];
+    const int B = buf.B, Bp = (B + 15) & ~15;
+    MT = std::max(MT, Bp / 16);
+    MkParams& p = L.g[g];
+    p.B = B; p.d = d; p.H = D.n_text_head; p.L = D.n_text_layer; p.V = D.n_vocab; p.TX = D.n_text_ctx;
+    p.mode = mode; p.n_steps = n_steps; p.skip = dec_skip_mask(); p.xa_pf = dec_xa_prefetch(ng);
+    p.layers = buf.layers; p.maps = buf.maps;
+    p.emb = (const __nv_bfloat16*)wxb_weight(ctx, "dec.emb");
+    p.pos_emb = (const float*)wxb_weight(ctx, "dec.pos");
+    p.lnf_w = (const float*)wxb_weight(ctx, "dec.ln.w");
+    p.lnf_b = (const float*)wxb_weight(ctx, "dec.ln.b");
+    if (!p.emb || !p.pos_emb || !p.lnf_w || !p.lnf_b) return WXB_ERR_STATE;
+    p.tokens = buf.tokens; p.tok_stride = buf.tok_stride; p.d_pos = buf.d_pos;
+    p.x = buf.x; p.xn = buf.xn; p.att = buf.att; p.hid = buf.hid; p.part = buf.part;
+    p.self_kv = buf.self_kv; p.cross_kv = buf.cross_kv;
+    p.logits = logits_out[g]; p.ldl = ldl;
+    p.apart = buf.apart; p.ticket = buf.ticket; p.bar = buf.bar;
+    if (g == 0 && dec_prof_enabled()) {
+      p.prof = (unsigned long long*)wxb_named(ctx, "dec.prof", PROF_SLOTS * 8);
+      if ((size_t)n_steps * (11 * p.L + 4) > (size_t)PROF_XA) p.prof = nullptr;
+      g_prof_last.mode = mode; g_prof_last.n_steps = n_steps; g_prof_last.L = p.L; g_prof_last.nsp = sps[g].nsp_out != nullptr;
+      g_prof_last.dev = p.prof;
+    }
+    p.g_qkv = plan_gemv(3 * d, d, B, Bp, G, false);
+    p.g_dd = plan_gemv(d, d, B, Bp, G, false);
+    p.g_fc1 = plan_gemv(4 * d, d, B, Bp, G, true);
+    p.g_fc2 = plan_gemv(d, 4 * d, B, Bp, G, false);
+    p.g_logits = plan_gemv(D.n_vocab, d, B, Bp, G, true);
+    if (!p.g_qkv.gk || !p.g_dd.gk || !p.g_fc1.gk || !p.g_fc2.gk || !p.g_logits.gk)
+      return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: no GEMV tiling fits (d=%d, batch %d)", d, B);
+    p.sp = sps[g];
+    p.scale = 1.0f / sqrtf(64.f);
+  }
+  if (MT > (ng == 1 ? 4 : 2)) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: %d sequence groups of up to %d rows", ng, 16 * MT);
+  WXB_CUDA(ctx, cudaMemsetAsync(sync, 0, (256 + 8) * 4, st));
+  switch (ng * 10 + MT) {
+    case 11: return launch_instance<1, 1>(ctx, L, st);
+    case 12: return launch_instance<2, 1>(ctx, L, st);
+    case 13: return launch_instance<3, 1>(ctx, L, st);
+    case 14: return launch_instance<4, 1>(ctx, L, st);
+    case 21: return launch_instance<1, 2>(ctx, L, st);
+    case 22: return launch_instance<2, 2>(ctx, L, st);
+    case 31: return launch_instance<1, 3>(ctx, L, st);
+    case 32: return launch_instance<2, 3>(ctx, L, st);
+  }
+  return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: no kernel instance for %d groups x %d batch tiles", ng, MT);
+}
+
+// Sequence groups decoded side by side by one launch (WXB_DEC_GROUPS overrides; profiling / tuning aid).
+int pick_groups(int B) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("WXB_DEC_GROUPS");
+    forced = e ? atoi(e) : 0;
+  }
+  int ng = forced > 0 ? forced : 1;  // measured on B200: side-by-side groups lose to one group (register budget of 128 / thread)
+  ng = std::min(std::min(ng, MAX_OCC), B);
+  while (ng < MAX_OCC && ceil_div(B, ng) > (ng == 1 ? MAX_GROUP : 32)) ++ng;
+  return ng;
 }
 
 int dump_prof(wxb_ctx* ctx) {
@@ -1309,13 +1534,6 @@ int dump_prof(wxb_ctx* ctx) {
   static const char* tn[4] = {"lnf", "logits", "sample", "x"};
   for (int i = 11; i < 15; ++i) if (cnt[i]) fprintf(stderr, " %s %.2f", tn[i - 11], sum[i] / cnt[i]);
   fprintf(stderr, " | step %.1f us\n", (double)(t[n - 1] - t[0]) * 1e-3 / P.n_steps);
-  unsigned long long xa[16];
-  WXB_CUDA(ctx, cudaMemcpy(xa, P.dev + PROF_XA, sizeof(xa), cudaMemcpyDeviceToHost));
-  for (int w = 0; w < 2; ++w)
-    if (xa[8 * w + 5])
-      fprintf(stderr, "[wxb dec prof] cross-attention warp %d of CTA 0, kcycles per phase: wait+ldmatrix %.1f item-start %.1f producer %.1f math %.1f item-end %.1f | in phase %.1f\n",
-              w, xa[8 * w] * 1e-3 / xa[8 * w + 5], xa[8 * w + 1] * 1e-3 / xa[8 * w + 5], xa[8 * w + 2] * 1e-3 / xa[8 * w + 5],
-              xa[8 * w + 3] * 1e-3 / xa[8 * w + 5], xa[8 * w + 4] * 1e-3 / xa[8 * w + 5], xa[8 * w + 6] * 1e-3 / xa[8 * w + 5]);
   return WXB_OK;
 }
 
@@ -1323,8 +1541,7 @@ int dump_prof(wxb_ctx* ctx) {
 
 void wxb_decoder_reset_graphs() {
   g_layers_model = nullptr;
-  g_maps_key[0] = MapsKey();
-  g_maps_key[1] = MapsKey();
+  for (int i = 0; i < MAX_OCC; ++i) g_maps_key[i] = MapsKey();
 }
 
 extern "C" int wxb_decode_greedy(wxb_ctx* ctx, const void* enc_out_dev, int B, const int32_t* prompt_host, int prompt_len,
@@ -1345,43 +1562,26 @@ extern "C" int wxb_decode_greedy(wxb_ctx* ctx, const void* enc_out_dev, int B, c
   WXB_CUDA(ctx, cudaSetDevice(ctx->device));
   const int stride = D.n_text_ctx + 1;
   int rc;
-  // Batch groups: one persistent kernel decodes up to 64 sequences; larger batches are two groups on two
-  // private streams (own buffers).
-  const int ng = (B > MAX_GROUP) ? 2 : 1;
-  if (B > MAX_GROUP * ng) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "wxb_decode_greedy: at most %d sequences per call", MAX_GROUP * 2);
-  cudaStream_t sg[2] = {st, st};
-  if (ng == 2) {
-    for (int g = 0; g < 2; ++g) {
-      if (!ctx->dec_streams[g]) {
-        cudaStream_t s2;
-        WXB_CUDA(ctx, cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
-        ctx->dec_streams[g] = s2;
-      }
-      sg[g] = (cudaStream_t)ctx->dec_streams[g];
-    }
-    if (!ctx->dec_events[0])
-      for (int i = 0; i < 3; ++i) {
-        cudaEvent_t ev;
-        WXB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        ctx->dec_events[i] = ev;
-      }
-  }
-  const int g0[3] = {0, (ng == 2) ? (B + 1) / 2 : B, B};
-  DecBuffers buf[2];
-  SampleParams sp[2];
+  // Sequence groups: the batch is cut into ng independent groups (own buffers, own grid barrier) that one
+  // persistent launch decodes side by side, ng CTAs per SM (see MkLaunch).
+  const int ng = pick_groups(B);
+  if (ceil_div(B, ng) > (ng == 1 ? MAX_GROUP : 32))
+    return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "wxb_decode_greedy: at most %d sequences per call", 32 * MAX_OCC);
+  int g0[MAX_OCC + 1];
+  for (int g = 0; g <= ng; ++g) g0[g] = (int)(((long long)B * g + ng - 1) / ng);
+  DecBuffers buf[MAX_OCC];
+  SampleParams sp[MAX_OCC];
+  float* lg[MAX_OCC];
   for (int g = 0; g < ng; ++g) {
     const int Bg = g0[g + 1] - g0[g];
     if ((rc = alloc_buffers(ctx, Bg, stride, g, &buf[g])) != WXB_OK) return rc;
+    lg[g] = buf[g].logits;
   }
   wxb_dec_timing tm;
   WXB_CUDA(ctx, cudaEventCreate(&tm.e0));
   WXB_CUDA(ctx, cudaEventCreate(&tm.e1));
   WXB_CUDA(ctx, cudaEventCreate(&tm.e2));
   WXB_CUDA(ctx, cudaEventRecord(tm.e0, st));
-  if (ng == 2) {
-    WXB_CUDA(ctx, cudaEventRecord((cudaEvent_t)ctx->dec_events[0], st));
-    for (int g = 0; g < 2; ++g) WXB_CUDA(ctx, cudaStreamWaitEvent(sg[g], (cudaEvent_t)ctx->dec_events[0], 0));
-  }
   std::vector<int> init((size_t)B * stride, opts->eot);
   for (int b = 0; b < B; ++b)
     for (int i = 0; i < prompt_len; ++i) init[(size_t)b * stride + i] = prompt_host[i];
@@ -1389,11 +1589,11 @@ extern "C" int wxb_decode_greedy(wxb_ctx* ctx, const void* enc_out_dev, int B, c
   for (int g = 0; g < ng; ++g) {
     const int Bg = buf[g].B;
     // tokens[b, :prompt_len] = prompt; state reset
-    WXB_CUDA(ctx, cudaMemcpyAsync(buf[g].tokens, init.data() + (size_t)g0[g] * stride, (size_t)Bg * stride * 4, cudaMemcpyHostToDevice, sg[g]));
-    WXB_CUDA(ctx, cudaMemsetAsync(buf[g].d_pos, 0, 4, sg[g]));
-    WXB_CUDA(ctx, cudaMemsetAsync(buf[g].done, 0, (size_t)Bg * 4, sg[g]));
-    WXB_CUDA(ctx, cudaMemsetAsync(buf[g].sum_lp, 0, (size_t)Bg * 4, sg[g]));
-    if ((rc = cross_kv_precompute(ctx, (const __nv_bfloat16*)enc_out_dev + (size_t)g0[g] * enc_row, buf[g], sg[g])) != WXB_OK) return rc;
+    WXB_CUDA(ctx, cudaMemcpyAsync(buf[g].tokens, init.data() + (size_t)g0[g] * stride, (size_t)Bg * stride * 4, cudaMemcpyHostToDevice, st));
+    WXB_CUDA(ctx, cudaMemsetAsync(buf[g].d_pos, 0, 4, st));
+    WXB_CUDA(ctx, cudaMemsetAsync(buf[g].done, 0, (size_t)Bg * 4, st));
+    WXB_CUDA(ctx, cudaMemsetAsync(buf[g].sum_lp, 0, (size_t)Bg * 4, st));
+    if ((rc = cross_kv_precompute(ctx, (const __nv_bfloat16*)enc_out_dev + (size_t)g0[g] * enc_row, buf[g], st)) != WXB_OK) return rc;
     SampleParams& s1 = sp[g];
     s1 = SampleParams{};
     s1.logits = buf[g].logits; s1.V = D.n_vocab; s1.tokens = buf[g].tokens; s1.stride = stride;
@@ -1401,18 +1601,22 @@ extern "C" int wxb_decode_greedy(wxb_ctx* ctx, const void* enc_out_dev, int B, c
     s1.n_suppress = opts->n_suppress; s1.suppress = opts->suppress_dev; s1.sum_logprob = buf[g].sum_lp; s1.done = buf[g].done;
     s1.nsp_out = nullptr; s1.nsp_token = opts->no_speech;
   }
-  for (int g = 0; g < ng; ++g) WXB_CUDA(ctx, cudaStreamSynchronize(sg[g]));  // `init` is pageable host memory
-  WXB_CUDA(ctx, cudaEventRecord(tm.e1, sg[0]));
+  WXB_CUDA(ctx, cudaStreamSynchronize(st));  // `init` is pageable host memory
+  WXB_CUDA(ctx, cudaEventRecord(tm.e1, st));
 
   const bool want_nsp = (opts->no_speech >= 0 && no_speech_prob_dev);
+  auto with_nsp = [&](SampleParams* dst, bool nsp) {
+    for (int g = 0; g < ng; ++g) {
+      dst[g] = sp[g];
+      if (nsp) dst[g].nsp_out = no_speech_prob_dev + g0[g];
+    }
+  };
   // prompt positions 0 .. prompt_len-2 (forced tokens); logits only at position 0 for no_speech_prob
   for (int pos = 0; pos < prompt_len - 1; ++pos) {
-    for (int g = 0; g < ng; ++g) {
-      SampleParams s1 = sp[g];
-      const bool nsp = (pos == 0 && want_nsp);
-      if (nsp) s1.nsp_out = no_speech_prob_dev + g0[g];
-      if ((rc = launch_steps(ctx, buf[g], nsp ? 1 : 0, 1, s1, buf[g].logits, D.n_vocab, sg[g])) != WXB_OK) return rc;
-    }
+    SampleParams s1[MAX_OCC];
+    const bool nsp = (pos == 0 && want_nsp);
+    with_nsp(s1, nsp);
+    if ((rc = launch_steps(ctx, buf, ng, nsp ? 1 : 0, 1, s1, lg, D.n_vocab, st)) != WXB_OK) return rc;
   }
   const int check_every = opts->check_every > 0 ? opts->check_every : 16;
   std::vector<int> done_host(B);
@@ -1421,30 +1625,24 @@ extern "C" int wxb_decode_greedy(wxb_ctx* ctx, const void* enc_out_dev, int B, c
     // a single-token prompt makes the SOT position the first sampling position: that step also emits no_speech_prob
     const bool nsp_now = (n_sampled == 0 && prompt_len == 1 && want_nsp);
     const int n = nsp_now ? 1 : std::min(check_every, sample_len - n_sampled);
-    for (int g = 0; g < ng; ++g) {
-      SampleParams s1 = sp[g];
-      if (nsp_now) s1.nsp_out = no_speech_prob_dev + g0[g];
-      if ((rc = launch_steps(ctx, buf[g], 2, n, s1, buf[g].logits, D.n_vocab, sg[g])) != WXB_OK) return rc;
-    }
+    SampleParams s1[MAX_OCC];
+    with_nsp(s1, nsp_now);
+    if ((rc = launch_steps(ctx, buf, ng, 2, n, s1, lg, D.n_vocab, st)) != WXB_OK) return rc;
     n_sampled += n;
     if (n_sampled < sample_len && !nsp_now) {
       for (int g = 0; g < ng; ++g)
-        WXB_CUDA(ctx, cudaMemcpyAsync(done_host.data() + g0[g], buf[g].done, (size_t)buf[g].B * 4, cudaMemcpyDeviceToHost, sg[g]));
-      for (int g = 0; g < ng; ++g) WXB_CUDA(ctx, cudaStreamSynchronize(sg[g]));
+        WXB_CUDA(ctx, cudaMemcpyAsync(done_host.data() + g0[g], buf[g].done, (size_t)buf[g].B * 4, cudaMemcpyDeviceToHost, st));
+      WXB_CUDA(ctx, cudaStreamSynchronize(st));
       bool all = true;
       for (int b = 0; b < B; ++b) all = all && done_host[b];
       if (all) break;  // mlx_whisper_batch_decoder.py:357
     }
   }
   for (int g = 0; g < ng; ++g) {
-    dec_finalize_kernel<<<buf[g].B, 256, 0, sg[g]>>>(buf[g].tokens, stride, prompt_len, n_sampled, sample_len, opts->eot,
-                                                   tokens_out_dev + (size_t)g0[g] * sample_len, n_tokens_dev + g0[g]);
+    dec_finalize_kernel<<<buf[g].B, 256, 0, st>>>(buf[g].tokens, stride, prompt_len, n_sampled, sample_len, opts->eot,
+                                                  tokens_out_dev + (size_t)g0[g] * sample_len, n_tokens_dev + g0[g]);
     WXB_LAUNCH_CHECK(ctx);
-    WXB_CUDA(ctx, cudaMemcpyAsync(sum_logprob_dev + g0[g], buf[g].sum_lp, (size_t)buf[g].B * 4, cudaMemcpyDeviceToDevice, sg[g]));
-    if (ng == 2) {
-      WXB_CUDA(ctx, cudaEventRecord((cudaEvent_t)ctx->dec_events[1 + g], sg[g]));
-      WXB_CUDA(ctx, cudaStreamWaitEvent(st, (cudaEvent_t)ctx->dec_events[1 + g], 0));
-    }
+    WXB_CUDA(ctx, cudaMemcpyAsync(sum_logprob_dev + g0[g], buf[g].sum_lp, (size_t)buf[g].B * 4, cudaMemcpyDeviceToDevice, st));
   }
   WXB_CUDA(ctx, cudaEventRecord(tm.e2, st));
   tm.steps = prompt_len - 1 + n_sampled;
@@ -1490,7 +1688,9 @@ extern "C" int wxb_decoder_logits(wxb_ctx* ctx, const void* enc_out_dev, int B, 
   WXB_CUDA(ctx, cudaMemsetAsync(buf.d_pos, 0, 4, st));
   if ((rc = cross_kv_precompute(ctx, (const __nv_bfloat16*)enc_out_dev, buf, st)) != WXB_OK) return rc;
   SampleParams sp = {};
-  for (int pos = 0; pos < n_tok; ++pos)
-    if ((rc = launch_steps(ctx, buf, 1, 1, sp, logits_out_dev + (size_t)pos * D.n_vocab, (long long)n_tok * D.n_vocab, st)) != WXB_OK) return rc;
+  for (int pos = 0; pos < n_tok; ++pos) {
+    float* lg = logits_out_dev + (size_t)pos * D.n_vocab;
+    if ((rc = launch_steps(ctx, &buf, 1, 1, 1, &sp, &lg, (long long)n_tok * D.n_vocab, st)) != WXB_OK) return rc;
+  }
   return WXB_OK;
 }
