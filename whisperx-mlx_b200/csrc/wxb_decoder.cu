@@ -70,14 +70,14 @@ constexpr int QRAW_BYTES = 2 * QRAW_ROWS * 64 * 4;        // two items in flight
 constexpr int SCRATCH_BYTES = SST_BYTES + QRAW_BYTES;     // attention scratch behind the ring
 template <int OCC>
 struct MkCfg {
-  static constexpr int XA_NST = OCC == 1 ? 6 : OCC == 2 ? 3 : 2;
-  static constexpr int GV_NST = OCC == 1 ? 6 : OCC == 2 ? 4 : 2;
+  static constexpr int XA_NST = OCC == 1 ? 6 : 3;
+  static constexpr int GV_NST = OCC == 1 ? 6 : 4;
   static constexpr int MT_MAX = OCC == 1 ? 4 : 2;         // m16 batch tiles per group
   static constexpr int RING_BYTES = XA_NST * 2 * XA_HALF;
   static constexpr size_t SMEM = RING_BYTES + SCRATCH_BYTES + 1024;
   static_assert(GV_NST * (GV_A_BYTES + 16 * MT_MAX * GV_BK * 2) <= RING_BYTES, "GEMV ring must fit the shared region");
 };
-constexpr int MAX_OCC = 3;
+constexpr int MAX_OCC = 2;
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -165,14 +165,14 @@ struct MkParams {
   float scale;
 };
 
-// One launch decodes up to MAX_OCC independent sequence groups: the grid holds n_groups x nc CTAs, exactly
-// n_groups per SM (the shared-memory footprint allows no more), and every SM hosts one CTA of every group.
-// While one group streams its cross-attention K/V, the latency-bound GEMV / LayerNorm chain of the others runs
-// underneath on the same SMs; groups never synchronise with each other (own buffers, own grid barrier).
+// Kernel parameter.  n_groups == 1: one group, one CTA per SM, every CTA walks the whole schedule.
+// n_groups == 2: split roles, 2 x nc CTAs, two per SM (see dec_step_kernel).
 struct MkLaunch {
   int n_groups, nc;
-  unsigned* sm_slots;  // [256] zero-initialised per launch: arrival order of the CTAs of one SM
-  unsigned* grp_ctas;  // [MAX_OCC] zero-initialised per launch: CTAs that joined each group so far
+  unsigned* sm_slots;   // [256] zero-initialised per launch: arrival order of the CTAs of one SM
+  unsigned* role_ctas;  // [2]   zero-initialised per launch: CTAs seated per role
+  unsigned* y_bar;      // [2 teams, 32 words apart] grid barriers of the chain teams (the cross CTAs poll them)
+  unsigned* x_done;     // [2 groups, 32 words apart] consumer warps of cross CTAs that finished a phase
   MkParams g[MAX_OCC];
 };
 
@@ -759,9 +759,13 @@ __device__ __forceinline__ void xa_block(const uint32_t (*ka)[4][4], const uint3
 // partials of the cq GEMV) of the next items, every consumer warp sums them for itself, deposits its (m, l, O) state of
 // a finished item in a double-buffered shared-memory slot and moves straight on; consumer warp (item % 7) merges the
 // 7 states once all have arrived (mbarrier) and writes the output.
+// Split-role launches (see dec_step_kernel) pass `y_bar` / `y_need` / `x_done`: the q rows of the phase's first item are
+// staged only once the chain CTAs' barrier counter has reached y_need (their cq GEMV is complete grid-wide), K/V
+// stages are requested before that, and every consumer warp reports the end of its work list on x_done.
 template <int XA_NST>
 __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const float* __restrict__ cq_b, uint8_t* ring,
-                                                 float* scratch, MkSync& sy) {
+                                                 float* scratch, MkSync& sy, const unsigned* y_bar = nullptr, unsigned y_need = 0,
+                                                 unsigned* x_done = nullptr) {
   constexpr uint32_t STAGE = 2 * XA_HALF;
   float* sst = scratch;                                                                          // [2 item parities][7 warps][66]: m, l, O[64]
   float* qraw = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(scratch) + SST_BYTES);      // [2 item parities][QRAW_ROWS][64]
@@ -789,6 +793,49 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
     XaItem x = {}, px = {};
     if (n_items > 0) { x = xa_item(0, cta, qw, G, P, plen); kk = x.k0; px = x; pkk = kk; }
     uint32_t issued = sy.xa_count;
+    int q_item = 0;  // next item whose q rows have not been staged yet
+    // the first item's q rows wait until XA_NST of its stages are on their way (or all of them, if fewer)
+    int q_hold = 0;
+    if (y_bar && n_items > 0) {
+      int n0 = 0;
+      for (int i = 0, acc = 0; i < n_items && acc < XA_NST; ++i) {
+        const XaItem xi = xa_item(i, cta, qw, G, P, plen);
+        acc += (xi.k1 - xi.k0 + XA_KEYS - 1) / XA_KEYS;
+        n0 = acc;
+      }
+      q_hold = n0 < XA_NST ? n0 : XA_NST;
+    }
+    auto stage_q = [&](int qi) {
+      // raw q rows of item qi (row gk = bias, rows 0 .. gk-1 = split-K partials of the cq GEMV), 2 rows per pass
+      const XaItem xq = xa_item(qi, cta, qw, G, P, plen);
+      const uint32_t gi = sy.xa_items + (uint32_t)qi, qpar = gi & 1;
+      mbar_wait(sy.mb(MB_Q_FREE + qpar), ((gi >> 1) & 1) ^ 1);  // the consumers have used the rows of item gi - 2
+      float* dst = qraw + qpar * (QRAW_ROWS * 64);
+      const int b = xq.slab / H, h = xq.slab - b * H;
+      const int half = lane >> 4, l16 = lane & 15;
+      for (int r0 = 0; r0 <= gk; r0 += 2) {
+        const int row = r0 + half;
+        if (row <= gk) {
+          const float* src = (row == gk) ? (cq_b + h * 64) : (part_q + ((size_t)row * B + b) * d + h * 64);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + row * 64 + l16 * 4)), "l"(src + l16 * 4) : "memory");
+        }
+      }
+      cp_async_mbar_arrive(sy.mb(MB_Q_FULL + qpar));
+    };
+    auto stage_upto = [&](int last) {
+      if (q_item == 0 && y_bar) {
+        // the chain CTAs have finished this phase's cq GEMV once their barrier counter reaches y_need
+        if (lane == 0) {
+          unsigned v, spins = 0;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(y_bar) : "memory");
+            if (++spins > (1u << 26)) __trap();
+          } while ((int)(v - y_need) < 0);
+        }
+        __syncwarp();
+      }
+      while (q_item <= last) stage_q(q_item++);
+    };
     while (it < n_items) {
       if (xa_pf > 0) {
         while (pit < n_items && ahead <= xa_pf) {
@@ -805,22 +852,7 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
           }
         }
       }
-      if (kk == x.k0) {
-        // first stage of an item: its raw q rows (row gk = bias, rows 0 .. gk-1 = split-K partials), 2 rows per pass
-        const uint32_t gi = sy.xa_items + (uint32_t)it, qpar = gi & 1;
-        mbar_wait(sy.mb(MB_Q_FREE + qpar), ((gi >> 1) & 1) ^ 1);  // the consumers have used the rows of item gi - 2
-        float* dst = qraw + qpar * (QRAW_ROWS * 64);
-        const int b = x.slab / H, h = x.slab - b * H;
-        const int half = lane >> 4, l16 = lane & 15;
-        for (int r0 = 0; r0 <= gk; r0 += 2) {
-          const int row = r0 + half;
-          if (row <= gk) {
-            const float* src = (row == gk) ? (cq_b + h * 64) : (part_q + ((size_t)row * B + b) * d + h * 64);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + row * 64 + l16 * 4)), "l"(src + l16 * 4) : "memory");
-          }
-        }
-        cp_async_mbar_arrive(sy.mb(MB_Q_FULL + qpar));
-      }
+      if (q_item <= it && (int)(issued - sy.xa_count) >= q_hold) stage_upto(it);
       if (lane == 0) {
         const uint32_t sl = issued % XA_NST, par = (issued / XA_NST) & 1;
         mbar_wait(sy.mb(MB_XA_EMPTY + sl), par ^ 1);
@@ -840,6 +872,7 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
         if (it < n_items) { x = xa_item(it, cta, qw, G, P, plen); kk = x.k0; }
       }
     }
+    if (q_item < n_items) stage_upto(n_items - 1);  // fewer stages than the hold-back in this CTA's whole list
   } else {
     // ------------------------------- consumer warps -------------------------------
     const int cw = warp - 1;
@@ -848,6 +881,10 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
     const int rowV = cw * 16 + (lane & 7) + ((lane >> 4) & 1) * 8, chV = (lane >> 3) & 1;   // V (transposed): chunk 2 mt + chV
     const int sw = lane & 7;
     uint32_t consumed = sy.xa_count;
+    // WXB_DEC_PROF (split roles): consumer warp 1 of cross CTA 0 splits the phase into waiting for q and streaming
+    unsigned long long* xprof = (x_done && p.prof && cta == 0 && warp == 1 && lane == 0) ? p.prof + PROF_XA : nullptr;
+    unsigned long long t_enter = 0, t_q = 0;
+    if (xprof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_enter));
     for (int it = 0; it < n_items; ++it) {
       const XaItem x = xa_item(it, cta, qw, G, P, plen);
       const int b = x.slab / H, h = x.slab - b * H;
@@ -855,6 +892,7 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
       const uint32_t ipar = gi & 1, iph = (gi >> 1) & 1;
       // scaled q = (bias + split-K partials in slice order) * scale; lane holds dims lane and lane + 32
       mbar_wait(sy.mb(MB_Q_FULL + ipar), iph);
+      if (xprof && it == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_q));
       float qn0, qn1;
       {
         const float* qr = qraw + ipar * (QRAW_ROWS * 64);
@@ -968,6 +1006,16 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
         }
       }
     }
+    if (xprof) {
+      unsigned long long t_end;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+      xprof[0] += t_q - t_enter; xprof[1] += t_end - t_q; xprof[2] += 1;
+    }
+  }
+  if (x_done && warp != 0) {
+    // this warp's outputs (merges it performed) are written: report to the chain CTAs
+    __syncwarp();
+    if (lane == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(x_done) : "memory");
   }
   // every thread advances the uniform cursors by this CTA's work list
   {
@@ -1071,132 +1119,207 @@ __device__ __forceinline__ void sample_phase(const SampleParams& p, int B, int p
 // phase kinds of the step schedule: 11 per layer, then final LN | logits | sampling
 enum { PH_LN = 0, PH_GEMV = 1, PH_SELF = 2, PH_CROSS = 3, PH_SAMPLE = 4 };
 
-// The step loop of one CTA.  `p` must be a compile-time-indexed member of the kernel parameter, so that every p.field
-// is a constant-bank operand: behind a run-time group index the compiler loads the fields instead and hoists dozens
-// of them into registers across the whole phase loop.
+// One operator of the step schedule for one sequence group.  `p` must be a compile-time-indexed member of the kernel
+// parameter, so that every p.field is a constant-bank operand.
+// k: 0 LN1 | 1 QKV | 2 self-attention | 3 out | 4 LN2 | 5 cq | 6 cross-attention | 7 cout | 8 LN3 | 9 fc1 | 10 fc2
+//    11 final LN | 12 logits | 13 (no_speech_prob,) filters + sampling
 template <int MT, int OCC>
-__device__ __forceinline__ void dec_step_body(const MkParams& p, const int cta, const int nc) {
+__device__ __forceinline__ void run_op(const MkParams& p, const DecLayerW* s_layers, int l, int k, int pos, uint8_t* ring,
+                                       float* scratch, float* red, int* red_i, MkSync& sy) {
   using C = MkCfg<OCC>;
-  constexpr int GV_NST = C::GV_NST, XA_NST = C::XA_NST;
-  extern __shared__ uint8_t mk_smem_raw[];
-  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(mk_smem_raw) + 1023) & ~(uintptr_t)1023);
-  float* scratch = reinterpret_cast<float*>(ring + C::RING_BYTES);
-  __shared__ float red[MK_WARPS];
-  __shared__ int red_i[MK_WARPS];
-  __shared__ __align__(8) uint64_t bars[MB_COUNT];
-  __shared__ uint32_t tmem_slot;
-  __shared__ DecLayerW s_layers[MAX_LAYERS];  // pointer table of every layer: no dependent global load per phase
-  for (int i = threadIdx.x; i < p.L * (int)(sizeof(DecLayerW) / 8); i += MK_THREADS)
-    reinterpret_cast<unsigned long long*>(s_layers)[i] = reinterpret_cast<const unsigned long long*>(p.layers)[i];
-  const int warp = threadIdx.x >> 5;
-  MkSync sy;
-  sy.cta = cta; sy.nc = nc;
-  sy.bars = smem_u32(bars);
-  sy.gv_count = 0; sy.acc_count = 0; sy.xa_count = 0; sy.xa_items = 0;
+  const DecLayerW& w = s_layers[l];
+  const int kind = (k == 0 || k == 4 || k == 8 || k == 11) ? PH_LN : (k == 2) ? PH_SELF : (k == 6) ? PH_CROSS : (k == 13) ? PH_SAMPLE : PH_GEMV;
+  if (kind == PH_LN) {
+    if (!(p.skip & 8)) {
+      // the LayerNorm phase first folds the previous GEMV's split-K partials (+ bias) into the residual row
+      const bool from_embed = (k == 0 && l == 0);
+      const int gk = (k == 0 || k == 11) ? p.g_fc2.gk : p.g_dd.gk;
+      const float* pb = (k == 0) ? (l > 0 ? s_layers[l - 1].fc2_b : nullptr) : (k == 4) ? w.out_b : (k == 8) ? w.cout_b : w.fc2_b;
+      const float* lw = (k == 0) ? w.ln1_w : (k == 4) ? w.ln2_w : (k == 8) ? w.ln3_w : p.lnf_w;
+      const float* lb = (k == 0) ? w.ln1_b : (k == 4) ? w.ln2_b : (k == 8) ? w.ln3_b : p.lnf_b;
+      ln_phase(p, from_embed, gk, pb, lw, lb, pos, red, sy);
+    }
+  } else if (kind == PH_GEMV) {
+    if (!(p.skip & 2)) {
+      const CUtensorMap* lm = p.maps + (size_t)l * TM_PER_LAYER;
+      const CUtensorMap* am = p.maps + (size_t)p.L * TM_PER_LAYER;  // emb, xn, att, hid
+      const MkGemv& g = (k == 1) ? p.g_qkv : (k == 9) ? p.g_fc1 : (k == 10) ? p.g_fc2 : (k == 12) ? p.g_logits : p.g_dd;
+      const CUtensorMap* wm = (k == 1) ? lm + TM_QKV : (k == 3) ? lm + TM_OUT : (k == 5) ? lm + TM_CQ : (k == 7) ? lm + TM_COUT
+                              : (k == 9) ? lm + TM_FC1 : (k == 10) ? lm + TM_FC2 : am;
+      const CUtensorMap* xm = (k == 3 || k == 7) ? am + 2 : (k == 10) ? am + 3 : am + 1;
+      const int epi = (k == 9) ? EPI_GELU_BF16 : (k == 12) ? EPI_LOGITS : EPI_PART;
+      if constexpr (OCC == 1) gemv_phase<MT, C::GV_NST>(p, g, wm, xm, w.fc1_b, epi, ring, sy);
+      else gemv_phase_mma<MT, C::GV_NST>(p, g, wm, xm, w.fc1_b, epi, ring, sy);
+    }
+  } else if (kind == PH_SELF) {
+    if (!(p.skip & 4)) self_attn_phase(p, l, w.qkv_b, pos, sy);
+  } else if (kind == PH_CROSS) {
+    if constexpr (OCC == 1) {
+      if (!(p.skip & 1)) cross_attn_phase<C::XA_NST>(p, l, w.cq_b, ring, scratch, sy);
+    }
+  } else {
+    sample_phase(p.sp, p.B, pos, p.mode == 2, red, red_i, sy);
+  }
+}
+
+template <int OCC>
+__device__ __forceinline__ void init_barriers(const MkSync& sy) {
+  using C = MkCfg<OCC>;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < GV_NST; ++i) { mbar_init(sy.mb(MB_GV_FULL + i), 1); mbar_init(sy.mb(MB_GV_EMPTY + i), OCC == 1 ? 1 : MK_WARPS); }
+    for (int i = 0; i < C::GV_NST; ++i) { mbar_init(sy.mb(MB_GV_FULL + i), 1); mbar_init(sy.mb(MB_GV_EMPTY + i), OCC == 1 ? 1 : MK_WARPS); }
     mbar_init(sy.mb(MB_ACC_FULL), 1);
-    for (int i = 0; i < XA_NST; ++i) { mbar_init(sy.mb(MB_XA_FULL + i), 1); mbar_init(sy.mb(MB_XA_EMPTY + i), XA_CW); }
+    for (int i = 0; i < C::XA_NST; ++i) { mbar_init(sy.mb(MB_XA_FULL + i), 1); mbar_init(sy.mb(MB_XA_EMPTY + i), XA_CW); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(sy.mb(MB_ST_FULL + i), XA_CW); mbar_init(sy.mb(MB_ST_FREE + i), 1);
       mbar_init(sy.mb(MB_Q_FULL + i), 32); mbar_init(sy.mb(MB_Q_FREE + i), XA_CW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if constexpr (OCC == 1) {  // tensor memory only where the tcgen05 GEMV runs (it pins the kernel to one CTA per SM)
-    if (warp == 2) tmem_alloc(&tmem_slot, 64);
-    tc_fence_before();
-  }
-  __syncthreads();
-  if constexpr (OCC == 1) {
-    tc_fence_after();
-    sy.tmem = tmem_slot;
-  } else {
-    sy.tmem = 0;
-  }
+}
 
+// operators per decode step of one group in the chain schedule (the cross-attention slot 6 included)
+__device__ __forceinline__ int ops_per_step(const MkParams& p) {
+  return 11 * p.L + (p.mode >= 1 ? 2 : 0) + ((p.mode == 2 || p.sp.nsp_out) ? 1 : 0);
+}
+
+// ---- one group, one CTA per SM: every CTA walks the whole schedule, operators separated by grid barriers ----
+template <int MT>
+__device__ __forceinline__ void dec_step_body(const MkParams& p, uint8_t* ring, float* scratch, float* red, int* red_i,
+                                              const DecLayerW* s_layers, uint32_t* tmem_slot, MkSync& sy) {
+  const int warp = threadIdx.x >> 5;
+  if (warp == 2) tmem_alloc(tmem_slot, 64);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  sy.tmem = *tmem_slot;
   unsigned bar_target = 0;
   int prof_n = 0;
   const int pos0 = *p.d_pos;  // written only after the last barrier of this launch
-  const int tail = (p.mode >= 1 ? 2 : 0) + ((p.mode == 2 || p.sp.nsp_out) ? 1 : 0);
-  const int n_ph = 11 * p.L + tail;
+  const int n_ph = ops_per_step(p);
   for (int s = 0; s < p.n_steps; ++s) {
     const int pos = pos0 + s;
     for (int ph = 0; ph < n_ph; ++ph) {
       int l = ph / 11, k = ph - 11 * l;
       if (l >= p.L) { k = 11 + (ph - 11 * p.L); l = p.L - 1; }
-      const DecLayerW& w = s_layers[l];
-      // k: 0 LN1 | 1 QKV | 2 self-attention | 3 out | 4 LN2 | 5 cq | 6 cross-attention | 7 cout | 8 LN3 | 9 fc1 | 10 fc2
-      //    11 final LN | 12 logits | 13 (no_speech_prob,) filters + sampling
-      const int kind = (k == 0 || k == 4 || k == 8 || k == 11) ? PH_LN : (k == 2) ? PH_SELF : (k == 6) ? PH_CROSS : (k == 13) ? PH_SAMPLE : PH_GEMV;
-      if (kind == PH_LN) {
-        if (!(p.skip & 8)) {
-          // the LayerNorm phase first folds the previous GEMV's split-K partials (+ bias) into the residual row
-          const bool from_embed = (k == 0 && l == 0);
-          const int gk = (k == 0 || k == 11) ? p.g_fc2.gk : p.g_dd.gk;
-          const float* pb = (k == 0) ? (l > 0 ? s_layers[l - 1].fc2_b : nullptr) : (k == 4) ? w.out_b : (k == 8) ? w.cout_b : w.fc2_b;
-          const float* lw = (k == 0) ? w.ln1_w : (k == 4) ? w.ln2_w : (k == 8) ? w.ln3_w : p.lnf_w;
-          const float* lb = (k == 0) ? w.ln1_b : (k == 4) ? w.ln2_b : (k == 8) ? w.ln3_b : p.lnf_b;
-          ln_phase(p, from_embed, gk, pb, lw, lb, pos, red, sy);
-        }
-      } else if (kind == PH_GEMV) {
-        if (!(p.skip & 2)) {
-          const CUtensorMap* lm = p.maps + (size_t)l * TM_PER_LAYER;
-          const CUtensorMap* am = p.maps + (size_t)p.L * TM_PER_LAYER;  // emb, xn, att, hid
-          const MkGemv& g = (k == 1) ? p.g_qkv : (k == 9) ? p.g_fc1 : (k == 10) ? p.g_fc2 : (k == 12) ? p.g_logits : p.g_dd;
-          const CUtensorMap* wm = (k == 1) ? lm + TM_QKV : (k == 3) ? lm + TM_OUT : (k == 5) ? lm + TM_CQ : (k == 7) ? lm + TM_COUT
-                                  : (k == 9) ? lm + TM_FC1 : (k == 10) ? lm + TM_FC2 : am;
-          const CUtensorMap* xm = (k == 3 || k == 7) ? am + 2 : (k == 10) ? am + 3 : am + 1;
-          const int epi = (k == 9) ? EPI_GELU_BF16 : (k == 12) ? EPI_LOGITS : EPI_PART;
-          if constexpr (OCC == 1) gemv_phase<MT, GV_NST>(p, g, wm, xm, w.fc1_b, epi, ring, sy);
-          else gemv_phase_mma<MT, GV_NST>(p, g, wm, xm, w.fc1_b, epi, ring, sy);
-        }
-      } else if (kind == PH_SELF) {
-        if (!(p.skip & 4)) self_attn_phase(p, l, w.qkv_b, pos, sy);
-      } else if (kind == PH_CROSS) {
-        if (!(p.skip & 1)) cross_attn_phase<XA_NST>(p, l, w.cq_b, ring, scratch, sy);
-      } else {
-        sample_phase(p.sp, p.B, pos, p.mode == 2, red, red_i, sy);
-      }
+      run_op<MT, 1>(p, s_layers, l, k, pos, ring, scratch, red, red_i, sy);
       if (ph + 1 < n_ph || s + 1 < p.n_steps) grid_sync(p.bar, bar_target, sy.nc, sy.cta, p.prof, prof_n);
     }
   }
   if (sy.cta == 0 && threadIdx.x == 0) *p.d_pos = pos0 + p.n_steps;
-  if constexpr (OCC == 1) {
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 2) {
-      tc_fence_after();
-      tmem_dealloc(sy.tmem, 64);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(sy.tmem, 64);
+  }
+}
+
+// ---- split roles, two CTAs per SM (no tensor memory: a kernel that allocates it is pinned to one CTA per SM) ----
+// The batch is cut into two sequence groups A and B.  The CHAIN CTAs run the latency-bound operator chain (LayerNorm /
+// GEMV / self-attention / sampling): even ones for group A, odd ones for group B, each team with its own grid barrier,
+// so the two chains are independent of each other.  The CROSS CTA of every SM does nothing but cross-attention: its
+// producer warp streams K/V of (step, layer, group) phases back to back without ever draining, the q rows of a phase
+// are picked up as soon as the team's barrier counter shows that the group's cq GEMV is complete, and a team waits for
+// the phase's completion count before its cout GEMV.  So HBM streams one group's K/V while the other group's chain
+// runs underneath; the stagger between the groups arises by itself (B's first cross-attention queues behind A's).
+__device__ __forceinline__ int chain_ops_per_step(const MkParams& p) { return ops_per_step(p) - p.L; }  // no cross slot
+
+template <int OCC>
+__device__ __forceinline__ void dec_cross_role(const MkLaunch& L, uint8_t* ring, float* scratch, const DecLayerW* s_layers, MkSync& sy) {
+  using C = MkCfg<OCC>;
+  const MkParams& pa = L.g[0];
+  const unsigned team = (unsigned)(L.nc / 2);
+  const int per_step = chain_ops_per_step(pa);
+  for (int s = 0; s < pa.n_steps; ++s)
+    for (int l = 0; l < pa.L; ++l) {
+      if (pa.skip & 1) continue;
+      const unsigned need = team * (unsigned)(s * per_step + 10 * l + 5 + 1);  // barriers a team has passed once its cq GEMV is complete
+      cross_attn_phase<C::XA_NST>(L.g[0], l, s_layers[l].cq_b, ring, scratch, sy, L.y_bar, need, L.x_done);
+      cross_attn_phase<C::XA_NST>(L.g[1], l, s_layers[l].cq_b, ring, scratch, sy, L.y_bar + 32, need, L.x_done + 32);
+    }
+}
+
+template <int MT, int OCC>
+__device__ __forceinline__ void dec_chain_team(const MkParams& p, const unsigned* x_done, unsigned* y_bar, int n_cross_ctas, uint8_t* ring,
+                                               float* scratch, float* red, int* red_i, const DecLayerW* s_layers, MkSync& sy) {
+  unsigned bar_target = 0;
+  int prof_n = 0;
+  const int pos0 = *p.d_pos;
+  const int n_ph = ops_per_step(p);
+  for (int s = 0; s < p.n_steps; ++s) {
+    for (int ph = 0; ph < n_ph; ++ph) {
+      int l = ph / 11, k = ph - 11 * l;
+      if (l >= p.L) { k = 11 + (ph - 11 * p.L); l = p.L - 1; }
+      if (k == 6) continue;  // the cross CTAs' operator
+      if (k == 7 && !(p.skip & 1)) {
+        // the group's cross-attention of this layer is complete once every consumer warp of every cross CTA has reported
+        if (threadIdx.x == 0) {
+          const unsigned need = (unsigned)(n_cross_ctas * XA_CW) * (unsigned)(s * p.L + l + 1);
+          unsigned v, spins = 0;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(x_done) : "memory");
+            if (++spins > (1u << 26)) __trap();
+          } while ((int)(v - need) < 0);
+          fence_proxy_async_all();  // `att` was written by generic stores; thread 0 reads it through TMA next
+        }
+        __syncthreads();
+      }
+      run_op<MT, OCC>(p, s_layers, l, k, pos0 + s, ring, scratch, red, red_i, sy);
+      if (ph + 1 < n_ph || s + 1 < p.n_steps) grid_sync(y_bar, bar_target, sy.nc, sy.cta, p.prof, prof_n);
     }
   }
+  if (sy.cta == 0 && threadIdx.x == 0) *p.d_pos = pos0 + p.n_steps;
 }
 
 template <int MT, int OCC>
 __global__ void __launch_bounds__(MK_THREADS, OCC) dec_step_kernel(const __grid_constant__ MkLaunch L) {
+  using C = MkCfg<OCC>;
+  extern __shared__ uint8_t mk_smem_raw[];
+  uint8_t* ring = mk_smem_raw + ((1024u - (smem_u32(mk_smem_raw) & 1023u)) & 1023u);  // 1024-byte aligned (swizzle atoms)
+  float* scratch = reinterpret_cast<float*>(ring + C::RING_BYTES);
+  __shared__ float red[MK_WARPS];
+  __shared__ int red_i[MK_WARPS];
+  __shared__ __align__(8) uint64_t bars[MB_COUNT];
+  __shared__ uint32_t tmem_slot;
   __shared__ int s_seat[2];
-  // ---- seat: which sequence group this CTA serves, and its index there.  CTAs of one SM take the groups in
-  // arrival order, so every SM hosts one CTA of every group; a full group passes the CTA on to the next one.
-  if (threadIdx.x == 0) {
-    int grp = 0, cta = blockIdx.x;
-    if (L.n_groups > 1) {
+  __shared__ DecLayerW s_layers[MAX_LAYERS];  // pointer table of every layer: no dependent global load per phase
+  const MkParams& p0 = L.g[0];
+  for (int i = threadIdx.x; i < p0.L * (int)(sizeof(DecLayerW) / 8); i += MK_THREADS)
+    reinterpret_cast<unsigned long long*>(s_layers)[i] = reinterpret_cast<const unsigned long long*>(p0.layers)[i];
+  MkSync sy;
+  sy.bars = smem_u32(bars);
+  sy.gv_count = 0; sy.acc_count = 0; sy.xa_count = 0; sy.xa_items = 0; sy.tmem = 0;
+  sy.cta = blockIdx.x; sy.nc = L.nc;
+  init_barriers<OCC>(sy);
+  if constexpr (OCC == 1) {
+    dec_step_body<MT>(L.g[0], ring, scratch, red, red_i, s_layers, &tmem_slot, sy);
+  } else {
+    // ---- seat: the first CTA to arrive on an SM takes the cross role, the second the chain role; a role that is
+    // already complete (nc CTAs) passes the CTA on to the other one, so both roles always end up with nc CTAs.
+    if (threadIdx.x == 0) {
       unsigned smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      grp = (int)(atomicAdd(L.sm_slots + (smid & 255u), 1u) % (unsigned)L.n_groups);
+      int role = (int)(atomicAdd(L.sm_slots + (smid & 255u), 1u) & 1u), idx;
       for (;;) {
-        cta = (int)atomicAdd(L.grp_ctas + grp, 1u);
-        if (cta < L.nc) break;
-        grp = (grp + 1) % L.n_groups;
+        idx = (int)atomicAdd(L.role_ctas + role, 1u);
+        if (idx < L.nc) break;
+        role ^= 1;
       }
+      s_seat[0] = role;
+      s_seat[1] = idx;
     }
-    s_seat[0] = grp;
-    s_seat[1] = cta;
+    __syncthreads();
+    sy.cta = s_seat[1];
+    if (s_seat[0] == 0) {
+      dec_cross_role<OCC>(L, ring, scratch, s_layers, sy);
+    } else {
+      const int team = sy.cta & 1;
+      sy.cta >>= 1;
+      sy.nc = L.nc / 2;
+      if (team == 0) dec_chain_team<MT, OCC>(L.g[0], L.x_done, L.y_bar, L.nc, ring, scratch, red, red_i, s_layers, sy);
+      else dec_chain_team<MT, OCC>(L.g[1], L.x_done + 32, L.y_bar + 32, L.nc, ring, scratch, red, red_i, s_layers, sy);
+    }
   }
-  __syncthreads();
-  const int grp = s_seat[0], cta = s_seat[1];
-  if (OCC == 1 || grp == 0) dec_step_body<MT, OCC>(L.g[0], cta, L.nc);
-  else if (OCC == 2 || grp == 1) dec_step_body<MT, OCC>(L.g[1], cta, L.nc);
-  else dec_step_body<MT, OCC>(L.g[2], cta, L.nc);
 }
 
 // n_tokens[b] = sampled tokens before the first EOT; tokens_out[b, i] = sampled token i (EOT padded)
@@ -1219,6 +1342,10 @@ __global__ void dec_finalize_kernel(const int* __restrict__ tokens, int stride, 
 constexpr int MAX_GROUP = 64;           // sequences per group when the launch holds one group (4 m16 tiles)
 constexpr size_t PART_FLOATS = (size_t)4 << 20;  // 16 MB of fp32 split-K partials per group
 
+// "dec.sync" words: [0, 256) CTAs seated per SM | 256 + {0, 1} CTAs seated per role | 288 grid barrier (one group) or
+// 288, 320 barriers of the two chain teams (split roles) | 352, 384 cross-attention completion counters of groups A, B
+constexpr int SYNC_WORDS = 416, SYNC_ROLES = 256, SYNC_BAR = 288, SYNC_XDONE = 352;
+
 struct DecBuffers {
   float *x, *logits, *part, *apart, *sum_lp;
   __nv_bfloat16 *att, *xn, *hid, *self_kv, *cross_kv;
@@ -1236,7 +1363,7 @@ int dec_xa_prefetch(int ng) {
     const char* e = getenv("WXB_XA_PF");
     v = e ? atoi(e) : -1;
   }
-  return v >= 0 ? v : 0;
+  return v >= 0 ? v : (ng == 2 ? 8 : 0);  // the split-role ring holds 3 stages only: back it with L2 prefetches
 }
 
 // profiling aid only (results become meaningless): WXB_DEC_SKIP bitmask, see MkParams::skip
@@ -1260,7 +1387,7 @@ bool dec_prof_enabled() {
   return v == 1;
 }
 constexpr size_t PROF_SLOTS = 1 << 16;
-struct ProfLast { int mode = 0, n_steps = 0, L = 0; bool nsp = false; unsigned long long* dev = nullptr; } g_prof_last;
+struct ProfLast { int mode = 0, n_steps = 0, L = 0, ng = 1; bool nsp = false; unsigned long long* dev = nullptr; } g_prof_last;
 
 const void* g_layers_model = nullptr;  // the model whose DecLayerW table is resident in "dec.layers"
 
@@ -1316,9 +1443,9 @@ int alloc_buffers(wxb_ctx* ctx, int B, int tok_stride, int group, DecBuffers* o)
   o->cross_kv = (__nv_bfloat16*)wxb_named(ctx, nm("dec.cross_kv").c_str(), (size_t)L * 2 * B * H * T_AUDIO * 64 * 2);
   o->ticket = (int*)wxb_named(ctx, nm("dec.ticket").c_str(), (size_t)1024 * 4, true);
   o->d_pos = (int*)wxb_named(ctx, nm("dec.pos").c_str(), 64);
-  // launch-scoped counters shared by the groups: [256] CTAs seated per SM | [4] CTAs seated per group | [4] grid barriers
-  unsigned* sync = (unsigned*)wxb_named(ctx, "dec.sync", (256 + 8) * 4, true);
-  o->bar = sync ? sync + 256 + 4 + group : nullptr;
+  // launch-scoped counters (zeroed before every launch), see SYNC_* below
+  unsigned* sync = (unsigned*)wxb_named(ctx, "dec.sync", SYNC_WORDS * 4, true);
+  o->bar = sync ? sync + SYNC_BAR : nullptr;
   o->tokens = (int*)wxb_named(ctx, nm("dec.tokens").c_str(), (size_t)B * tok_stride * 4);
   o->done = (int*)wxb_named(ctx, nm("dec.done").c_str(), (size_t)B * 4);
   DecLayerW* layers = (DecLayerW*)wxb_named(ctx, "dec.layers", (size_t)L * sizeof(DecLayerW));
@@ -1416,7 +1543,7 @@ int launch_instance(wxb_ctx* ctx, const MkLaunch& L, cudaStream_t st) {
     attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(L.nc * L.n_groups);
+  cfg.gridDim = dim3(L.nc * OCC);
   cfg.blockDim = dim3(MK_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
@@ -1437,13 +1564,16 @@ int launch_steps(wxb_ctx* ctx, const DecBuffers* bufs, int ng, int mode, int n_s
   const wxb_dims& D = ctx->model->dims;
   const int d = D.n_text_state;
   const int G = ctx->sm_count;
+  const int Gt = ng == 2 ? G / 2 : G;  // CTAs that share one group's GEMV tiles
   MkLaunch L = {};
   L.n_groups = ng;
   L.nc = G;
-  unsigned* sync = (unsigned*)wxb_named(ctx, "dec.sync", (256 + 8) * 4, true);
+  unsigned* sync = (unsigned*)wxb_named(ctx, "dec.sync", SYNC_WORDS * 4, true);
   if (!sync) return WXB_ERR_CUDA;
   L.sm_slots = sync;
-  L.grp_ctas = sync + 256;
+  L.role_ctas = sync + SYNC_ROLES;
+  L.y_bar = sync + SYNC_BAR;
+  L.x_done = sync + SYNC_XDONE;
   int MT = 1;
   for (int g = 0; g < ng; ++g) {
     const DecBuffers& buf = bufs[g];
@@ -1463,24 +1593,26 @@ int launch_steps(wxb_ctx* ctx, const DecBuffers* bufs, int ng, int mode, int n_s
     p.self_kv = buf.self_kv; p.cross_kv = buf.cross_kv;
     p.logits = logits_out[g]; p.ldl = ldl;
     p.apart = buf.apart; p.ticket = buf.ticket; p.bar = buf.bar;
-    if (g == 0 && dec_prof_enabled()) {
-      p.prof = (unsigned long long*)wxb_named(ctx, "dec.prof", PROF_SLOTS * 8);
+    if (dec_prof_enabled()) {
+      p.prof = (unsigned long long*)wxb_named(ctx, "dec.prof", 2 * PROF_SLOTS * 8);
+      if (p.prof && g == 1) p.prof += PROF_SLOTS;
       if ((size_t)n_steps * (11 * p.L + 4) > (size_t)PROF_XA) p.prof = nullptr;
-      g_prof_last.mode = mode; g_prof_last.n_steps = n_steps; g_prof_last.L = p.L; g_prof_last.nsp = sps[g].nsp_out != nullptr;
-      g_prof_last.dev = p.prof;
+      if (p.prof) WXB_CUDA(ctx, cudaMemsetAsync(p.prof + PROF_XA, 0, 32 * 8, st));
+      g_prof_last.ng = ng; g_prof_last.mode = mode; g_prof_last.n_steps = n_steps; g_prof_last.L = p.L; g_prof_last.nsp = sps[g].nsp_out != nullptr;
+      if (g == 0) g_prof_last.dev = p.prof;
     }
-    p.g_qkv = plan_gemv(3 * d, d, B, Bp, G, false);
-    p.g_dd = plan_gemv(d, d, B, Bp, G, false);
-    p.g_fc1 = plan_gemv(4 * d, d, B, Bp, G, true);
-    p.g_fc2 = plan_gemv(d, 4 * d, B, Bp, G, false);
-    p.g_logits = plan_gemv(D.n_vocab, d, B, Bp, G, true);
+    p.g_qkv = plan_gemv(3 * d, d, B, Bp, Gt, false);
+    p.g_dd = plan_gemv(d, d, B, Bp, Gt, false);
+    p.g_fc1 = plan_gemv(4 * d, d, B, Bp, Gt, true);
+    p.g_fc2 = plan_gemv(d, 4 * d, B, Bp, Gt, false);
+    p.g_logits = plan_gemv(D.n_vocab, d, B, Bp, Gt, true);
     if (!p.g_qkv.gk || !p.g_dd.gk || !p.g_fc1.gk || !p.g_fc2.gk || !p.g_logits.gk)
       return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: no GEMV tiling fits (d=%d, batch %d)", d, B);
     p.sp = sps[g];
     p.scale = 1.0f / sqrtf(64.f);
   }
   if (MT > (ng == 1 ? 4 : 2)) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: %d sequence groups of up to %d rows", ng, 16 * MT);
-  WXB_CUDA(ctx, cudaMemsetAsync(sync, 0, (256 + 8) * 4, st));
+  WXB_CUDA(ctx, cudaMemsetAsync(sync, 0, SYNC_WORDS * 4, st));
   switch (ng * 10 + MT) {
     case 11: return launch_instance<1, 1>(ctx, L, st);
     case 12: return launch_instance<2, 1>(ctx, L, st);
@@ -1488,8 +1620,6 @@ int launch_steps(wxb_ctx* ctx, const DecBuffers* bufs, int ng, int mode, int n_s
     case 14: return launch_instance<4, 1>(ctx, L, st);
     case 21: return launch_instance<1, 2>(ctx, L, st);
     case 22: return launch_instance<2, 2>(ctx, L, st);
-    case 31: return launch_instance<1, 3>(ctx, L, st);
-    case 32: return launch_instance<2, 3>(ctx, L, st);
   }
   return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: no kernel instance for %d groups x %d batch tiles", ng, MT);
 }
@@ -1501,9 +1631,9 @@ int pick_groups(int B) {
     const char* e = getenv("WXB_DEC_GROUPS");
     forced = e ? atoi(e) : 0;
   }
-  int ng = forced > 0 ? forced : 1;  // measured on B200: side-by-side groups lose to one group (register budget of 128 / thread)
+  int ng = forced > 0 ? forced : (B >= 16 ? 2 : 1);
   ng = std::min(std::min(ng, MAX_OCC), B);
-  while (ng < MAX_OCC && ceil_div(B, ng) > (ng == 1 ? MAX_GROUP : 32)) ++ng;
+  if (ng == 2 && ceil_div(B, 2) > 32) ng = 1;  // split roles hold two groups of <= 32 sequences
   return ng;
 }
 
@@ -1511,6 +1641,32 @@ int dump_prof(wxb_ctx* ctx) {
   const ProfLast& P = g_prof_last;
   if (!P.dev) return WXB_OK;
   WXB_CUDA(ctx, cudaDeviceSynchronize());
+  if (P.ng == 2) {
+    // split roles: barrier-exit timestamps of chain CTA 0 of team A; its operators exclude the cross-attention slot
+    const int tail = (P.mode >= 1 ? 2 : 0) + ((P.mode == 2 || P.nsp) ? 1 : 0);
+    const int per_step = 10 * P.L + tail, n = per_step * P.n_steps - 1;
+    std::vector<unsigned long long> t(n);
+    WXB_CUDA(ctx, cudaMemcpy(t.data(), P.dev, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    double sum[16] = {0};
+    long cnt[16] = {0};
+    for (int k = 1; k < n; ++k) {
+      const int ph = k % per_step;
+      const int slot = ph < 10 * P.L ? ph % 10 : 10 + (ph - 10 * P.L);
+      sum[slot] += (double)(t[k] - t[k - 1]) * 1e-3; cnt[slot]++;
+    }
+    static const char* names[13] = {"ln1", "qkv", "self", "out", "ln2", "cq", "wait-cross+cout", "ln3", "fc1", "fc2", "lnf", "logits", "sample"};
+    fprintf(stderr, "[wxb dec prof] split roles, team A, %d steps/launch, per-operator mean us (operator + its barrier):", P.n_steps);
+    double layer = 0;
+    for (int i = 0; i < 13; ++i) if (cnt[i]) { fprintf(stderr, " %s %.2f", names[i], sum[i] / cnt[i]); if (i < 10) layer += sum[i] / cnt[i]; }
+    fprintf(stderr, " | layer %.2f | step %.1f us\n", layer, (double)(t[n - 1] - t[0]) * 1e-3 / P.n_steps);
+    for (int g = 0; g < 2; ++g) {
+      unsigned long long xa[3];
+      WXB_CUDA(ctx, cudaMemcpy(xa, P.dev + (size_t)g * PROF_SLOTS + PROF_XA, sizeof(xa), cudaMemcpyDeviceToHost));
+      if (xa[2]) fprintf(stderr, "[wxb dec prof] cross CTA 0, group %c: mean us per phase waiting for q %.2f, streaming %.2f (%llu phases)\n",
+                         'A' + g, xa[0] * 1e-3 / xa[2], xa[1] * 1e-3 / xa[2], xa[2]);
+    }
+    return WXB_OK;
+  }
   const int tail = (P.mode >= 1 ? 2 : 0) + ((P.mode == 2 || P.nsp) ? 1 : 0);
   const int per_step = 11 * P.L + tail;  // phases = barriers per step (the last phase of the launch has none)
   const int n = per_step * P.n_steps - 1;
@@ -1564,9 +1720,9 @@ extern "C" int wxb_decode_greedy(wxb_ctx* ctx, const void* enc_out_dev, int B, c
   int rc;
   // Sequence groups: the batch is cut into ng independent groups (own buffers, own grid barrier) that one
   // persistent launch decodes side by side, ng CTAs per SM (see MkLaunch).
-  const int ng = pick_groups(B);
+  const int ng = (ctx->sm_count & 1) ? 1 : pick_groups(B);  // split roles pair the chain CTAs into two teams
   if (ceil_div(B, ng) > (ng == 1 ? MAX_GROUP : 32))
-    return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "wxb_decode_greedy: at most %d sequences per call", 32 * MAX_OCC);
+    return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "wxb_decode_greedy: at most %d sequences per call", MAX_GROUP);
   int g0[MAX_OCC + 1];
   for (int g = 0; g <= ng; ++g) g0[g] = (int)(((long long)B * g + ng - 1) / ng);
   DecBuffers buf[MAX_OCC];
