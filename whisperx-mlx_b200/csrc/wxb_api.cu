@@ -80,9 +80,6 @@ void wxb_destroy(wxb_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   wxb_model_free(ctx);
-  if (ctx->cap_stream) cudaStreamDestroy((cudaStream_t)ctx->cap_stream);
-  for (void* s2 : ctx->dec_streams) if (s2) cudaStreamDestroy((cudaStream_t)s2);
-  for (void* e2 : ctx->dec_events) if (e2) cudaEventDestroy((cudaEvent_t)e2);
   wxb_buf* bufs[] = {&ctx->ws_ctc_trellis, &ctx->ws_ctc_hist, &ctx->ws_ctc_meta, &ctx->ws_mel_max,
                      &ctx->ws_mel_band};
   for (wxb_buf* b : bufs)

@@ -33,9 +33,6 @@ struct wxb_ctx {
   wxb_model* model = nullptr;
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled (driver entry point), lazily resolved
   std::vector<wxb_dec_timing> dec_timings;  // one entry per wxb_decode_greedy call since the last reset
-  void* dec_streams[2] = {nullptr, nullptr};  // private streams of the two decode batch groups
-  void* dec_events[3] = {nullptr, nullptr, nullptr};
-  void* cap_stream = nullptr;    // private non-blocking stream used only to CAPTURE decoder step graphs
   bool lm_tables_ready = false;  // log-mel window/twiddle tables uploaded to this device
 };
 

@@ -48,15 +48,13 @@ constexpr int MK_WARPS = MK_THREADS / 32;
 constexpr int LN_V4 = 2;    // LayerNorm phase: float4 groups per thread, d <= 4 * 2 * 256
 constexpr int GK_MAX = 10;  // largest split-K factor a GEMV plan may use
 constexpr int MAX_LAYERS = 32;
-constexpr int PROF_XA = (1 << 16) - 32;  // profile buffer: cross-attention cycle counters live behind the timestamps
+
 
 // ---- shared-memory plan of the persistent kernel (dynamic, 1024-byte aligned base) -------------------------
 // One region is time-shared by the two TMA rings (GEMV phases and cross-attention never overlap inside a CTA):
 //   GEMV ring   GV_NST stages x (A: 128 weight rows x 64 k bf16 = 16 KB | B: Bp batch rows x 64 k), 128-byte swizzle
 //   KV ring     XA_NST stages x (K: 112 keys x 64 dims bf16 = 14 KB | V: 14 KB), 128-byte swizzle
 // followed by the attention scratch (warp states of two items, raw q rows of two items).
-// OCC = CTAs per SM = independent sequence groups decoded side by side (see dec_step_kernel): the ring depth shrinks
-// with OCC so that OCC CTAs fit one SM; shallow rings are backed by TMA prefetches into L2.
 constexpr int GV_ROWS = 128;                 // weight rows per tile = UMMA M
 constexpr int GV_BK = 64;                    // k per stage (one 128-byte swizzle row)
 constexpr int GV_A_BYTES = GV_ROWS * GV_BK * 2;
@@ -68,16 +66,11 @@ constexpr int SST_BYTES = 3712;                           // [2 item parities][7
 constexpr int QRAW_ROWS = GK_MAX + 1;                     // bias row + up to GK_MAX split-K partial rows of q
 constexpr int QRAW_BYTES = 2 * QRAW_ROWS * 64 * 4;        // two items in flight
 constexpr int SCRATCH_BYTES = SST_BYTES + QRAW_BYTES;     // attention scratch behind the ring
-template <int OCC>
-struct MkCfg {
-  static constexpr int XA_NST = OCC == 1 ? 6 : 3;
-  static constexpr int GV_NST = OCC == 1 ? 6 : 4;
-  static constexpr int MT_MAX = OCC == 1 ? 4 : 2;         // m16 batch tiles per group
-  static constexpr int RING_BYTES = XA_NST * 2 * XA_HALF;
-  static constexpr size_t SMEM = RING_BYTES + SCRATCH_BYTES + 1024;
-  static_assert(GV_NST * (GV_A_BYTES + 16 * MT_MAX * GV_BK * 2) <= RING_BYTES, "GEMV ring must fit the shared region");
-};
-constexpr int MAX_OCC = 2;
+constexpr int XA_NST = 6;                    // K/V ring depth
+constexpr int GV_NST = 6;                    // GEMV ring depth
+constexpr int RING_BYTES = XA_NST * 2 * XA_HALF;
+constexpr size_t MK_SMEM = RING_BYTES + SCRATCH_BYTES + 1024;
+static_assert(GV_NST * (GV_A_BYTES + 64 * GV_BK * 2) <= RING_BYTES, "GEMV ring must fit the shared region");
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -87,9 +80,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 
 // Grid barrier of the cooperative launch: monotone arrival counter (zeroed by the host before the launch).
 // Arrival is a release-add (orders this CTA's earlier writes, made visible to thread 0 by the block barrier),
-// the wait an acquire-poll.  The proxy fences order the generic-proxy global writes of a phase with the TMA
-// (async-proxy) reads of the next one.  With `prof` set, CTA 0 records the global timer at every barrier exit.
-__device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& target, int nc, int cta, unsigned long long* prof, int& prof_n) {
+// the wait an acquire-poll.  The proxy fence orders the generic-proxy global writes of a phase with the TMA
+// (async-proxy) reads of the next one.  While thread 0 arrives and waits, thread 32 runs `pre`: work of the NEXT
+// operator that does not depend on this one (requesting its weight / K/V tiles), so that HBM latency is spent
+// while the barrier completes.  With `prof` set, CTA 0 records the global timer at every barrier exit.
+template <class Pre>
+__device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& target, int nc, int cta, unsigned long long* prof, int& prof_n, Pre pre) {
   __syncthreads();
   if (threadIdx.x == 0) {
     target += (unsigned)nc;
@@ -97,16 +93,17 @@ __device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& target, int n
     unsigned v;
     unsigned spins = 0;
     do {
-      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
-      if (++spins > (1u << 26)) __trap();  // ~30 s: a CTA of the group is missing; fail the launch instead of hanging the GPU
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+      if (++spins > (1u << 26)) __trap();  // ~30 s: a CTA is missing; fail the launch instead of hanging the GPU
     } while ((int)(v - target) < 0);
-    asm volatile("fence.acq_rel.gpu;" ::: "memory");
     fence_proxy_async_all();  // thread 0 is also the TMA producer of the next phase
     if (prof && cta == 0) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       prof[prof_n] = t;
     }
+  } else if (threadIdx.x == 32) {
+    pre();
   }
   ++prof_n;
   __syncthreads();
@@ -157,23 +154,12 @@ struct MkParams {
   float* logits;
   long long ldl;
   float* apart;  // cross-attention piece states [pieces][66]
-  int* ticket;   // [<= CTAs of the group] zero-initialised, self-cleaning
+  int* ticket;   // [<= gridDim] zero-initialised, self-cleaning
   unsigned* bar;
   unsigned long long* prof;  // optional: barrier-exit timestamps of CTA 0 (WXB_DEC_PROF)
   MkGemv g_qkv, g_dd, g_fc1, g_fc2, g_logits;
   SampleParams sp;
   float scale;
-};
-
-// Kernel parameter.  n_groups == 1: one group, one CTA per SM, every CTA walks the whole schedule.
-// n_groups == 2: split roles, 2 x nc CTAs, two per SM (see dec_step_kernel).
-struct MkLaunch {
-  int n_groups, nc;
-  unsigned* sm_slots;   // [256] zero-initialised per launch: arrival order of the CTAs of one SM
-  unsigned* role_ctas;  // [2]   zero-initialised per launch: CTAs seated per role
-  unsigned* y_bar;      // [2 teams, 32 words apart] grid barriers of the chain teams (the cross CTAs poll them)
-  unsigned* x_done;     // [2 groups, 32 words apart] consumer warps of cross CTAs that finished a phase
-  MkParams g[MAX_OCC];
 };
 
 // mbarriers + ring cursors of the persistent kernel.  The barriers live in one shared array (fixed slots sized for
@@ -199,6 +185,7 @@ struct MkSync {
   uint32_t xa_count;   // KV stages issued so far
   uint32_t xa_items;   // cross-attention work items finished so far
   uint32_t tmem;       // TMEM base address (64 fp32 columns x 128 lanes)
+  int pre;             // thread 0: stages of the coming operator already requested before the barrier wait (grid_sync)
   int cta, nc;         // this CTA's index within its group, CTAs per group
   __device__ __forceinline__ uint32_t mb(int slot) const { return bars + 8u * (uint32_t)slot; }
 };
@@ -326,7 +313,7 @@ __device__ __forceinline__ void mma_16816(float* c, const uint32_t* a, uint32_t 
 // tcgen05.mma, all 8 warps read the accumulator back (tcgen05.ld, lane = weight row) for the epilogue.
 // Split-K tiles write fp32 partials [ks][B][N]; their consumer phase performs the reduction.
 // ---------------------------------------------------------------------------------------------
-template <int MT, int GV_NST>
+template <int MT>
 __device__ __forceinline__ void gemv_phase(const MkParams& p, const MkGemv& g, const CUtensorMap* wmap, const CUtensorMap* amap,
                                            const float* __restrict__ bias, const int epi, uint8_t* ring, MkSync& sy) {
   constexpr int Bp = 16 * MT;
@@ -341,14 +328,18 @@ __device__ __forceinline__ void gemv_phase(const MkParams& p, const MkGemv& g, c
     if (warp == 0 && lane == 0) {
       // ---- TMA producer: the whole K-slice is requested as fast as ring slots free up ----
       uint32_t c = sy.gv_count;
+      const int pre = (tile == sy.cta) ? sy.pre : 0;  // weight halves of the first stages were requested before the barrier wait
       for (int kb = 0; kb < nkb; ++kb, ++c) {
         const uint32_t slot = c % GV_NST, par = (c / GV_NST) & 1;
-        mbar_wait(sy.mb(MB_GV_EMPTY + slot), par ^ 1);
         uint8_t* sa = ring + slot * STAGE;
-        mbar_arrive_expect_tx(sy.mb(MB_GV_FULL + slot), STAGE);
-        tma_load_2d(sa, wmap, sy.mb(MB_GV_FULL + slot), k0 + kb * GV_BK, row0);
+        if (kb >= pre) {
+          mbar_wait(sy.mb(MB_GV_EMPTY + slot), par ^ 1);
+          mbar_arrive_expect_tx(sy.mb(MB_GV_FULL + slot), STAGE);
+          tma_load_2d(sa, wmap, sy.mb(MB_GV_FULL + slot), k0 + kb * GV_BK, row0);
+        }
         tma_load_2d(sa + GV_A_BYTES, amap, sy.mb(MB_GV_FULL + slot), k0 + kb * GV_BK, 0);
       }
+      sy.pre = 0;
     } else if (warp == 1 && lane == 0) {
       // ---- MMA issuer ----
       const uint32_t idesc = make_idesc_bf16(GV_ROWS, Bp);
@@ -400,91 +391,6 @@ __device__ __forceinline__ void gemv_phase(const MkParams& p, const MkGemv& g, c
     }
     tc_fence_before();
     __syncthreads();  // the next tile's first MMA overwrites the accumulator
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// GEMV phase on the legacy tensor pipe (mma.sync), used when several CTAs share an SM: a kernel that allocates
-// tensor memory is limited to one CTA per SM by the driver, and at batch <= 32 the phase is bound by the weight
-// stream and its latency, not by the MMA rate.  Same tiles, same TMA ring and swizzle as the tcgen05 variant:
-// warp w owns weight rows 16 w .. 16 w + 15 of the tile (A fragments by ldmatrix), all warps read the whole
-// activation slice (B fragments by ldmatrix, two 8-row batch tiles per instruction), fp32 accumulators in
-// registers.  Lane 0 of warp 0 refills a ring slot as soon as all 8 warps have released it.
-// ---------------------------------------------------------------------------------------------
-template <int MT, int GV_NST>
-__device__ __forceinline__ void gemv_phase_mma(const MkParams& p, const MkGemv& g, const CUtensorMap* wmap, const CUtensorMap* amap,
-                                               const float* __restrict__ bias, const int epi, uint8_t* ring, MkSync& sy) {
-  constexpr int Bp = 16 * MT;
-  constexpr int B_BYTES = Bp * GV_BK * 2;
-  constexpr int STAGE = GV_A_BYTES + B_BYTES;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
-  const int B = p.B;
-  const int Ks = g.K / g.gk, nkb = Ks / GV_BK;
-  const bool producer = (warp == 0 && lane == 0);
-  // ldmatrix lane addressing (128-byte swizzle: chunk' = chunk ^ (row & 7))
-  const int rowA = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, chA = lane >> 4;  // weights: chunk 2 kq + chA
-  const int rowB = (lane & 7) + (lane >> 4) * 8, chB = (lane >> 3) & 1;              // batch rows 16 j2 + rowB: chunk 2 kq + chB
-  const int sw = lane & 7;
-  for (int tile = sy.cta; tile < g.tiles; tile += sy.nc) {
-    const int ks = tile % g.gk, rb = tile / g.gk;
-    const int k0 = ks * Ks, row0 = rb * GV_ROWS;
-    auto issue = [&](int kb) {
-      const uint32_t c = sy.gv_count + (uint32_t)kb;
-      const uint32_t slot = c % GV_NST, par = (c / GV_NST) & 1;
-      mbar_wait(sy.mb(MB_GV_EMPTY + slot), par ^ 1);
-      uint8_t* sa = ring + slot * STAGE;
-      mbar_arrive_expect_tx(sy.mb(MB_GV_FULL + slot), STAGE);
-      tma_load_2d(sa, wmap, sy.mb(MB_GV_FULL + slot), k0 + kb * GV_BK, row0);
-      tma_load_2d(sa + GV_A_BYTES, amap, sy.mb(MB_GV_FULL + slot), k0 + kb * GV_BK, 0);
-    };
-    if (producer)
-      for (int kb = 0; kb < nkb && kb < GV_NST; ++kb) issue(kb);
-    float acc[2 * MT][4];
-#pragma unroll
-    for (int j = 0; j < 2 * MT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-    for (int kb = 0; kb < nkb; ++kb) {
-      const uint32_t c = sy.gv_count + (uint32_t)kb;
-      const uint32_t slot = c % GV_NST, par = (c / GV_NST) & 1;
-      mbar_wait(sy.mb(MB_GV_FULL + slot), par);
-      const uint32_t abase = smem_u32(ring + slot * STAGE), bbase = abase + GV_A_BYTES;
-#pragma unroll
-      for (int kq = 0; kq < GV_BK / 16; ++kq) {
-        uint32_t a[4];
-        ldsm_x4(a, abase + rowA * 128 + (((2 * kq + chA) ^ sw) << 4));
-#pragma unroll
-        for (int j2 = 0; j2 < MT; ++j2) {
-          uint32_t b[4];  // {b0, b1} of batch tile 2 j2, {b0, b1} of batch tile 2 j2 + 1
-          ldsm_x4(b, bbase + (16 * j2 + rowB) * 128 + (((2 * kq + chB) ^ sw) << 4));
-          mma_16816(acc[2 * j2], a, b[0], b[1]);
-          mma_16816(acc[2 * j2 + 1], a, b[2], b[3]);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(sy.mb(MB_GV_EMPTY + slot));
-      if (producer && kb + GV_NST < nkb) issue(kb + GV_NST);
-    }
-    sy.gv_count += nkb;
-    // ---- epilogue: lane (gq, t) holds weight rows n0 = row0 + 16 w + gq and n0 + 8, batch columns 8 j + 2 t, + 1 ----
-#pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      const int n = row0 + warp * 16 + gq + 8 * hh;
-      if (n < g.N) {
-        const float bn = (epi == EPI_GELU_BF16) ? __ldg(bias + n) : 0.f;
-#pragma unroll
-        for (int j = 0; j < 2 * MT; ++j) {
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int b = 8 * j + 2 * t + e;
-            const float v = acc[j][2 * hh + e];
-            if (b < B) {
-              if (epi == EPI_PART) p.part[((size_t)ks * B + b) * g.N + n] = v;
-              else if (epi == EPI_GELU_BF16) p.hid[(size_t)b * g.N + n] = __float2bfloat16_rn(gelu_erf(v + bn));
-              else p.logits[(size_t)b * p.ldl + n] = v;
-            }
-          }
-        }
-      }
-    }
   }
 }
 
@@ -759,13 +665,8 @@ __device__ __forceinline__ void xa_block(const uint32_t (*ka)[4][4], const uint3
 // partials of the cq GEMV) of the next items, every consumer warp sums them for itself, deposits its (m, l, O) state of
 // a finished item in a double-buffered shared-memory slot and moves straight on; consumer warp (item % 7) merges the
 // 7 states once all have arrived (mbarrier) and writes the output.
-// Split-role launches (see dec_step_kernel) pass `y_bar` / `y_need` / `x_done`: the q rows of the phase's first item are
-// staged only once the chain CTAs' barrier counter has reached y_need (their cq GEMV is complete grid-wide), K/V
-// stages are requested before that, and every consumer warp reports the end of its work list on x_done.
-template <int XA_NST>
 __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const float* __restrict__ cq_b, uint8_t* ring,
-                                                 float* scratch, MkSync& sy, const unsigned* y_bar = nullptr, unsigned y_need = 0,
-                                                 unsigned* x_done = nullptr) {
+                                                 float* scratch, MkSync& sy) {
   constexpr uint32_t STAGE = 2 * XA_HALF;
   float* sst = scratch;                                                                          // [2 item parities][7 warps][66]: m, l, O[64]
   float* qraw = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(scratch) + SST_BYTES);      // [2 item parities][QRAW_ROWS][64]
@@ -793,18 +694,6 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
     XaItem x = {}, px = {};
     if (n_items > 0) { x = xa_item(0, cta, qw, G, P, plen); kk = x.k0; px = x; pkk = kk; }
     uint32_t issued = sy.xa_count;
-    int q_item = 0;  // next item whose q rows have not been staged yet
-    // the first item's q rows wait until XA_NST of its stages are on their way (or all of them, if fewer)
-    int q_hold = 0;
-    if (y_bar && n_items > 0) {
-      int n0 = 0;
-      for (int i = 0, acc = 0; i < n_items && acc < XA_NST; ++i) {
-        const XaItem xi = xa_item(i, cta, qw, G, P, plen);
-        acc += (xi.k1 - xi.k0 + XA_KEYS - 1) / XA_KEYS;
-        n0 = acc;
-      }
-      q_hold = n0 < XA_NST ? n0 : XA_NST;
-    }
     auto stage_q = [&](int qi) {
       // raw q rows of item qi (row gk = bias, rows 0 .. gk-1 = split-K partials of the cq GEMV), 2 rows per pass
       const XaItem xq = xa_item(qi, cta, qw, G, P, plen);
@@ -822,20 +711,6 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
       }
       cp_async_mbar_arrive(sy.mb(MB_Q_FULL + qpar));
     };
-    auto stage_upto = [&](int last) {
-      if (q_item == 0 && y_bar) {
-        // the chain CTAs have finished this phase's cq GEMV once their barrier counter reaches y_need
-        if (lane == 0) {
-          unsigned v, spins = 0;
-          do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(y_bar) : "memory");
-            if (++spins > (1u << 26)) __trap();
-          } while ((int)(v - y_need) < 0);
-        }
-        __syncwarp();
-      }
-      while (q_item <= last) stage_q(q_item++);
-    };
     while (it < n_items) {
       if (xa_pf > 0) {
         while (pit < n_items && ahead <= xa_pf) {
@@ -852,8 +727,8 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
           }
         }
       }
-      if (q_item <= it && (int)(issued - sy.xa_count) >= q_hold) stage_upto(it);
-      if (lane == 0) {
+      if (kk == x.k0) stage_q(it);  // first stage of an item: its raw q rows
+      if (lane == 0 && (int)(issued - sy.xa_count) >= sy.pre) {  // the first sy.pre stages were requested before the barrier wait
         const uint32_t sl = issued % XA_NST, par = (issued / XA_NST) & 1;
         mbar_wait(sy.mb(MB_XA_EMPTY + sl), par ^ 1);
         const bool tail = (x.k1 - kk <= XA_TAIL);  // keys past the item (or the tensor: zero-filled) are masked by the consumer
@@ -872,7 +747,7 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
         if (it < n_items) { x = xa_item(it, cta, qw, G, P, plen); kk = x.k0; }
       }
     }
-    if (q_item < n_items) stage_upto(n_items - 1);  // fewer stages than the hold-back in this CTA's whole list
+    sy.pre = 0;
   } else {
     // ------------------------------- consumer warps -------------------------------
     const int cw = warp - 1;
@@ -881,10 +756,6 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
     const int rowV = cw * 16 + (lane & 7) + ((lane >> 4) & 1) * 8, chV = (lane >> 3) & 1;   // V (transposed): chunk 2 mt + chV
     const int sw = lane & 7;
     uint32_t consumed = sy.xa_count;
-    // WXB_DEC_PROF (split roles): consumer warp 1 of cross CTA 0 splits the phase into waiting for q and streaming
-    unsigned long long* xprof = (x_done && p.prof && cta == 0 && warp == 1 && lane == 0) ? p.prof + PROF_XA : nullptr;
-    unsigned long long t_enter = 0, t_q = 0;
-    if (xprof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_enter));
     for (int it = 0; it < n_items; ++it) {
       const XaItem x = xa_item(it, cta, qw, G, P, plen);
       const int b = x.slab / H, h = x.slab - b * H;
@@ -892,7 +763,6 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
       const uint32_t ipar = gi & 1, iph = (gi >> 1) & 1;
       // scaled q = (bias + split-K partials in slice order) * scale; lane holds dims lane and lane + 32
       mbar_wait(sy.mb(MB_Q_FULL + ipar), iph);
-      if (xprof && it == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_q));
       float qn0, qn1;
       {
         const float* qr = qraw + ipar * (QRAW_ROWS * 64);
@@ -1006,16 +876,6 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
         }
       }
     }
-    if (xprof) {
-      unsigned long long t_end;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
-      xprof[0] += t_q - t_enter; xprof[1] += t_end - t_q; xprof[2] += 1;
-    }
-  }
-  if (x_done && warp != 0) {
-    // this warp's outputs (merges it performed) are written: report to the chain CTAs
-    __syncwarp();
-    if (lane == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(x_done) : "memory");
   }
   // every thread advances the uniform cursors by this CTA's work list
   {
@@ -1119,16 +979,92 @@ __device__ __forceinline__ void sample_phase(const SampleParams& p, int B, int p
 // phase kinds of the step schedule: 11 per layer, then final LN | logits | sampling
 enum { PH_LN = 0, PH_GEMV = 1, PH_SELF = 2, PH_CROSS = 3, PH_SAMPLE = 4 };
 
-// One operator of the step schedule for one sequence group.  `p` must be a compile-time-indexed member of the kernel
-// parameter, so that every p.field is a constant-bank operand.
+__device__ __forceinline__ int op_kind(int k) {
+  return (k == 0 || k == 4 || k == 8 || k == 11) ? PH_LN : (k == 2) ? PH_SELF : (k == 6) ? PH_CROSS : (k == 13) ? PH_SAMPLE : PH_GEMV;
+}
+// operands of GEMV operator k of layer l
+struct GemvOp {
+  const MkGemv* g;
+  const CUtensorMap *wm, *xm;
+  int epi;
+};
+__device__ __forceinline__ GemvOp gemv_op(const MkParams& p, int l, int k) {
+  const CUtensorMap* lm = p.maps + (size_t)l * TM_PER_LAYER;
+  const CUtensorMap* am = p.maps + (size_t)p.L * TM_PER_LAYER;  // emb, xn, att, hid
+  GemvOp o;
+  o.g = (k == 1) ? &p.g_qkv : (k == 9) ? &p.g_fc1 : (k == 10) ? &p.g_fc2 : (k == 12) ? &p.g_logits : &p.g_dd;
+  o.wm = (k == 1) ? lm + TM_QKV : (k == 3) ? lm + TM_OUT : (k == 5) ? lm + TM_CQ : (k == 7) ? lm + TM_COUT
+         : (k == 9) ? lm + TM_FC1 : (k == 10) ? lm + TM_FC2 : am;
+  o.xm = (k == 3 || k == 7) ? am + 2 : (k == 10) ? am + 3 : am + 1;
+  o.epi = (k == 9) ? EPI_GELU_BF16 : (k == 12) ? EPI_LOGITS : EPI_PART;
+  return o;
+}
+
+// While a grid barrier completes (grid_sync): request the first tiles of operator (l, k) that do not depend on the
+// operator just finished: the weight halves of a GEMV's first ring stages, or the first K/V stages of a
+// cross-attention phase.  Every thread calls this and learns the number of stages (sy.pre, skipped by the producer
+// loops of those phases); only `issue` threads touch the barriers and the TMA unit.
+template <int MT>
+__device__ __forceinline__ void pre_issue(const MkParams& p, int l, int k, uint8_t* ring, MkSync& sy, const bool issue) {
+  const int kind = op_kind(k);
+  sy.pre = 0;
+  if (kind == PH_GEMV && !(p.skip & 2)) {
+    constexpr int STAGE = GV_A_BYTES + 16 * MT * GV_BK * 2;
+    const GemvOp o = gemv_op(p, l, k);
+    const MkGemv& g = *o.g;
+    const int tile = sy.cta;
+    if (tile >= g.tiles) return;
+    const int Ks = g.K / g.gk, nkb = Ks / GV_BK;
+    const int k0 = (tile % g.gk) * Ks, row0 = (tile / g.gk) * GV_ROWS;
+    const int n = nkb < GV_NST ? nkb : GV_NST;
+    for (int kb = 0; issue && kb < n; ++kb) {
+      const uint32_t c = sy.gv_count + (uint32_t)kb, slot = c % GV_NST, par = (c / GV_NST) & 1;
+      mbar_wait(sy.mb(MB_GV_EMPTY + slot), par ^ 1);
+      mbar_arrive_expect_tx(sy.mb(MB_GV_FULL + slot), STAGE);
+      tma_load_2d(ring + slot * STAGE, o.wm, sy.mb(MB_GV_FULL + slot), k0 + kb * GV_BK, row0);
+    }
+    sy.pre = n;
+  } else if (kind == PH_CROSS && !(p.skip & 1)) {
+    constexpr uint32_t STAGE = 2 * XA_HALF;
+    const int G = sy.nc, cta = sy.cta;
+    const CUtensorMap* kvmap = p.maps + (size_t)p.L * TM_PER_LAYER + 4;
+    const int n_slabs = p.B * p.H, qw = n_slabs / G, r = n_slabs - qw * G;
+    const int krow0 = (l * 2) * n_slabs * T_AUDIO, vrow0 = (l * 2 + 1) * n_slabs * T_AUDIO;
+    int P = 0, plen = T_AUDIO;
+    if (r > 0) {
+      const int want = (G + r - 1) / r;
+      plen = (T_AUDIO + want - 1) / want;
+      P = (T_AUDIO + plen - 1) / plen;
+    }
+    const int n_items = qw + ((r > 0 && cta < r * P) ? ((r * P - 1 - cta) / G + 1) : 0);
+    int it = 0, n = 0;
+    while (it < n_items && n < XA_NST) {
+      const XaItem x = xa_item(it, cta, qw, G, P, plen);
+      for (int kk = x.k0; kk < x.k1 && n < XA_NST; kk += XA_KEYS, ++n) {
+        if (!issue) continue;
+        const uint32_t c = sy.xa_count + (uint32_t)n, sl = c % XA_NST, par = (c / XA_NST) & 1;
+        mbar_wait(sy.mb(MB_XA_EMPTY + sl), par ^ 1);
+        const bool tail = (x.k1 - kk <= XA_TAIL);
+        const CUtensorMap* m = tail ? kvmap + 1 : kvmap;
+        uint8_t* dst = ring + (size_t)sl * STAGE;
+        mbar_arrive_expect_tx(sy.mb(MB_XA_FULL + sl), tail ? 2 * XA_TAIL * 128 : STAGE);
+        tma_load_2d_hint(dst, m, sy.mb(MB_XA_FULL + sl), 0, krow0 + x.slab * T_AUDIO + kk, L2_EVICT_FIRST);
+        tma_load_2d_hint(dst + XA_HALF, m, sy.mb(MB_XA_FULL + sl), 0, vrow0 + x.slab * T_AUDIO + kk, L2_EVICT_FIRST);
+      }
+      ++it;
+    }
+    sy.pre = n;
+  }
+}
+
+// One operator of the step schedule.
 // k: 0 LN1 | 1 QKV | 2 self-attention | 3 out | 4 LN2 | 5 cq | 6 cross-attention | 7 cout | 8 LN3 | 9 fc1 | 10 fc2
 //    11 final LN | 12 logits | 13 (no_speech_prob,) filters + sampling
-template <int MT, int OCC>
+template <int MT>
 __device__ __forceinline__ void run_op(const MkParams& p, const DecLayerW* s_layers, int l, int k, int pos, uint8_t* ring,
                                        float* scratch, float* red, int* red_i, MkSync& sy) {
-  using C = MkCfg<OCC>;
   const DecLayerW& w = s_layers[l];
-  const int kind = (k == 0 || k == 4 || k == 8 || k == 11) ? PH_LN : (k == 2) ? PH_SELF : (k == 6) ? PH_CROSS : (k == 13) ? PH_SAMPLE : PH_GEMV;
+  const int kind = op_kind(k);
   if (kind == PH_LN) {
     if (!(p.skip & 8)) {
       // the LayerNorm phase first folds the previous GEMV's split-K partials (+ bias) into the residual row
@@ -1141,57 +1077,59 @@ __device__ __forceinline__ void run_op(const MkParams& p, const DecLayerW* s_lay
     }
   } else if (kind == PH_GEMV) {
     if (!(p.skip & 2)) {
-      const CUtensorMap* lm = p.maps + (size_t)l * TM_PER_LAYER;
-      const CUtensorMap* am = p.maps + (size_t)p.L * TM_PER_LAYER;  // emb, xn, att, hid
-      const MkGemv& g = (k == 1) ? p.g_qkv : (k == 9) ? p.g_fc1 : (k == 10) ? p.g_fc2 : (k == 12) ? p.g_logits : p.g_dd;
-      const CUtensorMap* wm = (k == 1) ? lm + TM_QKV : (k == 3) ? lm + TM_OUT : (k == 5) ? lm + TM_CQ : (k == 7) ? lm + TM_COUT
-                              : (k == 9) ? lm + TM_FC1 : (k == 10) ? lm + TM_FC2 : am;
-      const CUtensorMap* xm = (k == 3 || k == 7) ? am + 2 : (k == 10) ? am + 3 : am + 1;
-      const int epi = (k == 9) ? EPI_GELU_BF16 : (k == 12) ? EPI_LOGITS : EPI_PART;
-      if constexpr (OCC == 1) gemv_phase<MT, C::GV_NST>(p, g, wm, xm, w.fc1_b, epi, ring, sy);
-      else gemv_phase_mma<MT, C::GV_NST>(p, g, wm, xm, w.fc1_b, epi, ring, sy);
+      const GemvOp o = gemv_op(p, l, k);
+      gemv_phase<MT>(p, *o.g, o.wm, o.xm, w.fc1_b, o.epi, ring, sy);
     }
   } else if (kind == PH_SELF) {
     if (!(p.skip & 4)) self_attn_phase(p, l, w.qkv_b, pos, sy);
   } else if (kind == PH_CROSS) {
-    if constexpr (OCC == 1) {
-      if (!(p.skip & 1)) cross_attn_phase<C::XA_NST>(p, l, w.cq_b, ring, scratch, sy);
-    }
+    if (!(p.skip & 1)) cross_attn_phase(p, l, w.cq_b, ring, scratch, sy);
   } else {
     sample_phase(p.sp, p.B, pos, p.mode == 2, red, red_i, sy);
   }
 }
 
-template <int OCC>
-__device__ __forceinline__ void init_barriers(const MkSync& sy) {
-  using C = MkCfg<OCC>;
+// operators per decode step
+__device__ __forceinline__ int ops_per_step(const MkParams& p) {
+  return 11 * p.L + (p.mode >= 1 ? 2 : 0) + ((p.mode == 2 || p.sp.nsp_out) ? 1 : 0);
+}
+
+// One CTA per SM (cooperative launch); every CTA walks the whole schedule, operators separated by grid barriers.
+// (Running several CTAs per SM so that one sequence group's chain hides under another group's K/V stream was tried
+// and measured slower; see DESIGN.md.  A kernel that allocates tensor memory is pinned to one CTA per SM anyway.)
+template <int MT>
+__global__ void __launch_bounds__(MK_THREADS, 1) dec_step_kernel(const __grid_constant__ MkParams p) {
+  extern __shared__ uint8_t mk_smem_raw[];
+  uint8_t* ring = mk_smem_raw + ((1024u - (smem_u32(mk_smem_raw) & 1023u)) & 1023u);  // 1024-byte aligned (swizzle atoms)
+  float* scratch = reinterpret_cast<float*>(ring + RING_BYTES);
+  __shared__ float red[MK_WARPS];
+  __shared__ int red_i[MK_WARPS];
+  __shared__ __align__(8) uint64_t bars[MB_COUNT];
+  __shared__ uint32_t tmem_slot;
+  __shared__ DecLayerW s_layers[MAX_LAYERS];  // pointer table of every layer: no dependent global load per phase
+  for (int i = threadIdx.x; i < p.L * (int)(sizeof(DecLayerW) / 8); i += MK_THREADS)
+    reinterpret_cast<unsigned long long*>(s_layers)[i] = reinterpret_cast<const unsigned long long*>(p.layers)[i];
+  const int warp = threadIdx.x >> 5;
+  MkSync sy;
+  sy.bars = smem_u32(bars);
+  sy.gv_count = 0; sy.acc_count = 0; sy.xa_count = 0; sy.xa_items = 0; sy.pre = 0;
+  sy.cta = blockIdx.x; sy.nc = gridDim.x;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < C::GV_NST; ++i) { mbar_init(sy.mb(MB_GV_FULL + i), 1); mbar_init(sy.mb(MB_GV_EMPTY + i), OCC == 1 ? 1 : MK_WARPS); }
+    for (int i = 0; i < GV_NST; ++i) { mbar_init(sy.mb(MB_GV_FULL + i), 1); mbar_init(sy.mb(MB_GV_EMPTY + i), 1); }
     mbar_init(sy.mb(MB_ACC_FULL), 1);
-    for (int i = 0; i < C::XA_NST; ++i) { mbar_init(sy.mb(MB_XA_FULL + i), 1); mbar_init(sy.mb(MB_XA_EMPTY + i), XA_CW); }
+    for (int i = 0; i < XA_NST; ++i) { mbar_init(sy.mb(MB_XA_FULL + i), 1); mbar_init(sy.mb(MB_XA_EMPTY + i), XA_CW); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(sy.mb(MB_ST_FULL + i), XA_CW); mbar_init(sy.mb(MB_ST_FREE + i), 1);
       mbar_init(sy.mb(MB_Q_FULL + i), 32); mbar_init(sy.mb(MB_Q_FREE + i), XA_CW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-}
-
-// operators per decode step of one group in the chain schedule (the cross-attention slot 6 included)
-__device__ __forceinline__ int ops_per_step(const MkParams& p) {
-  return 11 * p.L + (p.mode >= 1 ? 2 : 0) + ((p.mode == 2 || p.sp.nsp_out) ? 1 : 0);
-}
-
-// ---- one group, one CTA per SM: every CTA walks the whole schedule, operators separated by grid barriers ----
-template <int MT>
-__device__ __forceinline__ void dec_step_body(const MkParams& p, uint8_t* ring, float* scratch, float* red, int* red_i,
-                                              const DecLayerW* s_layers, uint32_t* tmem_slot, MkSync& sy) {
-  const int warp = threadIdx.x >> 5;
-  if (warp == 2) tmem_alloc(tmem_slot, 64);
+  if (warp == 2) tmem_alloc(&tmem_slot, 64);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  sy.tmem = *tmem_slot;
+  sy.tmem = tmem_slot;
+
   unsigned bar_target = 0;
   int prof_n = 0;
   const int pos0 = *p.d_pos;  // written only after the last barrier of this launch
@@ -1201,8 +1139,15 @@ __device__ __forceinline__ void dec_step_body(const MkParams& p, uint8_t* ring, 
     for (int ph = 0; ph < n_ph; ++ph) {
       int l = ph / 11, k = ph - 11 * l;
       if (l >= p.L) { k = 11 + (ph - 11 * p.L); l = p.L - 1; }
-      run_op<MT, 1>(p, s_layers, l, k, pos, ring, scratch, red, red_i, sy);
-      if (ph + 1 < n_ph || s + 1 < p.n_steps) grid_sync(p.bar, bar_target, sy.nc, sy.cta, p.prof, prof_n);
+      run_op<MT>(p, s_layers, l, k, pos, ring, scratch, red, red_i, sy);
+      if (ph + 1 < n_ph || s + 1 < p.n_steps) {
+        // the operator after the barrier: (l2, k2)
+        const int ph2 = (ph + 1 < n_ph) ? ph + 1 : 0;
+        int l2 = ph2 / 11, k2 = ph2 - 11 * l2;
+        if (l2 >= p.L) { k2 = 11 + (ph2 - 11 * p.L); l2 = p.L - 1; }
+        grid_sync(p.bar, bar_target, sy.nc, sy.cta, p.prof, prof_n, [&]() { pre_issue<MT>(p, l2, k2, ring, sy, true); });
+        if (threadIdx.x == 0) pre_issue<MT>(p, l2, k2, ring, sy, false);  // the producer thread only needs the count
+      }
     }
   }
   if (sy.cta == 0 && threadIdx.x == 0) *p.d_pos = pos0 + p.n_steps;
@@ -1211,114 +1156,6 @@ __device__ __forceinline__ void dec_step_body(const MkParams& p, uint8_t* ring, 
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(sy.tmem, 64);
-  }
-}
-
-// ---- split roles, two CTAs per SM (no tensor memory: a kernel that allocates it is pinned to one CTA per SM) ----
-// The batch is cut into two sequence groups A and B.  The CHAIN CTAs run the latency-bound operator chain (LayerNorm /
-// GEMV / self-attention / sampling): even ones for group A, odd ones for group B, each team with its own grid barrier,
-// so the two chains are independent of each other.  The CROSS CTA of every SM does nothing but cross-attention: its
-// producer warp streams K/V of (step, layer, group) phases back to back without ever draining, the q rows of a phase
-// are picked up as soon as the team's barrier counter shows that the group's cq GEMV is complete, and a team waits for
-// the phase's completion count before its cout GEMV.  So HBM streams one group's K/V while the other group's chain
-// runs underneath; the stagger between the groups arises by itself (B's first cross-attention queues behind A's).
-__device__ __forceinline__ int chain_ops_per_step(const MkParams& p) { return ops_per_step(p) - p.L; }  // no cross slot
-
-template <int OCC>
-__device__ __forceinline__ void dec_cross_role(const MkLaunch& L, uint8_t* ring, float* scratch, const DecLayerW* s_layers, MkSync& sy) {
-  using C = MkCfg<OCC>;
-  const MkParams& pa = L.g[0];
-  const unsigned team = (unsigned)(L.nc / 2);
-  const int per_step = chain_ops_per_step(pa);
-  for (int s = 0; s < pa.n_steps; ++s)
-    for (int l = 0; l < pa.L; ++l) {
-      if (pa.skip & 1) continue;
-      const unsigned need = team * (unsigned)(s * per_step + 10 * l + 5 + 1);  // barriers a team has passed once its cq GEMV is complete
-      cross_attn_phase<C::XA_NST>(L.g[0], l, s_layers[l].cq_b, ring, scratch, sy, L.y_bar, need, L.x_done);
-      cross_attn_phase<C::XA_NST>(L.g[1], l, s_layers[l].cq_b, ring, scratch, sy, L.y_bar + 32, need, L.x_done + 32);
-    }
-}
-
-template <int MT, int OCC>
-__device__ __forceinline__ void dec_chain_team(const MkParams& p, const unsigned* x_done, unsigned* y_bar, int n_cross_ctas, uint8_t* ring,
-                                               float* scratch, float* red, int* red_i, const DecLayerW* s_layers, MkSync& sy) {
-  unsigned bar_target = 0;
-  int prof_n = 0;
-  const int pos0 = *p.d_pos;
-  const int n_ph = ops_per_step(p);
-  for (int s = 0; s < p.n_steps; ++s) {
-    for (int ph = 0; ph < n_ph; ++ph) {
-      int l = ph / 11, k = ph - 11 * l;
-      if (l >= p.L) { k = 11 + (ph - 11 * p.L); l = p.L - 1; }
-      if (k == 6) continue;  // the cross CTAs' operator
-      if (k == 7 && !(p.skip & 1)) {
-        // the group's cross-attention of this layer is complete once every consumer warp of every cross CTA has reported
-        if (threadIdx.x == 0) {
-          const unsigned need = (unsigned)(n_cross_ctas * XA_CW) * (unsigned)(s * p.L + l + 1);
-          unsigned v, spins = 0;
-          do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(x_done) : "memory");
-            if (++spins > (1u << 26)) __trap();
-          } while ((int)(v - need) < 0);
-          fence_proxy_async_all();  // `att` was written by generic stores; thread 0 reads it through TMA next
-        }
-        __syncthreads();
-      }
-      run_op<MT, OCC>(p, s_layers, l, k, pos0 + s, ring, scratch, red, red_i, sy);
-      if (ph + 1 < n_ph || s + 1 < p.n_steps) grid_sync(y_bar, bar_target, sy.nc, sy.cta, p.prof, prof_n);
-    }
-  }
-  if (sy.cta == 0 && threadIdx.x == 0) *p.d_pos = pos0 + p.n_steps;
-}
-
-template <int MT, int OCC>
-__global__ void __launch_bounds__(MK_THREADS, OCC) dec_step_kernel(const __grid_constant__ MkLaunch L) {
-  using C = MkCfg<OCC>;
-  extern __shared__ uint8_t mk_smem_raw[];
-  uint8_t* ring = mk_smem_raw + ((1024u - (smem_u32(mk_smem_raw) & 1023u)) & 1023u);  // 1024-byte aligned (swizzle atoms)
-  float* scratch = reinterpret_cast<float*>(ring + C::RING_BYTES);
-  __shared__ float red[MK_WARPS];
-  __shared__ int red_i[MK_WARPS];
-  __shared__ __align__(8) uint64_t bars[MB_COUNT];
-  __shared__ uint32_t tmem_slot;
-  __shared__ int s_seat[2];
-  __shared__ DecLayerW s_layers[MAX_LAYERS];  // pointer table of every layer: no dependent global load per phase
-  const MkParams& p0 = L.g[0];
-  for (int i = threadIdx.x; i < p0.L * (int)(sizeof(DecLayerW) / 8); i += MK_THREADS)
-    reinterpret_cast<unsigned long long*>(s_layers)[i] = reinterpret_cast<const unsigned long long*>(p0.layers)[i];
-  MkSync sy;
-  sy.bars = smem_u32(bars);
-  sy.gv_count = 0; sy.acc_count = 0; sy.xa_count = 0; sy.xa_items = 0; sy.tmem = 0;
-  sy.cta = blockIdx.x; sy.nc = L.nc;
-  init_barriers<OCC>(sy);
-  if constexpr (OCC == 1) {
-    dec_step_body<MT>(L.g[0], ring, scratch, red, red_i, s_layers, &tmem_slot, sy);
-  } else {
-    // ---- seat: the first CTA to arrive on an SM takes the cross role, the second the chain role; a role that is
-    // already complete (nc CTAs) passes the CTA on to the other one, so both roles always end up with nc CTAs.
-    if (threadIdx.x == 0) {
-      unsigned smid;
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      int role = (int)(atomicAdd(L.sm_slots + (smid & 255u), 1u) & 1u), idx;
-      for (;;) {
-        idx = (int)atomicAdd(L.role_ctas + role, 1u);
-        if (idx < L.nc) break;
-        role ^= 1;
-      }
-      s_seat[0] = role;
-      s_seat[1] = idx;
-    }
-    __syncthreads();
-    sy.cta = s_seat[1];
-    if (s_seat[0] == 0) {
-      dec_cross_role<OCC>(L, ring, scratch, s_layers, sy);
-    } else {
-      const int team = sy.cta & 1;
-      sy.cta >>= 1;
-      sy.nc = L.nc / 2;
-      if (team == 0) dec_chain_team<MT, OCC>(L.g[0], L.x_done, L.y_bar, L.nc, ring, scratch, red, red_i, s_layers, sy);
-      else dec_chain_team<MT, OCC>(L.g[1], L.x_done + 32, L.y_bar + 32, L.nc, ring, scratch, red, red_i, s_layers, sy);
-    }
   }
 }
 
@@ -1339,12 +1176,8 @@ __global__ void dec_finalize_kernel(const int* __restrict__ tokens, int stride, 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-constexpr int MAX_GROUP = 64;           // sequences per group when the launch holds one group (4 m16 tiles)
+constexpr int MAX_GROUP = 64;           // sequences per call (4 m16 batch tiles)
 constexpr size_t PART_FLOATS = (size_t)4 << 20;  // 16 MB of fp32 split-K partials per group
-
-// "dec.sync" words: [0, 256) CTAs seated per SM | 256 + {0, 1} CTAs seated per role | 288 grid barrier (one group) or
-// 288, 320 barriers of the two chain teams (split roles) | 352, 384 cross-attention completion counters of groups A, B
-constexpr int SYNC_WORDS = 416, SYNC_ROLES = 256, SYNC_BAR = 288, SYNC_XDONE = 352;
 
 struct DecBuffers {
   float *x, *logits, *part, *apart, *sum_lp;
@@ -1357,13 +1190,13 @@ struct DecBuffers {
 };
 
 // tuning aid: WXB_XA_PF overrides the L2 prefetch distance of the cross-attention stream
-int dec_xa_prefetch(int ng) {
+int dec_xa_prefetch() {
   static int v = -2;
   if (v == -2) {
     const char* e = getenv("WXB_XA_PF");
     v = e ? atoi(e) : -1;
   }
-  return v >= 0 ? v : (ng == 2 ? 8 : 0);  // the split-role ring holds 3 stages only: back it with L2 prefetches
+  return v >= 0 ? v : 0;
 }
 
 // profiling aid only (results become meaningless): WXB_DEC_SKIP bitmask, see MkParams::skip
@@ -1387,7 +1220,7 @@ bool dec_prof_enabled() {
   return v == 1;
 }
 constexpr size_t PROF_SLOTS = 1 << 16;
-struct ProfLast { int mode = 0, n_steps = 0, L = 0, ng = 1; bool nsp = false; unsigned long long* dev = nullptr; } g_prof_last;
+struct ProfLast { int mode = 0, n_steps = 0, L = 0; bool nsp = false; unsigned long long* dev = nullptr; } g_prof_last;
 
 const void* g_layers_model = nullptr;  // the model whose DecLayerW table is resident in "dec.layers"
 
@@ -1413,21 +1246,20 @@ MkGemv plan_gemv(int N, int K, int B, int Bp, int G, bool full_k) {
   return best;
 }
 
-// identity of the tensor-map table resident in "dec.maps<group>"
+// identity of the tensor-map table resident in "dec.maps"
 struct MapsKey {
   const void* model = nullptr;
   const void *xn = nullptr, *att = nullptr, *hid = nullptr, *ckv = nullptr;
   int B = 0;
-} g_maps_key[MAX_OCC];
+} g_maps_key;
 
-int alloc_buffers(wxb_ctx* ctx, int B, int tok_stride, int group, DecBuffers* o) {
-  const std::string sfx = group ? (".g" + std::to_string(group)) : std::string();
-  auto nm = [&](const char* base) { return std::string(base) + sfx; };
+int alloc_buffers(wxb_ctx* ctx, int B, int tok_stride, DecBuffers* o) {
+  auto nm = [&](const char* base) { return std::string(base); };
   const wxb_dims& D = ctx->model->dims;
   const int d = D.n_text_state, L = D.n_text_layer, H = D.n_text_head, V = D.n_vocab;
   o->B = B;
   o->tok_stride = tok_stride;
-  if (B > MAX_GROUP) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: batch %d > %d sequences per group", B, MAX_GROUP);
+  if (B > MAX_GROUP) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: batch %d > %d sequences per call", B, MAX_GROUP);
   if (L > MAX_LAYERS) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: %d layers > %d", L, MAX_LAYERS);
   if (d > 4 * LN_V4 * MK_THREADS || d % 64)
     return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: n_text_state=%d unsupported (multiple of 64, <= %d)", d, 4 * LN_V4 * MK_THREADS);
@@ -1443,9 +1275,7 @@ int alloc_buffers(wxb_ctx* ctx, int B, int tok_stride, int group, DecBuffers* o)
   o->cross_kv = (__nv_bfloat16*)wxb_named(ctx, nm("dec.cross_kv").c_str(), (size_t)L * 2 * B * H * T_AUDIO * 64 * 2);
   o->ticket = (int*)wxb_named(ctx, nm("dec.ticket").c_str(), (size_t)1024 * 4, true);
   o->d_pos = (int*)wxb_named(ctx, nm("dec.pos").c_str(), 64);
-  // launch-scoped counters (zeroed before every launch), see SYNC_* below
-  unsigned* sync = (unsigned*)wxb_named(ctx, "dec.sync", SYNC_WORDS * 4, true);
-  o->bar = sync ? sync + SYNC_BAR : nullptr;
+  o->bar = (unsigned*)wxb_named(ctx, "dec.bar", 128, true);  // grid-barrier counter, zeroed before every launch
   o->tokens = (int*)wxb_named(ctx, nm("dec.tokens").c_str(), (size_t)B * tok_stride * 4);
   o->done = (int*)wxb_named(ctx, nm("dec.done").c_str(), (size_t)B * 4);
   DecLayerW* layers = (DecLayerW*)wxb_named(ctx, "dec.layers", (size_t)L * sizeof(DecLayerW));
@@ -1467,7 +1297,7 @@ int alloc_buffers(wxb_ctx* ctx, int B, int tok_stride, int group, DecBuffers* o)
   const size_t n_maps = (size_t)TM_PER_LAYER * L + 6;
   CUtensorMap* maps = (CUtensorMap*)wxb_named(ctx, nm("dec.maps").c_str(), n_maps * sizeof(CUtensorMap));
   if (!maps) return WXB_ERR_CUDA;
-  MapsKey& key = g_maps_key[group];
+  MapsKey& key = g_maps_key;
   if (key.model != (const void*)ctx->model || key.xn != o->xn || key.att != o->att || key.hid != o->hid || key.ckv != o->cross_kv || key.B != B) {
     std::vector<CUtensorMap> h(n_maps);
     const int Bp = (B + 15) & ~15;
@@ -1518,155 +1348,72 @@ int cross_kv_precompute(wxb_ctx* ctx, const __nv_bfloat16* enc_out, const DecBuf
   return WXB_OK;
 }
 
-template <int MT, int OCC>
-int launch_instance(wxb_ctx* ctx, const MkLaunch& L, cudaStream_t st) {
-  auto kern = dec_step_kernel<MT, OCC>;
-  constexpr size_t smem = MkCfg<OCC>::SMEM;
-  static bool attr_set = false;
-  if (!attr_set) {
-    WXB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WXB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    int per_sm = 0;
-    WXB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MK_THREADS, smem));
-    // exactly OCC CTAs per SM: fewer and the grid is not co-resident, more and an SM could host two CTAs of one group
-    if (per_sm != OCC) {
-      cudaFuncAttributes fa = {};
-      cudaFuncGetAttributes(&fa, kern);
-      int sm_smem = 0, occ_half = 0;
-      cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, ctx->device);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_half, kern, MK_THREADS, smem / 2);
-      return wxb_fail(ctx, WXB_ERR_UNSUPPORTED,
-                      "decoder: step kernel occupancy %d CTAs/SM, expected %d (regs %d, static smem %zu, dynamic %zu, max dynamic %d, "
-                      "local %zu, SM smem %d, occupancy at half the dynamic smem %d)",
-                      per_sm, OCC, fa.numRegs, fa.sharedSizeBytes, smem, fa.maxDynamicSharedSizeBytes, fa.localSizeBytes, sm_smem, occ_half);
-    }
-    attr_set = true;
+// Launch the persistent step kernel: n_steps consecutive positions starting at *d_pos.
+int launch_steps(wxb_ctx* ctx, const DecBuffers& buf, int mode, int n_steps, const SampleParams& sp, float* logits_out,
+                 long long ldl, cudaStream_t st) {
+  const wxb_dims& D = ctx->model->dims;
+  const int d = D.n_text_state, B = buf.B;
+  const int Bp = (B + 15) & ~15, MT = Bp / 16;
+  const int G = ctx->sm_count;
+  MkParams p = {};
+  p.B = B; p.d = d; p.H = D.n_text_head; p.L = D.n_text_layer; p.V = D.n_vocab; p.TX = D.n_text_ctx;
+  p.mode = mode; p.n_steps = n_steps; p.skip = dec_skip_mask(); p.xa_pf = dec_xa_prefetch();
+  p.layers = buf.layers; p.maps = buf.maps;
+  p.emb = (const __nv_bfloat16*)wxb_weight(ctx, "dec.emb");
+  p.pos_emb = (const float*)wxb_weight(ctx, "dec.pos");
+  p.lnf_w = (const float*)wxb_weight(ctx, "dec.ln.w");
+  p.lnf_b = (const float*)wxb_weight(ctx, "dec.ln.b");
+  if (!p.emb || !p.pos_emb || !p.lnf_w || !p.lnf_b) return WXB_ERR_STATE;
+  p.tokens = buf.tokens; p.tok_stride = buf.tok_stride; p.d_pos = buf.d_pos;
+  p.x = buf.x; p.xn = buf.xn; p.att = buf.att; p.hid = buf.hid; p.part = buf.part;
+  p.self_kv = buf.self_kv; p.cross_kv = buf.cross_kv;
+  p.logits = logits_out; p.ldl = ldl;
+  p.apart = buf.apart; p.ticket = buf.ticket; p.bar = buf.bar;
+  if (dec_prof_enabled()) {
+    p.prof = (unsigned long long*)wxb_named(ctx, "dec.prof", PROF_SLOTS * 8);
+    if ((size_t)n_steps * (11 * p.L + 4) > PROF_SLOTS) p.prof = nullptr;
+    g_prof_last.mode = mode; g_prof_last.n_steps = n_steps; g_prof_last.L = p.L; g_prof_last.nsp = sp.nsp_out != nullptr;
+    g_prof_last.dev = p.prof;
   }
+  p.g_qkv = plan_gemv(3 * d, d, B, Bp, G, false);
+  p.g_dd = plan_gemv(d, d, B, Bp, G, false);
+  p.g_fc1 = plan_gemv(4 * d, d, B, Bp, G, true);
+  p.g_fc2 = plan_gemv(d, 4 * d, B, Bp, G, false);
+  p.g_logits = plan_gemv(D.n_vocab, d, B, Bp, G, true);
+  if (!p.g_qkv.gk || !p.g_dd.gk || !p.g_fc1.gk || !p.g_fc2.gk || !p.g_logits.gk)
+    return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: no GEMV tiling fits (d=%d, batch %d)", d, B);
+  p.sp = sp;
+  p.scale = 1.0f / sqrtf(64.f);
+  void (*kern)(const MkParams) = MT == 1 ? dec_step_kernel<1> : MT == 2 ? dec_step_kernel<2> : MT == 3 ? dec_step_kernel<3> : dec_step_kernel<4>;
+  static bool attr_set[5] = {false, false, false, false, false};
+  if (!attr_set[MT]) {
+    WXB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MK_SMEM));
+    int per_sm = 0;
+    WXB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MK_THREADS, MK_SMEM));
+    if (per_sm < 1) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: persistent step kernel does not fit an SM");
+    attr_set[MT] = true;
+  }
+  WXB_CUDA(ctx, cudaMemsetAsync(buf.bar, 0, 4, st));
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(L.nc * OCC);
+  cfg.gridDim = dim3(G);
   cfg.blockDim = dim3(MK_THREADS);
-  cfg.dynamicSmemBytes = smem;
+  cfg.dynamicSmemBytes = MK_SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident: the grid barriers cannot deadlock
+  attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident: the grid barrier cannot deadlock
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, L);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
   ctx->launches++;
   if (e != cudaSuccess) return wxb_fail(ctx, WXB_ERR_CUDA, "decoder step launch failed: %s", cudaGetErrorString(e));
   return WXB_OK;
-}
-
-// Launch the persistent step kernel: n_steps consecutive positions starting at *d_pos, for ng sequence groups at once.
-int launch_steps(wxb_ctx* ctx, const DecBuffers* bufs, int ng, int mode, int n_steps, const SampleParams* sps,
-                 float* const* logits_out, long long ldl, cudaStream_t st) {
-  const wxb_dims& D = ctx->model->dims;
-  const int d = D.n_text_state;
-  const int G = ctx->sm_count;
-  const int Gt = ng == 2 ? G / 2 : G;  // CTAs that share one group's GEMV tiles
-  MkLaunch L = {};
-  L.n_groups = ng;
-  L.nc = G;
-  unsigned* sync = (unsigned*)wxb_named(ctx, "dec.sync", SYNC_WORDS * 4, true);
-  if (!sync) return WXB_ERR_CUDA;
-  L.sm_slots = sync;
-  L.role_ctas = sync + SYNC_ROLES;
-  L.y_bar = sync + SYNC_BAR;
-  L.x_done = sync + SYNC_XDONE;
-  int MT = 1;
-  for (int g = 0; g < ng; ++g) {
-    const DecBuffers& buf = bufs[g];
-    const int B = buf.B, Bp = (B + 15) & ~15;
-    MT = std::max(MT, Bp / 16);
-    MkParams& p = L.g[g];
-    p.B = B; p.d = d; p.H = D.n_text_head; p.L = D.n_text_layer; p.V = D.n_vocab; p.TX = D.n_text_ctx;
-    p.mode = mode; p.n_steps = n_steps; p.skip = dec_skip_mask(); p.xa_pf = dec_xa_prefetch(ng);
-    p.layers = buf.layers; p.maps = buf.maps;
-    p.emb = (const __nv_bfloat16*)wxb_weight(ctx, "dec.emb");
-    p.pos_emb = (const float*)wxb_weight(ctx, "dec.pos");
-    p.lnf_w = (const float*)wxb_weight(ctx, "dec.ln.w");
-    p.lnf_b = (const float*)wxb_weight(ctx, "dec.ln.b");
-    if (!p.emb || !p.pos_emb || !p.lnf_w || !p.lnf_b) return WXB_ERR_STATE;
-    p.tokens = buf.tokens; p.tok_stride = buf.tok_stride; p.d_pos = buf.d_pos;
-    p.x = buf.x; p.xn = buf.xn; p.att = buf.att; p.hid = buf.hid; p.part = buf.part;
-    p.self_kv = buf.self_kv; p.cross_kv = buf.cross_kv;
-    p.logits = logits_out[g]; p.ldl = ldl;
-    p.apart = buf.apart; p.ticket = buf.ticket; p.bar = buf.bar;
-    if (dec_prof_enabled()) {
-      p.prof = (unsigned long long*)wxb_named(ctx, "dec.prof", 2 * PROF_SLOTS * 8);
-      if (p.prof && g == 1) p.prof += PROF_SLOTS;
-      if ((size_t)n_steps * (11 * p.L + 4) > (size_t)PROF_XA) p.prof = nullptr;
-      if (p.prof) WXB_CUDA(ctx, cudaMemsetAsync(p.prof + PROF_XA, 0, 32 * 8, st));
-      g_prof_last.ng = ng; g_prof_last.mode = mode; g_prof_last.n_steps = n_steps; g_prof_last.L = p.L; g_prof_last.nsp = sps[g].nsp_out != nullptr;
-      if (g == 0) g_prof_last.dev = p.prof;
-    }
-    p.g_qkv = plan_gemv(3 * d, d, B, Bp, Gt, false);
-    p.g_dd = plan_gemv(d, d, B, Bp, Gt, false);
-    p.g_fc1 = plan_gemv(4 * d, d, B, Bp, Gt, true);
-    p.g_fc2 = plan_gemv(d, 4 * d, B, Bp, Gt, false);
-    p.g_logits = plan_gemv(D.n_vocab, d, B, Bp, Gt, true);
-    if (!p.g_qkv.gk || !p.g_dd.gk || !p.g_fc1.gk || !p.g_fc2.gk || !p.g_logits.gk)
-      return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: no GEMV tiling fits (d=%d, batch %d)", d, B);
-    p.sp = sps[g];
-    p.scale = 1.0f / sqrtf(64.f);
-  }
-  if (MT > (ng == 1 ? 4 : 2)) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: %d sequence groups of up to %d rows", ng, 16 * MT);
-  WXB_CUDA(ctx, cudaMemsetAsync(sync, 0, SYNC_WORDS * 4, st));
-  switch (ng * 10 + MT) {
-    case 11: return launch_instance<1, 1>(ctx, L, st);
-    case 12: return launch_instance<2, 1>(ctx, L, st);
-    case 13: return launch_instance<3, 1>(ctx, L, st);
-    case 14: return launch_instance<4, 1>(ctx, L, st);
-    case 21: return launch_instance<1, 2>(ctx, L, st);
-    case 22: return launch_instance<2, 2>(ctx, L, st);
-  }
-  return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: no kernel instance for %d groups x %d batch tiles", ng, MT);
-}
-
-// Sequence groups decoded side by side by one launch (WXB_DEC_GROUPS overrides; profiling / tuning aid).
-int pick_groups(int B) {
-  static int forced = -1;
-  if (forced < 0) {
-    const char* e = getenv("WXB_DEC_GROUPS");
-    forced = e ? atoi(e) : 0;
-  }
-  int ng = forced > 0 ? forced : (B >= 16 ? 2 : 1);
-  ng = std::min(std::min(ng, MAX_OCC), B);
-  if (ng == 2 && ceil_div(B, 2) > 32) ng = 1;  // split roles hold two groups of <= 32 sequences
-  return ng;
 }
 
 int dump_prof(wxb_ctx* ctx) {
   const ProfLast& P = g_prof_last;
   if (!P.dev) return WXB_OK;
   WXB_CUDA(ctx, cudaDeviceSynchronize());
-  if (P.ng == 2) {
-    // split roles: barrier-exit timestamps of chain CTA 0 of team A; its operators exclude the cross-attention slot
-    const int tail = (P.mode >= 1 ? 2 : 0) + ((P.mode == 2 || P.nsp) ? 1 : 0);
-    const int per_step = 10 * P.L + tail, n = per_step * P.n_steps - 1;
-    std::vector<unsigned long long> t(n);
-    WXB_CUDA(ctx, cudaMemcpy(t.data(), P.dev, (size_t)n * 8, cudaMemcpyDeviceToHost));
-    double sum[16] = {0};
-    long cnt[16] = {0};
-    for (int k = 1; k < n; ++k) {
-      const int ph = k % per_step;
-      const int slot = ph < 10 * P.L ? ph % 10 : 10 + (ph - 10 * P.L);
-      sum[slot] += (double)(t[k] - t[k - 1]) * 1e-3; cnt[slot]++;
-    }
-    static const char* names[13] = {"ln1", "qkv", "self", "out", "ln2", "cq", "wait-cross+cout", "ln3", "fc1", "fc2", "lnf", "logits", "sample"};
-    fprintf(stderr, "[wxb dec prof] split roles, team A, %d steps/launch, per-operator mean us (operator + its barrier):", P.n_steps);
-    double layer = 0;
-    for (int i = 0; i < 13; ++i) if (cnt[i]) { fprintf(stderr, " %s %.2f", names[i], sum[i] / cnt[i]); if (i < 10) layer += sum[i] / cnt[i]; }
-    fprintf(stderr, " | layer %.2f | step %.1f us\n", layer, (double)(t[n - 1] - t[0]) * 1e-3 / P.n_steps);
-    for (int g = 0; g < 2; ++g) {
-      unsigned long long xa[3];
-      WXB_CUDA(ctx, cudaMemcpy(xa, P.dev + (size_t)g * PROF_SLOTS + PROF_XA, sizeof(xa), cudaMemcpyDeviceToHost));
-      if (xa[2]) fprintf(stderr, "[wxb dec prof] cross CTA 0, group %c: mean us per phase waiting for q %.2f, streaming %.2f (%llu phases)\n",
-                         'A' + g, xa[0] * 1e-3 / xa[2], xa[1] * 1e-3 / xa[2], xa[2]);
-    }
-    return WXB_OK;
-  }
   const int tail = (P.mode >= 1 ? 2 : 0) + ((P.mode == 2 || P.nsp) ? 1 : 0);
   const int per_step = 11 * P.L + tail;  // phases = barriers per step (the last phase of the launch has none)
   const int n = per_step * P.n_steps - 1;
@@ -1697,7 +1444,7 @@ int dump_prof(wxb_ctx* ctx) {
 
 void wxb_decoder_reset_graphs() {
   g_layers_model = nullptr;
-  for (int i = 0; i < MAX_OCC; ++i) g_maps_key[i] = MapsKey();
+  g_maps_key = MapsKey();
 }
 
 extern "C" int wxb_decode_greedy(wxb_ctx* ctx, const void* enc_out_dev, int B, const int32_t* prompt_host, int prompt_len,
@@ -1718,61 +1465,37 @@ extern "C" int wxb_decode_greedy(wxb_ctx* ctx, const void* enc_out_dev, int B, c
   WXB_CUDA(ctx, cudaSetDevice(ctx->device));
   const int stride = D.n_text_ctx + 1;
   int rc;
-  // Sequence groups: the batch is cut into ng independent groups (own buffers, own grid barrier) that one
-  // persistent launch decodes side by side, ng CTAs per SM (see MkLaunch).
-  const int ng = (ctx->sm_count & 1) ? 1 : pick_groups(B);  // split roles pair the chain CTAs into two teams
-  if (ceil_div(B, ng) > (ng == 1 ? MAX_GROUP : 32))
-    return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "wxb_decode_greedy: at most %d sequences per call", MAX_GROUP);
-  int g0[MAX_OCC + 1];
-  for (int g = 0; g <= ng; ++g) g0[g] = (int)(((long long)B * g + ng - 1) / ng);
-  DecBuffers buf[MAX_OCC];
-  SampleParams sp[MAX_OCC];
-  float* lg[MAX_OCC];
-  for (int g = 0; g < ng; ++g) {
-    const int Bg = g0[g + 1] - g0[g];
-    if ((rc = alloc_buffers(ctx, Bg, stride, g, &buf[g])) != WXB_OK) return rc;
-    lg[g] = buf[g].logits;
-  }
+  DecBuffers buf;
+  if ((rc = alloc_buffers(ctx, B, stride, &buf)) != WXB_OK) return rc;
   wxb_dec_timing tm;
   WXB_CUDA(ctx, cudaEventCreate(&tm.e0));
   WXB_CUDA(ctx, cudaEventCreate(&tm.e1));
   WXB_CUDA(ctx, cudaEventCreate(&tm.e2));
   WXB_CUDA(ctx, cudaEventRecord(tm.e0, st));
+  // tokens[b, :prompt_len] = prompt; state reset
   std::vector<int> init((size_t)B * stride, opts->eot);
   for (int b = 0; b < B; ++b)
     for (int i = 0; i < prompt_len; ++i) init[(size_t)b * stride + i] = prompt_host[i];
-  const size_t enc_row = (size_t)T_AUDIO * D.n_audio_state;
-  for (int g = 0; g < ng; ++g) {
-    const int Bg = buf[g].B;
-    // tokens[b, :prompt_len] = prompt; state reset
-    WXB_CUDA(ctx, cudaMemcpyAsync(buf[g].tokens, init.data() + (size_t)g0[g] * stride, (size_t)Bg * stride * 4, cudaMemcpyHostToDevice, st));
-    WXB_CUDA(ctx, cudaMemsetAsync(buf[g].d_pos, 0, 4, st));
-    WXB_CUDA(ctx, cudaMemsetAsync(buf[g].done, 0, (size_t)Bg * 4, st));
-    WXB_CUDA(ctx, cudaMemsetAsync(buf[g].sum_lp, 0, (size_t)Bg * 4, st));
-    if ((rc = cross_kv_precompute(ctx, (const __nv_bfloat16*)enc_out_dev + (size_t)g0[g] * enc_row, buf[g], st)) != WXB_OK) return rc;
-    SampleParams& s1 = sp[g];
-    s1 = SampleParams{};
-    s1.logits = buf[g].logits; s1.V = D.n_vocab; s1.tokens = buf[g].tokens; s1.stride = stride;
-    s1.prompt_len = prompt_len; s1.eot = opts->eot; s1.suppress_blank = opts->suppress_blank; s1.blank_token = opts->blank_token;
-    s1.n_suppress = opts->n_suppress; s1.suppress = opts->suppress_dev; s1.sum_logprob = buf[g].sum_lp; s1.done = buf[g].done;
-    s1.nsp_out = nullptr; s1.nsp_token = opts->no_speech;
-  }
+  WXB_CUDA(ctx, cudaMemcpyAsync(buf.tokens, init.data(), (size_t)B * stride * 4, cudaMemcpyHostToDevice, st));
+  WXB_CUDA(ctx, cudaMemsetAsync(buf.d_pos, 0, 4, st));
+  WXB_CUDA(ctx, cudaMemsetAsync(buf.done, 0, (size_t)B * 4, st));
+  WXB_CUDA(ctx, cudaMemsetAsync(buf.sum_lp, 0, (size_t)B * 4, st));
+  if ((rc = cross_kv_precompute(ctx, (const __nv_bfloat16*)enc_out_dev, buf, st)) != WXB_OK) return rc;
+  SampleParams sp = {};
+  sp.logits = buf.logits; sp.V = D.n_vocab; sp.tokens = buf.tokens; sp.stride = stride;
+  sp.prompt_len = prompt_len; sp.eot = opts->eot; sp.suppress_blank = opts->suppress_blank; sp.blank_token = opts->blank_token;
+  sp.n_suppress = opts->n_suppress; sp.suppress = opts->suppress_dev; sp.sum_logprob = buf.sum_lp; sp.done = buf.done;
+  sp.nsp_out = nullptr; sp.nsp_token = opts->no_speech;
   WXB_CUDA(ctx, cudaStreamSynchronize(st));  // `init` is pageable host memory
   WXB_CUDA(ctx, cudaEventRecord(tm.e1, st));
 
   const bool want_nsp = (opts->no_speech >= 0 && no_speech_prob_dev);
-  auto with_nsp = [&](SampleParams* dst, bool nsp) {
-    for (int g = 0; g < ng; ++g) {
-      dst[g] = sp[g];
-      if (nsp) dst[g].nsp_out = no_speech_prob_dev + g0[g];
-    }
-  };
   // prompt positions 0 .. prompt_len-2 (forced tokens); logits only at position 0 for no_speech_prob
   for (int pos = 0; pos < prompt_len - 1; ++pos) {
-    SampleParams s1[MAX_OCC];
+    SampleParams s1 = sp;
     const bool nsp = (pos == 0 && want_nsp);
-    with_nsp(s1, nsp);
-    if ((rc = launch_steps(ctx, buf, ng, nsp ? 1 : 0, 1, s1, lg, D.n_vocab, st)) != WXB_OK) return rc;
+    if (nsp) s1.nsp_out = no_speech_prob_dev;
+    if ((rc = launch_steps(ctx, buf, nsp ? 1 : 0, 1, s1, buf.logits, D.n_vocab, st)) != WXB_OK) return rc;
   }
   const int check_every = opts->check_every > 0 ? opts->check_every : 16;
   std::vector<int> done_host(B);
@@ -1781,25 +1504,21 @@ extern "C" int wxb_decode_greedy(wxb_ctx* ctx, const void* enc_out_dev, int B, c
     // a single-token prompt makes the SOT position the first sampling position: that step also emits no_speech_prob
     const bool nsp_now = (n_sampled == 0 && prompt_len == 1 && want_nsp);
     const int n = nsp_now ? 1 : std::min(check_every, sample_len - n_sampled);
-    SampleParams s1[MAX_OCC];
-    with_nsp(s1, nsp_now);
-    if ((rc = launch_steps(ctx, buf, ng, 2, n, s1, lg, D.n_vocab, st)) != WXB_OK) return rc;
+    SampleParams s1 = sp;
+    if (nsp_now) s1.nsp_out = no_speech_prob_dev;
+    if ((rc = launch_steps(ctx, buf, 2, n, s1, buf.logits, D.n_vocab, st)) != WXB_OK) return rc;
     n_sampled += n;
     if (n_sampled < sample_len && !nsp_now) {
-      for (int g = 0; g < ng; ++g)
-        WXB_CUDA(ctx, cudaMemcpyAsync(done_host.data() + g0[g], buf[g].done, (size_t)buf[g].B * 4, cudaMemcpyDeviceToHost, st));
+      WXB_CUDA(ctx, cudaMemcpyAsync(done_host.data(), buf.done, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
       WXB_CUDA(ctx, cudaStreamSynchronize(st));
       bool all = true;
       for (int b = 0; b < B; ++b) all = all && done_host[b];
       if (all) break;  // mlx_whisper_batch_decoder.py:357
     }
   }
-  for (int g = 0; g < ng; ++g) {
-    dec_finalize_kernel<<<buf[g].B, 256, 0, st>>>(buf[g].tokens, stride, prompt_len, n_sampled, sample_len, opts->eot,
-                                                  tokens_out_dev + (size_t)g0[g] * sample_len, n_tokens_dev + g0[g]);
-    WXB_LAUNCH_CHECK(ctx);
-    WXB_CUDA(ctx, cudaMemcpyAsync(sum_logprob_dev + g0[g], buf[g].sum_lp, (size_t)buf[g].B * 4, cudaMemcpyDeviceToDevice, st));
-  }
+  dec_finalize_kernel<<<B, 256, 0, st>>>(buf.tokens, stride, prompt_len, n_sampled, sample_len, opts->eot, tokens_out_dev, n_tokens_dev);
+  WXB_LAUNCH_CHECK(ctx);
+  WXB_CUDA(ctx, cudaMemcpyAsync(sum_logprob_dev, buf.sum_lp, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
   WXB_CUDA(ctx, cudaEventRecord(tm.e2, st));
   tm.steps = prompt_len - 1 + n_sampled;
   ctx->dec_timings.push_back(tm);
@@ -1839,14 +1558,12 @@ extern "C" int wxb_decoder_logits(wxb_ctx* ctx, const void* enc_out_dev, int B, 
   WXB_CUDA(ctx, cudaSetDevice(ctx->device));
   DecBuffers buf;
   int rc;
-  if ((rc = alloc_buffers(ctx, B, n_tok, 0, &buf)) != WXB_OK) return rc;
+  if ((rc = alloc_buffers(ctx, B, n_tok, &buf)) != WXB_OK) return rc;
   WXB_CUDA(ctx, cudaMemcpyAsync(buf.tokens, tokens_host, (size_t)B * n_tok * 4, cudaMemcpyHostToDevice, st));
   WXB_CUDA(ctx, cudaMemsetAsync(buf.d_pos, 0, 4, st));
   if ((rc = cross_kv_precompute(ctx, (const __nv_bfloat16*)enc_out_dev, buf, st)) != WXB_OK) return rc;
   SampleParams sp = {};
-  for (int pos = 0; pos < n_tok; ++pos) {
-    float* lg = logits_out_dev + (size_t)pos * D.n_vocab;
-    if ((rc = launch_steps(ctx, &buf, 1, 1, 1, &sp, &lg, (long long)n_tok * D.n_vocab, st)) != WXB_OK) return rc;
-  }
+  for (int pos = 0; pos < n_tok; ++pos)
+    if ((rc = launch_steps(ctx, buf, 1, 1, sp, logits_out_dev + (size_t)pos * D.n_vocab, (long long)n_tok * D.n_vocab, st)) != WXB_OK) return rc;
   return WXB_OK;
 }

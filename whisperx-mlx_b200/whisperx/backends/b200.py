@@ -99,6 +99,7 @@ class B200WhisperBackend(WhisperBackend):
         prompt = self.tokenizer.prompt(language, task, self.options["without_timestamps"])
         n = len(offs)
         out = {"tokens": [], "n_tokens": [], "sum_logprob": [], "no_speech_prob": []}
+        batch_size = min(int(batch_size), 64)  # sequences per wxb_decode_greedy call (include/wxb200.h)
         for i in range(0, n, batch_size):
             j = min(n, i + batch_size)
             mel = self.ctx.logmel(audio_dev, offs[i:j], lens[i:j], N_SAMPLES, self.dims["n_mels"], self._filters)
