@@ -20,6 +20,11 @@ def _dims(name):
     if name == "mini":
         return dict(n_mels=80, n_audio_ctx=1500, n_audio_state=128, n_audio_head=2, n_audio_layer=1,
                     n_vocab=1000, n_text_ctx=448, n_text_state=128, n_text_head=2, n_text_layer=2)
+    if name == "wide":
+        # 20 heads x 60 sequences = 1200 attention units on 148 x 8 warps: the self-attention phase's shared-unit
+        # round (8 warps of a CTA per unit) and the cross-attention remainder pieces only occur at this width
+        return dict(n_mels=80, n_audio_ctx=1500, n_audio_state=1280, n_audio_head=20, n_audio_layer=1,
+                    n_vocab=1000, n_text_ctx=448, n_text_state=1280, n_text_head=20, n_text_layer=1)
     return bw.dims_for(name)
 
 
@@ -39,10 +44,10 @@ def _setup(ctx, name, B, std=0.05, seed=5, mutate=None):
     return dims, w_ref, enc, ow
 
 
-@pytest.mark.parametrize("name,B", [("mini", 3), ("tiny", 2), ("mini", 19)])
+@pytest.mark.parametrize("name,B", [("mini", 3), ("tiny", 2), ("mini", 19), ("wide", 60)])
 def test_teacher_forced_logits(wxb_ctx, name, B):
-    dims, w_ref, enc, ow = _setup(wxb_ctx, name, B)
-    n_tok = 6
+    dims, w_ref, enc, ow = _setup(wxb_ctx, name, B, std=0.02 if name == "wide" else 0.05)
+    n_tok = 12 if name == "wide" else 6
     toks = np.random.RandomState(0).randint(0, dims["n_vocab"], size=(B, n_tok)).astype(np.int32)
     got = wxb_ctx.decoder_logits(enc, toks).float().cpu()
     with torch.no_grad():

@@ -446,134 +446,196 @@ __device__ __forceinline__ void att_consume(const uint4* kv, uint4* vv, int kb, 
   }
 }
 
-// Causal self-attention, one warp per (sequence, head).  The warp first finishes the QKV GEMV for its head
-// (sum of split-K partials + bias), appends the new K/V row to the cache, and attends over the pos cached rows
-// plus the new one (taken from registers, rounded to bf16 like its cached copy).
-__device__ __forceinline__ void self_attn_phase(const MkParams& p, int l, const float* __restrict__ qkv_b, int pos, const MkSync& sy) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, slot = lane >> 3, c8 = lane & 7;
-  const int d = p.d, H = p.H, B = p.B, TX = p.TX, gk = p.g_qkv.gk, N3 = 3 * d;
-  __nv_bfloat16* sk = p.self_kv + (size_t)l * 2 * B * H * TX * 64;
-  __nv_bfloat16* sv = sk + (size_t)B * H * TX * 64;
-  for (int u0 = sy.cta * MK_WARPS + warp; u0 < B * H; u0 += sy.nc * MK_WARPS) {
-    const int b = u0 / H, h = u0 - b * H;
-    const int col = h * 64 + c8 * 8;
-    float q8[8], k8[8], v8[8];
-    {
-      const float4 a0 = __ldg(reinterpret_cast<const float4*>(qkv_b + col)), a1 = __ldg(reinterpret_cast<const float4*>(qkv_b + col + 4));
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(qkv_b + d + col)), b1 = __ldg(reinterpret_cast<const float4*>(qkv_b + d + col + 4));
-      const float4 c0 = __ldg(reinterpret_cast<const float4*>(qkv_b + 2 * d + col)), c1 = __ldg(reinterpret_cast<const float4*>(qkv_b + 2 * d + col + 4));
-      q8[0] = a0.x; q8[1] = a0.y; q8[2] = a0.z; q8[3] = a0.w; q8[4] = a1.x; q8[5] = a1.y; q8[6] = a1.z; q8[7] = a1.w;
-      k8[0] = b0.x; k8[1] = b0.y; k8[2] = b0.z; k8[3] = b0.w; k8[4] = b1.x; k8[5] = b1.y; k8[6] = b1.z; k8[7] = b1.w;
-      v8[0] = c0.x; v8[1] = c0.y; v8[2] = c0.z; v8[3] = c0.w; v8[4] = c1.x; v8[5] = c1.y; v8[6] = c1.z; v8[7] = c1.w;
-    }
-    for (int ks0 = 0; ks0 < gk; ks0 += 4) {
-      // slot s fetches slice ks0 + s (6 independent 16-byte loads), then the 4 slots are summed by shuffles:
-      // one L2 round trip per 4 slices and a fixed summation order
-      float t[24];
+// Causal self-attention.  A (sequence, head) unit is finished by one warp: it completes the QKV GEMV for its head
+// (sum of split-K partials + bias), appends the new K/V row to the cache, and attends over cached keys plus the new one
+// (taken from registers, rounded to bf16 like its cached copy).  Units that do not fill a whole round of warps
+// (B H = 1200 on 1184 warps at batch 60) are NOT given a second round of their own: the 8 warps of a CTA share such
+// a unit, each attending over an eighth of the cached keys, and merge their states through shared memory.
+struct SelfUnit {
+  float q8[8];   // scaled q, dims 8 c8 .. 8 c8 + 7
+  uint4 kq, vq;  // the new key / value row (bf16), same dims
+};
+__device__ __forceinline__ SelfUnit self_unit_qkv(const MkParams& p, const float* __restrict__ qkv_b, int b, int h, int slot, int c8) {
+  const int d = p.d, B = p.B, gk = p.g_qkv.gk, N3 = 3 * d;
+  const int col = h * 64 + c8 * 8;
+  float q8[8], k8[8], v8[8];
+  {
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(qkv_b + col)), a1 = __ldg(reinterpret_cast<const float4*>(qkv_b + col + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(qkv_b + d + col)), b1 = __ldg(reinterpret_cast<const float4*>(qkv_b + d + col + 4));
+    const float4 c0 = __ldg(reinterpret_cast<const float4*>(qkv_b + 2 * d + col)), c1 = __ldg(reinterpret_cast<const float4*>(qkv_b + 2 * d + col + 4));
+    q8[0] = a0.x; q8[1] = a0.y; q8[2] = a0.z; q8[3] = a0.w; q8[4] = a1.x; q8[5] = a1.y; q8[6] = a1.z; q8[7] = a1.w;
+    k8[0] = b0.x; k8[1] = b0.y; k8[2] = b0.z; k8[3] = b0.w; k8[4] = b1.x; k8[5] = b1.y; k8[6] = b1.z; k8[7] = b1.w;
+    v8[0] = c0.x; v8[1] = c0.y; v8[2] = c0.z; v8[3] = c0.w; v8[4] = c1.x; v8[5] = c1.y; v8[6] = c1.z; v8[7] = c1.w;
+  }
+  for (int ks0 = 0; ks0 < gk; ks0 += 4) {
+    // slot s fetches slice ks0 + s (6 independent 16-byte loads), then the 4 slots are summed by shuffles:
+    // one L2 round trip per 4 slices and a fixed summation order
+    float t[24];
 #pragma unroll
-      for (int j = 0; j < 24; ++j) t[j] = 0.f;
-      if (ks0 + slot < gk) {
-        const float* base = p.part + ((size_t)(ks0 + slot) * B + b) * N3 + col;
+    for (int j = 0; j < 24; ++j) t[j] = 0.f;
+    if (ks0 + slot < gk) {
+      const float* base = p.part + ((size_t)(ks0 + slot) * B + b) * N3 + col;
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const float4 a0 = __ldcg(reinterpret_cast<const float4*>(base + j * d));
-          const float4 a1 = __ldcg(reinterpret_cast<const float4*>(base + j * d + 4));
-          t[8 * j + 0] = a0.x; t[8 * j + 1] = a0.y; t[8 * j + 2] = a0.z; t[8 * j + 3] = a0.w;
-          t[8 * j + 4] = a1.x; t[8 * j + 5] = a1.y; t[8 * j + 6] = a1.z; t[8 * j + 7] = a1.w;
-        }
+      for (int j = 0; j < 3; ++j) {
+        const float4 a0 = __ldcg(reinterpret_cast<const float4*>(base + j * d));
+        const float4 a1 = __ldcg(reinterpret_cast<const float4*>(base + j * d + 4));
+        t[8 * j + 0] = a0.x; t[8 * j + 1] = a0.y; t[8 * j + 2] = a0.z; t[8 * j + 3] = a0.w;
+        t[8 * j + 4] = a1.x; t[8 * j + 5] = a1.y; t[8 * j + 6] = a1.z; t[8 * j + 7] = a1.w;
       }
-#pragma unroll
-      for (int j = 0; j < 24; ++j) {
-        t[j] += __shfl_xor_sync(0xffffffffu, t[j], 8);
-        t[j] += __shfl_xor_sync(0xffffffffu, t[j], 16);
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { q8[j] += t[j]; k8[j] += t[8 + j]; v8[j] += t[16 + j]; }
     }
-    uint4 kq, vq;
-    kq.x = pack_bf16(k8[0], k8[1]); kq.y = pack_bf16(k8[2], k8[3]); kq.z = pack_bf16(k8[4], k8[5]); kq.w = pack_bf16(k8[6], k8[7]);
-    vq.x = pack_bf16(v8[0], v8[1]); vq.y = pack_bf16(v8[2], v8[3]); vq.z = pack_bf16(v8[4], v8[5]); vq.w = pack_bf16(v8[6], v8[7]);
-    const size_t slab = ((size_t)b * H + h) * TX * 64;
+#pragma unroll
+    for (int j = 0; j < 24; ++j) {
+      t[j] += __shfl_xor_sync(0xffffffffu, t[j], 8);
+      t[j] += __shfl_xor_sync(0xffffffffu, t[j], 16);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { q8[j] += t[j]; k8[j] += t[8 + j]; v8[j] += t[16 + j]; }
+  }
+  SelfUnit u;
+  u.kq.x = pack_bf16(k8[0], k8[1]); u.kq.y = pack_bf16(k8[2], k8[3]); u.kq.z = pack_bf16(k8[4], k8[5]); u.kq.w = pack_bf16(k8[6], k8[7]);
+  u.vq.x = pack_bf16(v8[0], v8[1]); u.vq.y = pack_bf16(v8[2], v8[3]); u.vq.z = pack_bf16(v8[4], v8[5]); u.vq.w = pack_bf16(v8[6], v8[7]);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) u.q8[j] = q8[j] * p.scale;
+  return u;
+}
+// online-softmax state of one warp over the cached keys [k_begin, k_end) (and the new key if with_new), merged over
+// the warp's 4 key slots: on return every lane holds m, l and the 8 output dims of its c8
+__device__ __forceinline__ void self_unit_attend(const SelfUnit& u, const __nv_bfloat16* Kb, const __nv_bfloat16* Vb, int k_begin, int k_end,
+                                                 bool with_new, int slot, int c8, float& m, float& lsum, float* acc) {
+  m = -INFINITY; lsum = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (with_new) {  // warp-uniform
+    const __nv_bfloat162* kh = reinterpret_cast<const __nv_bfloat162*>(&u.kq);
+    const __nv_bfloat162* vh = reinterpret_cast<const __nv_bfloat162*>(&u.vq);
+    float sdot = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(kh[j]);
+      sdot = fmaf(u.q8[2 * j], f.x, sdot);
+      sdot = fmaf(u.q8[2 * j + 1], f.y, sdot);
+    }
+    sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+    sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+    sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
     if (slot == 0) {
-      *reinterpret_cast<uint4*>(sk + slab + (size_t)pos * 64 + c8 * 8) = kq;
-      *reinterpret_cast<uint4*>(sv + slab + (size_t)pos * 64 + c8 * 8) = vq;
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) q8[j] *= p.scale;
-    // new key (slot 0 only)
-    float m = -INFINITY, lsum = 0.f, acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    {
-      const __nv_bfloat162* kh = reinterpret_cast<const __nv_bfloat162*>(&kq);
-      const __nv_bfloat162* vh = reinterpret_cast<const __nv_bfloat162*>(&vq);
-      float sdot = 0.f;
+      m = sdot;
+      lsum = 1.f;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 f = __bfloat1622float2(kh[j]);
-        sdot = fmaf(q8[2 * j], f.x, sdot);
-        sdot = fmaf(q8[2 * j + 1], f.y, sdot);
+        const float2 f = __bfloat1622float2(vh[j]);
+        acc[2 * j] = f.x;
+        acc[2 * j + 1] = f.y;
       }
-      sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
-      sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
-      sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
+    }
+  }
+  // cached keys (written by earlier steps): 16 keys per iteration, next iteration's rows in flight
+  const int n = k_end;
+  uint4 kA[4], vA[4], kB[4], vB[4];
+  auto sload = [&](uint4* kv, uint4* vv, int kb) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int key = kb + i * 4 + slot;
+      if (key < n) {
+        kv[i] = __ldcg(reinterpret_cast<const uint4*>(Kb + (size_t)key * 64 + c8 * 8));
+        vv[i] = __ldcg(reinterpret_cast<const uint4*>(Vb + (size_t)key * 64 + c8 * 8));
+      }
+    }
+  };
+  if (k_begin < n) sload(kA, vA, k_begin);
+  for (int kb = k_begin; kb < n; kb += 32) {
+    if (kb + 16 < n) sload(kB, vB, kb + 16);
+    att_consume<4>(kA, vA, kb, slot, n, u.q8, m, lsum, acc);
+    if (kb + 32 < n) sload(kA, vA, kb + 32);
+    if (kb + 16 < n) att_consume<4>(kB, vB, kb + 16, slot, n, u.q8, m, lsum, acc);
+  }
+  // merge the 4 slot states (lanes differing in bits 3 and 4)
+#pragma unroll
+  for (int o = 8; o <= 16; o <<= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+    const float l2 = __shfl_xor_sync(0xffffffffu, lsum, o);
+    const float mn = fmaxf(m, m2);
+    const float w1 = (m > -INFINITY) ? __expf(m - mn) : 0.f;
+    const float w2 = (m2 > -INFINITY) ? __expf(m2 - mn) : 0.f;
+    lsum = lsum * w1 + l2 * w2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float a2 = __shfl_xor_sync(0xffffffffu, acc[j], o);
+      acc[j] = acc[j] * w1 + a2 * w2;
+    }
+    m = mn;
+  }
+}
+__device__ __forceinline__ void self_unit_store(const MkParams& p, int b, int h, int c8, float lsum, const float* acc) {
+  const float inv = 1.f / lsum;
+  uint4 pk;
+  pk.x = pack_bf16(acc[0] * inv, acc[1] * inv);
+  pk.y = pack_bf16(acc[2] * inv, acc[3] * inv);
+  pk.z = pack_bf16(acc[4] * inv, acc[5] * inv);
+  pk.w = pack_bf16(acc[6] * inv, acc[7] * inv);
+  *reinterpret_cast<uint4*>(p.att + (size_t)b * p.d + h * 64 + c8 * 8) = pk;
+}
+
+__device__ __forceinline__ void self_attn_phase(const MkParams& p, int l, const float* __restrict__ qkv_b, int pos, float* scratch,
+                                                const MkSync& sy) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, slot = lane >> 3, c8 = lane & 7;
+  const int H = p.H, B = p.B, TX = p.TX;
+  __nv_bfloat16* sk = p.self_kv + (size_t)l * 2 * B * H * TX * 64;
+  __nv_bfloat16* sv = sk + (size_t)B * H * TX * 64;
+  const int n_units = B * H, n_warps = sy.nc * MK_WARPS;
+  int n_solo = n_units;  // units [0, n_solo) get a warp each; units [n_solo, n_units) a CTA each
+  const int left = n_units % n_warps;
+  if (left > 0 && left <= sy.nc && n_units > n_warps) n_solo = n_units - left;
+  // work items of this warp: its solo units, then (CTAs with a shared unit) an eighth of that unit's cached keys
+  const int n_rounds = (n_solo + n_warps - 1) / n_warps;
+  const bool shared_unit = n_solo + sy.cta < n_units;  // CTA-uniform
+  for (int round = 0; round < n_rounds + (shared_unit ? 1 : 0); ++round) {
+    const bool coop = round == n_rounds;
+    const int u0 = coop ? n_solo + sy.cta : round * n_warps + sy.cta * MK_WARPS + warp;
+    if (u0 >= (coop ? n_units : n_solo)) continue;
+    const int b = u0 / H, h = u0 - b * H;
+    const SelfUnit u = self_unit_qkv(p, qkv_b, b, h, slot, c8);
+    const size_t slab = ((size_t)b * H + h) * TX * 64;
+    if (slot == 0 && (!coop || warp == 0)) {
+      *reinterpret_cast<uint4*>(sk + slab + (size_t)pos * 64 + c8 * 8) = u.kq;
+      *reinterpret_cast<uint4*>(sv + slab + (size_t)pos * 64 + c8 * 8) = u.vq;
+    }
+    int k0 = 0, k1 = pos;
+    if (coop) {
+      const int per = (pos + MK_WARPS - 1) / MK_WARPS;  // cached keys per warp
+      k0 = min(pos, warp * per);
+      k1 = min(pos, k0 + per);
+    }
+    float m, lsum, acc[8];
+    self_unit_attend(u, sk + slab, sv + slab, k0, k1, !coop || warp == 0, slot, c8, m, lsum, acc);
+    if (!coop) {
+      if (slot == 0) self_unit_store(p, b, h, c8, lsum, acc);
+    } else {
+      float* st = scratch + warp * 66;  // m, l, O[64] of this warp
+      if (lane == 0) { st[0] = m; st[1] = lsum; }
       if (slot == 0) {
-        m = sdot;
-        lsum = 1.f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = __bfloat1622float2(vh[j]);
-          acc[2 * j] = f.x;
-          acc[2 * j + 1] = f.y;
+        for (int j = 0; j < 8; ++j) st[2 + c8 * 8 + j] = acc[j];
+      }
+      __syncthreads();
+      if (warp == 0 && slot == 0) {
+        float M = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < MK_WARPS; ++w) M = fmaxf(M, scratch[w * 66]);
+        float L = 0.f, o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = 0.f;
+#pragma unroll
+        for (int w = 0; w < MK_WARPS; ++w) {
+          const float mw = scratch[w * 66];
+          const float wt = (mw > -INFINITY) ? __expf(mw - M) : 0.f;
+          L += wt * scratch[w * 66 + 1];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += wt * scratch[w * 66 + 2 + c8 * 8 + j];
         }
+        self_unit_store(p, b, h, c8, L, o);
       }
-    }
-    // cached keys 0 .. pos-1 (written by earlier steps): 16 keys per iteration, next iteration's rows in flight
-    const __nv_bfloat16* Kb = sk + slab;
-    const __nv_bfloat16* Vb = sv + slab;
-    const int n = pos;
-    uint4 kA[4], vA[4], kB[4], vB[4];
-    auto sload = [&](uint4* kv, uint4* vv, int kb) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int key = kb + u * 4 + slot;
-        if (key < n) {
-          kv[u] = __ldcg(reinterpret_cast<const uint4*>(Kb + (size_t)key * 64 + c8 * 8));
-          vv[u] = __ldcg(reinterpret_cast<const uint4*>(Vb + (size_t)key * 64 + c8 * 8));
-        }
-      }
-    };
-    if (n > 0) sload(kA, vA, 0);
-    for (int kb = 0; kb < n; kb += 32) {
-      if (kb + 16 < n) sload(kB, vB, kb + 16);
-      att_consume<4>(kA, vA, kb, slot, n, q8, m, lsum, acc);
-      if (kb + 32 < n) sload(kA, vA, kb + 32);
-      if (kb + 16 < n) att_consume<4>(kB, vB, kb + 16, slot, n, q8, m, lsum, acc);
-    }
-    // merge the 4 slot states (lanes differing in bits 3 and 4)
-#pragma unroll
-    for (int o = 8; o <= 16; o <<= 1) {
-      const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
-      const float l2 = __shfl_xor_sync(0xffffffffu, lsum, o);
-      const float mn = fmaxf(m, m2);
-      const float w1 = (m > -INFINITY) ? __expf(m - mn) : 0.f;
-      const float w2 = (m2 > -INFINITY) ? __expf(m2 - mn) : 0.f;
-      lsum = lsum * w1 + l2 * w2;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float a2 = __shfl_xor_sync(0xffffffffu, acc[j], o);
-        acc[j] = acc[j] * w1 + a2 * w2;
-      }
-      m = mn;
-    }
-    if (slot == 0) {
-      const float inv = 1.f / lsum;
-      uint4 pk;
-      pk.x = pack_bf16(acc[0] * inv, acc[1] * inv);
-      pk.y = pack_bf16(acc[2] * inv, acc[3] * inv);
-      pk.z = pack_bf16(acc[4] * inv, acc[5] * inv);
-      pk.w = pack_bf16(acc[6] * inv, acc[7] * inv);
-      *reinterpret_cast<uint4*>(p.att + (size_t)b * d + col) = pk;
+      __syncthreads();  // the scratch is the attention scratch of the next cross-attention phase
     }
   }
 }
@@ -1081,7 +1143,7 @@ __device__ __forceinline__ void run_op(const MkParams& p, const DecLayerW* s_lay
       gemv_phase<MT>(p, *o.g, o.wm, o.xm, w.fc1_b, o.epi, ring, sy);
     }
   } else if (kind == PH_SELF) {
-    if (!(p.skip & 4)) self_attn_phase(p, l, w.qkv_b, pos, sy);
+    if (!(p.skip & 4)) self_attn_phase(p, l, w.qkv_b, pos, scratch, sy);
   } else if (kind == PH_CROSS) {
     if (!(p.skip & 1)) cross_attn_phase(p, l, w.cq_b, ring, scratch, sy);
   } else {
