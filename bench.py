@@ -105,7 +105,7 @@ def flops_encoder(dims):
 
 def decode_bytes_per_step(dims, B, t_mean):
     d, L, V = dims["n_text_state"], dims["n_text_layer"], dims["n_vocab"]
-    weights = 2 * (L * 14 * d * d + V * d)       # once per step per batch group of <= 16 rows (from HBM once; L2 after)
+    weights = 2 * (L * 14 * d * d + V * d)       # once per step
     cross = B * 2 * (L * 2 * 1500 * d)
     selfkv = B * 2 * (L * 2 * t_mean * d)
     return weights, cross, selfkv
@@ -298,25 +298,34 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel set: the decode step (one CUDA-graph launch = 1 + 8 L + 3 kernels) ----
+    # ---- roofline of the dominant kernel: dec_step_kernel, the persistent cooperative decode kernel.  One launch
+    # walks STEPS_PER_LAUNCH decode positions (wxb_decode_opts.check_every); its duration is measured with CUDA
+    # events on the launching stream inside wxb_decode_greedy (wxb_decode_stats), summed over the timed region.
     P = peaks()
     B = args.batch_size
-    n_batches = int(np.ceil(n_chunks / B))
     prompt_len = len(prompt)
     t_mean = (prompt_len + sample_len) / 2.0
-    wbytes, cbytes, sbytes = decode_bytes_per_step(dims, B, t_mean)
-    groups = int(np.ceil(B / 16))
+    wbytes, cbytes, sbytes = decode_bytes_per_step(dims, min(B, n_chunks), t_mean)
     bytes_step = wbytes + cbytes + sbytes  # algorithmic: weights once per step, cross-KV + self-KV per sequence
     steps_per_pass = n_dec_steps / args.steps
     dec_ms_per_step = steps_ms / max(n_dec_steps, 1)
+    steps_per_launch = min(16, sample_len)
     achieved = bytes_step / (dec_ms_per_step * 1e-3) / 1e9
     enc_flops = flops_encoder(dims) * n_chunks
     ckv_flops = 2 * 1500 * dims["n_text_state"] * dims["n_audio_state"] * 2 * dims["n_text_layer"] * n_chunks
     mel_bytes = n_chunks * (4 * 480000 + dims["n_mels"] * 3000 * 4)
-    roofline = {"bound": "hbm", "kernel": f"decode step (CUDA graph of {1 + 11 * dims['n_text_layer'] + 4} kernels: dec_gemv / dec_attn / sample)",
-                "achieved": achieved, "peak": P["hbm_gbs"], "unit": "GB/s", "frac": achieved / P["hbm_gbs"], "traffic": None,
-                "peak_source": P["source"], "bytes_per_launch": bytes_step, "ms_per_launch": dec_ms_per_step,
-                "weight_reads_per_step": groups,
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "dec_step_traffic.json")  # from the committed `ncu --set full` capture
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("model") == be.model_name and tj.get("batch") == B:
+            traffic = tj["dram_bytes_per_launch"]
+    roofline = {"bound": "hbm", "kernel": "dec_step_kernel (persistent cooperative kernel: %d operators per decode step separated by grid barriers, "
+                                          "%d steps per launch)" % (11 * dims["n_text_layer"] + 3, steps_per_launch),
+                "achieved": achieved, "peak": P["hbm_gbs"], "unit": "GB/s", "frac": achieved / P["hbm_gbs"], "traffic": traffic,
+                "peak_source": P["source"], "bytes_per_launch": bytes_step * steps_per_launch,
+                "ms_per_launch": dec_ms_per_step * steps_per_launch, "steps_per_launch": steps_per_launch,
+                "bytes_per_step": bytes_step, "ms_per_step": dec_ms_per_step,
                 "stages": {
                     "mel": {"ms": stage_ms["mel"], "GB/s": mel_bytes / (stage_ms["mel"] * 1e-3) / 1e9, "frac_hbm": mel_bytes / (stage_ms["mel"] * 1e-3) / 1e9 / P["hbm_gbs"]},
                     "encoder": {"ms": stage_ms["encoder"], "TFLOP/s": enc_flops / (stage_ms["encoder"] * 1e-3) / 1e12,

@@ -5,7 +5,7 @@ timeout 600 python bench.py --no-cpu-baseline > $o/bench_q.json 2> $o/bench_q.er
 python - <<'PY'
 import json
 d=json.loads(open('gpurun_out/bench_q.json').read().strip().splitlines()[-1]); r=d['roofline']
-print('value %.1f e2e %.1f ms/step %.1f | dec ms/step %.3f frac %.3f | enc ms %.1f frac %.3f | mel ms %.3f | ckv %.1f ctc %.2f' % (d['value'], d['e2e']['value'], d['ms_per_step'], r['ms_per_launch'], r['frac'], r['stages']['encoder']['ms'], r['stages']['encoder']['frac_bf16_burst'], r['stages']['mel']['ms'], r['stages']['cross_kv_gemm']['ms'], r['stages']['ctc']['ms']))
+print('value %.1f e2e %.1f ms/step %.1f | dec ms/step %.3f frac %.3f | enc ms %.1f frac %.3f | mel ms %.3f | ckv %.1f ctc %.2f' % (d['value'], d['e2e']['value'], d['ms_per_step'], r['ms_per_step'], r['frac'], r['stages']['encoder']['ms'], r['stages']['encoder']['frac_bf16_burst'], r['stages']['mel']['ms'], r['stages']['cross_kv_gemm']['ms'], r['stages']['ctc']['ms']))
 PY
 WXB_ATTN=tc timeout 600 python bench.py --no-cpu-baseline --no-e2e --steps 2 > $o/bench_q_tc.json 2> $o/bench_q_tc.err; echo "bench tc rc=$?"
 python - <<'PY'
