@@ -168,6 +168,10 @@ int wxb_decoder_logits(wxb_ctx* ctx, const void* enc_out_dev, int B, const int32
 int wxb_gemm_bf16(wxb_ctx* ctx, const void* A_dev, const void* W_dev, const float* bias_dev,
                   void* D_dev, int M, int N, int K, int flags, void* stream);
 
+/* Stand-alone encoder self-attention (exposed for parity tests and roofline timing): non-causal softmax(Q K^T / 8) V
+ * per head, head_dim 64.  qkv_dev bf16 [B*T, 3d] (Q | K | V column blocks, head h at columns 64h), out_dev bf16 [B*T, d]. */
+int wxb_encoder_attention(wxb_ctx* ctx, const void* qkv_dev, void* out_dev, int B, int T, int d, int H, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

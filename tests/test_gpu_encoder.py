@@ -67,3 +67,20 @@ def test_encoder_vs_oracle(wxb_ctx, cfg):
     print(f"[{cfg}] encoder max-abs err {float(err.max()):.4f} (mean {float(err.mean()):.5f}) at output scale {scale:.2f}")
     assert float(err.max()) <= 0.06 * max(1.0, scale), float(err.max())
     assert float(err.mean()) <= 0.006 * max(1.0, scale)
+
+
+@pytest.mark.parametrize("B,T,H", [(1, 1500, 2), (2, 1500, 6), (3, 700, 3), (1, 128, 1), (2, 129, 2)])
+def test_encoder_attention_vs_torch(wxb_ctx, B, T, H):
+    """Stand-alone self-attention vs torch fp32 SDPA on the same bf16 inputs.  P is rounded to bf16 before the PV
+    product (2^-9 relative per term), the output to bf16: max-abs tolerance 0.02 at |V| ~ 1."""
+    d = 64 * H
+    g = torch.Generator(device="cuda").manual_seed(B * 100 + T + H)
+    qkv = torch.randn(B * T, 3 * d, device="cuda", generator=g)
+    qkv[:, :d] *= 2.0  # scores of a few units: a real softmax, not a near-uniform one
+    qkv = qkv.to(torch.bfloat16)
+    got = wxb_ctx.encoder_attention(qkv, B, T, H).float()
+    q, k, v = [x.float().view(B, T, H, 64).transpose(1, 2) for x in qkv.split(d, dim=1)]
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B * T, d)
+    err = float((got - ref).abs().max())
+    print(f"[B={B} T={T} H={H}] attention max-abs err {err:.4f}")
+    assert err < 0.02, err

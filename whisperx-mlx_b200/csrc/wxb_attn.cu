@@ -1,15 +1,16 @@
 // wxb_attn.cu — encoder self-attention (non-causal, head_dim 64, T = 1500) on the 5th-gen tensor cores.
 //
-// One CTA = one (128-query tile, head, chunk).  Per 128-key tile j:
-//   S_j = Q K_j^T          tcgen05.mma M=128 N=128 K=64  (Q, K_j: TMA 128B-swizzled K-major tiles)  -> TMEM
-//   P_j = exp2(S_j c - m_j c)   softmax warps: one thread per query row reads its S row with tcgen05.ld,
-//                               keeps the running max / sum in registers, writes P_j (bf16) into shared
-//                               memory in the canonical K-major swizzled layout (A operand of the next MMA)
-//   O_j = P_j V_j          tcgen05.mma M=128 N=64 K=128 (V^T tiles from a pre-transposed copy)     -> TMEM
-//   o   = (o + O_{j-1}) * exp2((m_{j-1} - m_j) c)   accumulated in registers (no TMEM read-modify-write)
-// S and O are double-buffered in TMEM and K/V/P in shared memory, so the tensor core computes S_{j+1} and
-// O_{j-1} while the softmax warps work on tile j.  Warp roles: 0 = TMA producer, 1 = MMA issuer,
-// 2 = TMEM allocator, 4..7 = softmax / output.
+// One CTA = two 128-query tiles A and B of one (head, chunk), worked on by two softmax warpgroups in ping-pong: while
+// warpgroup A exponentiates S_A the tensor core computes S_B and P_B V, and vice versa.  Per 128-key tile j and q tile t:
+//   S_t = Q_t K_j^T        tcgen05.mma M=128 N=128 K=64  (Q, K_j: TMA 128B-swizzled K-major tiles)  -> TMEM
+//   P_t = exp2((S_t - m) c)    softmax warps: one thread per query row reads its S row with tcgen05.ld, keeps the
+//                              max / sum in registers, writes P_t (bf16) into shared memory in the canonical K-major
+//                              swizzled layout (A operand of the next MMA)
+//   O_t += P_t V_j         tcgen05.mma M=128 N=64 K=128 (V^T tiles from a pre-transposed copy), accumulated IN TMEM
+// The offset m baked into O_t and the row sum is only moved when the running row maximum has grown by more than 2^8
+// (P stays within bf16 / fp32 range), so the O_t rescale (tcgen05.ld, multiply, tcgen05.st) is rare after the first
+// tiles and the softmax threads touch O only once more, for the final 1 / sum.
+// Warp roles: 0..3 softmax A, 4..7 softmax B, 8 = TMA producer, 9 = MMA issuer, 10 = TMEM allocator.
 #include "wxb_common.cuh"
 #include "wxb_tc.cuh"
 #include <math.h>
@@ -19,26 +20,40 @@ using namespace wxbtc;
 namespace {
 
 constexpr int BQ = 128, BKV = 128;
-constexpr int AT_THREADS = 256;
-constexpr int Q_BYTES = BQ * 64 * 2;          // 16 KB
+constexpr int AT_THREADS = 384;
+constexpr int Q_BYTES = BQ * 64 * 2;          // 16 KB per q tile
 constexpr int K_BYTES = BKV * 64 * 2;         // 16 KB
 constexpr int VB_BYTES = 64 * 64 * 2;         // one [64 dims x 64 keys] K-block of V^T, 8 KB
 constexpr int V_BYTES = 2 * VB_BYTES;         // 16 KB
 constexpr int PB_BYTES = BQ * 64 * 2;         // one [128 q x 64 keys] K-block of P, 16 KB
-constexpr int P_BYTES = 2 * PB_BYTES;         // 32 KB
+constexpr int P_BYTES = 2 * PB_BYTES;         // 32 KB per q tile
 constexpr int OFF_Q = 0;
-constexpr int OFF_K = OFF_Q + Q_BYTES;
+constexpr int OFF_K = OFF_Q + 2 * Q_BYTES;
 constexpr int OFF_V = OFF_K + 2 * K_BYTES;
 constexpr int OFF_P = OFF_V + 2 * V_BYTES;
-constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;  // 147456
+constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;  // 163840
 constexpr int AT_SMEM = OFF_BAR + 16 * 8 + 16 + 1024;
-constexpr int TM_S = 0, TM_O = 256;           // TMEM columns: S[2] at 0/128, O[2] at 256/320
+constexpr int TM_S = 0, TM_O = 256;           // TMEM columns: S_A, S_B at 0 / 128, O_A, O_B at 256 / 320
+constexpr float RESCALE_LOG2 = 8.f;           // move the softmax offset only when the row max grew by more than 2^8
 
 struct AttnTcParams {
   int T, Tpad, d, H, n_kv_tiles;
   float scale_log2;
   __nv_bfloat16* out;
 };
+
+__device__ __forceinline__ void tc_st_32x32(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+        "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+        "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // V part of qkv [B*T, 3d] -> vT [(b*H + h)*64 + j][Tpad] (keys contiguous), zero in the T..Tpad-1 padding
 __global__ void __launch_bounds__(256)
@@ -70,51 +85,48 @@ v_transpose_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
   extern __shared__ uint8_t at_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = at_smem_raw + ((1024u - (smem_u32(at_smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;    // [2]
-  uint64_t* kv_empty = bars + 3;   // [2]
-  uint64_t* s_full = bars + 5;     // [2]
-  uint64_t* s_empty = bars + 7;    // [2]
-  uint64_t* p_full = bars + 9;     // [2]
-  uint64_t* o_full = bars + 11;    // [2]
-  uint64_t* o_empty = bars + 13;   // [2]
+  uint64_t* kv_full = bars + 1;    // [2 stages]
+  uint64_t* kv_empty = bars + 3;   // [2 stages]
+  uint64_t* s_full = bars + 5;     // [2 q tiles]  MMA -> softmax: S_t(j) complete
+  uint64_t* p_full = bars + 7;     // [2 q tiles]  softmax -> MMA: P_t(j) written, S_t(j) fully read, O_t rescaled if needed
+  uint64_t* pv_done = bars + 9;    // [2 q tiles]  MMA -> softmax: O_t += P_t(j) V_j complete (P_t buffer free, O_t current)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = blockIdx.x * 2 * BQ, h = blockIdx.y, b = blockIdx.z;
   const int n = p.n_kv_tiles;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQK)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmV)) : "memory");
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == 9 && lane == 0) {
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(kv_full + i, 1);
       mbar_init(kv_empty + i, 1);
       mbar_init(s_full + i, 1);
-      mbar_init(s_empty + i, 4);
       mbar_init(p_full + i, 4);
-      mbar_init(o_full + i, 1);
-      mbar_init(o_empty + i, 4);
+      mbar_init(pv_done + i, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (warp == 10) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == 8) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       const int row0 = b * p.T;
-      mbar_arrive_expect_tx(q_full, Q_BYTES);
+      mbar_arrive_expect_tx(q_full, 2 * Q_BYTES);
       tma_load_2d(smem + OFF_Q, &tmQK, q_full, h * 64, row0 + q0);
+      tma_load_2d(smem + OFF_Q + Q_BYTES, &tmQK, q_full, h * 64, row0 + q0 + BQ);
       for (int j = 0; j < n; ++j) {
         const int st = j & 1;
         mbar_wait(kv_empty + st, ((j >> 1) & 1) ^ 1);
@@ -124,162 +136,175 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
         tma_load_2d(smem + OFF_V + st * V_BYTES + VB_BYTES, &tmV, kv_full + st, j * BKV + 64, (b * p.H + h) * 64);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idescS = make_idesc_bf16(128, 128), idescO = make_idesc_bf16(128, 64);
-      const uint32_t sQ = smem_u32(smem + OFF_Q);
-      auto issue_S = [&](int j) {
-        const int st = j & 1;
-        mbar_wait(kv_full + st, (j >> 1) & 1);
-        mbar_wait(s_empty + st, ((j >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint64_t adesc = make_sw128_desc(sQ);
-        const uint64_t bdesc = make_sw128_desc(smem_u32(smem + OFF_K + st * K_BYTES));
+      auto issue_S = [&](int t, int j) {  // S_t(j) = Q_t K_j^T
+        const uint64_t adesc = make_sw128_desc(smem_u32(smem + OFF_Q + t * Q_BYTES));
+        const uint64_t bdesc = make_sw128_desc(smem_u32(smem + OFF_K + (j & 1) * K_BYTES));
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          tc_mma_bf16(tmem_base + TM_S + st * 128, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idescS, k != 0);
-        tc_commit(s_full + st);
+          tc_mma_bf16(tmem_base + TM_S + t * 128, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idescS, k != 0);
+        tc_commit(s_full + t);
       };
       mbar_wait(q_full, 0);
-      issue_S(0);
+      mbar_wait(kv_full + 0, 0);
+      tc_fence_after();
+      issue_S(0, 0);
+      issue_S(1, 0);
       for (int j = 0; j < n; ++j) {
         const int st = j & 1;
-        if (j + 1 < n) issue_S(j + 1);
-        mbar_wait(p_full + st, (j >> 1) & 1);
-        mbar_wait(o_empty + st, ((j >> 1) & 1) ^ 1);
-        tc_fence_after();
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(p_full + t, j & 1);
+          tc_fence_after();
 #pragma unroll
-        for (int kb2 = 0; kb2 < 2; ++kb2) {
-          const uint64_t adesc = make_sw128_desc(smem_u32(smem + OFF_P + st * P_BYTES + kb2 * PB_BYTES));
-          const uint64_t bdesc = make_sw128_desc(smem_u32(smem + OFF_V + st * V_BYTES + kb2 * VB_BYTES));
+          for (int kb2 = 0; kb2 < 2; ++kb2) {
+            const uint64_t adesc = make_sw128_desc(smem_u32(smem + OFF_P + t * P_BYTES + kb2 * PB_BYTES));
+            const uint64_t bdesc = make_sw128_desc(smem_u32(smem + OFF_V + st * V_BYTES + kb2 * VB_BYTES));
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc_mma_bf16(tmem_base + TM_O + st * 64, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idescO, (kb2 | k) != 0);
+            for (int k = 0; k < 4; ++k)
+              tc_mma_bf16(tmem_base + TM_O + t * 64, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idescO, (j | kb2 | k) != 0);
+          }
+          tc_commit(pv_done + t);
+          if (t == 1) tc_commit(kv_empty + st);  // S_A, S_B, PV_A, PV_B of this stage are all behind this commit
+          if (j + 1 < n) {
+            if (t == 0) {
+              mbar_wait(kv_full + ((j + 1) & 1), ((j + 1) >> 1) & 1);
+              tc_fence_after();
+            }
+            issue_S(t, j + 1);  // S_t is free: P_t(j) is only published after S_t(j) has been read completely
+          }
         }
-        tc_commit(o_full + st);
-        tc_commit(kv_empty + st);
       }
     }
-  } else if (warp >= 4) {
-    // ------------------------------------------------------------------ softmax + output
-    const int ew = warp - 4;
+  } else if (warp < 8) {
+    // ------------------------------------------------------------------ softmax warpgroups + output
+    const int t = warp >> 2, ew = warp & 3;
     const int r = ew * 32 + lane;  // query row inside the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
+    const uint32_t s_addr = tmem_base + lane_addr + TM_S + t * 128;
+    const uint32_t o_addr = tmem_base + lane_addr + TM_O + t * 64;
     const float sl = p.scale_log2;
-    float m_run = -INFINITY, l_run = 0.f;
-    float o[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) o[i] = 0.f;
+    float m_used = -INFINITY, m_run = -INFINITY, l_run = 0.f;
+    uint8_t* prow = smem + OFF_P + t * P_BYTES + r * 128;
 
     for (int j = 0; j < n; ++j) {
-      const int st = j & 1;
       const int valid = p.T - j * BKV;  // keys of this tile that exist (>= 128 except for the last tile)
-      mbar_wait(s_full + st, (j >> 1) & 1);
+      mbar_wait(s_full + t, j & 1);
       tc_fence_after();
-      const uint32_t s_addr = tmem_base + lane_addr + TM_S + st * 128;
+      // columns 64..127 stay in registers, columns 0..63 are read twice (max, then exp)
+      uint32_t hi[64];
+      tc_ld_32x32(s_addr + 64, hi);
+      tc_ld_32x32(s_addr + 96, hi + 32);
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tc_ld_32x32(s_addr + c * 32, v);
+      {
+        uint32_t lo[64];
+        tc_ld_32x32(s_addr, lo);
+        tc_ld_32x32(s_addr + 32, lo + 32);
         tc_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float f = (c * 32 + i < valid) ? __uint_as_float(v[i]) : -INFINITY;
-          mx = fmaxf(mx, f);
+        for (int i = 0; i < 64; ++i) {
+          if (i < valid) mx = fmaxf(mx, __uint_as_float(lo[i]));
+          if (64 + i < valid) mx = fmaxf(mx, __uint_as_float(hi[i]));
         }
       }
-      const float m_new = fmaxf(m_run, mx);
-      const float alpha = exp2f((m_run - m_new) * sl);
-      const float off = m_new * sl;
-      float rowsum = 0.f;
-      uint8_t* prow = smem + OFF_P + st * P_BYTES + r * 128;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tc_ld_32x32(s_addr + c * 32, v);
-        tc_wait_ld();
-        uint32_t pk[16];
+      m_run = fmaxf(m_run, mx);
+      const bool need = (m_run - m_used) * sl > RESCALE_LOG2;  // always true for the first tile (m_used = -inf)
+      if (j > 0) {
+        // P_t is free and O_t holds all tiles < j once PV_t(j-1) has completed
+        mbar_wait(pv_done + t, (j - 1) & 1);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, need)) {
+          const float alpha = need ? exp2f((m_used - m_run) * sl) : 1.f;
+          l_run *= alpha;
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float p0 = (c * 32 + i < valid) ? exp2f(__uint_as_float(v[i]) * sl - off) : 0.f;
-          const float p1 = (c * 32 + i + 1 < valid) ? exp2f(__uint_as_float(v[i + 1]) * sl - off) : 0.f;
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tc_ld_32x32(o_addr + c * 32, v);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tc_st_32x32(o_addr + c * 32, v);
+          }
+          tc_wait_st();
+        }
+      }
+      if (need) m_used = m_run;
+      const float off = m_used * sl;
+      float rowsum = 0.f;
+      // keys 64..127 -> P block 1
+      {
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 64; i += 2) {
+          const float p0 = (64 + i < valid) ? exp2f(fmaf(__uint_as_float(hi[i]), sl, -off)) : 0.f;
+          const float p1 = (64 + i + 1 < valid) ? exp2f(fmaf(__uint_as_float(hi[i + 1]), sl, -off)) : 0.f;
           rowsum += p0 + p1;
           __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
           pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);
         }
-        uint8_t* blk = prow + (c >> 1) * PB_BYTES;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int ch = (c & 1) * 4 + q;
-          *reinterpret_cast<uint4*>(blk + ((ch ^ (r & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-        }
+        for (int ch = 0; ch < 8; ++ch)
+          *reinterpret_cast<uint4*>(prow + PB_BYTES + ((ch ^ (r & 7)) << 4)) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
       }
-      // S_j fully read, P_j written: release the S buffer, publish P to the tensor core (async proxy)
+      // keys 0..63 -> P block 0
+      {
+        uint32_t lo[64];
+        tc_ld_32x32(s_addr, lo);
+        tc_ld_32x32(s_addr + 32, lo + 32);
+        tc_wait_ld();
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 64; i += 2) {
+          const float p0 = (i < valid) ? exp2f(fmaf(__uint_as_float(lo[i]), sl, -off)) : 0.f;
+          const float p1 = (i + 1 < valid) ? exp2f(fmaf(__uint_as_float(lo[i + 1]), sl, -off)) : 0.f;
+          rowsum += p0 + p1;
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
+          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch)
+          *reinterpret_cast<uint4*>(prow + ((ch ^ (r & 7)) << 4)) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+      }
+      l_run += rowsum;
+      // S_t(j) fully read, O_t consistent, P_t(j) written: publish to the tensor core (async proxy)
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(s_empty + st);
-        mbar_arrive(p_full + st);
-      }
-      l_run = l_run * alpha + rowsum;
-      m_run = m_new;
-      if (j > 0) {
-        const int sp = (j - 1) & 1;
-        mbar_wait(o_full + sp, ((j - 1) >> 1) & 1);
-        tc_fence_after();
-        const uint32_t o_addr = tmem_base + lane_addr + TM_O + sp * 64;
+      if (lane == 0) mbar_arrive(p_full + t);
+    }
+    // ---- output: O_t / l
+    mbar_wait(pv_done + t, (n - 1) & 1);
+    tc_fence_after();
+    const int q = q0 + t * BQ + r;
+    const float inv = 1.f / l_run;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t v[32];
-          tc_ld_32x32(o_addr + c * 32, v);
-          tc_wait_ld();
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tc_ld_32x32(o_addr + c * 32, v);
+      tc_wait_ld();
+      if (q < p.T) {
+        __nv_bfloat16* dst = p.out + ((size_t)b * p.T + q) * p.d + h * 64 + c * 32;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[c * 32 + i] = (o[c * 32 + i] + __uint_as_float(v[i])) * alpha;
+        for (int i = 0; i < 32; i += 8) {
+          uint4 pk;
+          __nv_bfloat162 b0 = __floats2bfloat162_rn(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
+          __nv_bfloat162 b1 = __floats2bfloat162_rn(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv);
+          __nv_bfloat162 b3 = __floats2bfloat162_rn(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv);
+          pk.x = *reinterpret_cast<uint32_t*>(&b0);
+          pk.y = *reinterpret_cast<uint32_t*>(&b1);
+          pk.z = *reinterpret_cast<uint32_t*>(&b2);
+          pk.w = *reinterpret_cast<uint32_t*>(&b3);
+          *reinterpret_cast<uint4*>(dst + i) = pk;
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(o_empty + sp);
-      }
-    }
-    {
-      const int sp = (n - 1) & 1;
-      mbar_wait(o_full + sp, ((n - 1) >> 1) & 1);
-      tc_fence_after();
-      const uint32_t o_addr = tmem_base + lane_addr + TM_O + sp * 64;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tc_ld_32x32(o_addr + c * 32, v);
-        tc_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] += __uint_as_float(v[i]);
-      }
-    }
-    const int q = q0 + r;
-    if (q < p.T) {
-      const float inv = 1.f / l_run;
-      __nv_bfloat16* dst = p.out + ((size_t)b * p.T + q) * p.d + h * 64;
-#pragma unroll
-      for (int i = 0; i < 64; i += 8) {
-        uint4 pk;
-        __nv_bfloat162 b0 = __floats2bfloat162_rn(o[i] * inv, o[i + 1] * inv);
-        __nv_bfloat162 b1 = __floats2bfloat162_rn(o[i + 2] * inv, o[i + 3] * inv);
-        __nv_bfloat162 b2 = __floats2bfloat162_rn(o[i + 4] * inv, o[i + 5] * inv);
-        __nv_bfloat162 b3 = __floats2bfloat162_rn(o[i + 6] * inv, o[i + 7] * inv);
-        pk.x = *reinterpret_cast<uint32_t*>(&b0);
-        pk.y = *reinterpret_cast<uint32_t*>(&b1);
-        pk.z = *reinterpret_cast<uint32_t*>(&b2);
-        pk.w = *reinterpret_cast<uint32_t*>(&b3);
-        *reinterpret_cast<uint4*>(dst + i) = pk;
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 10) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -309,7 +334,7 @@ int wxb_attention_tc(wxb_ctx* ctx, const __nv_bfloat16* qkv, __nv_bfloat16* vT, 
   p.T = T; p.Tpad = Tpad; p.d = d; p.H = H; p.n_kv_tiles = ceil_div(T, BKV);
   p.scale_log2 = (1.0f / sqrtf(64.f)) * 1.44269504088896341f;
   p.out = out;
-  attention_tc_kernel<<<dim3(ceil_div(T, BQ), H, B), AT_THREADS, AT_SMEM, st>>>(tmQK, tmV, p);
+  attention_tc_kernel<<<dim3(ceil_div(T, 2 * BQ), H, B), AT_THREADS, AT_SMEM, st>>>(tmQK, tmV, p);
   WXB_LAUNCH_CHECK(ctx);
   return WXB_OK;
 }

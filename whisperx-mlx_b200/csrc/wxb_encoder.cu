@@ -296,7 +296,7 @@ static bool use_tc_attention() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("WXB_ATTN");
-    v = (e && e[0] == 't') ? 1 : 0;  // WXB_ATTN=tc selects the tcgen05 kernel (correct, not yet faster: see DESIGN.md)
+    v = (e && e[0] == 'm') ? 0 : 1;  // WXB_ATTN=mma selects the older mma.sync kernel (A/B timing only)
   }
   return v == 1;
 }
@@ -394,6 +394,30 @@ int wxb_encode_impl(wxb_ctx* ctx, const float* mel_dev, int B, __nv_bfloat16* en
     }
   }
   return launch_layernorm(ctx, x, lnp_w, lnp_b, enc_out, M, d, st);
+}
+
+extern "C" int wxb_encoder_attention(wxb_ctx* ctx, const void* qkv_dev, void* out_dev, int B, int T, int d, int H, void* stream) {
+  if (!ctx) return WXB_ERR_INVALID;
+  if (!qkv_dev || !out_dev || B <= 0 || T <= 0 || H <= 0 || d != 64 * H)
+    return wxb_fail(ctx, WXB_ERR_INVALID, "wxb_encoder_attention: bad argument (head_dim must be 64)");
+  WXB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (use_tc_attention()) {
+    const int Tpad = (T + 7) & ~7;
+    __nv_bfloat16* vT = (__nv_bfloat16*)wxb_named(ctx, "enc.vT", (size_t)B * H * 64 * Tpad * 2);
+    if (!vT) return WXB_ERR_CUDA;
+    return wxb_attention_tc(ctx, (const __nv_bfloat16*)qkv_dev, vT, (__nv_bfloat16*)out_dev, B, T, d, H, st);
+  }
+  static bool attr = false;
+  if (!attr) {
+    WXB_CUDA(ctx, cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BQ * 128 + 4 * ATT_BK * 128));
+    attr = true;
+  }
+  const float scale_log2 = (1.0f / sqrtf(64.f)) * 1.44269504088896341f;
+  attention_kernel<<<dim3(ceil_div(T, ATT_BQ), H, B), ATT_THREADS, ATT_BQ * 128 + 4 * ATT_BK * 128, st>>>(
+      (const __nv_bfloat16*)qkv_dev, (__nv_bfloat16*)out_dev, T, d, scale_log2);
+  WXB_LAUNCH_CHECK(ctx);
+  return WXB_OK;
 }
 
 extern "C" int wxb_encode(wxb_ctx* ctx, const float* mel_dev, int B, void* enc_out_dev, void* stream) {

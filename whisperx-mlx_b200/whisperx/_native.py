@@ -77,6 +77,8 @@ def load_library(path: Optional[str] = None):
         lib.wxb_decoder_logits.argtypes = [vp, vp, i32, vp, i32, vp, vp]
         lib.wxb_gemm_bf16.restype = i32
         lib.wxb_gemm_bf16.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
+        lib.wxb_encoder_attention.restype = i32
+        lib.wxb_encoder_attention.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
         if lib.wxb_abi_version() != 1:
             raise WxbError("libwxb200.so ABI version mismatch")
         if path is None:
@@ -87,7 +89,7 @@ def load_library(path: Optional[str] = None):
 EXPORTED_SYMBOLS = (
     "wxb_abi_version", "wxb_create", "wxb_destroy", "wxb_last_error", "wxb_launch_count", "wxb_logmel",
     "wxb_ctc_align", "wxb_log_softmax_rows", "wxb_set_model", "wxb_encode", "wxb_decode_greedy",
-    "wxb_decoder_logits", "wxb_gemm_bf16", "wxb_decode_stats")
+    "wxb_decoder_logits", "wxb_gemm_bf16", "wxb_decode_stats", "wxb_encoder_attention")
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -258,6 +260,15 @@ class Context:
         flags = (1 if gelu else 0) | (2 if out_f32 else 0)
         self._check(self.lib.wxb_gemm_bf16(self.h, _ptr(A), _ptr(W), _ptr(bias), _ptr(D), M, N, K, flags, self._stream()))
         return D
+
+
+    def encoder_attention(self, qkv: torch.Tensor, B: int, T: int, H: int) -> torch.Tensor:
+        """qkv bf16 [B*T, 3*64*H] -> softmax(Q K^T / 8) V per head, bf16 [B*T, 64*H]."""
+        d = 64 * H
+        assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and tuple(qkv.shape) == (B * T, 3 * d)
+        out = torch.empty((B * T, d), dtype=torch.bfloat16, device=self.device)
+        self._check(self.lib.wxb_encoder_attention(self.h, _ptr(qkv), _ptr(out), B, T, d, H, self._stream()))
+        return out
 
 
 _contexts: Dict[int, Context] = {}
