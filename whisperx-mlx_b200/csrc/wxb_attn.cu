@@ -55,6 +55,87 @@ __device__ __forceinline__ void tc_st_32x32(uint32_t taddr, const uint32_t* v) {
 }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// ---- packed fp32 pairs (sm_100 FFMA2 / FADD2), 3-input max, bare MUFU.EX2 -------------------------------------------
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// p = 2^(s c - off) for 64 scores of one query row, rounded to bf16 into one 128-byte row of a swizzled P block; returns
+// the row sum.  The MUFU unit delivers 4 exponentials per clock and scheduler, an eighth of the FMA rate, so every other
+// PAIR of elements is exponentiated on the FMA pipe instead: round-to-nearest split x = n + f by the 1.5 * 2^23 trick,
+// 2^f by a degree-3 minimax polynomial on [-0.5, 0.5] (relative error 1e-4, far below the bf16 rounding of P),
+// 2^n by adding n to the exponent field.
+template <bool FULL>
+__device__ __forceinline__ float exp_block64(const uint32_t* sv, int col0, int valid, float sl, float off, uint8_t* prow_blk, int r) {
+  const uint64_t sl2 = pack2(sl, sl), noff2 = pack2(-off, -off);
+  const uint64_t magic2 = pack2(12582912.f, 12582912.f), nmagic2 = pack2(-12582912.f, -12582912.f), neg1 = pack2(-1.f, -1.f);
+  const uint64_t c3 = pack2(0.05500893f, 0.05500893f), c2 = pack2(0.24221097f, 0.24221097f), c1 = pack2(0.69328293f, 0.69328293f);
+  const uint64_t one2 = pack2(1.f, 1.f);
+  uint64_t acc = pack2(0.f, 0.f);
+  uint32_t pk[32];
+#pragma unroll
+  for (int i = 0; i < 64; i += 2) {
+    const uint64_t x2 = ffma2(pack2(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), sl2, noff2);
+    float p0, p1;
+    if ((i >> 1) & 1) {
+      float x0, x1;
+      unpack2(x2, x0, x1);
+      const uint64_t xc = pack2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+      const uint64_t rr = fadd2(xc, magic2);                       // low mantissa bits = round(x)
+      const uint64_t f2 = ffma2(fadd2(rr, nmagic2), neg1, xc);     // x - round(x)
+      uint64_t q2 = ffma2(f2, c3, c2);
+      q2 = ffma2(q2, f2, c1);
+      q2 = ffma2(q2, f2, one2);
+      float q0, q1, r0, r1;
+      unpack2(q2, q0, q1);
+      unpack2(rr, r0, r1);
+      p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(r0) << 23));
+      p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(r1) << 23));
+    } else {
+      float x0, x1;
+      unpack2(x2, x0, x1);
+      p0 = ex2(x0);
+      p1 = ex2(x1);
+    }
+    if (!FULL) {
+      if (col0 + i >= valid) p0 = 0.f;
+      if (col0 + i + 1 >= valid) p1 = 0.f;
+    }
+    acc = fadd2(acc, pack2(p0, p1));
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
+    pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);
+  }
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch)
+    *reinterpret_cast<uint4*>(prow_blk + ((ch ^ (r & 7)) << 4)) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+  float a0, a1;
+  unpack2(acc, a0, a1);
+  return a0 + a1;
+}
+
 // V part of qkv [B*T, 3d] -> vT [(b*H + h)*64 + j][Tpad] (keys contiguous), zero in the T..Tpad-1 padding
 __global__ void __launch_bounds__(256)
 v_transpose_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ vT, int T, int Tpad, int d, int H) {
@@ -203,10 +284,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
         tc_ld_32x32(s_addr, lo);
         tc_ld_32x32(s_addr + 32, lo + 32);
         tc_wait_ld();
+        if (valid >= BKV) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) {
-          if (i < valid) mx = fmaxf(mx, __uint_as_float(lo[i]));
-          if (64 + i < valid) mx = fmaxf(mx, __uint_as_float(hi[i]));
+          for (int i = 0; i < 64; i += 2) {
+            mx = max3(mx, __uint_as_float(lo[i]), __uint_as_float(lo[i + 1]));
+            mx = max3(mx, __uint_as_float(hi[i]), __uint_as_float(hi[i + 1]));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) {
+            if (i < valid) mx = fmaxf(mx, __uint_as_float(lo[i]));
+            if (64 + i < valid) mx = fmaxf(mx, __uint_as_float(hi[i]));
+          }
         }
       }
       m_run = fmaxf(m_run, mx);
@@ -232,40 +321,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
       }
       if (need) m_used = m_run;
       const float off = m_used * sl;
-      float rowsum = 0.f;
+      float rowsum;
+      const bool full = valid >= BKV;
       // keys 64..127 -> P block 1
-      {
-        uint32_t pk[32];
-#pragma unroll
-        for (int i = 0; i < 64; i += 2) {
-          const float p0 = (64 + i < valid) ? exp2f(fmaf(__uint_as_float(hi[i]), sl, -off)) : 0.f;
-          const float p1 = (64 + i + 1 < valid) ? exp2f(fmaf(__uint_as_float(hi[i + 1]), sl, -off)) : 0.f;
-          rowsum += p0 + p1;
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
-          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);
-        }
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch)
-          *reinterpret_cast<uint4*>(prow + PB_BYTES + ((ch ^ (r & 7)) << 4)) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
-      }
+      rowsum = full ? exp_block64<true>(hi, 64, valid, sl, off, prow + PB_BYTES, r) : exp_block64<false>(hi, 64, valid, sl, off, prow + PB_BYTES, r);
       // keys 0..63 -> P block 0
       {
         uint32_t lo[64];
         tc_ld_32x32(s_addr, lo);
         tc_ld_32x32(s_addr + 32, lo + 32);
         tc_wait_ld();
-        uint32_t pk[32];
-#pragma unroll
-        for (int i = 0; i < 64; i += 2) {
-          const float p0 = (i < valid) ? exp2f(fmaf(__uint_as_float(lo[i]), sl, -off)) : 0.f;
-          const float p1 = (i + 1 < valid) ? exp2f(fmaf(__uint_as_float(lo[i + 1]), sl, -off)) : 0.f;
-          rowsum += p0 + p1;
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
-          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);
-        }
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch)
-          *reinterpret_cast<uint4*>(prow + ((ch ^ (r & 7)) << 4)) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+        rowsum += full ? exp_block64<true>(lo, 0, valid, sl, off, prow, r) : exp_block64<false>(lo, 0, valid, sl, off, prow, r);
       }
       l_run += rowsum;
       // S_t(j) fully read, O_t consistent, P_t(j) written: publish to the tensor core (async proxy)
