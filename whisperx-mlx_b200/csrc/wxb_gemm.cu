@@ -7,18 +7,28 @@
 //               four times per stage; tcgen05.commit releases the stage / publishes the accumulator.
 //   warp 2      TMEM allocator (2 x BN columns: double-buffered accumulator so the epilogue of
 //               tile i overlaps the main loop of tile i+1).
-//   warps 4-7   epilogue: tcgen05.ld (32 lanes x 32 columns per instruction) -> bias, GELU(erf),
-//               residual / positional add, row remap (conv stem) -> bf16 or f32 global stores.
+//   warps 4-11  epilogue: two warps per TMEM lane quarter, each half of the tile's columns; tcgen05.ld (32 lanes x
+//               32 columns per instruction, the next chunk's load in flight) -> bias, GELU(erf), residual /
+//               positional add, row remap (conv stem) -> bf16 or f32 global stores.
 // Grid = min(#tiles, #SMs); tiles are walked m-fastest so concurrently running CTAs share W tiles.
+// PAIR variant (default for large problems): clusters of two CTAs issue ONE tcgen05.mma.cta_group::2 of M = 256 over two
+// m-adjacent tiles of the same n block.  Each CTA stages its own 128 A rows and only HALF of the W tile (the
+// tensor cores of both SMs read both halves), so a k block costs 32 KB of shared-memory fill and 8 KB of operand reads
+// per MMA and SM instead of 48 KB and 12 KB: with single-CTA 128 x 256 tiles the shared-memory port (TMA fill +
+// operand reads ~ 132 B/clk at full rate), not the tensor pipe, is the limit.  The leader CTA (rank 0) issues the MMAs;
+// both CTAs' TMA loads complete on the leader's full barrier, tcgen05.commit multicasts onto both CTAs' barriers, and
+// the peer's epilogue warps release the accumulator on the leader's barrier through the cluster window.
 #include "wxb_gemm.cuh"
 #include "wxb_tc.cuh"
+#include <stdlib.h>
 
 namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NTHREADS = 256;
+constexpr int NTHREADS = 384;
+constexpr int EPI_WARPS = 8;
 
 struct GemmParams {
   int M, N, K;
@@ -39,19 +49,55 @@ using namespace wxbtc;
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool PAIR = false>
 struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;  // a pair's CTA holds half of the W tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFF + 8 * (2 * STAGES + 4) + 16 + 1024;  // + alignment slack
 };
 
-template <int BN, int STAGES>
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// In the cluster window the shared-memory addresses of the two CTAs of a pair differ in bit 24; clearing it names the
+// leader's copy of an object (same offset) from either CTA.
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+// 2-D TMA load into this CTA's shared memory whose bytes complete on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// tcgen05.commit of the pair's MMAs arriving on the mbarrier at this offset in both CTAs
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// arrive on the leader's copy of `bar` (from either CTA)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
+}
+
+template <int BN, int STAGES, bool PAIR>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using L = SmemLayout<BN, STAGES>;
+  using L = SmemLayout<BN, STAGES, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
@@ -61,7 +107,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  // PAIR: a work item is a pair of m-adjacent tiles; this CTA takes m block 2 * mp + rank (a phantom block past the
+  // matrix still loads its W half and keeps the barriers in step: TMA zero-fills its A rows, the epilogue masks them)
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int num_mp = PAIR ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles;
+  const int num_tiles = num_mp * p.num_n_tiles;
+  const int first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -74,16 +126,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar + a, 1);
-      mbar_init(tempty_bar + a, 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar + a, PAIR ? 2 * EPI_WARPS : EPI_WARPS);  // one arrive per epilogue warp (of both CTAs)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {  // the same warp of both CTAs allocates for the pair
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -92,30 +150,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % p.num_m_tiles, n_blk = tile / p.num_m_tiles;
+      for (int tile = first; tile < num_tiles; tile += step) {
+        const int m_blk = PAIR ? 2 * (tile % num_mp) + rank : tile % num_mp, n_blk = tile / num_mp;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(empty_bar + stage, phase ^ 1);
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
-          mbar_arrive_expect_tx(full_bar + stage, L::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, full_bar + stage, kb * BK, m_blk * BM);
-          tma_load_2d(sb, &tmB, full_bar + stage, kb * BK, n_blk * BN);
+          if (PAIR) {
+            if (rank == 0) mbar_arrive_expect_tx(full_bar + stage, 2 * L::STAGE_BYTES);  // both CTAs' tiles
+            tma_load_2d_pair(sa, &tmA, full_bar + stage, kb * BK, m_blk * BM);
+            tma_load_2d_pair(sb, &tmB, full_bar + stage, kb * BK, n_blk * BN + rank * (BN / 2));
+          } else {
+            mbar_arrive_expect_tx(full_bar + stage, L::STAGE_BYTES);
+            tma_load_2d(sa, &tmA, full_bar + stage, kb * BK, m_blk * BM);
+            tma_load_2d(sb, &tmB, full_bar + stage, kb * BK, n_blk * BN);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       // instruction descriptor: D=f32 (bit 4), A=bf16 (bit 7), B=bf16 (bit 10), K-major A and B,
-      // N>>3 at bit 17, M>>4 at bit 24
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      // N>>3 at bit 17, M>>4 at bit 24 (M = 256 for the pair's MMA)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((PAIR ? 2 * BM : BM) >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = first; tile < num_tiles; tile += step) {
         mbar_wait(tempty_bar + acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
@@ -128,22 +192,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-            tc_mma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            if (PAIR) tc_mma_bf16_pair(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            else tc_mma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
           }
-          tc_commit(empty_bar + stage);
+          if (PAIR) tc_commit_pair(empty_bar + stage);  // frees the slot in both CTAs
+          else tc_commit(empty_bar + stage);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit(tfull_bar + acc);
+        if (PAIR) tc_commit_pair(tfull_bar + acc);  // both CTAs' epilogues read their 128 rows of the accumulator
+        else tc_commit(tfull_bar + acc);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
-    const int ew = warp - 4;  // == warp % 4: TMEM lane quarter this warp may read
+    const int ew = warp & 3;          // TMEM lane quarter this warp may read (warp % 4)
+    const int half = (warp - 4) >> 2;  // which half of the tile's 32-column chunks it handles
+    constexpr int CHUNKS = BN / 64;    // chunks per warp
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile % p.num_m_tiles, n_blk = tile / p.num_m_tiles;
+    for (int tile = first; tile < num_tiles; tile += step) {
+      const int m_blk = PAIR ? 2 * (tile % num_mp) + rank : tile % num_mp, n_blk = tile / num_mp;
       mbar_wait(tfull_bar + acc, acc_phase);
       tc_fence_after();
       const int r = m_blk * BM + ew * 32 + lane;  // GEMM row of this thread
@@ -159,22 +228,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const float* res_row = nullptr;
       if (p.res_mode == 1) res_row = p.residual + out_row * p.ldr;
       else if (p.res_mode == 2) res_row = p.residual + (long long)t_in_group * p.ldr;
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + half * CHUNKS * 32);
+      uint32_t vn[32];
+      tc_ld_32x32(taddr0, vn);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int cc = 0; cc < CHUNKS; ++cc) {
         uint32_t v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + c * 32);
-        tc_ld_32x32(taddr, v);
         tc_wait_ld();
-        const int n0 = n_blk * BN + c * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = vn[i];
+        if (cc + 1 < CHUNKS) tc_ld_32x32(taddr0 + (cc + 1) * 32, vn);  // in flight while this chunk is processed
+        const int n0 = n_blk * BN + (half * CHUNKS + cc) * 32;
         if (row_ok && n0 < p.N) {
           float f[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
           const bool full = (n0 + 32 <= p.N);
           if (p.bias) {
+            if (full) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (full || n0 + i < p.N) f[i] += __ldg(p.bias + n0 + i);
+              for (int i = 0; i < 32; i += 4) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
+                f[i] += bb.x; f[i + 1] += bb.y; f[i + 2] += bb.z; f[i + 3] += bb.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (n0 + i < p.N) f[i] += __ldg(p.bias + n0 + i);
+            }
           }
           if (p.gelu) {
 #pragma unroll
@@ -234,16 +315,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar + acc);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_leader(tempty_bar + acc);
+        else mbar_arrive(tempty_bar + acc);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
   // ------------------------------------------------------------------ teardown
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // no CTA leaves while its peer may still multicast into its shared memory
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
   }
 }
 
@@ -281,19 +367,46 @@ int wxb_make_tmap_bf16(wxb_ctx* ctx, CUtensorMap* tm, const void* base, uint64_t
 
 namespace {
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool PAIR>
 int launch_cfg(wxb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
-  using L = SmemLayout<BN, STAGES>;
+  using L = SmemLayout<BN, STAGES, PAIR>;
+  auto kern = gemm_tc_kernel<BN, STAGES, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
-    WXB_CUDA(ctx, cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    WXB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_set = true;
   }
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
-  const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
-  gemm_tc_kernel<BN, STAGES><<<grid, NTHREADS, L::TOTAL, st>>>(tmA, tmB, p);
-  WXB_LAUNCH_CHECK(ctx);
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = L::TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (PAIR) {
+    const int pairs = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+    const int max_pairs = ctx->sm_count / 2;
+    cfg.gridDim = dim3(2 * (pairs < max_pairs ? pairs : max_pairs));
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  } else {
+    const int tiles = p.num_m_tiles * p.num_n_tiles;
+    cfg.gridDim = dim3(tiles < ctx->sm_count ? tiles : ctx->sm_count);
+  }
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
+  ctx->launches++;
+  if (e != cudaSuccess) return wxb_fail(ctx, WXB_ERR_CUDA, "gemm launch failed: %s", cudaGetErrorString(e));
   return WXB_OK;
+}
+
+// WXB_GEMM=1cta keeps every GEMM on the single-CTA kernel (A/B timing)
+bool gemm_pairs_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WXB_GEMM");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 }  // namespace
@@ -318,9 +431,12 @@ int wxb_gemm_launch(wxb_ctx* ctx, const GemmArgs& a, cudaStream_t st) {
   int rc;
   const long long lda = a.lda ? a.lda : a.K;
   if ((rc = wxb_make_tmap_bf16(ctx, &tmA, a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)lda * 2, BK, BM)) != WXB_OK) return rc;
-  if ((rc = wxb_make_tmap_bf16(ctx, &tmB, a.W, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.K * 2, BK, BN)) != WXB_OK) return rc;
-  if (BN == 256) return launch_cfg<256, 4>(ctx, tmA, tmB, p, st);
-  return launch_cfg<128, 6>(ctx, tmA, tmB, p, st);
+  // pairs of CTAs sharing the W tile where there is enough work for every pair of SMs
+  const bool pair = gemm_pairs_enabled() && BN == 256 && p.num_m_tiles * p.num_n_tiles >= 2 * ctx->sm_count;
+  if ((rc = wxb_make_tmap_bf16(ctx, &tmB, a.W, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.K * 2, BK, pair ? BN / 2 : BN)) != WXB_OK) return rc;
+  if (pair) return launch_cfg<256, 6, true>(ctx, tmA, tmB, p, st);
+  if (BN == 256) return launch_cfg<256, 4, false>(ctx, tmA, tmB, p, st);
+  return launch_cfg<128, 6, false>(ctx, tmA, tmB, p, st);
 }
 
 extern "C" int wxb_gemm_bf16(wxb_ctx* ctx, const void* A_dev, const void* W_dev, const float* bias_dev, void* D_dev,
