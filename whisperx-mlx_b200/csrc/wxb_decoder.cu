@@ -954,6 +954,7 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
 // mlx_whisper_batch_decoder.py:267-303 for one row per CTA: (no_speech_prob from the unfiltered logits,)
 // filters, argmax (first max), logprob accounting, EOT latch.  Row loops keep 8 independent loads in flight.
 __device__ __forceinline__ void sample_phase(const SampleParams& p, int B, int pos, bool do_sample, float* red, int* red_i, const MkSync& sy) {
+  __shared__ float red_s[MK_WARPS];
   const int tid = threadIdx.x;
   constexpr int U = 8;
   for (int b = sy.cta; b < B; b += sy.nc) {
@@ -990,7 +991,8 @@ __device__ __forceinline__ void sample_phase(const SampleParams& p, int B, int p
       x[p.eot] = -INFINITY;
     }
     __syncthreads();
-    float best = -INFINITY;
+    // one pass: running (max, first index of the max, sum of exp relative to the max) per thread, merged per block
+    float best = -INFINITY, s = 0.f;
     int bi = 0x7fffffff;
     for (int i0 = tid; i0 < p.V; i0 += MK_THREADS * U) {
       float t[U];
@@ -999,31 +1001,36 @@ __device__ __forceinline__ void sample_phase(const SampleParams& p, int B, int p
 #pragma unroll
       for (int j = 0; j < U; ++j) {
         const int i = i0 + MK_THREADS * j;  // increasing within the thread: strict > keeps the first maximum
-        if (i < p.V && (t[j] > best || bi == 0x7fffffff)) { best = t[j]; bi = i; }
+        if (t[j] > best) {
+          s = s * __expf(best - t[j]) + 1.f;  // best = -inf -> s = 0
+          best = t[j];
+          bi = i;
+        } else if (t[j] > -INFINITY) {
+          s += __expf(t[j] - best);
+        }
       }
     }
+    auto merge = [](float& m, int& mi, float& ms, float om, int oi, float os) {
+      if (om > m || (om == m && oi < mi)) {
+        ms = (m > -INFINITY ? ms * __expf(m - om) : 0.f) + os;
+        m = om; mi = oi;
+      } else if (om > -INFINITY) {
+        ms += os * __expf(om - m);
+      }
+    };
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const float ov = __shfl_xor_sync(0xffffffffu, best, o);
       const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+      const float os = __shfl_xor_sync(0xffffffffu, s, o);
+      merge(best, bi, s, ov, oi, os);
     }
     __syncthreads();
-    if ((tid & 31) == 0) { red[tid >> 5] = best; red_i[tid >> 5] = bi; }
+    if ((tid & 31) == 0) { red[tid >> 5] = best; red_i[tid >> 5] = bi; red_s[tid >> 5] = s; }
     __syncthreads();
-    best = red[0]; bi = red_i[0];
+    best = red[0]; bi = red_i[0]; s = red_s[0];
 #pragma unroll
-    for (int w = 1; w < MK_WARPS; ++w)
-      if (red[w] > best || (red[w] == best && red_i[w] < bi)) { best = red[w]; bi = red_i[w]; }
-    float s = 0.f;
-    for (int i0 = tid; i0 < p.V; i0 += MK_THREADS * U) {
-      float t[U];
-#pragma unroll
-      for (int j = 0; j < U; ++j) { const int i = i0 + MK_THREADS * j; t[j] = i < p.V ? __ldcg(x + i) : -INFINITY; }
-#pragma unroll
-      for (int j = 0; j < U; ++j) s += expf(t[j] - best);
-    }
-    s = block_sum(s, red);
+    for (int w = 1; w < MK_WARPS; ++w) merge(best, bi, s, red[w], red_i[w], red_s[w]);
     if (tid == 0) {
       const float logprob = -logf(s);  // x[bi] - (best + log(sum)) with x[bi] == best
       int* row = p.tokens + (size_t)b * p.stride;
