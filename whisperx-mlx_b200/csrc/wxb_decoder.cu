@@ -500,8 +500,11 @@ __device__ __forceinline__ SelfUnit self_unit_qkv(const MkParams& p, const float
 }
 // online-softmax state of one warp over the cached keys [k_begin, k_end) (and the new key if with_new), merged over
 // the warp's 4 key slots: on return every lane holds m, l and the 8 output dims of its c8
+constexpr int SA_AHEAD = 4;            // chunks of 16 keys requested ahead of the one being consumed
+constexpr int SA_RING = SA_AHEAD + 1;  // 4 KB chunk slots per warp
+static_assert(MK_WARPS * SA_RING * 4096 <= RING_BYTES, "self-attention staging must fit the TMA ring region");
 __device__ __forceinline__ void self_unit_attend(const SelfUnit& u, const __nv_bfloat16* Kb, const __nv_bfloat16* Vb, int k_begin, int k_end,
-                                                 bool with_new, int slot, int c8, float& m, float& lsum, float* acc) {
+                                                 bool with_new, int slot, int c8, uint32_t stage, float& m, float& lsum, float* acc) {
   m = -INFINITY; lsum = 0.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -529,26 +532,42 @@ __device__ __forceinline__ void self_unit_attend(const SelfUnit& u, const __nv_b
       }
     }
   }
-  // cached keys (written by earlier steps): 16 keys per iteration, next iteration's rows in flight
+  // Cached keys (written by earlier steps), 16 per chunk.  The loop is bound by memory latency, not bandwidth, so the
+  // rows of the next SA_AHEAD chunks are kept in flight with cp.async into this warp's slice of the (idle) TMA ring:
+  // a lane copies exactly the 16-byte pieces it will read back itself, so shared memory only extends its registers.
   const int n = k_end;
-  uint4 kA[4], vA[4], kB[4], vB[4];
-  auto sload = [&](uint4* kv, uint4* vv, int kb) {
+  const int nch = (n > k_begin) ? (n - k_begin + 15) >> 4 : 0;
+  const uint32_t lane_off = (uint32_t)((slot * 8 + c8) * 16);  // inside a 512-byte row group (4 keys x 128 B)
+  auto issue = [&](int c) {  // chunk c: keys k_begin + 16 c + 4 i + slot; K pieces at [c % SA_RING][i], V pieces 2 KB behind
+    if (c < nch) {
+      const int kb = k_begin + (c << 4);
+      const uint32_t dst = stage + (uint32_t)((c % SA_RING) * 4096) + lane_off;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int key = kb + i * 4 + slot;
-      if (key < n) {
-        kv[i] = __ldcg(reinterpret_cast<const uint4*>(Kb + (size_t)key * 64 + c8 * 8));
-        vv[i] = __ldcg(reinterpret_cast<const uint4*>(Vb + (size_t)key * 64 + c8 * 8));
+      for (int i = 0; i < 4; ++i) {
+        const int key = kb + i * 4 + slot;
+        if (key < n) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 512), "l"(Kb + (size_t)key * 64 + c8 * 8) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 2048 + i * 512), "l"(Vb + (size_t)key * 64 + c8 * 8) : "memory");
+        }
       }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");  // one group per chunk index, empty or not: the wait below counts groups
   };
-  if (k_begin < n) sload(kA, vA, k_begin);
-  for (int kb = k_begin; kb < n; kb += 32) {
-    if (kb + 16 < n) sload(kB, vB, kb + 16);
-    att_consume<4>(kA, vA, kb, slot, n, u.q8, m, lsum, acc);
-    if (kb + 32 < n) sload(kA, vA, kb + 32);
-    if (kb + 16 < n) att_consume<4>(kB, vB, kb + 16, slot, n, u.q8, m, lsum, acc);
+#pragma unroll
+  for (int c = 0; c < SA_AHEAD; ++c) issue(c);
+  for (int c = 0; c < nch; ++c) {
+    issue(c + SA_AHEAD);
+    asm volatile("cp.async.wait_group %0;" ::"n"(SA_AHEAD) : "memory");  // chunk c has landed
+    const uint32_t src = stage + (uint32_t)((c % SA_RING) * 4096) + lane_off;
+    uint4 kA[4], vA[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(kA[i].x), "=r"(kA[i].y), "=r"(kA[i].z), "=r"(kA[i].w) : "r"(src + i * 512));
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(vA[i].x), "=r"(vA[i].y), "=r"(vA[i].z), "=r"(vA[i].w) : "r"(src + 2048 + i * 512));
+    }
+    att_consume<4>(kA, vA, k_begin + (c << 4), slot, n, u.q8, m, lsum, acc);
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   // merge the 4 slot states (lanes differing in bits 3 and 4)
 #pragma unroll
   for (int o = 8; o <= 16; o <<= 1) {
@@ -576,9 +595,10 @@ __device__ __forceinline__ void self_unit_store(const MkParams& p, int b, int h,
   *reinterpret_cast<uint4*>(p.att + (size_t)b * p.d + h * 64 + c8 * 8) = pk;
 }
 
-__device__ __forceinline__ void self_attn_phase(const MkParams& p, int l, const float* __restrict__ qkv_b, int pos, float* scratch,
-                                                const MkSync& sy) {
+__device__ __forceinline__ void self_attn_phase(const MkParams& p, int l, const float* __restrict__ qkv_b, int pos, uint8_t* ring,
+                                                float* scratch, const MkSync& sy) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, slot = lane >> 3, c8 = lane & 7;
+  const uint32_t stage = smem_u32(ring) + (uint32_t)(warp * SA_RING * 4096);  // this warp's K/V staging slots
   const int H = p.H, B = p.B, TX = p.TX;
   __nv_bfloat16* sk = p.self_kv + (size_t)l * 2 * B * H * TX * 64;
   __nv_bfloat16* sv = sk + (size_t)B * H * TX * 64;
@@ -607,7 +627,7 @@ __device__ __forceinline__ void self_attn_phase(const MkParams& p, int l, const 
       k1 = min(pos, k0 + per);
     }
     float m, lsum, acc[8];
-    self_unit_attend(u, sk + slab, sv + slab, k0, k1, !coop || warp == 0, slot, c8, m, lsum, acc);
+    self_unit_attend(u, sk + slab, sv + slab, k0, k1, !coop || warp == 0, slot, c8, stage, m, lsum, acc);
     if (!coop) {
       if (slot == 0) self_unit_store(p, b, h, c8, lsum, acc);
     } else {
@@ -1150,7 +1170,7 @@ __device__ __forceinline__ void run_op(const MkParams& p, const DecLayerW* s_lay
       gemv_phase<MT>(p, *o.g, o.wm, o.xm, w.fc1_b, o.epi, ring, sy);
     }
   } else if (kind == PH_SELF) {
-    if (!(p.skip & 4)) self_attn_phase(p, l, w.qkv_b, pos, scratch, sy);
+    if (!(p.skip & 4)) self_attn_phase(p, l, w.qkv_b, pos, ring, scratch, sy);
   } else if (kind == PH_CROSS) {
     if (!(p.skip & 1)) cross_attn_phase(p, l, w.cq_b, ring, scratch, sy);
   } else {
