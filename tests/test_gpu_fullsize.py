@@ -1,0 +1,117 @@
+"""BASELINE.json's full sizes through size-independent properties (no CPU oracle can follow at these sizes in
+seconds, so the checks are properties of the path itself, plus oracle spot checks on a few units):
+
+  * log-mel, 60 x 30 s chunks, 128 bins: every chunk of the batch is bit-identical to the same chunk alone
+    (the per-chunk max clamp must not leak across chunks); three chunks against the numpy oracle;
+  * CTC beam-2, 60 segments of T = 1499 in one launch: every path is monotone, starts at token 0, ends at the
+    last token and has T points; three segments bit-exact against the oracle;
+  * large-v3 dims (32 + 32 layers, d = 1280, 20 heads), batch 8 (BASELINE config 3): the encoder is bit-identical
+    under batching (GEMM rows and attention heads are independent of the batch), teacher-forced decoder logits of a
+    sequence agree between batch 8 and batch 3 within the bf16 rounding budget (the cross-attention slabs are cut
+    and merged differently, so fp32 sums re-associate), the decode is deterministic, and a full greedy call fills every row with in-range tokens.
+"""
+import numpy as np
+import pytest
+import torch
+
+from fake_ctc_model import synthetic_speech
+from oracle import ctc as octc
+from oracle import mel as omel
+
+pytestmark = pytest.mark.gpu
+
+
+def test_logmel_full_batch_chunk_independence(wxb_ctx):
+    import whisperx.audio as wa
+    base = synthetic_speech(60.0, seed=1234)
+    audio = np.tile(base, 30)
+    chunks = [audio[i * 480000:(i + 1) * 480000] * (0.05 + 0.95 * ((i * 7) % 10) / 9.0) for i in range(60)]
+    chunks[17] = chunks[17][:123457]   # a ragged one and a silent one in the middle of the batch
+    chunks[41] = np.zeros(480000, np.float32)
+    got = wa.log_mel_chunks(chunks, 128)
+    assert got.shape == (60, 128, 3000)
+    for i in (0, 17, 41, 59):
+        alone = wa.log_mel_chunks([chunks[i]], 128)[0]
+        assert torch.equal(got[i], alone), f"chunk {i} differs inside the batch"
+    ref = omel.log_mel_chunks([chunks[i] for i in (3, 17, 58)], 128)
+    for j, i in enumerate((3, 17, 58)):
+        err = np.abs(got[i].cpu().numpy() - ref[j]) / np.maximum(1.0, np.abs(ref[j]))
+        assert err.max() <= 1e-4, (i, float(err.max()))
+
+
+def test_ctc_full_batch_path_properties(wxb_ctx):
+    from whisperx._native import CTC_BEAM2
+    rng = np.random.RandomState(11)
+    T, V, n_seg = 1499, 29, 60
+    emis = torch.log_softmax(torch.randn(n_seg, T, V, generator=torch.Generator().manual_seed(5)) * 3.0, -1)
+    toks = []
+    for _ in range(n_seg):
+        n = int(rng.randint(50, 451))
+        t = rng.randint(1, V, size=n).astype(np.int32)
+        t[rng.rand(n) < 0.05] = -1
+        toks.append(t)
+    t_off = (np.arange(n_seg + 1) * T).astype(np.int32)
+    n_off = np.concatenate([[0], np.cumsum([len(t) for t in toks])]).astype(np.int32)
+    r = wxb_ctx.ctc_align(emis.reshape(-1, V).cuda(), t_off, torch.from_numpy(np.concatenate(toks)).cuda(), n_off, 0, CTC_BEAM2)
+    status = r["status"].cpu().numpy()
+    ptok = r["path_tok"].cpu().numpy()
+    plp = r["path_lp"].cpu().numpy()
+    assert (status == 0).all()
+    for i in range(n_seg):
+        p = ptok[t_off[i]:t_off[i + 1]]
+        assert len(p) == T and p[0] == 0 and p[-1] == len(toks[i]) - 1
+        d = np.diff(p)
+        assert ((d == 0) | (d == 1)).all(), f"segment {i}: path is not monotone"
+        assert np.isfinite(plp[t_off[i]:t_off[i + 1]]).all()
+    for i in (0, 29, 59):
+        e = emis[i].numpy()
+        ref = octc.backtrack_beam(octc.get_trellis(e, toks[i].tolist(), 0), e, toks[i].tolist(), 0, beam_width=2)
+        assert ptok[t_off[i]:t_off[i + 1]].tolist() == [q.token_index for q in ref], i
+
+
+def test_large_v3_batch8_properties(wxb_ctx):
+    from whisperx.backends import b200_weights as bw
+    dims = bw.dims_for("large-v3")
+    sp = bw.special_tokens(dims)
+    w = bw.init_random_weights(dims, seed=0)
+    kw = bw.to_kernel_layout(w, dims, "cuda")
+    del w
+    wxb_ctx.set_model(dims, kw)
+    B = 8
+    g = torch.Generator().manual_seed(77)
+    mel = (torch.randn(B, dims["n_mels"], 3000, generator=g) * 0.5).cuda()
+    enc = wxb_ctx.encode(mel)
+    assert enc.shape == (B, 1500, dims["n_audio_state"]) and torch.isfinite(enc.float()).all()
+    # encoder: batching does not change a chunk's numerics at all
+    for i in (0, 5):
+        assert torch.equal(wxb_ctx.encode(mel[i:i + 1].contiguous())[0], enc[i]), f"encoder row {i} depends on the batch"
+    # decoder: logits of a sequence in batch 8 vs the same sequences as a batch of 3 (other slab cuts, other GEMV tiles)
+    n_tok = 5
+    toks = np.random.RandomState(3).randint(0, dims["n_vocab"], size=(B, n_tok)).astype(np.int32)
+    full = wxb_ctx.decoder_logits(enc, toks).float()
+    again = wxb_ctx.decoder_logits(enc, toks).float()
+    assert torch.equal(full, again), "decoder is not deterministic"
+    sub = wxb_ctx.decoder_logits(enc[2:5].contiguous(), toks[2:5].copy()).float()
+    sigma = float(full.std())
+    diff = float((full[2:5] - sub).abs().max())
+    print(f"large-v3 batch 8 vs 3: logits max-abs diff {diff:.2e} at logit std {sigma:.3f}")
+    # not bit-equal: a re-associated fp32 sum can flip the bf16 rounding of an activation (2^-9 relative), and that
+    # propagates through 32 layers; the bound is the bf16 budget the oracle comparison uses as well
+    assert diff <= 0.03 * max(sigma, 1.0), diff
+    # greedy decode: every row is filled with in-range tokens, lengths and logprobs are consistent
+    prompt = [sp["sot"], sp["sot"] + 1, sp["transcribe"], sp["no_timestamps"]]
+    r = wxb_ctx.decode_greedy(enc, prompt, sp["eot"], no_speech=sp["no_speech"], sample_len=24, suppress_blank=True,
+                              blank_token=sp["blank"])
+    tokens = r["tokens"].cpu().numpy()
+    n = r["n_tokens"].cpu().numpy()
+    assert tokens.shape == (B, 24) and ((tokens >= 0) & (tokens < dims["n_vocab"])).all()
+    for b in range(B):
+        row = tokens[b].tolist()
+        assert n[b] == (row.index(sp["eot"]) if sp["eot"] in row else 24)
+        assert (tokens[b, n[b]:] == sp["eot"]).all()
+    lp = r["sum_logprob"].cpu().numpy()
+    nsp = r["no_speech_prob"].cpu().numpy()
+    assert np.isfinite(lp).all() and (lp <= 0).all() and ((nsp >= 0) & (nsp <= 1)).all()
+    r2 = wxb_ctx.decode_greedy(enc, prompt, sp["eot"], no_speech=sp["no_speech"], sample_len=24, suppress_blank=True,
+                               blank_token=sp["blank"])
+    assert torch.equal(r["tokens"], r2["tokens"]) and torch.equal(r["sum_logprob"], r2["sum_logprob"])
