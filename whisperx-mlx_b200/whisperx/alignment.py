@@ -11,7 +11,7 @@ equal the reference's value for value.
 """
 import math
 from dataclasses import dataclass
-from typing import Iterable, List, Optional, Union
+from typing import Any, Dict, Iterable, List, Optional, Union
 
 import numpy as np
 import pandas as pd
@@ -431,6 +431,20 @@ def _assemble(text, prep, char_segments, ratio, t1, spaced, interpolate_method, 
     return df.to_dict("records")
 
 
+_PINNED: Dict[int, Any] = {}
+
+
+def _pinned_rows(device_index: int, rows: int, V: int) -> torch.Tensor:
+    """[rows, V] f32 view of a grow-only pinned staging buffer; waits for the copy that read it last."""
+    ent = _PINNED.get(device_index)
+    if ent is None or ent[0].numel() < rows * V:
+        ent = [torch.empty(max(rows * V, 1), dtype=torch.float32).pin_memory(), None]
+        _PINNED[device_index] = ent
+    if ent[1] is not None:
+        ent[1].synchronize()
+    return ent[0][: rows * V].view(rows, V)
+
+
 def align_from_emissions(emission_logits: List[np.ndarray], token_lists: List[List[int]], blank_id: int = 0,
                          device_index: int = 0, beam: bool = True):
     """Numeric core of align() for callers that already hold the CTC model's output (host arrays):
@@ -440,12 +454,14 @@ def align_from_emissions(emission_logits: List[np.ndarray], token_lists: List[Li
     ctx = get_context(device_index)
     T = [int(e.shape[0]) for e in emission_logits]
     V = int(emission_logits[0].shape[1])
-    host = torch.empty((sum(T), V), dtype=torch.float32).pin_memory()
+    host = _pinned_rows(device_index, sum(T), V)  # staging kept between calls: page-locking is the expensive part
     off = 0
     for e in emission_logits:
         host[off:off + e.shape[0]] = torch.from_numpy(np.ascontiguousarray(e, dtype=np.float32))
         off += e.shape[0]
     emis = host.to(ctx.device, non_blocking=True)
+    _PINNED[device_index][1] = torch.cuda.Event()
+    _PINNED[device_index][1].record()
     ctx.log_softmax_rows_(emis)
     t_off = np.concatenate([[0], np.cumsum(T)]).astype(np.int32)
     n_off = np.concatenate([[0], np.cumsum([len(t) for t in token_lists])]).astype(np.int32)

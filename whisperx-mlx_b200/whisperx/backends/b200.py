@@ -86,11 +86,20 @@ class B200WhisperBackend(WhisperBackend):
         if len(chunks) > 1:
             offs[1:] = np.cumsum(lens[:-1])
         total = int(lens.sum())
-        host = torch.empty(max(total, 1), dtype=torch.float32).pin_memory()
-        hv = host.numpy()
+        # the pinned staging buffer is kept between calls (page-locking 100+ MB costs tens of ms); the copy that
+        # read it last has completed before it is overwritten
+        if getattr(self, "_staging", None) is None or self._staging.numel() < max(total, 1):
+            self._staging = torch.empty(max(total, 1), dtype=torch.float32).pin_memory()
+            self._staging_done = None
+        if self._staging_done is not None:
+            self._staging_done.synchronize()
+        hv = self._staging.numpy()
         for c, o, l in zip(chunks, offs, lens):
             hv[o:o + l] = np.asarray(c[:l], dtype=np.float32)
-        return host.to(self.device, non_blocking=True), offs, lens
+        dev = self._staging[: max(total, 1)].to(self.device, non_blocking=True)
+        self._staging_done = torch.cuda.Event()
+        self._staging_done.record()
+        return dev, offs, lens
 
     def transcribe_device(self, audio_dev: torch.Tensor, offs: np.ndarray, lens: np.ndarray, batch_size: int,
                           language: str, task: str):
