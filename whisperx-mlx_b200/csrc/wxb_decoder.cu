@@ -67,6 +67,10 @@ constexpr int QRAW_ROWS = GK_MAX + 1;                     // bias row + up to GK
 constexpr int QRAW_BYTES = 2 * QRAW_ROWS * 64 * 4;        // two items in flight
 constexpr int SCRATCH_BYTES = SST_BYTES + QRAW_BYTES;     // attention scratch behind the ring
 constexpr int XA_NST = 6;                    // K/V ring depth
+#ifndef WXB_XA_NS
+#define WXB_XA_NS 2
+#endif
+constexpr int XA_NS = WXB_XA_NS;             // K/V stages per consumer iteration
 constexpr int GV_NST = 6;                    // GEMV ring depth
 constexpr int RING_BYTES = XA_NST * 2 * XA_HALF;
 constexpr size_t MK_SMEM = RING_BYTES + SCRATCH_BYTES + 1024;
@@ -139,6 +143,9 @@ struct MkParams {
   int n_steps;  // consecutive positions decoded by this launch (> 1 only in mode 2)
   int xa_pf;    // L2 prefetch distance of the cross-attention K/V stream in stages (0 = off)
   int skip;     // profiling aid (WXB_DEC_SKIP): 1 cross-attention, 2 GEMV, 4 self-attention, 8 LayerNorm, 16 cross math, 32 cross merge
+  int l2pf;     // L2 staging during the latency-bound phases (l2_stage): 1 self K/V, 2 head of the cross K/V stream, 4 GEMV weights
+  int xa_ns;    // cross-attention stages per consumer iteration (1 or 2)
+  int l2_xa;    // cross K/V stages (28 KB) per CTA staged in L2 ahead of a cross-attention phase
   const DecLayerW* layers;  // device array [L]
   const CUtensorMap* maps;  // device array [6 L + 5]
   const __nv_bfloat16* emb;
@@ -817,8 +824,14 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
         const CUtensorMap* m = tail ? kvmap + 1 : kvmap;
         uint8_t* dst = ring + (size_t)sl * STAGE;
         mbar_arrive_expect_tx(sy.mb(MB_XA_FULL + sl), tail ? 2 * XA_TAIL * 128 : STAGE);
+        const int slab_ld = (skip & 64) ? (x.slab & 3) : x.slab;  // probe: every CTA streams the same 4 slabs (all L2 hits)
+        if (skip & 64) {
+          tma_load_2d(dst, m, sy.mb(MB_XA_FULL + sl), 0, krow0 + slab_ld * T_AUDIO + kk);
+          tma_load_2d(dst + XA_HALF, m, sy.mb(MB_XA_FULL + sl), 0, vrow0 + slab_ld * T_AUDIO + kk);
+        } else {
         tma_load_2d_hint(dst, m, sy.mb(MB_XA_FULL + sl), 0, krow0 + x.slab * T_AUDIO + kk, L2_EVICT_FIRST);
         tma_load_2d_hint(dst + XA_HALF, m, sy.mb(MB_XA_FULL + sl), 0, vrow0 + x.slab * T_AUDIO + kk, L2_EVICT_FIRST);
+        }
       }
       __syncwarp();
       ++issued;
@@ -869,23 +882,88 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
       float m = -INFINITY, lsum = 0.f, o[4][4];
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt) o[mt][0] = o[mt][1] = o[mt][2] = o[mt][3] = 0.f;
-      for (int kk = x.k0; kk < x.k1; kk += XA_KEYS) {
-        const uint32_t sl = consumed % XA_NST, par = (consumed / XA_NST) & 1;
-        const bool act = kk + cw * 16 < x.k1;  // warp-uniform: this warp's 16 keys hold at least one key of the item
-        uint32_t ka[1][4][4], va[1][4][4];
-        mbar_wait(sy.mb(MB_XA_FULL + sl), par);
-        if (act) {
-          const uint32_t kbase = smem_u32(ring + (size_t)sl * STAGE), vbase = kbase + XA_HALF;
-          // all fragments go to registers first, so the slot is released (and refilled) before the math
+      // XA_NS stages per iteration: the QK products, shuffles and exponentials of the stages overlap instead of forming
+      // one dependent chain per stage (the consumer math, not the K/V stream, bounds the phase once K/V hit L2).  K
+      // fragments of all stages are read first; the V fragments of a stage are read right before its PV products (and
+      // only then is the slot released), which keeps the register peak at one stage of V.
+      int kk = x.k0;
+      while (kk < x.k1) {
+        const int ns = (XA_NS == 2 && kk + XA_KEYS < x.k1) ? 2 : 1;  // warp-uniform
+        uint32_t ka[XA_NS][4][4];
+        uint32_t vb[XA_NS], slv[XA_NS];
+        bool act[XA_NS];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) ldsm_x4(ka[0][j], kbase + rowA * 128 + (((2 * j + chA) ^ sw) << 4));
+        for (int n = 0; n < XA_NS; ++n) {
+          act[n] = false;
+          if (n < ns) {
+            const uint32_t sl = consumed % XA_NST, par = (consumed / XA_NST) & 1;
+            act[n] = kk + n * XA_KEYS + cw * 16 < x.k1;  // warp-uniform: this warp's 16 keys hold at least one key of the item
+            mbar_wait(sy.mb(MB_XA_FULL + sl), par);
+            const uint32_t kbase = smem_u32(ring + (size_t)sl * STAGE);
+            vb[n] = kbase + XA_HALF; slv[n] = sl;
+            if (act[n]) {
 #pragma unroll
-          for (int mt = 0; mt < 4; ++mt) ldsm_x4_t(va[0][mt], vbase + rowV * 128 + (((2 * mt + chV) ^ sw) << 4));
+              for (int j = 0; j < 4; ++j) ldsm_x4(ka[n][j], kbase + rowA * 128 + (((2 * j + chA) ^ sw) << 4));
+            }
+            ++consumed;
+          }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(sy.mb(MB_XA_EMPTY + sl));  // this warp is done reading the stage
-        ++consumed;
-        if (act && !(skip & 16)) xa_block<1>(ka, va, qb, kk + cw * 16 + g, x.k1, lane, g, t, m, lsum, o);
+        // scores of the stages (two accumulators per stage), one max reduction for all of them
+        float sc[XA_NS][2];
+#pragma unroll
+        for (int n = 0; n < XA_NS; ++n) {
+          sc[n][0] = sc[n][1] = -INFINITY;
+          if (n < ns && act[n] && !(skip & 16)) {
+            float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+            mma_16816(c0, ka[n][0], qb[0][0], qb[0][1]);
+            mma_16816(c1, ka[n][1], qb[1][0], qb[1][1]);
+            mma_16816(c0, ka[n][2], qb[2][0], qb[2][1]);
+            mma_16816(c1, ka[n][3], qb[3][0], qb[3][1]);
+            const int key0 = kk + n * XA_KEYS + cw * 16 + g;
+            const float s0 = __shfl_sync(0xffffffffu, (c0[0] + c0[1]) + (c1[0] + c1[1]), lane & ~3);
+            const float s1 = __shfl_sync(0xffffffffu, (c0[2] + c0[3]) + (c1[2] + c1[3]), lane & ~3);
+            sc[n][0] = (key0 < x.k1) ? s0 : -INFINITY;
+            sc[n][1] = (key0 + 8 < x.k1) ? s1 : -INFINITY;
+          }
+        }
+        float mx = fmaxf(sc[0][0], sc[0][1]);
+#pragma unroll
+        for (int n = 1; n < XA_NS; ++n) mx = fmaxf(mx, fmaxf(sc[n][0], sc[n][1]));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+        const float mn = fmaxf(m, mx);
+        if (mn > m) {  // warp-uniform
+          const float alpha = __expf(m - mn);  // m = -inf -> 0
+          lsum *= alpha;
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) { o[mt][0] *= alpha; o[mt][1] *= alpha; o[mt][2] *= alpha; o[mt][3] *= alpha; }
+          m = mn;
+        }
+#pragma unroll
+        for (int n = 0; n < XA_NS; ++n) {
+          if (n < ns) {
+            const bool live = act[n] && m > -INFINITY && !(skip & 16);
+            uint32_t va[4][4];
+            if (live) {
+#pragma unroll
+              for (int mt = 0; mt < 4; ++mt) ldsm_x4_t(va[mt], vb[n] + rowV * 128 + (((2 * mt + chV) ^ sw) << 4));
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(sy.mb(MB_XA_EMPTY + slv[n]));  // this warp is done reading the stage
+            if (live) {
+              const float p0 = __expf(sc[n][0] - m), p1 = __expf(sc[n][1] - m);  // -inf -> 0
+              lsum += p0 + p1;  // per-quad partial sum (identical in the 4 lanes of a quad)
+              // B fragment of p: lane (g, t) needs keys 2t, 2t+1 (b0) and 2t+8, 2t+9 (b1): quads 2t and 2t+1
+              const float x0 = __shfl_sync(0xffffffffu, p0, 8 * t), x1 = __shfl_sync(0xffffffffu, p0, 8 * t + 4);
+              const float y0 = __shfl_sync(0xffffffffu, p1, 8 * t), y1 = __shfl_sync(0xffffffffu, p1, 8 * t + 4);
+              const uint32_t pb0 = split_pack(x0, x1, g), pb1 = split_pack(y0, y1, g);
+#pragma unroll
+              for (int mt = 0; mt < 4; ++mt) mma_16816(o[mt], va[mt], pb0, pb1);
+            }
+          }
+        }
+        kk += ns * XA_KEYS;
       }
       // ---- deposit this warp's state; consumer warp (item % 7) merges the 7 states and writes the output ----
       lsum += __shfl_xor_sync(0xffffffffu, lsum, 4);
@@ -1146,6 +1224,81 @@ __device__ __forceinline__ void pre_issue(const MkParams& p, int l, int k, uint8
   }
 }
 
+
+// L2 staging.  Outside the cross-attention phase the step is a chain of latency-bound operators during which HBM idles,
+// and everything the coming operators will stream (weights, cached self K/V, the cross K/V slabs) is known in advance.
+// The last warp of every CTA therefore issues L2-only TMA prefetches at the start of a phase for data that is consumed
+// a few phases later: the consumer's loads then hit L2 (a third of the HBM latency at the same ring depth), and the
+// head of the cross K/V stream is already on chip when the bandwidth-bound phase begins.
+//   self K/V of layer l      rows [0, pos) of this CTA's own units: at fc2 of layer l - 1 (layer 0: at LN1)
+//   cross K/V of layer l     the first l2_xa stages of this CTA's work list: at the out projection (3 phases ahead)
+//   weights of GEMV (l, k)   two phases ahead, boxes dealt round-robin over all CTAs (L2 is shared)
+__device__ __forceinline__ void l2_bulk_prefetch(const void* ptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void l2_stage(const MkParams& p, int l, int k, int pos, const MkSync& sy) {
+  const int lane = threadIdx.x & 31, f = p.l2pf;
+  if (f & 4) {
+    int l2 = l, k2 = -1;
+    if (k == 1 || k == 3 || k == 5 || k == 7) k2 = k + 2;
+    else if (k == 8) k2 = 10;
+    else if (k == 10 && l + 1 < p.L) { l2 = l + 1; k2 = 1; }
+    else if (k == 11) { l2 = 0; k2 = 1; }  // first operator of the next step
+    if (k2 > 0) {
+      const GemvOp o = gemv_op(p, l2, k2);
+      const MkGemv& g = *o.g;
+      const int Ks = g.K / g.gk, nkb = Ks / GV_BK, n_box = g.tiles * nkb;
+      for (int i = lane * sy.nc + sy.cta; i < n_box; i += 32 * sy.nc) {
+        const int tile = i / nkb, kb = i - tile * nkb;
+        tma_prefetch_2d(o.wm, (tile % g.gk) * Ks + kb * GV_BK, (tile / g.gk) * GV_ROWS);
+      }
+    }
+  }
+  if ((f & 1) && pos > 0 && ((k == 10 && l + 1 < p.L) || (k == 0 && l == 0))) {
+    const int ls = (k == 0) ? 0 : l + 1;
+    const int H = p.H, B = p.B, TX = p.TX;
+    const __nv_bfloat16* sk = p.self_kv + (size_t)ls * 2 * B * H * TX * 64;
+    const size_t vofs = (size_t)B * H * TX * 64;
+    const int n_units = B * H, n_warps = sy.nc * MK_WARPS;
+    int n_solo = n_units;
+    const int left = n_units % n_warps;
+    if (left > 0 && left <= sy.nc && n_units > n_warps) n_solo = n_units - left;
+    const int n_rounds = (n_solo + n_warps - 1) / n_warps;
+    // lane = 2 w + kv: K (kv = 0) or V (kv = 1) rows of the unit of warp w, one request per round
+    const int w = lane >> 1, kv = lane & 1;
+    if (w < MK_WARPS) {
+      for (int round = 0; round < n_rounds; ++round) {
+        const int u0 = round * n_warps + sy.cta * MK_WARPS + w;
+        if (u0 < n_solo) l2_bulk_prefetch(sk + kv * vofs + (size_t)u0 * TX * 64, (uint32_t)pos * 128u);
+      }
+    } else if (w == MK_WARPS && n_solo + sy.cta < n_units) {
+      l2_bulk_prefetch(sk + kv * vofs + (size_t)(n_solo + sy.cta) * TX * 64, (uint32_t)pos * 128u);
+    }
+  }
+  if ((f & 2) && k == 3) {
+    const int G = sy.nc, cta = sy.cta;
+    const CUtensorMap* kvmap = p.maps + (size_t)p.L * TM_PER_LAYER + 4;
+    const int n_slabs = p.B * p.H, qw = n_slabs / G, r = n_slabs - qw * G;
+    const int krow0 = (l * 2) * n_slabs * T_AUDIO, vrow0 = (l * 2 + 1) * n_slabs * T_AUDIO;
+    int P = 0, plen = T_AUDIO;
+    if (r > 0) {
+      const int want = (G + r - 1) / r;
+      plen = (T_AUDIO + want - 1) / want;
+      P = (T_AUDIO + plen - 1) / plen;
+    }
+    const int n_items = qw + ((r > 0 && cta < r * P) ? ((r * P - 1 - cta) / G + 1) : 0);
+    int n = 0;
+    for (int it = 0; it < n_items && n < p.l2_xa; ++it) {
+      const XaItem x = xa_item(it, cta, qw, G, P, plen);
+      for (int kk = x.k0; kk < x.k1 && n < p.l2_xa; kk += XA_KEYS, ++n) {
+        if ((n & 15) != (lane >> 1)) continue;  // lane pair (K, V) per stage
+        const CUtensorMap* m = (x.k1 - kk <= XA_TAIL) ? kvmap + 1 : kvmap;
+        tma_prefetch_2d(m, 0, ((lane & 1) ? vrow0 : krow0) + x.slab * T_AUDIO + kk);
+      }
+    }
+  }
+}
+
 // One operator of the step schedule.
 // k: 0 LN1 | 1 QKV | 2 self-attention | 3 out | 4 LN2 | 5 cq | 6 cross-attention | 7 cout | 8 LN3 | 9 fc1 | 10 fc2
 //    11 final LN | 12 logits | 13 (no_speech_prob,) filters + sampling
@@ -1228,6 +1381,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) dec_step_kernel(const __grid_co
     for (int ph = 0; ph < n_ph; ++ph) {
       int l = ph / 11, k = ph - 11 * l;
       if (l >= p.L) { k = 11 + (ph - 11 * p.L); l = p.L - 1; }
+      if (p.l2pf && warp == MK_WARPS - 1) l2_stage(p, l, k, pos, sy);
       run_op<MT>(p, s_layers, l, k, pos, ring, scratch, red, red_i, sy);
       if (ph + 1 < n_ph || s + 1 < p.n_steps) {
         // the operator after the barrier: (l2, k2)
@@ -1286,6 +1440,24 @@ int dec_xa_prefetch() {
     v = e ? atoi(e) : -1;
   }
   return v >= 0 ? v : 0;
+}
+
+// L2 staging plan (MkParams::l2pf / l2_xa); WXB_DEC_L2PF = mask, WXB_DEC_L2XA = cross K/V stages per CTA
+int dec_l2pf() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WXB_DEC_L2PF");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+int dec_l2xa() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WXB_DEC_L2XA");
+    v = e ? atoi(e) : 24;
+  }
+  return v;
 }
 
 // profiling aid only (results become meaningless): WXB_DEC_SKIP bitmask, see MkParams::skip
@@ -1447,6 +1619,8 @@ int launch_steps(wxb_ctx* ctx, const DecBuffers& buf, int mode, int n_steps, con
   MkParams p = {};
   p.B = B; p.d = d; p.H = D.n_text_head; p.L = D.n_text_layer; p.V = D.n_vocab; p.TX = D.n_text_ctx;
   p.mode = mode; p.n_steps = n_steps; p.skip = dec_skip_mask(); p.xa_pf = dec_xa_prefetch();
+  p.l2pf = dec_l2pf(); p.l2_xa = dec_l2xa();
+  { static int ns = -1; if (ns < 0) { const char* e = getenv("WXB_XA_NS"); ns = e ? atoi(e) : 1; } p.xa_ns = ns; }
   p.layers = buf.layers; p.maps = buf.maps;
   p.emb = (const __nv_bfloat16*)wxb_weight(ctx, "dec.emb");
   p.pos_emb = (const float*)wxb_weight(ctx, "dec.pos");
