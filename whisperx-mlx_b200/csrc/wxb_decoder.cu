@@ -51,32 +51,30 @@ constexpr int MAX_LAYERS = 32;
 
 
 // ---- shared-memory plan of the persistent kernel (dynamic, 1024-byte aligned base) -------------------------
-// One region is time-shared by the two TMA rings (GEMV phases and cross-attention never overlap inside a CTA) and
-// the self-attention staging:
+// One region is time-shared by the two TMA rings (GEMV phases and cross-attention never overlap inside a CTA):
 //   GEMV ring   GV_NST stages x (A: 128 weight rows x 64 k bf16 = 16 KB | B: Bp batch rows x 64 k), 128-byte swizzle
-//   KV ring     XA_NST stages x (K: 128 keys x 64 dims bf16 = 16 KB | V: 16 KB), 128-byte swizzle
-// followed by regions that belong to the cross-attention phase alone (zeroed once at kernel start, never touched by
-// another phase): two P operand tiles (8 rows x 128 keys bf16, only rows 0 / 1 are ever written; the UMMA descriptor
-// maps all 16 row groups of the M = 128 operand onto these 8 rows), two q operand tiles (16 rows x 64 dims), the raw
-// q rows of two items and a small float scratch.
+//   KV ring     XA_NST stages x (K: 112 keys x 64 dims bf16 = 14 KB | V: 14 KB), 128-byte swizzle
+// followed by the attention scratch (warp states of two items, raw q rows of two items).
 constexpr int GV_ROWS = 128;                 // weight rows per tile = UMMA M
 constexpr int GV_BK = 64;                    // k per stage (one 128-byte swizzle row)
 constexpr int GV_A_BYTES = GV_ROWS * GV_BK * 2;
-constexpr int XA_KEYS = 128;                 // keys per stage = UMMA M of the score product
+constexpr int XA_CW = 7;                     // cross-attention consumer warps (hardware warps 1 .. 7); warp 0 produces
+constexpr int XA_KEYS = 16 * XA_CW;          // keys per stage: one m16 tile per consumer warp
 constexpr int XA_HALF = XA_KEYS * 128;       // bytes of K (or V) per stage
-constexpr int XA_TAIL = 96;                  // rows of the short TMA box used when <= 96 keys of an item remain
-constexpr int XA_NST = 6;                    // K/V ring depth
-constexpr int GV_NST = 6;                    // GEMV ring depth
-constexpr int RING_BYTES = XA_NST * 2 * XA_HALF;
-constexpr int XP_BYTES = 2 * 2048;                        // P operand tiles [2]: two 64-key chunks of 8 rows x 128 B each
-constexpr int XQ_BYTES = 2 * 16 * 128;                    // q operand tiles of two items
+constexpr int XA_TAIL = 48;                  // rows of the short TMA box used when <= 48 keys of an item remain
+constexpr int SST_BYTES = 3712;                           // [2 item parities][7 warps][66] floats, padded
 constexpr int QRAW_ROWS = GK_MAX + 1;                     // bias row + up to GK_MAX split-K partial rows of q
 constexpr int QRAW_BYTES = 2 * QRAW_ROWS * 64 * 4;        // two items in flight
-constexpr int FSCR_BYTES = 2304;                          // float scratch (self-attention merge: 8 x 66, cross-attention exchange)
-constexpr int SCRATCH_BYTES = FSCR_BYTES + QRAW_BYTES;
-constexpr size_t MK_SMEM = RING_BYTES + XP_BYTES + XQ_BYTES + SCRATCH_BYTES + 1024;
+constexpr int SCRATCH_BYTES = SST_BYTES + QRAW_BYTES;     // attention scratch behind the ring
+constexpr int XA_NST = 6;                    // K/V ring depth
+#ifndef WXB_XA_NS
+#define WXB_XA_NS 2
+#endif
+constexpr int XA_NS = WXB_XA_NS;             // K/V stages per consumer iteration
+constexpr int GV_NST = 6;                    // GEMV ring depth
+constexpr int RING_BYTES = XA_NST * 2 * XA_HALF;
+constexpr size_t MK_SMEM = RING_BYTES + SCRATCH_BYTES + 1024;
 static_assert(GV_NST * (GV_A_BYTES + 64 * GV_BK * 2) <= RING_BYTES, "GEMV ring must fit the shared region");
-static_assert(MK_SMEM <= 227 * 1024 - 8 * 1024, "dynamic + static shared memory must fit an SM");
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -177,30 +175,23 @@ struct MkParams {
 // holds its own consistent copy.
 enum {
   MB_GV_FULL = 0,    // [6] TMA -> MMA
-  MB_GV_EMPTY = 6,   // [6] MMA (tcgen05.commit) -> TMA
+  MB_GV_EMPTY = 6,   // [6] MMA (tcgen05.commit / 8 warp arrivals) -> TMA
   MB_ACC_FULL = 12,  // [1] MMA -> epilogue
-  MB_XA_FULL = 13,   // [6] TMA -> MMA issuer (K and V of a stage landed)
-  MB_XA_EMPTY = 19,  // [6] PV product of the stage complete (tcgen05.commit) -> producer
-  MB_S_FULL = 25,    // [2] score product complete -> softmax warps
-  MB_S_FREE = 27,    // [2] 4 softmax warps have read the scores -> MMA issuer
-  MB_P_FULL = 29,    // [2] 4 softmax warps have written P -> MMA issuer
-  MB_P_FREE = 31,    // [2] PV product complete -> softmax warps (P tile reusable, O up to date)
-  MB_Q_FULL = 33,    // [2] raw q rows of an item landed (cp.async arrive-on of the 32 producer lanes)
-  MB_Q_FREE = 35,    // [2] the q-tile warp has consumed the raw rows
-  MB_QT_FULL = 37,   // [2] q operand tile of an item written -> MMA issuer
-  MB_QT_FREE = 39,   // [2] last score product of the item complete -> q-tile warp
-  MB_O_FULL = 41,    // [2] last PV product of an item complete -> output warp
-  MB_O_FREE = 43,    // [2] output warp has read the accumulator -> MMA issuer
-  MB_COUNT = 45
+  MB_XA_FULL = 13,   // [6] TMA -> attention warps
+  MB_XA_EMPTY = 19,  // [6] 7 consumer-warp arrivals -> producer
+  MB_ST_FULL = 25,   // [2] 7 warp states of an item deposited -> merging warp
+  MB_ST_FREE = 27,   // [2] merging warp -> writers of the item after next
+  MB_Q_FULL = 29,    // [2] raw q rows of an item landed (cp.async arrive-on of the 32 producer lanes)
+  MB_Q_FREE = 31,    // [2] 7 consumer warps have built their q fragments
+  MB_COUNT = 33
 };
-static_assert(XA_NST <= 6 && GV_NST <= 6, "barrier slots are sized for rings of at most 6 stages");
 struct MkSync {
   uint32_t bars;       // shared-memory address of the barrier array
   uint32_t gv_count;   // GEMV stages issued so far (slot = count % GV_NST, parity = (count / GV_NST) & 1)
   uint32_t acc_count;  // accumulator hand-offs so far
   uint32_t xa_count;   // KV stages issued so far
   uint32_t xa_items;   // cross-attention work items finished so far
-  uint32_t tmem;       // TMEM base address (256 fp32 columns x 128 lanes): GEMV accumulator / O[0] | O[1] | S[0] | S[1]
+  uint32_t tmem;       // TMEM base address (64 fp32 columns x 128 lanes)
   int pre;             // thread 0: stages of the coming operator already requested before the barrier wait (grid_sync)
   int cta, nc;         // this CTA's index within its group, CTAs per group
   __device__ __forceinline__ uint32_t mb(int slot) const { return bars + 8u * (uint32_t)slot; }
@@ -341,22 +332,28 @@ __device__ __forceinline__ void gemv_phase(const MkParams& p, const MkGemv& g, c
   for (int tile = sy.cta; tile < g.tiles; tile += sy.nc) {
     const int ks = tile % g.gk, rb = tile / g.gk;
     const int k0 = ks * Ks, row0 = rb * GV_ROWS;
-    if (warp == 0 && lane == 0) {
+    // Producer and issuer warps run converged (every lane polls the barriers, operands are warp-uniform) and ONE
+    // elected lane issues: under a divergent `lane == 0` branch ptxas wraps every TMA / tcgen05 instruction in an
+    // ELECT + 5 x R2UR + branch sequence (~14 instructions each), which is what the issuing thread's time went into.
+    if (warp == 0) {
       // ---- TMA producer: the whole K-slice is requested as fast as ring slots free up ----
       uint32_t c = sy.gv_count;
       const int pre = (tile == sy.cta) ? sy.pre : 0;  // weight halves of the first stages were requested before the barrier wait
       for (int kb = 0; kb < nkb; ++kb, ++c) {
         const uint32_t slot = c % GV_NST, par = (c / GV_NST) & 1;
         uint8_t* sa = ring + slot * STAGE;
-        if (kb >= pre) {
-          mbar_wait(sy.mb(MB_GV_EMPTY + slot), par ^ 1);
-          mbar_arrive_expect_tx(sy.mb(MB_GV_FULL + slot), STAGE);
-          tma_load_2d(sa, wmap, sy.mb(MB_GV_FULL + slot), k0 + kb * GV_BK, row0);
+        if (kb >= pre) mbar_wait(sy.mb(MB_GV_EMPTY + slot), par ^ 1);
+        if (elect_one()) {
+          if (kb >= pre) {
+            mbar_arrive_expect_tx(sy.mb(MB_GV_FULL + slot), STAGE);
+            tma_load_2d(sa, wmap, sy.mb(MB_GV_FULL + slot), k0 + kb * GV_BK, row0);
+          }
+          tma_load_2d(sa + GV_A_BYTES, amap, sy.mb(MB_GV_FULL + slot), k0 + kb * GV_BK, 0);
         }
-        tma_load_2d(sa + GV_A_BYTES, amap, sy.mb(MB_GV_FULL + slot), k0 + kb * GV_BK, 0);
+        __syncwarp();
       }
       sy.pre = 0;
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
       // ---- MMA issuer ----
       const uint32_t idesc = make_idesc_bf16(GV_ROWS, Bp);
       uint32_t c = sy.gv_count;
@@ -367,12 +364,15 @@ __device__ __forceinline__ void gemv_phase(const MkParams& p, const MkGemv& g, c
         const uint32_t sa = smem_u32(ring + slot * STAGE);
         const uint64_t adesc = make_sw128_desc(sa);
         const uint64_t bdesc = make_sw128_desc(sa + GV_A_BYTES);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < GV_BK / 16; ++k)  // +32 bytes along K inside the swizzle row = +2 in the address field
-          tc_mma_bf16(sy.tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-        tc_commit(sy.mb(MB_GV_EMPTY + slot));
+          for (int k = 0; k < GV_BK / 16; ++k)  // +32 bytes along K inside the swizzle row = +2 in the address field
+            tc_mma_bf16(sy.tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          tc_commit(sy.mb(MB_GV_EMPTY + slot));
+          if (kb == nkb - 1) tc_commit(sy.mb(MB_ACC_FULL));
+        }
+        __syncwarp();
       }
-      tc_commit(sy.mb(MB_ACC_FULL));
     }
     sy.gv_count += nkb;
     __syncwarp();
@@ -676,24 +676,19 @@ __device__ __forceinline__ void self_attn_phase(const MkParams& p, int l, const 
   }
 }
 
-// Cross-attention over the 1500 encoder positions on the 5th-gen tensor cores.  n_slabs = B * H (sequence, head)
-// slabs of 192 KB K + 192 KB V.  Every CTA streams floor(n_slabs / G) whole slabs; the n_slabs % G remaining slabs
-// are cut into pieces (merged by the last-arriving CTA) so that the tail is spread over all CTAs as well.
+// Cross-attention over the 1500 encoder positions.  n_slabs = B * H (sequence, head) slabs of 192 KB K + 192 KB V.
+// Every CTA streams floor(n_slabs / G) whole slabs; the n_slabs % G remaining slabs are cut into pieces so that
+// the tail is spread over all CTAs as well.  Warp 0 is a dedicated producer: K/V do not depend on q, so it keeps
+// XA_NST stages of 112 keys (14 KB K + 14 KB V, 2-D TMA boxes with the 128-byte swizzle, L2 evict-first, completing
+// on an mbarrier) in flight ACROSS work items and, for shallow rings, pulls the stages behind them into L2 with
+// TMA prefetches; it also stages the raw q rows of upcoming items with cp.async.  The HBM stream never drains
+// while a slab's states are merged or the next q is assembled.
 //
-// The decode step has ONE query per (sequence, head), so the products are skinny; what matters is that a key costs
-// a fraction of an instruction per warp instead of ~9 (the mma.sync formulation this replaces was bound by the
-// consumer warps' dependent instruction chains at ~80 us per layer, measured with all K/V served from L2):
-//   S[128 keys, 16]  = K_tile[128, 64] Qt[16, 64]^T     tcgen05.mma M128 N16 K64; A = the K stage exactly as TMA wrote
-//                      it (K-major, 128-byte swizzle); Qt row 0 = bf16 hi part of the scaled q, row 1 = its lo part
-//                      (q - hi), rows 2..15 zero, so S[:,0] + S[:,1] carries ~16 mantissa bits of q
-//   softmax          one key per thread (4 warps = 128 TMEM lanes), tile maximum through shared memory; the reference
-//                      offset m only moves when the tile maximum exceeds it by more than 8 (then O is rescaled in TMEM)
-//   O[128, 64]      += P[128, 128 keys] V_tile[128 keys, 64]   M128 N64 K128; A = P tile in shared memory whose row 0 /
-//                      row 1 hold the hi / lo parts of p (rows 2..127 stay zero), B = the V stage as TMA wrote it, read
-//                      as an MN-major operand (keys are the K dimension).  O = row 0 + row 1 of the accumulator.
-// Warp roles: 0 TMA producer (K/V stages across work items, raw q rows of upcoming items), 1 MMA issuer, 2 q-tile
-// builder, 4..7 softmax (warp 4 also rescales / reads out O and merges remainder pieces).  Nothing meets at a block
-// barrier inside the phase.
+// Math on the (otherwise idle) legacy tensor pipe, one query per head: consumer warp w owns keys 16 w .. 16 w + 15 of a stage.
+//   S = K q      mma.m16n8k16: A = K rows (ldmatrix), B column 0 = bf16 hi part of the scaled q, column 1 = its
+//                bf16 lo part (q - hi), so S = c0 + c1 carries ~16 mantissa bits of q; columns 2-7 are zero.
+//   softmax      online over 16-key blocks (scores replicated per quad, max by shuffles over the quads).
+//   O += V^T p   mma.m16n8k16: A = V^T (ldmatrix.trans, 16 dims x 16 keys), B column 0 / 1 = hi / lo part of p.
 struct XaItem {
   int slab, k0, k1, piece, lj;
 };
@@ -708,259 +703,314 @@ __device__ __forceinline__ XaItem xa_item(int it, int cta, int qw, int G, int P,
   }
   return x;
 }
-// TMEM columns of the cross-attention phase (the GEMV accumulator aliases O[0]; the phases never overlap)
-constexpr uint32_t XT_O = 0, XT_S = 128;
+// bf16 hi / lo split of two floats, packed for an MMA B fragment: sel 0 -> (hi(x), hi(y)), 1 -> (lo(x), lo(y)), else 0.
+// Branch-free (sel differs between the lanes of a warp).
+__device__ __forceinline__ uint32_t split_pack(float x, float y, int sel) {
+  const uint32_t hi = pack_bf16(x, y);  // x in the low half
+  const float hx = __uint_as_float(hi << 16), hy = __uint_as_float(hi & 0xffff0000u);
+  const uint32_t lo = pack_bf16(x - hx, y - hy);
+  return sel == 0 ? hi : (sel == 1 ? lo : 0u);
+}
 
+// One online-softmax update over NS consecutive stages (NS x 16 keys of this warp): the QK products of all
+// blocks are issued back to back (two accumulators per block), one max reduction serves all blocks, and the PV
+// products follow, so the long HMMA / shuffle latencies overlap across blocks instead of adding up per stage.
+template <int NS>
+__device__ __forceinline__ void xa_block(const uint32_t (*ka)[4][4], const uint32_t (*va)[4][4], const uint32_t (*qb)[2],
+                                         int key0, int k1, int lane, int g, int t, float& m, float& lsum, float (*o)[4]) {
+  float s[NS][2];
+#pragma unroll
+  for (int n = 0; n < NS; ++n) {
+    float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+    mma_16816(c0, ka[n][0], qb[0][0], qb[0][1]);
+    mma_16816(c1, ka[n][1], qb[1][0], qb[1][1]);
+    mma_16816(c0, ka[n][2], qb[2][0], qb[2][1]);
+    mma_16816(c1, ka[n][3], qb[3][0], qb[3][1]);
+    s[n][0] = __shfl_sync(0xffffffffu, (c0[0] + c0[1]) + (c1[0] + c1[1]), lane & ~3);
+    s[n][1] = __shfl_sync(0xffffffffu, (c0[2] + c0[3]) + (c1[2] + c1[3]), lane & ~3);
+    if (key0 + n * XA_KEYS >= k1) s[n][0] = -INFINITY;
+    if (key0 + n * XA_KEYS + 8 >= k1) s[n][1] = -INFINITY;
+  }
+  float mx = fmaxf(s[0][0], s[0][1]);
+#pragma unroll
+  for (int n = 1; n < NS; ++n) mx = fmaxf(mx, fmaxf(s[n][0], s[n][1]));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+  const float mn = fmaxf(m, mx);
+  if (mn == -INFINITY) return;  // every key of the blocks is outside the range (warp-uniform)
+  if (mn > m) {                 // warp-uniform
+    const float alpha = __expf(m - mn);  // m = -inf -> 0
+    lsum *= alpha;
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) { o[mt][0] *= alpha; o[mt][1] *= alpha; o[mt][2] *= alpha; o[mt][3] *= alpha; }
+    m = mn;
+  }
+#pragma unroll
+  for (int n = 0; n < NS; ++n) {
+    const float p0 = __expf(s[n][0] - m), p1 = __expf(s[n][1] - m);  // -inf -> 0
+    lsum += p0 + p1;  // per-quad partial sum (identical in the 4 lanes of a quad)
+    // B fragment of p: lane (g, t) needs keys 2t, 2t+1 (b0) and 2t+8, 2t+9 (b1): quads 2t and 2t+1
+    const float x0 = __shfl_sync(0xffffffffu, p0, 8 * t), x1 = __shfl_sync(0xffffffffu, p0, 8 * t + 4);
+    const float y0 = __shfl_sync(0xffffffffu, p1, 8 * t), y1 = __shfl_sync(0xffffffffu, p1, 8 * t + 4);
+    const uint32_t pb0 = split_pack(x0, x1, g), pb1 = split_pack(y0, y1, g);
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) mma_16816(o[mt], va[n][mt], pb0, pb1);
+  }
+}
+
+// The warps never meet at a block barrier inside the phase: the producer warp stages the raw q rows (bias + split-K
+// partials of the cq GEMV) of the next items, every consumer warp sums them for itself, deposits its (m, l, O) state of
+// a finished item in a double-buffered shared-memory slot and moves straight on; consumer warp (item % 7) merges the
+// 7 states once all have arrived (mbarrier) and writes the output.
 __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const float* __restrict__ cq_b, uint8_t* ring,
                                                  float* scratch, MkSync& sy) {
   constexpr uint32_t STAGE = 2 * XA_HALF;
-  uint8_t* xp = ring + RING_BYTES;                       // P operand tile
-  uint8_t* xq = xp + XP_BYTES;                           // q operand tiles [2]
-  float* fscr = scratch;                                 // [2][4] tile maxima | [2][4] row sums | [64] O hand-off
-  float* qraw = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(scratch) + FSCR_BYTES);  // [2 item parities][QRAW_ROWS][64]
+  float* sst = scratch;                                                                          // [2 item parities][7 warps][66]: m, l, O[64]
+  float* qraw = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(scratch) + SST_BYTES);      // [2 item parities][QRAW_ROWS][64]
   const float scale = p.scale;
+  const int skip = p.skip, xa_pf = p.xa_pf;
   const float* __restrict__ part_q = p.part;
   __nv_bfloat16* __restrict__ att = p.att;
   float* __restrict__ apart = p.apart;
   int* __restrict__ ticket = p.ticket;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int B = p.B, H = p.H, d = p.d, G = sy.nc, cta = sy.cta, gk = p.g_dd.gk;
-  const __nv_bfloat16* __restrict__ kvbase = p.cross_kv;
+  const CUtensorMap* kvmap = p.maps + (size_t)p.L * TM_PER_LAYER + 4;  // 112-key boxes; kvmap + 1: 48-key boxes
   const int n_slabs = B * H, qw = n_slabs / G, r = n_slabs - qw * G;
   const int krow0 = (l * 2) * n_slabs * T_AUDIO, vrow0 = (l * 2 + 1) * n_slabs * T_AUDIO;  // rows of the [rows, 64] K/V tensor
   int P = 0, plen = T_AUDIO;
   if (r > 0) {
     const int want = (G + r - 1) / r;
-    plen = ((T_AUDIO + want - 1) / want + 7) & ~7;  // piece starts stay multiples of 8 keys (the swizzle period)
+    plen = (T_AUDIO + want - 1) / want;
     P = (T_AUDIO + plen - 1) / plen;
   }
   const int n_items = qw + ((r > 0 && cta < r * P) ? ((r * P - 1 - cta) / G + 1) : 0);
   if (warp == 0) {
-    // ------------------------------- TMA producer -------------------------------
+    // ------------------------------- producer warp -------------------------------
+    int it = 0, kk = 0, pit = 0, pkk = 0, ahead = 0;  // load cursor, L2-prefetch cursor, distance between them in stages
+    XaItem x = {}, px = {};
+    if (n_items > 0) { x = xa_item(0, cta, qw, G, P, plen); kk = x.k0; px = x; pkk = kk; }
     uint32_t issued = sy.xa_count;
-    for (int it = 0; it < n_items; ++it) {
-      const XaItem x = xa_item(it, cta, qw, G, P, plen);
-      {
-        // raw q rows of the item (row gk = bias, rows 0 .. gk-1 = split-K partials of the cq GEMV), 2 rows per pass
-        const uint32_t gi = sy.xa_items + (uint32_t)it, qpar = gi & 1;
-        mbar_wait(sy.mb(MB_Q_FREE + qpar), ((gi >> 1) & 1) ^ 1);  // the rows of item gi - 2 have been consumed
-        float* dst = qraw + qpar * (QRAW_ROWS * 64);
-        const int b = x.slab / H, h = x.slab - b * H;
-        const int half = lane >> 4, l16 = lane & 15;
-        for (int r0 = 0; r0 <= gk; r0 += 2) {
-          const int row = r0 + half;
-          if (row <= gk) {
-            const float* src = (row == gk) ? (cq_b + h * 64) : (part_q + ((size_t)row * B + b) * d + h * 64);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + row * 64 + l16 * 4)), "l"(src + l16 * 4) : "memory");
+    auto stage_q = [&](int qi) {
+      // raw q rows of item qi (row gk = bias, rows 0 .. gk-1 = split-K partials of the cq GEMV), 2 rows per pass
+      const XaItem xq = xa_item(qi, cta, qw, G, P, plen);
+      const uint32_t gi = sy.xa_items + (uint32_t)qi, qpar = gi & 1;
+      mbar_wait(sy.mb(MB_Q_FREE + qpar), ((gi >> 1) & 1) ^ 1);  // the consumers have used the rows of item gi - 2
+      float* dst = qraw + qpar * (QRAW_ROWS * 64);
+      const int b = xq.slab / H, h = xq.slab - b * H;
+      const int half = lane >> 4, l16 = lane & 15;
+      for (int r0 = 0; r0 <= gk; r0 += 2) {
+        const int row = r0 + half;
+        if (row <= gk) {
+          const float* src = (row == gk) ? (cq_b + h * 64) : (part_q + ((size_t)row * B + b) * d + h * 64);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + row * 64 + l16 * 4)), "l"(src + l16 * 4) : "memory");
+        }
+      }
+      cp_async_mbar_arrive(sy.mb(MB_Q_FULL + qpar));
+    };
+    while (it < n_items) {
+      if (xa_pf > 0) {
+        while (pit < n_items && ahead <= xa_pf) {
+          if (ahead >= XA_NST && lane == 0) {
+            const CUtensorMap* m = (px.k1 - pkk <= XA_TAIL) ? kvmap + 1 : kvmap;
+            tma_prefetch_2d(m, 0, krow0 + px.slab * T_AUDIO + pkk);
+            tma_prefetch_2d(m, 0, vrow0 + px.slab * T_AUDIO + pkk);
+          }
+          ++ahead;
+          pkk += XA_KEYS;
+          if (pkk >= px.k1) {
+            ++pit;
+            if (pit < n_items) { px = xa_item(pit, cta, qw, G, P, plen); pkk = px.k0; }
           }
         }
-        cp_async_mbar_arrive(sy.mb(MB_Q_FULL + qpar));
       }
-      for (int kk = x.k0; kk < x.k1; kk += XA_KEYS, ++issued) {
-        if (lane == 0 && (int)(issued - sy.xa_count) >= sy.pre) {  // the first sy.pre stages were requested before the barrier wait
-          const uint32_t sl = issued % XA_NST, par = (issued / XA_NST) & 1;
-          mbar_wait(sy.mb(MB_XA_EMPTY + sl), par ^ 1);
-          // K/V are stored pre-swizzled (see wxb_gemm.cu, kv_mode), so a stage is two contiguous runs of the slab and
-          // plain bulk copies land exactly the bytes a 128-byte-swizzled tensor copy would, without the tensor path's
-          // 128-byte-row granularity (measured: ~58 GB/s per SM, which capped this phase at ~51 us)
-          const int rows = min(XA_KEYS, x.k1 - kk);
-          uint8_t* dst = ring + (size_t)sl * STAGE;
-          const int src_slab = (p.skip & 64) ? (x.slab & 3) : x.slab;  // probe: every CTA streams the same 4 slabs (all L2 hits)
-          mbar_arrive_expect_tx(sy.mb(MB_XA_FULL + sl), (uint32_t)rows * 256u);
-          bulk_load_1d_hint(dst, kvbase + ((size_t)krow0 + (size_t)src_slab * T_AUDIO + kk) * 64, (uint32_t)rows * 128u, sy.mb(MB_XA_FULL + sl), L2_EVICT_FIRST);
-          bulk_load_1d_hint(dst + XA_HALF, kvbase + ((size_t)vrow0 + (size_t)src_slab * T_AUDIO + kk) * 64, (uint32_t)rows * 128u, sy.mb(MB_XA_FULL + sl), L2_EVICT_FIRST);
+      if (kk == x.k0) stage_q(it);  // first stage of an item: its raw q rows
+      if (lane == 0 && (int)(issued - sy.xa_count) >= sy.pre) {  // the first sy.pre stages were requested before the barrier wait
+        const uint32_t sl = issued % XA_NST, par = (issued / XA_NST) & 1;
+        mbar_wait(sy.mb(MB_XA_EMPTY + sl), par ^ 1);
+        const bool tail = (x.k1 - kk <= XA_TAIL);  // keys past the item (or the tensor: zero-filled) are masked by the consumer
+        const CUtensorMap* m = tail ? kvmap + 1 : kvmap;
+        uint8_t* dst = ring + (size_t)sl * STAGE;
+        mbar_arrive_expect_tx(sy.mb(MB_XA_FULL + sl), tail ? 2 * XA_TAIL * 128 : STAGE);
+        const int slab_ld = (skip & 64) ? (x.slab & 3) : x.slab;  // probe: every CTA streams the same 4 slabs (all L2 hits)
+        if (skip & 64) {
+          tma_load_2d(dst, m, sy.mb(MB_XA_FULL + sl), 0, krow0 + slab_ld * T_AUDIO + kk);
+          tma_load_2d(dst + XA_HALF, m, sy.mb(MB_XA_FULL + sl), 0, vrow0 + slab_ld * T_AUDIO + kk);
+        } else {
+        tma_load_2d_hint(dst, m, sy.mb(MB_XA_FULL + sl), 0, krow0 + x.slab * T_AUDIO + kk, L2_EVICT_FIRST);
+        tma_load_2d_hint(dst + XA_HALF, m, sy.mb(MB_XA_FULL + sl), 0, vrow0 + x.slab * T_AUDIO + kk, L2_EVICT_FIRST);
         }
-        __syncwarp();
+      }
+      __syncwarp();
+      ++issued;
+      --ahead;
+      kk += XA_KEYS;
+      if (kk >= x.k1) {
+        ++it;
+        if (it < n_items) { x = xa_item(it, cta, qw, G, P, plen); kk = x.k0; }
       }
     }
     sy.pre = 0;
-  } else if (warp == 1) {
-    // ------------------------------- MMA issuer -------------------------------
-    // The whole warp runs this loop converged (every lane polls the barriers, all operands are warp-uniform) and one
-    // elected lane issues: with a divergent `if (lane == 0)` around the loop every tcgen05 instruction cost an
-    // ELECT / 5 x R2UR / branch sequence and the issuing thread, at ~1900 cycles per tile, bounded the whole phase.
-    {
-      const uint32_t idesc_s = make_idesc_bf16(128, 16);
-      const uint32_t idesc_o = make_idesc_bf16(128, 64) | (1u << 16);  // B (= V) is MN-major
-      const uint32_t ring_a = smem_u32(ring), xp_a = smem_u32(xp), xq_a = smem_u32(xq);
-      const int skip = p.skip;
-      // Two cursors over the CTA's tiles: the score product runs QK_AHEAD tiles ahead of the PV product.  The S buffer
-      // of tile t + 2 is free as soon as the softmax warps have READ the scores of tile t (early in their pass), so its
-      // score product executes under that pass instead of queueing behind PV(t), which can only start when the pass ends.
-      struct Cur { int it, tl, ntile; uint32_t g; };
-      auto tiles_of = [&](int it) { const XaItem x = xa_item(it, cta, qw, G, P, plen); return (x.k1 - x.k0 + XA_KEYS - 1) / XA_KEYS; };
-      Cur q = {0, 0, n_items > 0 ? tiles_of(0) : 0, sy.xa_count}, v = q;
-      auto issue_qk = [&]() {
-        const uint32_t gi = sy.xa_items + (uint32_t)q.it, sl = q.g % XA_NST;
-        if (q.tl == 0) mbar_wait(sy.mb(MB_QT_FULL + (gi & 1)), (gi >> 1) & 1);
-        mbar_wait(sy.mb(MB_XA_FULL + sl), (q.g / XA_NST) & 1);
-        mbar_wait(sy.mb(MB_S_FREE + (q.g & 1)), ((q.g >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint64_t kdesc = make_sw128_desc(ring_a + sl * STAGE), qdesc = make_sw128_desc(xq_a + (gi & 1) * 2048);
-        if (elect_one()) {
-          if (!(skip & 32)) {
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              tc_mma_bf16(sy.tmem + XT_S + 16u * (q.g & 1), kdesc + (uint64_t)(ks * 2), qdesc + (uint64_t)(ks * 2), idesc_s, ks != 0);
-          }
-          tc_commit(sy.mb(MB_S_FULL + (q.g & 1)));
-          if (q.tl == q.ntile - 1) tc_commit(sy.mb(MB_QT_FREE + (gi & 1)));
-        }
-        __syncwarp();
-        ++q.g;
-        if (++q.tl == q.ntile) { ++q.it; q.tl = 0; q.ntile = q.it < n_items ? tiles_of(q.it) : 0; }
-      };
-      auto issue_pv = [&]() {
-        const uint32_t gi = sy.xa_items + (uint32_t)v.it, sl = v.g % XA_NST;
-        const bool first = v.tl == 0, last = v.tl == v.ntile - 1;
-        mbar_wait(sy.mb(MB_P_FULL + (v.g & 1)), (v.g >> 1) & 1);
-        if (first) mbar_wait(sy.mb(MB_O_FREE + (gi & 1)), ((gi >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint64_t vdesc = make_sw128_desc(ring_a + sl * STAGE + XA_HALF);
-        const uint32_t od = sy.tmem + XT_O + 64u * (gi & 1);
-        const uint64_t pdesc = (skip & 256) ? make_sw128_desc_sbo(ring_a, 1024) : make_sw128_desc_sbo(xp_a + (v.g & 1) * 2048, 0);  // stride 0 between 8-row groups: rows r and r % 8 coincide
-        const uint32_t idesc_o2 = (skip & 128) ? make_idesc_bf16(128, 64) : idesc_o;  // probes (wrong results): K-major B / distinct A row groups
-        if (elect_one()) {
-          if (!(skip & 16)) {
-#pragma unroll
-            for (int ks = 0; ks < XA_KEYS / 16; ++ks)  // P: 64-key chunks 1 KB apart, +32 B per step inside; V: 16 keys = 2 KB per step
-              tc_mma_bf16(((skip & 512) && (ks & 1)) ? sy.tmem + 160u : od, pdesc + (uint64_t)((ks >> 2) * (((skip & 256) ? 16384 : 1024) >> 4) + (ks & 3) * 2), vdesc + (uint64_t)(ks * (2048 >> 4)), idesc_o2,
-                          !(first && ks == 0));
-          }
-          tc_commit(sy.mb(MB_XA_EMPTY + sl));
-          tc_commit(sy.mb(MB_P_FREE + (v.g & 1)));
-          if (last) tc_commit(sy.mb(MB_O_FULL + (gi & 1)));
-        }
-        __syncwarp();
-        ++v.g;
-        if (++v.tl == v.ntile) { ++v.it; v.tl = 0; v.ntile = v.it < n_items ? tiles_of(v.it) : 0; }
-      };
-      constexpr int QK_AHEAD = 2;
-      for (int i = 0; i < QK_AHEAD && q.it < n_items; ++i) issue_qk();
-      while (v.it < n_items) {
-        if (q.it < n_items) issue_qk();
-        issue_pv();
-      }
-    }
-  } else if (warp == 2) {
-    // ------------------------------- q operand tiles -------------------------------
-    for (int it = 0; it < n_items; ++it) {
-      const uint32_t gi = sy.xa_items + (uint32_t)it, ipar = gi & 1, iph = (gi >> 1) & 1;
-      mbar_wait(sy.mb(MB_Q_FULL + ipar), iph);
-      // scaled q = (bias + split-K partials in slice order) * scale; lane holds dims lane and lane + 32
-      const float* qr = qraw + ipar * (QRAW_ROWS * 64);
-      float a0 = qr[gk * 64 + lane], a1 = qr[gk * 64 + lane + 32];
-      for (int ks = 0; ks < gk; ++ks) { a0 += qr[ks * 64 + lane]; a1 += qr[ks * 64 + lane + 32]; }
-      a0 *= scale; a1 *= scale;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(sy.mb(MB_Q_FREE + ipar));
-      const __nv_bfloat16 h0 = __float2bfloat16_rn(a0), h1 = __float2bfloat16_rn(a1);
-      const __nv_bfloat16 l0 = __float2bfloat16_rn(a0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(a1 - __bfloat162float(h1));
-      mbar_wait(sy.mb(MB_QT_FREE + ipar), iph ^ 1);  // the score products of item gi - 2 are complete
-      // K-major 128-byte swizzle: (row r, dim j) at r * 128 + ((j / 8) ^ r) * 16 + (j % 8) * 2
-      uint8_t* qt = xq + ipar * 2048;
-      const int j0 = lane, j1 = lane + 32;
-      *reinterpret_cast<__nv_bfloat16*>(qt + ((j0 >> 3) << 4) + (j0 & 7) * 2) = h0;
-      *reinterpret_cast<__nv_bfloat16*>(qt + ((j1 >> 3) << 4) + (j1 & 7) * 2) = h1;
-      *reinterpret_cast<__nv_bfloat16*>(qt + 128 + (((j0 >> 3) ^ 1) << 4) + (j0 & 7) * 2) = l0;
-      *reinterpret_cast<__nv_bfloat16*>(qt + 128 + (((j1 >> 3) ^ 1) << 4) + (j1 & 7) * 2) = l1;
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(sy.mb(MB_QT_FULL + ipar));
-    }
-  } else if (warp >= 4) {
-    // ------------------------------- softmax warps: one key per thread -------------------------------
-    const int q4 = warp - 4;                       // TMEM lane quarter of this warp
-    const int kl = q4 * 32 + lane;                 // key within a tile = TMEM lane
-    const uint32_t tl_addr = sy.tmem + ((uint32_t)(q4 * 32) << 16);
-    // P tile (K-major, 128-byte swizzle, 64-key chunks 1 KB apart): (row r, key k) at chunk + r * 128 + (((k % 64) / 8) ^ r) * 16 + (k % 8) * 2
-    uint8_t* prow0 = xp + (kl >> 6) * 1024 + (((kl & 63) >> 3) << 4) + (kl & 7) * 2;
-    uint8_t* prow1 = xp + (kl >> 6) * 1024 + 128 + ((((kl & 63) >> 3) ^ 1) << 4) + (kl & 7) * 2;
-    uint32_t g = sy.xa_count;
+  } else {
+    // ------------------------------- consumer warps -------------------------------
+    const int cw = warp - 1;
+    // ldmatrix lane addressing inside a 112-row x 128-byte swizzled tile (chunk' = chunk ^ (row & 7)); this warp's rows 16 cw ..
+    const int rowA = cw * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, chA = lane >> 4;         // K (non-transposed): chunk 2 j + chA
+    const int rowV = cw * 16 + (lane & 7) + ((lane >> 4) & 1) * 8, chV = (lane >> 3) & 1;   // V (transposed): chunk 2 mt + chV
+    const int sw = lane & 7;
+    uint32_t consumed = sy.xa_count;
     for (int it = 0; it < n_items; ++it) {
       const XaItem x = xa_item(it, cta, qw, G, P, plen);
-      const uint32_t gi = sy.xa_items + (uint32_t)it, ipar = gi & 1, iph = (gi >> 1) & 1;
-      const int ntile = (x.k1 - x.k0 + XA_KEYS - 1) / XA_KEYS;
-      float m = -INFINITY, lsum = 0.f;
-      for (int tl = 0; tl < ntile; ++tl, ++g) {
-        mbar_wait(sy.mb(MB_S_FULL + (g & 1)), (g >> 1) & 1);
-        tc_fence_after();
-        uint32_t shi, slo;
-        tc_ld_32x32_x2(tl_addr + XT_S + 16u * (g & 1), shi, slo);
-        tc_wait_ld();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(sy.mb(MB_S_FREE + (g & 1)));
-        const float sc = (x.k0 + tl * XA_KEYS + kl < x.k1) ? __uint_as_float(shi) + __uint_as_float(slo) : -INFINITY;
-        const float wmx = warp_max(sc);
-        float* tmx = fscr + (g & 1) * 4;
-        if (lane == 0) tmx[q4] = wmx;
-        named_bar_sync(1, 128);
-        const float tmax = fmaxf(fmaxf(tmx[0], tmx[1]), fmaxf(tmx[2], tmx[3]));  // finite: a tile holds at least one key of the item
-        if (tl == 0) {
-          m = tmax;
-        } else if (tmax > m + 8.f) {  // uniform over the 128 threads
-          // rare: move the reference offset; the PV product of the previous tile must have completed (O up to date)
-          mbar_wait(sy.mb(MB_P_FREE + ((g - 1) & 1)), ((g - 1) >> 1) & 1);
-          const float alpha = __expf(m - tmax);
-          lsum *= alpha;
-          m = tmax;
-          if (q4 == 0) {  // rows 0 / 1 of the accumulator live in this warp's lanes 0 / 1
-            tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              uint32_t v[32];
-              tc_ld_32x32(tl_addr + XT_O + 64u * ipar + 32u * c, v);
-              tc_wait_ld();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-              tc_st_32x32(tl_addr + XT_O + 64u * ipar + 32u * c, v);
-            }
-            tc_wait_st();
-            tc_fence_before();
-          }
-        }
-        const float pr = __expf(sc - m);  // masked key: 0
-        lsum += pr;
-        const __nv_bfloat16 ph = __float2bfloat16_rn(pr);
-        const __nv_bfloat16 pl = __float2bfloat16_rn(pr - __bfloat162float(ph));
-        mbar_wait(sy.mb(MB_P_FREE + (g & 1)), ((g >> 1) & 1) ^ 1);  // the PV product of tile g - 2 has read this P tile
-        *reinterpret_cast<__nv_bfloat16*>(prow0 + (g & 1) * 2048) = ph;
-        *reinterpret_cast<__nv_bfloat16*>(prow1 + (g & 1) * 2048) = pl;
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(sy.mb(MB_P_FULL + (g & 1)));
+      const int b = x.slab / H, h = x.slab - b * H;
+      const uint32_t gi = sy.xa_items + (uint32_t)it;  // items since kernel start: parity and phase of the double-buffered slots
+      const uint32_t ipar = gi & 1, iph = (gi >> 1) & 1;
+      // scaled q = (bias + split-K partials in slice order) * scale; lane holds dims lane and lane + 32
+      mbar_wait(sy.mb(MB_Q_FULL + ipar), iph);
+      float qn0, qn1;
+      {
+        const float* qr = qraw + ipar * (QRAW_ROWS * 64);
+        float a0 = qr[gk * 64 + lane], a1 = qr[gk * 64 + lane + 32];
+        for (int ks = 0; ks < gk; ++ks) { a0 += qr[ks * 64 + lane]; a1 += qr[ks * 64 + lane + 32]; }
+        qn0 = a0 * scale;
+        qn1 = a1 * scale;
       }
-      // ---- item finished: row sum over the 128 threads, then warp 4 reads O out ----
-      lsum = warp_sum(lsum);
-      float* lsm = fscr + 8 + ipar * 4;
-      if (lane == 0) lsm[q4] = lsum;
-      named_bar_sync(1, 128);
-      if (q4 == 0) {
-        const float Ls = (lsm[0] + lsm[1]) + (lsm[2] + lsm[3]);
-        const float M = m;
-        mbar_wait(sy.mb(MB_O_FULL + ipar), iph);
-        tc_fence_after();
-        float* oh = fscr + 16;  // [64]
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sy.mb(MB_Q_FREE + ipar));
+      // B fragments of q: lane (g, t) holds elements 16 j + 2 t + {0, 1} and + {8, 9}; column g = 0 hi part, g = 1 lo part
+      uint32_t qb[4][2];
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t v[32];
-          tc_ld_32x32(tl_addr + XT_O + 64u * ipar + 32u * c, v);
-          tc_wait_ld();
+      for (int j = 0; j < 4; ++j) {
+        const float src = (j < 2) ? qn0 : qn1;
+        const int e = (16 * j + 2 * t) & 31;
+        const float v0 = __shfl_sync(0xffffffffu, src, e), v1 = __shfl_sync(0xffffffffu, src, e + 1);
+        const float v8 = __shfl_sync(0xffffffffu, src, e + 8), v9 = __shfl_sync(0xffffffffu, src, e + 9);
+        qb[j][0] = split_pack(v0, v1, g);
+        qb[j][1] = split_pack(v8, v9, g);
+      }
+      float m = -INFINITY, lsum = 0.f, o[4][4];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float o = __uint_as_float(v[i]) + __shfl_down_sync(0xffffffffu, __uint_as_float(v[i]), 1);  // hi row + lo row
-            if (lane == 0) oh[32 * c + i] = o;
+      for (int mt = 0; mt < 4; ++mt) o[mt][0] = o[mt][1] = o[mt][2] = o[mt][3] = 0.f;
+      // XA_NS stages per iteration: the QK products, shuffles and exponentials of the stages overlap instead of forming
+      // one dependent chain per stage (the consumer math, not the K/V stream, bounds the phase once K/V hit L2).  K
+      // fragments of all stages are read first; the V fragments of a stage are read right before its PV products (and
+      // only then is the slot released), which keeps the register peak at one stage of V.
+      int kk = x.k0;
+      while (kk < x.k1) {
+        const int ns = (XA_NS == 2 && kk + XA_KEYS < x.k1) ? 2 : 1;  // warp-uniform
+        uint32_t ka[XA_NS][4][4];
+        uint32_t vb[XA_NS], slv[XA_NS];
+        bool act[XA_NS];
+#pragma unroll
+        for (int n = 0; n < XA_NS; ++n) {
+          act[n] = false;
+          if (n < ns) {
+            const uint32_t sl = consumed % XA_NST, par = (consumed / XA_NST) & 1;
+            act[n] = kk + n * XA_KEYS + cw * 16 < x.k1;  // warp-uniform: this warp's 16 keys hold at least one key of the item
+            mbar_wait(sy.mb(MB_XA_FULL + sl), par);
+            const uint32_t kbase = smem_u32(ring + (size_t)sl * STAGE);
+            vb[n] = kbase + XA_HALF; slv[n] = sl;
+            if (act[n]) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) ldsm_x4(ka[n][j], kbase + rowA * 128 + (((2 * j + chA) ^ sw) << 4));
+            }
+            ++consumed;
           }
         }
-        tc_fence_before();
+        // scores of the stages (two accumulators per stage), one max reduction for all of them
+        float sc[XA_NS][2];
+#pragma unroll
+        for (int n = 0; n < XA_NS; ++n) {
+          sc[n][0] = sc[n][1] = -INFINITY;
+          if (n < ns && act[n] && !(skip & 16)) {
+            float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+            mma_16816(c0, ka[n][0], qb[0][0], qb[0][1]);
+            mma_16816(c1, ka[n][1], qb[1][0], qb[1][1]);
+            mma_16816(c0, ka[n][2], qb[2][0], qb[2][1]);
+            mma_16816(c1, ka[n][3], qb[3][0], qb[3][1]);
+            const int key0 = kk + n * XA_KEYS + cw * 16 + g;
+            const float s0 = __shfl_sync(0xffffffffu, (c0[0] + c0[1]) + (c1[0] + c1[1]), lane & ~3);
+            const float s1 = __shfl_sync(0xffffffffu, (c0[2] + c0[3]) + (c1[2] + c1[3]), lane & ~3);
+            sc[n][0] = (key0 < x.k1) ? s0 : -INFINITY;
+            sc[n][1] = (key0 + 8 < x.k1) ? s1 : -INFINITY;
+          }
+        }
+        float mx = fmaxf(sc[0][0], sc[0][1]);
+#pragma unroll
+        for (int n = 1; n < XA_NS; ++n) mx = fmaxf(mx, fmaxf(sc[n][0], sc[n][1]));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+        const float mn = fmaxf(m, mx);
+        if (mn > m) {  // warp-uniform
+          const float alpha = __expf(m - mn);  // m = -inf -> 0
+          lsum *= alpha;
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) { o[mt][0] *= alpha; o[mt][1] *= alpha; o[mt][2] *= alpha; o[mt][3] *= alpha; }
+          m = mn;
+        }
+#pragma unroll
+        for (int n = 0; n < XA_NS; ++n) {
+          if (n < ns) {
+            const bool live = act[n] && m > -INFINITY && !(skip & 16);
+            uint32_t va[4][4];
+            if (live) {
+#pragma unroll
+              for (int mt = 0; mt < 4; ++mt) ldsm_x4_t(va[mt], vb[n] + rowV * 128 + (((2 * mt + chV) ^ sw) << 4));
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(sy.mb(MB_XA_EMPTY + slv[n]));  // this warp is done reading the stage
+            if (live) {
+              const float p0 = __expf(sc[n][0] - m), p1 = __expf(sc[n][1] - m);  // -inf -> 0
+              lsum += p0 + p1;  // per-quad partial sum (identical in the 4 lanes of a quad)
+              // B fragment of p: lane (g, t) needs keys 2t, 2t+1 (b0) and 2t+8, 2t+9 (b1): quads 2t and 2t+1
+              const float x0 = __shfl_sync(0xffffffffu, p0, 8 * t), x1 = __shfl_sync(0xffffffffu, p0, 8 * t + 4);
+              const float y0 = __shfl_sync(0xffffffffu, p1, 8 * t), y1 = __shfl_sync(0xffffffffu, p1, 8 * t + 4);
+              const uint32_t pb0 = split_pack(x0, x1, g), pb1 = split_pack(y0, y1, g);
+#pragma unroll
+              for (int mt = 0; mt < 4; ++mt) mma_16816(o[mt], va[mt], pb0, pb1);
+            }
+          }
+        }
+        kk += ns * XA_KEYS;
+      }
+      // ---- deposit this warp's state; consumer warp (item % 7) merges the 7 states and writes the output ----
+      lsum += __shfl_xor_sync(0xffffffffu, lsum, 4);
+      lsum += __shfl_xor_sync(0xffffffffu, lsum, 8);
+      lsum += __shfl_xor_sync(0xffffffffu, lsum, 16);
+      mbar_wait(sy.mb(MB_ST_FREE + ipar), iph ^ 1);  // the merge of item gi - 2 has released this slot
+      {
+        float* st = sst + (ipar * XA_CW + cw) * 66;
+        if (lane == 0) { st[0] = m; st[1] = lsum; }
+        if (t == 0) {
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) {
+            st[2 + 16 * mt + g] = o[mt][0] + o[mt][1];
+            st[2 + 16 * mt + g + 8] = o[mt][2] + o[mt][3];
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sy.mb(MB_ST_FULL + ipar));
+      if (cw == (int)(gi % XA_CW)) {
+        mbar_wait(sy.mb(MB_ST_FULL + ipar), iph);
+        const float* st = sst + (size_t)ipar * XA_CW * 66;
+        float M = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < XA_CW; ++i) M = fmaxf(M, st[i * 66]);
+        float Ls = 0.f, o0 = 0.f, o1 = 0.f;  // dims lane and lane + 32
+#pragma unroll
+        for (int i = 0; i < XA_CW; ++i) {
+          const float w = __expf(st[i * 66] - M);  // a warp that saw no key of the item: m = -inf -> 0
+          Ls += w * st[i * 66 + 1];
+          o0 += w * st[i * 66 + 2 + lane];
+          o1 += w * st[i * 66 + 2 + lane + 32];
+        }
         __syncwarp();
-        if (lane == 0) mbar_arrive(sy.mb(MB_O_FREE + ipar));
-        const float o0 = oh[lane], o1 = oh[lane + 32];
-        __syncwarp();  // oh is rewritten by the next item
-        const int b = x.slab / H, h = x.slab - b * H;
+        if (lane == 0) mbar_arrive(sy.mb(MB_ST_FREE + ipar));
         __nv_bfloat16* out = att + (size_t)b * d + h * 64;
-        if (x.piece < 0) {
+        if (skip & 32) {
+        } else if (x.piece < 0) {
           out[lane] = __float2bfloat16_rn(o0 / Ls);
           out[lane + 32] = __float2bfloat16_rn(o1 / Ls);
         } else {
@@ -1159,7 +1209,7 @@ __device__ __forceinline__ void pre_issue(const MkParams& p, int l, int k, uint8
     int P = 0, plen = T_AUDIO;
     if (r > 0) {
       const int want = (G + r - 1) / r;
-      plen = ((T_AUDIO + want - 1) / want + 7) & ~7;  // piece starts stay multiples of 8 keys (the swizzle period)
+      plen = (T_AUDIO + want - 1) / want;
       P = (T_AUDIO + plen - 1) / plen;
     }
     const int n_items = qw + ((r > 0 && cta < r * P) ? ((r * P - 1 - cta) / G + 1) : 0);
@@ -1170,11 +1220,12 @@ __device__ __forceinline__ void pre_issue(const MkParams& p, int l, int k, uint8
         if (!issue) continue;
         const uint32_t c = sy.xa_count + (uint32_t)n, sl = c % XA_NST, par = (c / XA_NST) & 1;
         mbar_wait(sy.mb(MB_XA_EMPTY + sl), par ^ 1);
-        const int rows = min(XA_KEYS, x.k1 - kk);
+        const bool tail = (x.k1 - kk <= XA_TAIL);
+        const CUtensorMap* m = tail ? kvmap + 1 : kvmap;
         uint8_t* dst = ring + (size_t)sl * STAGE;
-        mbar_arrive_expect_tx(sy.mb(MB_XA_FULL + sl), (uint32_t)rows * 256u);
-        bulk_load_1d_hint(dst, p.cross_kv + ((size_t)krow0 + (size_t)x.slab * T_AUDIO + kk) * 64, (uint32_t)rows * 128u, sy.mb(MB_XA_FULL + sl), L2_EVICT_FIRST);
-        bulk_load_1d_hint(dst + XA_HALF, p.cross_kv + ((size_t)vrow0 + (size_t)x.slab * T_AUDIO + kk) * 64, (uint32_t)rows * 128u, sy.mb(MB_XA_FULL + sl), L2_EVICT_FIRST);
+        mbar_arrive_expect_tx(sy.mb(MB_XA_FULL + sl), tail ? 2 * XA_TAIL * 128 : STAGE);
+        tma_load_2d_hint(dst, m, sy.mb(MB_XA_FULL + sl), 0, krow0 + x.slab * T_AUDIO + kk, L2_EVICT_FIRST);
+        tma_load_2d_hint(dst + XA_HALF, m, sy.mb(MB_XA_FULL + sl), 0, vrow0 + x.slab * T_AUDIO + kk, L2_EVICT_FIRST);
       }
       ++it;
     }
@@ -1241,7 +1292,7 @@ __device__ __forceinline__ void l2_stage(const MkParams& p, int l, int k, int po
     int P = 0, plen = T_AUDIO;
     if (r > 0) {
       const int want = (G + r - 1) / r;
-      plen = ((T_AUDIO + want - 1) / want + 7) & ~7;  // piece starts stay multiples of 8 keys (the swizzle period)
+      plen = (T_AUDIO + want - 1) / want;
       P = (T_AUDIO + plen - 1) / plen;
     }
     const int n_items = qw + ((r > 0 && cta < r * P) ? ((r * P - 1 - cta) / G + 1) : 0);
@@ -1301,7 +1352,7 @@ template <int MT>
 __global__ void __launch_bounds__(MK_THREADS, 1) dec_step_kernel(const __grid_constant__ MkParams p) {
   extern __shared__ uint8_t mk_smem_raw[];
   uint8_t* ring = mk_smem_raw + ((1024u - (smem_u32(mk_smem_raw) & 1023u)) & 1023u);  // 1024-byte aligned (swizzle atoms)
-  float* scratch = reinterpret_cast<float*>(ring + RING_BYTES + XP_BYTES + XQ_BYTES);
+  float* scratch = reinterpret_cast<float*>(ring + RING_BYTES);
   __shared__ float red[MK_WARPS];
   __shared__ int red_i[MK_WARPS];
   __shared__ __align__(8) uint64_t bars[MB_COUNT];
@@ -1317,21 +1368,14 @@ __global__ void __launch_bounds__(MK_THREADS, 1) dec_step_kernel(const __grid_co
   if (threadIdx.x == 0) {
     for (int i = 0; i < GV_NST; ++i) { mbar_init(sy.mb(MB_GV_FULL + i), 1); mbar_init(sy.mb(MB_GV_EMPTY + i), 1); }
     mbar_init(sy.mb(MB_ACC_FULL), 1);
-    for (int i = 0; i < XA_NST; ++i) { mbar_init(sy.mb(MB_XA_FULL + i), 1); mbar_init(sy.mb(MB_XA_EMPTY + i), 1); }
+    for (int i = 0; i < XA_NST; ++i) { mbar_init(sy.mb(MB_XA_FULL + i), 1); mbar_init(sy.mb(MB_XA_EMPTY + i), XA_CW); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(sy.mb(MB_S_FULL + i), 1); mbar_init(sy.mb(MB_S_FREE + i), 4);
-      mbar_init(sy.mb(MB_P_FULL + i), 4); mbar_init(sy.mb(MB_P_FREE + i), 1);
-      mbar_init(sy.mb(MB_Q_FULL + i), 32); mbar_init(sy.mb(MB_Q_FREE + i), 1);
-      mbar_init(sy.mb(MB_QT_FULL + i), 1); mbar_init(sy.mb(MB_QT_FREE + i), 1);
-      mbar_init(sy.mb(MB_O_FULL + i), 1); mbar_init(sy.mb(MB_O_FREE + i), 1);
+      mbar_init(sy.mb(MB_ST_FULL + i), XA_CW); mbar_init(sy.mb(MB_ST_FREE + i), 1);
+      mbar_init(sy.mb(MB_Q_FULL + i), 32); mbar_init(sy.mb(MB_Q_FREE + i), XA_CW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) tmem_alloc(&tmem_slot, 256);
-  // stale shared memory is multiplied by zero probabilities / zero operand rows: it must hold finite values
-  for (int i = threadIdx.x; i < (int)((RING_BYTES + XP_BYTES + XQ_BYTES + SCRATCH_BYTES) / 16); i += MK_THREADS)
-    reinterpret_cast<uint4*>(ring)[i] = make_uint4(0u, 0u, 0u, 0u);
-  fence_proxy_async();
+  if (warp == 2) tmem_alloc(&tmem_slot, 64);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1354,7 +1398,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) dec_step_kernel(const __grid_co
         int l2 = ph2 / 11, k2 = ph2 - 11 * l2;
         if (l2 >= p.L) { k2 = 11 + (ph2 - 11 * p.L); l2 = p.L - 1; }
         grid_sync(p.bar, bar_target, sy.nc, sy.cta, p.prof, prof_n, [&]() { pre_issue<MT>(p, l2, k2, ring, sy, true); });
-        if (threadIdx.x == 0) pre_issue<MT>(p, l2, k2, ring, sy, false);  // the producer thread only needs the count
+        if (warp == 0) pre_issue<MT>(p, l2, k2, ring, sy, false);  // the producer warp only needs the count
       }
     }
   }
@@ -1363,7 +1407,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) dec_step_kernel(const __grid_co
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(sy.tmem, 256);
+    tmem_dealloc(sy.tmem, 64);
   }
 }
 
@@ -1545,7 +1589,7 @@ int alloc_buffers(wxb_ctx* ctx, int B, int tok_stride, DecBuffers* o) {
     if ((rc = wxb_make_tmap_bf16(ctx, am + 1, o->xn, (uint64_t)d, (uint64_t)B, (uint64_t)d * 2, GV_BK, Bp)) != WXB_OK) return rc;
     if ((rc = wxb_make_tmap_bf16(ctx, am + 2, o->att, (uint64_t)d, (uint64_t)B, (uint64_t)d * 2, GV_BK, Bp)) != WXB_OK) return rc;
     if ((rc = wxb_make_tmap_bf16(ctx, am + 3, o->hid, (uint64_t)4 * d, (uint64_t)B, (uint64_t)4 * d * 2, GV_BK, Bp)) != WXB_OK) return rc;
-    // cross K/V of all layers as one [rows, 64] tensor read in 128-key boxes (96-key boxes at the end of an item)
+    // cross K/V of all layers as one [rows, 64] tensor read in 112-key boxes (48-key boxes at the end of an item)
     if ((rc = wxb_make_tmap_bf16(ctx, am + 4, o->cross_kv, 64, (uint64_t)L * 2 * B * H * T_AUDIO, 128, 64, XA_KEYS)) != WXB_OK) return rc;
     if ((rc = wxb_make_tmap_bf16(ctx, am + 5, o->cross_kv, 64, (uint64_t)L * 2 * B * H * T_AUDIO, 128, 64, XA_TAIL)) != WXB_OK) return rc;
     WXB_CUDA(ctx, cudaDeviceSynchronize());  // a previous decode may still be reading the old table

@@ -284,7 +284,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           } else {
             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldo + n0;
-            int swz = 0;  // kv_mode: 16-byte chunk c of key row t is stored at chunk c ^ (t & 7) (the 128-byte swizzle, applied in HBM)
             if (p.kv_mode) {
               const int dm = p.N >> 1;
               const int kv = n0 / dm, rem = n0 - kv * dm;
@@ -292,9 +291,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int bb = r / p.kv_T, tt = r - bb * p.kv_T;
               o = reinterpret_cast<__nv_bfloat16*>(p.out) +
                   ((((long long)kv * p.kv_B + bb) * p.kv_H + hh) * p.kv_T + tt) * 64 + j0;
-              swz = (tt & 7) << 3;  // in elements; j0 is 0 or 32, so (j0 + i) ^ swz stays inside the row
-              o -= j0;
-              swz ^= j0;            // o[(i ^ swz)] == row[(j0 + i) ^ ((tt & 7) << 3)] for i < 32, i % 8 == 0
             }
             if (full) {
 #pragma unroll
@@ -308,7 +304,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 pk.y = *reinterpret_cast<uint32_t*>(&b1);
                 pk.z = *reinterpret_cast<uint32_t*>(&b2);
                 pk.w = *reinterpret_cast<uint32_t*>(&b3);
-                *reinterpret_cast<uint4*>(o + (i ^ swz)) = pk;
+                *reinterpret_cast<uint4*>(o + i) = pk;
               }
             } else {
               for (int i = 0; i < 32; ++i)

@@ -25,9 +25,7 @@ struct GemmArgs {
   // output row = g * g_out + t + out_off.  Defaults = identity.
   int g_in = 0, g_valid = 0, g_out = 0, out_off = 0;
   // kv_mode (cross-attention K|V projection): N = 2*d, bf16 output scattered head-major:
-  //   out[((kv*kv_B + b)*kv_H + h)*kv_T + t][j ^ ((t & 7) << 3)]  with r = b*kv_T + t, n = kv*d + h*64 + j
-  // (rows are stored with the 128-byte shared-memory swizzle already applied, so the decoder streams them with
-  //  plain bulk copies and hands them to tcgen05.mma as swizzled operand tiles)
+  //   out[((kv*kv_B + b)*kv_H + h)*kv_T + t][j]  with r = b*kv_T + t, n = kv*d + h*64 + j
   int kv_mode = 0, kv_B = 0, kv_H = 0, kv_T = 0;
 };
 
