@@ -43,7 +43,10 @@ namespace {
 using namespace wxbtc;
 
 constexpr int T_AUDIO = 1500;
-constexpr int MK_THREADS = 256;
+#ifndef WXB_MK_THREADS
+#define WXB_MK_THREADS 384
+#endif
+constexpr int MK_THREADS = WXB_MK_THREADS;  // 12 warps: the attention phases are bound by per-warp dependent chains, so more warps = more throughput
 constexpr int MK_WARPS = MK_THREADS / 32;
 constexpr int LN_V4 = 2;    // LayerNorm phase: float4 groups per thread, d <= 4 * 2 * 256
 constexpr int GK_MAX = 10;  // largest split-K factor a GEMV plan may use
@@ -51,30 +54,44 @@ constexpr int MAX_LAYERS = 32;
 
 
 // ---- shared-memory plan of the persistent kernel (dynamic, 1024-byte aligned base) -------------------------
-// One region is time-shared by the two TMA rings (GEMV phases and cross-attention never overlap inside a CTA):
-//   GEMV ring   GV_NST stages x (A: 128 weight rows x 64 k bf16 = 16 KB | B: Bp batch rows x 64 k), 128-byte swizzle
-//   KV ring     XA_NST stages x (K: 112 keys x 64 dims bf16 = 14 KB | V: 14 KB), 128-byte swizzle
+// One region is time-shared by the phases (they never overlap inside a CTA):
+//   GEMV ring        GV_NST stages x (A: 128 weight rows x 64 k bf16 = 16 KB | B: Bp batch rows x 64 k), 128-byte swizzle
+//   cross-attention  K ring: XA_NST stages x (16 XA_CW keys x 64 dims bf16), filled by TMA (128-byte swizzle);
+//                    V rings: XA_CW warps x XA_VD private slots x (16 keys x 128 B), filled by the consumer warps
+//                    themselves with cp.async (same swizzle)
+//   self-attention   per-warp K/V staging
 // followed by the attention scratch (warp states of two items, raw q rows of two items).
 constexpr int GV_ROWS = 128;                 // weight rows per tile = UMMA M
 constexpr int GV_BK = 64;                    // k per stage (one 128-byte swizzle row)
 constexpr int GV_A_BYTES = GV_ROWS * GV_BK * 2;
-constexpr int XA_CW = 7;                     // cross-attention consumer warps (hardware warps 1 .. 7); warp 0 produces
+constexpr int XA_CW = MK_WARPS - 1;          // cross-attention consumer warps (hardware warps 1 ..); warp 0 produces
 constexpr int XA_KEYS = 16 * XA_CW;          // keys per stage: one m16 tile per consumer warp
-constexpr int XA_HALF = XA_KEYS * 128;       // bytes of K (or V) per stage
-constexpr int XA_TAIL = 48;                  // rows of the short TMA box used when <= 48 keys of an item remain
-constexpr int SST_BYTES = 3712;                           // [2 item parities][7 warps][66] floats, padded
+constexpr int XA_HALF = XA_KEYS * 128;       // bytes of K per stage
+constexpr int XA_TAIL = MK_WARPS == 8 ? 48 : 96;  // rows of the short TMA box used when at most this many keys of an item remain (1500 = 8 x 176 + 92)
+#ifndef WXB_XA_NST
+#define WXB_XA_NST 6
+#endif
+#ifndef WXB_XA_VD
+#define WXB_XA_VD 3
+#endif
+constexpr int XA_NST = WXB_XA_NST;           // K ring depth
+constexpr int XA_VD = WXB_XA_VD;             // private V slots per consumer warp (V rows are requested XA_VD - 1 stages ahead)
+constexpr int XA_KRING = XA_NST * XA_HALF;
+constexpr int XA_VRING = XA_CW * XA_VD * 2048;
+constexpr int SST_BYTES = (2 * XA_CW * 66 * 4 + 127) & ~127;  // [2 item parities][XA_CW warps][66] floats, padded
 constexpr int QRAW_ROWS = GK_MAX + 1;                     // bias row + up to GK_MAX split-K partial rows of q
 constexpr int QRAW_BYTES = 2 * QRAW_ROWS * 64 * 4;        // two items in flight
 constexpr int SCRATCH_BYTES = SST_BYTES + QRAW_BYTES;     // attention scratch behind the ring
-constexpr int XA_NST = 6;                    // K/V ring depth
 #ifndef WXB_XA_NS
-#define WXB_XA_NS 2
+#define WXB_XA_NS 1
 #endif
 constexpr int XA_NS = WXB_XA_NS;             // K/V stages per consumer iteration
 constexpr int GV_NST = 6;                    // GEMV ring depth
-constexpr int RING_BYTES = XA_NST * 2 * XA_HALF;
+constexpr int RING_BYTES = XA_KRING + XA_VRING;
 constexpr size_t MK_SMEM = RING_BYTES + SCRATCH_BYTES + 1024;
+static_assert(XA_KRING % 1024 == 0, "the V rings start on a swizzle-atom boundary");
 static_assert(GV_NST * (GV_A_BYTES + 64 * GV_BK * 2) <= RING_BYTES, "GEMV ring must fit the shared region");
+static_assert(MK_SMEM + 6 * 1024 <= 227 * 1024, "dynamic + static shared memory must fit an SM");
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -143,9 +160,7 @@ struct MkParams {
   int n_steps;  // consecutive positions decoded by this launch (> 1 only in mode 2)
   int xa_pf;    // L2 prefetch distance of the cross-attention K/V stream in stages (0 = off)
   int skip;     // profiling aid (WXB_DEC_SKIP): 1 cross-attention, 2 GEMV, 4 self-attention, 8 LayerNorm, 16 cross math, 32 cross merge
-  int l2pf;     // L2 staging during the latency-bound phases (l2_stage): 1 self K/V, 2 head of the cross K/V stream, 4 GEMV weights
   int xa_ns;    // cross-attention stages per consumer iteration (1 or 2)
-  int l2_xa;    // cross K/V stages (28 KB) per CTA staged in L2 ahead of a cross-attention phase
   const DecLayerW* layers;  // device array [L]
   const CUtensorMap* maps;  // device array [6 L + 5]
   const __nv_bfloat16* emb;
@@ -381,7 +396,7 @@ __device__ __forceinline__ void gemv_phase(const MkParams& p, const MkGemv& g, c
     tc_fence_after();
     // ---- epilogue: warp w reads TMEM lanes 32 (w & 3) .. +31 (weight rows), 16-column groups j = w >> 2, + 2, .. ----
     const int n = row0 + (warp & 3) * 32 + lane;
-    for (int j = warp >> 2; j < MT; j += 2) {
+    for (int j = warp >> 2; j < MT; j += MK_WARPS / 4) {
       uint32_t v[16];
       tc_ld_32x32_x16(sy.tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(j * 16), v);
       tc_wait_ld();
@@ -516,7 +531,7 @@ __device__ __forceinline__ SelfUnit self_unit_qkv(const MkParams& p, const float
 }
 // online-softmax state of one warp over the cached keys [k_begin, k_end) (and the new key if with_new), merged over
 // the warp's 4 key slots: on return every lane holds m, l and the 8 output dims of its c8
-constexpr int SA_AHEAD = 4;            // chunks of 16 keys requested ahead of the one being consumed
+constexpr int SA_AHEAD = MK_WARPS == 8 ? 4 : 3;  // chunks of 16 keys requested ahead of the one being consumed
 constexpr int SA_RING = SA_AHEAD + 1;  // 4 KB chunk slots per warp
 static_assert(MK_WARPS * SA_RING * 4096 <= RING_BYTES, "self-attention staging must fit the TMA ring region");
 __device__ __forceinline__ void self_unit_attend(const SelfUnit& u, const __nv_bfloat16* Kb, const __nv_bfloat16* Vb, int k_begin, int k_end,
@@ -765,11 +780,11 @@ __device__ __forceinline__ void xa_block(const uint32_t (*ka)[4][4], const uint3
 // 7 states once all have arrived (mbarrier) and writes the output.
 __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const float* __restrict__ cq_b, uint8_t* ring,
                                                  float* scratch, MkSync& sy) {
-  constexpr uint32_t STAGE = 2 * XA_HALF;
+  constexpr uint32_t STAGE = XA_HALF;  // the TMA ring holds K only
   float* sst = scratch;                                                                          // [2 item parities][7 warps][66]: m, l, O[64]
   float* qraw = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(scratch) + SST_BYTES);      // [2 item parities][QRAW_ROWS][64]
   const float scale = p.scale;
-  const int skip = p.skip, xa_pf = p.xa_pf;
+  const int skip = p.skip;
   const float* __restrict__ part_q = p.part;
   __nv_bfloat16* __restrict__ att = p.att;
   float* __restrict__ apart = p.apart;
@@ -788,9 +803,9 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
   const int n_items = qw + ((r > 0 && cta < r * P) ? ((r * P - 1 - cta) / G + 1) : 0);
   if (warp == 0) {
     // ------------------------------- producer warp -------------------------------
-    int it = 0, kk = 0, pit = 0, pkk = 0, ahead = 0;  // load cursor, L2-prefetch cursor, distance between them in stages
-    XaItem x = {}, px = {};
-    if (n_items > 0) { x = xa_item(0, cta, qw, G, P, plen); kk = x.k0; px = x; pkk = kk; }
+    int it = 0, kk = 0;  // load cursor
+    XaItem x = {};
+    if (n_items > 0) { x = xa_item(0, cta, qw, G, P, plen); kk = x.k0; }
     uint32_t issued = sy.xa_count;
     auto stage_q = [&](int qi) {
       // raw q rows of item qi (row gk = bias, rows 0 .. gk-1 = split-K partials of the cq GEMV), 2 rows per pass
@@ -810,21 +825,6 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
       cp_async_mbar_arrive(sy.mb(MB_Q_FULL + qpar));
     };
     while (it < n_items) {
-      if (xa_pf > 0) {
-        while (pit < n_items && ahead <= xa_pf) {
-          if (ahead >= XA_NST && lane == 0) {
-            const CUtensorMap* m = (px.k1 - pkk <= XA_TAIL) ? kvmap + 1 : kvmap;
-            tma_prefetch_2d(m, 0, krow0 + px.slab * T_AUDIO + pkk);
-            tma_prefetch_2d(m, 0, vrow0 + px.slab * T_AUDIO + pkk);
-          }
-          ++ahead;
-          pkk += XA_KEYS;
-          if (pkk >= px.k1) {
-            ++pit;
-            if (pit < n_items) { px = xa_item(pit, cta, qw, G, P, plen); pkk = px.k0; }
-          }
-        }
-      }
       if (kk == x.k0) stage_q(it);  // first stage of an item: its raw q rows
       if (lane == 0 && (int)(issued - sy.xa_count) >= sy.pre) {  // the first sy.pre stages were requested before the barrier wait
         const uint32_t sl = issued % XA_NST, par = (issued / XA_NST) & 1;
@@ -832,19 +832,11 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
         const bool tail = (x.k1 - kk <= XA_TAIL);  // keys past the item (or the tensor: zero-filled) are masked by the consumer
         const CUtensorMap* m = tail ? kvmap + 1 : kvmap;
         uint8_t* dst = ring + (size_t)sl * STAGE;
-        mbar_arrive_expect_tx(sy.mb(MB_XA_FULL + sl), tail ? 2 * XA_TAIL * 128 : STAGE);
-        const int slab_ld = (skip & 64) ? (x.slab & 3) : x.slab;  // probe: every CTA streams the same 4 slabs (all L2 hits)
-        if (skip & 64) {
-          tma_load_2d(dst, m, sy.mb(MB_XA_FULL + sl), 0, krow0 + slab_ld * T_AUDIO + kk);
-          tma_load_2d(dst + XA_HALF, m, sy.mb(MB_XA_FULL + sl), 0, vrow0 + slab_ld * T_AUDIO + kk);
-        } else {
+        mbar_arrive_expect_tx(sy.mb(MB_XA_FULL + sl), tail ? XA_TAIL * 128 : STAGE);
         tma_load_2d_hint(dst, m, sy.mb(MB_XA_FULL + sl), 0, krow0 + x.slab * T_AUDIO + kk, L2_EVICT_FIRST);
-        tma_load_2d_hint(dst + XA_HALF, m, sy.mb(MB_XA_FULL + sl), 0, vrow0 + x.slab * T_AUDIO + kk, L2_EVICT_FIRST);
-        }
       }
       __syncwarp();
       ++issued;
-      --ahead;
       kk += XA_KEYS;
       if (kk >= x.k1) {
         ++it;
@@ -857,9 +849,44 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
     const int cw = warp - 1;
     // ldmatrix lane addressing inside a 112-row x 128-byte swizzled tile (chunk' = chunk ^ (row & 7)); this warp's rows 16 cw ..
     const int rowA = cw * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, chA = lane >> 4;         // K (non-transposed): chunk 2 j + chA
-    const int rowV = cw * 16 + (lane & 7) + ((lane >> 4) & 1) * 8, chV = (lane >> 3) & 1;   // V (transposed): chunk 2 mt + chV
+    const int rowV = (lane & 7) + ((lane >> 4) & 1) * 8, chV = (lane >> 3) & 1;             // V (transposed, private 16-row slot): chunk 2 mt + chV
     const int sw = lane & 7;
     uint32_t consumed = sy.xa_count;
+    // V does not go through the TMA ring.  A single SM's TMA engine sustains only ~39 GB/s from HBM (~58 GB/s on L2 hits,
+    // whatever the ring depth or copy flavour), below this phase's 49 GB/s share of the HBM read ceiling, while plain loads
+    // reach that ceiling with 64 KB in flight.  So K streams through TMA and every consumer warp fetches the 16 V rows IT
+    // will multiply (its own rows of the stage, 2 KB) with cp.async into a private ring of XA_VD slots, XA_VD - 1 stages
+    // ahead along the CTA's work list: two engines in parallel and no barrier on the V path.
+    const uint32_t vring = smem_u32(ring) + XA_KRING + (uint32_t)(cw * XA_VD * 2048);
+    int v_it = 0, v_kk = 0;
+    uint32_t v_cnt = 0, v_used = 0;
+    XaItem vx = {};
+    if (n_items > 0) { vx = xa_item(0, cta, qw, G, P, plen); v_kk = vx.k0; }
+    const __nv_bfloat16* __restrict__ vsrc0 = p.cross_kv + (size_t)vrow0 * 64 + (lane & 7) * 8;  // this lane's 16-byte chunk of a row
+    auto v_issue = [&]() {
+      if (v_it < n_items) {
+        const int key0 = v_kk + cw * 16;
+        if (key0 < vx.k1) {  // warp-uniform
+          const uint32_t dst = vring + (v_cnt % XA_VD) * 2048;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = (lane >> 3) + 4 * i;                 // row of the slot; chunk c = lane & 7 goes to chunk c ^ (r & 7)
+            const int key = min(key0 + r, vx.k1 - 1);          // rows past the item are masked by p = 0: any finite data will do
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + r * 128 + (((lane & 7) ^ (r & 7)) << 4)),
+                         "l"(vsrc0 + ((size_t)vx.slab * T_AUDIO + key) * 64) : "memory");
+          }
+        }
+        v_kk += XA_KEYS;
+        if (v_kk >= vx.k1) {
+          ++v_it;
+          if (v_it < n_items) { vx = xa_item(v_it, cta, qw, G, P, plen); v_kk = vx.k0; }
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");  // one group per stage, empty or not: the wait below counts groups
+      ++v_cnt;
+    };
+#pragma unroll
+    for (int i = 0; i < XA_VD - 1; ++i) v_issue();
     for (int it = 0; it < n_items; ++it) {
       const XaItem x = xa_item(it, cta, qw, G, P, plen);
       const int b = x.slab / H, h = x.slab - b * H;
@@ -899,7 +926,7 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
       while (kk < x.k1) {
         const int ns = (XA_NS == 2 && kk + XA_KEYS < x.k1) ? 2 : 1;  // warp-uniform
         uint32_t ka[XA_NS][4][4];
-        uint32_t vb[XA_NS], slv[XA_NS];
+        uint32_t vb[XA_NS];
         bool act[XA_NS];
 #pragma unroll
         for (int n = 0; n < XA_NS; ++n) {
@@ -907,13 +934,17 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
           if (n < ns) {
             const uint32_t sl = consumed % XA_NST, par = (consumed / XA_NST) & 1;
             act[n] = kk + n * XA_KEYS + cw * 16 < x.k1;  // warp-uniform: this warp's 16 keys hold at least one key of the item
+            v_issue();  // V rows XA_VD - 1 stages ahead, into the slot read one stage ago
+            vb[n] = vring + (v_used % XA_VD) * 2048;
+            ++v_used;
             mbar_wait(sy.mb(MB_XA_FULL + sl), par);
             const uint32_t kbase = smem_u32(ring + (size_t)sl * STAGE);
-            vb[n] = kbase + XA_HALF; slv[n] = sl;
             if (act[n]) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) ldsm_x4(ka[n][j], kbase + rowA * 128 + (((2 * j + chA) ^ sw) << 4));
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(sy.mb(MB_XA_EMPTY + sl));  // this warp is done reading the K stage
             ++consumed;
           }
         }
@@ -954,12 +985,15 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
           if (n < ns) {
             const bool live = act[n] && m > -INFINITY && !(skip & 16);
             uint32_t va[4][4];
+            // the V rows of this stage have landed: all but the newest XA_VD - 1 groups (+ 1 for the later stage of a pair) are complete
+            if (XA_NS == 2 && n == 0 && ns == 2) asm volatile("cp.async.wait_group %0;" ::"n"(XA_VD) : "memory");
+            else asm volatile("cp.async.wait_group %0;" ::"n"(XA_VD - 1) : "memory");
+            __syncwarp();
             if (live) {
 #pragma unroll
               for (int mt = 0; mt < 4; ++mt) ldsm_x4_t(va[mt], vb[n] + rowV * 128 + (((2 * mt + chV) ^ sw) << 4));
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(sy.mb(MB_XA_EMPTY + slv[n]));  // this warp is done reading the stage
+            __syncwarp();  // the slot is refilled by the whole warp at the next stage
             if (live) {
               const float p0 = __expf(sc[n][0] - m), p1 = __expf(sc[n][1] - m);  // -inf -> 0
               lsum += p0 + p1;  // per-quad partial sum (identical in the 4 lanes of a quad)
@@ -1201,7 +1235,7 @@ __device__ __forceinline__ void pre_issue(const MkParams& p, int l, int k, uint8
     }
     sy.pre = n;
   } else if (kind == PH_CROSS && !(p.skip & 1)) {
-    constexpr uint32_t STAGE = 2 * XA_HALF;
+    constexpr uint32_t STAGE = XA_HALF;  // the TMA ring holds K only
     const int G = sy.nc, cta = sy.cta;
     const CUtensorMap* kvmap = p.maps + (size_t)p.L * TM_PER_LAYER + 4;
     const int n_slabs = p.B * p.H, qw = n_slabs / G, r = n_slabs - qw * G;
@@ -1223,9 +1257,8 @@ __device__ __forceinline__ void pre_issue(const MkParams& p, int l, int k, uint8
         const bool tail = (x.k1 - kk <= XA_TAIL);
         const CUtensorMap* m = tail ? kvmap + 1 : kvmap;
         uint8_t* dst = ring + (size_t)sl * STAGE;
-        mbar_arrive_expect_tx(sy.mb(MB_XA_FULL + sl), tail ? 2 * XA_TAIL * 128 : STAGE);
+        mbar_arrive_expect_tx(sy.mb(MB_XA_FULL + sl), tail ? XA_TAIL * 128 : STAGE);
         tma_load_2d_hint(dst, m, sy.mb(MB_XA_FULL + sl), 0, krow0 + x.slab * T_AUDIO + kk, L2_EVICT_FIRST);
-        tma_load_2d_hint(dst + XA_HALF, m, sy.mb(MB_XA_FULL + sl), 0, vrow0 + x.slab * T_AUDIO + kk, L2_EVICT_FIRST);
       }
       ++it;
     }
@@ -1233,80 +1266,6 @@ __device__ __forceinline__ void pre_issue(const MkParams& p, int l, int k, uint8
   }
 }
 
-
-// L2 staging.  Outside the cross-attention phase the step is a chain of latency-bound operators during which HBM idles,
-// and everything the coming operators will stream (weights, cached self K/V, the cross K/V slabs) is known in advance.
-// The last warp of every CTA therefore issues L2-only TMA prefetches at the start of a phase for data that is consumed
-// a few phases later: the consumer's loads then hit L2 (a third of the HBM latency at the same ring depth), and the
-// head of the cross K/V stream is already on chip when the bandwidth-bound phase begins.
-//   self K/V of layer l      rows [0, pos) of this CTA's own units: at fc2 of layer l - 1 (layer 0: at LN1)
-//   cross K/V of layer l     the first l2_xa stages of this CTA's work list: at the out projection (3 phases ahead)
-//   weights of GEMV (l, k)   two phases ahead, boxes dealt round-robin over all CTAs (L2 is shared)
-__device__ __forceinline__ void l2_bulk_prefetch(const void* ptr, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void l2_stage(const MkParams& p, int l, int k, int pos, const MkSync& sy) {
-  const int lane = threadIdx.x & 31, f = p.l2pf;
-  if (f & 4) {
-    int l2 = l, k2 = -1;
-    if (k == 1 || k == 3 || k == 5 || k == 7) k2 = k + 2;
-    else if (k == 8) k2 = 10;
-    else if (k == 10 && l + 1 < p.L) { l2 = l + 1; k2 = 1; }
-    else if (k == 11) { l2 = 0; k2 = 1; }  // first operator of the next step
-    if (k2 > 0) {
-      const GemvOp o = gemv_op(p, l2, k2);
-      const MkGemv& g = *o.g;
-      const int Ks = g.K / g.gk, nkb = Ks / GV_BK, n_box = g.tiles * nkb;
-      for (int i = lane * sy.nc + sy.cta; i < n_box; i += 32 * sy.nc) {
-        const int tile = i / nkb, kb = i - tile * nkb;
-        tma_prefetch_2d(o.wm, (tile % g.gk) * Ks + kb * GV_BK, (tile / g.gk) * GV_ROWS);
-      }
-    }
-  }
-  if ((f & 1) && pos > 0 && ((k == 10 && l + 1 < p.L) || (k == 0 && l == 0))) {
-    const int ls = (k == 0) ? 0 : l + 1;
-    const int H = p.H, B = p.B, TX = p.TX;
-    const __nv_bfloat16* sk = p.self_kv + (size_t)ls * 2 * B * H * TX * 64;
-    const size_t vofs = (size_t)B * H * TX * 64;
-    const int n_units = B * H, n_warps = sy.nc * MK_WARPS;
-    int n_solo = n_units;
-    const int left = n_units % n_warps;
-    if (left > 0 && left <= sy.nc && n_units > n_warps) n_solo = n_units - left;
-    const int n_rounds = (n_solo + n_warps - 1) / n_warps;
-    // lane = 2 w + kv: K (kv = 0) or V (kv = 1) rows of the unit of warp w, one request per round
-    const int w = lane >> 1, kv = lane & 1;
-    if (w < MK_WARPS) {
-      for (int round = 0; round < n_rounds; ++round) {
-        const int u0 = round * n_warps + sy.cta * MK_WARPS + w;
-        if (u0 < n_solo) l2_bulk_prefetch(sk + kv * vofs + (size_t)u0 * TX * 64, (uint32_t)pos * 128u);
-      }
-    } else if (w == MK_WARPS && n_solo + sy.cta < n_units) {
-      l2_bulk_prefetch(sk + kv * vofs + (size_t)(n_solo + sy.cta) * TX * 64, (uint32_t)pos * 128u);
-    }
-  }
-  if ((f & 2) && k == 3) {
-    const int G = sy.nc, cta = sy.cta;
-    const CUtensorMap* kvmap = p.maps + (size_t)p.L * TM_PER_LAYER + 4;
-    const int n_slabs = p.B * p.H, qw = n_slabs / G, r = n_slabs - qw * G;
-    const int krow0 = (l * 2) * n_slabs * T_AUDIO, vrow0 = (l * 2 + 1) * n_slabs * T_AUDIO;
-    int P = 0, plen = T_AUDIO;
-    if (r > 0) {
-      const int want = (G + r - 1) / r;
-      plen = (T_AUDIO + want - 1) / want;
-      P = (T_AUDIO + plen - 1) / plen;
-    }
-    const int n_items = qw + ((r > 0 && cta < r * P) ? ((r * P - 1 - cta) / G + 1) : 0);
-    int n = 0;
-    for (int it = 0; it < n_items && n < p.l2_xa; ++it) {
-      const XaItem x = xa_item(it, cta, qw, G, P, plen);
-      for (int kk = x.k0; kk < x.k1 && n < p.l2_xa; kk += XA_KEYS, ++n) {
-        if ((n & 15) != (lane >> 1)) continue;  // lane pair (K, V) per stage
-        const CUtensorMap* m = (x.k1 - kk <= XA_TAIL) ? kvmap + 1 : kvmap;
-        tma_prefetch_2d(m, 0, ((lane & 1) ? vrow0 : krow0) + x.slab * T_AUDIO + kk);
-      }
-    }
-  }
-}
 
 // One operator of the step schedule.
 // k: 0 LN1 | 1 QKV | 2 self-attention | 3 out | 4 LN2 | 5 cq | 6 cross-attention | 7 cout | 8 LN3 | 9 fc1 | 10 fc2
@@ -1390,7 +1349,6 @@ __global__ void __launch_bounds__(MK_THREADS, 1) dec_step_kernel(const __grid_co
     for (int ph = 0; ph < n_ph; ++ph) {
       int l = ph / 11, k = ph - 11 * l;
       if (l >= p.L) { k = 11 + (ph - 11 * p.L); l = p.L - 1; }
-      if (p.l2pf && warp == MK_WARPS - 1) l2_stage(p, l, k, pos, sy);
       run_op<MT>(p, s_layers, l, k, pos, ring, scratch, red, red_i, sy);
       if (ph + 1 < n_ph || s + 1 < p.n_steps) {
         // the operator after the barrier: (l2, k2)
@@ -1449,24 +1407,6 @@ int dec_xa_prefetch() {
     v = e ? atoi(e) : -1;
   }
   return v >= 0 ? v : 0;
-}
-
-// L2 staging plan (MkParams::l2pf / l2_xa); WXB_DEC_L2PF = mask, WXB_DEC_L2XA = cross K/V stages per CTA
-int dec_l2pf() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("WXB_DEC_L2PF");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
-}
-int dec_l2xa() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("WXB_DEC_L2XA");
-    v = e ? atoi(e) : 24;
-  }
-  return v;
 }
 
 // profiling aid only (results become meaningless): WXB_DEC_SKIP bitmask, see MkParams::skip
@@ -1628,7 +1568,6 @@ int launch_steps(wxb_ctx* ctx, const DecBuffers& buf, int mode, int n_steps, con
   MkParams p = {};
   p.B = B; p.d = d; p.H = D.n_text_head; p.L = D.n_text_layer; p.V = D.n_vocab; p.TX = D.n_text_ctx;
   p.mode = mode; p.n_steps = n_steps; p.skip = dec_skip_mask(); p.xa_pf = dec_xa_prefetch();
-  p.l2pf = dec_l2pf(); p.l2_xa = dec_l2xa();
   { static int ns = -1; if (ns < 0) { const char* e = getenv("WXB_XA_NS"); ns = e ? atoi(e) : 1; } p.xa_ns = ns; }
   p.layers = buf.layers; p.maps = buf.maps;
   p.emb = (const __nv_bfloat16*)wxb_weight(ctx, "dec.emb");
