@@ -46,7 +46,7 @@ constexpr int T_AUDIO = 1500;
 #ifndef WXB_MK_THREADS
 #define WXB_MK_THREADS 384
 #endif
-constexpr int MK_THREADS = WXB_MK_THREADS;  // 12 warps: the attention phases are bound by per-warp dependent chains, so more warps = more throughput
+constexpr int MK_THREADS = WXB_MK_THREADS;  // 12 warps: 11 cross-attention consumer warps, one self-attention round at 1200 units
 constexpr int MK_WARPS = MK_THREADS / 32;
 constexpr int LN_V4 = 2;    // LayerNorm phase: float4 groups per thread, d <= 4 * 2 * 256
 constexpr int GK_MAX = 10;  // largest split-K factor a GEMV plan may use
@@ -54,44 +54,30 @@ constexpr int MAX_LAYERS = 32;
 
 
 // ---- shared-memory plan of the persistent kernel (dynamic, 1024-byte aligned base) -------------------------
-// One region is time-shared by the phases (they never overlap inside a CTA):
-//   GEMV ring        GV_NST stages x (A: 128 weight rows x 64 k bf16 = 16 KB | B: Bp batch rows x 64 k), 128-byte swizzle
-//   cross-attention  K ring: XA_NST stages x (16 XA_CW keys x 64 dims bf16), filled by TMA (128-byte swizzle);
-//                    V rings: XA_CW warps x XA_VD private slots x (16 keys x 128 B), filled by the consumer warps
-//                    themselves with cp.async (same swizzle)
-//   self-attention   per-warp K/V staging
+// One region is time-shared by the two TMA rings (GEMV phases and cross-attention never overlap inside a CTA):
+//   GEMV ring   GV_NST stages x (A: 128 weight rows x 64 k bf16 = 16 KB | B: Bp batch rows x 64 k), 128-byte swizzle
+//   KV ring     XA_NST stages x (K: 112 keys x 64 dims bf16 = 14 KB | V: 14 KB), 128-byte swizzle
 // followed by the attention scratch (warp states of two items, raw q rows of two items).
 constexpr int GV_ROWS = 128;                 // weight rows per tile = UMMA M
 constexpr int GV_BK = 64;                    // k per stage (one 128-byte swizzle row)
 constexpr int GV_A_BYTES = GV_ROWS * GV_BK * 2;
 constexpr int XA_CW = MK_WARPS - 1;          // cross-attention consumer warps (hardware warps 1 ..); warp 0 produces
 constexpr int XA_KEYS = 16 * XA_CW;          // keys per stage: one m16 tile per consumer warp
-constexpr int XA_HALF = XA_KEYS * 128;       // bytes of K per stage
+constexpr int XA_HALF = XA_KEYS * 128;       // bytes of K (or V) per stage
 constexpr int XA_TAIL = MK_WARPS == 8 ? 48 : 96;  // rows of the short TMA box used when at most this many keys of an item remain (1500 = 8 x 176 + 92)
-#ifndef WXB_XA_NST
-#define WXB_XA_NST 6
-#endif
-#ifndef WXB_XA_VD
-#define WXB_XA_VD 3
-#endif
-constexpr int XA_NST = WXB_XA_NST;           // K ring depth
-constexpr int XA_VD = WXB_XA_VD;             // private V slots per consumer warp (V rows are requested XA_VD - 1 stages ahead)
-constexpr int XA_KRING = XA_NST * XA_HALF;
-constexpr int XA_VRING = XA_CW * XA_VD * 2048;
 constexpr int SST_BYTES = (2 * XA_CW * 66 * 4 + 127) & ~127;  // [2 item parities][XA_CW warps][66] floats, padded
 constexpr int QRAW_ROWS = GK_MAX + 1;                     // bias row + up to GK_MAX split-K partial rows of q
 constexpr int QRAW_BYTES = 2 * QRAW_ROWS * 64 * 4;        // two items in flight
 constexpr int SCRATCH_BYTES = SST_BYTES + QRAW_BYTES;     // attention scratch behind the ring
+constexpr int XA_NST = MK_WARPS == 8 ? 6 : 4;  // K/V ring depth (stages of 2 x 16 XA_CW keys x 128 B)
 #ifndef WXB_XA_NS
 #define WXB_XA_NS 1
 #endif
 constexpr int XA_NS = WXB_XA_NS;             // K/V stages per consumer iteration
 constexpr int GV_NST = 6;                    // GEMV ring depth
-constexpr int RING_BYTES = XA_KRING + XA_VRING;
+constexpr int RING_BYTES = XA_NST * 2 * XA_HALF;
 constexpr size_t MK_SMEM = RING_BYTES + SCRATCH_BYTES + 1024;
-static_assert(XA_KRING % 1024 == 0, "the V rings start on a swizzle-atom boundary");
 static_assert(GV_NST * (GV_A_BYTES + 64 * GV_BK * 2) <= RING_BYTES, "GEMV ring must fit the shared region");
-static_assert(MK_SMEM + 6 * 1024 <= 227 * 1024, "dynamic + static shared memory must fit an SM");
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -158,9 +144,7 @@ struct MkParams {
   int B, d, H, L, V, TX;
   int mode;     // 0: no logits (forced prompt token); 1: logits; 2: logits + sampling
   int n_steps;  // consecutive positions decoded by this launch (> 1 only in mode 2)
-  int xa_pf;    // L2 prefetch distance of the cross-attention K/V stream in stages (0 = off)
   int skip;     // profiling aid (WXB_DEC_SKIP): 1 cross-attention, 2 GEMV, 4 self-attention, 8 LayerNorm, 16 cross math, 32 cross merge
-  int xa_ns;    // cross-attention stages per consumer iteration (1 or 2)
   const DecLayerW* layers;  // device array [L]
   const CUtensorMap* maps;  // device array [6 L + 5]
   const __nv_bfloat16* emb;
@@ -531,7 +515,7 @@ __device__ __forceinline__ SelfUnit self_unit_qkv(const MkParams& p, const float
 }
 // online-softmax state of one warp over the cached keys [k_begin, k_end) (and the new key if with_new), merged over
 // the warp's 4 key slots: on return every lane holds m, l and the 8 output dims of its c8
-constexpr int SA_AHEAD = MK_WARPS == 8 ? 4 : 3;  // chunks of 16 keys requested ahead of the one being consumed
+constexpr int SA_AHEAD = MK_WARPS == 8 ? 4 : 2;  // chunks of 16 keys requested ahead of the one being consumed
 constexpr int SA_RING = SA_AHEAD + 1;  // 4 KB chunk slots per warp
 static_assert(MK_WARPS * SA_RING * 4096 <= RING_BYTES, "self-attention staging must fit the TMA ring region");
 __device__ __forceinline__ void self_unit_attend(const SelfUnit& u, const __nv_bfloat16* Kb, const __nv_bfloat16* Vb, int k_begin, int k_end,
@@ -780,7 +764,7 @@ __device__ __forceinline__ void xa_block(const uint32_t (*ka)[4][4], const uint3
 // 7 states once all have arrived (mbarrier) and writes the output.
 __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const float* __restrict__ cq_b, uint8_t* ring,
                                                  float* scratch, MkSync& sy) {
-  constexpr uint32_t STAGE = XA_HALF;  // the TMA ring holds K only
+  constexpr uint32_t STAGE = 2 * XA_HALF;
   float* sst = scratch;                                                                          // [2 item parities][7 warps][66]: m, l, O[64]
   float* qraw = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(scratch) + SST_BYTES);      // [2 item parities][QRAW_ROWS][64]
   const float scale = p.scale;
@@ -832,8 +816,15 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
         const bool tail = (x.k1 - kk <= XA_TAIL);  // keys past the item (or the tensor: zero-filled) are masked by the consumer
         const CUtensorMap* m = tail ? kvmap + 1 : kvmap;
         uint8_t* dst = ring + (size_t)sl * STAGE;
-        mbar_arrive_expect_tx(sy.mb(MB_XA_FULL + sl), tail ? XA_TAIL * 128 : STAGE);
+        mbar_arrive_expect_tx(sy.mb(MB_XA_FULL + sl), tail ? 2 * XA_TAIL * 128 : STAGE);
+        const int slab_ld = (skip & 64) ? (x.slab & 3) : x.slab;  // probe: every CTA streams the same 4 slabs (all L2 hits)
+        if (skip & 64) {
+          tma_load_2d(dst, m, sy.mb(MB_XA_FULL + sl), 0, krow0 + slab_ld * T_AUDIO + kk);
+          tma_load_2d(dst + XA_HALF, m, sy.mb(MB_XA_FULL + sl), 0, vrow0 + slab_ld * T_AUDIO + kk);
+        } else {
         tma_load_2d_hint(dst, m, sy.mb(MB_XA_FULL + sl), 0, krow0 + x.slab * T_AUDIO + kk, L2_EVICT_FIRST);
+        tma_load_2d_hint(dst + XA_HALF, m, sy.mb(MB_XA_FULL + sl), 0, vrow0 + x.slab * T_AUDIO + kk, L2_EVICT_FIRST);
+        }
       }
       __syncwarp();
       ++issued;
@@ -849,44 +840,9 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
     const int cw = warp - 1;
     // ldmatrix lane addressing inside a 112-row x 128-byte swizzled tile (chunk' = chunk ^ (row & 7)); this warp's rows 16 cw ..
     const int rowA = cw * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, chA = lane >> 4;         // K (non-transposed): chunk 2 j + chA
-    const int rowV = (lane & 7) + ((lane >> 4) & 1) * 8, chV = (lane >> 3) & 1;             // V (transposed, private 16-row slot): chunk 2 mt + chV
+    const int rowV = cw * 16 + (lane & 7) + ((lane >> 4) & 1) * 8, chV = (lane >> 3) & 1;   // V (transposed): chunk 2 mt + chV
     const int sw = lane & 7;
     uint32_t consumed = sy.xa_count;
-    // V does not go through the TMA ring.  A single SM's TMA engine sustains only ~39 GB/s from HBM (~58 GB/s on L2 hits,
-    // whatever the ring depth or copy flavour), below this phase's 49 GB/s share of the HBM read ceiling, while plain loads
-    // reach that ceiling with 64 KB in flight.  So K streams through TMA and every consumer warp fetches the 16 V rows IT
-    // will multiply (its own rows of the stage, 2 KB) with cp.async into a private ring of XA_VD slots, XA_VD - 1 stages
-    // ahead along the CTA's work list: two engines in parallel and no barrier on the V path.
-    const uint32_t vring = smem_u32(ring) + XA_KRING + (uint32_t)(cw * XA_VD * 2048);
-    int v_it = 0, v_kk = 0;
-    uint32_t v_cnt = 0, v_used = 0;
-    XaItem vx = {};
-    if (n_items > 0) { vx = xa_item(0, cta, qw, G, P, plen); v_kk = vx.k0; }
-    const __nv_bfloat16* __restrict__ vsrc0 = p.cross_kv + (size_t)vrow0 * 64 + (lane & 7) * 8;  // this lane's 16-byte chunk of a row
-    auto v_issue = [&]() {
-      if (v_it < n_items) {
-        const int key0 = v_kk + cw * 16;
-        if (key0 < vx.k1) {  // warp-uniform
-          const uint32_t dst = vring + (v_cnt % XA_VD) * 2048;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = (lane >> 3) + 4 * i;                 // row of the slot; chunk c = lane & 7 goes to chunk c ^ (r & 7)
-            const int key = min(key0 + r, vx.k1 - 1);          // rows past the item are masked by p = 0: any finite data will do
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + r * 128 + (((lane & 7) ^ (r & 7)) << 4)),
-                         "l"(vsrc0 + ((size_t)vx.slab * T_AUDIO + key) * 64) : "memory");
-          }
-        }
-        v_kk += XA_KEYS;
-        if (v_kk >= vx.k1) {
-          ++v_it;
-          if (v_it < n_items) { vx = xa_item(v_it, cta, qw, G, P, plen); v_kk = vx.k0; }
-        }
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");  // one group per stage, empty or not: the wait below counts groups
-      ++v_cnt;
-    };
-#pragma unroll
-    for (int i = 0; i < XA_VD - 1; ++i) v_issue();
     for (int it = 0; it < n_items; ++it) {
       const XaItem x = xa_item(it, cta, qw, G, P, plen);
       const int b = x.slab / H, h = x.slab - b * H;
@@ -926,7 +882,7 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
       while (kk < x.k1) {
         const int ns = (XA_NS == 2 && kk + XA_KEYS < x.k1) ? 2 : 1;  // warp-uniform
         uint32_t ka[XA_NS][4][4];
-        uint32_t vb[XA_NS];
+        uint32_t vb[XA_NS], slv[XA_NS];
         bool act[XA_NS];
 #pragma unroll
         for (int n = 0; n < XA_NS; ++n) {
@@ -934,17 +890,13 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
           if (n < ns) {
             const uint32_t sl = consumed % XA_NST, par = (consumed / XA_NST) & 1;
             act[n] = kk + n * XA_KEYS + cw * 16 < x.k1;  // warp-uniform: this warp's 16 keys hold at least one key of the item
-            v_issue();  // V rows XA_VD - 1 stages ahead, into the slot read one stage ago
-            vb[n] = vring + (v_used % XA_VD) * 2048;
-            ++v_used;
             mbar_wait(sy.mb(MB_XA_FULL + sl), par);
             const uint32_t kbase = smem_u32(ring + (size_t)sl * STAGE);
+            vb[n] = kbase + XA_HALF; slv[n] = sl;
             if (act[n]) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) ldsm_x4(ka[n][j], kbase + rowA * 128 + (((2 * j + chA) ^ sw) << 4));
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(sy.mb(MB_XA_EMPTY + sl));  // this warp is done reading the K stage
             ++consumed;
           }
         }
@@ -985,15 +937,12 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
           if (n < ns) {
             const bool live = act[n] && m > -INFINITY && !(skip & 16);
             uint32_t va[4][4];
-            // the V rows of this stage have landed: all but the newest XA_VD - 1 groups (+ 1 for the later stage of a pair) are complete
-            if (XA_NS == 2 && n == 0 && ns == 2) asm volatile("cp.async.wait_group %0;" ::"n"(XA_VD) : "memory");
-            else asm volatile("cp.async.wait_group %0;" ::"n"(XA_VD - 1) : "memory");
-            __syncwarp();
             if (live) {
 #pragma unroll
               for (int mt = 0; mt < 4; ++mt) ldsm_x4_t(va[mt], vb[n] + rowV * 128 + (((2 * mt + chV) ^ sw) << 4));
             }
-            __syncwarp();  // the slot is refilled by the whole warp at the next stage
+            __syncwarp();
+            if (lane == 0) mbar_arrive(sy.mb(MB_XA_EMPTY + slv[n]));  // this warp is done reading the stage
             if (live) {
               const float p0 = __expf(sc[n][0] - m), p1 = __expf(sc[n][1] - m);  // -inf -> 0
               lsum += p0 + p1;  // per-quad partial sum (identical in the 4 lanes of a quad)
@@ -1235,7 +1184,7 @@ __device__ __forceinline__ void pre_issue(const MkParams& p, int l, int k, uint8
     }
     sy.pre = n;
   } else if (kind == PH_CROSS && !(p.skip & 1)) {
-    constexpr uint32_t STAGE = XA_HALF;  // the TMA ring holds K only
+    constexpr uint32_t STAGE = 2 * XA_HALF;
     const int G = sy.nc, cta = sy.cta;
     const CUtensorMap* kvmap = p.maps + (size_t)p.L * TM_PER_LAYER + 4;
     const int n_slabs = p.B * p.H, qw = n_slabs / G, r = n_slabs - qw * G;
@@ -1257,8 +1206,9 @@ __device__ __forceinline__ void pre_issue(const MkParams& p, int l, int k, uint8
         const bool tail = (x.k1 - kk <= XA_TAIL);
         const CUtensorMap* m = tail ? kvmap + 1 : kvmap;
         uint8_t* dst = ring + (size_t)sl * STAGE;
-        mbar_arrive_expect_tx(sy.mb(MB_XA_FULL + sl), tail ? XA_TAIL * 128 : STAGE);
+        mbar_arrive_expect_tx(sy.mb(MB_XA_FULL + sl), tail ? 2 * XA_TAIL * 128 : STAGE);
         tma_load_2d_hint(dst, m, sy.mb(MB_XA_FULL + sl), 0, krow0 + x.slab * T_AUDIO + kk, L2_EVICT_FIRST);
+        tma_load_2d_hint(dst + XA_HALF, m, sy.mb(MB_XA_FULL + sl), 0, vrow0 + x.slab * T_AUDIO + kk, L2_EVICT_FIRST);
       }
       ++it;
     }
@@ -1398,16 +1348,6 @@ struct DecBuffers {
   const CUtensorMap* maps;
   int B, tok_stride;
 };
-
-// tuning aid: WXB_XA_PF overrides the L2 prefetch distance of the cross-attention stream
-int dec_xa_prefetch() {
-  static int v = -2;
-  if (v == -2) {
-    const char* e = getenv("WXB_XA_PF");
-    v = e ? atoi(e) : -1;
-  }
-  return v >= 0 ? v : 0;
-}
 
 // profiling aid only (results become meaningless): WXB_DEC_SKIP bitmask, see MkParams::skip
 int dec_skip_mask() {
@@ -1567,8 +1507,7 @@ int launch_steps(wxb_ctx* ctx, const DecBuffers& buf, int mode, int n_steps, con
   const int G = ctx->sm_count;
   MkParams p = {};
   p.B = B; p.d = d; p.H = D.n_text_head; p.L = D.n_text_layer; p.V = D.n_vocab; p.TX = D.n_text_ctx;
-  p.mode = mode; p.n_steps = n_steps; p.skip = dec_skip_mask(); p.xa_pf = dec_xa_prefetch();
-  { static int ns = -1; if (ns < 0) { const char* e = getenv("WXB_XA_NS"); ns = e ? atoi(e) : 1; } p.xa_ns = ns; }
+  p.mode = mode; p.n_steps = n_steps; p.skip = dec_skip_mask();
   p.layers = buf.layers; p.maps = buf.maps;
   p.emb = (const __nv_bfloat16*)wxb_weight(ctx, "dec.emb");
   p.pos_emb = (const float*)wxb_weight(ctx, "dec.pos");
