@@ -147,7 +147,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // (producer and issuer warps run converged, one elect.sync lane issues: under a divergent `lane == 0` branch ptxas
+    //  wraps every TMA / tcgen05 instruction in an ELECT + R2UR + branch sequence of ~14 instructions)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = first; tile < num_tiles; tile += step) {
@@ -156,22 +158,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(empty_bar + stage, phase ^ 1);
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
-          if (PAIR) {
-            if (rank == 0) mbar_arrive_expect_tx(full_bar + stage, 2 * L::STAGE_BYTES);  // both CTAs' tiles
-            tma_load_2d_pair(sa, &tmA, full_bar + stage, kb * BK, m_blk * BM);
-            tma_load_2d_pair(sb, &tmB, full_bar + stage, kb * BK, n_blk * BN + rank * (BN / 2));
-          } else {
-            mbar_arrive_expect_tx(full_bar + stage, L::STAGE_BYTES);
-            tma_load_2d(sa, &tmA, full_bar + stage, kb * BK, m_blk * BM);
-            tma_load_2d(sb, &tmB, full_bar + stage, kb * BK, n_blk * BN);
+          if (elect_one()) {
+            if (PAIR) {
+              if (rank == 0) mbar_arrive_expect_tx(full_bar + stage, 2 * L::STAGE_BYTES);  // both CTAs' tiles
+              tma_load_2d_pair(sa, &tmA, full_bar + stage, kb * BK, m_blk * BM);
+              tma_load_2d_pair(sb, &tmB, full_bar + stage, kb * BK, n_blk * BN + rank * (BN / 2));
+            } else {
+              mbar_arrive_expect_tx(full_bar + stage, L::STAGE_BYTES);
+              tma_load_2d(sa, &tmA, full_bar + stage, kb * BK, m_blk * BM);
+              tma_load_2d(sb, &tmB, full_bar + stage, kb * BK, n_blk * BN);
+            }
           }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
       // instruction descriptor: D=f32 (bit 4), A=bf16 (bit 7), B=bf16 (bit 10), K-major A and B,
       // N>>3 at bit 17, M>>4 at bit 24 (M = 256 for the pair's MMA)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((PAIR ? 2 * BM : BM) >> 4) << 24);
@@ -189,18 +194,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
           const uint64_t adesc = make_sw128_desc(sa);
           const uint64_t bdesc = make_sw128_desc(sa + L::A_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
-            if (PAIR) tc_mma_bf16_pair(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-            else tc_mma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (addr >> 4) field
+              if (PAIR) tc_mma_bf16_pair(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+              else tc_mma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            }
+            if (PAIR) tc_commit_pair(empty_bar + stage);  // frees the slot in both CTAs
+            else tc_commit(empty_bar + stage);
+            if (kb == p.num_k_blocks - 1) {
+              if (PAIR) tc_commit_pair(tfull_bar + acc);  // both CTAs' epilogues read their 128 rows of the accumulator
+              else tc_commit(tfull_bar + acc);
+            }
           }
-          if (PAIR) tc_commit_pair(empty_bar + stage);  // frees the slot in both CTAs
-          else tc_commit(empty_bar + stage);
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (PAIR) tc_commit_pair(tfull_bar + acc);  // both CTAs' epilogues read their 128 rows of the accumulator
-        else tc_commit(tfull_bar + acc);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
