@@ -164,7 +164,7 @@ v_transpose_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
 }
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const AttnTcParams p) {
   extern __shared__ uint8_t at_smem_raw[];
   uint8_t* smem = at_smem_raw + ((1024u - (smem_u32(at_smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -182,7 +182,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
 
   if (warp == 8 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQK)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmV)) : "memory");
   }
   if (warp == 9 && lane == 0) {
     mbar_init(q_full, 1);
@@ -213,14 +212,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
         mbar_wait(kv_empty + st, ((j >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(kv_full + st, K_BYTES + V_BYTES);
         tma_load_2d(smem + OFF_K + st * K_BYTES, &tmQK, kv_full + st, p.d + h * 64, row0 + j * BKV);
-        tma_load_2d(smem + OFF_V + st * V_BYTES, &tmV, kv_full + st, j * BKV, (b * p.H + h) * 64);
-        tma_load_2d(smem + OFF_V + st * V_BYTES + VB_BYTES, &tmV, kv_full + st, j * BKV + 64, (b * p.H + h) * 64);
+        // V rows exactly as they sit in qkv ([key][64 dims], 128-byte swizzle): the PV product reads the tile as an
+        // MN-major B operand, so no transposed copy of V exists (keys past T are masked by p = 0; they hold finite data
+        // of the next chunk, or zeros past the tensor)
+        tma_load_2d(smem + OFF_V + st * V_BYTES, &tmQK, kv_full + st, 2 * p.d + h * 64, row0 + j * BKV);
       }
     }
   } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      const uint32_t idescS = make_idesc_bf16(128, 128), idescO = make_idesc_bf16(128, 64);
+      const uint32_t idescS = make_idesc_bf16(128, 128), idescO = make_idesc_bf16(128, 64) | (1u << 16);  // B = V is MN-major
       auto issue_S = [&](int t, int j) {  // S_t(j) = Q_t K_j^T
         const uint64_t adesc = make_sw128_desc(smem_u32(smem + OFF_Q + t * Q_BYTES));
         const uint64_t bdesc = make_sw128_desc(smem_u32(smem + OFF_K + (j & 1) * K_BYTES));
@@ -242,10 +243,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_const
 #pragma unroll
           for (int kb2 = 0; kb2 < 2; ++kb2) {
             const uint64_t adesc = make_sw128_desc(smem_u32(smem + OFF_P + t * P_BYTES + kb2 * PB_BYTES));
+            // MN-major B: 8-key groups 1024 B apart (SBO), one K = 16 step = 16 keys = 2048 B further into the tile
             const uint64_t bdesc = make_sw128_desc(smem_u32(smem + OFF_V + st * V_BYTES + kb2 * VB_BYTES));
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              tc_mma_bf16(tmem_base + TM_O + t * 64, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idescO, (j | kb2 | k) != 0);
+              tc_mma_bf16(tmem_base + TM_O + t * 64, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * (2048 >> 4)), idescO, (j | kb2 | k) != 0);
           }
           tc_commit(pv_done + t);
           if (t == 1) tc_commit(kv_empty + st);  // S_A, S_B, PV_A, PV_B of this stage are all behind this commit
@@ -385,12 +387,10 @@ int wxb_make_tmap_bf16(wxb_ctx* ctx, CUtensorMap* tm, const void* base, uint64_t
 int wxb_attention_tc(wxb_ctx* ctx, const __nv_bfloat16* qkv, __nv_bfloat16* vT, __nv_bfloat16* out, int B, int T, int d, int H,
                      cudaStream_t st) {
   const int Tpad = (T + 7) & ~7;
-  v_transpose_kernel<<<dim3(ceil_div(Tpad, 64), H, B), 256, 0, st>>>(qkv, vT, T, Tpad, d, H);
-  WXB_LAUNCH_CHECK(ctx);
-  CUtensorMap tmQK, tmV;
+  (void)vT;  // no transposed copy of V any more (kept in the signature for the callers' workspace layout)
+  CUtensorMap tmQK;
   int rc;
   if ((rc = wxb_make_tmap_bf16(ctx, &tmQK, qkv, (uint64_t)3 * d, (uint64_t)B * T, (uint64_t)3 * d * 2, 64, 128)) != WXB_OK) return rc;
-  if ((rc = wxb_make_tmap_bf16(ctx, &tmV, vT, (uint64_t)Tpad, (uint64_t)B * H * 64, (uint64_t)Tpad * 2, 64, 64)) != WXB_OK) return rc;
   static bool attr = false;
   if (!attr) {
     WXB_CUDA(ctx, cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
@@ -400,7 +400,7 @@ int wxb_attention_tc(wxb_ctx* ctx, const __nv_bfloat16* qkv, __nv_bfloat16* vT, 
   p.T = T; p.Tpad = Tpad; p.d = d; p.H = H; p.n_kv_tiles = ceil_div(T, BKV);
   p.scale_log2 = (1.0f / sqrtf(64.f)) * 1.44269504088896341f;
   p.out = out;
-  attention_tc_kernel<<<dim3(ceil_div(T, 2 * BQ), H, B), AT_THREADS, AT_SMEM, st>>>(tmQK, tmV, p);
+  attention_tc_kernel<<<dim3(ceil_div(T, 2 * BQ), H, B), AT_THREADS, AT_SMEM, st>>>(tmQK, p);
   WXB_LAUNCH_CHECK(ctx);
   return WXB_OK;
 }
