@@ -220,15 +220,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const AttnTcParams
     }
   } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // (the warp runs converged and one elect.sync lane issues: under a divergent `lane == 0` branch ptxas wraps every
+    //  tcgen05 instruction in an ELECT + 5 x R2UR + branch sequence, ~14 instructions per product)
+    {
       const uint32_t idescS = make_idesc_bf16(128, 128), idescO = make_idesc_bf16(128, 64) | (1u << 16);  // B = V is MN-major
       auto issue_S = [&](int t, int j) {  // S_t(j) = Q_t K_j^T
         const uint64_t adesc = make_sw128_desc(smem_u32(smem + OFF_Q + t * Q_BYTES));
         const uint64_t bdesc = make_sw128_desc(smem_u32(smem + OFF_K + (j & 1) * K_BYTES));
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tc_mma_bf16(tmem_base + TM_S + t * 128, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idescS, k != 0);
-        tc_commit(s_full + t);
+          for (int k = 0; k < 4; ++k)
+            tc_mma_bf16(tmem_base + TM_S + t * 128, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idescS, k != 0);
+          tc_commit(s_full + t);
+        }
+        __syncwarp();
       };
       mbar_wait(q_full, 0);
       mbar_wait(kv_full + 0, 0);
@@ -240,6 +245,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const AttnTcParams
         for (int t = 0; t < 2; ++t) {
           mbar_wait(p_full + t, j & 1);
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
           for (int kb2 = 0; kb2 < 2; ++kb2) {
             const uint64_t adesc = make_sw128_desc(smem_u32(smem + OFF_P + t * P_BYTES + kb2 * PB_BYTES));
@@ -251,6 +257,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const AttnTcParams
           }
           tc_commit(pv_done + t);
           if (t == 1) tc_commit(kv_empty + st);  // S_A, S_B, PV_A, PV_B of this stage are all behind this commit
+          }
+          __syncwarp();
           if (j + 1 < n) {
             if (t == 0) {
               mbar_wait(kv_full + ((j + 1) & 1), ((j + 1) >> 1) & 1);
