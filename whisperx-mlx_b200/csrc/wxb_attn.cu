@@ -33,7 +33,10 @@ constexpr int OFF_V = OFF_K + 2 * K_BYTES;
 constexpr int OFF_P = OFF_V + 2 * V_BYTES;
 constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;  // 163840
 constexpr int AT_SMEM = OFF_BAR + 16 * 8 + 16 + 1024;
-constexpr int TM_S = 0, TM_O = 256;           // TMEM columns: S_A, S_B at 0 / 128, O_A, O_B at 256 / 320
+constexpr int TM_S = 0, TM_O = 256, TM_P = 384;  // TMEM columns: S_A, S_B at 0 / 128, O_A, O_B at 256 / 320, P_A, P_B (bf16 pairs) at 384 / 448
+#ifndef WXB_ATTN_P_TMEM
+#define WXB_ATTN_P_TMEM 1
+#endif
 constexpr float RESCALE_LOG2 = 8.f;           // move the softmax offset only when the row max grew by more than 2^8
 
 struct AttnTcParams {
@@ -54,6 +57,16 @@ __device__ __forceinline__ void tc_st_32x32(uint32_t taddr, const uint32_t* v) {
       : "memory");
 }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (lane = row, one 32-bit column = two consecutive bf16 along K) never
+// passes through shared memory, so the product is not paced by the 128 A-row reads of the shared-memory form
+__device__ __forceinline__ void tc_mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
 
 // ---- packed fp32 pairs (sm_100 FFMA2 / FADD2), 3-input max, bare MUFU.EX2 -------------------------------------------
 __device__ __forceinline__ uint64_t pack2(float a, float b) {
@@ -89,7 +102,7 @@ __device__ __forceinline__ float ex2(float x) {
 // 2^f by a degree-3 minimax polynomial on [-0.5, 0.5] (relative error 1e-4, far below the bf16 rounding of P),
 // 2^n by adding n to the exponent field.
 template <bool FULL>
-__device__ __forceinline__ float exp_block64(const uint32_t* sv, int col0, int valid, float sl, float off, uint8_t* prow_blk, int r) {
+__device__ __forceinline__ float exp_block64(const uint32_t* sv, int col0, int valid, float sl, float off, uint8_t* prow_blk, int r, uint32_t p_taddr) {
   const uint64_t sl2 = pack2(sl, sl), noff2 = pack2(-off, -off);
   const uint64_t magic2 = pack2(12582912.f, 12582912.f), nmagic2 = pack2(-12582912.f, -12582912.f), neg1 = pack2(-1.f, -1.f);
   const uint64_t c3 = pack2(0.05500893f, 0.05500893f), c2 = pack2(0.24221097f, 0.24221097f), c1 = pack2(0.69328293f, 0.69328293f);
@@ -128,9 +141,13 @@ __device__ __forceinline__ float exp_block64(const uint32_t* sv, int col0, int v
     __nv_bfloat162 h2 = __floats2bfloat162_rn(p0, p1);
     pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h2);
   }
+#if WXB_ATTN_P_TMEM
+  tc_st_32x32(p_taddr, pk);  // 32 columns = this row's 64 probabilities as bf16 pairs
+#else
 #pragma unroll
   for (int ch = 0; ch < 8; ++ch)
     *reinterpret_cast<uint4*>(prow_blk + ((ch ^ (r & 7)) << 4)) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+#endif
   float a0, a1;
   unpack2(acc, a0, a1);
   return a0 + a1;
@@ -252,8 +269,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const AttnTcParams
             // MN-major B: 8-key groups 1024 B apart (SBO), one K = 16 step = 16 keys = 2048 B further into the tile
             const uint64_t bdesc = make_sw128_desc(smem_u32(smem + OFF_V + st * V_BYTES + kb2 * VB_BYTES));
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
+            for (int k = 0; k < 4; ++k) {
+#if WXB_ATTN_P_TMEM
+              (void)adesc;  // P comes from TMEM: 8 columns (16 keys) per step
+              tc_mma_bf16_ts(tmem_base + TM_O + t * 64, tmem_base + TM_P + t * 64 + kb2 * 32 + k * 8, bdesc + (uint64_t)(k * (2048 >> 4)), idescO, (j | kb2 | k) != 0);
+#else
               tc_mma_bf16(tmem_base + TM_O + t * 64, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * (2048 >> 4)), idescO, (j | kb2 | k) != 0);
+#endif
+            }
           }
           tc_commit(pv_done + t);
           if (t == 1) tc_commit(kv_empty + st);  // S_A, S_B, PV_A, PV_B of this stage are all behind this commit
@@ -276,6 +299,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const AttnTcParams
     const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
     const uint32_t s_addr = tmem_base + lane_addr + TM_S + t * 128;
     const uint32_t o_addr = tmem_base + lane_addr + TM_O + t * 64;
+    const uint32_t p_addr = tmem_base + lane_addr + TM_P + t * 64;
     const float sl = p.scale_log2;
     float m_used = -INFINITY, m_run = -INFINITY, l_run = 0.f;
     uint8_t* prow = smem + OFF_P + t * P_BYTES + r * 128;
@@ -334,19 +358,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const AttnTcParams
       float rowsum;
       const bool full = valid >= BKV;
       // keys 64..127 -> P block 1
-      rowsum = full ? exp_block64<true>(hi, 64, valid, sl, off, prow + PB_BYTES, r) : exp_block64<false>(hi, 64, valid, sl, off, prow + PB_BYTES, r);
+      rowsum = full ? exp_block64<true>(hi, 64, valid, sl, off, prow + PB_BYTES, r, p_addr + 32) : exp_block64<false>(hi, 64, valid, sl, off, prow + PB_BYTES, r, p_addr + 32);
       // keys 0..63 -> P block 0
       {
         uint32_t lo[64];
         tc_ld_32x32(s_addr, lo);
         tc_ld_32x32(s_addr + 32, lo + 32);
         tc_wait_ld();
-        rowsum += full ? exp_block64<true>(lo, 0, valid, sl, off, prow, r) : exp_block64<false>(lo, 0, valid, sl, off, prow, r);
+        rowsum += full ? exp_block64<true>(lo, 0, valid, sl, off, prow, r, p_addr) : exp_block64<false>(lo, 0, valid, sl, off, prow, r, p_addr);
       }
       l_run += rowsum;
-      // S_t(j) fully read, O_t consistent, P_t(j) written: publish to the tensor core (async proxy)
+      // S_t(j) fully read, O_t consistent, P_t(j) written: publish to the tensor core
+#if WXB_ATTN_P_TMEM
+      tc_wait_st();
+      tc_fence_before();
+#else
       tc_fence_before();
       fence_proxy_async();
+#endif
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full + t);
     }
