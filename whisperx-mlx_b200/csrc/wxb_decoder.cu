@@ -69,7 +69,7 @@ constexpr int SST_BYTES = (2 * XA_CW * 66 * 4 + 127) & ~127;  // [2 item paritie
 constexpr int QRAW_ROWS = GK_MAX + 1;                     // bias row + up to GK_MAX split-K partial rows of q
 constexpr int QRAW_BYTES = 2 * QRAW_ROWS * 64 * 4;        // two items in flight
 constexpr int SCRATCH_BYTES = SST_BYTES + QRAW_BYTES;     // attention scratch behind the ring
-constexpr int XA_NST = MK_WARPS == 8 ? 6 : 4;  // K/V ring depth (stages of 2 x 16 XA_CW keys x 128 B)
+constexpr int XA_NST = MK_WARPS == 8 ? 6 : MK_WARPS == 10 ? 5 : 4;  // K/V ring depth (stages of 2 x 16 XA_CW keys x 128 B)
 #ifndef WXB_XA_NS
 #define WXB_XA_NS 1
 #endif
@@ -92,7 +92,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // operator that does not depend on this one (requesting its weight / K/V tiles), so that HBM latency is spent
 // while the barrier completes.  With `prof` set, CTA 0 records the global timer at every barrier exit.
 template <class Pre>
-__device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& target, int nc, int cta, unsigned long long* prof, int& prof_n, Pre pre) {
+__device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& target, int nc, int cta, unsigned long long* prof, Pre pre) {
   __syncthreads();
   if (threadIdx.x == 0) {
     target += (unsigned)nc;
@@ -107,12 +107,11 @@ __device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& target, int n
     if (prof && cta == 0) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      prof[prof_n] = t;
+      prof[target / (unsigned)nc - 1u] = t;  // barrier index within the launch
     }
   } else if (threadIdx.x == 32) {
     pre();
   }
-  ++prof_n;
   __syncthreads();
 }
 
@@ -144,7 +143,8 @@ struct MkParams {
   int B, d, H, L, V, TX;
   int mode;     // 0: no logits (forced prompt token); 1: logits; 2: logits + sampling
   int n_steps;  // consecutive positions decoded by this launch (> 1 only in mode 2)
-  int skip;     // profiling aid (WXB_DEC_SKIP): 1 cross-attention, 2 GEMV, 4 self-attention, 8 LayerNorm, 16 cross math, 32 cross merge
+  int skip;     // profiling aid (WXB_DEC_SKIP): 1 cross-attention, 2 GEMV, 4 self-attention, 8 LayerNorm, 16 cross math, 32 cross merge,
+                //   64 every CTA streams the same 4 K/V slabs (all L2 hits)
   const DecLayerW* layers;  // device array [L]
   const CUtensorMap* maps;  // device array [6 L + 5]
   const __nv_bfloat16* emb;
@@ -188,8 +188,6 @@ struct MkSync {
   uint32_t bars;       // shared-memory address of the barrier array
   uint32_t gv_count;   // GEMV stages issued so far (slot = count % GV_NST, parity = (count / GV_NST) & 1)
   uint32_t acc_count;  // accumulator hand-offs so far
-  uint32_t xa_count;   // KV stages issued so far
-  uint32_t xa_items;   // cross-attention work items finished so far
   uint32_t tmem;       // TMEM base address (64 fp32 columns x 128 lanes)
   int pre;             // thread 0: stages of the coming operator already requested before the barrier wait (grid_sync)
   int cta, nc;         // this CTA's index within its group, CTAs per group
@@ -252,14 +250,14 @@ __device__ __forceinline__ void ln_phase(const MkParams& p, bool from_embed, int
           const float4 bb = __ldg(reinterpret_cast<const float4*>(prev_bias) + c4);
           a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
 #pragma unroll
-          for (int k0 = 0; k0 < GK_MAX; k0 += 8) {
+          for (int k0 = 0; k0 < GK_MAX; k0 += 5) {
             if (k0 < gk) {
-              float4 pp[8];
+              float4 pp[5];
 #pragma unroll
-              for (int ks = 0; ks < 8; ++ks)
+              for (int ks = 0; ks < 5; ++ks)
                 if (k0 + ks < gk) pp[ks] = __ldcg(reinterpret_cast<const float4*>(p.part + ((size_t)(k0 + ks) * p.B + b) * d) + c4);
 #pragma unroll
-              for (int ks = 0; ks < 8; ++ks)
+              for (int ks = 0; ks < 5; ++ks)
                 if (k0 + ks < gk) { a.x += pp[ks].x; a.y += pp[ks].y; a.z += pp[ks].z; a.w += pp[ks].w; }
             }
           }
@@ -380,7 +378,9 @@ __device__ __forceinline__ void gemv_phase(const MkParams& p, const MkGemv& g, c
     tc_fence_after();
     // ---- epilogue: warp w reads TMEM lanes 32 (w & 3) .. +31 (weight rows), 16-column groups j = w >> 2, + 2, .. ----
     const int n = row0 + (warp & 3) * 32 + lane;
-    for (int j = warp >> 2; j < MT; j += MK_WARPS / 4) {
+    // whole groups of 4 warps (one per TMEM lane quarter) share the 16-column groups; the warps of an incomplete last group skip
+    constexpr int EPI_GROUPS = MK_WARPS / 4;
+    for (int j = (warp >> 2) < EPI_GROUPS ? (warp >> 2) : MT; j < MT; j += EPI_GROUPS) {
       uint32_t v[16];
       tc_ld_32x32_x16(sy.tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(j * 16), v);
       tc_wait_ld();
@@ -515,7 +515,7 @@ __device__ __forceinline__ SelfUnit self_unit_qkv(const MkParams& p, const float
 }
 // online-softmax state of one warp over the cached keys [k_begin, k_end) (and the new key if with_new), merged over
 // the warp's 4 key slots: on return every lane holds m, l and the 8 output dims of its c8
-constexpr int SA_AHEAD = MK_WARPS == 8 ? 4 : 2;  // chunks of 16 keys requested ahead of the one being consumed
+constexpr int SA_AHEAD = MK_WARPS == 8 ? 4 : MK_WARPS == 10 ? 3 : 2;  // chunks of 16 keys requested ahead of the one being consumed
 constexpr int SA_RING = SA_AHEAD + 1;  // 4 KB chunk slots per warp
 static_assert(MK_WARPS * SA_RING * 4096 <= RING_BYTES, "self-attention staging must fit the TMA ring region");
 __device__ __forceinline__ void self_unit_attend(const SelfUnit& u, const __nv_bfloat16* Kb, const __nv_bfloat16* Vb, int k_begin, int k_end,
@@ -702,6 +702,17 @@ __device__ __forceinline__ XaItem xa_item(int it, int cta, int qw, int G, int P,
   }
   return x;
 }
+// K/V stages of CTA `cta`'s work list in one cross-attention phase.  Every phase of a launch has the same list, so the
+// ring and item cursors of phase number xq (cross-attention phases completed since the kernel started) are xq times the
+// per-phase counts: they are recomputed at the start of a phase instead of living in registers across all the others.
+__device__ __forceinline__ uint32_t xa_stage_count(int cta, int qw, int G, int P, int plen, int n_items) {
+  uint32_t n_st = (uint32_t)qw * ((T_AUDIO + XA_KEYS - 1) / XA_KEYS);
+  for (int it = qw; it < n_items; ++it) {
+    const XaItem x = xa_item(it, cta, qw, G, P, plen);
+    n_st += (uint32_t)((x.k1 - x.k0 + XA_KEYS - 1) / XA_KEYS);
+  }
+  return n_st;
+}
 // bf16 hi / lo split of two floats, packed for an MMA B fragment: sel 0 -> (hi(x), hi(y)), 1 -> (lo(x), lo(y)), else 0.
 // Branch-free (sel differs between the lanes of a warp).
 __device__ __forceinline__ uint32_t split_pack(float x, float y, int sel) {
@@ -762,7 +773,7 @@ __device__ __forceinline__ void xa_block(const uint32_t (*ka)[4][4], const uint3
 // partials of the cq GEMV) of the next items, every consumer warp sums them for itself, deposits its (m, l, O) state of
 // a finished item in a double-buffered shared-memory slot and moves straight on; consumer warp (item % 7) merges the
 // 7 states once all have arrived (mbarrier) and writes the output.
-__device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const float* __restrict__ cq_b, uint8_t* ring,
+__device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, int xq, const float* __restrict__ cq_b, uint8_t* ring,
                                                  float* scratch, MkSync& sy) {
   constexpr uint32_t STAGE = 2 * XA_HALF;
   float* sst = scratch;                                                                          // [2 item parities][7 warps][66]: m, l, O[64]
@@ -785,16 +796,17 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
     P = (T_AUDIO + plen - 1) / plen;
   }
   const int n_items = qw + ((r > 0 && cta < r * P) ? ((r * P - 1 - cta) / G + 1) : 0);
+  const uint32_t xa_count0 = (uint32_t)xq * xa_stage_count(cta, qw, G, P, plen, n_items), xa_items0 = (uint32_t)xq * (uint32_t)n_items;
   if (warp == 0) {
     // ------------------------------- producer warp -------------------------------
     int it = 0, kk = 0;  // load cursor
     XaItem x = {};
     if (n_items > 0) { x = xa_item(0, cta, qw, G, P, plen); kk = x.k0; }
-    uint32_t issued = sy.xa_count;
+    uint32_t issued = xa_count0;
     auto stage_q = [&](int qi) {
       // raw q rows of item qi (row gk = bias, rows 0 .. gk-1 = split-K partials of the cq GEMV), 2 rows per pass
       const XaItem xq = xa_item(qi, cta, qw, G, P, plen);
-      const uint32_t gi = sy.xa_items + (uint32_t)qi, qpar = gi & 1;
+      const uint32_t gi = xa_items0 + (uint32_t)qi, qpar = gi & 1;
       mbar_wait(sy.mb(MB_Q_FREE + qpar), ((gi >> 1) & 1) ^ 1);  // the consumers have used the rows of item gi - 2
       float* dst = qraw + qpar * (QRAW_ROWS * 64);
       const int b = xq.slab / H, h = xq.slab - b * H;
@@ -810,7 +822,7 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
     };
     while (it < n_items) {
       if (kk == x.k0) stage_q(it);  // first stage of an item: its raw q rows
-      if (lane == 0 && (int)(issued - sy.xa_count) >= sy.pre) {  // the first sy.pre stages were requested before the barrier wait
+      if (lane == 0 && (int)(issued - xa_count0) >= sy.pre) {  // the first sy.pre stages were requested before the barrier wait
         const uint32_t sl = issued % XA_NST, par = (issued / XA_NST) & 1;
         mbar_wait(sy.mb(MB_XA_EMPTY + sl), par ^ 1);
         const bool tail = (x.k1 - kk <= XA_TAIL);  // keys past the item (or the tensor: zero-filled) are masked by the consumer
@@ -842,11 +854,11 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
     const int rowA = cw * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, chA = lane >> 4;         // K (non-transposed): chunk 2 j + chA
     const int rowV = cw * 16 + (lane & 7) + ((lane >> 4) & 1) * 8, chV = (lane >> 3) & 1;   // V (transposed): chunk 2 mt + chV
     const int sw = lane & 7;
-    uint32_t consumed = sy.xa_count;
+    uint32_t consumed = xa_count0;
     for (int it = 0; it < n_items; ++it) {
       const XaItem x = xa_item(it, cta, qw, G, P, plen);
       const int b = x.slab / H, h = x.slab - b * H;
-      const uint32_t gi = sy.xa_items + (uint32_t)it;  // items since kernel start: parity and phase of the double-buffered slots
+      const uint32_t gi = xa_items0 + (uint32_t)it;  // items since kernel start: parity and phase of the double-buffered slots
       const uint32_t ipar = gi & 1, iph = (gi >> 1) & 1;
       // scaled q = (bias + split-K partials in slice order) * scale; lane holds dims lane and lane + 32
       mbar_wait(sy.mb(MB_Q_FULL + ipar), iph);
@@ -1029,16 +1041,6 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, const
       }
     }
   }
-  // every thread advances the uniform cursors by this CTA's work list
-  {
-    uint32_t n_st = (uint32_t)qw * ((T_AUDIO + XA_KEYS - 1) / XA_KEYS);
-    for (int it = qw; it < n_items; ++it) {
-      const XaItem x = xa_item(it, cta, qw, G, P, plen);
-      n_st += (uint32_t)((x.k1 - x.k0 + XA_KEYS - 1) / XA_KEYS);
-    }
-    sy.xa_count += n_st;
-    sy.xa_items += (uint32_t)n_items;
-  }
 }
 
 // mlx_whisper_batch_decoder.py:267-303 for one row per CTA: (no_speech_prob from the unfiltered logits,)
@@ -1164,7 +1166,7 @@ __device__ __forceinline__ GemvOp gemv_op(const MkParams& p, int l, int k) {
 // cross-attention phase.  Every thread calls this and learns the number of stages (sy.pre, skipped by the producer
 // loops of those phases); only `issue` threads touch the barriers and the TMA unit.
 template <int MT>
-__device__ __forceinline__ void pre_issue(const MkParams& p, int l, int k, uint8_t* ring, MkSync& sy, const bool issue) {
+__device__ __forceinline__ void pre_issue(const MkParams& p, int l, int k, int xq, uint8_t* ring, MkSync& sy, const bool issue) {
   const int kind = op_kind(k);
   sy.pre = 0;
   if (kind == PH_GEMV && !(p.skip & 2)) {
@@ -1196,12 +1198,13 @@ __device__ __forceinline__ void pre_issue(const MkParams& p, int l, int k, uint8
       P = (T_AUDIO + plen - 1) / plen;
     }
     const int n_items = qw + ((r > 0 && cta < r * P) ? ((r * P - 1 - cta) / G + 1) : 0);
+    const uint32_t xa_count0 = (uint32_t)xq * xa_stage_count(cta, qw, G, P, plen, n_items);
     int it = 0, n = 0;
     while (it < n_items && n < XA_NST) {
       const XaItem x = xa_item(it, cta, qw, G, P, plen);
       for (int kk = x.k0; kk < x.k1 && n < XA_NST; kk += XA_KEYS, ++n) {
         if (!issue) continue;
-        const uint32_t c = sy.xa_count + (uint32_t)n, sl = c % XA_NST, par = (c / XA_NST) & 1;
+        const uint32_t c = xa_count0 + (uint32_t)n, sl = c % XA_NST, par = (c / XA_NST) & 1;
         mbar_wait(sy.mb(MB_XA_EMPTY + sl), par ^ 1);
         const bool tail = (x.k1 - kk <= XA_TAIL);
         const CUtensorMap* m = tail ? kvmap + 1 : kvmap;
@@ -1221,12 +1224,17 @@ __device__ __forceinline__ void pre_issue(const MkParams& p, int l, int k, uint8
 // k: 0 LN1 | 1 QKV | 2 self-attention | 3 out | 4 LN2 | 5 cq | 6 cross-attention | 7 cout | 8 LN3 | 9 fc1 | 10 fc2
 //    11 final LN | 12 logits | 13 (no_speech_prob,) filters + sampling
 template <int MT>
-__device__ __forceinline__ void run_op(const MkParams& p, const DecLayerW* s_layers, int l, int k, int pos, uint8_t* ring,
+__device__ __forceinline__ void run_op(const MkParams& p, const DecLayerW* s_layers, int l, int k, int pos, int xq, uint8_t* ring,
                                        float* scratch, float* red, int* red_i, MkSync& sy) {
   const DecLayerW& w = s_layers[l];
   const int kind = op_kind(k);
+#ifdef WXB_STUB
+  constexpr int stub = WXB_STUB;
+#else
+  constexpr int stub = 0;
+#endif
   if (kind == PH_LN) {
-    if (!(p.skip & 8)) {
+    if (!(stub & 8) && !(p.skip & 8)) {
       // the LayerNorm phase first folds the previous GEMV's split-K partials (+ bias) into the residual row
       const bool from_embed = (k == 0 && l == 0);
       const int gk = (k == 0 || k == 11) ? p.g_fc2.gk : p.g_dd.gk;
@@ -1236,16 +1244,16 @@ __device__ __forceinline__ void run_op(const MkParams& p, const DecLayerW* s_lay
       ln_phase(p, from_embed, gk, pb, lw, lb, pos, red, sy);
     }
   } else if (kind == PH_GEMV) {
-    if (!(p.skip & 2)) {
+    if (!(stub & 2) && !(p.skip & 2)) {
       const GemvOp o = gemv_op(p, l, k);
       gemv_phase<MT>(p, *o.g, o.wm, o.xm, w.fc1_b, o.epi, ring, sy);
     }
   } else if (kind == PH_SELF) {
-    if (!(p.skip & 4)) self_attn_phase(p, l, w.qkv_b, pos, ring, scratch, sy);
+    if (!(stub & 4) && !(p.skip & 4)) self_attn_phase(p, l, w.qkv_b, pos, ring, scratch, sy);
   } else if (kind == PH_CROSS) {
-    if (!(p.skip & 1)) cross_attn_phase(p, l, w.cq_b, ring, scratch, sy);
+    if (!(stub & 1) && !(p.skip & 1)) cross_attn_phase(p, l, xq, w.cq_b, ring, scratch, sy);
   } else {
-    sample_phase(p.sp, p.B, pos, p.mode == 2, red, red_i, sy);
+    if (!(stub & 16)) sample_phase(p.sp, p.B, pos, p.mode == 2, red, red_i, sy);
   }
 }
 
@@ -1272,7 +1280,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) dec_step_kernel(const __grid_co
   const int warp = threadIdx.x >> 5;
   MkSync sy;
   sy.bars = smem_u32(bars);
-  sy.gv_count = 0; sy.acc_count = 0; sy.xa_count = 0; sy.xa_items = 0; sy.pre = 0;
+  sy.gv_count = 0; sy.acc_count = 0; sy.pre = 0;
   sy.cta = blockIdx.x; sy.nc = gridDim.x;
   if (threadIdx.x == 0) {
     for (int i = 0; i < GV_NST; ++i) { mbar_init(sy.mb(MB_GV_FULL + i), 1); mbar_init(sy.mb(MB_GV_EMPTY + i), 1); }
@@ -1291,7 +1299,6 @@ __global__ void __launch_bounds__(MK_THREADS, 1) dec_step_kernel(const __grid_co
   sy.tmem = tmem_slot;
 
   unsigned bar_target = 0;
-  int prof_n = 0;
   const int pos0 = *p.d_pos;  // written only after the last barrier of this launch
   const int n_ph = ops_per_step(p);
   for (int s = 0; s < p.n_steps; ++s) {
@@ -1299,14 +1306,15 @@ __global__ void __launch_bounds__(MK_THREADS, 1) dec_step_kernel(const __grid_co
     for (int ph = 0; ph < n_ph; ++ph) {
       int l = ph / 11, k = ph - 11 * l;
       if (l >= p.L) { k = 11 + (ph - 11 * p.L); l = p.L - 1; }
-      run_op<MT>(p, s_layers, l, k, pos, ring, scratch, red, red_i, sy);
+      run_op<MT>(p, s_layers, l, k, pos, s * p.L + l, ring, scratch, red, red_i, sy);
       if (ph + 1 < n_ph || s + 1 < p.n_steps) {
         // the operator after the barrier: (l2, k2)
         const int ph2 = (ph + 1 < n_ph) ? ph + 1 : 0;
         int l2 = ph2 / 11, k2 = ph2 - 11 * l2;
         if (l2 >= p.L) { k2 = 11 + (ph2 - 11 * p.L); l2 = p.L - 1; }
-        grid_sync(p.bar, bar_target, sy.nc, sy.cta, p.prof, prof_n, [&]() { pre_issue<MT>(p, l2, k2, ring, sy, true); });
-        if (warp == 0) pre_issue<MT>(p, l2, k2, ring, sy, false);  // the producer warp only needs the count
+        const int xq2 = (ph + 1 < n_ph ? s : s + 1) * p.L + l2;  // cross-attention phases completed before operator (l2, k2)
+        grid_sync(p.bar, bar_target, sy.nc, sy.cta, p.prof, [&]() { pre_issue<MT>(p, l2, k2, xq2, ring, sy, true); });
+        if (warp == 0) pre_issue<MT>(p, l2, k2, xq2, ring, sy, false);  // the producer warp only needs the count
       }
     }
   }
