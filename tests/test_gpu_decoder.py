@@ -25,6 +25,11 @@ def _dims(name):
         # round (8 warps of a CTA per unit) and the cross-attention remainder pieces only occur at this width
         return dict(n_mels=80, n_audio_ctx=1500, n_audio_state=1280, n_audio_head=20, n_audio_layer=1,
                     n_vocab=1000, n_text_ctx=448, n_text_state=1280, n_text_head=20, n_text_layer=1)
+    if name == "turbo-dec":
+        # decoder of large-v3-turbo (BASELINE config 4: 4 layers, d = 1280, 20 heads, 51866-token vocabulary) behind a
+        # one-layer encoder of the same width, so the CPU oracle stays small
+        return dict(n_mels=128, n_audio_ctx=1500, n_audio_state=1280, n_audio_head=20, n_audio_layer=1,
+                    n_vocab=51866, n_text_ctx=448, n_text_state=1280, n_text_head=20, n_text_layer=4)
     return bw.dims_for(name)
 
 
@@ -44,9 +49,10 @@ def _setup(ctx, name, B, std=0.05, seed=5, mutate=None):
     return dims, w_ref, enc, ow
 
 
-@pytest.mark.parametrize("name,B", [("mini", 3), ("tiny", 2), ("mini", 19), ("wide", 60)])
+@pytest.mark.parametrize("name,B", [("mini", 3), ("tiny", 2), ("mini", 19), ("wide", 60), ("base", 16), ("turbo-dec", 8)])
 def test_teacher_forced_logits(wxb_ctx, name, B):
-    dims, w_ref, enc, ow = _setup(wxb_ctx, name, B, std=0.02 if name == "wide" else 0.05)
+    # ("base", 16) is BASELINE config 2 (whisper-base, 16 chunks, batch 16); "turbo-dec" the decoder of config 4
+    dims, w_ref, enc, ow = _setup(wxb_ctx, name, B, std=0.02 if name in ("wide", "turbo-dec") else 0.05)
     n_tok = 12 if name == "wide" else 6
     toks = np.random.RandomState(0).randint(0, dims["n_vocab"], size=(B, n_tok)).astype(np.int32)
     got = wxb_ctx.decoder_logits(enc, toks).float().cpu()
