@@ -35,7 +35,7 @@ def _tiny_dims(n_mels=80, d=128, heads=2, layers=2, vocab=1000):
                 n_vocab=vocab, n_text_ctx=448, n_text_state=d, n_text_head=heads, n_text_layer=layers)
 
 
-@pytest.mark.parametrize("cfg", ["mini80", "mini128", "tiny"])
+@pytest.mark.parametrize("cfg", ["mini80", "mini128", "tiny", "base"])
 def test_encoder_vs_oracle(wxb_ctx, cfg):
     """Encoder hidden states vs the fp32 oracle on the same (bf16-rounded) weights.  Tolerance is the
     bf16 budget: activations are rounded to bf16 (2^-9 relative) at every GEMM input; the stated
@@ -45,8 +45,8 @@ def test_encoder_vs_oracle(wxb_ctx, cfg):
     from fake_ctc_model import synthetic_speech
     import whisperx.audio as wa
 
-    if cfg == "tiny":
-        dims = bw.dims_for("tiny")
+    if cfg in ("tiny", "base"):  # "base" is the architecture of BASELINE config 2
+        dims = bw.dims_for(cfg)
     elif cfg == "mini80":
         dims = _tiny_dims(80, 128, 2, 2)
     else:
