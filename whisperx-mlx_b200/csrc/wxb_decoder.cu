@@ -722,53 +722,6 @@ __device__ __forceinline__ uint32_t split_pack(float x, float y, int sel) {
   return sel == 0 ? hi : (sel == 1 ? lo : 0u);
 }
 
-// One online-softmax update over NS consecutive stages (NS x 16 keys of this warp): the QK products of all
-// blocks are issued back to back (two accumulators per block), one max reduction serves all blocks, and the PV
-// products follow, so the long HMMA / shuffle latencies overlap across blocks instead of adding up per stage.
-template <int NS>
-__device__ __forceinline__ void xa_block(const uint32_t (*ka)[4][4], const uint32_t (*va)[4][4], const uint32_t (*qb)[2],
-                                         int key0, int k1, int lane, int g, int t, float& m, float& lsum, float (*o)[4]) {
-  float s[NS][2];
-#pragma unroll
-  for (int n = 0; n < NS; ++n) {
-    float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
-    mma_16816(c0, ka[n][0], qb[0][0], qb[0][1]);
-    mma_16816(c1, ka[n][1], qb[1][0], qb[1][1]);
-    mma_16816(c0, ka[n][2], qb[2][0], qb[2][1]);
-    mma_16816(c1, ka[n][3], qb[3][0], qb[3][1]);
-    s[n][0] = __shfl_sync(0xffffffffu, (c0[0] + c0[1]) + (c1[0] + c1[1]), lane & ~3);
-    s[n][1] = __shfl_sync(0xffffffffu, (c0[2] + c0[3]) + (c1[2] + c1[3]), lane & ~3);
-    if (key0 + n * XA_KEYS >= k1) s[n][0] = -INFINITY;
-    if (key0 + n * XA_KEYS + 8 >= k1) s[n][1] = -INFINITY;
-  }
-  float mx = fmaxf(s[0][0], s[0][1]);
-#pragma unroll
-  for (int n = 1; n < NS; ++n) mx = fmaxf(mx, fmaxf(s[n][0], s[n][1]));
-  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
-  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
-  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
-  const float mn = fmaxf(m, mx);
-  if (mn == -INFINITY) return;  // every key of the blocks is outside the range (warp-uniform)
-  if (mn > m) {                 // warp-uniform
-    const float alpha = __expf(m - mn);  // m = -inf -> 0
-    lsum *= alpha;
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt) { o[mt][0] *= alpha; o[mt][1] *= alpha; o[mt][2] *= alpha; o[mt][3] *= alpha; }
-    m = mn;
-  }
-#pragma unroll
-  for (int n = 0; n < NS; ++n) {
-    const float p0 = __expf(s[n][0] - m), p1 = __expf(s[n][1] - m);  // -inf -> 0
-    lsum += p0 + p1;  // per-quad partial sum (identical in the 4 lanes of a quad)
-    // B fragment of p: lane (g, t) needs keys 2t, 2t+1 (b0) and 2t+8, 2t+9 (b1): quads 2t and 2t+1
-    const float x0 = __shfl_sync(0xffffffffu, p0, 8 * t), x1 = __shfl_sync(0xffffffffu, p0, 8 * t + 4);
-    const float y0 = __shfl_sync(0xffffffffu, p1, 8 * t), y1 = __shfl_sync(0xffffffffu, p1, 8 * t + 4);
-    const uint32_t pb0 = split_pack(x0, x1, g), pb1 = split_pack(y0, y1, g);
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt) mma_16816(o[mt], va[n][mt], pb0, pb1);
-  }
-}
-
 // The warps never meet at a block barrier inside the phase: the producer warp stages the raw q rows (bias + split-K
 // partials of the cq GEMV) of the next items, every consumer warp sums them for itself, deposits its (m, l, O) state of
 // a finished item in a double-buffered shared-memory slot and moves straight on; consumer warp (item % 7) merges the
