@@ -94,12 +94,42 @@ class B200WhisperBackend(WhisperBackend):
         if self._staging_done is not None:
             self._staging_done.synchronize()
         hv = self._staging.numpy()
-        for c, o, l in zip(chunks, offs, lens):
-            hv[o:o + l] = np.asarray(c[:l], dtype=np.float32)
-        dev = self._staging[: max(total, 1)].to(self.device, non_blocking=True)
+        dev = torch.empty(max(total, 1), dtype=torch.float32, device=self.device)
+        # Groups of chunks: host copy into the pinned buffer, then an asynchronous H2D of that range, so the PCIe
+        # transfer of one group runs under the host copy of the next.  Chunks that are back-to-back views of one
+        # float32 array (what transcribe() cuts) are copied as one range with torch's multi-threaded copy.
+        n, group = len(chunks), 12
+        for g0 in range(0, n, group):
+            g1 = min(n, g0 + group)
+            lo, hi = int(offs[g0]), int(offs[g1 - 1] + lens[g1 - 1])
+            if hi > lo:
+                run = self._contiguous_run(chunks[g0:g1], lens[g0:g1])
+                if run is not None:
+                    self._staging[lo:hi].copy_(torch.from_numpy(run))
+                else:
+                    for c, o, l in zip(chunks[g0:g1], offs[g0:g1], lens[g0:g1]):
+                        hv[o:o + l] = np.asarray(c[:l], dtype=np.float32)
+                dev[lo:hi].copy_(self._staging[lo:hi], non_blocking=True)
         self._staging_done = torch.cuda.Event()
         self._staging_done.record()
         return dev, offs, lens
+
+    @staticmethod
+    def _contiguous_run(chunks, lens):
+        """The single float32 array the (clipped) chunks tile back to back in memory, or None."""
+        first = chunks[0]
+        if not (isinstance(first, np.ndarray) and first.dtype == np.float32 and first.ndim == 1 and first.flags.c_contiguous):
+            return None
+        addr = first.__array_interface__["data"][0]
+        start = addr
+        for c, l in zip(chunks, lens):
+            if not (isinstance(c, np.ndarray) and c.dtype == np.float32 and c.ndim == 1 and c.flags.c_contiguous):
+                return None
+            if c.__array_interface__["data"][0] != addr or len(c) != int(l):
+                return None  # a gap, a reordering, or a chunk clipped to 30 s
+            addr += int(l) * 4
+        total = (addr - start) // 4
+        return np.lib.stride_tricks.as_strided(first, shape=(total,), strides=(4,), writeable=False)
 
     def transcribe_device(self, audio_dev: torch.Tensor, offs: np.ndarray, lens: np.ndarray, batch_size: int,
                           language: str, task: str):
