@@ -96,3 +96,20 @@ def test_align_host_assembly_matches_reference_golden(golden_dir):
     for tag, chars in (("words", False), ("chars", True)):
         got = json.loads(json.dumps(_oracle_align(g["transcript"], audio, chars), default=float))
         _close(got, g["result"][tag]["segments"], tag)
+
+
+def test_upload_contiguous_run_detection():
+    """upload_chunks copies back-to-back views of one float32 array as a single range; anything else (gaps, reordering,
+    clipped or strided chunks, other dtypes) must fall back to the per-chunk copy."""
+    import numpy as np
+    from whisperx.backends.b200 import B200WhisperBackend as B
+    a = np.arange(1000, dtype=np.float32)
+    run = B._contiguous_run([a[0:300], a[300:600], a[600:1000]], [300, 300, 400])
+    assert run is not None and run.shape == (1000,) and np.array_equal(run, a)
+    assert np.array_equal(B._contiguous_run([a[100:400]], [300]), a[100:400])
+    assert B._contiguous_run([a[0:300], a[301:600]], [300, 299]) is None          # gap
+    assert B._contiguous_run([a[300:600], a[0:300]], [300, 300]) is None          # reordered
+    assert B._contiguous_run([a[0:300], a[300:600]], [300, 200]) is None          # second chunk clipped
+    assert B._contiguous_run([a[::2]], [500]) is None                             # strided
+    assert B._contiguous_run([a.astype(np.float64)], [1000]) is None              # other dtype
+    assert B._contiguous_run([a.tolist()], [1000]) is None                        # not an array
