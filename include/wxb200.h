@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define WXB_ABI_VERSION 1
+#define WXB_ABI_VERSION 2
 
 typedef struct wxb_ctx wxb_ctx;
 
@@ -139,7 +139,16 @@ typedef struct {
   int32_t blank_token;     /* id of encode(" ") (only used when suppress_blank) */
   int32_t n_suppress;      /* length of suppress_dev */
   const int32_t* suppress_dev; /* device int32 ids set to -inf every step */
-  int32_t check_every;     /* host polls "all rows hit EOT" every this many steps (0 = 16) */
+  int32_t check_every;     /* host polls the EOT flags every this many steps (0 = 16); rows that have finished leave
+                              the batch at these boundaries (active-sequence compaction,
+                              mlx_whisper_batch_decoder.py:37-100) */
+  int32_t no_compaction;   /* 1: finished rows keep riding along until every row is done (A/B timing, tests) */
+  /* ApplyTimestampRules (decode with timestamps, mlx_lightning.py:187-193 `without_timestamps=False`); the last
+   * clause is the reference's batch-safe patch mlx_ultra_optimized_batch.py:38-71 */
+  int32_t apply_timestamp_rules;        /* 0 = off (prompt ends with <|notimestamps|>) */
+  int32_t timestamp_begin;              /* id of <|0.00|> */
+  int32_t no_timestamps;                /* id of <|notimestamps|>, suppressed when the rules are on (-1 = none) */
+  int32_t max_initial_timestamp_index;  /* 50 = 1.0 s / 0.02 s; < 0 = unlimited */
 } wxb_decode_opts;
 
 /* Batched greedy KV-cache decode.  enc_out bf16 [B,1500,d]; prompt_host int32[prompt_len]
@@ -154,7 +163,9 @@ int wxb_decode_greedy(wxb_ctx* ctx, const void* enc_out_dev, int B, const int32_
 
 /* Device-side timing of the wxb_decode_greedy calls made since the last reset (CUDA events recorded
  * on the caller's stream; this call synchronises on them): total milliseconds spent in the cross-KV
- * projection GEMMs, in the per-token step loop, and the number of decoder steps run. */
+ * projection GEMMs, in the per-token step loop, and the number of decoder steps run.  Timing is OPT-IN:
+ * nothing is recorded until the first call with reset = 1 (a serving process that never asks pays for
+ * no events); at most 4096 calls are kept between resets. */
 int wxb_decode_stats(wxb_ctx* ctx, double* cross_kv_ms, double* steps_ms, int64_t* n_steps, int reset);
 
 /* Teacher-forced logits for parity tests: runs the decoder over tokens_host int32 [B, n_tok]

@@ -118,11 +118,44 @@ def decoder_forward(w, dims, tokens: torch.Tensor, cache: DecoderCache) -> torch
     return (x @ w["decoder.token_embedding.weight"].t()).float()
 
 
+def apply_timestamp_rules(logits: torch.Tensor, sampled: torch.Tensor, eot: int, ts_begin: int, no_timestamps: int,
+                          max_initial_timestamp_index: Optional[int] = 50) -> torch.Tensor:
+    """ApplyTimestampRules of the decoding module the reference uses (mlx_whisper.decoding, a port of OpenAI
+    whisper/decoding.py; un-vendored, restated from the published algorithm, SURVEY A.3 filter 3).  logits f32 [B, V]
+    (modified in place and returned), sampled int64 [B, n] = the tokens sampled so far (prompt excluded).  The last clause
+    is the one the reference patches to be batch-safe, /root/reference/mlx_ultra_optimized_batch.py:38-71 (keepdims)."""
+    B, n = sampled.shape
+    if no_timestamps is not None and no_timestamps >= 0:
+        logits[:, no_timestamps] = -float("inf")
+    for k in range(B):
+        seq = sampled[k].tolist()
+        last_was_ts = len(seq) >= 1 and seq[-1] >= ts_begin
+        pen_was_ts = len(seq) < 2 or seq[-2] >= ts_begin
+        if last_was_ts:
+            if pen_was_ts:
+                logits[k, ts_begin:] = -float("inf")
+            else:
+                logits[k, :eot] = -float("inf")
+        ts = [t for t in seq if t >= ts_begin]
+        if ts:
+            last = ts[-1] if (last_was_ts and not pen_was_ts) else ts[-1] + 1
+            logits[k, ts_begin:last] = -float("inf")
+    if n == 0:
+        logits[:, :ts_begin] = -float("inf")
+        if max_initial_timestamp_index is not None:
+            logits[:, ts_begin + max_initial_timestamp_index + 1:] = -float("inf")
+    logprobs = logits - torch.logsumexp(logits, -1, keepdim=True)
+    ts_lp = torch.logsumexp(logprobs[:, ts_begin:], -1, keepdim=True)
+    max_text = logprobs[:, :ts_begin].max(-1, keepdim=True).values
+    logits[:, :ts_begin] = torch.where(ts_lp > max_text, torch.full_like(logits[:, :ts_begin], -float("inf")), logits[:, :ts_begin])
+    return logits
+
+
 def greedy_decode(w, dims, enc_out: torch.Tensor, prompt: List[int], eot: int, no_speech: int = -1,
                   sample_len: int = 224, suppress_blank: bool = False, blank_token: int = 220,
-                  suppress_tokens=(), return_logits: bool = False):
+                  suppress_tokens=(), return_logits: bool = False, timestamp_rules: Optional[dict] = None):
     """Batched greedy loop, mlx_whisper_batch_decoder.py:317-384 + :267-303, with the SuppressBlank /
-    SuppressTokens filters (timestamp rules are not applied: without_timestamps prompt).
+    SuppressTokens filters and, with `timestamp_rules` (a dict like the kernel binding takes), ApplyTimestampRules.
 
     Returns dict(tokens=[B][...] up to first EOT, sum_logprob[B], avg_logprob[B], no_speech_prob[B],
     all_tokens int64 [B, n_sampled], step_logits (optional, filtered f32 logits per step)).
@@ -148,6 +181,10 @@ def greedy_decode(w, dims, enc_out: torch.Tensor, prompt: List[int], eot: int, n
             logits[:, eot] = -float("inf")
         if len(suppress):
             logits[:, suppress] = -float("inf")
+        if timestamp_rules:
+            hist = torch.stack(sampled, 1) if sampled else torch.zeros((B, 0), dtype=torch.long)
+            apply_timestamp_rules(logits, hist, eot, timestamp_rules["timestamp_begin"], timestamp_rules.get("no_timestamps", -1),
+                                  timestamp_rules.get("max_initial_timestamp_index", 50))
         if return_logits:
             step_logits.append(logits.clone())
         nxt = logits.argmax(-1)

@@ -44,6 +44,11 @@ void* wxb_named(wxb_ctx* ctx, const char* name, size_t bytes, bool zero_on_alloc
   return b.p;
 }
 
+void wxb_dec_timings_clear(wxb_ctx* ctx) {
+  for (auto& t : ctx->dec_timings) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); cudaEventDestroy(t.e2); }
+  ctx->dec_timings.clear();
+}
+
 extern "C" {
 
 int wxb_abi_version(void) { return WXB_ABI_VERSION; }
@@ -80,6 +85,7 @@ void wxb_destroy(wxb_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   wxb_model_free(ctx);
+  wxb_dec_timings_clear(ctx);
   wxb_buf* bufs[] = {&ctx->ws_ctc_trellis, &ctx->ws_ctc_hist, &ctx->ws_ctc_meta, &ctx->ws_mel_max,
                      &ctx->ws_mel_band};
   for (wxb_buf* b : bufs)

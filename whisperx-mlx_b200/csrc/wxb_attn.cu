@@ -6,7 +6,7 @@
 //   P_t = exp2((S_t - m) c)    softmax warps: one thread per query row reads its S row with tcgen05.ld, keeps the
 //                              max / sum in registers, writes P_t (bf16) into shared memory in the canonical K-major
 //                              swizzled layout (A operand of the next MMA)
-//   O_t += P_t V_j         tcgen05.mma M=128 N=64 K=128 (V^T tiles from a pre-transposed copy), accumulated IN TMEM
+//   O_t += P_t V_j         tcgen05.mma M=128 N=64 K=128 (P from TMEM, V_j rows as an MN-major B operand), accumulated IN TMEM
 // The offset m baked into O_t and the row sum is only moved when the running row maximum has grown by more than 2^8
 // (P stays within bf16 / fp32 range), so the O_t rescale (tcgen05.ld, multiply, tcgen05.st) is rare after the first
 // tiles and the softmax threads touch O only once more, for the final 1 / sum.
@@ -151,33 +151,6 @@ __device__ __forceinline__ float exp_block64(const uint32_t* sv, int col0, int v
   float a0, a1;
   unpack2(acc, a0, a1);
   return a0 + a1;
-}
-
-// V part of qkv [B*T, 3d] -> vT [(b*H + h)*64 + j][Tpad] (keys contiguous), zero in the T..Tpad-1 padding
-__global__ void __launch_bounds__(256)
-v_transpose_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ vT, int T, int Tpad, int d, int H) {
-  __shared__ __nv_bfloat16 tile[64][66];
-  const int t0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
-  const int tid = threadIdx.x;
-  for (int idx = tid; idx < 64 * 32; idx += 256) {
-    const int r = idx >> 5, c2 = idx & 31;  // row = time, c2 = pair of dims
-    const int t = t0 + r;
-    __nv_bfloat162 v = __floats2bfloat162_rn(0.f, 0.f);
-    if (t < T) v = *reinterpret_cast<const __nv_bfloat162*>(qkv + ((size_t)b * T + t) * 3 * d + 2 * d + h * 64 + 2 * c2);
-    tile[r][2 * c2] = __low2bfloat16(v);
-    tile[r][2 * c2 + 1] = __high2bfloat16(v);
-  }
-  __syncthreads();
-  for (int idx = tid; idx < 64 * 32; idx += 256) {
-    const int j = idx >> 5, t2 = idx & 31;  // row = dim, t2 = pair of times
-    const int t = t0 + 2 * t2;
-    if (t < Tpad) {
-      __nv_bfloat162 v;
-      v.x = tile[2 * t2][j];
-      v.y = tile[2 * t2 + 1][j];
-      *reinterpret_cast<__nv_bfloat162*>(vT + ((size_t)(b * H + h) * 64 + j) * Tpad + t) = v;
-    }
-  }
 }
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
@@ -420,19 +393,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const AttnTcParams
 int wxb_make_tmap_bf16(wxb_ctx* ctx, CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
                        uint32_t box_inner, uint32_t box_rows);
 
-// qkv bf16 [B*T, 3d] -> out bf16 [B*T, d]; vT = scratch bf16 [B*H*64, Tpad]
-int wxb_attention_tc(wxb_ctx* ctx, const __nv_bfloat16* qkv, __nv_bfloat16* vT, __nv_bfloat16* out, int B, int T, int d, int H,
-                     cudaStream_t st) {
+// qkv bf16 [B*T, 3d] -> out bf16 [B*T, d]
+int wxb_attention_tc(wxb_ctx* ctx, const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int d, int H, cudaStream_t st) {
   const int Tpad = (T + 7) & ~7;
-  (void)vT;  // no transposed copy of V any more (kept in the signature for the callers' workspace layout)
   CUtensorMap tmQK;
   int rc;
   if ((rc = wxb_make_tmap_bf16(ctx, &tmQK, qkv, (uint64_t)3 * d, (uint64_t)B * T, (uint64_t)3 * d * 2, 64, 128)) != WXB_OK) return rc;
-  static bool attr = false;
-  if (!attr) {
-    WXB_CUDA(ctx, cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-    attr = true;
-  }
+  if ((rc = wxb_func_smem(ctx, attention_tc_kernel, AT_SMEM)) != WXB_OK) return rc;
   AttnTcParams p;
   p.T = T; p.Tpad = Tpad; p.d = d; p.H = H; p.n_kv_tiles = ceil_div(T, BKV);
   p.scale_log2 = (1.0f / sqrtf(64.f)) * 1.44269504088896341f;

@@ -22,6 +22,13 @@ struct wxb_dec_timing {
   int steps;
 };
 
+// identity of the decoder's device-resident tensor-map table ("dec.maps")
+struct wxb_dec_maps_key {
+  const void* model = nullptr;
+  const void *xn = nullptr, *att = nullptr, *hid = nullptr, *ckv = nullptr;
+  int B = 0;
+};
+
 struct wxb_ctx {
   int device = 0;
   int sm_count = 148;
@@ -32,9 +39,21 @@ struct wxb_ctx {
   std::map<std::string, wxb_buf> named;  // model-side activations / caches keyed by name
   wxb_model* model = nullptr;
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled (driver entry point), lazily resolved
-  std::vector<wxb_dec_timing> dec_timings;  // one entry per wxb_decode_greedy call since the last reset
+  // decode timing is opt-in: wxb_decode_stats(reset = 1) switches it on; entries are owned by the ctx (freed by the next
+  // reset, by wxb_destroy, and capped at WXB_MAX_DEC_TIMINGS so a serving process cannot grow without bound)
+  bool dec_timing_on = false;
+  std::vector<wxb_dec_timing> dec_timings;  // one entry per timed wxb_decode_greedy call since the last reset
   bool lm_tables_ready = false;  // log-mel window/twiddle tables uploaded to this device
+  // per-device state that must not be process-global (a process may hold one ctx per GPU):
+  std::map<const void*, int> func_smem;        // kernels whose MaxDynamicSharedMemorySize attribute was raised on this device
+  const void* dec_layers_model = nullptr;      // the model whose DecLayerW table is resident in "dec.layers"
+  wxb_dec_maps_key dec_maps_key;               // identity of the tensor-map table resident in "dec.maps"
+  std::map<std::string, std::vector<unsigned char>> tmap_cache;  // encoded CUtensorMaps keyed by (base, shape, box)
 };
+
+constexpr size_t WXB_MAX_DEC_TIMINGS = 4096;
+void wxb_dec_timings_clear(wxb_ctx* ctx);  // wxb_api.cu
+
 
 int wxb_fail(wxb_ctx* ctx, int code, const char* fmt, ...);
 int wxb_reserve(wxb_ctx* ctx, wxb_buf& b, size_t bytes);
@@ -57,6 +76,17 @@ void wxb_model_free(wxb_ctx* ctx);  // wxb_model.cu
       return wxb_fail((ctx), WXB_ERR_CUDA, "kernel launch failed: %s (%s:%d)",           \
                       cudaGetErrorString(_e), __FILE__, __LINE__);                       \
   } while (0)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (ctx = device, kernel): the attribute is a per-device setting
+template <class K>
+static inline int wxb_func_smem(wxb_ctx* ctx, K kern, int bytes) {
+  const void* key = reinterpret_cast<const void*>(kern);
+  auto it = ctx->func_smem.find(key);
+  if (it != ctx->func_smem.end() && it->second >= bytes) return WXB_OK;
+  WXB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  ctx->func_smem[key] = bytes;
+  return WXB_OK;
+}
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -45,12 +45,12 @@ __device__ __forceinline__ float wild_max_global(const float* row, int V, int bl
 __global__ void __launch_bounds__(CTC_WARPS * 32)
 ctc_align_kernel(const float* __restrict__ emis, const int* __restrict__ tok,
                  const CtcSeg* __restrict__ segs, int n_seg, int V, int Vpad, int blank, int mode,
-                 int nmax_pad, float* __restrict__ trellis, int2* __restrict__ hist,
+                 int nmax_pad, int wpb, float* __restrict__ trellis, int2* __restrict__ hist,
                  int* __restrict__ path_tok, float* __restrict__ path_lp,
                  float* __restrict__ path_prob, int* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int seg_id = blockIdx.x * CTC_WARPS + warp;
+  const int seg_id = blockIdx.x * wpb + warp;  // wpb = warps (segments) per block, chosen by the host so the shared memory fits
   if (seg_id >= n_seg) return;
   // per-warp carve-up
   const size_t per_warp = (size_t)nmax_pad * 12 + (size_t)CTC_RING * Vpad * 4;
@@ -322,9 +322,14 @@ int wxb_ctc_align(wxb_ctx* ctx, const float* emis_dev, const int32_t* t_off_host
   const long long sumT = t_off_host[n_seg];
   const int nmax_pad = (nmax + 31) & ~31;
   const int Vpad = (V + 3) & ~3;
-  const size_t smem = ((size_t)nmax_pad * 12 + (size_t)CTC_RING * Vpad * 4) * CTC_WARPS;
+  // shared memory per warp: token ids + two trellis rows + the emission ring; large vocabularies (the ja / zh align models
+  // have 2-3.5 k labels) get fewer warps per block instead of an error
+  const size_t per_warp = (size_t)nmax_pad * 12 + (size_t)CTC_RING * Vpad * 4;
+  int wpb = CTC_WARPS;
+  while (wpb > 1 && per_warp * wpb > 220 * 1024) wpb >>= 1;
+  const size_t smem = per_warp * wpb;
   if (smem > 220 * 1024)
-    return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "wxb_ctc_align: segment with %d tokens needs %zu B smem", nmax, smem);
+    return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "wxb_ctc_align: a segment with %d tokens over %d labels needs %zu B of shared memory", nmax, V, smem);
   int rc;
   if ((rc = wxb_reserve(ctx, ctx->ws_ctc_meta, sizeof(CtcSeg) * n_seg)) != WXB_OK) return rc;
   if (!trellis_dev) {
@@ -335,10 +340,10 @@ int wxb_ctc_align(wxb_ctx* ctx, const float* emis_dev, const int32_t* t_off_host
   WXB_CUDA(ctx, cudaMemcpyAsync(ctx->ws_ctc_meta.p, segs.data(), sizeof(CtcSeg) * n_seg, cudaMemcpyHostToDevice, st));
   // the pageable source buffer `segs` dies at return: the copy above is staged synchronously by
   // the runtime for pageable memory, so this is safe.
-  WXB_CUDA(ctx, cudaFuncSetAttribute(ctc_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = ceil_div(n_seg, CTC_WARPS);
-  ctc_align_kernel<<<grid, CTC_WARPS * 32, smem, st>>>(
-      emis_dev, tok_dev, (const CtcSeg*)ctx->ws_ctc_meta.p, n_seg, V, Vpad, blank, mode, nmax_pad,
+  if ((rc = wxb_func_smem(ctx, ctc_align_kernel, (int)smem)) != WXB_OK) return rc;
+  const int grid = ceil_div(n_seg, wpb);
+  ctc_align_kernel<<<grid, wpb * 32, smem, st>>>(
+      emis_dev, tok_dev, (const CtcSeg*)ctx->ws_ctc_meta.p, n_seg, V, Vpad, blank, mode, nmax_pad, wpb,
       trellis_dev, (int2*)ctx->ws_ctc_hist.p, path_tok_dev, path_lp_dev, path_prob_dev, status_dev);
   WXB_LAUNCH_CHECK(ctx);
   return WXB_OK;

@@ -2,28 +2,35 @@
 //
 // Behavioural spec: the reference's in-tree batched loop
 //   /root/reference/mlx_whisper_batch_decoder.py:317-384 (_main_loop_batch), :267-303 (update),
-//   :386-468 (run: EOT trimming, avg_logprob), filters per SURVEY A.3 (SuppressBlank, SuppressTokens).
+//   :386-468 (run: EOT trimming, avg_logprob), :37-100 (active-sequence masking), filters per SURVEY A.3
+//   (SuppressBlank, SuppressTokens, ApplyTimestampRules: /root/reference/mlx_ultra_optimized_batch.py:38-71).
 //
 // One decode step streams ~17 GB at large-v3 / batch 60 (weights once, cross-KV once per sequence) through
 // ~350 dependent small operators.  Launch/dependency latency, not bandwidth, dominated a kernel-per-operator
 // design (measured: 8.7 us per dependent kernel, chain 3.1 ms + attention 2.9 ms per step, not overlapping),
-// so the whole step is ONE persistent cooperative kernel: one CTA per SM, operators are phases separated by
-// a grid barrier (one L2 atomic + acquire poll, ~0.5 us):
+// so the whole step is ONE persistent cooperative kernel: one 12-warp CTA per SM, operators are phases separated by
+// a grid barrier (release-add + acquire-poll on one L2 counter, ~1.3 us):
 //
 //   per layer   LN1 | QKV | self-attention | out | LN2 | cq | cross-attention | cout | LN3 | fc1 | fc2
 //   then        final LN | logits | no_speech_prob + filters + argmax + logsumexp + EOT latch
 //
-//   GEMV phases   y[b,n] = sum_k act[b,k] W[n,k]: mma.sync m16n8k16 with the BATCH as the M tile and 8 weight
-//                 rows as the N tile.  A K-permutation shared by the A and B fragments lets natural row-major
-//                 weights go from HBM straight into B fragments with 16-byte loads (no repack); up to 16 such
-//                 loads per lane are in flight (two register batches).  A CTA tile is (64*nb weight rows) x
-//                 (K / gk slice); its activation slice is cp.async'ed into shared memory.  Split-K tiles write
-//                 fp32 partials [gk][B][N]; the CONSUMER phase sums them in slice order (deterministic) together
-//                 with bias / residual / LayerNorm / q-scaling / KV-cache append, so no reduction phase exists.
-//   attention     8 lanes x 16 B per key row (128 B, fully coalesced), online softmax per 8-lane key slot,
-//                 K/V rows of the next keys requested one iteration ahead.  Cross-attention gives every CTA
-//                 the same number of whole (sequence, head) slabs; the remainder slabs are cut into pieces
-//                 whose partial states are merged by the last-arriving CTA (self-cleaning ticket).
+//   GEMV phases   y[b,n] = sum_k act[b,k] W[n,k] on the 5th-gen tensor cores: tcgen05.mma with the WEIGHTS as the M
+//                 operand (128 rows per tile) and the (live) batch rows as the N operand (16 MT <= 64), both staged by
+//                 TMA (128-byte swizzle) into a 6-stage mbarrier ring, fp32 accumulators in TMEM (interleaved over
+//                 GV_NACC independent accumulators so consecutive products do not wait on one another), read back
+//                 with tcgen05.ld.  A CTA tile is 128 weight rows x (K / gk slice).  Split-K tiles write fp32 partials
+//                 [gk][B][N]; the CONSUMER phase sums them in slice order (deterministic) together with bias /
+//                 residual / LayerNorm / q-scaling / KV-cache append, so no reduction phase exists.
+//   self-attn     one warp per (sequence, head): 8 lanes x 16 B per key row, online softmax per 8-lane key slot,
+//                 cached K/V rows staged a few 16-key chunks ahead with cp.async.
+//   cross-attn    every CTA streams whole (sequence, head) slabs of 192 KB K + 192 KB V through a TMA ring (warp 0 =
+//                 producer), 11 consumer warps do S = K q / O += V^T p with mma.sync m16n8k16; the remainder slabs are
+//                 cut into pieces whose partial states are merged by the last-arriving CTA (self-cleaning ticket).
+//
+// Active-sequence compaction (reference :37-100): rows that have emitted EOT leave the batch at launch boundaries.  The
+// host polls the done flags every `check_every` steps; the next launch carries the list of live rows (`rows`), so GEMV
+// batch tiles, LayerNorm rows, attention units and cross-K/V slabs exist only for live rows; finished rows keep their
+// latched EOT (written by the host-side finalize).
 //
 // HBM layout (L decoder layers, B sequences, H heads, d = 64 H):
 //   self K/V  bf16 [L][2][B][H][448][64]      cross K/V bf16 [L][2][B][H][1500][64]
@@ -43,6 +50,11 @@ namespace {
 using namespace wxbtc;
 
 constexpr int T_AUDIO = 1500;
+// Timing probes that leave phases out (results become meaningless).  The mask is a kernel PARAMETER that only a
+// -DWXB_PROBE build of the host code can set (dec_skip_mask(): the shipped library ignores WXB_DEC_SKIP and always passes 0).
+// The tests stay in the kernel on purpose: compiling them out changes ptxas' register allocation of the persistent kernel
+// enough to create an 8-byte stack frame, and any stack frame costs 4 % or more of every phase (DESIGN.md "Stack frames").
+#define WXB_SKIP(mask, bit) (((mask) & (bit)) != 0)
 #ifndef WXB_MK_THREADS
 #define WXB_MK_THREADS 384
 #endif
@@ -51,6 +63,10 @@ constexpr int MK_WARPS = MK_THREADS / 32;
 constexpr int LN_V4 = 2;    // LayerNorm phase: float4 groups per thread, d <= 4 * 2 * 256
 constexpr int GK_MAX = 10;  // largest split-K factor a GEMV plan may use
 constexpr int MAX_LAYERS = 32;
+constexpr int MAX_GROUP = 64;  // sequences per call (4 m16 batch tiles)
+// original row of every live (compact) row of the launch; file-scope shared memory so that no pointer to it is carried in
+// registers across the phases of the persistent kernel (the kernel has no register to spare: see DESIGN.md "Stack frames")
+__shared__ int s_rows[MAX_GROUP];
 
 
 // ---- shared-memory plan of the persistent kernel (dynamic, 1024-byte aligned base) -------------------------
@@ -75,6 +91,14 @@ constexpr int XA_NST = MK_WARPS == 8 ? 6 : MK_WARPS == 10 ? 5 : 4;  // K/V ring 
 #endif
 constexpr int XA_NS = WXB_XA_NS;             // K/V stages per consumer iteration
 constexpr int GV_NST = 6;                    // GEMV ring depth
+#ifndef WXB_GV_NACC
+#define WXB_GV_NACC 4
+#endif
+// Independent TMEM accumulators of a GEMV tile: the K = 16 products of one ring stage go to accumulators 0 .. 3 in turn,
+// so back-to-back tcgen05.mma never form one dependent accumulation chain; the epilogue adds them in a fixed order.
+constexpr int GV_NACC = WXB_GV_NACC;         // 1, 2 or 4
+constexpr int GV_TMEM_COLS = 64 * GV_NACC < 32 ? 32 : 64 * GV_NACC;
+static_assert(GV_NACC == 1 || GV_NACC == 2 || GV_NACC == 4, "GV_NACC");
 constexpr int RING_BYTES = XA_NST * 2 * XA_HALF;
 constexpr size_t MK_SMEM = RING_BYTES + SCRATCH_BYTES + 1024;
 static_assert(GV_NST * (GV_A_BYTES + 64 * GV_BK * 2) <= RING_BYTES, "GEMV ring must fit the shared region");
@@ -123,7 +147,8 @@ struct MkGemv {
 };
 
 struct SampleParams {
-  float* logits;  // [B, V] (filters are applied in place)
+  float* logits;  // [B, ldl] (static filters are applied in place), rows 16-byte aligned
+  long long ldl;
   int V;
   int* tokens;    // [B, stride]: prompt + sampled tokens; a step at position pos writes column pos + 1
   int stride;
@@ -134,13 +159,24 @@ struct SampleParams {
   int* done;           // [B] 1 once the row has emitted EOT
   float* nsp_out;      // if set: softmax prob of nsp_token from the UNFILTERED logits of this step
   int nsp_token;
+  // ApplyTimestampRules (decoding with timestamps, `without_timestamps=False`): SURVEY A.3 filter 3; the last clause is the
+  // reference's batch-safe patch /root/reference/mlx_ultra_optimized_batch.py:38-71
+  int ts_rules;        // 0 = off
+  int ts_begin;        // first timestamp token id
+  int no_timestamps;   // <|notimestamps|> id, suppressed when the rules are on
+  int max_initial_ts;  // max_initial_timestamp_index (50), < 0 = unlimited
+  int* ts_last;        // [B] last sampled timestamp token of each row, -1 = none yet
 };
 
 // tensor-map table (device array): per layer {qkv, out, cq, cout, fc1, fc2} weight maps, then emb, xn, att, hid, cross K/V
 enum { TM_QKV = 0, TM_OUT = 1, TM_CQ = 2, TM_COUT = 3, TM_FC1 = 4, TM_FC2 = 5, TM_PER_LAYER = 6 };
+// table behind the per-layer weight maps: emb | (xn, att, hid) boxes of 16, 32, 48, 64 rows | cross K/V full and tail boxes
+enum { TM_EMB = 0, TM_ACT = 1, TM_KV = 13, TM_TAIL_COUNT = 15 };
 
 struct MkParams {
-  int B, d, H, L, V, TX;
+  int B, d, H, L, V, TX;  // B = LIVE rows of this launch (activation buffers are indexed by the compact row number)
+  int B0;                 // rows the K/V caches, token table and per-row outputs were allocated for (original row numbers)
+  const int* rows;        // [B] original row of compact row i (identity while every row is live)
   int mode;     // 0: no logits (forced prompt token); 1: logits; 2: logits + sampling
   int n_steps;  // consecutive positions decoded by this launch (> 1 only in mode 2)
   int skip;     // profiling aid (WXB_DEC_SKIP): 1 cross-attention, 2 GEMV, 4 self-attention, 8 LayerNorm, 16 cross math, 32 cross merge,
@@ -188,7 +224,7 @@ struct MkSync {
   uint32_t bars;       // shared-memory address of the barrier array
   uint32_t gv_count;   // GEMV stages issued so far (slot = count % GV_NST, parity = (count / GV_NST) & 1)
   uint32_t acc_count;  // accumulator hand-offs so far
-  uint32_t tmem;       // TMEM base address (64 fp32 columns x 128 lanes)
+  uint32_t tmem;       // TMEM base address (GV_NACC accumulators of 64 fp32 columns x 128 lanes)
   int pre;             // thread 0: stages of the coming operator already requested before the barrier wait (grid_sync)
   int cta, nc;         // this CTA's index within its group, CTAs per group
   __device__ __forceinline__ uint32_t mb(int slot) const { return bars + 8u * (uint32_t)slot; }
@@ -230,7 +266,7 @@ __device__ __forceinline__ void ln_phase(const MkParams& p, bool from_embed, int
     float s = 0.f;
     int token = 0;
     if (from_embed) {
-      token = __ldcg(p.tokens + (size_t)b * p.tok_stride + pos);
+      token = __ldcg(p.tokens + (size_t)s_rows[b] * p.tok_stride + pos);
       token = min(max(token, 0), p.V - 1);
     }
 #pragma unroll
@@ -364,7 +400,8 @@ __device__ __forceinline__ void gemv_phase(const MkParams& p, const MkGemv& g, c
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < GV_BK / 16; ++k)  // +32 bytes along K inside the swizzle row = +2 in the address field
-            tc_mma_bf16(sy.tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            tc_mma_bf16(sy.tmem + (uint32_t)((k % GV_NACC) * 64), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                        (kb | (k / GV_NACC)) != 0);
           tc_commit(sy.mb(MB_GV_EMPTY + slot));
           if (kb == nkb - 1) tc_commit(sy.mb(MB_ACC_FULL));
         }
@@ -382,8 +419,20 @@ __device__ __forceinline__ void gemv_phase(const MkParams& p, const MkGemv& g, c
     constexpr int EPI_GROUPS = MK_WARPS / 4;
     for (int j = (warp >> 2) < EPI_GROUPS ? (warp >> 2) : MT; j < MT; j += EPI_GROUPS) {
       uint32_t v[16];
-      tc_ld_32x32_x16(sy.tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(j * 16), v);
-      tc_wait_ld();
+      const uint32_t taddr = sy.tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(j * 16);
+      tc_ld_32x32_x16(taddr, v);
+      if (GV_NACC > 1) {
+        uint32_t w[16];
+#pragma unroll
+        for (int a = 1; a < GV_NACC; ++a) {
+          tc_ld_32x32_x16(taddr + (uint32_t)(a * 64), w);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w[i]));
+        }
+      } else {
+        tc_wait_ld();
+      }
       if (n < g.N) {
         if (epi == EPI_PART) {
           float* o = p.part + ((size_t)ks * B + j * 16) * g.N + n;
@@ -615,8 +664,8 @@ __device__ __forceinline__ void self_attn_phase(const MkParams& p, int l, const 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, slot = lane >> 3, c8 = lane & 7;
   const uint32_t stage = smem_u32(ring) + (uint32_t)(warp * SA_RING * 4096);  // this warp's K/V staging slots
   const int H = p.H, B = p.B, TX = p.TX;
-  __nv_bfloat16* sk = p.self_kv + (size_t)l * 2 * B * H * TX * 64;
-  __nv_bfloat16* sv = sk + (size_t)B * H * TX * 64;
+  __nv_bfloat16* sk = p.self_kv + (size_t)l * 2 * p.B0 * H * TX * 64;
+  __nv_bfloat16* sv = sk + (size_t)p.B0 * H * TX * 64;
   const int n_units = B * H, n_warps = sy.nc * MK_WARPS;
   int n_solo = n_units;  // units [0, n_solo) get a warp each; units [n_solo, n_units) a CTA each
   const int left = n_units % n_warps;
@@ -630,7 +679,7 @@ __device__ __forceinline__ void self_attn_phase(const MkParams& p, int l, const 
     if (u0 >= (coop ? n_units : n_solo)) continue;
     const int b = u0 / H, h = u0 - b * H;
     const SelfUnit u = self_unit_qkv(p, qkv_b, b, h, slot, c8);
-    const size_t slab = ((size_t)b * H + h) * TX * 64;
+    const size_t slab = ((size_t)s_rows[b] * H + h) * TX * 64;
     if (slot == 0 && (!coop || warp == 0)) {
       *reinterpret_cast<uint4*>(sk + slab + (size_t)pos * 64 + c8 * 8) = u.kq;
       *reinterpret_cast<uint4*>(sv + slab + (size_t)pos * 64 + c8 * 8) = u.vq;
@@ -739,9 +788,10 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, int x
   int* __restrict__ ticket = p.ticket;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int B = p.B, H = p.H, d = p.d, G = sy.nc, cta = sy.cta, gk = p.g_dd.gk;
-  const CUtensorMap* kvmap = p.maps + (size_t)p.L * TM_PER_LAYER + 4;  // 112-key boxes; kvmap + 1: 48-key boxes
+  const CUtensorMap* kvmap = p.maps + (size_t)p.L * TM_PER_LAYER + TM_KV;  // full-stage boxes; kvmap + 1: tail boxes
   const int n_slabs = B * H, qw = n_slabs / G, r = n_slabs - qw * G;
-  const int krow0 = (l * 2) * n_slabs * T_AUDIO, vrow0 = (l * 2 + 1) * n_slabs * T_AUDIO;  // rows of the [rows, 64] K/V tensor
+  // rows of the [rows, 64] K/V tensor: the cache holds B0 (allocated) sequences per layer, slabs are addressed by the ORIGINAL row
+  const int krow0 = (l * 2) * p.B0 * H * T_AUDIO, vrow0 = (l * 2 + 1) * p.B0 * H * T_AUDIO;
   int P = 0, plen = T_AUDIO;
   if (r > 0) {
     const int want = (G + r - 1) / r;
@@ -754,7 +804,9 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, int x
     // ------------------------------- producer warp -------------------------------
     int it = 0, kk = 0;  // load cursor
     XaItem x = {};
-    if (n_items > 0) { x = xa_item(0, cta, qw, G, P, plen); kk = x.k0; }
+    int oslab = 0;  // K/V slab of the item's ORIGINAL row
+    auto orig_slab = [&](int slab) { const int b = slab / H; return s_rows[b] * H + (slab - b * H); };
+    if (n_items > 0) { x = xa_item(0, cta, qw, G, P, plen); kk = x.k0; oslab = orig_slab(x.slab); }
     uint32_t issued = xa_count0;
     auto stage_q = [&](int qi) {
       // raw q rows of item qi (row gk = bias, rows 0 .. gk-1 = split-K partials of the cq GEMV), 2 rows per pass
@@ -782,13 +834,13 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, int x
         const CUtensorMap* m = tail ? kvmap + 1 : kvmap;
         uint8_t* dst = ring + (size_t)sl * STAGE;
         mbar_arrive_expect_tx(sy.mb(MB_XA_FULL + sl), tail ? 2 * XA_TAIL * 128 : STAGE);
-        const int slab_ld = (skip & 64) ? (x.slab & 3) : x.slab;  // probe: every CTA streams the same 4 slabs (all L2 hits)
-        if (skip & 64) {
+        const int slab_ld = WXB_SKIP(skip, 64) ? (oslab & 3) : oslab;  // probe: every CTA streams the same 4 slabs (all L2 hits)
+        if (WXB_SKIP(skip, 64)) {
           tma_load_2d(dst, m, sy.mb(MB_XA_FULL + sl), 0, krow0 + slab_ld * T_AUDIO + kk);
           tma_load_2d(dst + XA_HALF, m, sy.mb(MB_XA_FULL + sl), 0, vrow0 + slab_ld * T_AUDIO + kk);
         } else {
-        tma_load_2d_hint(dst, m, sy.mb(MB_XA_FULL + sl), 0, krow0 + x.slab * T_AUDIO + kk, L2_EVICT_FIRST);
-        tma_load_2d_hint(dst + XA_HALF, m, sy.mb(MB_XA_FULL + sl), 0, vrow0 + x.slab * T_AUDIO + kk, L2_EVICT_FIRST);
+        tma_load_2d_hint(dst, m, sy.mb(MB_XA_FULL + sl), 0, krow0 + oslab * T_AUDIO + kk, L2_EVICT_FIRST);
+        tma_load_2d_hint(dst + XA_HALF, m, sy.mb(MB_XA_FULL + sl), 0, vrow0 + oslab * T_AUDIO + kk, L2_EVICT_FIRST);
         }
       }
       __syncwarp();
@@ -796,7 +848,7 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, int x
       kk += XA_KEYS;
       if (kk >= x.k1) {
         ++it;
-        if (it < n_items) { x = xa_item(it, cta, qw, G, P, plen); kk = x.k0; }
+        if (it < n_items) { x = xa_item(it, cta, qw, G, P, plen); kk = x.k0; oslab = orig_slab(x.slab); }
       }
     }
     sy.pre = 0;
@@ -870,7 +922,7 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, int x
 #pragma unroll
         for (int n = 0; n < XA_NS; ++n) {
           sc[n][0] = sc[n][1] = -INFINITY;
-          if (n < ns && act[n] && !(skip & 16)) {
+          if (n < ns && act[n] && !WXB_SKIP(skip, 16)) {
             float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
             mma_16816(c0, ka[n][0], qb[0][0], qb[0][1]);
             mma_16816(c1, ka[n][1], qb[1][0], qb[1][1]);
@@ -900,7 +952,7 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, int x
 #pragma unroll
         for (int n = 0; n < XA_NS; ++n) {
           if (n < ns) {
-            const bool live = act[n] && m > -INFINITY && !(skip & 16);
+            const bool live = act[n] && m > -INFINITY && !WXB_SKIP(skip, 16);
             uint32_t va[4][4];
             if (live) {
 #pragma unroll
@@ -957,7 +1009,7 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, int x
         __syncwarp();
         if (lane == 0) mbar_arrive(sy.mb(MB_ST_FREE + ipar));
         __nv_bfloat16* out = att + (size_t)b * d + h * 64;
-        if (skip & 32) {
+        if (WXB_SKIP(skip, 32)) {
         } else if (x.piece < 0) {
           out[lane] = __float2bfloat16_rn(o0 / Ls);
           out[lane + 32] = __float2bfloat16_rn(o1 / Ls);
@@ -996,34 +1048,80 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, int x
   }
 }
 
-// mlx_whisper_batch_decoder.py:267-303 for one row per CTA: (no_speech_prob from the unfiltered logits,)
-// filters, argmax (first max), logprob accounting, EOT latch.  Row loops keep 8 independent loads in flight.
-__device__ __forceinline__ void sample_phase(const SampleParams& p, int B, int pos, bool do_sample, float* red, int* red_i, const MkSync& sy) {
+// mlx_whisper_batch_decoder.py:267-303 for one row per CTA: (no_speech_prob from the unfiltered logits,) filters, argmax
+// (first max), logprob accounting, EOT latch.  The logits row is read once with 16-byte loads (rows are 16-byte aligned:
+// ldl is a multiple of 4), 4 loads in flight per thread.
+//
+// Timestamp rules (sp.ts_rules, decoding with `without_timestamps=False`), per row, from its sampled tokens seq:
+//   <|notimestamps|> is suppressed; after a timestamp: a second one forbids timestamps, a single one forbids text below eot;
+//   timestamps never decrease (the open half of a pair may repeat, a closed pair must move on); the first sampled token
+//   must be a timestamp <= max_initial_ts; and if logsumexp(timestamp logprobs) > max(text logprob) only timestamps remain
+//   (/root/reference/mlx_ultra_optimized_batch.py:38-71).  Range rules are predicates on the token id (nothing is written
+//   back); the pass keeps (max, first argmax, sum of exponentials) separately for ids below / from ts_begin.
+struct RowStat {
+  float m;  // running maximum
+  int i;    // first index of the maximum
+  float s;  // sum of exp(x - m)
+};
+__device__ __forceinline__ void stat_add(RowStat& a, float v, int idx) {
+  if (v > a.m) {
+    a.s = a.s * __expf(a.m - v) + 1.f;  // a.m = -inf -> s = 0
+    a.m = v; a.i = idx;
+  } else if (v > -INFINITY) {
+    a.s += __expf(v - a.m);
+  }
+}
+__device__ __forceinline__ void stat_merge(RowStat& a, float om, int oi, float os) {
+  if (om > a.m || (om == a.m && oi < a.i)) {
+    a.s = (a.m > -INFINITY ? a.s * __expf(a.m - om) : 0.f) + os;
+    a.m = om; a.i = oi;
+  } else if (om > -INFINITY) {
+    a.s += os * __expf(om - a.m);
+  }
+}
+__device__ __forceinline__ void stat_block(RowStat& a, float* red, int* red_i, float* red_s) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, a.m, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, a.i, o);
+    const float os = __shfl_xor_sync(0xffffffffu, a.s, o);
+    stat_merge(a, ov, oi, os);
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = a.m; red_i[threadIdx.x >> 5] = a.i; red_s[threadIdx.x >> 5] = a.s; }
+  __syncthreads();
+  a.m = red[0]; a.i = red_i[0]; a.s = red_s[0];
+#pragma unroll
+  for (int w = 1; w < MK_WARPS; ++w) stat_merge(a, red[w], red_i[w], red_s[w]);
+}
+
+__device__ __forceinline__ void sample_phase(const SampleParams& p, int B, int pos, bool do_sample, float* red, int* red_i,
+                                             const MkSync& sy) {
   __shared__ float red_s[MK_WARPS];
   const int tid = threadIdx.x;
-  constexpr int U = 8;
+  constexpr int U = 2;  // float4 loads in flight per thread (3 or more cost the persistent kernel a stack frame)
+  const int V4 = (p.V + 3) >> 2;  // the padding elements of the last group are masked by index
   for (int b = sy.cta; b < B; b += sy.nc) {
-    float* x = p.logits + (size_t)b * p.V;
+    float* x = p.logits + (size_t)b * p.ldl;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const int ob = s_rows[b];
     if (p.nsp_out) {
-      float m = -INFINITY;
-      for (int i0 = tid; i0 < p.V; i0 += MK_THREADS * U) {
-        float t[U];
+      RowStat a = {-INFINITY, 0x7fffffff, 0.f};
+      for (int i0 = tid; i0 < V4; i0 += MK_THREADS * U) {
+        float4 t[U];
 #pragma unroll
-        for (int j = 0; j < U; ++j) { const int i = i0 + MK_THREADS * j; t[j] = i < p.V ? __ldcg(x + i) : -INFINITY; }
+        for (int j = 0; j < U; ++j) { const int i = i0 + MK_THREADS * j; t[j] = i < V4 ? __ldcg(x4 + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY); }
 #pragma unroll
-        for (int j = 0; j < U; ++j) m = fmaxf(m, t[j]);
+        for (int j = 0; j < U; ++j) {
+          const int i = 4 * (i0 + MK_THREADS * j);
+          stat_add(a, t[j].x, i);
+          if (i + 1 < p.V) stat_add(a, t[j].y, i + 1);
+          if (i + 2 < p.V) stat_add(a, t[j].z, i + 2);
+          if (i + 3 < p.V) stat_add(a, t[j].w, i + 3);
+        }
       }
-      m = block_max(m, red);
-      float s = 0.f;
-      for (int i0 = tid; i0 < p.V; i0 += MK_THREADS * U) {
-        float t[U];
-#pragma unroll
-        for (int j = 0; j < U; ++j) { const int i = i0 + MK_THREADS * j; t[j] = i < p.V ? __ldcg(x + i) : -INFINITY; }
-#pragma unroll
-        for (int j = 0; j < U; ++j) s += expf(t[j] - m);
-      }
-      s = block_sum(s, red);
-      if (tid == 0) p.nsp_out[b] = expf(__ldcg(x + p.nsp_token) - m) / s;
+      stat_block(a, red, red_i, red_s);
+      if (tid == 0) p.nsp_out[ob] = __expf(__ldcg(x + p.nsp_token) - a.m) / a.s;
     }
     if (!do_sample) continue;
     __syncthreads();
@@ -1035,56 +1133,74 @@ __device__ __forceinline__ void sample_phase(const SampleParams& p, int B, int p
       if (p.blank_token >= 0 && p.blank_token < p.V) x[p.blank_token] = -INFINITY;
       x[p.eot] = -INFINITY;
     }
+    // range rules of this row: ids < lo_text are masked, timestamps in [ts_begin, ts_lo) and ids > ts_hi are masked
+    int lo_text = 0, ts_lo = p.V, ts_hi = p.V - 1, tsb = p.V;
+    const int* row_tok = p.tokens + (size_t)ob * p.stride;
+    if (p.ts_rules) {
+      tsb = p.ts_begin; ts_lo = tsb;
+      if (tid == 0 && p.no_timestamps >= 0 && p.no_timestamps < p.V) x[p.no_timestamps] = -INFINITY;
+      const int n_seq = pos + 1 - p.prompt_len;  // sampled tokens so far
+      const bool last_ts = n_seq >= 1 && __ldcg(row_tok + pos) >= tsb;
+      const bool pen_ts = n_seq < 2 || __ldcg(row_tok + pos - 1) >= tsb;
+      if (last_ts) {
+        if (pen_ts) ts_lo = p.V;   // a closed pair: no timestamp may follow
+        else lo_text = p.eot;      // an open timestamp: no text token below eot may follow
+      }
+      const int tl = __ldcg(p.ts_last + ob);
+      if (tl >= 0) {
+        const int first_ok = (last_ts && !pen_ts) ? tl : tl + 1;  // timestamps must not decrease
+        ts_lo = max(ts_lo, first_ok);
+      }
+      if (n_seq == 0) {
+        lo_text = tsb;  // the first sampled token is a timestamp ...
+        if (p.max_initial_ts >= 0) ts_hi = min(ts_hi, tsb + p.max_initial_ts);  // ... not later than max_initial_timestamp
+      }
+    }
     __syncthreads();
-    // one pass: running (max, first index of the max, sum of exp relative to the max) per thread, merged per block
-    float best = -INFINITY, s = 0.f;
-    int bi = 0x7fffffff;
-    for (int i0 = tid; i0 < p.V; i0 += MK_THREADS * U) {
-      float t[U];
+    RowStat tx = {-INFINITY, 0x7fffffff, 0.f}, tt = {-INFINITY, 0x7fffffff, 0.f};  // ids below / from ts_begin
+    for (int i0 = tid; i0 < V4; i0 += MK_THREADS * U) {
+      float4 t[U];
 #pragma unroll
-      for (int j = 0; j < U; ++j) { const int i = i0 + MK_THREADS * j; t[j] = i < p.V ? __ldcg(x + i) : -INFINITY; }
+      for (int j = 0; j < U; ++j) { const int i = i0 + MK_THREADS * j; t[j] = i < V4 ? __ldcg(x4 + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY); }
 #pragma unroll
       for (int j = 0; j < U; ++j) {
-        const int i = i0 + MK_THREADS * j;  // increasing within the thread: strict > keeps the first maximum
-        if (t[j] > best) {
-          s = s * __expf(best - t[j]) + 1.f;  // best = -inf -> s = 0
-          best = t[j];
-          bi = i;
-        } else if (t[j] > -INFINITY) {
-          s += __expf(t[j] - best);
+        const int i = 4 * (i0 + MK_THREADS * j);  // increasing within the thread: strict > keeps the first maximum
+        const float e[4] = {t[j].x, t[j].y, t[j].z, t[j].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int id = i + q;
+          if (id < tsb) {
+            if (id >= lo_text) stat_add(tx, e[q], id);
+          } else if (id >= ts_lo && id <= ts_hi) {
+            stat_add(tt, e[q], id);
+          }
         }
       }
     }
-    auto merge = [](float& m, int& mi, float& ms, float om, int oi, float os) {
-      if (om > m || (om == m && oi < mi)) {
-        ms = (m > -INFINITY ? ms * __expf(m - om) : 0.f) + os;
-        m = om; mi = oi;
-      } else if (om > -INFINITY) {
-        ms += os * __expf(om - m);
-      }
-    };
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      const float os = __shfl_xor_sync(0xffffffffu, s, o);
-      merge(best, bi, s, ov, oi, os);
-    }
-    __syncthreads();
-    if ((tid & 31) == 0) { red[tid >> 5] = best; red_i[tid >> 5] = bi; red_s[tid >> 5] = s; }
-    __syncthreads();
-    best = red[0]; bi = red_i[0]; s = red_s[0];
-#pragma unroll
-    for (int w = 1; w < MK_WARPS; ++w) merge(best, bi, s, red[w], red_i[w], red_s[w]);
+    stat_block(tx, red, red_i, red_s);
+    if (p.ts_rules) stat_block(tt, red, red_i, red_s);
     if (tid == 0) {
-      const float logprob = -logf(s);  // x[bi] - (best + log(sum)) with x[bi] == best
-      int* row = p.tokens + (size_t)b * p.stride;
+      float best = tx.m, ssum = tx.s;
+      int bi = tx.i;
+      if (p.ts_rules && tt.m > -INFINITY) {
+        // logsumexp over timestamps vs the best text logprob (the common normaliser cancels): timestamps win -> only they remain
+        const bool ts_only = !(tx.m > -INFINITY) || (tt.m + __logf(tt.s) > tx.m);
+        if (ts_only) { best = tt.m; bi = tt.i; ssum = tt.s; }
+        else {
+          RowStat all = tx;
+          stat_merge(all, tt.m, tt.i, tt.s);
+          best = all.m; bi = all.i; ssum = all.s;
+        }
+      }
+      const float logprob = -logf(ssum);  // x[bi] - (best + log(sum)) with x[bi] == best
+      int* row = p.tokens + (size_t)ob * p.stride;
       const int last = __ldcg(row + pos);
       const bool was_eot = (last == p.eot) && (pos >= p.prompt_len);  // prompt tokens never latch
-      if (!was_eot) p.sum_logprob[b] += logprob;
+      if (!was_eot) p.sum_logprob[ob] += logprob;
       const int next = was_eot ? p.eot : bi;
       row[pos + 1] = next;
-      if (next == p.eot) p.done[b] = 1;
+      if (next == p.eot) p.done[ob] = 1;
+      if (p.ts_rules && next >= p.ts_begin) p.ts_last[ob] = next;
     }
     __syncthreads();
   }
@@ -1102,13 +1218,15 @@ struct GemvOp {
   const CUtensorMap *wm, *xm;
   int epi;
 };
+template <int MT>
 __device__ __forceinline__ GemvOp gemv_op(const MkParams& p, int l, int k) {
   const CUtensorMap* lm = p.maps + (size_t)l * TM_PER_LAYER;
-  const CUtensorMap* am = p.maps + (size_t)p.L * TM_PER_LAYER;  // emb, xn, att, hid
+  const CUtensorMap* am = p.maps + (size_t)p.L * TM_PER_LAYER + TM_ACT + (MT - 1) * 3 - 1;  // am[0] unused here, am[1..3] = xn, att, hid of this MT
+  const CUtensorMap* emb = p.maps + (size_t)p.L * TM_PER_LAYER + TM_EMB;
   GemvOp o;
   o.g = (k == 1) ? &p.g_qkv : (k == 9) ? &p.g_fc1 : (k == 10) ? &p.g_fc2 : (k == 12) ? &p.g_logits : &p.g_dd;
   o.wm = (k == 1) ? lm + TM_QKV : (k == 3) ? lm + TM_OUT : (k == 5) ? lm + TM_CQ : (k == 7) ? lm + TM_COUT
-         : (k == 9) ? lm + TM_FC1 : (k == 10) ? lm + TM_FC2 : am;
+         : (k == 9) ? lm + TM_FC1 : (k == 10) ? lm + TM_FC2 : emb;
   o.xm = (k == 3 || k == 7) ? am + 2 : (k == 10) ? am + 3 : am + 1;
   o.epi = (k == 9) ? EPI_GELU_BF16 : (k == 12) ? EPI_LOGITS : EPI_PART;
   return o;
@@ -1119,12 +1237,13 @@ __device__ __forceinline__ GemvOp gemv_op(const MkParams& p, int l, int k) {
 // cross-attention phase.  Every thread calls this and learns the number of stages (sy.pre, skipped by the producer
 // loops of those phases); only `issue` threads touch the barriers and the TMA unit.
 template <int MT>
-__device__ __forceinline__ void pre_issue(const MkParams& p, int l, int k, int xq, uint8_t* ring, MkSync& sy, const bool issue) {
+__device__ __forceinline__ void pre_issue(const MkParams& p, int l, int k, int xq, uint8_t* ring, MkSync& sy,
+                                          const bool issue) {
   const int kind = op_kind(k);
   sy.pre = 0;
-  if (kind == PH_GEMV && !(p.skip & 2)) {
+  if (kind == PH_GEMV && !WXB_SKIP(p.skip, 2)) {
     constexpr int STAGE = GV_A_BYTES + 16 * MT * GV_BK * 2;
-    const GemvOp o = gemv_op(p, l, k);
+    const GemvOp o = gemv_op<MT>(p, l, k);
     const MkGemv& g = *o.g;
     const int tile = sy.cta;
     if (tile >= g.tiles) return;
@@ -1138,12 +1257,12 @@ __device__ __forceinline__ void pre_issue(const MkParams& p, int l, int k, int x
       tma_load_2d(ring + slot * STAGE, o.wm, sy.mb(MB_GV_FULL + slot), k0 + kb * GV_BK, row0);
     }
     sy.pre = n;
-  } else if (kind == PH_CROSS && !(p.skip & 1)) {
+  } else if (kind == PH_CROSS && !WXB_SKIP(p.skip, 1)) {
     constexpr uint32_t STAGE = 2 * XA_HALF;
     const int G = sy.nc, cta = sy.cta;
-    const CUtensorMap* kvmap = p.maps + (size_t)p.L * TM_PER_LAYER + 4;
+    const CUtensorMap* kvmap = p.maps + (size_t)p.L * TM_PER_LAYER + TM_KV;
     const int n_slabs = p.B * p.H, qw = n_slabs / G, r = n_slabs - qw * G;
-    const int krow0 = (l * 2) * n_slabs * T_AUDIO, vrow0 = (l * 2 + 1) * n_slabs * T_AUDIO;
+    const int krow0 = (l * 2) * p.B0 * p.H * T_AUDIO, vrow0 = (l * 2 + 1) * p.B0 * p.H * T_AUDIO;
     int P = 0, plen = T_AUDIO;
     if (r > 0) {
       const int want = (G + r - 1) / r;
@@ -1155,6 +1274,7 @@ __device__ __forceinline__ void pre_issue(const MkParams& p, int l, int k, int x
     int it = 0, n = 0;
     while (it < n_items && n < XA_NST) {
       const XaItem x = xa_item(it, cta, qw, G, P, plen);
+      const int xb = x.slab / p.H, oslab = s_rows[xb] * p.H + (x.slab - xb * p.H);
       for (int kk = x.k0; kk < x.k1 && n < XA_NST; kk += XA_KEYS, ++n) {
         if (!issue) continue;
         const uint32_t c = xa_count0 + (uint32_t)n, sl = c % XA_NST, par = (c / XA_NST) & 1;
@@ -1163,8 +1283,8 @@ __device__ __forceinline__ void pre_issue(const MkParams& p, int l, int k, int x
         const CUtensorMap* m = tail ? kvmap + 1 : kvmap;
         uint8_t* dst = ring + (size_t)sl * STAGE;
         mbar_arrive_expect_tx(sy.mb(MB_XA_FULL + sl), tail ? 2 * XA_TAIL * 128 : STAGE);
-        tma_load_2d_hint(dst, m, sy.mb(MB_XA_FULL + sl), 0, krow0 + x.slab * T_AUDIO + kk, L2_EVICT_FIRST);
-        tma_load_2d_hint(dst + XA_HALF, m, sy.mb(MB_XA_FULL + sl), 0, vrow0 + x.slab * T_AUDIO + kk, L2_EVICT_FIRST);
+        tma_load_2d_hint(dst, m, sy.mb(MB_XA_FULL + sl), 0, krow0 + oslab * T_AUDIO + kk, L2_EVICT_FIRST);
+        tma_load_2d_hint(dst + XA_HALF, m, sy.mb(MB_XA_FULL + sl), 0, vrow0 + oslab * T_AUDIO + kk, L2_EVICT_FIRST);
       }
       ++it;
     }
@@ -1177,8 +1297,8 @@ __device__ __forceinline__ void pre_issue(const MkParams& p, int l, int k, int x
 // k: 0 LN1 | 1 QKV | 2 self-attention | 3 out | 4 LN2 | 5 cq | 6 cross-attention | 7 cout | 8 LN3 | 9 fc1 | 10 fc2
 //    11 final LN | 12 logits | 13 (no_speech_prob,) filters + sampling
 template <int MT>
-__device__ __forceinline__ void run_op(const MkParams& p, const DecLayerW* s_layers, int l, int k, int pos, int xq, uint8_t* ring,
-                                       float* scratch, float* red, int* red_i, MkSync& sy) {
+__device__ __forceinline__ void run_op(const MkParams& p, const DecLayerW* s_layers, int l, int k, int pos, int xq,
+                                       uint8_t* ring, float* scratch, float* red, int* red_i, MkSync& sy) {
   const DecLayerW& w = s_layers[l];
   const int kind = op_kind(k);
 #ifdef WXB_STUB
@@ -1187,7 +1307,7 @@ __device__ __forceinline__ void run_op(const MkParams& p, const DecLayerW* s_lay
   constexpr int stub = 0;
 #endif
   if (kind == PH_LN) {
-    if (!(stub & 8) && !(p.skip & 8)) {
+    if (!(stub & 8) && !WXB_SKIP(p.skip, 8)) {
       // the LayerNorm phase first folds the previous GEMV's split-K partials (+ bias) into the residual row
       const bool from_embed = (k == 0 && l == 0);
       const int gk = (k == 0 || k == 11) ? p.g_fc2.gk : p.g_dd.gk;
@@ -1197,14 +1317,14 @@ __device__ __forceinline__ void run_op(const MkParams& p, const DecLayerW* s_lay
       ln_phase(p, from_embed, gk, pb, lw, lb, pos, red, sy);
     }
   } else if (kind == PH_GEMV) {
-    if (!(stub & 2) && !(p.skip & 2)) {
-      const GemvOp o = gemv_op(p, l, k);
+    if (!(stub & 2) && !WXB_SKIP(p.skip, 2)) {
+      const GemvOp o = gemv_op<MT>(p, l, k);
       gemv_phase<MT>(p, *o.g, o.wm, o.xm, w.fc1_b, o.epi, ring, sy);
     }
   } else if (kind == PH_SELF) {
-    if (!(stub & 4) && !(p.skip & 4)) self_attn_phase(p, l, w.qkv_b, pos, ring, scratch, sy);
+    if (!(stub & 4) && !WXB_SKIP(p.skip, 4)) self_attn_phase(p, l, w.qkv_b, pos, ring, scratch, sy);
   } else if (kind == PH_CROSS) {
-    if (!(stub & 1) && !(p.skip & 1)) cross_attn_phase(p, l, xq, w.cq_b, ring, scratch, sy);
+    if (!(stub & 1) && !WXB_SKIP(p.skip, 1)) cross_attn_phase(p, l, xq, w.cq_b, ring, scratch, sy);
   } else {
     if (!(stub & 16)) sample_phase(p.sp, p.B, pos, p.mode == 2, red, red_i, sy);
   }
@@ -1230,6 +1350,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) dec_step_kernel(const __grid_co
   __shared__ DecLayerW s_layers[MAX_LAYERS];  // pointer table of every layer: no dependent global load per phase
   for (int i = threadIdx.x; i < p.L * (int)(sizeof(DecLayerW) / 8); i += MK_THREADS)
     reinterpret_cast<unsigned long long*>(s_layers)[i] = reinterpret_cast<const unsigned long long*>(p.layers)[i];
+  for (int i = threadIdx.x; i < p.B; i += MK_THREADS) s_rows[i] = p.rows ? p.rows[i] : i;
   const int warp = threadIdx.x >> 5;
   MkSync sy;
   sy.bars = smem_u32(bars);
@@ -1245,7 +1366,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) dec_step_kernel(const __grid_co
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) tmem_alloc(&tmem_slot, 64);
+  if (warp == 2) tmem_alloc(&tmem_slot, GV_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1276,7 +1397,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) dec_step_kernel(const __grid_co
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(sy.tmem, 64);
+    tmem_dealloc(sy.tmem, GV_TMEM_COLS);
   }
 }
 
@@ -1297,27 +1418,31 @@ __global__ void dec_finalize_kernel(const int* __restrict__ tokens, int stride, 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-constexpr int MAX_GROUP = 64;           // sequences per call (4 m16 batch tiles)
 constexpr size_t PART_FLOATS = (size_t)4 << 20;  // 16 MB of fp32 split-K partials per group
 
 struct DecBuffers {
   float *x, *logits, *part, *apart, *sum_lp;
   __nv_bfloat16 *att, *xn, *hid, *self_kv, *cross_kv;
-  int *ticket, *d_pos, *tokens, *done;
+  int *ticket, *d_pos, *tokens, *done, *rows, *ts_last;
   unsigned* bar;
   const DecLayerW* layers;
   const CUtensorMap* maps;
   int B, tok_stride;
+  long long ldl;  // row stride of `logits` (n_vocab rounded up to 4 floats: 16-byte aligned rows)
 };
 
-// profiling aid only (results become meaningless): WXB_DEC_SKIP bitmask, see MkParams::skip
+// profiling aid of -DWXB_PROBE builds only (results become meaningless): WXB_DEC_SKIP bitmask, see MkParams::skip
 int dec_skip_mask() {
+#ifdef WXB_PROBE
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("WXB_DEC_SKIP");
     v = e ? atoi(e) : 0;
   }
   return v;
+#else
+  return 0;
+#endif
 }
 
 // WXB_DEC_PROF=1: CTA 0 of the step kernel records the global timer at every grid barrier; after a decode the
@@ -1332,8 +1457,6 @@ bool dec_prof_enabled() {
 }
 constexpr size_t PROF_SLOTS = 1 << 16;
 struct ProfLast { int mode = 0, n_steps = 0, L = 0; bool nsp = false; unsigned long long* dev = nullptr; } g_prof_last;
-
-const void* g_layers_model = nullptr;  // the model whose DecLayerW table is resident in "dec.layers"
 
 // Pick the split-K factor for y[B, N] = act[B, K] W[N, K]^T on G CTAs (tiles of 128 weight rows x K / gk).
 // Cost model in microseconds: a CTA pulls its weight tile at ~60 KB/us and its activation slice from L2 at
@@ -1357,19 +1480,13 @@ MkGemv plan_gemv(int N, int K, int B, int Bp, int G, bool full_k) {
   return best;
 }
 
-// identity of the tensor-map table resident in "dec.maps"
-struct MapsKey {
-  const void* model = nullptr;
-  const void *xn = nullptr, *att = nullptr, *hid = nullptr, *ckv = nullptr;
-  int B = 0;
-} g_maps_key;
-
 int alloc_buffers(wxb_ctx* ctx, int B, int tok_stride, DecBuffers* o) {
   auto nm = [&](const char* base) { return std::string(base); };
   const wxb_dims& D = ctx->model->dims;
   const int d = D.n_text_state, L = D.n_text_layer, H = D.n_text_head, V = D.n_vocab;
   o->B = B;
   o->tok_stride = tok_stride;
+  o->ldl = ((long long)V + 3) & ~3LL;
   if (B > MAX_GROUP) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: batch %d > %d sequences per call", B, MAX_GROUP);
   if (L > MAX_LAYERS) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: %d layers > %d", L, MAX_LAYERS);
   if (d > 4 * LN_V4 * MK_THREADS || d % 64)
@@ -1379,7 +1496,7 @@ int alloc_buffers(wxb_ctx* ctx, int B, int tok_stride, DecBuffers* o) {
   o->xn = (__nv_bfloat16*)wxb_named(ctx, nm("dec.xn").c_str(), (size_t)B * d * 2);
   o->part = (float*)wxb_named(ctx, nm("dec.part").c_str(), PART_FLOATS * 4);
   o->hid = (__nv_bfloat16*)wxb_named(ctx, nm("dec.hid").c_str(), (size_t)B * 4 * d * 2);
-  o->logits = (float*)wxb_named(ctx, nm("dec.logits").c_str(), (size_t)B * V * 4);
+  o->logits = (float*)wxb_named(ctx, nm("dec.logits").c_str(), (size_t)B * o->ldl * 4);
   o->apart = (float*)wxb_named(ctx, nm("dec.apart").c_str(), (size_t)2 * 1024 * 66 * 4);
   o->sum_lp = (float*)wxb_named(ctx, nm("dec.sum_lp").c_str(), (size_t)B * 4);
   o->self_kv = (__nv_bfloat16*)wxb_named(ctx, nm("dec.self_kv").c_str(), (size_t)L * 2 * B * H * D.n_text_ctx * 64 * 2);
@@ -1389,29 +1506,31 @@ int alloc_buffers(wxb_ctx* ctx, int B, int tok_stride, DecBuffers* o) {
   o->bar = (unsigned*)wxb_named(ctx, "dec.bar", 128, true);  // grid-barrier counter, zeroed before every launch
   o->tokens = (int*)wxb_named(ctx, nm("dec.tokens").c_str(), (size_t)B * tok_stride * 4);
   o->done = (int*)wxb_named(ctx, nm("dec.done").c_str(), (size_t)B * 4);
+  o->rows = (int*)wxb_named(ctx, "dec.rows", (size_t)2 * MAX_GROUP * 4);  // two row lists: a launch may still read the other one
+  o->ts_last = (int*)wxb_named(ctx, "dec.ts_last", (size_t)MAX_GROUP * 4);
   DecLayerW* layers = (DecLayerW*)wxb_named(ctx, "dec.layers", (size_t)L * sizeof(DecLayerW));
   if (!o->x || !o->att || !o->hid || !o->logits || !o->part || !o->apart || !o->sum_lp || !o->self_kv || !o->cross_kv ||
-      !o->ticket || !o->d_pos || !o->bar || !o->tokens || !o->done || !o->xn || !layers)
+      !o->ticket || !o->d_pos || !o->bar || !o->tokens || !o->done || !o->xn || !layers || !o->rows || !o->ts_last)
     return WXB_ERR_CUDA;
-  if (g_layers_model != (const void*)ctx->model) {
+  if (ctx->dec_layers_model != (const void*)ctx->model) {
     std::vector<DecLayerW> h(L);
     for (int l = 0; l < L; ++l) {
       int rc = wxb_dec_layer(ctx, l, &h[l]);
       if (rc != WXB_OK) return rc;
     }
     WXB_CUDA(ctx, cudaMemcpy(layers, h.data(), (size_t)L * sizeof(DecLayerW), cudaMemcpyHostToDevice));
-    g_layers_model = ctx->model;
+    ctx->dec_layers_model = ctx->model;
   }
   o->layers = layers;
-  // tensor maps (128-byte swizzle, 64-element boxes): weights [N, K] in 128-row boxes, activations [B, K] in one
-  // Bp-row box whose rows >= B are zero-filled by the TMA unit
-  const size_t n_maps = (size_t)TM_PER_LAYER * L + 6;
+  // tensor maps (128-byte swizzle, 64-element boxes): weights [N, K] in 128-row boxes, activations [B, K] in boxes of
+  // 16 MT rows (one map per batch-tile count MT = 1 .. 4: a launch over fewer live rows uses the narrower box); rows >= B
+  // are zero-filled by the TMA unit
+  const size_t n_maps = (size_t)TM_PER_LAYER * L + TM_TAIL_COUNT;
   CUtensorMap* maps = (CUtensorMap*)wxb_named(ctx, nm("dec.maps").c_str(), n_maps * sizeof(CUtensorMap));
   if (!maps) return WXB_ERR_CUDA;
-  MapsKey& key = g_maps_key;
+  wxb_dec_maps_key& key = ctx->dec_maps_key;
   if (key.model != (const void*)ctx->model || key.xn != o->xn || key.att != o->att || key.hid != o->hid || key.ckv != o->cross_kv || key.B != B) {
     std::vector<CUtensorMap> h(n_maps);
-    const int Bp = (B + 15) & ~15;
     int rc;
     for (int l = 0; l < L; ++l) {
       DecLayerW w;
@@ -1426,13 +1545,16 @@ int alloc_buffers(wxb_ctx* ctx, int B, int tok_stride, DecBuffers* o) {
     const void* emb = wxb_weight(ctx, "dec.emb");
     if (!emb) return WXB_ERR_STATE;
     CUtensorMap* am = &h[(size_t)TM_PER_LAYER * L];
-    if ((rc = wxb_make_tmap_bf16(ctx, am + 0, emb, (uint64_t)d, (uint64_t)V, (uint64_t)d * 2, GV_BK, GV_ROWS)) != WXB_OK) return rc;
-    if ((rc = wxb_make_tmap_bf16(ctx, am + 1, o->xn, (uint64_t)d, (uint64_t)B, (uint64_t)d * 2, GV_BK, Bp)) != WXB_OK) return rc;
-    if ((rc = wxb_make_tmap_bf16(ctx, am + 2, o->att, (uint64_t)d, (uint64_t)B, (uint64_t)d * 2, GV_BK, Bp)) != WXB_OK) return rc;
-    if ((rc = wxb_make_tmap_bf16(ctx, am + 3, o->hid, (uint64_t)4 * d, (uint64_t)B, (uint64_t)4 * d * 2, GV_BK, Bp)) != WXB_OK) return rc;
-    // cross K/V of all layers as one [rows, 64] tensor read in 112-key boxes (48-key boxes at the end of an item)
-    if ((rc = wxb_make_tmap_bf16(ctx, am + 4, o->cross_kv, 64, (uint64_t)L * 2 * B * H * T_AUDIO, 128, 64, XA_KEYS)) != WXB_OK) return rc;
-    if ((rc = wxb_make_tmap_bf16(ctx, am + 5, o->cross_kv, 64, (uint64_t)L * 2 * B * H * T_AUDIO, 128, 64, XA_TAIL)) != WXB_OK) return rc;
+    if ((rc = wxb_make_tmap_bf16(ctx, am + TM_EMB, emb, (uint64_t)d, (uint64_t)V, (uint64_t)d * 2, GV_BK, GV_ROWS)) != WXB_OK) return rc;
+    for (int mt = 1; mt <= 4; ++mt) {
+      CUtensorMap* a3 = am + TM_ACT + (mt - 1) * 3;
+      if ((rc = wxb_make_tmap_bf16(ctx, a3 + 0, o->xn, (uint64_t)d, (uint64_t)B, (uint64_t)d * 2, GV_BK, 16 * mt)) != WXB_OK) return rc;
+      if ((rc = wxb_make_tmap_bf16(ctx, a3 + 1, o->att, (uint64_t)d, (uint64_t)B, (uint64_t)d * 2, GV_BK, 16 * mt)) != WXB_OK) return rc;
+      if ((rc = wxb_make_tmap_bf16(ctx, a3 + 2, o->hid, (uint64_t)4 * d, (uint64_t)B, (uint64_t)4 * d * 2, GV_BK, 16 * mt)) != WXB_OK) return rc;
+    }
+    // cross K/V of all layers as one [rows, 64] tensor read in full-stage boxes (shorter boxes at the end of an item)
+    if ((rc = wxb_make_tmap_bf16(ctx, am + TM_KV, o->cross_kv, 64, (uint64_t)L * 2 * B * H * T_AUDIO, 128, 64, XA_KEYS)) != WXB_OK) return rc;
+    if ((rc = wxb_make_tmap_bf16(ctx, am + TM_KV + 1, o->cross_kv, 64, (uint64_t)L * 2 * B * H * T_AUDIO, 128, 64, XA_TAIL)) != WXB_OK) return rc;
     WXB_CUDA(ctx, cudaDeviceSynchronize());  // a previous decode may still be reading the old table
     WXB_CUDA(ctx, cudaMemcpy(maps, h.data(), n_maps * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
     key.model = ctx->model; key.xn = o->xn; key.att = o->att; key.hid = o->hid; key.ckv = o->cross_kv; key.B = B;
@@ -1459,15 +1581,17 @@ int cross_kv_precompute(wxb_ctx* ctx, const __nv_bfloat16* enc_out, const DecBuf
   return WXB_OK;
 }
 
-// Launch the persistent step kernel: n_steps consecutive positions starting at *d_pos.
+// Launch the persistent step kernel: n_steps consecutive positions starting at *d_pos, over the n_live rows listed in
+// rows_dev (original row numbers; nullptr = all buf.B rows).
 int launch_steps(wxb_ctx* ctx, const DecBuffers& buf, int mode, int n_steps, const SampleParams& sp, float* logits_out,
-                 long long ldl, cudaStream_t st) {
+                 long long ldl, int n_live, const int* rows_dev, cudaStream_t st) {
   const wxb_dims& D = ctx->model->dims;
-  const int d = D.n_text_state, B = buf.B;
+  const int d = D.n_text_state, B = n_live;
   const int Bp = (B + 15) & ~15, MT = Bp / 16;
   const int G = ctx->sm_count;
   MkParams p = {};
-  p.B = B; p.d = d; p.H = D.n_text_head; p.L = D.n_text_layer; p.V = D.n_vocab; p.TX = D.n_text_ctx;
+  p.B = B; p.B0 = buf.B; p.rows = rows_dev;
+  p.d = d; p.H = D.n_text_head; p.L = D.n_text_layer; p.V = D.n_vocab; p.TX = D.n_text_ctx;
   p.mode = mode; p.n_steps = n_steps; p.skip = dec_skip_mask();
   p.layers = buf.layers; p.maps = buf.maps;
   p.emb = (const __nv_bfloat16*)wxb_weight(ctx, "dec.emb");
@@ -1496,13 +1620,12 @@ int launch_steps(wxb_ctx* ctx, const DecBuffers& buf, int mode, int n_steps, con
   p.sp = sp;
   p.scale = 1.0f / sqrtf(64.f);
   void (*kern)(const MkParams) = MT == 1 ? dec_step_kernel<1> : MT == 2 ? dec_step_kernel<2> : MT == 3 ? dec_step_kernel<3> : dec_step_kernel<4>;
-  static bool attr_set[5] = {false, false, false, false, false};
-  if (!attr_set[MT]) {
-    WXB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MK_SMEM));
+  if (ctx->func_smem.find(reinterpret_cast<const void*>(kern)) == ctx->func_smem.end()) {
+    int rc = wxb_func_smem(ctx, kern, (int)MK_SMEM);
+    if (rc != WXB_OK) return rc;
     int per_sm = 0;
     WXB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MK_THREADS, MK_SMEM));
     if (per_sm < 1) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: persistent step kernel does not fit an SM");
-    attr_set[MT] = true;
   }
   WXB_CUDA(ctx, cudaMemsetAsync(buf.bar, 0, 4, st));
   cudaLaunchConfig_t cfg = {};
@@ -1553,9 +1676,9 @@ int dump_prof(wxb_ctx* ctx) {
 
 }  // namespace
 
-void wxb_decoder_reset_graphs() {
-  g_layers_model = nullptr;
-  g_maps_key = MapsKey();
+void wxb_decoder_reset(wxb_ctx* ctx) {
+  ctx->dec_layers_model = nullptr;
+  ctx->dec_maps_key = wxb_dec_maps_key();
 }
 
 extern "C" int wxb_decode_greedy(wxb_ctx* ctx, const void* enc_out_dev, int B, const int32_t* prompt_host, int prompt_len,
@@ -1572,17 +1695,29 @@ extern "C" int wxb_decode_greedy(wxb_ctx* ctx, const void* enc_out_dev, int B, c
                     sample_len, D.n_text_ctx);
   if (opts->eot < 0 || opts->eot >= D.n_vocab) return wxb_fail(ctx, WXB_ERR_INVALID, "wxb_decode_greedy: eot out of range");
   if (opts->no_speech >= D.n_vocab) return wxb_fail(ctx, WXB_ERR_INVALID, "wxb_decode_greedy: no_speech out of range");
+  if (opts->apply_timestamp_rules && (opts->timestamp_begin <= opts->eot || opts->timestamp_begin >= D.n_vocab))
+    return wxb_fail(ctx, WXB_ERR_INVALID, "wxb_decode_greedy: timestamp_begin %d out of range (eot %d, n_vocab %d)",
+                    opts->timestamp_begin, opts->eot, D.n_vocab);
   cudaStream_t st = (cudaStream_t)stream;
   WXB_CUDA(ctx, cudaSetDevice(ctx->device));
   const int stride = D.n_text_ctx + 1;
   int rc;
   DecBuffers buf;
   if ((rc = alloc_buffers(ctx, B, stride, &buf)) != WXB_OK) return rc;
-  wxb_dec_timing tm;
-  WXB_CUDA(ctx, cudaEventCreate(&tm.e0));
-  WXB_CUDA(ctx, cudaEventCreate(&tm.e1));
-  WXB_CUDA(ctx, cudaEventCreate(&tm.e2));
-  WXB_CUDA(ctx, cudaEventRecord(tm.e0, st));
+  // device-side timing is opt-in (wxb_decode_stats(reset = 1) switches it on); the events belong to the ctx from the moment
+  // they exist, so an error return below cannot leak them
+  wxb_dec_timing* tm = nullptr;
+  if (ctx->dec_timing_on) {
+    if (ctx->dec_timings.size() >= WXB_MAX_DEC_TIMINGS) wxb_dec_timings_clear(ctx);
+    wxb_dec_timing t = {};
+    WXB_CUDA(ctx, cudaEventCreate(&t.e0));
+    if (cudaEventCreate(&t.e1) != cudaSuccess) { cudaEventDestroy(t.e0); return wxb_fail(ctx, WXB_ERR_CUDA, "cudaEventCreate failed"); }
+    if (cudaEventCreate(&t.e2) != cudaSuccess) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); return wxb_fail(ctx, WXB_ERR_CUDA, "cudaEventCreate failed"); }
+    ctx->dec_timings.push_back(t);
+    tm = &ctx->dec_timings.back();
+    // e1 / e2 are recorded below; an early error return leaves them unrecorded, wxb_decode_stats skips such entries
+    WXB_CUDA(ctx, cudaEventRecord(tm->e0, st));
+  }
   // tokens[b, :prompt_len] = prompt; state reset
   std::vector<int> init((size_t)B * stride, opts->eot);
   for (int b = 0; b < B; ++b)
@@ -1591,14 +1726,17 @@ extern "C" int wxb_decode_greedy(wxb_ctx* ctx, const void* enc_out_dev, int B, c
   WXB_CUDA(ctx, cudaMemsetAsync(buf.d_pos, 0, 4, st));
   WXB_CUDA(ctx, cudaMemsetAsync(buf.done, 0, (size_t)B * 4, st));
   WXB_CUDA(ctx, cudaMemsetAsync(buf.sum_lp, 0, (size_t)B * 4, st));
+  WXB_CUDA(ctx, cudaMemsetAsync(buf.ts_last, 0xff, (size_t)MAX_GROUP * 4, st));  // -1: no timestamp sampled yet
   if ((rc = cross_kv_precompute(ctx, (const __nv_bfloat16*)enc_out_dev, buf, st)) != WXB_OK) return rc;
   SampleParams sp = {};
-  sp.logits = buf.logits; sp.V = D.n_vocab; sp.tokens = buf.tokens; sp.stride = stride;
+  sp.logits = buf.logits; sp.ldl = buf.ldl; sp.V = D.n_vocab; sp.tokens = buf.tokens; sp.stride = stride;
   sp.prompt_len = prompt_len; sp.eot = opts->eot; sp.suppress_blank = opts->suppress_blank; sp.blank_token = opts->blank_token;
   sp.n_suppress = opts->n_suppress; sp.suppress = opts->suppress_dev; sp.sum_logprob = buf.sum_lp; sp.done = buf.done;
   sp.nsp_out = nullptr; sp.nsp_token = opts->no_speech;
+  sp.ts_rules = opts->apply_timestamp_rules ? 1 : 0; sp.ts_begin = opts->timestamp_begin; sp.no_timestamps = opts->no_timestamps;
+  sp.max_initial_ts = opts->max_initial_timestamp_index; sp.ts_last = buf.ts_last;
   WXB_CUDA(ctx, cudaStreamSynchronize(st));  // `init` is pageable host memory
-  WXB_CUDA(ctx, cudaEventRecord(tm.e1, st));
+  if (tm) WXB_CUDA(ctx, cudaEventRecord(tm->e1, st));
 
   const bool want_nsp = (opts->no_speech >= 0 && no_speech_prob_dev);
   // prompt positions 0 .. prompt_len-2 (forced tokens); logits only at position 0 for no_speech_prob
@@ -1606,33 +1744,47 @@ extern "C" int wxb_decode_greedy(wxb_ctx* ctx, const void* enc_out_dev, int B, c
     SampleParams s1 = sp;
     const bool nsp = (pos == 0 && want_nsp);
     if (nsp) s1.nsp_out = no_speech_prob_dev;
-    if ((rc = launch_steps(ctx, buf, nsp ? 1 : 0, 1, s1, buf.logits, D.n_vocab, st)) != WXB_OK) return rc;
+    if ((rc = launch_steps(ctx, buf, nsp ? 1 : 0, 1, s1, buf.logits, buf.ldl, B, nullptr, st)) != WXB_OK) return rc;
   }
+  // Sampling loop.  Every `check_every` positions the host reads the EOT flags (mlx_whisper_batch_decoder.py:357) and the
+  // next launch runs over the rows that are still live (:37-100: finished sequences leave the batch; their K/V slabs are
+  // no longer streamed and their GEMV / LayerNorm / attention work disappears).
   const int check_every = opts->check_every > 0 ? opts->check_every : 16;
-  std::vector<int> done_host(B);
-  int n_sampled = 0;
+  std::vector<int> done_host(B), live(B);
+  for (int b = 0; b < B; ++b) live[b] = b;
+  int n_live = B, n_sampled = 0, flip = 0;
+  const int* rows_dev = nullptr;  // identity
   while (n_sampled < sample_len) {
     // a single-token prompt makes the SOT position the first sampling position: that step also emits no_speech_prob
     const bool nsp_now = (n_sampled == 0 && prompt_len == 1 && want_nsp);
     const int n = nsp_now ? 1 : std::min(check_every, sample_len - n_sampled);
     SampleParams s1 = sp;
     if (nsp_now) s1.nsp_out = no_speech_prob_dev;
-    if ((rc = launch_steps(ctx, buf, 2, n, s1, buf.logits, D.n_vocab, st)) != WXB_OK) return rc;
+    if ((rc = launch_steps(ctx, buf, 2, n, s1, buf.logits, buf.ldl, n_live, rows_dev, st)) != WXB_OK) return rc;
     n_sampled += n;
     if (n_sampled < sample_len && !nsp_now) {
       WXB_CUDA(ctx, cudaMemcpyAsync(done_host.data(), buf.done, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
       WXB_CUDA(ctx, cudaStreamSynchronize(st));
-      bool all = true;
-      for (int b = 0; b < B; ++b) all = all && done_host[b];
-      if (all) break;  // mlx_whisper_batch_decoder.py:357
+      int m = 0;
+      for (int i = 0; i < n_live; ++i)
+        if (!done_host[live[i]]) live[m++] = live[i];
+      if (m == 0) break;  // every row has emitted EOT
+      if (m < n_live && !opts->no_compaction) {
+        n_live = m;
+        int* dst = buf.rows + (flip ? MAX_GROUP : 0);
+        flip ^= 1;
+        WXB_CUDA(ctx, cudaMemcpyAsync(dst, live.data(), (size_t)n_live * 4, cudaMemcpyHostToDevice, st));
+        rows_dev = dst;
+      }
     }
   }
   dec_finalize_kernel<<<B, 256, 0, st>>>(buf.tokens, stride, prompt_len, n_sampled, sample_len, opts->eot, tokens_out_dev, n_tokens_dev);
   WXB_LAUNCH_CHECK(ctx);
   WXB_CUDA(ctx, cudaMemcpyAsync(sum_logprob_dev, buf.sum_lp, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
-  WXB_CUDA(ctx, cudaEventRecord(tm.e2, st));
-  tm.steps = prompt_len - 1 + n_sampled;
-  ctx->dec_timings.push_back(tm);
+  if (tm) {
+    WXB_CUDA(ctx, cudaEventRecord(tm->e2, st));
+    tm->steps = prompt_len - 1 + n_sampled;
+  }
   if (dec_prof_enabled()) return dump_prof(ctx);
   return WXB_OK;
 }
@@ -1642,6 +1794,7 @@ extern "C" int wxb_decode_stats(wxb_ctx* ctx, double* cross_kv_ms, double* steps
   double a = 0, b = 0;
   int64_t n = 0;
   for (auto& t : ctx->dec_timings) {
+    if (t.steps <= 0) continue;  // a call that failed before its last event was recorded
     WXB_CUDA(ctx, cudaEventSynchronize(t.e2));
     float x = 0.f, y = 0.f;
     WXB_CUDA(ctx, cudaEventElapsedTime(&x, t.e0, t.e1));
@@ -1652,8 +1805,8 @@ extern "C" int wxb_decode_stats(wxb_ctx* ctx, double* cross_kv_ms, double* steps
   if (steps_ms) *steps_ms = b;
   if (n_steps) *n_steps = n;
   if (reset) {
-    for (auto& t : ctx->dec_timings) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); cudaEventDestroy(t.e2); }
-    ctx->dec_timings.clear();
+    wxb_dec_timings_clear(ctx);
+    ctx->dec_timing_on = true;  // timing is opt-in: the first reset switches it on
   }
   return WXB_OK;
 }
@@ -1675,6 +1828,6 @@ extern "C" int wxb_decoder_logits(wxb_ctx* ctx, const void* enc_out_dev, int B, 
   if ((rc = cross_kv_precompute(ctx, (const __nv_bfloat16*)enc_out_dev, buf, st)) != WXB_OK) return rc;
   SampleParams sp = {};
   for (int pos = 0; pos < n_tok; ++pos)
-    if ((rc = launch_steps(ctx, buf, 1, 1, sp, logits_out_dev + (size_t)pos * D.n_vocab, (long long)n_tok * D.n_vocab, st)) != WXB_OK) return rc;
+    if ((rc = launch_steps(ctx, buf, 1, 1, sp, logits_out_dev + (size_t)pos * D.n_vocab, (long long)n_tok * D.n_vocab, B, nullptr, st)) != WXB_OK) return rc;
   return WXB_OK;
 }

@@ -108,175 +108,6 @@ layernorm_bf16_kernel(const float* __restrict__ x, const float* __restrict__ w, 
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Non-causal multi-head attention over T = 1500 positions, head_dim 64 (v1: flash-style online
-// softmax on mma.sync m16n8k16 bf16; 128 query rows per CTA, 64-key tiles double-buffered with
-// cp.async, XOR-swizzled shared memory for conflict-free ldmatrix).
-// ---------------------------------------------------------------------------------------------
-constexpr int ATT_BQ = 128, ATT_BK = 64, ATT_THREADS = 256;
-
-__device__ __forceinline__ void ldsm_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x4_t(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-__device__ __forceinline__ void mma_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void cp_async16(uint32_t smem, const void* gmem, int src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem), "l"(gmem), "r"(src_bytes));
-}
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-// tile of [rows][64] bf16, 128 B per row, 16-byte chunk c of row r stored at chunk c ^ (r & 7)
-__device__ __forceinline__ uint32_t sw_off(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
-
-// load `rows` x 64 bf16 starting at global row `g0` (row stride ld elements) into a swizzled tile;
-// rows >= g_end are zero-filled
-__device__ __forceinline__ void load_tile_async(uint32_t smem_base, const __nv_bfloat16* gbase, long long ld, int g0,
-                                                int g_end, int rows, int tid) {
-  for (int idx = tid; idx < rows * 8; idx += ATT_THREADS) {
-    const int r = idx >> 3, c = idx & 7;
-    const int gr = g0 + r;
-    const bool ok = gr < g_end;
-    const __nv_bfloat16* src = gbase + (long long)(ok ? gr : (g_end - 1)) * ld + c * 8;
-    cp_async16(smem_base + sw_off(r, c), src, ok ? 16 : 0);
-  }
-}
-
-__global__ void __launch_bounds__(ATT_THREADS)
-attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T, int d, float scale_log2) {
-  extern __shared__ __align__(128) uint8_t att_smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int g = lane >> 2, t4 = lane & 3;
-  const int q0 = blockIdx.x * ATT_BQ, h = blockIdx.y, b = blockIdx.z;
-  const long long ld = 3LL * d;
-  const __nv_bfloat16* qb = qkv + (long long)b * T * ld + h * 64;
-  const __nv_bfloat16* kb = qb + d;
-  const __nv_bfloat16* vb = qb + 2 * d;
-  const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(att_smem);
-  const uint32_t sK = sQ + ATT_BQ * 128;            // 2 buffers of 64 x 128 B
-  const uint32_t sV = sK + 2 * ATT_BK * 128;        // 2 buffers
-  const int nkt = (T + ATT_BK - 1) / ATT_BK;
-
-  load_tile_async(sQ, qb, ld, q0, T, ATT_BQ, tid);
-  load_tile_async(sK, kb, ld, 0, T, ATT_BK, tid);
-  load_tile_async(sV, vb, ld, 0, T, ATT_BK, tid);
-  asm volatile("cp.async.commit_group;");
-
-  uint32_t qf[4][4];
-  float o[8][4];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-  float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
-
-  for (int kt = 0; kt < nkt; ++kt) {
-    asm volatile("cp.async.wait_group 0;");
-    __syncthreads();
-    if (kt + 1 < nkt) {
-      const int nb = (kt + 1) & 1;
-      load_tile_async(sK + nb * ATT_BK * 128, kb, ld, (kt + 1) * ATT_BK, T, ATT_BK, tid);
-      load_tile_async(sV + nb * ATT_BK * 128, vb, ld, (kt + 1) * ATT_BK, T, ATT_BK, tid);
-      asm volatile("cp.async.commit_group;");
-    }
-    if (kt == 0) {
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        const int m = lane >> 3;
-        const int row = warp * 16 + (m & 1) * 8 + (lane & 7);
-        ldsm_x4(qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], sQ + sw_off(row, ks * 2 + (m >> 1)));
-      }
-    }
-    const uint32_t cK = sK + (kt & 1) * ATT_BK * 128, cV = sV + (kt & 1) * ATT_BK * 128;
-    float s[8][4];
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-      uint32_t bf[8];
-      const int krow = nt * 8 + (lane & 7);
-      const int m = lane >> 3;
-      ldsm_x4(bf[0], bf[1], bf[2], bf[3], cK + sw_off(krow, m));
-      ldsm_x4(bf[4], bf[5], bf[6], bf[7], cK + sw_off(krow, 4 + m));
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) mma_16816(s[nt], qf[ks], bf[2 * ks], bf[2 * ks + 1]);
-    }
-    // mask keys beyond T (only the last tile)
-    const int kbase = kt * ATT_BK;
-    if (kbase + ATT_BK > T) {
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const int k0 = kbase + nt * 8 + 2 * t4;
-        if (k0 >= T) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
-        if (k0 + 1 >= T) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
-      }
-    }
-    float mx_lo = -INFINITY, mx_hi = -INFINITY;
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      mx_lo = fmaxf(mx_lo, fmaxf(s[nt][0], s[nt][1]));
-      mx_hi = fmaxf(mx_hi, fmaxf(s[nt][2], s[nt][3]));
-    }
-    mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1));
-    mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
-    mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
-    mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
-    const float mn_lo = fmaxf(m_lo, mx_lo), mn_hi = fmaxf(m_hi, mx_hi);
-    const float a_lo = exp2f((m_lo - mn_lo) * scale_log2), a_hi = exp2f((m_hi - mn_hi) * scale_log2);
-    m_lo = mn_lo; m_hi = mn_hi;
-    const float off_lo = mn_lo * scale_log2, off_hi = mn_hi * scale_log2;
-    float sum_lo = 0.f, sum_hi = 0.f;
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      s[nt][0] = exp2f(s[nt][0] * scale_log2 - off_lo);
-      s[nt][1] = exp2f(s[nt][1] * scale_log2 - off_lo);
-      s[nt][2] = exp2f(s[nt][2] * scale_log2 - off_hi);
-      s[nt][3] = exp2f(s[nt][3] * scale_log2 - off_hi);
-      sum_lo += s[nt][0] + s[nt][1];
-      sum_hi += s[nt][2] + s[nt][3];
-    }
-    l_lo = l_lo * a_lo + sum_lo;
-    l_hi = l_hi * a_hi + sum_hi;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { o[i][0] *= a_lo; o[i][1] *= a_lo; o[i][2] *= a_hi; o[i][3] *= a_hi; }
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      uint32_t pa[4];
-      pa[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
-      pa[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
-      pa[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-      pa[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-#pragma unroll
-      for (int dp = 0; dp < 4; ++dp) {
-        const int m = lane >> 3;
-        const int vrow = kk * 16 + (m & 1) * 8 + (lane & 7);
-        uint32_t v0, v1, v2, v3;
-        ldsm_x4_t(v0, v1, v2, v3, cV + sw_off(vrow, 2 * dp + (m >> 1)));
-        mma_16816(o[2 * dp], pa, v0, v1);
-        mma_16816(o[2 * dp + 1], pa, v2, v3);
-      }
-    }
-  }
-  // row sums live spread over the 4 lanes of a quad
-  l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1);
-  l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
-  l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1);
-  l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
-  const float inv_lo = 1.f / l_lo, inv_hi = 1.f / l_hi;
-  const int r_lo = q0 + warp * 16 + g, r_hi = r_lo + 8;
-  __nv_bfloat16* ob = out + (long long)b * T * d + h * 64;
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt) {
-    const int col = nt * 8 + 2 * t4;
-    if (r_lo < T) *reinterpret_cast<uint32_t*>(ob + (long long)r_lo * d + col) = pack_bf16(o[nt][0] * inv_lo, o[nt][1] * inv_lo);
-    if (r_hi < T) *reinterpret_cast<uint32_t*>(ob + (long long)r_hi * d + col) = pack_bf16(o[nt][2] * inv_hi, o[nt][3] * inv_hi);
-  }
-}
-
 int launch_layernorm(wxb_ctx* ctx, const float* x, const float* w, const float* b, __nv_bfloat16* y, long long rows, int d,
                      cudaStream_t st) {
   if (d % 4 || d > 128 * 10) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "layernorm: d=%d", d);
@@ -289,17 +120,7 @@ int launch_layernorm(wxb_ctx* ctx, const float* x, const float* w, const float* 
 
 }  // namespace
 
-int wxb_attention_tc(wxb_ctx* ctx, const __nv_bfloat16* qkv, __nv_bfloat16* vT, __nv_bfloat16* out, int B, int T, int d, int H,
-                     cudaStream_t st);  // wxb_attn.cu
-
-static bool use_tc_attention() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("WXB_ATTN");
-    v = (e && e[0] == 'm') ? 0 : 1;  // WXB_ATTN=mma selects the older mma.sync kernel (A/B timing only)
-  }
-  return v == 1;
-}
+int wxb_attention_tc(wxb_ctx* ctx, const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int d, int H, cudaStream_t st);  // wxb_attn.cu
 
 // exported to wxb_decoder.cu
 int wxb_launch_layernorm(wxb_ctx* ctx, const float* x, const float* w, const float* b, __nv_bfloat16* y, long long rows,
@@ -320,8 +141,7 @@ int wxb_encode_impl(wxb_ctx* ctx, const float* mel_dev, int B, __nv_bfloat16* en
   __nv_bfloat16* qkv = (__nv_bfloat16*)wxb_named(ctx, "enc.qkv", M * 3 * d * 2);
   __nv_bfloat16* att = (__nv_bfloat16*)wxb_named(ctx, "enc.att", M * d * 2);
   __nv_bfloat16* hid = (__nv_bfloat16*)wxb_named(ctx, "enc.hid", M * 4 * d * 2);
-  __nv_bfloat16* vT = (__nv_bfloat16*)wxb_named(ctx, "enc.vT", (size_t)B * H * 64 * 1504 * 2);
-  if (!melT || !h1 || !x || !xn || !qkv || !att || !hid || !vT) return WXB_ERR_CUDA;
+  if (!melT || !h1 || !x || !xn || !qkv || !att || !hid) return WXB_ERR_CUDA;
 
   const __nv_bfloat16* c1w = (const __nv_bfloat16*)wxb_weight(ctx, "enc.conv1.w");
   const float* c1b = (const float*)wxb_weight(ctx, "enc.conv1.b");
@@ -355,8 +175,6 @@ int wxb_encode_impl(wxb_ctx* ctx, const float* mel_dev, int B, __nv_bfloat16* en
     a.g_in = T_AUDIO + 1; a.g_valid = T_AUDIO; a.g_out = T_AUDIO; a.out_off = 0;
     if ((rc = wxb_gemm_launch(ctx, a, st)) != WXB_OK) return rc;
   }
-  const float scale_log2 = (1.0f / sqrtf(64.f)) * 1.44269504088896341f;
-  const int att_smem = ATT_BQ * 128 + 4 * ATT_BK * 128;
   for (int l = 0; l < D.n_audio_layer; ++l) {
     EncLayerW w;
     if ((rc = wxb_enc_layer(ctx, l, &w)) != WXB_OK) return rc;
@@ -367,12 +185,7 @@ int wxb_encode_impl(wxb_ctx* ctx, const float* mel_dev, int B, __nv_bfloat16* en
       a.out = qkv; a.ldo = 3 * d;
       if ((rc = wxb_gemm_launch(ctx, a, st)) != WXB_OK) return rc;
     }
-    if (use_tc_attention()) {
-      if ((rc = wxb_attention_tc(ctx, qkv, vT, att, B, T_AUDIO, d, H, st)) != WXB_OK) return rc;
-    } else {
-      attention_kernel<<<dim3(ceil_div(T_AUDIO, ATT_BQ), H, B), ATT_THREADS, att_smem, st>>>(qkv, att, T_AUDIO, d, scale_log2);
-      WXB_LAUNCH_CHECK(ctx);
-    }
+    if ((rc = wxb_attention_tc(ctx, qkv, att, B, T_AUDIO, d, H, st)) != WXB_OK) return rc;
     {
       GemmArgs a;
       a.A = att; a.lda = d; a.M = (int)M; a.W = w.out_w; a.N = d; a.K = d; a.bias = w.out_b;
@@ -401,33 +214,12 @@ extern "C" int wxb_encoder_attention(wxb_ctx* ctx, const void* qkv_dev, void* ou
   if (!qkv_dev || !out_dev || B <= 0 || T <= 0 || H <= 0 || d != 64 * H)
     return wxb_fail(ctx, WXB_ERR_INVALID, "wxb_encoder_attention: bad argument (head_dim must be 64)");
   WXB_CUDA(ctx, cudaSetDevice(ctx->device));
-  cudaStream_t st = (cudaStream_t)stream;
-  if (use_tc_attention()) {
-    const int Tpad = (T + 7) & ~7;
-    __nv_bfloat16* vT = (__nv_bfloat16*)wxb_named(ctx, "enc.vT", (size_t)B * H * 64 * Tpad * 2);
-    if (!vT) return WXB_ERR_CUDA;
-    return wxb_attention_tc(ctx, (const __nv_bfloat16*)qkv_dev, vT, (__nv_bfloat16*)out_dev, B, T, d, H, st);
-  }
-  static bool attr = false;
-  if (!attr) {
-    WXB_CUDA(ctx, cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BQ * 128 + 4 * ATT_BK * 128));
-    attr = true;
-  }
-  const float scale_log2 = (1.0f / sqrtf(64.f)) * 1.44269504088896341f;
-  attention_kernel<<<dim3(ceil_div(T, ATT_BQ), H, B), ATT_THREADS, ATT_BQ * 128 + 4 * ATT_BK * 128, st>>>(
-      (const __nv_bfloat16*)qkv_dev, (__nv_bfloat16*)out_dev, T, d, scale_log2);
-  WXB_LAUNCH_CHECK(ctx);
-  return WXB_OK;
+  return wxb_attention_tc(ctx, (const __nv_bfloat16*)qkv_dev, (__nv_bfloat16*)out_dev, B, T, d, H, (cudaStream_t)stream);
 }
 
 extern "C" int wxb_encode(wxb_ctx* ctx, const float* mel_dev, int B, void* enc_out_dev, void* stream) {
   if (!ctx) return WXB_ERR_INVALID;
   if (!mel_dev || !enc_out_dev || B <= 0) return wxb_fail(ctx, WXB_ERR_INVALID, "wxb_encode: bad argument");
   WXB_CUDA(ctx, cudaSetDevice(ctx->device));
-  static bool attr = false;
-  if (!attr) {
-    WXB_CUDA(ctx, cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_BQ * 128 + 4 * ATT_BK * 128));
-    attr = true;
-  }
   return wxb_encode_impl(ctx, mel_dev, B, (__nv_bfloat16*)enc_out_dev, (cudaStream_t)stream);
 }

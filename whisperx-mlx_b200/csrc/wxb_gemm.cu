@@ -21,6 +21,7 @@
 #include "wxb_gemm.cuh"
 #include "wxb_tc.cuh"
 #include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -362,6 +363,15 @@ int wxb_make_tmap_bf16(wxb_ctx* ctx, CUtensorMap* tm, const void* base, uint64_t
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (row_stride_bytes & 15))
     return wxb_fail(ctx, WXB_ERR_INVALID, "TMA operand must be 16-byte aligned (base %p, row stride %llu B)", base,
                     (unsigned long long)row_stride_bytes);
+  // encoded maps are cached per ctx: the encoder makes ~200 GEMM calls per pass over a handful of (buffer, shape) pairs
+  char keybuf[160];
+  snprintf(keybuf, sizeof(keybuf), "%p/%llu/%llu/%llu/%u/%u", base, (unsigned long long)inner, (unsigned long long)rows,
+           (unsigned long long)row_stride_bytes, box_inner, box_rows);
+  auto hit = ctx->tmap_cache.find(keybuf);
+  if (hit != ctx->tmap_cache.end()) {
+    memcpy(tm, hit->second.data(), sizeof(CUtensorMap));
+    return WXB_OK;
+  }
   cuuint64_t gdim[2] = {inner, rows};
   cuuint64_t gstride[1] = {row_stride_bytes};
   cuuint32_t box[2] = {box_inner, box_rows};
@@ -372,6 +382,10 @@ int wxb_make_tmap_bf16(wxb_ctx* ctx, CUtensorMap* tm, const void* base, uint64_t
   if (r != CUDA_SUCCESS)
     return wxb_fail(ctx, WXB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) inner=%llu rows=%llu stride=%llu", (int)r,
                     (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)row_stride_bytes);
+  if (ctx->tmap_cache.size() > 4096) ctx->tmap_cache.clear();
+  std::vector<unsigned char>& slot = ctx->tmap_cache[keybuf];
+  slot.resize(sizeof(CUtensorMap));
+  memcpy(slot.data(), tm, sizeof(CUtensorMap));
   return WXB_OK;
 }
 
@@ -381,10 +395,9 @@ template <int BN, int STAGES, bool PAIR>
 int launch_cfg(wxb_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
   using L = SmemLayout<BN, STAGES, PAIR>;
   auto kern = gemm_tc_kernel<BN, STAGES, PAIR>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    WXB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    attr_set = true;
+  {
+    int rc = wxb_func_smem(ctx, kern, L::TOTAL);
+    if (rc != WXB_OK) return rc;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(NTHREADS);

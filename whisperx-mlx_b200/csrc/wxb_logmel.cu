@@ -217,7 +217,7 @@ int wxb_logmel_raw(wxb_ctx* ctx, const float* audio_dev, const int64_t* chunk_of
   WXB_CUDA(ctx, cudaMemcpyAsync(d_len, chunk_len_host, (size_t)n_chunks * 4, cudaMemcpyHostToDevice, st));
   logmel_setup_kernel<<<1, 128, 0, st>>>(filters_dev, n_mels, (int2*)ctx->ws_mel_band.p, d_max, n_chunks);
   WXB_LAUNCH_CHECK(ctx);
-  WXB_CUDA(ctx, cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LmSmem)));
+  if ((rc = wxb_func_smem(ctx, logmel_kernel, (int)sizeof(LmSmem))) != WXB_OK) return rc;
   dim3 grid(ceil_div(n_frames, LM_FRAMES), n_chunks);
   logmel_kernel<<<grid, LM_THREADS, sizeof(LmSmem), st>>>(audio_dev, d_off, d_len, n_samples_padded, n_frames,
                                                          n_mels, filters_dev, (const int2*)ctx->ws_mel_band.p,

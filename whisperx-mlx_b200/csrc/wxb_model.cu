@@ -1,10 +1,10 @@
 // wxb_model.cu — wxb_set_model: records the borrowed device pointers by name.
 #include "wxb_model.cuh"
 
-void wxb_decoder_reset_graphs();  // wxb_decoder.cu: captured step graphs hold weight pointers
+void wxb_decoder_reset(wxb_ctx* ctx);  // wxb_decoder.cu: the cached layer / tensor-map tables hold weight pointers
 
 void wxb_model_free(wxb_ctx* ctx) {
-  wxb_decoder_reset_graphs();
+  wxb_decoder_reset(ctx);
   delete ctx->model;
   ctx->model = nullptr;
 }

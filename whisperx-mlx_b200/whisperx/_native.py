@@ -33,7 +33,9 @@ class Dims(C.Structure):
 class DecodeOpts(C.Structure):
     _fields_ = [("eot", C.c_int32), ("no_speech", C.c_int32), ("sample_len", C.c_int32),
                 ("suppress_blank", C.c_int32), ("blank_token", C.c_int32), ("n_suppress", C.c_int32),
-                ("suppress_dev", C.c_void_p), ("check_every", C.c_int32)]
+                ("suppress_dev", C.c_void_p), ("check_every", C.c_int32), ("no_compaction", C.c_int32),
+                ("apply_timestamp_rules", C.c_int32), ("timestamp_begin", C.c_int32), ("no_timestamps", C.c_int32),
+                ("max_initial_timestamp_index", C.c_int32)]
 
 
 def load_library(path: Optional[str] = None):
@@ -43,6 +45,9 @@ def load_library(path: Optional[str] = None):
         if _lib is not None and path is None:
             return _lib
         p = path or os.environ.get("WXB200_LIB", _LIB_PATH)
+        if path is None and "WXB200_LIB" in os.environ:
+            import sys
+            print(f"[whisperx b200] WXB200_LIB set: loading {p} instead of the in-tree library", file=sys.stderr)
         if not os.path.exists(p):
             raise WxbError(
                 f"libwxb200.so not found at {p}: build it with `python __graft_entry__.py` "
@@ -79,8 +84,9 @@ def load_library(path: Optional[str] = None):
         lib.wxb_gemm_bf16.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
         lib.wxb_encoder_attention.restype = i32
         lib.wxb_encoder_attention.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
-        if lib.wxb_abi_version() != 1:
+        if lib.wxb_abi_version() != 2:
             raise WxbError("libwxb200.so ABI version mismatch")
+        lib._wxb_path = os.path.abspath(p)
         if path is None:
             _lib = lib
         return lib
@@ -117,6 +123,7 @@ class Context:
             raise WxbError(self.lib.wxb_last_error(None).decode())
         self.h = h
         self._keep: Dict[str, object] = {}
+        self.model_owner = None  # the object (backend) whose weight table is resident, see set_model
 
     def close(self):
         if getattr(self, "h", None):
@@ -195,7 +202,9 @@ class Context:
         return x
 
     # ---------------------------------------------------------------- K2 / K3
-    def set_model(self, dims: dict, tensors: Dict[str, torch.Tensor]):
+    def set_model(self, dims: dict, tensors: Dict[str, torch.Tensor], owner=None):
+        """Borrow `tensors` as the resident model.  `owner` tags whose model it is: a Context is shared by everything on
+        its GPU, so callers that keep a model across calls re-bind when the owner changed (B200WhisperBackend._bind)."""
         d = Dims(**{k: int(dims[k]) for k, _ in Dims._fields_})
         names = list(tensors.keys())
         for k in names:
@@ -205,7 +214,9 @@ class Context:
         arr_p = (C.c_void_p * len(names))(*[tensors[n].data_ptr() for n in names])
         self._keep["model"] = tensors  # the library borrows the pointers
         self._keep["dims"] = dict(dims)
+        self.model_owner = None
         self._check(self.lib.wxb_set_model(self.h, C.byref(d), arr_n, arr_p, len(names)))
+        self.model_owner = owner
 
     def encode(self, mel_dev: torch.Tensor) -> torch.Tensor:
         """mel f32 cuda [B, n_mels, 3000] -> bf16 cuda [B, 1500, d]."""
@@ -218,7 +229,9 @@ class Context:
 
     def decode_greedy(self, enc_out: torch.Tensor, prompt, eot: int, no_speech: int = -1, sample_len: int = 224,
                       suppress_blank: bool = False, blank_token: int = 220, suppress_tokens=(),
-                      check_every: int = 16):
+                      check_every: int = 16, compaction: bool = True, timestamp_rules: Optional[dict] = None):
+        """timestamp_rules = dict(timestamp_begin=, no_timestamps=, max_initial_timestamp_index=) switches
+        ApplyTimestampRules on (decode with timestamps); None = off (prompt ends with <|notimestamps|>)."""
         assert enc_out.is_cuda and enc_out.dtype == torch.bfloat16 and enc_out.is_contiguous()
         B = enc_out.shape[0]
         dev = self.device
@@ -226,7 +239,14 @@ class Context:
         sup = torch.tensor(list(suppress_tokens), dtype=torch.int32, device=dev) if len(suppress_tokens) else None
         opts = DecodeOpts(eot=eot, no_speech=no_speech, sample_len=sample_len, suppress_blank=int(suppress_blank),
                           blank_token=blank_token, n_suppress=0 if sup is None else sup.numel(),
-                          suppress_dev=None if sup is None else sup.data_ptr(), check_every=check_every)
+                          suppress_dev=None if sup is None else sup.data_ptr(), check_every=check_every,
+                          no_compaction=0 if compaction else 1)
+        if timestamp_rules:
+            opts.apply_timestamp_rules = 1
+            opts.timestamp_begin = int(timestamp_rules["timestamp_begin"])
+            opts.no_timestamps = int(timestamp_rules.get("no_timestamps", -1))
+            mi = timestamp_rules.get("max_initial_timestamp_index", 50)
+            opts.max_initial_timestamp_index = -1 if mi is None else int(mi)
         tokens = torch.full((B, sample_len), eot, dtype=torch.int32, device=dev)
         n_tok = torch.zeros((B,), dtype=torch.int32, device=dev)
         sum_lp = torch.zeros((B,), dtype=torch.float32, device=dev)

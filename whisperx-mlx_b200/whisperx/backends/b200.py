@@ -22,6 +22,9 @@ from . import b200_weights as bw
 from .base import WhisperBackend
 
 
+MAX_BATCH = 64  # sequences per wxb_decode_greedy call
+
+
 class B200WhisperBackend(WhisperBackend):
     def __init__(self, model: str, device: str = "cuda", device_index: int = 0, compute_type: str = "bfloat16",
                  download_root: Optional[str] = None, local_files_only: bool = False, threads: int = 4,
@@ -44,12 +47,17 @@ class B200WhisperBackend(WhisperBackend):
             for k in ("suppress_blank", "suppress_tokens", "sample_len", "without_timestamps"):
                 if k in asr_options and asr_options[k] is not None:
                     self.options[k] = asr_options[k]
-        if self.options["suppress_tokens"] == [-1]:
-            self.options["suppress_tokens"] = []  # "-1" = tokenizer's non-speech set: needs a real vocabulary
+        if list(self.options["suppress_tokens"]) == [-1]:
+            # "-1" = the tokenizer's non-speech symbol set (the reference's default): it is a property of a real vocabulary file
+            warnings.warn("suppress_tokens=[-1] (the tokenizer's non-speech set) needs a real vocabulary; no token is suppressed "
+                          "- pass explicit ids to suppress")
+            self.options["suppress_tokens"] = []
+        self.options["without_timestamps"] = bool(self.options["without_timestamps"])
         self.specials = bw.special_tokens(self.dims)
         self.tokenizer = tokenizer or Tokenizer(self.specials, self.dims["n_vocab"])
         self.kernel_weights = self._load_weights(weights, seed)
-        self.ctx.set_model(self.dims, self.kernel_weights)
+        bw.validate_kernel_weights(self.kernel_weights, self.dims)
+        self._bind()
         self._filters = mel_filters(self.device, self.dims["n_mels"])
         self.align_model = kwargs.get("align_model")  # optional (model, metadata) for _align_words
         self.last_stats: Dict[str, Any] = {}
@@ -65,9 +73,17 @@ class B200WhisperBackend(WhisperBackend):
             weights = sd.get("model_state_dict", sd)
         if any(k.startswith("model.encoder.") for k in weights):
             weights = bw.from_hf_state_dict(weights)
-        if "enc.conv1.w" in weights:  # already in kernel layout
-            return {k: v.to(self.device).contiguous() for k, v in weights.items()}
+        if "enc.conv1.w" in weights:  # already in kernel layout: cast to the dtypes the kernels read
+            exp = bw.expected_kernel_tensors(self.dims)
+            return {k: v.to(device=self.device, dtype=exp[k][1] if k in exp else v.dtype).contiguous() for k, v in weights.items()}
         return bw.to_kernel_layout(weights, self.dims, self.device)
+
+    def _bind(self):
+        """Make this backend's model the one resident in the (process-wide, per-GPU) context.  Several backends may share a
+        GPU: whichever runs re-binds its own weight table first (a pointer table, no copies), so one backend can never
+        transcribe with another one's weights or dims."""
+        if self.ctx.model_owner is not self:
+            self.ctx.set_model(self.dims, self.kernel_weights, owner=self)
 
     # ------------------------------------------------------------------ interface properties
     @property
@@ -129,16 +145,20 @@ class B200WhisperBackend(WhisperBackend):
                 return None  # a gap, a reordering, or a chunk clipped to 30 s
             addr += int(l) * 4
         total = (addr - start) // 4
-        return np.lib.stride_tricks.as_strided(first, shape=(total,), strides=(4,), writeable=False)
+        return np.lib.stride_tricks.as_strided(first, shape=(total,), strides=(4,))  # read below, never written
 
     def transcribe_device(self, audio_dev: torch.Tensor, offs: np.ndarray, lens: np.ndarray, batch_size: int,
                           language: str, task: str):
         """mel -> encode -> greedy decode for chunks already resident in HBM.  Returns device tensors
         (tokens [n, sample_len], n_tokens, sum_logprob, no_speech_prob)."""
-        prompt = self.tokenizer.prompt(language, task, self.options["without_timestamps"])
+        self._bind()
+        without_ts = self.options["without_timestamps"]
+        prompt = self.tokenizer.prompt(language, task, without_ts)
         n = len(offs)
         out = {"tokens": [], "n_tokens": [], "sum_logprob": [], "no_speech_prob": []}
-        batch_size = min(int(batch_size), 64)  # sequences per wxb_decode_greedy call (include/wxb200.h)
+        batch_size = int(batch_size)
+        if not 1 <= batch_size <= MAX_BATCH:
+            raise ValueError(f"batch_size={batch_size}: the decoder takes 1..{MAX_BATCH} sequences per call (include/wxb200.h)")
         for i in range(0, n, batch_size):
             j = min(n, i + batch_size)
             mel = self.ctx.logmel(audio_dev, offs[i:j], lens[i:j], N_SAMPLES, self.dims["n_mels"], self._filters)
@@ -147,7 +167,10 @@ class B200WhisperBackend(WhisperBackend):
                                        sample_len=int(self.options["sample_len"]),
                                        suppress_blank=bool(self.options["suppress_blank"]),
                                        blank_token=self.specials["blank"],
-                                       suppress_tokens=tuple(self.options["suppress_tokens"]))
+                                       suppress_tokens=tuple(self.options["suppress_tokens"]),
+                                       timestamp_rules=None if without_ts else dict(
+                                           timestamp_begin=self.specials["timestamp_begin"],
+                                           no_timestamps=self.specials["no_timestamps"], max_initial_timestamp_index=50))
             for k in out:
                 out[k].append(r[k])
         return {k: torch.cat(v, 0) for k, v in out.items()}
@@ -210,6 +233,7 @@ class B200WhisperBackend(WhisperBackend):
         """Language-id step: one decoder position on [sot]; argmax over the language tokens."""
         if not self.is_multilingual:
             return "en"
+        self._bind()
         audio = np.asarray(audio, dtype=np.float32)[:N_SAMPLES]
         audio_dev, offs, lens = self.upload_chunks([audio])
         mel = self.ctx.logmel(audio_dev, offs, lens, N_SAMPLES, self.dims["n_mels"], self._filters)

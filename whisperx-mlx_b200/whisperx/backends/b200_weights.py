@@ -198,6 +198,55 @@ def to_kernel_layout(w: Dict[str, torch.Tensor], dims: Dict[str, int], device) -
     return out
 
 
+def expected_kernel_tensors(dims: Dict[str, int]) -> Dict[str, tuple]:
+    """name -> (shape, dtype) of every tensor wxb_set_model borrows for these dims (the library reads them through raw
+    pointers, so a checkpoint of another architecture or dtype must be rejected before it gets there)."""
+    bf, f32 = torch.bfloat16, torch.float32
+    exp: Dict[str, tuple] = {}
+    d, nm = dims["n_audio_state"], dims["n_mels"]
+    exp["enc.conv1.w"], exp["enc.conv1.b"] = ((d, 3 * nm), bf), ((d,), f32)
+    exp["enc.conv2.w"], exp["enc.conv2.b"] = ((d, 3 * d), bf), ((d,), f32)
+    exp["enc.pos"] = ((dims["n_audio_ctx"], d), f32)
+
+    def block(p, width, cross):
+        for ln in (".ln1", ".ln2") + ((".ln3",) if cross else ()):
+            exp[p + ln + ".w"], exp[p + ln + ".b"] = ((width,), f32), ((width,), f32)
+        exp[p + ".qkv.w"], exp[p + ".qkv.b"] = ((3 * width, width), bf), ((3 * width,), f32)
+        exp[p + ".out.w"], exp[p + ".out.b"] = ((width, width), bf), ((width,), f32)
+        if cross:
+            exp[p + ".cq.w"], exp[p + ".cq.b"] = ((width, width), bf), ((width,), f32)
+            exp[p + ".ckv.w"], exp[p + ".ckv.b"] = ((2 * width, width), bf), ((2 * width,), f32)
+            exp[p + ".cout.w"], exp[p + ".cout.b"] = ((width, width), bf), ((width,), f32)
+        exp[p + ".fc1.w"], exp[p + ".fc1.b"] = ((4 * width, width), bf), ((4 * width,), f32)
+        exp[p + ".fc2.w"], exp[p + ".fc2.b"] = ((width, 4 * width), bf), ((width,), f32)
+
+    for i in range(dims["n_audio_layer"]):
+        block(f"enc.{i}", d, False)
+    exp["enc.ln_post.w"], exp["enc.ln_post.b"] = ((d,), f32), ((d,), f32)
+    t = dims["n_text_state"]
+    exp["dec.emb"] = ((dims["n_vocab"], t), bf)
+    exp["dec.pos"] = ((dims["n_text_ctx"], t), f32)
+    for i in range(dims["n_text_layer"]):
+        block(f"dec.{i}", t, True)
+    exp["dec.ln.w"], exp["dec.ln.b"] = ((t,), f32), ((t,), f32)
+    return exp
+
+
+def validate_kernel_weights(k: Dict[str, torch.Tensor], dims: Dict[str, int]) -> None:
+    """Raise ValueError unless `k` holds exactly the tensors of expected_kernel_tensors(dims), on a CUDA device, contiguous."""
+    exp = expected_kernel_tensors(dims)
+    missing = sorted(set(exp) - set(k))
+    if missing:
+        raise ValueError(f"weights: {len(missing)} tensors missing for these dims, e.g. {missing[:4]}")
+    for name, (shape, dtype) in exp.items():
+        t = k[name]
+        if tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            raise ValueError(f"weights: '{name}' is {tuple(t.shape)} {t.dtype}, expected {tuple(shape)} {dtype} "
+                             "(checkpoint of another architecture, or not in kernel layout)")
+        if not t.is_cuda or not t.is_contiguous():
+            raise ValueError(f"weights: '{name}' must be a contiguous CUDA tensor")
+
+
 def random_kernel_weights_on_device(dims: Dict[str, int], device, seed: int = 0, std: float = 0.02):
     """Large models: draw the random-init weights directly on the GPU in kernel layout (avoids a
     multi-GB CPU generate + copy).  Same tensor set as to_kernel_layout(init_random_weights(...))."""
