@@ -173,6 +173,16 @@ int wxb_decode_stats(wxb_ctx* ctx, double* cross_kv_ms, double* steps_ms, int64_
 int wxb_decoder_logits(wxb_ctx* ctx, const void* enc_out_dev, int B, const int32_t* tokens_host,
                        int n_tok, float* logits_out_dev, void* stream);
 
+/* The decoder's sampling phase on its own, for parity tests of the greedy update rule on arbitrary logits
+ * (mlx_whisper_batch_decoder.py:267-303 + the filters of wxb_decode_opts): reads row b of logits_dev f32 [B, ldl]
+ * (ldl % 4 == 0, 16-byte aligned; static filters are applied IN PLACE), the row's last token tokens_dev[b, pos],
+ * writes tokens_dev[b, pos + 1], adds the token's log-prob to sum_logprob_dev[b] unless the row had already
+ * emitted EOT, sets done_dev[b] on EOT, updates ts_last_dev[b] (last sampled timestamp, -1 = none; timestamp
+ * rules only) and, if opts->no_speech >= 0 and no_speech_prob_dev != NULL, the unfiltered no-speech probability. */
+int wxb_decoder_sample(wxb_ctx* ctx, float* logits_dev, int64_t ldl, int B, int n_vocab, int32_t* tokens_dev,
+                       int stride, int pos, int prompt_len, const wxb_decode_opts* opts, float* sum_logprob_dev,
+                       int32_t* done_dev, int32_t* ts_last_dev, float* no_speech_prob_dev, void* stream);
+
 /* Stand-alone bf16 GEMM used by the encoder (exposed for parity tests and roofline timing):
  * D[M,N] = A[M,K] * W[N,K]^T (+bias[N]) (GELU) ; A,W bf16 row-major, D bf16 or f32.
  * flags: bit0 = GELU, bit1 = output f32. */

@@ -93,9 +93,10 @@ class DecoderCache:
         self.pos = 0
 
 
-def decoder_forward(w, dims, tokens: torch.Tensor, cache: DecoderCache) -> torch.Tensor:
+def decoder_forward(w, dims, tokens: torch.Tensor, cache: DecoderCache, positions=None) -> torch.Tensor:
     """tokens int64 [B, n] appended at positions cache.pos.. ; returns f32 logits [B, n, V]
-    (tied output head, HF modeling_whisper.py:971)."""
+    (tied output head, HF modeling_whisper.py:971).  `positions` (indices into the n new tokens) limits the vocabulary
+    projection to those positions: logits [B, len(positions), V]."""
     B, n = tokens.shape
     pos0 = cache.pos
     x = w["decoder.token_embedding.weight"][tokens] + w["decoder.positional_embedding"][pos0:pos0 + n][None]
@@ -114,6 +115,8 @@ def decoder_forward(w, dims, tokens: torch.Tensor, cache: DecoderCache) -> torch
         h = _ln(x, w[p + ".mlp_ln.weight"], w[p + ".mlp_ln.bias"])
         x = x + _lin(F.gelu(_lin(h, w, p + ".mlp.0")), w, p + ".mlp.2")
     cache.pos += n
+    if positions is not None:
+        x = x[:, list(positions)]
     x = _ln(x, w["decoder.ln.weight"], w["decoder.ln.bias"])
     return (x @ w["decoder.token_embedding.weight"].t()).float()
 
@@ -149,6 +152,40 @@ def apply_timestamp_rules(logits: torch.Tensor, sampled: torch.Tensor, eot: int,
     max_text = logprobs[:, :ts_begin].max(-1, keepdim=True).values
     logits[:, :ts_begin] = torch.where(ts_lp > max_text, torch.full_like(logits[:, :ts_begin], -float("inf")), logits[:, :ts_begin])
     return logits
+
+
+def greedy_update(last: torch.Tensor, logits: torch.Tensor, sum_lp: torch.Tensor, eot: int):
+    """BatchGreedyDecoder.update, mlx_whisper_batch_decoder.py:267-303: argmax, logprob of the chosen token added unless the
+    row's last token is EOT, rows at EOT keep emitting EOT.  Returns (next [B], completed [B], sum_logprob [B])."""
+    nxt = logits.argmax(-1)
+    lp = logits - torch.logsumexp(logits, -1, keepdim=True)
+    cur = lp[torch.arange(logits.shape[0]), nxt]
+    not_eot = last != eot
+    sum_lp = sum_lp + torch.where(not_eot, cur, torch.zeros_like(cur))
+    nxt = torch.where(last == eot, torch.full_like(nxt, eot), nxt)
+    return nxt, nxt == eot, sum_lp
+
+
+def greedy_loop(logits_fn, prompt: torch.Tensor, eot: int, no_speech: int, sample_len: int, n_ctx: int = 448):
+    """BatchDecodingTask._main_loop_batch, mlx_whisper_batch_decoder.py:317-384, over `logits_fn(step, tokens, active)`
+    -> f32 [B, V] (rows of inactive sequences are zeros there, :91-98).  Filters are the caller's business.  Note the
+    in-tree loop takes no_speech_prob from the FIRST SAMPLING step's logits (:347-352)."""
+    tokens = prompt.clone()
+    B = tokens.shape[0]
+    sum_lp = torch.zeros(B)
+    logits = logits_fn(0, tokens, torch.ones(B, dtype=torch.bool))
+    nxt, done, sum_lp = greedy_update(tokens[:, -1], logits, sum_lp, eot)
+    tokens = torch.cat([tokens, nxt[:, None]], 1)
+    nsp = torch.softmax(logits, -1)[:, no_speech] if no_speech >= 0 else torch.full((B,), float("nan"))
+    steps = 1
+    for i in range(1, sample_len):
+        if bool(done.all()) or tokens.shape[-1] > n_ctx:
+            break
+        logits = logits_fn(i, tokens, ~done)
+        steps += 1
+        nxt, done, sum_lp = greedy_update(tokens[:, -1], logits, sum_lp, eot)
+        tokens = torch.cat([tokens, nxt[:, None]], 1)
+    return tokens, sum_lp, nsp, steps
 
 
 def greedy_decode(w, dims, enc_out: torch.Tensor, prompt: List[int], eot: int, no_speech: int = -1,
@@ -187,10 +224,7 @@ def greedy_decode(w, dims, enc_out: torch.Tensor, prompt: List[int], eot: int, n
                                   timestamp_rules.get("max_initial_timestamp_index", 50))
         if return_logits:
             step_logits.append(logits.clone())
-        nxt = logits.argmax(-1)
-        lp = logits - torch.logsumexp(logits, -1, keepdim=True)
-        sum_lp = sum_lp + lp[torch.arange(B), nxt] * (last != eot)
-        nxt = torch.where(last == eot, torch.full_like(nxt, eot), nxt)
+        nxt, _, sum_lp = greedy_update(last, logits, sum_lp, eot)
         sampled.append(nxt)
         last = nxt
         if bool((last == eot).all()):

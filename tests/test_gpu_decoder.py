@@ -30,6 +30,10 @@ def _dims(name):
         # one-layer encoder of the same width, so the CPU oracle stays small
         return dict(n_mels=128, n_audio_ctx=1500, n_audio_state=1280, n_audio_head=20, n_audio_layer=1,
                     n_vocab=51866, n_text_ctx=448, n_text_state=1280, n_text_head=20, n_text_layer=4)
+    if name == "large-v3-dec":
+        # the 32-layer decoder of large-v3 (BASELINE config 3) behind a one-layer encoder of the same width
+        return dict(n_mels=128, n_audio_ctx=1500, n_audio_state=1280, n_audio_head=20, n_audio_layer=1,
+                    n_vocab=51866, n_text_ctx=448, n_text_state=1280, n_text_head=20, n_text_layer=32)
     return bw.dims_for(name)
 
 
@@ -159,3 +163,176 @@ def test_greedy_scripted_tokens_identical(wxb_ctx, B):
     assert identical == B
     assert torch.allclose(r["sum_logprob"].cpu(), ref["sum_logprob"], rtol=1e-2, atol=1e-3)
     assert torch.allclose(r["no_speech_prob"].cpu(), ref["no_speech_prob"], rtol=0.05, atol=1e-7)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Long positions: the benchmark decodes to position 227 and the model allows 448; everything the self-attention phase does
+# once the cache is longer than one staging round (cp.async ring, split over the warps of a CTA, KV append) is only
+# exercised there.
+# ---------------------------------------------------------------------------------------------------------------------
+LONG_POS = (0, 1, 15, 16, 17, 31, 32, 33, 47, 48, 63, 64, 65, 127, 128, 129, 223, 224, 225, 226, 227, 300, 446, 447)
+
+
+@pytest.mark.parametrize("name,B,n_tok", [("mini", 3, 228), ("mini", 3, 448), ("tiny", 19, 228), ("tiny", 19, 448), ("wide", 60, 448),
+                                          ("turbo-dec", 8, 228), ("large-v3-dec", 8, 40)])
+def test_teacher_forced_logits_long_positions(wxb_ctx, name, B, n_tok):
+    """Teacher-forced logits vs the oracle at positions up to n_tok - 1 (all of them for the small vocabulary, the LONG_POS
+    subset for 51 865-token models).  ("turbo-dec", 8) is the decoder of BASELINE config 4, ("large-v3-dec", 8) the 32-layer
+    decoder of config 3 (batch 8) behind a one-layer encoder."""
+    big = name in ("wide", "turbo-dec", "large-v3-dec")
+    dims, w_ref, enc, ow = _setup(wxb_ctx, name, B, std=0.02 if big else 0.05)
+    toks = np.random.RandomState(1).randint(0, dims["n_vocab"], size=(B, n_tok)).astype(np.int32)
+    pos = [p for p in LONG_POS if p < n_tok] if dims["n_vocab"] > 5000 or name == "wide" else list(range(n_tok))
+    got = wxb_ctx.decoder_logits(enc, toks)[:, pos].float().cpu()
+    with torch.no_grad():
+        cache = ow.DecoderCache(w_ref, dims, enc.float().cpu())
+        ref = ow.decoder_forward(w_ref, dims, torch.from_numpy(toks).long(), cache, positions=pos)
+    err = (got - ref).abs()
+    sigma = float(ref.std())
+    worst = int(err.amax(dim=(0, 2)).argmax())
+    print(f"[{name} B={B} n_tok={n_tok}] logits max-abs err {float(err.max()):.4f} (at position {pos[worst]}), mean {float(err.mean()):.5f}, "
+          f"logit std {sigma:.3f}; err at last position {float(err[:, -1].max()):.4f}")
+    assert float(err.max()) <= 0.05 * max(sigma, 1.0) + 0.02, float(err.max())
+    assert float(err.mean()) <= 0.006 * max(sigma, 1.0) + 0.002
+    # the argmax agrees wherever the oracle's top-2 margin exceeds the measured error
+    top2 = torch.topk(ref, 2, -1)
+    clear = (top2.values[..., 0] - top2.values[..., 1]) > 2.5 * float(err.max())
+    assert bool((got.argmax(-1)[clear] == top2.indices[..., 0][clear]).all())
+
+
+def test_greedy_margin_aware_full_length(wxb_ctx):
+    """Free-running greedy over all 224 sampled positions (mlx_whisper_batch_decoder.py:355-384 runs to sample_len = 224):
+    every step where the kernel's token differs from the oracle's argmax (teacher-forced on the kernel's tokens) must be a
+    near-tie; sum_logprob accumulates over the whole length."""
+    B, sample_len = 3, 224
+    dims, w_ref, enc, ow = _setup(wxb_ctx, "tiny", B)
+    eot, no_speech, prompt = 50257, 50362, [50258, 50259, 50359, 50363]
+    r = wxb_ctx.decode_greedy(enc, prompt, eot, no_speech=no_speech, sample_len=sample_len, suppress_blank=True, blank_token=220)
+    got = r["tokens"].cpu().numpy()
+    n_exact = n_tie = 0
+    with torch.no_grad():
+        cache = ow.DecoderCache(w_ref, dims, enc.float().cpu())
+        cur = ow.decoder_forward(w_ref, dims, torch.tensor(prompt)[None].expand(B, -1).contiguous(), cache)[:, -1].clone()
+        sum_lp = torch.zeros(B)
+        alive = torch.ones(B, dtype=torch.bool)
+        for i in range(sample_len):
+            if i == 0:
+                cur[:, 220] = -float("inf"); cur[:, eot] = -float("inf")
+            lp = cur - torch.logsumexp(cur, -1, keepdim=True)
+            top = torch.topk(cur, 2, -1)
+            for b in range(B):
+                tok = int(got[b, i])
+                if not alive[b]:
+                    assert tok == eot
+                    continue
+                if tok == int(top.indices[b, 0]):
+                    n_exact += 1
+                else:
+                    margin = float(top.values[b, 0] - cur[b, tok])
+                    assert margin < 0.05, f"row {b} step {i}: kernel token {tok} loses by {margin:.4f} (not a near-tie)"
+                    print(f"DIVERGENCE row {b} step {i}: kernel {tok} vs oracle {int(top.indices[b, 0])}, oracle margin {margin:.5f}")
+                    n_tie += 1
+                sum_lp[b] += lp[b, tok]
+                if tok == eot:
+                    alive[b] = False
+            if i + 1 < sample_len:
+                cur = ow.decoder_forward(w_ref, dims, torch.from_numpy(got[:, i:i + 1]).long(), cache)[:, -1].clone()
+    print(f"[tiny, 224 positions] greedy steps exact {n_exact}, near-tie divergences {n_tie}")
+    assert torch.allclose(r["sum_logprob"].cpu(), sum_lp, rtol=2e-3, atol=0.3)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Ragged EOT + active-sequence compaction (mlx_whisper_batch_decoder.py:37-100).  Weights and the encoder output are
+# engineered so that every row's argmax has a large margin at every step and rows of different groups emit EOT at
+# different steps: the scripted token of position p is aligned with the positional embedding of p; <eot>'s embedding is
+# alpha * u with u orthogonal to all of that; the u-component of the residual stream is S(p) + g_b where S is a staircase
+# over positions (built into the positional table) and g_b enters through layer 0's cross-attention (W_v = W_o = I, every
+# encoder frame of row b equal to g_b * u), so group k crosses the EOT threshold exactly at its own step.
+# ---------------------------------------------------------------------------------------------------------------------
+def _ragged_script(dims, prompt_len, eot, eot_steps, first_tok, stride_tok, alpha=4.0, M=4.0):
+    d, n_ctx = dims["n_text_state"], dims["n_text_ctx"]
+    u = torch.ones(d)
+    u[1::2] = -1.0
+    u = u / u.norm()
+    thresholds = [prompt_len - 1 + i for i in eot_steps]  # decoder position that samples EOT for group k
+    theta = 0.05 * d / alpha
+
+    def mutate(w, dims_):
+        g = torch.Generator().manual_seed(99)
+        r = torch.randn(n_ctx, d, generator=g)
+        perp = r - (r @ u)[:, None] * u[None]
+        perp = perp * (d ** 0.5 / perp.norm(dim=1, keepdim=True))  # |perp[p]|^2 = d exactly: the scripted logit is the same at every position
+        S = torch.tensor([M * sum(1 for t in thresholds if t <= p) for p in range(n_ctx)])
+        w["decoder.positional_embedding"] = perp + S[:, None] * u[None]
+        emb = w["decoder.token_embedding.weight"]
+        for p in range(n_ctx):
+            emb[first_tok + stride_tok * p] = 0.05 * perp[p]
+        emb[eot] = alpha * u
+        for k in list(w):
+            if k.endswith("_ln.weight") and k.startswith("decoder") or k == "decoder.ln.weight":
+                w[k] = torch.ones_like(w[k])
+            if k.endswith("_ln.bias") and k.startswith("decoder") or k == "decoder.ln.bias":
+                w[k] = torch.zeros_like(w[k])
+        eye = torch.eye(d)
+        w["decoder.blocks.0.cross_attn.value.weight"] = eye.clone()
+        w["decoder.blocks.0.cross_attn.value.bias"] = torch.zeros(d)
+        w["decoder.blocks.0.cross_attn.out.weight"] = eye.clone()
+        w["decoder.blocks.0.cross_attn.out.bias"] = torch.zeros(d)
+
+    def enc_for(B):
+        gb = torch.tensor([theta - M * ((b % len(eot_steps)) + 0.5) for b in range(B)])
+        e = gb[:, None] * u[None]                                  # [B, d]
+        return e[:, None, :].expand(B, 1500, d).contiguous().to(torch.bfloat16)
+
+    return mutate, enc_for
+
+
+@pytest.mark.parametrize("name,B", [("tiny", 60), ("wide", 60), ("mini", 7)])
+def test_ragged_eot_compaction_identical_tokens(wxb_ctx, name, B):
+    from oracle import whisper as ow
+    from whisperx.backends import b200_weights as bw
+    dims = _dims(name)
+    V = dims["n_vocab"]
+    eot = 50257 if V > 50000 else 3
+    prompt = [50258, 50259, 50359, 50363] if V > 50000 else [1, 2, 4]
+    first_tok, stride_tok = (1000, 7) if V > 50000 else (10, 2)
+    eot_steps = [5, 21, 37, 60, 90, 130, 170, 200]
+    sample_len = 224
+    # small random weights elsewhere: the self-attention / MLP contributions along u must stay far below the staircase height
+    mutate, enc_for = _ragged_script(dims, len(prompt), eot, eot_steps, first_tok, stride_tok, M=2.0 if name == "mini" else 4.0)
+    w = bw.init_random_weights(dims, seed=5, std=0.02 if name == "mini" else 0.006)
+    mutate(w, dims)
+    kw = bw.to_kernel_layout(w, dims, "cuda")
+    wxb_ctx.set_model(dims, kw)
+    w_ref = bw.kernel_layout_to_openai_fp32(kw, dims)
+    enc = enc_for(B).cuda()
+    wxb_ctx.decode_stats(reset=True)
+    r_on = wxb_ctx.decode_greedy(enc, prompt, eot, sample_len=sample_len, check_every=16)
+    _, ms_on, steps_on = wxb_ctx.decode_stats(reset=True)
+    r_off = wxb_ctx.decode_greedy(enc, prompt, eot, sample_len=sample_len, check_every=16, compaction=False)
+    _, ms_off, steps_off = wxb_ctx.decode_stats(reset=True)
+    G = min(B, len(eot_steps))  # rows b and b + 8 see identical inputs: the oracle runs one row per group
+    with torch.no_grad():
+        ref = ow.greedy_decode(w_ref, dims, enc[:G].float().cpu(), prompt, eot, sample_len=sample_len)
+    got, n_tok = r_on["tokens"].cpu().numpy(), r_on["n_tokens"].cpu().numpy()
+    identical = 0
+    for b in range(B):
+        k = b % len(eot_steps)
+        want = ref["tokens"][k]
+        assert len(want) == eot_steps[k], f"oracle row {b}: {len(want)} tokens, script says {eot_steps[k]}"
+        assert want == [first_tok + stride_tok * (len(prompt) - 1 + i) for i in range(eot_steps[k])]
+        same = got[b, :n_tok[b]].tolist() == want and (got[b, n_tok[b]:] == eot).all()
+        identical += int(same)
+        if not same:
+            print(f"DIVERGENCE row {b}: kernel n={n_tok[b]} vs oracle n={len(want)}")
+    print(f"[{name} B={B}] ragged EOT: {identical}/{B} rows identical to the oracle; decode steps {steps_on}: "
+          f"{ms_on:.2f} ms with compaction vs {ms_off:.2f} ms without")
+    assert identical == B
+    # compaction changes WHICH rows ride along, never a live row's result
+    assert torch.equal(r_on["tokens"], r_off["tokens"]) and torch.equal(r_on["n_tokens"], r_off["n_tokens"])
+    assert torch.allclose(r_on["sum_logprob"], r_off["sum_logprob"], rtol=1e-4, atol=1e-4)
+    ref_lp = torch.stack([ref["sum_logprob"][b % len(eot_steps)] for b in range(B)])
+    assert torch.allclose(r_on["sum_logprob"].cpu(), ref_lp, rtol=1e-2, atol=2e-2)
+    assert steps_on == steps_off == len(prompt) - 1 + 208  # the last group finishes at sampled step 200: launches of 16 up to 208
+    if name == "wide":
+        assert ms_on < 0.9 * ms_off, "step time must fall as rows finish (cross-K/V of finished rows is no longer streamed)"

@@ -115,3 +115,35 @@ def test_large_v3_batch8_properties(wxb_ctx):
     r2 = wxb_ctx.decode_greedy(enc, prompt, sp["eot"], no_speech=sp["no_speech"], sample_len=24, suppress_blank=True,
                                blank_token=sp["blank"])
     assert torch.equal(r["tokens"], r2["tokens"]) and torch.equal(r["sum_logprob"], r2["sum_logprob"])
+
+
+def test_large_v3_encoder_vs_oracle(wxb_ctx):
+    """BASELINE config 3's encoder (32 layers, d = 1280, 20 heads, 128 mel bins) against the fp32 oracle on the same
+    bf16-rounded weights: one full 30 s chunk and one 9 s chunk.  This is the only place the 2-CTA GEMM, the d = 1280
+    LayerNorm and 20-head attention run as a 32-layer stack against an independent implementation.  Tolerance = the bf16
+    budget of 32 pre-LN layers (activations rounded to bf16 at every GEMM input, fp32 residual stream), stated relative to
+    the output scale (ln_post output is O(1))."""
+    from oracle import whisper as ow
+    from whisperx.backends import b200_weights as bw
+    import whisperx.audio as wa
+    dims = dict(bw.dims_for("large-v3"))
+    dims["n_text_layer"] = 1  # the decoder is not under test here: keep the CPU weight set small
+    w = bw.init_random_weights(dims, seed=3, std=0.02)
+    kw = bw.to_kernel_layout(w, dims, "cuda")
+    del w
+    wxb_ctx.set_model(dims, kw)
+    chunks = [synthetic_speech(30.0, seed=21), synthetic_speech(9.0, seed=22)]
+    mel = wa.log_mel_chunks(chunks, 128)
+    got = wxb_ctx.encode(mel).float().cpu()
+    assert got.shape == (2, 1500, 1280)
+    w_ref = bw.kernel_layout_to_openai_fp32(kw, dims)
+    with torch.no_grad():
+        ref, layers = ow.encoder_forward(w_ref, dims, mel.cpu(), return_layers=True)
+    err = (got - ref).abs()
+    scale = float(ref.abs().max())
+    rel_l2 = float((got - ref).norm() / ref.norm())
+    print(f"[large-v3 encoder, 32 layers] max-abs err {float(err.max()):.4f} (mean {float(err.mean()):.5f}, relative L2 {rel_l2:.5f}) "
+          f"at output scale {scale:.2f}; residual-stream scale before ln_post {float(layers[-1].abs().max()):.1f}")
+    assert float(err.max()) <= 0.1 * max(1.0, scale), float(err.max())
+    assert float(err.mean()) <= 0.01 * max(1.0, scale)
+    assert rel_l2 <= 0.02

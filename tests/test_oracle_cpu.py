@@ -100,3 +100,52 @@ def test_whisper_oracle_matches_hf_transformers():
     assert torch.allclose(enc, ref_enc, atol=2e-4, rtol=1e-4), (enc - ref_enc).abs().max()
     got = torch.cat([logits_a, logits_b], 1)
     assert torch.allclose(got, ref_logits, atol=5e-4, rtol=1e-4), (got - ref_logits).abs().max()
+
+
+# ---- greedy decoding rule: the oracle against outputs of the reference's OWN code (tests/golden/make_greedy_golden.py runs
+# mlx_whisper_batch_decoder.py / mlx_ultra_optimized_batch.py under a numpy shim of mlx.core) -------------------------------
+def test_greedy_update_oracle_vs_reference_golden(golden_dir):
+    from oracle import whisper as ow
+    g = np.load(os.path.join(golden_dir, "greedy_golden.npz"))
+    eot = int(g["update_eot"])
+    last = torch.from_numpy(g["update_first_last"])
+    sum_lp = torch.zeros(last.shape[0])
+    for step in range(g["update_logits"].shape[0]):
+        nxt, done, sum_lp = ow.greedy_update(last, torch.from_numpy(g["update_logits"][step]), sum_lp, eot)
+        assert nxt.tolist() == g["update_next"][step].tolist(), step
+        assert done.tolist() == g["update_done"][step].tolist(), step
+        assert np.allclose(sum_lp.numpy(), g["update_sum_logprob"][step], rtol=1e-5, atol=1e-5), step
+        last = nxt
+    assert bool(g["update_done"][3].all())  # the fixture contains the all-EOT step
+
+
+def test_greedy_loop_oracle_vs_reference_golden(golden_dir):
+    from oracle import whisper as ow
+    g = np.load(os.path.join(golden_dir, "greedy_golden.npz"))
+    script = torch.from_numpy(g["loop_script"])
+
+    def logits_fn(step, tokens, active):
+        lg = script[step].clone()
+        lg[~active] = 0.0
+        return lg
+
+    toks, sum_lp, nsp, steps = ow.greedy_loop(logits_fn, torch.from_numpy(g["loop_prompt"]), int(g["loop_eot"]),
+                                              int(g["loop_no_speech"]), int(g["loop_sample_len"]))
+    assert steps == int(g["loop_steps_run"])
+    assert toks.tolist() == g["loop_tokens"].tolist()
+    assert np.allclose(sum_lp.numpy(), g["loop_sum_logprob"], rtol=1e-5, atol=1e-5)
+    assert np.allclose(nsp.numpy(), g["loop_no_speech_prob"], rtol=1e-5, atol=1e-8)
+
+
+def test_timestamp_clause_oracle_vs_reference_golden(golden_dir):
+    """The clause the reference patches (mlx_ultra_optimized_batch.py:38-71): with a history that triggers no other rule
+    (two text tokens sampled), oracle.apply_timestamp_rules must suppress text exactly where the reference does."""
+    from oracle import whisper as ow
+    g = np.load(os.path.join(golden_dir, "greedy_golden.npz"))
+    ts_begin = int(g["ts_begin"])
+    logits = torch.from_numpy(g["ts_logits"].copy())
+    hist = torch.full((logits.shape[0], 2), 7, dtype=torch.long)
+    out = ow.apply_timestamp_rules(logits, hist, eot=100, ts_begin=ts_begin, no_timestamps=-1)
+    suppressed = torch.isneginf(out[:, :ts_begin]).all(1)
+    assert suppressed.tolist() == g["ts_text_suppressed"].tolist()
+    assert out.argmax(-1).tolist() == g["ts_argmax"].tolist()

@@ -1401,6 +1401,18 @@ __global__ void __launch_bounds__(MK_THREADS, 1) dec_step_kernel(const __grid_co
   }
 }
 
+// The sampling phase on its own (one CTA per row), for parity tests of the sampling rule on arbitrary logits
+// (wxb_decoder_sample): exactly the code the persistent kernel runs after the logits GEMV.
+__global__ void __launch_bounds__(MK_THREADS, 1) dec_sample_kernel(const SampleParams sp, int B, int pos, int do_sample) {
+  __shared__ float red[MK_WARPS];
+  __shared__ int red_i[MK_WARPS];
+  for (int i = threadIdx.x; i < B && i < MAX_GROUP; i += MK_THREADS) s_rows[i] = i;
+  __syncthreads();
+  MkSync sy = {};
+  sy.cta = blockIdx.x; sy.nc = gridDim.x;
+  sample_phase(sp, B, pos, do_sample != 0, red, red_i, sy);
+}
+
 // n_tokens[b] = sampled tokens before the first EOT; tokens_out[b, i] = sampled token i (EOT padded)
 __global__ void dec_finalize_kernel(const int* __restrict__ tokens, int stride, int prompt_len, int n_sampled, int sample_len,
                                     int eot, int* __restrict__ tokens_out, int* __restrict__ n_tokens) {
@@ -1808,6 +1820,29 @@ extern "C" int wxb_decode_stats(wxb_ctx* ctx, double* cross_kv_ms, double* steps
     wxb_dec_timings_clear(ctx);
     ctx->dec_timing_on = true;  // timing is opt-in: the first reset switches it on
   }
+  return WXB_OK;
+}
+
+extern "C" int wxb_decoder_sample(wxb_ctx* ctx, float* logits_dev, int64_t ldl, int B, int n_vocab, int32_t* tokens_dev, int stride,
+                                  int pos, int prompt_len, const wxb_decode_opts* opts, float* sum_logprob_dev, int32_t* done_dev,
+                                  int32_t* ts_last_dev, float* no_speech_prob_dev, void* stream) {
+  if (!ctx) return WXB_ERR_INVALID;
+  if (!logits_dev || B <= 0 || B > MAX_GROUP || n_vocab <= 0 || ldl < n_vocab || (ldl & 3) || !tokens_dev || pos < 0 || pos + 1 >= stride ||
+      prompt_len <= 0 || !opts || !sum_logprob_dev || !done_dev || (reinterpret_cast<uintptr_t>(logits_dev) & 15))
+    return wxb_fail(ctx, WXB_ERR_INVALID, "wxb_decoder_sample: bad argument (ldl must be a multiple of 4 floats, logits 16-byte aligned)");
+  if (opts->eot < 0 || opts->eot >= n_vocab) return wxb_fail(ctx, WXB_ERR_INVALID, "wxb_decoder_sample: eot out of range");
+  if (opts->apply_timestamp_rules && (!ts_last_dev || opts->timestamp_begin <= opts->eot || opts->timestamp_begin >= n_vocab))
+    return wxb_fail(ctx, WXB_ERR_INVALID, "wxb_decoder_sample: timestamp rules need ts_last_dev and eot < timestamp_begin < n_vocab");
+  WXB_CUDA(ctx, cudaSetDevice(ctx->device));
+  SampleParams sp = {};
+  sp.logits = logits_dev; sp.ldl = ldl; sp.V = n_vocab; sp.tokens = tokens_dev; sp.stride = stride; sp.prompt_len = prompt_len;
+  sp.eot = opts->eot; sp.suppress_blank = opts->suppress_blank; sp.blank_token = opts->blank_token;
+  sp.n_suppress = opts->n_suppress; sp.suppress = opts->suppress_dev; sp.sum_logprob = sum_logprob_dev; sp.done = done_dev;
+  sp.nsp_out = (opts->no_speech >= 0) ? no_speech_prob_dev : nullptr; sp.nsp_token = opts->no_speech;
+  sp.ts_rules = opts->apply_timestamp_rules ? 1 : 0; sp.ts_begin = opts->timestamp_begin; sp.no_timestamps = opts->no_timestamps;
+  sp.max_initial_ts = opts->max_initial_timestamp_index; sp.ts_last = ts_last_dev;
+  dec_sample_kernel<<<B, MK_THREADS, 0, (cudaStream_t)stream>>>(sp, B, pos, 1);
+  WXB_LAUNCH_CHECK(ctx);
   return WXB_OK;
 }
 

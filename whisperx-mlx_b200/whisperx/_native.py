@@ -78,6 +78,8 @@ def load_library(path: Optional[str] = None):
         lib.wxb_decode_greedy.argtypes = [vp, vp, i32, vp, i32, C.POINTER(DecodeOpts), vp, vp, vp, vp, vp]
         lib.wxb_decode_stats.restype = i32
         lib.wxb_decode_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64), i32]
+        lib.wxb_decoder_sample.restype = i32
+        lib.wxb_decoder_sample.argtypes = [vp, vp, i64, i32, i32, vp, i32, i32, i32, C.POINTER(DecodeOpts), vp, vp, vp, vp, vp]
         lib.wxb_decoder_logits.restype = i32
         lib.wxb_decoder_logits.argtypes = [vp, vp, i32, vp, i32, vp, vp]
         lib.wxb_gemm_bf16.restype = i32
@@ -95,7 +97,7 @@ def load_library(path: Optional[str] = None):
 EXPORTED_SYMBOLS = (
     "wxb_abi_version", "wxb_create", "wxb_destroy", "wxb_last_error", "wxb_launch_count", "wxb_logmel",
     "wxb_ctc_align", "wxb_log_softmax_rows", "wxb_set_model", "wxb_encode", "wxb_decode_greedy",
-    "wxb_decoder_logits", "wxb_gemm_bf16", "wxb_decode_stats", "wxb_encoder_attention")
+    "wxb_decoder_logits", "wxb_gemm_bf16", "wxb_decode_stats", "wxb_encoder_attention", "wxb_decoder_sample")
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -236,6 +238,20 @@ class Context:
         B = enc_out.shape[0]
         dev = self.device
         prompt_np = np.ascontiguousarray(prompt, dtype=np.int32)
+        opts, sup = self._decode_opts(eot, no_speech, sample_len, suppress_blank, blank_token, suppress_tokens, check_every,
+                                      compaction, timestamp_rules)
+        tokens = torch.full((B, sample_len), eot, dtype=torch.int32, device=dev)
+        n_tok = torch.zeros((B,), dtype=torch.int32, device=dev)
+        sum_lp = torch.zeros((B,), dtype=torch.float32, device=dev)
+        nsp = torch.zeros((B,), dtype=torch.float32, device=dev)
+        self._check(self.lib.wxb_decode_greedy(self.h, _ptr(enc_out), B, _np_ptr(prompt_np), len(prompt_np),
+                                               C.byref(opts), _ptr(tokens), _ptr(n_tok), _ptr(sum_lp), _ptr(nsp),
+                                               self._stream()))
+        return dict(tokens=tokens, n_tokens=n_tok, sum_logprob=sum_lp, no_speech_prob=nsp)
+
+    def _decode_opts(self, eot, no_speech, sample_len, suppress_blank, blank_token, suppress_tokens, check_every, compaction,
+                     timestamp_rules):
+        dev = self.device
         sup = torch.tensor(list(suppress_tokens), dtype=torch.int32, device=dev) if len(suppress_tokens) else None
         opts = DecodeOpts(eot=eot, no_speech=no_speech, sample_len=sample_len, suppress_blank=int(suppress_blank),
                           blank_token=blank_token, n_suppress=0 if sup is None else sup.numel(),
@@ -247,14 +263,26 @@ class Context:
             opts.no_timestamps = int(timestamp_rules.get("no_timestamps", -1))
             mi = timestamp_rules.get("max_initial_timestamp_index", 50)
             opts.max_initial_timestamp_index = -1 if mi is None else int(mi)
-        tokens = torch.full((B, sample_len), eot, dtype=torch.int32, device=dev)
-        n_tok = torch.zeros((B,), dtype=torch.int32, device=dev)
-        sum_lp = torch.zeros((B,), dtype=torch.float32, device=dev)
-        nsp = torch.zeros((B,), dtype=torch.float32, device=dev)
-        self._check(self.lib.wxb_decode_greedy(self.h, _ptr(enc_out), B, _np_ptr(prompt_np), len(prompt_np),
-                                               C.byref(opts), _ptr(tokens), _ptr(n_tok), _ptr(sum_lp), _ptr(nsp),
-                                               self._stream()))
-        return dict(tokens=tokens, n_tokens=n_tok, sum_logprob=sum_lp, no_speech_prob=nsp)
+        return opts, sup
+
+    def sample_step(self, logits: torch.Tensor, tokens: torch.Tensor, pos: int, prompt_len: int, eot: int,
+                    sum_logprob: torch.Tensor, done: torch.Tensor, ts_last: Optional[torch.Tensor] = None,
+                    no_speech: int = -1, suppress_blank: bool = False, blank_token: int = 220, suppress_tokens=(),
+                    timestamp_rules: Optional[dict] = None):
+        """The decoder's sampling phase on caller-supplied logits (parity tests of the greedy update rule).
+        logits f32 cuda [B, V] (copied into a 16-byte-aligned padded buffer); tokens int32 cuda [B, stride] updated in
+        place at column pos + 1; sum_logprob f32 [B], done int32 [B], ts_last int32 [B] updated in place."""
+        B, V = logits.shape
+        ldl = (V + 3) & ~3
+        buf = torch.full((B, ldl), float("-inf"), dtype=torch.float32, device=self.device)
+        buf[:, :V] = logits
+        opts, sup = self._decode_opts(eot, no_speech, 1, suppress_blank, blank_token, suppress_tokens, 16, True, timestamp_rules)
+        nsp = torch.zeros((B,), dtype=torch.float32, device=self.device) if no_speech >= 0 else None
+        assert tokens.dtype == torch.int32 and tokens.is_contiguous() and done.dtype == torch.int32
+        self._check(self.lib.wxb_decoder_sample(self.h, _ptr(buf), ldl, B, V, _ptr(tokens), tokens.shape[1], int(pos),
+                                                int(prompt_len), C.byref(opts), _ptr(sum_logprob), _ptr(done), _ptr(ts_last),
+                                                _ptr(nsp), self._stream()))
+        return buf[:, :V], nsp
 
     def decode_stats(self, reset: bool = True):
         """(cross_kv_ms, steps_ms, n_steps) summed over the decode_greedy calls since the last reset."""
