@@ -2,15 +2,20 @@
 """
 bench.py — large-v3 RTFx (audio seconds / wall second) of the WhisperX hot path on B200.
 
-  python bench.py --gpus 1 --steps K --warmup W                 our arm (CUDA kernels through the C-ABI)
+  python bench.py --gpus 1 --steps K --warmup W                   our arm (CUDA kernels through the C-ABI)
   python bench.py --impl reference --gpus 1 --steps K --warmup W  the reference's CPU path (oracle port)
-  torchrun --nproc-per-node N bench.py --gpus N ...             one rank per GPU, weak scaling
+  torchrun --nproc-per-node N bench.py --gpus N ...               one rank per GPU
 
-One "step" = one pass of the hot path over one 30-minute batch of synthetic audio per GPU:
-log-mel -> encoder -> batched greedy decode (all 224 sampled positions: random-init weights never emit
-EOT) -> CTC trellis + beam-2 backtrack over synthetic wav2vec2-shaped emissions, 60 x 30 s VAD chunks.
-`value` times the device-resident path; `e2e` times the public API (whisperx.load_model(...).transcribe
-+ alignment from host emissions) with host buffers, H2D / D2H inside the timed region.
+One "step" = one pass of the hot path over ONE 30-minute job of synthetic audio: log-mel -> encoder -> batched greedy
+decode (all 224 sampled positions: random-init weights never emit EOT) -> wav2vec2 emissions -> CTC trellis + beam-2
+backtrack, 60 x 30 s VAD chunks.  With N > 1 the job's chunks are dealt to the N GPUs (LPT queues, whisperx/multi_gpu.py),
+every rank works through its own queue and the per-chunk results are gathered on rank 0 (host gather, no data-path
+collective): `value` is STRONG scaling of one job.  The weak-scaling figure (every rank its own 30 minutes) is the sub-field
+`weak`.  `value` times the device-resident path; `e2e` times the public API (whisperx.load_model(...).transcribe... +
+whisperx.align()) with host buffers, H2D / D2H and the host gather inside the timed region.
+
+Sub-records in the same JSON line: `batch8` (BASELINE config 3: large-v3, 8 chunks, batch 8, N = 1 only) and `turbo`
+(config 4: large-v3-turbo, the same 30-minute job sharded like the headline).
 """
 import argparse
 import json
@@ -32,6 +37,18 @@ from fake_ctc_model import synthetic_speech  # noqa: E402  (deterministic synthe
 
 SR = 16000
 CHUNK_S = 30.0
+# environment knobs of the library: tracing ones are echoed, anything else aborts the run (a bench number must come from the
+# default code path of the in-tree library)
+ENV_TRACING = {"WXB_DEC_PROF"}
+
+
+def env_guard(allow):
+    found = {k: v for k, v in os.environ.items() if k.startswith("WXB")}
+    bad = [k for k in found if k not in ENV_TRACING and not allow]
+    if bad:
+        sys.exit(f"bench.py: refusing to run with {bad} set (library variant / probe knobs); unset them or pass --allow-env "
+                 "for an A/B run whose number is not a bench value")
+    return found
 
 
 def peaks():
@@ -80,14 +97,18 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def workload(model, minutes, seed):
-    n_chunks = int(round(minutes * 60 / CHUNK_S))
-    base = synthetic_speech(60.0, seed=seed)  # 60 s of deterministic speech-like signal, tiled (generation is host-side prep)
-    reps = int(np.ceil(n_chunks * CHUNK_S / 60.0))
-    audio = np.tile(base, reps)[: int(n_chunks * CHUNK_S * SR)]
-    rng = np.random.RandomState(seed)
-    # alignment inputs: wav2vec2-shaped emissions T=1499, V=29; transcripts N~U(50,450), 5 % wildcards
+def job_audio(minutes, seed):
+    """The job: `minutes` of deterministic speech-like audio (60 s pattern tiled; generation is host-side preparation)."""
+    n = int(round(minutes * 60 * SR))
+    base = synthetic_speech(60.0, seed=seed)
+    return np.tile(base, int(np.ceil(n / len(base))))[:n]
+
+
+def align_inputs(n_chunks, seed):
+    """Alignment inputs of SURVEY 8d for callers WITHOUT an alignment model (the CPU arm): wav2vec2-shaped emissions
+    T = 1499, V = 29 and transcripts N ~ U(50, 450) with 5 % wildcards."""
     T, V = 1499, 29
+    rng = np.random.RandomState(seed)
     emis = (np.random.RandomState(seed + 1).standard_normal((n_chunks, T, V)) * 3.0).astype(np.float32)
     toks = []
     for _ in range(n_chunks):
@@ -95,7 +116,7 @@ def workload(model, minutes, seed):
         t = rng.randint(1, V, size=n).astype(np.int32)
         t[rng.rand(n) < 0.05] = -1
         toks.append(t)
-    return audio, n_chunks, emis, toks
+    return emis, toks
 
 
 def flops_encoder(dims):
@@ -123,7 +144,9 @@ def run_reference(args):
     dims = bw.dims_for(args.model)
     sp = bw.special_tokens(dims)
     w = bw.round_to_bf16(bw.init_random_weights(dims, seed=0))
-    audio, n_chunks, emis, toks = workload(args.model, args.minutes, 1234)
+    audio = job_audio(args.minutes, 1234)
+    n_chunks = int(round(args.minutes * 60 / CHUNK_S))
+    emis, toks = align_inputs(n_chunks, 1234)
     n = args.cpu_chunks
     chunks = [audio[i * 480000:(i + 1) * 480000] for i in range(n)]
     prompt = [sp["sot"], sp["sot"] + 1, sp["transcribe"], sp["no_timestamps"]]
@@ -140,7 +163,7 @@ def run_reference(args):
     sample = f"{n} of {n_chunks} chunks ({n * CHUNK_S:.0f} s audio), batch {n}, all 224 decode positions, mel+encoder+decoder+ctc"
     line = {"impl": "reference", "metric": "large-v3 RTFx (audio s / wall s)", "value": value, "unit": "x realtime",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"whisper-{args.model}, {args.minutes:g} min synthetic audio, 30 s VAD chunks (bounded sample per step)",
                        "parallelism": "cpu"},
             "cpu_baseline": {"value": value, "unit": "x realtime", "cores": torch.get_num_threads(), "kind": "port", "sample": sample,
@@ -150,6 +173,139 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------------
+class Job:
+    """One model on this rank's GPU + this rank's share of a job's chunks, resident in HBM."""
+
+    def __init__(self, args, model, local, rank, world, audio, segments, shard, batch_size, align_bundle):
+        import whisperx
+        from whisperx.multi_gpu import shard_segments
+        self.args, self.rank, self.world, self.local = args, rank, world, local
+        self.pipe = whisperx.load_model(model, device="cuda", device_index=local, backend="b200", language="en",
+                                        vad_method="uniform", batch_size=batch_size, align_model=align_bundle)
+        self.be = self.pipe.backend
+        self.ctx, self.dims = self.be.ctx, self.be.dims
+        if args.sample_len > 0:
+            self.be.options["sample_len"] = args.sample_len
+        self.sample_len = int(self.be.options["sample_len"])
+        self.batch_size = batch_size
+        self.audio = audio
+        self.segments = segments
+        self.mine = shard_segments(segments, rank, world) if shard else list(segments)
+        self.chunks = [audio[int(s["start"] * SR): int(s["end"] * SR)] for s in self.mine]
+        self.n_mine = len(self.chunks)
+        self.audio_dev, self.offs, self.lens = self.be.upload_chunks(self.chunks) if self.chunks else (None, [], [])
+        self.prompt = self.be.tokenizer.prompt("en", "transcribe", True)
+        self.align_bundle = align_bundle
+        self.stage_ev = {k: [] for k in ("mel", "encoder", "decode", "w2v", "ctc")}
+
+    def step_device(self, record):
+        """Device-resident pass over this rank's chunks: K1 -> K2 -> K3, then wav2vec2 emissions + K4 for every chunk."""
+        ctx, be, dims = self.ctx, self.be, self.dims
+
+        def ev():
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            return e
+
+        be._bind()
+        toks_dev = []
+        for i in range(0, self.n_mine, self.batch_size):
+            j = min(self.n_mine, i + self.batch_size)
+            e0 = ev()
+            mel = ctx.logmel(self.audio_dev, self.offs[i:j], self.lens[i:j], 480000, dims["n_mels"], be._filters)
+            e1 = ev()
+            enc = ctx.encode(mel)
+            e2 = ev()
+            r = ctx.decode_greedy(enc, self.prompt, be.specials["eot"], no_speech=be.specials["no_speech"], sample_len=self.sample_len,
+                                  suppress_blank=True, blank_token=be.specials["blank"])
+            e3 = ev()
+            toks_dev.append(r["tokens"])
+            if record:
+                self.stage_ev["mel"].append((e0, e1)); self.stage_ev["encoder"].append((e1, e2)); self.stage_ev["decode"].append((e2, e3))
+        if self.align_bundle is not None and self.n_mine:
+            self.align_device(record, ev)
+        return toks_dev
+
+    def align_device(self, record, ev):
+        """Alignment leg with everything resident: wav2vec2 forward over this rank's chunks (own kernels) + log_softmax + K4 on
+        fixed synthetic transcripts (the decoded text needs the host tokenizer; that round trip is what `e2e` times)."""
+        from whisperx._native import CTC_BEAM2
+        model, _meta = self.align_bundle
+        e4 = ev()
+        emis, t_off = model.emissions_device(self.audio_dev, self.offs, self.lens)  # [sumT, V] f32 logits, frame offsets
+        e5 = ev()
+        self.ctx.log_softmax_rows_(emis)
+        if getattr(self, "_ctc_tok", None) is None:
+            rng = np.random.RandomState(4321 + self.rank)
+            V = emis.shape[1]
+            toks = []
+            for k in range(self.n_mine):
+                T = int(t_off[k + 1] - t_off[k])
+                n = int(rng.randint(50, max(51, min(451, T))))
+                t = rng.randint(1, V, size=n).astype(np.int32)
+                t[rng.rand(n) < 0.05] = -1
+                toks.append(t)
+            self._ctc_tok = torch.from_numpy(np.concatenate(toks)).to(self.ctx.device)
+            self._ctc_noff = np.concatenate([[0], np.cumsum([len(t) for t in toks])]).astype(np.int32)
+        res = self.ctx.ctc_align(emis, t_off, self._ctc_tok, self._ctc_noff, 0, CTC_BEAM2)
+        e6 = ev()
+        if record:
+            self.stage_ev["w2v"].append((e4, e5)); self.stage_ev["ctc"].append((e5, e6))
+        return res
+
+
+def timed(job, dist, world, steps, warmup, flush, sampler=None):
+    """W warm-up passes, then `steps` timed passes bracketed by barrier + synchronize; returns (ms per step = max over ranks,
+    launches, decode stats, stage ms)."""
+    dev = job.ctx.device
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        job.step_device(False)
+    job.ctx.decode_stats(reset=True)
+    for v in job.stage_ev.values():
+        v.clear()
+    barrier()
+    if sampler is not None:
+        sampler.start()
+    launches0 = job.ctx.launches
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        flush.zero_()  # > L2: nothing of the previous pass is cache-resident
+        job.step_device(True)
+    t1.record()
+    barrier()
+    ms = t0.elapsed_time(t1)
+    clock_info = sampler.stop() if sampler is not None else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    cross_ms, steps_ms, n_dec = job.ctx.decode_stats(reset=True)
+    stage_ms = {k: float(sum(a.elapsed_time(b) for a, b in v)) / steps for k, v in job.stage_ev.items()}
+    return dict(ms_step=float(t.item()) / steps, launches=job.ctx.launches - launches0, cross_ms=cross_ms / steps,
+                dec_ms=steps_ms / steps, n_dec=n_dec / steps, stage_ms=stage_ms, clocks=clock_info)
+
+
+def decode_roofline(job, r, P, n_rows):
+    """Algorithmic bytes of the decode steps this rank ran / their device time."""
+    prompt_len = len(job.prompt)
+    t_mean = (prompt_len + job.sample_len) / 2.0
+    n_groups = max(1, -(-n_rows // job.batch_size))
+    rows = n_rows / n_groups  # sequences per decode call (mean)
+    wbytes, cbytes, sbytes = decode_bytes_per_step(job.dims, rows, t_mean)
+    bytes_step = wbytes + cbytes + sbytes
+    ms_per_step = r["dec_ms"] / max(r["n_dec"], 1)
+    achieved = bytes_step / (ms_per_step * 1e-3) / 1e9
+    return dict(bytes_per_step=bytes_step, ms_per_step=ms_per_step, achieved=achieved, frac=achieved / P["hbm_gbs"],
+                rows_per_call=rows, steps=r["n_dec"])
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -163,177 +319,171 @@ def main():
     ap.add_argument("--sample-len", type=int, default=0, help="override the number of sampled positions (profiling only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the batch8 / turbo / weak sub-records")
+    ap.add_argument("--no-align", action="store_true", help="leave the wav2vec2 + CTC alignment leg out (profiling only)")
+    ap.add_argument("--allow-env", action="store_true", help="run although WXB_* variables are set (A/B runs, not a bench value)")
     args = ap.parse_args()
+    env_seen = env_guard(args.allow_env)
     if args.impl == "reference":
         return run_reference(args)
 
+    import warnings
     import torch.distributed as dist
-    from whisperx._native import CTC_BEAM2
-    from whisperx.alignment import align_from_emissions
     import whisperx
+    from whisperx import multi_gpu
+    from whisperx._native import load_library
+    from whisperx.vads import synthetic_vad_cuts
+    warnings.simplefilter("ignore")
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    hgroup = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        hgroup = multi_gpu.host_group(world)
     dev = torch.device("cuda", local)
+    lib_path = load_library()._wxb_path
 
-    import warnings
-    warnings.simplefilter("ignore")
-    pipe = whisperx.load_model(args.model, device="cuda", device_index=local, backend="b200", language="en",
-                               vad_method="uniform", batch_size=args.batch_size)
-    be = pipe.backend
-    ctx, dims = be.ctx, be.dims
-    audio, n_chunks, emis, toks = workload(args.model, args.minutes, 1234 + rank)  # every rank: its own 30 min (weak scaling)
-    chunks = [audio[i * 480000:(i + 1) * 480000] for i in range(n_chunks)]
-    audio_s = n_chunks * CHUNK_S
-
-    # device-resident inputs for `value`
-    audio_dev, offs, lens = be.upload_chunks(chunks)
-    T, V = emis.shape[1], emis.shape[2]
-    emis_dev = torch.from_numpy(emis.reshape(-1, V)).to(dev)
-    emis_work = torch.empty_like(emis_dev)
-    tok_dev = torch.from_numpy(np.concatenate(toks)).to(dev)
-    t_off = (np.arange(n_chunks + 1) * T).astype(np.int32)
-    n_off = np.concatenate([[0], np.cumsum([len(t) for t in toks])]).astype(np.int32)
+    # the job: ONE 30-minute recording, 60 uniform 30 s VAD chunks; identical on every rank
+    audio = job_audio(args.minutes, 1234)
+    audio_s = len(audio) / SR
+    segments = synthetic_vad_cuts(audio_s, "uniform", chunk_size=CHUNK_S)
+    n_chunks = len(segments)
+    align_bundle = None
+    if not args.no_align:
+        align_bundle = whisperx.load_align_model("en", dev, model_name="WAV2VEC2_ASR_BASE_960H", random_init=True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    prompt = be.tokenizer.prompt("en", "transcribe", True)
-    if args.sample_len > 0:
-        be.options["sample_len"] = args.sample_len
-    sample_len = int(be.options["sample_len"])
 
-    stage_ev = {k: [] for k in ("mel", "encoder", "decode", "ctc")}
+    job = Job(args, args.model, local, rank, world, audio, segments, True, args.batch_size, align_bundle)
+    be, dims = job.be, job.dims
+    sampler = ClockSampler(local) if rank == 0 else None
+    r = timed(job, dist, world, args.steps, args.warmup, flush, sampler)
+    value = audio_s / (r["ms_step"] / 1e3)
 
-    def ev():
-        e = torch.cuda.Event(enable_timing=True)
-        e.record()
-        return e
-
-    def step_device(record):
-        flush.zero_()
-        for i in range(0, n_chunks, args.batch_size):
-            j = min(n_chunks, i + args.batch_size)
-            e0 = ev()
-            mel = ctx.logmel(audio_dev, offs[i:j], lens[i:j], 480000, dims["n_mels"], be._filters)
-            e1 = ev()
-            enc = ctx.encode(mel)
-            e2 = ev()
-            r = ctx.decode_greedy(enc, prompt, be.specials["eot"], no_speech=be.specials["no_speech"], sample_len=sample_len,
-                                  suppress_blank=True, blank_token=be.specials["blank"])
-            e3 = ev()
-            if record:
-                stage_ev["mel"].append((e0, e1)); stage_ev["encoder"].append((e1, e2)); stage_ev["decode"].append((e2, e3))
-        e4 = ev()
-        emis_work.copy_(emis_dev)
-        ctx.log_softmax_rows_(emis_work)
-        res = ctx.ctc_align(emis_work, t_off, tok_dev, n_off, 0, CTC_BEAM2)
-        e5 = ev()
-        if record:
-            stage_ev["ctc"].append((e4, e5))
-        return r, res
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step_device(False)
-    ctx.decode_stats(reset=True)
-    barrier()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-    launches0 = ctx.launches
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_start.record()
-    for _ in range(args.steps):
-        step_device(True)
-    t_end.record()
-    barrier()
-    ms_total = t_start.elapsed_time(t_end)
-    launches = ctx.launches - launches0
-    clock_info = clocks.stop() if rank == 0 else None
-    cross_ms, steps_ms, n_dec_steps = ctx.decode_stats(reset=True)
-    stage_ms = {k: float(sum(a.elapsed_time(b) for a, b in v)) / args.steps for k, v in stage_ev.items()}
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
-    value = world * audio_s / (ms_step / 1e3)
-
-    # ---- e2e through the public API with host buffers ------------------------------------------------
+    # ---- e2e: the public API with host buffers; chunks sharded, results gathered on rank 0 inside the timed region -------
     e2e = None
     if not args.no_e2e:
-        emis_list = [emis[i] for i in range(n_chunks)]
-        tok_lists = [t.tolist() for t in toks]
+        def align_fn(local_result, mine):
+            if align_bundle is None or not local_result["segments"]:
+                return local_result
+            model, meta = align_bundle
+            out = whisperx.align(local_result["segments"], model, meta, audio, str(dev))
+            out["language"] = local_result["language"]
+            return out
 
         def step_e2e():
-            out = pipe.transcribe(audio, batch_size=args.batch_size, chunk_size=30)  # numpy in -> dicts out (H2D + D2H inside)
-            paths = align_from_emissions(emis_list, tok_lists, 0, device_index=local)  # pinned H2D -> K4 -> D2H
-            return out, paths
+            return multi_gpu.transcribe_sharded(job.pipe, audio, rank, world, batch_size=args.batch_size, chunk_size=30,
+                                                group=hgroup, align_fn=align_fn)
 
         for _ in range(min(args.warmup, 2)):
             step_e2e()
-        barrier()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            out, paths = step_e2e()
+            out = step_e2e()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         te = torch.tensor([dt], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         sec = float(te.item()) / args.steps
-        h2d = audio.nbytes + emis.nbytes + sum(t.nbytes for t in toks)
-        d2h = n_chunks * (sample_len * 4 + 12) + n_chunks * T * 8 + n_chunks * 4
-        e2e = {"value": world * audio_s / sec, "unit": "x realtime", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": sec * 1e3, "segments_returned": len(out["segments"]), "aligned_ok": int(sum(1 for p in paths if p[0] == 0))}
+        h2d = sum(int(c.nbytes) for c in job.chunks)
+        d2h = job.n_mine * (job.sample_len * 4 + 12)
+        if align_bundle is not None:
+            st = getattr(align_bundle[0], "last_stats", {})
+            h2d += int(st.get("h2d_bytes", 0))
+            d2h += int(st.get("d2h_bytes", 0))
+        tb = torch.tensor([h2d, d2h], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.SUM)
+        e2e = {"value": audio_s / sec, "unit": "x realtime", "h2d_bytes_per_step": int(tb[0].item()), "d2h_bytes_per_step": int(tb[1].item()),
+               "ms_per_step": sec * 1e3}
+        if rank == 0:
+            e2e["segments_returned"] = len(out["segments"])
+            e2e["words_returned"] = len(out.get("word_segments", []))
+            e2e["api"] = ("whisperx.load_model(..., backend='b200') -> multi_gpu.transcribe_sharded (VAD cuts, LPT shard, "
+                          "backend.transcribe_batch, whisperx.align on the transcribing rank, host gather on rank 0)")
+
+    # ---- sub-records ---------------------------------------------------------------------------------------------------------
+    P = peaks()
+    extras = {}
+    if not args.no_extras:
+        if world > 1:
+            # weak scaling: every rank its own 30 minutes (what round 1 reported); one warm-up, `steps` passes
+            wjob = Job(args, args.model, local, rank, world, job_audio(args.minutes, 1234 + rank), segments, False, args.batch_size,
+                       align_bundle)
+            wr = timed(wjob, dist, world, args.steps, 1, flush)
+            extras["weak"] = {"value": world * audio_s / (wr["ms_step"] / 1e3), "unit": "x realtime", "ms_per_step": wr["ms_step"],
+                              "audio_s_per_gpu": audio_s, "note": "every rank transcribes its own 30 min (no sharing, no gather)"}
+            del wjob
+        else:
+            extras["weak"] = {"value": value, "unit": "x realtime", "ms_per_step": r["ms_step"], "audio_s_per_gpu": audio_s}
+            # BASELINE config 3: large-v3, batch 8 (8 chunks of the same job)
+            b8 = Job(args, args.model, local, 0, 1, audio, segments[:8], False, 8, None)
+            r8 = timed(b8, dist, 1, args.steps, 2, flush)
+            d8 = decode_roofline(b8, r8, P, 8)
+            extras["batch8"] = {"config": "whisper-large-v3, 8 x 30 s chunks, batch 8 (BASELINE config 3), mel + encoder + greedy decode",
+                                "value": 8 * CHUNK_S / (r8["ms_step"] / 1e3), "unit": "x realtime", "ms_per_step": r8["ms_step"],
+                                "decode": {"ms_per_step": d8["ms_per_step"], "GB/s": d8["achieved"], "frac_hbm": d8["frac"],
+                                           "bytes_per_step": d8["bytes_per_step"]},
+                                "encoder_ms": r8["stage_ms"]["encoder"],
+                                "encoder_TFLOP/s": flops_encoder(dims) * 8 / (r8["stage_ms"]["encoder"] * 1e-3) / 1e12}
+            del b8
+        # BASELINE config 4: large-v3-turbo, the same 30-minute job sharded over the ranks
+        tj = Job(args, "large-v3-turbo", local, rank, world, audio, segments, True, args.batch_size, None)
+        tr = timed(tj, dist, world, args.steps, 2, flush)
+        dt_ = decode_roofline(tj, tr, P, tj.n_mine)
+        extras["turbo"] = {"config": f"whisper-large-v3-turbo (4-layer decoder), {args.minutes:g} min = {n_chunks} chunks sharded over "
+                                     f"{world} GPU(s) (BASELINE config 4), mel + encoder + greedy decode",
+                           "value": audio_s / (tr["ms_step"] / 1e3), "unit": "x realtime", "ms_per_step": tr["ms_step"],
+                           "decode_rank0": {"ms_per_step": dt_["ms_per_step"], "GB/s": dt_["achieved"], "frac_hbm": dt_["frac"],
+                                            "rows_per_call": dt_["rows_per_call"]}}
+        del tj
+        be._bind()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel: dec_step_kernel, the persistent cooperative decode kernel.  One launch
-    # walks STEPS_PER_LAUNCH decode positions (wxb_decode_opts.check_every); its duration is measured with CUDA
-    # events on the launching stream inside wxb_decode_greedy (wxb_decode_stats), summed over the timed region.
-    P = peaks()
-    B = args.batch_size
-    prompt_len = len(prompt)
-    t_mean = (prompt_len + sample_len) / 2.0
-    wbytes, cbytes, sbytes = decode_bytes_per_step(dims, min(B, n_chunks), t_mean)
-    bytes_step = wbytes + cbytes + sbytes  # algorithmic: weights once per step, cross-KV + self-KV per sequence
-    steps_per_pass = n_dec_steps / args.steps
-    dec_ms_per_step = steps_ms / max(n_dec_steps, 1)
-    steps_per_launch = min(16, sample_len)
-    achieved = bytes_step / (dec_ms_per_step * 1e-3) / 1e9
-    enc_flops = flops_encoder(dims) * n_chunks
-    ckv_flops = 2 * 1500 * dims["n_text_state"] * dims["n_audio_state"] * 2 * dims["n_text_layer"] * n_chunks
-    mel_bytes = n_chunks * (4 * 480000 + dims["n_mels"] * 3000 * 4)
+    # ---- roofline of the dominant kernel: dec_step_kernel, the persistent cooperative decode kernel.  One launch walks up
+    # to 16 decode positions (wxb_decode_opts.check_every); its duration is measured with CUDA events on the launching
+    # stream inside wxb_decode_greedy (wxb_decode_stats), summed over the timed region (rank 0's share of the job).
+    dr = decode_roofline(job, r, P, job.n_mine)
+    steps_per_launch = min(16, job.sample_len)
+    n_mine = job.n_mine
+    enc_flops = flops_encoder(dims) * n_mine
+    ckv_flops = 2 * 1500 * dims["n_text_state"] * dims["n_audio_state"] * 2 * dims["n_text_layer"] * n_mine
+    mel_bytes = n_mine * (4 * 480000 + dims["n_mels"] * 3000 * 4)
+    sm = r["stage_ms"]
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "dec_step_traffic.json")  # from the committed `ncu --set full` capture
     if os.path.exists(tpath):
-        tj = json.load(open(tpath))
-        if tj.get("model") == be.model_name and tj.get("batch") == B:
-            traffic = tj["dram_bytes_per_launch"]
-    roofline = {"bound": "hbm", "kernel": "dec_step_kernel (persistent cooperative kernel: %d operators per decode step separated by grid barriers, "
-                                          "%d steps per launch)" % (11 * dims["n_text_layer"] + 3, steps_per_launch),
-                "achieved": achieved, "peak": P["hbm_gbs"], "unit": "GB/s", "frac": achieved / P["hbm_gbs"], "traffic": traffic,
-                "peak_source": P["source"], "bytes_per_launch": bytes_step * steps_per_launch,
-                "ms_per_launch": dec_ms_per_step * steps_per_launch, "steps_per_launch": steps_per_launch,
-                "bytes_per_step": bytes_step, "ms_per_step": dec_ms_per_step,
-                "stages": {
-                    "mel": {"ms": stage_ms["mel"], "GB/s": mel_bytes / (stage_ms["mel"] * 1e-3) / 1e9, "frac_hbm": mel_bytes / (stage_ms["mel"] * 1e-3) / 1e9 / P["hbm_gbs"]},
-                    "encoder": {"ms": stage_ms["encoder"], "TFLOP/s": enc_flops / (stage_ms["encoder"] * 1e-3) / 1e12,
-                                "frac_bf16_burst": enc_flops / (stage_ms["encoder"] * 1e-3) / 1e12 / P["bf16_tflops"],
-                                "frac_bf16_sustained": enc_flops / (stage_ms["encoder"] * 1e-3) / 1e12 / (P["bf16_tflops_sustained"] or P["bf16_tflops"])},
-                    "cross_kv_gemm": {"ms": cross_ms / args.steps, "TFLOP/s": ckv_flops / (cross_ms / args.steps * 1e-3) / 1e12},
-                    "decode_steps": {"ms": steps_ms / args.steps, "steps": steps_per_pass, "GB/s": achieved},
-                    "ctc": {"ms": stage_ms["ctc"]}}}
+        tj_ = json.load(open(tpath))
+        if tj_.get("model") == be.model_name and tj_.get("batch") == min(args.batch_size, n_mine):
+            traffic = tj_["dram_bytes_per_launch"]
+    stages = {
+        "mel": {"ms": sm["mel"], "GB/s": mel_bytes / (sm["mel"] * 1e-3) / 1e9, "frac_hbm": mel_bytes / (sm["mel"] * 1e-3) / 1e9 / P["hbm_gbs"]},
+        "encoder": {"ms": sm["encoder"], "TFLOP/s": enc_flops / (sm["encoder"] * 1e-3) / 1e12,
+                    "frac_bf16_burst": enc_flops / (sm["encoder"] * 1e-3) / 1e12 / P["bf16_tflops"],
+                    "frac_bf16_sustained": enc_flops / (sm["encoder"] * 1e-3) / 1e12 / (P["bf16_tflops_sustained"] or P["bf16_tflops"])},
+        "cross_kv_gemm": {"ms": r["cross_ms"], "TFLOP/s": ckv_flops / (r["cross_ms"] * 1e-3) / 1e12},
+        "decode_steps": {"ms": r["dec_ms"], "steps": dr["steps"], "GB/s": dr["achieved"]}}
+    if align_bundle is not None:
+        st = getattr(align_bundle[0], "last_stats", {})
+        stages["wav2vec2"] = {"ms": sm["w2v"], "TFLOP/s": st.get("flops", 0) / max(sm["w2v"] * 1e-3, 1e-9) / 1e12, "frames": st.get("frames")}
+        stages["ctc"] = {"ms": sm["ctc"]}
+    roofline = {"bound": "hbm", "kernel": "dec_step_kernel (persistent cooperative kernel: %d operators per decode step separated by grid "
+                                          "barriers, %d steps per launch)" % (11 * dims["n_text_layer"] + 3, steps_per_launch),
+                "achieved": dr["achieved"], "peak": P["hbm_gbs"], "unit": "GB/s", "frac": dr["frac"], "traffic": traffic,
+                "peak_source": P["source"], "bytes_per_launch": dr["bytes_per_step"] * steps_per_launch,
+                "ms_per_launch": dr["ms_per_step"] * steps_per_launch, "steps_per_launch": steps_per_launch,
+                "bytes_per_step": dr["bytes_per_step"], "ms_per_step": dr["ms_per_step"], "rows_per_call": dr["rows_per_call"],
+                "stages": stages}
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
@@ -342,23 +492,29 @@ def main():
         torch.set_num_threads(os.cpu_count())
         w = bw.kernel_layout_to_openai_fp32(be.kernel_weights, dims)  # the very numbers the GPU used, as fp32
         n = args.cpu_chunks
+        emis, toks = align_inputs(n_chunks, 1234)
         t0 = time.perf_counter()
-        _, parts = cpu_hot_path(chunks[:n], dims, w, prompt, be.specials["eot"], be.specials["no_speech"], sample_len,
+        _, parts = cpu_hot_path(job.chunks[:n], dims, w, job.prompt, be.specials["eot"], be.specials["no_speech"], job.sample_len,
                                 [emis[i] for i in range(n)], [toks[i].tolist() for i in range(n)])
         sec = time.perf_counter() - t0
         cpu_baseline = {"value": n * CHUNK_S / sec, "unit": "x realtime", "cores": torch.get_num_threads(), "kind": "port",
-                        "sample": f"{n} of {n_chunks} chunks ({n * CHUNK_S:.0f} s audio), batch {n}, all {sample_len} decode positions, "
-                                  "mel+encoder+decoder+ctc (torch CPU fp32 stands in for faster-whisper/CTranslate2, see DESIGN.md)",
+                        "sample": f"{n} of {n_chunks} chunks ({n * CHUNK_S:.0f} s audio), batch {n}, all {job.sample_len} decode positions, "
+                                  "mel+encoder+decoder+ctc (torch CPU fp32 stands in for faster-whisper/CTranslate2, see DESIGN.md; "
+                                  "the wav2vec2 forward is not in the CPU sample)",
                         "seconds": sec, "stage_seconds": parts}
 
+    align_note = ("wav2vec2-base forward (own kernels, random-init) + CTC beam-2 alignment" if align_bundle is not None
+                  else "no alignment leg (--no-align)")
     line = {"metric": "large-v3 RTFx (audio s / wall s)", "value": value, "unit": "x realtime", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": r["ms_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"whisper-{be.model_name} (random-init), {args.minutes:g} min synthetic audio per GPU = {n_chunks} x 30 s VAD chunks, "
-                                   f"batch {B}, log-mel + encoder + greedy decode ({sample_len} positions) + CTC beam-2 alignment "
-                                   f"(T=1499, V=29 synthetic emissions; wav2vec2 forward not in the timed path)",
-                       "batch_size": B, "parallelism": f"dp{world} (chunk-sharded, no collective)", "l2": "256 MB flush buffer written before every step"},
-            "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline}
+            "config": {"workload": f"whisper-{be.model_name} (random-init), ONE {args.minutes:g} min synthetic recording = {n_chunks} x 30 s VAD chunks "
+                                   f"dealt to {world} GPU(s) (LPT queues, {n_mine} chunks on rank 0), batch {min(args.batch_size, n_mine)}, log-mel + "
+                                   f"encoder + greedy decode ({job.sample_len} positions) + {align_note}",
+                       "batch_size": args.batch_size, "parallelism": f"{world} x 1 GPU, chunk-sharded, host gather only (no collective)",
+                       "l2": "256 MB flush buffer written before every step", "library": lib_path, "env": env_seen},
+            "clocks": r["clocks"], "e2e": e2e, "gpu_launches": int(r["launches"]), "roofline": roofline, "cpu_baseline": cpu_baseline}
+    line.update(extras)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

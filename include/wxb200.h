@@ -183,6 +183,41 @@ int wxb_decoder_sample(wxb_ctx* ctx, float* logits_dev, int64_t ldl, int B, int 
                        int stride, int pos, int prompt_len, const wxb_decode_opts* opts, float* sum_logprob_dev,
                        int32_t* done_dev, int32_t* ts_last_dev, float* no_speech_prob_dev, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Alignment model — replaces the per-segment `model(waveform_segment)` forward of the reference's align()
+ *     (whisperx/alignment.py:240-258, one B = 1 call per segment, "TODO: batched inference") with ONE batched pass
+ *     over all segments: the wav2vec2-base CTC architecture (torchaudio WAV2VEC2_ASR_BASE_960H; layer list
+ *     whisperx/convert_alignment_models.py:31-70).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t conv_dim;    /* 512: channels of the 7-layer conv feature extractor (k 10,3,3,3,3,2,2; s 5,2,2,2,2,2,2; group-norm mode) */
+  int32_t embed_dim;   /* 768 */
+  int32_t n_heads;     /* 12 (head_dim must be 64) */
+  int32_t n_layers;    /* 12, post-LN */
+  int32_t ff_dim;      /* 3072 */
+  int32_t pos_kernel;  /* 128 */
+  int32_t pos_groups;  /* 16 */
+  int32_t n_out;       /* CTC labels (29) */
+} wxb_w2v_dims;
+
+/* Borrowed weight table like wxb_set_model: "w2v.conv0.w" f32 [512,10], "w2v.gn.w/b" f32 [512], "w2v.conv{1..6}.w" bf16
+ * [512, k*512] (column = tap*512 + in-channel), "w2v.fp.ln.w/b", "w2v.fp.w" bf16 [d,512], "w2v.fp.b", "w2v.pos.w" bf16
+ * [d, 128*d/groups] (weight-norm folded; column = tap*(d/groups) + in-channel of the group), "w2v.pos.b",
+ * "w2v.{i}.qkv.w" bf16 [3d,d] (Q|K|V), ".qkv.b", ".out.w/.b", ".ln1.w/.b", ".fc1.w/.b", ".fc2.w/.b", ".ln2.w/.b",
+ * "w2v.ln.w/b", "w2v.aux.w" bf16 [n_out,d], "w2v.aux.b". */
+int wxb_set_align_model(wxb_ctx* ctx, const wxb_w2v_dims* dims, const char* const* names,
+                        const void* const* ptrs_dev, int n_tensors);
+
+/* Emission frames the model produces for n_samples input samples: floor((n_samples - 400) / 320) + 1 for >= 400. */
+int wxb_w2v_frames(int n_samples);
+
+/* Batched forward.  audio_dev f32, segment b = seg_len_host[b] (>= 400) samples starting at seg_off_host[b];
+ * emis_out_dev f32 [sum T_b, n_out] receives the LOGITS of every segment back to back (t_off_host int32[n_seg+1] =
+ * prefix sums of wxb_w2v_frames(seg_len)); apply wxb_log_softmax_rows and hand the buffer to wxb_ctc_align. */
+int wxb_w2v_emissions(wxb_ctx* ctx, const float* audio_dev, const int64_t* seg_off_host,
+                      const int32_t* seg_len_host, int n_seg, float* emis_out_dev,
+                      const int32_t* t_off_host, void* stream);
+
 /* Stand-alone bf16 GEMM used by the encoder (exposed for parity tests and roofline timing):
  * D[M,N] = A[M,K] * W[N,K]^T (+bias[N]) (GELU) ; A,W bf16 row-major, D bf16 or f32.
  * flags: bit0 = GELU, bit1 = output f32. */

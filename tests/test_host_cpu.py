@@ -113,3 +113,31 @@ def test_upload_contiguous_run_detection():
     assert B._contiguous_run([a[::2]], [500]) is None                             # strided
     assert B._contiguous_run([a.astype(np.float64)], [1000]) is None              # other dtype
     assert B._contiguous_run([a.tolist()], [1000]) is None                        # not an array
+
+
+def test_w2v_weight_layout_round_trip_and_frames():
+    """Kernel-layout conversion of the alignment model (weight-norm folded, Q|K|V fused, conv kernels tap-major) inverts
+    exactly; the frame-count formula matches torchaudio's own length arithmetic."""
+    import torch
+    import torchaudio
+    from whisperx.align_model import (W2V_BASE_DIMS, frames_for, from_torchaudio_state_dict, kernel_layout_to_torchaudio,
+                                      random_init_torchaudio)
+    dims = dict(W2V_BASE_DIMS, n_layers=1)
+    params = dict(torchaudio.pipelines.WAV2VEC2_ASR_BASE_960H._params, encoder_num_layers=1)
+    m = random_init_torchaudio(params, 0)
+    k = from_torchaudio_state_dict(m.state_dict(), dims, "cpu")
+    assert k["w2v.pos.w"].shape == (768, 128 * 48) and k["w2v.conv1.w"].shape == (512, 1536) and k["w2v.0.qkv.w"].shape == (2304, 768)
+    back = kernel_layout_to_torchaudio(k, dims)
+    torch.nn.utils.parametrize.remove_parametrizations(m.encoder.transformer.pos_conv_embed.conv, "weight")
+    sd = m.state_dict()
+    assert set(back) == set(sd)
+    for name, t in sd.items():
+        want = t.to(torch.bfloat16).float() if t.dim() >= 2 and "conv_layers.0" not in name else t.float()
+        if "pos_conv_embed.conv.weight" in name:  # weight norm folded in fp32 on both sides, then rounded: one bf16 ulp of slack
+            assert torch.allclose(back[name], want, rtol=2 ** -7, atol=1e-6), name
+        else:
+            assert torch.equal(back[name], want), name
+    for n in (400, 401, 719, 720, 16000, 123457, 480000):
+        _, lens = m.feature_extractor(torch.zeros(1, n), torch.tensor([n]))
+        assert frames_for(n) == int(lens[0]) == (n - 400) // 320 + 1
+    assert frames_for(399) == 0

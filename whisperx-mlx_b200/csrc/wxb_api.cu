@@ -85,6 +85,7 @@ void wxb_destroy(wxb_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   wxb_model_free(ctx);
+  wxb_align_model_free(ctx);
   wxb_dec_timings_clear(ctx);
   wxb_buf* bufs[] = {&ctx->ws_ctc_trellis, &ctx->ws_ctc_hist, &ctx->ws_ctc_meta, &ctx->ws_mel_max,
                      &ctx->ws_mel_band};

@@ -40,7 +40,9 @@ constexpr int TM_S = 0, TM_O = 256, TM_P = 384;  // TMEM columns: S_A, S_B at 0 
 constexpr float RESCALE_LOG2 = 8.f;           // move the softmax offset only when the row max grew by more than 2^8
 
 struct AttnTcParams {
-  int T, Tpad, d, H, n_kv_tiles;
+  int T;            // rows per sequence in qkv / out (row stride between sequences)
+  int d, H;
+  const int* lens;  // optional [B]: valid positions of every sequence (<= T); nullptr = T for all
   float scale_log2;
   __nv_bfloat16* out;
 };
@@ -168,7 +170,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const AttnTcParams
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 2 * BQ, h = blockIdx.y, b = blockIdx.z;
-  const int n = p.n_kv_tiles;
+  const int Tb = p.lens ? min(__ldg(p.lens + b), p.T) : p.T;  // valid positions of this sequence (keys and queries)
+  if (q0 >= Tb) return;  // whole CTA: nothing allocated or initialised yet
+  const int n = (Tb + BKV - 1) / BKV;
 
   if (warp == 8 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQK)) : "memory");
@@ -278,7 +282,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const AttnTcParams
     uint8_t* prow = smem + OFF_P + t * P_BYTES + r * 128;
 
     for (int j = 0; j < n; ++j) {
-      const int valid = p.T - j * BKV;  // keys of this tile that exist (>= 128 except for the last tile)
+      const int valid = Tb - j * BKV;  // keys of this tile that exist (>= 128 except for the last tile)
       mbar_wait(s_full + t, j & 1);
       tc_fence_after();
       // columns 64..127 stay in registers, columns 0..63 are read twice (max, then exp)
@@ -362,7 +366,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const AttnTcParams
       uint32_t v[32];
       tc_ld_32x32(o_addr + c * 32, v);
       tc_wait_ld();
-      if (q < p.T) {
+      if (q < Tb) {
         __nv_bfloat16* dst = p.out + ((size_t)b * p.T + q) * p.d + h * 64 + c * 32;
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
@@ -393,15 +397,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQK, const AttnTcParams
 int wxb_make_tmap_bf16(wxb_ctx* ctx, CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
                        uint32_t box_inner, uint32_t box_rows);
 
-// qkv bf16 [B*T, 3d] -> out bf16 [B*T, d]
-int wxb_attention_tc(wxb_ctx* ctx, const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int d, int H, cudaStream_t st) {
-  const int Tpad = (T + 7) & ~7;
+// qkv bf16 [B*T, 3d] -> out bf16 [B*T, d]; lens_dev (optional, device int[B]) = valid positions per sequence
+int wxb_attention_tc(wxb_ctx* ctx, const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int d, int H, const int* lens_dev,
+                     cudaStream_t st) {
   CUtensorMap tmQK;
   int rc;
   if ((rc = wxb_make_tmap_bf16(ctx, &tmQK, qkv, (uint64_t)3 * d, (uint64_t)B * T, (uint64_t)3 * d * 2, 64, 128)) != WXB_OK) return rc;
   if ((rc = wxb_func_smem(ctx, attention_tc_kernel, AT_SMEM)) != WXB_OK) return rc;
   AttnTcParams p;
-  p.T = T; p.Tpad = Tpad; p.d = d; p.H = H; p.n_kv_tiles = ceil_div(T, BKV);
+  p.T = T; p.d = d; p.H = H; p.lens = lens_dev;
   p.scale_log2 = (1.0f / sqrtf(64.f)) * 1.44269504088896341f;
   p.out = out;
   attention_tc_kernel<<<dim3(ceil_div(T, 2 * BQ), H, B), AT_THREADS, AT_SMEM, st>>>(tmQK, p);

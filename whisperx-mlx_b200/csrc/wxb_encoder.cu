@@ -120,7 +120,8 @@ int launch_layernorm(wxb_ctx* ctx, const float* x, const float* w, const float* 
 
 }  // namespace
 
-int wxb_attention_tc(wxb_ctx* ctx, const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int d, int H, cudaStream_t st);  // wxb_attn.cu
+int wxb_attention_tc(wxb_ctx* ctx, const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int T, int d, int H, const int* lens_dev,
+                     cudaStream_t st);  // wxb_attn.cu
 
 // exported to wxb_decoder.cu
 int wxb_launch_layernorm(wxb_ctx* ctx, const float* x, const float* w, const float* b, __nv_bfloat16* y, long long rows,
@@ -185,7 +186,7 @@ int wxb_encode_impl(wxb_ctx* ctx, const float* mel_dev, int B, __nv_bfloat16* en
       a.out = qkv; a.ldo = 3 * d;
       if ((rc = wxb_gemm_launch(ctx, a, st)) != WXB_OK) return rc;
     }
-    if ((rc = wxb_attention_tc(ctx, qkv, att, B, T_AUDIO, d, H, st)) != WXB_OK) return rc;
+    if ((rc = wxb_attention_tc(ctx, qkv, att, B, T_AUDIO, d, H, nullptr, st)) != WXB_OK) return rc;
     {
       GemmArgs a;
       a.A = att; a.lda = d; a.M = (int)M; a.W = w.out_w; a.N = d; a.K = d; a.bias = w.out_b;
@@ -214,7 +215,7 @@ extern "C" int wxb_encoder_attention(wxb_ctx* ctx, const void* qkv_dev, void* ou
   if (!qkv_dev || !out_dev || B <= 0 || T <= 0 || H <= 0 || d != 64 * H)
     return wxb_fail(ctx, WXB_ERR_INVALID, "wxb_encoder_attention: bad argument (head_dim must be 64)");
   WXB_CUDA(ctx, cudaSetDevice(ctx->device));
-  return wxb_attention_tc(ctx, (const __nv_bfloat16*)qkv_dev, (__nv_bfloat16*)out_dev, B, T, d, H, (cudaStream_t)stream);
+  return wxb_attention_tc(ctx, (const __nv_bfloat16*)qkv_dev, (__nv_bfloat16*)out_dev, B, T, d, H, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int wxb_encode(wxb_ctx* ctx, const float* mel_dev, int B, void* enc_out_dev, void* stream) {

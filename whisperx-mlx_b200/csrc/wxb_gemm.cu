@@ -270,7 +270,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (p.gelu) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+            for (int i = 0; i < 32; ++i) f[i] = gelu_fast(f[i]);
           }
           if (res_row) {
             if (full) {

@@ -30,6 +30,10 @@ class Dims(C.Structure):
         "n_vocab", "n_text_ctx", "n_text_state", "n_text_head", "n_text_layer")]
 
 
+class W2vDims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("conv_dim", "embed_dim", "n_heads", "n_layers", "ff_dim", "pos_kernel", "pos_groups", "n_out")]
+
+
 class DecodeOpts(C.Structure):
     _fields_ = [("eot", C.c_int32), ("no_speech", C.c_int32), ("sample_len", C.c_int32),
                 ("suppress_blank", C.c_int32), ("blank_token", C.c_int32), ("n_suppress", C.c_int32),
@@ -78,6 +82,12 @@ def load_library(path: Optional[str] = None):
         lib.wxb_decode_greedy.argtypes = [vp, vp, i32, vp, i32, C.POINTER(DecodeOpts), vp, vp, vp, vp, vp]
         lib.wxb_decode_stats.restype = i32
         lib.wxb_decode_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64), i32]
+        lib.wxb_set_align_model.restype = i32
+        lib.wxb_set_align_model.argtypes = [vp, C.POINTER(W2vDims), C.POINTER(C.c_char_p), C.POINTER(vp), i32]
+        lib.wxb_w2v_frames.restype = i32
+        lib.wxb_w2v_frames.argtypes = [i32]
+        lib.wxb_w2v_emissions.restype = i32
+        lib.wxb_w2v_emissions.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp]
         lib.wxb_decoder_sample.restype = i32
         lib.wxb_decoder_sample.argtypes = [vp, vp, i64, i32, i32, vp, i32, i32, i32, C.POINTER(DecodeOpts), vp, vp, vp, vp, vp]
         lib.wxb_decoder_logits.restype = i32
@@ -97,7 +107,8 @@ def load_library(path: Optional[str] = None):
 EXPORTED_SYMBOLS = (
     "wxb_abi_version", "wxb_create", "wxb_destroy", "wxb_last_error", "wxb_launch_count", "wxb_logmel",
     "wxb_ctc_align", "wxb_log_softmax_rows", "wxb_set_model", "wxb_encode", "wxb_decode_greedy",
-    "wxb_decoder_logits", "wxb_gemm_bf16", "wxb_decode_stats", "wxb_encoder_attention", "wxb_decoder_sample")
+    "wxb_decoder_logits", "wxb_gemm_bf16", "wxb_decode_stats", "wxb_encoder_attention", "wxb_decoder_sample",
+    "wxb_set_align_model", "wxb_w2v_frames", "wxb_w2v_emissions")
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -126,6 +137,7 @@ class Context:
         self.h = h
         self._keep: Dict[str, object] = {}
         self.model_owner = None  # the object (backend) whose weight table is resident, see set_model
+        self.align_owner = None  # same for the alignment model
 
     def close(self):
         if getattr(self, "h", None):
@@ -219,6 +231,31 @@ class Context:
         self.model_owner = None
         self._check(self.lib.wxb_set_model(self.h, C.byref(d), arr_n, arr_p, len(names)))
         self.model_owner = owner
+
+    def set_align_model(self, dims: dict, tensors: Dict[str, torch.Tensor], owner=None):
+        d = W2vDims(**{k: int(dims[k]) for k, _ in W2vDims._fields_})
+        names = list(tensors.keys())
+        for k in names:
+            assert tensors[k].is_cuda and tensors[k].is_contiguous(), k
+        arr_n = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        arr_p = (C.c_void_p * len(names))(*[tensors[n].data_ptr() for n in names])
+        self._keep["align_model"] = tensors  # the library borrows the pointers
+        self.align_owner = None
+        self._check(self.lib.wxb_set_align_model(self.h, C.byref(d), arr_n, arr_p, len(names)))
+        self.align_owner = owner
+
+    def w2v_emissions(self, audio_dev: torch.Tensor, seg_off: np.ndarray, seg_len: np.ndarray, emis_out: torch.Tensor,
+                      t_off: np.ndarray):
+        assert audio_dev.is_cuda and audio_dev.dtype == torch.float32 and audio_dev.is_contiguous()
+        assert emis_out.is_cuda and emis_out.dtype == torch.float32 and emis_out.is_contiguous()
+        off = np.ascontiguousarray(seg_off, dtype=np.int64)
+        ln = np.ascontiguousarray(seg_len, dtype=np.int32)
+        to = np.ascontiguousarray(t_off, dtype=np.int32)
+        if len(off) and int((off + ln).max()) > audio_dev.numel():
+            raise ValueError("segment exceeds the audio buffer")
+        self._check(self.lib.wxb_w2v_emissions(self.h, _ptr(audio_dev), _np_ptr(off), _np_ptr(ln), len(off), _ptr(emis_out),
+                                               _np_ptr(to), self._stream()))
+        return emis_out
 
     def encode(self, mel_dev: torch.Tensor) -> torch.Tensor:
         """mel f32 cuda [B, n_mels, 3000] -> bf16 cuda [B, 1500, d]."""

@@ -52,8 +52,15 @@ DEFAULT_ALIGN_MODELS_HF = {
 # ------------------------------------------------------------------------------------------------
 # model loading (library code: torchaudio / transformers provide the CTC acoustic model)
 # ------------------------------------------------------------------------------------------------
-def load_align_model(language_code: str, device: str, model_name: Optional[str] = None, model_dir=None):
-    """Same contract as alignment.py:77-110: returns (model, {"language","dictionary","type"})."""
+def load_align_model(language_code: str, device: str, model_name: Optional[str] = None, model_dir=None,
+                     random_init: bool = False, native: bool = True, seed: int = 0):
+    """Same contract as alignment.py:77-110: returns (model, {"language","dictionary","type"}).
+
+    For torchaudio bundles of the wav2vec2-BASE architecture (the en / fr / de / es / it defaults) the returned model is the
+    B200-native `Wav2Vec2B200` (whisperx/align_model.py): same weights, forward pass on our own kernels, batched over all
+    segments by align().  `native=False` keeps the torch module; Hugging Face checkpoints (wav2vec2 LARGE / XLSR, a
+    layer-norm feature extractor) stay torch modules.  `random_init=True` builds the bundle's architecture with seeded random
+    weights instead of downloading a checkpoint (benchmarks and tests: there is no network)."""
     import torchaudio
 
     if model_name is None:
@@ -67,8 +74,24 @@ def load_align_model(language_code: str, device: str, model_name: Optional[str] 
     if model_name in torchaudio.pipelines.__all__:
         kind = "torchaudio"
         bundle = getattr(torchaudio.pipelines, model_name)
-        model = bundle.get_model(dl_kwargs={"model_dir": model_dir}).to(device)
+        if random_init:
+            from .align_model import random_init_torchaudio
+            model = random_init_torchaudio(bundle._params, seed)
+        else:
+            model = bundle.get_model(dl_kwargs={"model_dir": model_dir})
         dictionary = {label.lower(): idx for idx, label in enumerate(bundle.get_labels())}
+        params = bundle._params
+        base_arch = (params.get("extractor_mode") == "group_norm" and params.get("encoder_embed_dim", 0) <= 1024
+                     and not params.get("encoder_layer_norm_first", True))
+        if native and base_arch and torch.device(device).type == "cuda":
+            from .align_model import Wav2Vec2B200, W2V_BASE_DIMS
+            dims = dict(W2V_BASE_DIMS, embed_dim=params["encoder_embed_dim"], n_heads=params["encoder_num_heads"],
+                        n_layers=params["encoder_num_layers"], ff_dim=params["encoder_ff_interm_features"],
+                        pos_kernel=params["encoder_pos_conv_kernel"], pos_groups=params["encoder_pos_conv_groups"],
+                        n_out=params["aux_num_out"])
+            model = Wav2Vec2B200(model.state_dict(), device, dims)
+        else:
+            model = model.to(device)
     else:
         from transformers import Wav2Vec2ForCTC, Wav2Vec2Processor
         try:
@@ -303,6 +326,8 @@ def align(
     jobs = []  # (sdx, text_clean, tokens, T)
     emis_parts, tok_parts = [], []
     skip_reason = {}
+    native = bool(getattr(model, "is_b200_native", False))  # Wav2Vec2B200: ONE batched forward over all segments
+    native_waves = []
     for sdx, seg in enumerate(transcript):
         t1, t2 = seg["start"], seg["end"]
         if len(prepared[sdx]["clean_char"]) == 0:
@@ -315,6 +340,14 @@ def align(
         tokens = [dictionary.get(c, -1) for c in text_clean]
         f1, f2 = int(t1 * SAMPLE_RATE), int(t2 * SAMPLE_RATE)
         wave = audio[:, f1:f2]
+        if native:
+            if wave.shape[0] != 1:
+                raise ValueError("the B200 alignment model takes mono audio")
+            from .align_model import frames_for, MIN_SAMPLES
+            native_waves.append(wave[0].numpy() if not wave.is_cuda else wave[0].cpu().numpy())
+            tok_parts.append(np.asarray(tokens, dtype=np.int32))
+            jobs.append((sdx, text_clean, tokens, frames_for(max(wave.shape[-1], MIN_SAMPLES)), 1))
+            continue
         lengths = None
         if wave.shape[-1] < 400:  # minimum wav2vec2 input (alignment.py:243-249)
             lengths = torch.as_tensor([wave.shape[-1]]).to(device)
@@ -327,7 +360,12 @@ def align(
 
     results = {}
     if jobs:
-        emis = torch.cat(emis_parts, 0).contiguous()
+        if native:
+            if model.ctx is not ctx:
+                raise RuntimeError("the alignment model lives on another GPU than `device`")
+            emis, _ = model.emissions(native_waves)  # pinned upload -> batched wav2vec2 forward (csrc/wxb_w2v.cu) -> [sum T, V]
+        else:
+            emis = torch.cat(emis_parts, 0).contiguous()
         ctx.log_softmax_rows_(emis)  # alignment.py:258
         t_off = np.concatenate([[0], np.cumsum([j[3] for j in jobs])]).astype(np.int32)
         n_off = np.concatenate([[0], np.cumsum([len(t) for t in tok_parts])]).astype(np.int32)
@@ -336,6 +374,8 @@ def align(
         status = res["status"].cpu().numpy()
         path_tok = res["path_tok"].cpu().numpy()
         path_prob = torch.exp(res["path_lp"].cpu()).numpy()
+        if native:
+            model.last_stats["d2h_bytes"] = int(status.nbytes + path_tok.nbytes + path_prob.nbytes)
         for k, job in enumerate(jobs):
             a, b = int(t_off[k]), int(t_off[k + 1])
             results[job[0]] = (int(status[k]), path_tok[a:b], path_prob[a:b], job)

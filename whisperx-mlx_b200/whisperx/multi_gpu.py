@@ -42,3 +42,47 @@ def gather_results(local: Dict, rank: int, world_size: int, dst: int = 0):
         words = [w for r in bucket for w in r.get("word_segments", [])]
         out["word_segments"] = sorted(words, key=lambda w: (w.get("start", float("inf"))))
     return out
+
+
+def host_group(world_size: int):
+    """A gloo process group for the host-side gather (None when single-process): result dicts never touch the GPUs."""
+    import torch.distributed as dist
+    if world_size == 1:
+        return None
+    return dist.new_group(backend="gloo")
+
+
+def transcribe_sharded(pipeline, audio, rank: int, world_size: int, batch_size: int = 8, chunk_size: int = 30,
+                       group=None, align_fn=None, **kwargs):
+    """ONE transcription job on `world_size` GPUs (one process per GPU, replicated weights): the VAD-cut chunks of `audio`
+    are dealt to per-GPU queues (LPT), every rank transcribes its own queue in batches of `batch_size` on its own device,
+    and the per-chunk result dicts are gathered on rank 0 and merged by start time.  No data-path collective; the only
+    exchange is the final host gather (process pattern of /root/reference/whisperx/process_separation.py:87-172).
+    `align_fn(local_result, local_segments)` optionally aligns on the rank that transcribed (segments stay on their GPU).
+    Returns the merged result on rank 0, None elsewhere."""
+    import torch.distributed as dist
+    from .audio import SAMPLE_RATE
+    if pipeline.vad_model is None:
+        from .vads import synthetic_vad_cuts
+        segments = synthetic_vad_cuts(len(audio) / SAMPLE_RATE, "uniform", chunk_size=chunk_size)
+    else:
+        segments = pipeline._segment_audio_with_vad(audio, chunk_size)
+    mine = shard_segments(segments, rank, world_size)
+    for seg in mine:
+        seg["audio"] = audio[int(seg["start"] * SAMPLE_RATE): int(seg["end"] * SAMPLE_RATE)]
+    local = pipeline.backend.transcribe_batch(mine, batch_size=batch_size, **kwargs)
+    if align_fn is not None:
+        local = align_fn(local, mine)
+    if world_size == 1:
+        return local
+    bucket = [None] * world_size if rank == 0 else None
+    dist.gather_object(local, bucket, dst=0, group=group)
+    if rank != 0:
+        return None
+    merged = [s for r in bucket for s in r["segments"]]
+    merged.sort(key=lambda s: (s["start"], s["end"]))
+    out = {"segments": merged, "language": bucket[0].get("language", "en")}
+    if any("word_segments" in r for r in bucket):
+        words = [w for r in bucket for w in r.get("word_segments", [])]
+        out["word_segments"] = sorted(words, key=lambda w: (w.get("start", float("inf"))))
+    return out
