@@ -53,6 +53,12 @@ const char* wxb_last_error(const wxb_ctx* ctx);
 /* Number of kernel launches issued by this ctx since creation (bench.py's gpu_launches). */
 int64_t wxb_launch_count(const wxb_ctx* ctx);
 
+/* Bring-up aids (tools/w2v_debug.py; no effect on results): wxb_debug_set(ctx, "w2v_stop", s) makes wxb_w2v_emissions return
+ * after stage s (0..6 conv layer, 7 feature projection, 8 positional conv, 9 + l transformer layer l; -1 = off);
+ * wxb_debug_copy copies `bytes` of the ctx workspace called `name` (e.g. "w2v.c3", "w2v.x") to a device buffer. */
+int wxb_debug_set(wxb_ctx* ctx, const char* key, int value);
+int wxb_debug_copy(wxb_ctx* ctx, const char* name, void* dst_dev, int64_t offset, int64_t bytes);
+
 /* ------------------------------------------------------------------------------------------
  * K1  log-mel frontend — replaces whisperx/audio.py:112-159 log_mel_spectrogram
  *     (reflect-padded STFT n_fft=400 hop=160 periodic Hann, |X|^2, mel filterbank,

@@ -141,3 +141,36 @@ def test_w2v_weight_layout_round_trip_and_frames():
         _, lens = m.feature_extractor(torch.zeros(1, n), torch.tensor([n]))
         assert frames_for(n) == int(lens[0]) == (n - 400) // 320 + 1
     assert frames_for(399) == 0
+
+
+def test_align_assembly_numpy_path_equals_pandas_path():
+    """align()'s word / sentence assembly: the numpy path taken for single-sentence segments reproduces the reference's
+    pandas pipeline value for value (word min / max / rounded nan-mean, dropped NaN rows, char records)."""
+    import numpy as np
+    from whisperx import alignment as al
+    rng = np.random.RandomState(3)
+    letters = "abcdefghijklmnopqrstuvwxyz'"
+    n_checked = 0
+    for case in range(60):
+        n_words = int(rng.randint(1, 30))
+        words = ["".join(rng.choice(list(letters), size=int(rng.randint(1, 14)))) for _ in range(n_words)]
+        if case % 7 == 0:
+            words[int(rng.randint(0, n_words))] = "42"          # a word with no character in the dictionary
+        text = (" " if case % 3 == 0 else "") + " ".join(words) + ("  " if case % 5 == 0 else "")
+        if case == 11:
+            text = " 7 8 9 "                                     # nothing alignable at all
+        prep = al._prepare_segment(text, {c: i for i, c in enumerate("-|" + letters)}, True)
+        prep["clean_cdx"] = [c for c, ch in zip(prep["clean_cdx"], prep["clean_char"]) if ch != "*" or case % 2]
+        t = 0
+        segs = []
+        for _ in prep["clean_cdx"]:
+            dur = int(rng.randint(1, 9))
+            segs.append(al.Segment("x", t, t + dur, float(rng.rand())))
+            t += dur + int(rng.randint(0, 3))
+        ratio, t1 = 0.020013342228152101, float(rng.uniform(0, 1800))
+        for chars in (False, True):
+            a = al._assemble_single_sentence(text, prep, segs, ratio, t1, True, chars)
+            b = al._assemble_pandas(text, prep, segs, ratio, t1, True, "nearest", chars)
+            assert a == b, (case, a, b)
+            n_checked += 1
+    assert n_checked == 120

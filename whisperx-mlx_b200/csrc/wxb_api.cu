@@ -100,4 +100,21 @@ const char* wxb_last_error(const wxb_ctx* ctx) { return ctx ? ctx->err.c_str() :
 
 int64_t wxb_launch_count(const wxb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int wxb_debug_set(wxb_ctx* ctx, const char* key, int value) {
+  if (!ctx || !key) return WXB_ERR_INVALID;
+  if (std::string(key) == "w2v_stop") { ctx->w2v_stop = value; return WXB_OK; }
+  return wxb_fail(ctx, WXB_ERR_INVALID, "wxb_debug_set: unknown key '%s'", key);
+}
+
+int wxb_debug_copy(wxb_ctx* ctx, const char* name, void* dst_dev, int64_t offset, int64_t bytes) {
+  if (!ctx || !name || !dst_dev || bytes < 0 || offset < 0) return WXB_ERR_INVALID;
+  auto it = ctx->named.find(name);
+  if (it == ctx->named.end() || !it->second.p) return wxb_fail(ctx, WXB_ERR_STATE, "wxb_debug_copy: no workspace named '%s'", name);
+  if ((size_t)(offset + bytes) > it->second.cap) return wxb_fail(ctx, WXB_ERR_INVALID, "wxb_debug_copy: '%s' holds %zu bytes", name, it->second.cap);
+  WXB_CUDA(ctx, cudaSetDevice(ctx->device));
+  WXB_CUDA(ctx, cudaDeviceSynchronize());
+  WXB_CUDA(ctx, cudaMemcpy(dst_dev, (const char*)it->second.p + offset, (size_t)bytes, cudaMemcpyDeviceToDevice));
+  return WXB_OK;
+}
+
 }  // extern "C"

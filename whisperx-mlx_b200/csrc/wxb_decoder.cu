@@ -16,9 +16,7 @@
 //
 //   GEMV phases   y[b,n] = sum_k act[b,k] W[n,k] on the 5th-gen tensor cores: tcgen05.mma with the WEIGHTS as the M
 //                 operand (128 rows per tile) and the (live) batch rows as the N operand (16 MT <= 64), both staged by
-//                 TMA (128-byte swizzle) into a 6-stage mbarrier ring, fp32 accumulators in TMEM (interleaved over
-//                 GV_NACC independent accumulators so consecutive products do not wait on one another), read back
-//                 with tcgen05.ld.  A CTA tile is 128 weight rows x (K / gk slice).  Split-K tiles write fp32 partials
+//                 TMA (128-byte swizzle) into a 6-stage mbarrier ring, fp32 accumulators in TMEM, read back with tcgen05.ld.  A CTA tile is 128 weight rows x (K / gk slice).  Split-K tiles write fp32 partials
 //                 [gk][B][N]; the CONSUMER phase sums them in slice order (deterministic) together with bias /
 //                 residual / LayerNorm / q-scaling / KV-cache append, so no reduction phase exists.
 //   self-attn     one warp per (sequence, head): 8 lanes x 16 B per key row, online softmax per 8-lane key slot,
@@ -92,10 +90,12 @@ constexpr int XA_NST = MK_WARPS == 8 ? 6 : MK_WARPS == 10 ? 5 : 4;  // K/V ring 
 constexpr int XA_NS = WXB_XA_NS;             // K/V stages per consumer iteration
 constexpr int GV_NST = 6;                    // GEMV ring depth
 #ifndef WXB_GV_NACC
-#define WXB_GV_NACC 4
+#define WXB_GV_NACC 1
 #endif
-// Independent TMEM accumulators of a GEMV tile: the K = 16 products of one ring stage go to accumulators 0 .. 3 in turn,
-// so back-to-back tcgen05.mma never form one dependent accumulation chain; the epilogue adds them in a fixed order.
+// Independent TMEM accumulators of a GEMV tile (compile-time experiment): with 4, the K = 16 products of one ring stage go
+// to accumulators 0 .. 3 in turn so that back-to-back tcgen05.mma do not form one dependent accumulation chain, and the
+// epilogue adds them in a fixed order.  Measured A/B at batch 60 (profiles/r2_*.md): no phase got faster (the ~150 cycles per
+// small tcgen05.mma are not an accumulator dependency) and every GEMV phase lost 0.1-0.2 us to the extra tcgen05.ld: default 1.
 constexpr int GV_NACC = WXB_GV_NACC;         // 1, 2 or 4
 constexpr int GV_TMEM_COLS = 64 * GV_NACC < 32 ? 32 : 64 * GV_NACC;
 static_assert(GV_NACC == 1 || GV_NACC == 2 || GV_NACC == 4, "GV_NACC");

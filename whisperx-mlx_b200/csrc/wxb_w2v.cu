@@ -337,6 +337,7 @@ extern "C" int wxb_w2v_emissions(wxb_ctx* ctx, const float* audio_dev, const int
   const float* gn_b = (const float*)aw(ctx, "w2v.gn.b");
   if (!w0 || !gn_w || !gn_b) return WXB_ERR_STATE;
   int rc;
+  const int stop = ctx->w2v_stop;
   // ---- conv layer 0 + GroupNorm + GELU (fp32 CUDA cores)
   {
     const long long rows0 = (long long)P << 6;
@@ -346,6 +347,7 @@ extern "C" int wxb_w2v_emissions(wxb_ctx* ctx, const float* audio_dev, const int
     w2v_conv0_apply_kernel<<<grid, C0_THREADS, 0, st>>>(audio_dev, d_segs, w0, stats, gn_w, gn_b, c[0], rows0);
     WXB_LAUNCH_CHECK(ctx);
   }
+  if (stop == 0) return WXB_OK;
   // ---- conv layers 1 .. 6: one GEMM each over overlapping rows (row stride 2 * 512, row length k * 512), GELU, no bias
   for (int l = 1; l < N_CONV; ++l) {
     const __nv_bfloat16* w = (const __nv_bfloat16*)aw(ctx, "w2v.conv" + std::to_string(l) + ".w");
@@ -355,6 +357,7 @@ extern "C" int wxb_w2v_emissions(wxb_ctx* ctx, const float* audio_dev, const int
     a.W = w; a.N = C_CONV; a.K = CONV_K[l] * C_CONV;
     a.gelu = 1; a.out = c[l]; a.out_f32 = 0; a.ldo = C_CONV;
     if ((rc = wxb_gemm_launch(ctx, a, st)) != WXB_OK) return rc;
+    if (stop == l) return WXB_OK;
   }
   // ---- feature projection: LayerNorm(512) -> Linear(512 -> d)
   {
@@ -369,6 +372,7 @@ extern "C" int wxb_w2v_emissions(wxb_ctx* ctx, const float* audio_dev, const int
     a.out = x; a.out_f32 = 1; a.ldo = d;
     if ((rc = wxb_gemm_launch(ctx, a, st)) != WXB_OK) return rc;
   }
+  if (stop == 7) return WXB_OK;
   // ---- convolutional positional embedding: x += GELU(grouped conv(x) + bias)
   {
     const __nv_bfloat16* w = (const __nv_bfloat16*)aw(ctx, "w2v.pos.w");  // [d, 128 * cg]: row = output channel, column = tap * cg + input channel of the group
@@ -389,6 +393,7 @@ extern "C" int wxb_w2v_emissions(wxb_ctx* ctx, const float* audio_dev, const int
     }
     if ((rc = launch_ln<float>(ctx, x, nullptr, nullptr, nullptr, xn, M, d, 0, st)) != WXB_OK) return rc;  // bf16 copy, no norm
   }
+  if (stop == 8) return WXB_OK;
   // ---- 12 post-LN transformer layers
   for (int l = 0; l < D.n_layers; ++l) {
     const std::string pre = "w2v." + std::to_string(l) + ".";
@@ -431,6 +436,7 @@ extern "C" int wxb_w2v_emissions(wxb_ctx* ctx, const float* audio_dev, const int
       if ((rc = wxb_gemm_launch(ctx, a, st)) != WXB_OK) return rc;
     }
     if ((rc = launch_ln<float>(ctx, x, ln2_w, ln2_b, x, xn, M, d, 1, st)) != WXB_OK) return rc;
+    if (stop == 9 + l) return WXB_OK;
   }
   // ---- final LayerNorm -> Linear(d -> n_out); frames of every segment packed back to back
   {

@@ -88,6 +88,10 @@ def load_library(path: Optional[str] = None):
         lib.wxb_w2v_frames.argtypes = [i32]
         lib.wxb_w2v_emissions.restype = i32
         lib.wxb_w2v_emissions.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp]
+        lib.wxb_debug_set.restype = i32
+        lib.wxb_debug_set.argtypes = [vp, C.c_char_p, i32]
+        lib.wxb_debug_copy.restype = i32
+        lib.wxb_debug_copy.argtypes = [vp, C.c_char_p, vp, i64, i64]
         lib.wxb_decoder_sample.restype = i32
         lib.wxb_decoder_sample.argtypes = [vp, vp, i64, i32, i32, vp, i32, i32, i32, C.POINTER(DecodeOpts), vp, vp, vp, vp, vp]
         lib.wxb_decoder_logits.restype = i32
@@ -108,7 +112,7 @@ EXPORTED_SYMBOLS = (
     "wxb_abi_version", "wxb_create", "wxb_destroy", "wxb_last_error", "wxb_launch_count", "wxb_logmel",
     "wxb_ctc_align", "wxb_log_softmax_rows", "wxb_set_model", "wxb_encode", "wxb_decode_greedy",
     "wxb_decoder_logits", "wxb_gemm_bf16", "wxb_decode_stats", "wxb_encoder_attention", "wxb_decoder_sample",
-    "wxb_set_align_model", "wxb_w2v_frames", "wxb_w2v_emissions")
+    "wxb_set_align_model", "wxb_w2v_frames", "wxb_w2v_emissions", "wxb_debug_set", "wxb_debug_copy")
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -256,6 +260,14 @@ class Context:
         self._check(self.lib.wxb_w2v_emissions(self.h, _ptr(audio_dev), _np_ptr(off), _np_ptr(ln), len(off), _ptr(emis_out),
                                                _np_ptr(to), self._stream()))
         return emis_out
+
+    def debug_set(self, key: str, value: int):
+        self._check(self.lib.wxb_debug_set(self.h, key.encode(), int(value)))
+
+    def debug_buffer(self, name: str, shape, dtype, offset_bytes: int = 0) -> torch.Tensor:
+        out = torch.empty(shape, dtype=dtype, device=self.device)
+        self._check(self.lib.wxb_debug_copy(self.h, name.encode(), _ptr(out), int(offset_bytes), out.numel() * out.element_size()))
+        return out
 
     def encode(self, mel_dev: torch.Tensor) -> torch.Tensor:
         """mel f32 cuda [B, n_mels, 3000] -> bf16 cuda [B, 1500, d]."""

@@ -410,6 +410,96 @@ def align(
 
 
 def _assemble(text, prep, char_segments, ratio, t1, spaced, interpolate_method, return_char_alignments):
+    """Char -> word -> sentence aggregation (alignment.py:281-373).  A segment that is ONE sentence (always the case when
+    nltk is absent, and for most ASR segments) takes the numpy path below, which reproduces the pandas results value for
+    value (tests/test_host_cpu.py compares the two on random inputs); everything else goes through the reference's own
+    pandas primitives."""
+    spans = prep["sentence_spans"]
+    if len(spans) == 1:
+        return _assemble_single_sentence(text, prep, char_segments, ratio, t1, spaced, return_char_alignments)
+    return _assemble_pandas(text, prep, char_segments, ratio, t1, spaced, interpolate_method, return_char_alignments)
+
+
+def _assemble_single_sentence(text, prep, char_segments, ratio, t1, spaced, return_char_alignments):
+    """The pandas pipeline of alignment.py:308-373 for a single sentence span, on numpy arrays: per word min(start) /
+    max(end) / round(mean(score), 3) with NaN skipping (the mean exactly as pandas' nanmean: NaNs replaced by 0, one
+    ndarray.sum over the word's characters, divided by the count of non-NaN), then the one-row groupby(start, end): a row
+    whose start or end is NaN is dropped, otherwise the row comes back with native Python floats."""
+    n = len(text)
+    start = np.full(n, np.nan)
+    end = np.full(n, np.nan)
+    score = np.full(n, np.nan)
+    for k, cdx in enumerate(prep["clean_cdx"]):
+        cs = char_segments[k]
+        start[cdx] = round(cs.start * ratio + t1, 3)
+        end[cdx] = round(cs.end * ratio + t1, 3)
+        score[cdx] = round(cs.score, 3)
+    widx = np.empty(n, dtype=np.int64)
+    w = 0
+    for cdx in range(n):
+        widx[cdx] = w
+        if not spaced:
+            w += 1
+        elif cdx == n - 1 or text[cdx + 1] == " ":
+            w += 1
+    s0, s1 = prep["sentence_spans"][0]
+    lo, hi = max(int(s0), 0), min(int(s1), n - 1)  # `.loc` selection: both ends inclusive, clipped to the rows that exist
+    if hi < lo:
+        return []
+    is_space = np.frombuffer(text.encode("utf-32-le"), dtype=np.uint32) == 32
+
+    def nanmin(a):
+        a = a[~np.isnan(a)]
+        return a.min() if a.size else np.float64(np.nan)
+
+    def nanmax(a):
+        a = a[~np.isnan(a)]
+        return a.max() if a.size else np.float64(np.nan)
+
+    words = []
+    c = lo
+    while c <= hi:
+        e = c
+        while e + 1 <= hi and widx[e + 1] == widx[c]:
+            e += 1
+        wtext = text[c:e + 1].strip()
+        if len(wtext) > 0:
+            keep = ~is_space[c:e + 1]
+            ws, we, wsc = start[c:e + 1][keep], end[c:e + 1][keep], score[c:e + 1][keep]
+            w_start, w_end = nanmin(ws), nanmax(we)
+            nn = ~np.isnan(wsc)
+            cnt = int(nn.sum())
+            w_score = round(np.where(nn, wsc, 0.0).sum() / cnt, 3) if cnt else np.float64(np.nan)
+            entry = {"word": wtext}
+            if not np.isnan(w_start):
+                entry["start"] = w_start
+            if not np.isnan(w_end):
+                entry["end"] = w_end
+            if not np.isnan(w_score):
+                entry["score"] = w_score
+            words.append(entry)
+        c = e + 1
+    sent_start = nanmin(start[lo:hi + 1])
+    sent_end = nanmax(end[lo:hi + 1][~is_space[lo:hi + 1]])
+    if np.isnan(sent_start) or np.isnan(sent_end):
+        return []  # groupby drops rows with a NaN key (a single row has no neighbour to interpolate from)
+    out = {"start": float(sent_start), "end": float(sent_end), "text": text[s0:s1], "words": words}
+    if return_char_alignments:
+        chars = []
+        for cdx in range(lo, hi + 1):
+            rec = {"char": text[cdx]}
+            if not np.isnan(start[cdx]):
+                rec["start"] = float(start[cdx])
+            if not np.isnan(end[cdx]):
+                rec["end"] = float(end[cdx])
+            if not np.isnan(score[cdx]):
+                rec["score"] = float(score[cdx])
+            chars.append(rec)
+        out["chars"] = chars
+    return [out]
+
+
+def _assemble_pandas(text, prep, char_segments, ratio, t1, spaced, interpolate_method, return_char_alignments):
     """Char -> word -> sentence aggregation (alignment.py:281-373), same pandas primitives so the
     float results (min / max / mean, NaN handling, groupby ordering) are the reference's."""
     pos_of = {cdx: k for k, cdx in enumerate(prep["clean_cdx"])}
