@@ -212,9 +212,9 @@ class Job:
         for i in range(0, self.n_mine, self.batch_size):
             j = min(self.n_mine, i + self.batch_size)
             e0 = ev()
-            mel = ctx.logmel(self.audio_dev, self.offs[i:j], self.lens[i:j], 480000, dims["n_mels"], be._filters)
+            ctx.logmel_features(self.audio_dev, self.offs[i:j], self.lens[i:j], dims["n_mels"], be._filters)  # K1 -> K2 on the device
             e1 = ev()
-            enc = ctx.encode(mel)
+            enc = ctx.encode(None, n_chunks=j - i)
             e2 = ev()
             r = ctx.decode_greedy(enc, self.prompt, be.specials["eot"], no_speech=be.specials["no_speech"], sample_len=self.sample_len,
                                   suppress_blank=True, blank_token=be.specials["blank"])
@@ -458,7 +458,7 @@ def main():
     n_mine = job.n_mine
     enc_flops = flops_encoder(dims) * n_mine
     ckv_flops = 2 * 1500 * dims["n_text_state"] * dims["n_audio_state"] * 2 * dims["n_text_layer"] * n_mine
-    mel_bytes = n_mine * (4 * 480000 + dims["n_mels"] * 3000 * 4)
+    mel_bytes = n_mine * (4 * 480000 + dims["n_mels"] * 3000 * 2)  # f32 samples in, bf16 frame-major features out (what the encoder reads)
     sm = r["stage_ms"]
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "dec_step_traffic.json")  # from the committed `ncu --set full` capture

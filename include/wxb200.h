@@ -78,6 +78,13 @@ int wxb_logmel(wxb_ctx* ctx, const float* audio_dev, const int64_t* chunk_off_ho
                const int32_t* chunk_len_host, int n_chunks, int n_samples_padded, int n_mels,
                const float* filters_dev, float* mel_out_dev, void* stream);
 
+/* K1 -> K2 hand-off on the device for 30 s chunks (n_samples_padded = 480000): same computation, but the result is ALSO left
+ * in the context's encoder input buffer (bf16, frame-major) so that wxb_encode(ctx, NULL, n_chunks, ...) can consume it
+ * without an f32 round trip through HBM.  mel_out_dev (f32 [n_chunks, n_mels, 3000]) may be NULL. */
+int wxb_logmel_features(wxb_ctx* ctx, const float* audio_dev, const int64_t* chunk_off_host,
+                        const int32_t* chunk_len_host, int n_chunks, int n_mels, const float* filters_dev,
+                        float* mel_out_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K4  CTC forced alignment — replaces whisperx/alignment.py:387-404 get_trellis,
  *     :407-437 get_wildcard_emission, :447-481 backtrack, :500-579 backtrack_beam(beam_width=2)
@@ -134,7 +141,8 @@ typedef struct {
 int wxb_set_model(wxb_ctx* ctx, const wxb_dims* dims, const char* const* names,
                   const void* const* ptrs_dev, int n_tensors);
 
-/* Encoder: mel f32 [B, n_mels, 3000] (output layout of wxb_logmel) -> enc_out bf16 [B,1500,d]. */
+/* Encoder: mel f32 [B, n_mels, 3000] (output layout of wxb_logmel) -> enc_out bf16 [B,1500,d].
+ * mel_dev = NULL: encode the B chunks whose log-mel the last wxb_logmel_features call left on the device. */
 int wxb_encode(wxb_ctx* ctx, const float* mel_dev, int B, void* enc_out_dev, void* stream);
 
 typedef struct {

@@ -163,3 +163,26 @@ def test_align_end_to_end_vs_reference_golden(wxb_ctx, golden_dir):
                              return_char_alignments=chars)
         got = json.loads(json.dumps(got, default=float))
         _close(got, g["result"][tag], tag)
+
+
+def test_logmel_features_handoff_equals_f32_path(wxb_ctx):
+    """K1 -> K2 hand-off: the bf16 frame-major encoder input written by wxb_logmel_features is the rounded f32 log-mel, and
+    encode(None) on it equals encode(mel) bit for bit; ragged / silent chunks included."""
+    import whisperx.audio as wa
+    from whisperx.backends import b200_weights as bw
+    dims = dict(n_mels=80, n_audio_ctx=1500, n_audio_state=128, n_audio_head=2, n_audio_layer=1,
+                n_vocab=1000, n_text_ctx=448, n_text_state=128, n_text_head=2, n_text_layer=1)
+    wxb_ctx.set_model(dims, bw.to_kernel_layout(bw.init_random_weights(dims, seed=2, std=0.05), dims, "cuda"))
+    chunks = [synthetic_speech(30.0, seed=61), synthetic_speech(4.4, seed=62), np.zeros(160000, np.float32), synthetic_speech(30.0, seed=63)[:479999]]
+    lens = np.array([len(c) for c in chunks], dtype=np.int32)
+    offs = np.concatenate([[0], np.cumsum(lens[:-1])]).astype(np.int64)
+    audio = torch.from_numpy(np.concatenate(chunks)).cuda()
+    filt = wa.mel_filters(wxb_ctx.device, 80)
+    mel = wxb_ctx.logmel(audio, offs, lens, 480000, 80, filt)
+    mel2 = wxb_ctx.logmel_features(audio, offs, lens, 80, filt, want_f32=True)
+    assert torch.equal(mel, mel2)
+    enc_handoff = wxb_ctx.encode(None, n_chunks=len(chunks))
+    enc = wxb_ctx.encode(mel)
+    assert torch.equal(enc, enc_handoff)
+    with pytest.raises(Exception):
+        wxb_ctx.encode(None, n_chunks=len(chunks))  # the hand-off buffer was consumed

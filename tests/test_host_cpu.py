@@ -169,8 +169,17 @@ def test_align_assembly_numpy_path_equals_pandas_path():
             t += dur + int(rng.randint(0, 3))
         ratio, t1 = 0.020013342228152101, float(rng.uniform(0, 1800))
         for chars in (False, True):
-            a = al._assemble_single_sentence(text, prep, segs, ratio, t1, True, chars)
+            runs = ([g.start for g in segs], [g.end for g in segs], [g.score for g in segs])
+            a = al._assemble_single_sentence(text, prep, runs, ratio, t1, True, chars)
             b = al._assemble_pandas(text, prep, segs, ratio, t1, True, "nearest", chars)
             assert a == b, (case, a, b)
             n_checked += 1
     assert n_checked == 120
+    # run-length merge straight from the per-frame arrays == the reference's merge over Point objects
+    for T in (1, 7, 300):
+        tok = np.sort(rng.randint(0, 40, size=T)).astype(np.int32)
+        prob = rng.rand(T).astype(np.float32)
+        transcript = "".join(rng.choice(list(letters), size=40))
+        a = al._merge_repeats_arrays(tok, prob, transcript)
+        b = al.merge_repeats([al.Point(int(tok[t]), t, float(prob[t])) for t in range(T)], transcript)
+        assert a == b

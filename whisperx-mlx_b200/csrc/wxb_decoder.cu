@@ -1158,21 +1158,38 @@ __device__ __forceinline__ void sample_phase(const SampleParams& p, int B, int p
     }
     __syncthreads();
     RowStat tx = {-INFINITY, 0x7fffffff, 0.f}, tt = {-INFINITY, 0x7fffffff, 0.f};  // ids below / from ts_begin
-    for (int i0 = tid; i0 < V4; i0 += MK_THREADS * U) {
-      float4 t[U];
+    if (!p.ts_rules) {
+      // no range rule: one running (max, argmax, sum) over the whole row
+      for (int i0 = tid; i0 < V4; i0 += MK_THREADS * U) {
+        float4 t[U];
 #pragma unroll
-      for (int j = 0; j < U; ++j) { const int i = i0 + MK_THREADS * j; t[j] = i < V4 ? __ldcg(x4 + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY); }
+        for (int j = 0; j < U; ++j) { const int i = i0 + MK_THREADS * j; t[j] = i < V4 ? __ldcg(x4 + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY); }
 #pragma unroll
-      for (int j = 0; j < U; ++j) {
-        const int i = 4 * (i0 + MK_THREADS * j);  // increasing within the thread: strict > keeps the first maximum
-        const float e[4] = {t[j].x, t[j].y, t[j].z, t[j].w};
+        for (int j = 0; j < U; ++j) {
+          const int i = 4 * (i0 + MK_THREADS * j);  // increasing within the thread: strict > keeps the first maximum
+          stat_add(tx, t[j].x, i);
+          if (i + 1 < p.V) stat_add(tx, t[j].y, i + 1);
+          if (i + 2 < p.V) stat_add(tx, t[j].z, i + 2);
+          if (i + 3 < p.V) stat_add(tx, t[j].w, i + 3);
+        }
+      }
+    } else {
+      for (int i0 = tid; i0 < V4; i0 += MK_THREADS * U) {
+        float4 t[U];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int id = i + q;
-          if (id < tsb) {
-            if (id >= lo_text) stat_add(tx, e[q], id);
-          } else if (id >= ts_lo && id <= ts_hi) {
-            stat_add(tt, e[q], id);
+        for (int j = 0; j < U; ++j) { const int i = i0 + MK_THREADS * j; t[j] = i < V4 ? __ldcg(x4 + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY); }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const int i = 4 * (i0 + MK_THREADS * j);
+          const float e[4] = {t[j].x, t[j].y, t[j].z, t[j].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int id = i + q;
+            if (id < tsb) {
+              if (id >= lo_text) stat_add(tx, e[q], id);
+            } else if (id >= ts_lo && id <= ts_hi) {
+              stat_add(tt, e[q], id);
+            }
           }
         }
       }

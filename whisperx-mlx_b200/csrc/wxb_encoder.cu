@@ -153,13 +153,15 @@ int wxb_encode_impl(wxb_ctx* ctx, const float* mel_dev, int B, __nv_bfloat16* en
   const float* lnp_b = (const float*)wxb_weight(ctx, "enc.ln_post.b");
   if (!c1w || !c1b || !c2w || !c2b || !pos || !lnp_w || !lnp_b) return WXB_ERR_STATE;
 
-  // --- mel -> frame-major bf16 with zero frames around each chunk
+  // --- mel -> frame-major bf16 with zero frames around each chunk (already there when K1 handed it over: mel_dev == NULL)
   zero_pad_rows_kernel<<<2 * B + 2, 128, 0, st>>>(melT, B, nm);
   WXB_LAUNCH_CHECK(ctx);
   zero_pad_rows_kernel<<<2 * B + 2, 128, 0, st>>>(h1, B, d);
   WXB_LAUNCH_CHECK(ctx);
-  mel_transpose_kernel<<<dim3(ceil_div(T_MEL, 32), ceil_div(nm, 32), B), dim3(32, 8), 0, st>>>(mel_dev, melT, nm);
-  WXB_LAUNCH_CHECK(ctx);
+  if (mel_dev) {
+    mel_transpose_kernel<<<dim3(ceil_div(T_MEL, 32), ceil_div(nm, 32), B), dim3(32, 8), 0, st>>>(mel_dev, melT, nm);
+    WXB_LAUNCH_CHECK(ctx);
+  }
   int rc;
   {  // conv1 (k3, s1, p1) + GELU as one GEMM over overlapping rows
     GemmArgs a;
@@ -220,7 +222,15 @@ extern "C" int wxb_encoder_attention(wxb_ctx* ctx, const void* qkv_dev, void* ou
 
 extern "C" int wxb_encode(wxb_ctx* ctx, const float* mel_dev, int B, void* enc_out_dev, void* stream) {
   if (!ctx) return WXB_ERR_INVALID;
-  if (!mel_dev || !enc_out_dev || B <= 0) return wxb_fail(ctx, WXB_ERR_INVALID, "wxb_encode: bad argument");
+  if (!enc_out_dev || B <= 0) return wxb_fail(ctx, WXB_ERR_INVALID, "wxb_encode: bad argument");
+  if (!mel_dev) {
+    // the log-mel was left in the encoder's input buffer by wxb_logmel_features
+    if (!ctx->model) return wxb_fail(ctx, WXB_ERR_STATE, "wxb_encode: no model set");
+    if (ctx->melT_chunks != B || ctx->melT_mels != ctx->model->dims.n_mels)
+      return wxb_fail(ctx, WXB_ERR_STATE, "wxb_encode(mel = NULL): wxb_logmel_features left %d chunks of %d mel bins, asked for %d of %d",
+                      ctx->melT_chunks, ctx->melT_mels, B, ctx->model->dims.n_mels);
+  }
+  ctx->melT_chunks = 0;  // consumed (or about to be overwritten by the transpose of mel_dev)
   WXB_CUDA(ctx, cudaSetDevice(ctx->device));
   return wxb_encode_impl(ctx, mel_dev, B, (__nv_bfloat16*)enc_out_dev, (cudaStream_t)stream);
 }

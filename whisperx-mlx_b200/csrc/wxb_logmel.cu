@@ -1,14 +1,15 @@
 // wxb_logmel.cu — K1: log-mel frontend, replaces whisperx/audio.py:112-159.
 //
-// One CTA = 16 consecutive STFT frames of one chunk (160 threads).  The 2800 input samples the
-// frames cover are staged once in shared memory (reflect padding at the chunk edges and zero
-// padding beyond the chunk's valid length applied on the way in), two real frames share one
-// 400-point complex FFT (radix 4,4,5,5 Stockham in shared memory, wxb_fft400.h), |X|^2 goes
-// back to shared memory and the sparse (banded) mel filterbank + log10 are applied from there.
-// Output frames are written frame-contiguous per mel row (reference layout [n_mels, n_frames]).
-// The clamp `max(x, chunk_max - 8)` needs the chunk-wide max: phase 1 writes raw log10 values
-// and folds a per-chunk atomic max; phase 2 (logmel_finalize_kernel, L2-resident re-read)
-// applies the clamp and the (x+4)/4 scaling.
+// Pass 1 (logmel_kernel): one CTA = 16 consecutive STFT frames of one chunk (160 threads).  The 2800 input samples the frames
+// cover are staged once in shared memory (16-byte loads where the tile lies inside the chunk; reflect padding at the chunk
+// edges and zero padding beyond the chunk's valid length applied on the way in), two real frames share one 400-point complex
+// FFT (radix 4,4,5,5 Stockham in shared memory, wxb_fft400.h), |X|^2 goes back to shared memory and the sparse (banded) mel
+// filterbank — taps staged in shared memory as [n_mels][<= 16] — and log10 are applied from there.  Raw log10 values are
+// written FRAME-MAJOR [chunk][frame][n_mels] (a warp writes 32 consecutive mel bins of one frame: 128-byte stores) and a
+// per-chunk atomic max is folded, because the clamp `max(x, chunk_max - 8)` needs the chunk-wide maximum.
+// Pass 2 (logmel_finalize_kernel): reads the raw tile (L2-resident), applies clamp and (x + 4) / 4, and writes what the caller
+// asked for: the reference layout f32 [n_mels, n_frames] (transposed through shared memory) and / or the encoder's input
+// melT bf16 [chunk * 3002 + 1 + frame][n_mels] directly — no f32 round trip and no separate transpose kernel on the hot path.
 #include "wxb_common.cuh"
 #include "wxb_fft400.h"
 #include <math.h>
@@ -24,12 +25,19 @@
 __device__ float g_lm_window[LM_NFFT];
 __device__ float2 g_lm_tw[LM_NFFT];
 
+// tap table of the mel rows in shared memory: row stride 15 floats for <= 80 rows (widest row of mel_80: 14 taps), 11 for
+// <= 128 rows (mel_128: 9 taps) — odd strides, so the 32 lanes of a warp (32 different rows) hit 32 different banks.  Taps a
+// wider custom filter row may have beyond the stride are read from global memory.
+#define LM_COEF_FLOATS (128 * 11)
+
 struct LmSmem {
   float samp[LM_SAMPLES];
   float win[LM_NFFT];
   cpx tw[LM_NFFT];
   cpx bufA[LM_PAIRS * LM_NFFT];
   cpx bufB[LM_PAIRS * LM_NFFT];
+  float coef[LM_COEF_FLOATS];
+  int2 band[128];
   float red[8];
 };
 
@@ -54,7 +62,7 @@ __global__ void __launch_bounds__(LM_THREADS)
 logmel_kernel(const float* __restrict__ audio, const long long* __restrict__ chunk_off,
               const int* __restrict__ chunk_len, int S, int n_frames, int n_mels,
               const float* __restrict__ filters, const int2* __restrict__ band,
-              float* __restrict__ raw_out, float* __restrict__ chunk_max) {
+              float* __restrict__ raw_out /* [chunk][frame][n_mels] */, float* __restrict__ chunk_max) {
   extern __shared__ __align__(16) unsigned char lm_smem_raw[];
   LmSmem& sm = *reinterpret_cast<LmSmem*>(lm_smem_raw);
   const int tid = threadIdx.x;
@@ -68,15 +76,29 @@ logmel_kernel(const float* __restrict__ audio, const long long* __restrict__ chu
     const float2 t = g_lm_tw[i];
     sm.tw[i] = cpx{t.x, t.y};
   }
+  // filter taps of every mel row: coef[m][k] = F[m, band.x + k], k < band.y
+  for (int m = tid; m < n_mels; m += LM_THREADS) sm.band[m] = __ldg(band + m);
+  const int cld = n_mels > 80 ? 11 : 15;
+  for (int i = tid; i < n_mels * cld; i += LM_THREADS) {
+    const int m = i / cld, k = i - m * cld;
+    const int2 bd = __ldg(band + m);
+    sm.coef[i] = (k < bd.y) ? __ldg(filters + m * LM_NBIN + bd.x + k) : 0.f;
+  }
   // stage samples: torch.stft(center=True, pad_mode="reflect") over the zero-padded chunk
   const int base_n = frame0 * LM_HOP - LM_NFFT / 2;
-  for (int i = tid; i < LM_SAMPLES; i += LM_THREADS) {
-    int n = base_n + i;
-    if (n < 0) n = -n;
-    if (n >= S) n = 2 * (S - 1) - n;
-    float v = 0.f;
-    if (n >= 0 && n < len) v = __ldg(audio + off + n);
-    sm.samp[i] = v;
+  if (base_n >= 0 && base_n + LM_SAMPLES <= len && ((off + base_n) & 3) == 0) {
+    // the whole tile lies inside the chunk's valid samples: 16-byte loads
+    const float4* src = reinterpret_cast<const float4*>(audio + off + base_n);
+    for (int i = tid; i < LM_SAMPLES / 4; i += LM_THREADS) reinterpret_cast<float4*>(sm.samp)[i] = __ldg(src + i);
+  } else {
+    for (int i = tid; i < LM_SAMPLES; i += LM_THREADS) {
+      int n = base_n + i;
+      if (n < 0) n = -n;
+      if (n >= S) n = 2 * (S - 1) - n;
+      float v = 0.f;
+      if (n >= 0 && n < len) v = __ldg(audio + off + n);
+      sm.samp[i] = v;
+    }
   }
   __syncthreads();
 
@@ -136,20 +158,22 @@ logmel_kernel(const float* __restrict__ audio, const long long* __restrict__ chu
     s_pow[(2 * p + 1) * LM_NBIN + f] = 0.25f * (dr * dr + di * di);
   }
   __syncthreads();
-  // banded mel filterbank + log10; consecutive threads -> consecutive frames of one mel row
+  // banded mel filterbank + log10; consecutive threads -> consecutive mel rows of one frame (frame-major stores)
   float lmax = -INFINITY;
   float* out_chunk = raw_out + (size_t)chunk * n_mels * n_frames;
   for (int idx = tid; idx < LM_FRAMES * n_mels; idx += LM_THREADS) {
-    const int fr = idx & (LM_FRAMES - 1), m = idx >> 4;
-    const int2 bd = __ldg(band + m);
-    const float* frow = filters + m * LM_NBIN + bd.x;
+    const int fr = idx / n_mels, m = idx - fr * n_mels;
+    const int2 bd = sm.band[m];
+    const float* crow = sm.coef + m * cld;
     const float* prow = s_pow + fr * LM_NBIN + bd.x;
     float acc = 0.f;
-    for (int k = 0; k < bd.y; ++k) acc = fmaf(__ldg(frow + k), prow[k], acc);
+    const int nk = min(bd.y, cld);
+    for (int k = 0; k < nk; ++k) acc = fmaf(crow[k], prow[k], acc);
+    for (int k = nk; k < bd.y; ++k) acc = fmaf(__ldg(filters + m * LM_NBIN + bd.x + k), prow[k], acc);
     const float v = log10f(fmaxf(acc, 1e-10f));
     const int frame = frame0 + fr;
     if (frame < n_frames) {
-      out_chunk[(size_t)m * n_frames + frame] = v;
+      out_chunk[(size_t)frame * n_mels + m] = v;
       lmax = fmaxf(lmax, v);
     }
   }
@@ -163,13 +187,28 @@ logmel_kernel(const float* __restrict__ audio, const long long* __restrict__ chu
   }
 }
 
-// phase 2: out = (max(raw, chunk_max - 8) + 4) / 4, in place
-__global__ void logmel_finalize_kernel(float* __restrict__ x, const float* __restrict__ chunk_max,
-                                       long long per_chunk, long long total) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const float floor_v = chunk_max[i / per_chunk] - 8.0f;
-    x[i] = (fmaxf(x[i], floor_v) + 4.0f) / 4.0f;
+// pass 2: v = (max(raw, chunk_max - 8) + 4) / 4 for a tile of 32 frames x n_mels of one chunk; written as f32 [n_mels, n_frames]
+// (reference layout, through a shared-memory transpose) and / or as bf16 rows of the encoder's frame-major input
+__global__ void __launch_bounds__(256)
+logmel_finalize_kernel(const float* __restrict__ raw, const float* __restrict__ chunk_max, int n_frames, int n_mels,
+                       float* __restrict__ mel_out, __nv_bfloat16* __restrict__ melT, int melT_rows_per_chunk) {
+  __shared__ float tile[32][129];
+  const int chunk = blockIdx.y, f0 = blockIdx.x * 32;
+  const float floor_v = chunk_max[chunk] - 8.0f;
+  const float* src = raw + ((size_t)chunk * n_frames + f0) * n_mels;
+  const int nf = min(32, n_frames - f0);
+  for (int i = threadIdx.x; i < nf * n_mels; i += 256) {
+    const int fr = i / n_mels, m = i - fr * n_mels;
+    const float v = (fmaxf(src[i], floor_v) + 4.0f) / 4.0f;
+    tile[fr][m] = v;
+    if (melT) melT[((size_t)chunk * melT_rows_per_chunk + 1 + f0 + fr) * n_mels + m] = __float2bfloat16_rn(v);
+  }
+  if (!mel_out) return;
+  __syncthreads();
+  float* dst = mel_out + (size_t)chunk * n_mels * n_frames + f0;
+  for (int i = threadIdx.x; i < 32 * n_mels; i += 256) {
+    const int m = i >> 5, fr = i & 31;
+    if (fr < nf) dst[(size_t)m * n_frames + fr] = tile[fr][m];
   }
 }
 
@@ -227,6 +266,23 @@ int wxb_logmel_raw(wxb_ctx* ctx, const float* audio_dev, const int64_t* chunk_of
   return WXB_OK;
 }
 
+// both passes; mel_out_dev (f32 [n_chunks, n_mels, n_frames]) and melT (bf16 encoder input) are each optional
+static int logmel_run(wxb_ctx* ctx, const float* audio_dev, const int64_t* chunk_off_host, const int32_t* chunk_len_host, int n_chunks,
+                      int n_samples_padded, int n_mels, const float* filters_dev, float* mel_out_dev, __nv_bfloat16* melT,
+                      int melT_rows_per_chunk, cudaStream_t st) {
+  const int n_frames = n_samples_padded / LM_HOP;
+  float* raw = (float*)wxb_named(ctx, "mel.raw", (size_t)n_chunks * n_frames * n_mels * 4);
+  if (!raw) return WXB_ERR_CUDA;
+  float* d_max = nullptr;
+  int rc = wxb_logmel_raw(ctx, audio_dev, chunk_off_host, chunk_len_host, n_chunks, n_samples_padded, n_mels, filters_dev, raw,
+                          &d_max, st);
+  if (rc != WXB_OK) return rc;
+  logmel_finalize_kernel<<<dim3(ceil_div(n_frames, 32), n_chunks), 256, 0, st>>>(raw, d_max, n_frames, n_mels, mel_out_dev, melT,
+                                                                                melT_rows_per_chunk);
+  WXB_LAUNCH_CHECK(ctx);
+  return WXB_OK;
+}
+
 extern "C" int wxb_logmel(wxb_ctx* ctx, const float* audio_dev, const int64_t* chunk_off_host,
                           const int32_t* chunk_len_host, int n_chunks, int n_samples_padded, int n_mels,
                           const float* filters_dev, float* mel_out_dev, void* stream) {
@@ -234,18 +290,29 @@ extern "C" int wxb_logmel(wxb_ctx* ctx, const float* audio_dev, const int64_t* c
   if (n_chunks == 0) return WXB_OK;
   if (!audio_dev || !chunk_off_host || !chunk_len_host || n_chunks < 0 || !filters_dev || !mel_out_dev)
     return wxb_fail(ctx, WXB_ERR_INVALID, "wxb_logmel: bad argument");
-  cudaStream_t st = (cudaStream_t)stream;
   WXB_CUDA(ctx, cudaSetDevice(ctx->device));
-  float* d_max = nullptr;
-  int rc = wxb_logmel_raw(ctx, audio_dev, chunk_off_host, chunk_len_host, n_chunks, n_samples_padded, n_mels,
-                          filters_dev, mel_out_dev, &d_max, st);
+  return logmel_run(ctx, audio_dev, chunk_off_host, chunk_len_host, n_chunks, n_samples_padded, n_mels, filters_dev, mel_out_dev,
+                    nullptr, 0, (cudaStream_t)stream);
+}
+
+// K1 -> K2 hand-off on the device: the log-mel of 30 s chunks goes straight into the encoder's frame-major bf16 input
+// (ctx workspace "enc.melT"); wxb_encode(ctx, NULL, n_chunks, ...) consumes it.  mel_out_dev may be NULL.
+extern "C" int wxb_logmel_features(wxb_ctx* ctx, const float* audio_dev, const int64_t* chunk_off_host,
+                                   const int32_t* chunk_len_host, int n_chunks, int n_mels, const float* filters_dev,
+                                   float* mel_out_dev, void* stream) {
+  if (!ctx) return WXB_ERR_INVALID;
+  if (!audio_dev || !chunk_off_host || !chunk_len_host || n_chunks <= 0 || !filters_dev)
+    return wxb_fail(ctx, WXB_ERR_INVALID, "wxb_logmel_features: bad argument");
+  if (n_mels % 8) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "wxb_logmel_features: n_mels=%d must be a multiple of 8", n_mels);
+  WXB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int G1 = 3002;  // padded frames per chunk of the encoder input (wxb_encoder.cu)
+  __nv_bfloat16* melT = (__nv_bfloat16*)wxb_named(ctx, "enc.melT", ((size_t)n_chunks * G1 + 2) * n_mels * 2);
+  if (!melT) return WXB_ERR_CUDA;
+  ctx->melT_chunks = 0;
+  int rc = logmel_run(ctx, audio_dev, chunk_off_host, chunk_len_host, n_chunks, 480000, n_mels, filters_dev, mel_out_dev, melT, G1,
+                      (cudaStream_t)stream);
   if (rc != WXB_OK) return rc;
-  const long long per_chunk = (long long)n_mels * (n_samples_padded / LM_HOP);
-  const long long total = per_chunk * n_chunks;
-  const int threads = 256;
-  long long blocks = ceil_div64(total, threads * 4);
-  if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
-  logmel_finalize_kernel<<<(unsigned)blocks, threads, 0, st>>>(mel_out_dev, d_max, per_chunk, total);
-  WXB_LAUNCH_CHECK(ctx);
+  ctx->melT_chunks = n_chunks;
+  ctx->melT_mels = n_mels;
   return WXB_OK;
 }

@@ -70,6 +70,8 @@ def load_library(path: Optional[str] = None):
         lib.wxb_launch_count.argtypes = [vp]
         lib.wxb_logmel.restype = i32
         lib.wxb_logmel.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp]
+        lib.wxb_logmel_features.restype = i32
+        lib.wxb_logmel_features.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp]
         lib.wxb_ctc_align.restype = i32
         lib.wxb_ctc_align.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
         lib.wxb_log_softmax_rows.restype = i32
@@ -112,7 +114,7 @@ EXPORTED_SYMBOLS = (
     "wxb_abi_version", "wxb_create", "wxb_destroy", "wxb_last_error", "wxb_launch_count", "wxb_logmel",
     "wxb_ctc_align", "wxb_log_softmax_rows", "wxb_set_model", "wxb_encode", "wxb_decode_greedy",
     "wxb_decoder_logits", "wxb_gemm_bf16", "wxb_decode_stats", "wxb_encoder_attention", "wxb_decoder_sample",
-    "wxb_set_align_model", "wxb_w2v_frames", "wxb_w2v_emissions", "wxb_debug_set", "wxb_debug_copy")
+    "wxb_logmel_features", "wxb_set_align_model", "wxb_w2v_frames", "wxb_w2v_emissions", "wxb_debug_set", "wxb_debug_copy")
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -184,6 +186,21 @@ class Context:
         assert out.is_contiguous() and out.dtype == torch.float32 and out.numel() == n * n_mels * n_frames
         self._check(self.lib.wxb_logmel(self.h, _ptr(audio_dev), _np_ptr(off), _np_ptr(ln), n, n_samples_padded,
                                         n_mels, _ptr(filters_dev), _ptr(out), self._stream()))
+        return out
+
+    def logmel_features(self, audio_dev: torch.Tensor, chunk_off: np.ndarray, chunk_len: np.ndarray, n_mels: int,
+                        filters_dev: torch.Tensor, want_f32: bool = False) -> Optional[torch.Tensor]:
+        """K1 -> K2 hand-off for 30 s chunks: the log-mel is left in the context's encoder input buffer (bf16, frame-major);
+        follow with encode(None, n_chunks=...).  Returns the f32 [n, n_mels, 3000] tensor only if want_f32."""
+        assert audio_dev.is_cuda and audio_dev.dtype == torch.float32 and audio_dev.is_contiguous()
+        off = np.ascontiguousarray(chunk_off, dtype=np.int64)
+        ln = np.ascontiguousarray(chunk_len, dtype=np.int32)
+        n = len(off)
+        if n and int((off + ln).max()) > audio_dev.numel():
+            raise ValueError("chunk exceeds the audio buffer")
+        out = torch.empty((n, n_mels, 3000), dtype=torch.float32, device=self.device) if want_f32 else None
+        self._check(self.lib.wxb_logmel_features(self.h, _ptr(audio_dev), _np_ptr(off), _np_ptr(ln), n, n_mels, _ptr(filters_dev),
+                                                 _ptr(out), self._stream()))
         return out
 
     # ---------------------------------------------------------------- K4
@@ -269,11 +286,15 @@ class Context:
         self._check(self.lib.wxb_debug_copy(self.h, name.encode(), _ptr(out), int(offset_bytes), out.numel() * out.element_size()))
         return out
 
-    def encode(self, mel_dev: torch.Tensor) -> torch.Tensor:
-        """mel f32 cuda [B, n_mels, 3000] -> bf16 cuda [B, 1500, d]."""
+    def encode(self, mel_dev: Optional[torch.Tensor], n_chunks: Optional[int] = None) -> torch.Tensor:
+        """mel f32 cuda [B, n_mels, 3000] -> bf16 cuda [B, 1500, d].  mel_dev = None: encode the n_chunks chunks whose
+        log-mel the last logmel_features call left on the device."""
         dims = self._keep["dims"]
-        assert mel_dev.is_cuda and mel_dev.dtype == torch.float32 and mel_dev.is_contiguous()
-        B = mel_dev.shape[0]
+        if mel_dev is None:
+            B = int(n_chunks)
+        else:
+            assert mel_dev.is_cuda and mel_dev.dtype == torch.float32 and mel_dev.is_contiguous()
+            B = mel_dev.shape[0]
         out = torch.empty((B, dims["n_audio_ctx"], dims["n_audio_state"]), dtype=torch.bfloat16, device=self.device)
         self._check(self.lib.wxb_encode(self.h, _ptr(mel_dev), B, _ptr(out), self._stream()))
         return out

@@ -397,10 +397,9 @@ def align(
             aligned_segments.append(plain)
             continue
         _, text_clean, _tokens, T, n_channels = job
-        path = [Point(int(ptok[t]), t, float(pprob[t])) for t in range(T)]
-        char_segments = merge_repeats(path, text_clean)
+        runs = _merge_runs(ptok, pprob)
         ratio = (t2 - t1) * n_channels / (T - 1)
-        aligned_segments += _assemble(text, prepared[sdx], char_segments, ratio, t1, spaced,
+        aligned_segments += _assemble(text, prepared[sdx], runs, ratio, t1, spaced,
                                       interpolate_method, return_char_alignments)
 
     word_segments: List[SingleWordSegment] = []
@@ -409,94 +408,138 @@ def align(
     return {"segments": aligned_segments, "word_segments": word_segments}
 
 
-def _assemble(text, prep, char_segments, ratio, t1, spaced, interpolate_method, return_char_alignments):
+def _assemble(text, prep, runs, ratio, t1, spaced, interpolate_method, return_char_alignments):
     """Char -> word -> sentence aggregation (alignment.py:281-373).  A segment that is ONE sentence (always the case when
     nltk is absent, and for most ASR segments) takes the numpy path below, which reproduces the pandas results value for
     value (tests/test_host_cpu.py compares the two on random inputs); everything else goes through the reference's own
     pandas primitives."""
     spans = prep["sentence_spans"]
+    if runs and not isinstance(runs, tuple):  # a list of Segment objects (merge_repeats output)
+        runs = ([g.start for g in runs], [g.end for g in runs], [g.score for g in runs])
     if len(spans) == 1:
-        return _assemble_single_sentence(text, prep, char_segments, ratio, t1, spaced, return_char_alignments)
+        return _assemble_single_sentence(text, prep, runs, ratio, t1, spaced, return_char_alignments)
+    char_segments = [Segment("", a, b, v) for a, b, v in zip(*runs)]  # the pandas path only reads start / end / score
     return _assemble_pandas(text, prep, char_segments, ratio, t1, spaced, interpolate_method, return_char_alignments)
 
 
-def _assemble_single_sentence(text, prep, char_segments, ratio, t1, spaced, return_char_alignments):
-    """The pandas pipeline of alignment.py:308-373 for a single sentence span, on numpy arrays: per word min(start) /
-    max(end) / round(mean(score), 3) with NaN skipping (the mean exactly as pandas' nanmean: NaNs replaced by 0, one
-    ndarray.sum over the word's characters, divided by the count of non-NaN), then the one-row groupby(start, end): a row
-    whose start or end is NaN is dropped, otherwise the row comes back with native Python floats."""
+def _round3(a: np.ndarray) -> np.ndarray:
+    """Python's round(x, 3) (correctly rounded decimal, what the reference applies to every character time) for an array:
+    numpy's multiply-rint-divide gives the same double unless x sits on a rounding boundary; only those go through round()."""
+    out = np.round(a, 3)
+    y = a * 1000.0
+    for i in np.flatnonzero(np.abs(y - np.floor(y) - 0.5) < 1e-6).tolist():
+        out[i] = round(float(a[i]), 3)
+    return out
+
+
+def _assemble_single_sentence(text, prep, runs, ratio, t1, spaced, return_char_alignments):
+    """The pandas pipeline of alignment.py:308-373 for a single sentence span on numpy arrays, a handful of array operations
+    per SEGMENT instead of several pandas calls per WORD: per word fmin(start) / fmax(end) / round(nanmean(score), 3) through
+    ufunc.reduceat over the word's non-space characters (the mean exactly as pandas' nanmean: NaNs count as 0 in one sum,
+    divided by the number of non-NaN values), then the one-row groupby(start, end): a row whose start or end is NaN is
+    dropped, otherwise the row comes back with native Python floats.  `runs` = (first frame, end frame, mean prob) lists of
+    the merged path, one entry per clean character."""
     n = len(text)
+    r_start, r_end, r_score = runs
     start = np.full(n, np.nan)
     end = np.full(n, np.nan)
     score = np.full(n, np.nan)
-    for k, cdx in enumerate(prep["clean_cdx"]):
-        cs = char_segments[k]
-        start[cdx] = round(cs.start * ratio + t1, 3)
-        end[cdx] = round(cs.end * ratio + t1, 3)
-        score[cdx] = round(cs.score, 3)
-    widx = np.empty(n, dtype=np.int64)
-    w = 0
-    for cdx in range(n):
-        widx[cdx] = w
-        if not spaced:
-            w += 1
-        elif cdx == n - 1 or text[cdx + 1] == " ":
-            w += 1
+    cdx = prep["clean_cdx"]
+    if len(cdx):
+        start[cdx] = _round3(np.asarray(r_start, dtype=np.float64) * ratio + t1)
+        end[cdx] = _round3(np.asarray(r_end, dtype=np.float64) * ratio + t1)
+        score[cdx] = _round3(np.asarray(r_score, dtype=np.float64))
     s0, s1 = prep["sentence_spans"][0]
     lo, hi = max(int(s0), 0), min(int(s1), n - 1)  # `.loc` selection: both ends inclusive, clipped to the rows that exist
     if hi < lo:
         return []
     is_space = np.frombuffer(text.encode("utf-32-le"), dtype=np.uint32) == 32
-
-    def nanmin(a):
-        a = a[~np.isnan(a)]
-        return a.min() if a.size else np.float64(np.nan)
-
-    def nanmax(a):
-        a = a[~np.isnan(a)]
-        return a.max() if a.size else np.float64(np.nan)
-
+    if spaced:
+        widx = np.cumsum(is_space) - int(is_space[0])  # a new word starts AT each " " after the first character
+    else:
+        widx = np.arange(n)
+    sel = slice(lo, hi + 1)
     words = []
-    c = lo
-    while c <= hi:
-        e = c
-        while e + 1 <= hi and widx[e + 1] == widx[c]:
-            e += 1
-        wtext = text[c:e + 1].strip()
-        if len(wtext) > 0:
-            keep = ~is_space[c:e + 1]
-            ws, we, wsc = start[c:e + 1][keep], end[c:e + 1][keep], score[c:e + 1][keep]
-            w_start, w_end = nanmin(ws), nanmax(we)
-            nn = ~np.isnan(wsc)
-            cnt = int(nn.sum())
-            w_score = round(np.where(nn, wsc, 0.0).sum() / cnt, 3) if cnt else np.float64(np.nan)
-            entry = {"word": wtext}
-            if not np.isnan(w_start):
-                entry["start"] = w_start
-            if not np.isnan(w_end):
-                entry["end"] = w_end
-            if not np.isnan(w_score):
-                entry["score"] = w_score
-            words.append(entry)
-        c = e + 1
-    sent_start = nanmin(start[lo:hi + 1])
-    sent_end = nanmax(end[lo:hi + 1][~is_space[lo:hi + 1]])
+    sp = is_space[sel]
+    wsel = widx[sel]
+    first = np.concatenate([[0], np.flatnonzero(wsel[1:] != wsel[:-1]) + 1])  # reduceat offsets: one group per word of the selection
+    st_m = np.where(sp, np.nan, start[sel])   # spaces take no part in a word's times / score
+    en_m = np.where(sp, np.nan, end[sel])
+    sc_m = np.where(sp, np.nan, score[sel])
+    w_start = np.fmin.reduceat(st_m, first)
+    w_end = np.fmax.reduceat(en_m, first)
+    n_ns = np.add.reduceat((~sp).astype(np.int64), first).tolist()   # non-space characters per word
+    # score: pandas' nanmean = ONE ndarray.sum over the word's non-space characters with NaNs counted as 0, divided by the
+    # number of non-NaN values.  ndarray.sum's association is its own (neither left-to-right nor reduceat's); the orders
+    # differ by an ulp, which matters only when the mean sits on a rounding boundary of round(., 3): those words (and only
+    # those) are re-summed with ndarray.sum itself on the compacted array.
+    sc_ns = score[sel][~sp]
+    ok_ns = ~np.isnan(sc_ns)
+    z_ns = np.where(ok_ns, sc_ns, 0.0)
+    ok_cum = np.concatenate([[0], np.cumsum(ok_ns)]).tolist()
+    ok_m = ~np.isnan(sc_m)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        mean_fast = np.add.reduceat(np.where(ok_m, sc_m, 0.0), first) / np.add.reduceat(ok_m.astype(np.int64), first)
+        y = mean_fast * 1000.0
+        on_boundary = (np.abs(y - np.floor(y) - 0.5) < 1e-6).tolist()
+    score_fast = np.round(mean_fast, 3)
+    bounds = first.tolist() + [hi + 1 - lo]
+    has_s, has_e = (~np.isnan(w_start)).tolist(), (~np.isnan(w_end)).tolist()
+    j = 0  # cursor into the compacted (non-space) arrays
+    for k in range(len(first)):
+        c, e = lo + bounds[k], lo + bounds[k + 1]
+        j0, j = j, j + n_ns[k]
+        wtext = text[c:e].strip()
+        if not wtext:
+            continue
+        entry = {"word": wtext}
+        if has_s[k]:
+            entry["start"] = w_start[k]
+        if has_e[k]:
+            entry["end"] = w_end[k]
+        cnt = ok_cum[j] - ok_cum[j0]
+        if cnt:
+            entry["score"] = np.round(z_ns[j0:j].sum() / cnt, 3) if on_boundary[k] else score_fast[k]
+        words.append(entry)
+    ns = np.flatnonzero(~sp) + lo
+    sent_start = np.fmin.reduce(start[sel]) if hi >= lo else np.nan
+    sent_end = np.fmax.reduce(end[ns]) if ns.size else np.nan
     if np.isnan(sent_start) or np.isnan(sent_end):
         return []  # groupby drops rows with a NaN key (a single row has no neighbour to interpolate from)
     out = {"start": float(sent_start), "end": float(sent_end), "text": text[s0:s1], "words": words}
     if return_char_alignments:
         chars = []
-        for cdx in range(lo, hi + 1):
-            rec = {"char": text[cdx]}
-            if not np.isnan(start[cdx]):
-                rec["start"] = float(start[cdx])
-            if not np.isnan(end[cdx]):
-                rec["end"] = float(end[cdx])
-            if not np.isnan(score[cdx]):
-                rec["score"] = float(score[cdx])
+        st_l, en_l, sc_l = start.tolist(), end.tolist(), score.tolist()
+        for c in range(lo, hi + 1):
+            rec = {"char": text[c]}
+            if st_l[c] == st_l[c]:
+                rec["start"] = st_l[c]
+            if en_l[c] == en_l[c]:
+                rec["end"] = en_l[c]
+            if sc_l[c] == sc_l[c]:
+                rec["score"] = sc_l[c]
             chars.append(rec)
         out["chars"] = chars
     return [out]
+
+
+def _merge_runs(path_tok: np.ndarray, path_prob: np.ndarray):
+    """merge_repeats (alignment.py:597-613) straight from the kernel's per-frame arrays: (first frame, end frame, mean prob)
+    of every run of equal token index, as three lists.  The mean is the left-to-right double sum of the per-frame float
+    probabilities over the run length, exactly what merging T Point objects gives."""
+    T = len(path_tok)
+    if T == 0:
+        return [], [], []
+    cut = (np.flatnonzero(path_tok[1:] != path_tok[:-1]) + 1).tolist()
+    lo, hi = [0] + cut, cut + [T]
+    prob = path_prob.astype(np.float64).tolist()
+    return lo, hi, [sum(prob[a:b]) / (b - a) for a, b in zip(lo, hi)]
+
+
+def _merge_repeats_arrays(path_tok: np.ndarray, path_prob: np.ndarray, transcript: str) -> List[Segment]:
+    lo, hi, sc = _merge_runs(path_tok, path_prob)
+    tok = path_tok.tolist()
+    return [Segment(transcript[tok[a]], a, b, v) for a, b, v in zip(lo, hi, sc)]
 
 
 def _assemble_pandas(text, prep, char_segments, ratio, t1, spaced, interpolate_method, return_char_alignments):

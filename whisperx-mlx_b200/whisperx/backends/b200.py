@@ -161,8 +161,8 @@ class B200WhisperBackend(WhisperBackend):
             raise ValueError(f"batch_size={batch_size}: the decoder takes 1..{MAX_BATCH} sequences per call (include/wxb200.h)")
         for i in range(0, n, batch_size):
             j = min(n, i + batch_size)
-            mel = self.ctx.logmel(audio_dev, offs[i:j], lens[i:j], N_SAMPLES, self.dims["n_mels"], self._filters)
-            enc = self.ctx.encode(mel)
+            self.ctx.logmel_features(audio_dev, offs[i:j], lens[i:j], self.dims["n_mels"], self._filters)  # K1 -> K2 on the device
+            enc = self.ctx.encode(None, n_chunks=j - i)
             r = self.ctx.decode_greedy(enc, prompt, self.specials["eot"], no_speech=self.specials["no_speech"],
                                        sample_len=int(self.options["sample_len"]),
                                        suppress_blank=bool(self.options["suppress_blank"]),
