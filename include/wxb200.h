@@ -94,7 +94,7 @@ int wxb_logmel_features(wxb_ctx* ctx, const float* audio_dev, const int64_t* chu
  * t_off_host int32[n_seg+1]   frame offsets of each segment inside emis_dev
  * tok_dev    int32[sum N]     token ids per segment back to back, -1 = wildcard
  * n_off_host int32[n_seg+1]   token offsets
- * mode       WXB_CTC_BACKTRACK (alignment.py:447) or WXB_CTC_BEAM2 (alignment.py:500, width 2)
+ * mode       WXB_CTC_BACKTRACK (alignment.py:447), WXB_CTC_BEAM2 (alignment.py:500, width 2 as align() calls it) or WXB_CTC_BEAM(w)
  * trellis_dev   optional f32 buffer of sum(T_i*N_i) elements receiving every segment's trellis
  *               (row-major [T_i, N_i], back to back, offsets = prefix sums of T_i*N_i);
  *               NULL = use the ctx workspace.
@@ -105,6 +105,8 @@ int wxb_logmel_features(wxb_ctx* ctx, const float* audio_dev, const int64_t* chu
  * status_dev    int32[n_seg]  0 ok, 1 = "backtrack failed" (alignment.py:271 / assert :451)
  * ---------------------------------------------------------------------------------------- */
 enum { WXB_CTC_BACKTRACK = 0, WXB_CTC_BEAM2 = 1, WXB_CTC_TRELLIS_ONLY = 2 };
+/* backtrack_beam with another beam_width w in 1..8 (the reference's default is 5): mode = WXB_CTC_BEAM(w) */
+#define WXB_CTC_BEAM(w) (WXB_CTC_BEAM2 | ((w) << 8))
 
 int wxb_ctc_align(wxb_ctx* ctx, const float* emis_dev, const int32_t* t_off_host,
                   const int32_t* tok_dev, const int32_t* n_off_host, int n_seg, int V, int blank,

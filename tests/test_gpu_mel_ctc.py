@@ -186,3 +186,24 @@ def test_logmel_features_handoff_equals_f32_path(wxb_ctx):
     assert torch.equal(enc, enc_handoff)
     with pytest.raises(Exception):
         wxb_ctx.encode(None, n_chunks=len(chunks))  # the hand-off buffer was consumed
+
+
+@pytest.mark.parametrize("name", ["small", "medium_wild", "peaky", "blank_last", "one_token", "n_eq_t", "n_gt_t", "full"])
+def test_backtrack_beam_other_widths_vs_reference_golden(wxb_ctx, golden_dir, name):
+    """backtrack_beam for beam widths 1, 3, 5 (the reference's default) and 8: indices bit-exact against paths produced by
+    the reference itself (tests/golden/make_beam_golden.py)."""
+    import whisperx.alignment as wa
+    g = np.load(os.path.join(golden_dir, "ctc_golden.npz"))
+    gb = np.load(os.path.join(golden_dir, "beam_width_golden.npz"))
+    em = torch.from_numpy(g[f"{name}_emission"])
+    tokens = g[f"{name}_tokens"].tolist()
+    blank = int(g[f"{name}_blank"])
+    for w in gb["widths"].tolist():
+        p = wa.backtrack_beam(None, em, tokens, blank, beam_width=w)
+        if int(gb[f"{name}_w{w}_ok"]):
+            assert p is not None and [q.token_index for q in p] == gb[f"{name}_w{w}_tok"].tolist(), (name, w)
+            np.testing.assert_allclose([q.score for q in p], gb[f"{name}_w{w}_score"], rtol=1e-6)
+        else:
+            assert p is None, (name, w)
+    with pytest.raises(NotImplementedError):
+        wa.backtrack_beam(None, em, tokens, blank, beam_width=9)

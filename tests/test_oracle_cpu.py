@@ -149,3 +149,17 @@ def test_timestamp_clause_oracle_vs_reference_golden(golden_dir):
     suppressed = torch.isneginf(out[:, :ts_begin]).all(1)
     assert suppressed.tolist() == g["ts_text_suppressed"].tolist()
     assert out.argmax(-1).tolist() == g["ts_argmax"].tolist()
+
+
+@pytest.mark.parametrize("name", CTC_CASES)
+def test_ctc_oracle_beam_widths_vs_reference_golden(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, "ctc_golden.npz"))
+    gb = np.load(os.path.join(golden_dir, "beam_width_golden.npz"))
+    em, tokens, blank = g[f"{name}_emission"], g[f"{name}_tokens"].tolist(), int(g[f"{name}_blank"])
+    tr = octc.get_trellis(em, tokens, blank)
+    for w in gb["widths"].tolist():
+        p = octc.backtrack_beam(tr, em, tokens, blank, beam_width=w)
+        if int(gb[f"{name}_w{w}_ok"]):
+            assert [q.token_index for q in p] == gb[f"{name}_w{w}_tok"].tolist(), (name, w)
+        else:
+            assert p is None

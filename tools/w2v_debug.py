@@ -40,12 +40,14 @@ def oracle(wave):
             x, _ = layer(x, None)
             feats.append(x[0].t().contiguous())
         proj = ref.encoder.feature_projection(feats[-1][None])
-        xpos = proj + ref.encoder.transformer.pos_conv_embed(proj)
+        xpos = ref.encoder.transformer._preprocess(proj)  # LayerNorm(x + pos conv): the base model's Transformer is built layer_norm_first
         layers, h = [], xpos
         for layer in ref.encoder.transformer.layers:
             h, _ = layer(h)
             layers.append(h[0])
-        logits = ref.aux(ref.encoder.transformer.layer_norm(h))[0]
+        logits = ref.aux(h)[0]
+        full, _ = ref(torch.from_numpy(wave)[None])
+        assert float((full[0] - logits).abs().max()) < 1e-4, "staged oracle differs from the module's own forward"
     return feats, proj[0], xpos[0], layers, logits
 
 
@@ -74,7 +76,7 @@ for cfg in configs:
             elif stage == 7:
                 report(f"seg {b} feature projection", ctx.debug_buffer("w2v.x", (T, 768), torch.float32, offset_bytes=b * P * 768 * 4), proj)
             elif stage == 8:
-                report(f"seg {b} x + pos conv", ctx.debug_buffer("w2v.x", (T, 768), torch.float32, offset_bytes=b * P * 768 * 4), xpos)
+                report(f"seg {b} LN(x + pos conv)", ctx.debug_buffer("w2v.x", (T, 768), torch.float32, offset_bytes=b * P * 768 * 4), xpos)
             else:
                 l = stage - 9
                 if l == 0:

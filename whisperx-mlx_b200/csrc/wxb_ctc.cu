@@ -21,6 +21,7 @@ struct CtcSeg {
 };
 
 #define CTC_WARPS 4
+#define CTC_WMAX 8  // widest beam of the backtrack_beam walk (the reference's default is 5, align() uses 2)
 #define CTC_RING 8
 #define CTC_PD 6
 
@@ -42,10 +43,11 @@ __device__ __forceinline__ float wild_max_global(const float* row, int V, int bl
   return warp_max(m);
 }
 
+template <int WMAX>  // beam arrays sized (and loops unrolled) for widths <= WMAX: 2 keeps align()'s walk in registers
 __global__ void __launch_bounds__(CTC_WARPS * 32)
 ctc_align_kernel(const float* __restrict__ emis, const int* __restrict__ tok,
                  const CtcSeg* __restrict__ segs, int n_seg, int V, int Vpad, int blank, int mode,
-                 int nmax_pad, int wpb, float* __restrict__ trellis, int2* __restrict__ hist,
+                 int nmax_pad, int wpb, int beam_w, float* __restrict__ trellis, int2* __restrict__ hist,
                  int* __restrict__ path_tok, float* __restrict__ path_lp,
                  float* __restrict__ path_prob, int* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -189,29 +191,30 @@ ctc_align_kernel(const float* __restrict__ emis, const int* __restrict__ tok,
     return;
   }
 
-  // ------------------------------------------------------------------ beam-2 (:500-579)
-  // All live beams share the same time index.  hist[k*2+slot] = (j | parent<<30, lp bits) is the
-  // point appended at step k (time T-1-k) by the beam that ends up in `slot` after the sort.
-  int2* H = hist + (size_t)sg.t_off * 2;
-  int bj[2];
-  float bs[2];
+  // ------------------------------------------------------------------ beam search of width W (:500-579; align() uses W = 2)
+  // All live beams share the same time index.  hist[k*W+slot] = (j | parent<<28, lp bits) is the point appended at step k
+  // (time T-1-k) by the beam that ends up in `slot` after the sort.  Candidates are generated beam by beam as [stay, change]
+  // and the first W of a STABLE descending sort on the predecessor cell's score survive (Python's sorted(..., reverse=True):
+  // ties keep generation order; duplicates of one cell are not merged).
+  const int W = beam_w;
+  int2* H = hist + (size_t)sg.t_off * W;
+  int bj[WMAX];
   int nb = 1;
   int t = T - 1;
   bj[0] = N - 1;
-  bs[0] = TR[(size_t)t * N + (N - 1)];
-  bj[1] = 0;
-  bs[1] = 0.f;
   const float lp0 = E[(size_t)t * V + blank];
   int K = 0;
   while (nb > 0 && bj[0] > 0) {
-    int cj[4], cp[4];
-    float cs[4], cl[4];
+    int cj[2 * WMAX], cp[2 * WMAX];
+    float cs[2 * WMAX], cl[2 * WMAX];
     int nc = 0;
     if (t > 0) {
       const float* erow = E + (size_t)(t - 1) * V;
       const float* trow = TR + (size_t)(t - 1) * N;
       const float p_stay = __ldg(erow + blank);
-      for (int i = 0; i < nb; ++i) {
+#pragma unroll
+      for (int i = 0; i < WMAX; ++i) {
+        if (i >= nb) break;
         const int j = bj[i];
         const float stay_score = trow[j];
         if (!isinf(stay_score)) { cj[nc] = j; cs[nc] = stay_score; cp[nc] = i; cl[nc] = p_stay; nc++; }
@@ -225,25 +228,26 @@ ctc_align_kernel(const float* __restrict__ emis, const int* __restrict__ tok,
         }
       }
     }
-    // stable descending top-2 (Python sorted(..., reverse=True)[:2])
-    int i0 = -1, i1 = -1;
-    for (int i = 0; i < nc; ++i)
-      if (i0 < 0 || cs[i] > cs[i0]) i0 = i;
-    for (int i = 0; i < nc; ++i)
-      if (i != i0 && (i1 < 0 || cs[i] > cs[i1])) i1 = i;
-    nb = nc < 2 ? nc : 2;
+    // stable descending top-W: repeatedly take the first not-yet-taken candidate with the largest score
+    nb = nc < W ? nc : W;
     t -= 1;
     K += 1;
-    if (nb >= 1) {
-      bj[0] = cj[i0]; bs[0] = cs[i0];
-      if (lane == 0) H[(size_t)K * 2 + 0] = make_int2(cj[i0] | (cp[i0] << 30), __float_as_int(cl[i0]));
-    }
-    if (nb >= 2) {
-      bj[1] = cj[i1]; bs[1] = cs[i1];
-      if (lane == 0) H[(size_t)K * 2 + 1] = make_int2(cj[i1] | (cp[i1] << 30), __float_as_int(cl[i1]));
+    unsigned taken = 0u;
+#pragma unroll
+    for (int s2 = 0; s2 < WMAX; ++s2) {
+      if (s2 >= nb) break;
+      int best = -1;
+      float best_s = 0.f;
+      int best_j = 0, best_p = 0;
+      float best_l = 0.f;
+#pragma unroll
+      for (int i = 0; i < 2 * WMAX; ++i)
+        if (i < nc && !((taken >> i) & 1u) && (best < 0 || cs[i] > best_s)) { best = i; best_s = cs[i]; best_j = cj[i]; best_p = cp[i]; best_l = cl[i]; }
+      taken |= 1u << best;
+      bj[s2] = best_j;
+      if (lane == 0) H[(size_t)K * W + s2] = make_int2(best_j | (best_p << 28), __float_as_int(best_l));
     }
   }
-  (void)bs;
   if (nb == 0) {
     if (lane == 0) status[seg_id] = 1;  // reference returns None -> "backtrack failed"
     return;
@@ -261,12 +265,12 @@ ctc_align_kernel(const float* __restrict__ emis, const int* __restrict__ tok,
   {
     int slot = 0;
     for (int k = K; k >= 1; --k) {
-      const int2 h = H[(size_t)k * 2 + slot];
-      const int j = h.x & 0x3fffffff;
+      const int2 h = H[(size_t)k * W + slot];
+      const int j = h.x & 0x0fffffff;
       const float lp = __int_as_float(h.y);
       const int tt = T - 1 - k;
       if (lane == 0) { o_tok[tt] = j; o_lp[tt] = lp; o_pr[tt] = expf(lp); }
-      slot = (h.x >> 30) & 1;
+      slot = (h.x >> 28) & 7;
     }
     if (lane == 0) { o_tok[T - 1] = N - 1; o_lp[T - 1] = lp0; o_pr[T - 1] = expf(lp0); status[seg_id] = 0; }
   }
@@ -298,8 +302,15 @@ int wxb_ctc_align(wxb_ctx* ctx, const float* emis_dev, const int32_t* t_off_host
   if (!emis_dev || !t_off_host || !tok_dev || !n_off_host || n_seg < 0 || V <= 0 || blank < 0 ||
       blank >= V || !status_dev)
     return wxb_fail(ctx, WXB_ERR_INVALID, "wxb_ctc_align: bad argument");
+  // mode = base | beam_width << 8; a beam walk with no width given is the width align() uses (2)
+  int beam_w = (mode >> 8) & 0xff;
+  mode &= 0xff;
   if (mode != WXB_CTC_BACKTRACK && mode != WXB_CTC_BEAM2 && mode != WXB_CTC_TRELLIS_ONLY)
     return wxb_fail(ctx, WXB_ERR_INVALID, "wxb_ctc_align: unknown mode %d", mode);
+  if (mode == WXB_CTC_BEAM2 && beam_w == 0) beam_w = 2;
+  if (mode == WXB_CTC_BEAM2 && (beam_w < 1 || beam_w > CTC_WMAX))
+    return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "wxb_ctc_align: beam width %d (supported: 1..%d)", beam_w, CTC_WMAX);
+  if (mode != WXB_CTC_BEAM2) beam_w = 1;
   if (mode != WXB_CTC_TRELLIS_ONLY && (!path_tok_dev || !path_lp_dev || !path_prob_dev))
     return wxb_fail(ctx, WXB_ERR_INVALID, "wxb_ctc_align: path outputs are NULL");
   cudaStream_t st = (cudaStream_t)stream;
@@ -314,7 +325,7 @@ int wxb_ctc_align(wxb_ctx* ctx, const float* emis_dev, const int32_t* t_off_host
     g.n_off = n_off_host[s];
     g.N = n_off_host[s + 1] - n_off_host[s];
     if (g.T < 0 || g.N < 0) return wxb_fail(ctx, WXB_ERR_INVALID, "wxb_ctc_align: offsets not monotone");
-    if (g.N >= (1 << 30)) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "wxb_ctc_align: N too large");
+    if (g.N >= (1 << 28)) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "wxb_ctc_align: N too large");
     g.tr_off = tr_total;
     tr_total += (long long)g.T * g.N;
     if (g.N > nmax) nmax = g.N;
@@ -336,14 +347,15 @@ int wxb_ctc_align(wxb_ctx* ctx, const float* emis_dev, const int32_t* t_off_host
     if ((rc = wxb_reserve(ctx, ctx->ws_ctc_trellis, sizeof(float) * (size_t)(tr_total > 0 ? tr_total : 1))) != WXB_OK) return rc;
     trellis_dev = (float*)ctx->ws_ctc_trellis.p;
   }
-  if ((rc = wxb_reserve(ctx, ctx->ws_ctc_hist, sizeof(int2) * 2 * (size_t)(sumT + 1))) != WXB_OK) return rc;
+  if ((rc = wxb_reserve(ctx, ctx->ws_ctc_hist, sizeof(int2) * (size_t)beam_w * (size_t)(sumT + 1))) != WXB_OK) return rc;
   WXB_CUDA(ctx, cudaMemcpyAsync(ctx->ws_ctc_meta.p, segs.data(), sizeof(CtcSeg) * n_seg, cudaMemcpyHostToDevice, st));
   // the pageable source buffer `segs` dies at return: the copy above is staged synchronously by
   // the runtime for pageable memory, so this is safe.
-  if ((rc = wxb_func_smem(ctx, ctc_align_kernel, (int)smem)) != WXB_OK) return rc;
+  auto kern = beam_w <= 2 ? ctc_align_kernel<2> : ctc_align_kernel<CTC_WMAX>;
+  if ((rc = wxb_func_smem(ctx, kern, (int)smem)) != WXB_OK) return rc;
   const int grid = ceil_div(n_seg, wpb);
-  ctc_align_kernel<<<grid, wpb * 32, smem, st>>>(
-      emis_dev, tok_dev, (const CtcSeg*)ctx->ws_ctc_meta.p, n_seg, V, Vpad, blank, mode, nmax_pad, wpb,
+  kern<<<grid, wpb * 32, smem, st>>>(
+      emis_dev, tok_dev, (const CtcSeg*)ctx->ws_ctc_meta.p, n_seg, V, Vpad, blank, mode, nmax_pad, wpb, beam_w,
       trellis_dev, (int2*)ctx->ws_ctc_hist.p, path_tok_dev, path_lp_dev, path_prob_dev, status_dev);
   WXB_LAUNCH_CHECK(ctx);
   return WXB_OK;

@@ -6,9 +6,11 @@
 //   waveform -> conv(1->512, k10 s5) -> GroupNorm(512 groups: per channel over time) -> GELU
 //            -> 4 x [conv(512->512, k3 s2) -> GELU] -> 2 x [conv(512->512, k2 s2) -> GELU]          (no conv biases)
 //            -> LayerNorm(512) -> Linear(512->768)
-//            -> x + GELU(grouped conv(768->768, k128, 16 groups, pad 64, last frame dropped))        (weight-norm folded)
+//            -> LayerNorm(x + GELU(grouped conv(768->768, k128, 16 groups, pad 64, last frame dropped)))   (weight-norm folded;
+//               torchaudio builds the base model's Transformer with layer_norm_first = NOT encoder_layer_norm_first, i.e. its
+//               `layer_norm` sits right after the positional conv and there is no final LayerNorm: components.py:419-426, :756)
 //            -> 12 x [x = LN(x + MHA(x)); x = LN(x + W2 GELU(W1 x))]   (post-LN, 12 heads x 64)
-//            -> LayerNorm -> Linear(768->n_out) = emission logits [T, n_out], T = floor((S - 400) / 320) + 1
+//            -> Linear(768->n_out) = emission logits [T, n_out], T = floor((S - 400) / 320) + 1
 //
 // Data layout (B segments, P = padded frames per segment, frame-major / channels-last everywhere):
 //   c0 bf16 [B * 64P, 512], c1 [B * 32P, 512] ... c6 [B * P, 512]: conv stack outputs.  Segment b owns rows b * (P << (6 - l)) ..;
@@ -391,7 +393,10 @@ extern "C" int wxb_w2v_emissions(wxb_ctx* ctx, const float* audio_dev, const int
       a.g_in = Pg; a.g_valid = P; a.g_out = P; a.out_off = 0;  // im2col row u of a segment's block = output frame u
       if ((rc = wxb_gemm_launch(ctx, a, st)) != WXB_OK) return rc;
     }
-    if ((rc = launch_ln<float>(ctx, x, nullptr, nullptr, nullptr, xn, M, d, 0, st)) != WXB_OK) return rc;  // bf16 copy, no norm
+    const float* lw = (const float*)aw(ctx, "w2v.ln.w");
+    const float* lb = (const float*)aw(ctx, "w2v.ln.b");
+    if (!lw || !lb) return WXB_ERR_STATE;
+    if ((rc = launch_ln<float>(ctx, x, lw, lb, x, xn, M, d, 1, st)) != WXB_OK) return rc;  // transformer.layer_norm
   }
   if (stop == 8) return WXB_OK;
   // ---- 12 post-LN transformer layers
@@ -438,14 +443,11 @@ extern "C" int wxb_w2v_emissions(wxb_ctx* ctx, const float* audio_dev, const int
     if ((rc = launch_ln<float>(ctx, x, ln2_w, ln2_b, x, xn, M, d, 1, st)) != WXB_OK) return rc;
     if (stop == 9 + l) return WXB_OK;
   }
-  // ---- final LayerNorm -> Linear(d -> n_out); frames of every segment packed back to back
+  // ---- Linear(d -> n_out) on the last layer's output (xn); frames of every segment packed back to back
   {
-    const float* lw = (const float*)aw(ctx, "w2v.ln.w");
-    const float* lb = (const float*)aw(ctx, "w2v.ln.b");
     const __nv_bfloat16* w = (const __nv_bfloat16*)aw(ctx, "w2v.aux.w");
     const float* bias = (const float*)aw(ctx, "w2v.aux.b");
-    if (!lw || !lb || !w || !bias) return WXB_ERR_STATE;
-    if ((rc = launch_ln<float>(ctx, x, lw, lb, nullptr, xn, M, d, 1, st)) != WXB_OK) return rc;
+    if (!w || !bias) return WXB_ERR_STATE;
     GemmArgs a;
     a.A = xn; a.lda = d; a.M = (int)M; a.W = w; a.N = V; a.K = d; a.bias = bias; a.out = emis_pad; a.out_f32 = 1; a.ldo = V;
     if ((rc = wxb_gemm_launch(ctx, a, st)) != WXB_OK) return rc;

@@ -20,6 +20,13 @@ _lib_lock = threading.Lock()
 CTC_BACKTRACK, CTC_BEAM2, CTC_TRELLIS_ONLY = 0, 1, 2
 
 
+def ctc_beam_mode(beam_width: int) -> int:
+    """wxb_ctc_align mode of backtrack_beam with this beam width (WXB_CTC_BEAM(w) of include/wxb200.h)."""
+    if not 1 <= int(beam_width) <= 8:
+        raise NotImplementedError(f"backtrack_beam: beam_width={beam_width} (the kernel keeps 1..8 beams)")
+    return CTC_BEAM2 | (int(beam_width) << 8)
+
+
 class WxbError(RuntimeError):
     pass
 

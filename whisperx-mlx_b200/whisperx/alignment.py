@@ -191,12 +191,10 @@ def backtrack(trellis, emission, tokens, blank_id=0):
 
 
 def backtrack_beam(trellis, emission, tokens, blank_id=0, beam_width=5):
-    """alignment.py:500-579.  The device kernel implements the width the reference's align() uses
-    (beam_width=2, alignment.py:269); other widths are not on the hot path."""
-    from ._native import CTC_BEAM2
-    if beam_width != 2:
-        raise NotImplementedError("the b200 aligner implements backtrack_beam for beam_width=2 (what align() uses)")
-    res, T = _run_single(emission, tokens, blank_id, CTC_BEAM2)
+    """alignment.py:500-579 for beam widths 1..8 (the reference's default is 5; align() calls it with 2, alignment.py:269).
+    `trellis` is accepted for signature compatibility; the kernel recomputes it bit-identically."""
+    from ._native import ctc_beam_mode
+    res, T = _run_single(emission, tokens, blank_id, ctc_beam_mode(beam_width))
     if int(res["status"][0]) != 0:
         return None
     return _points_from(res, T)
