@@ -1,6 +1,6 @@
 // wxb_logmel.cu — K1: log-mel frontend, replaces whisperx/audio.py:112-159.
 //
-// Pass 1 (logmel_kernel): one CTA = 16 consecutive STFT frames of one chunk (160 threads).  The 2800 input samples the frames
+// Pass 1 (logmel_kernel): one CTA = 16 consecutive STFT frames of one chunk (LM_THREADS threads).  The 2800 input samples the frames
 // cover are staged once in shared memory (16-byte loads where the tile lies inside the chunk; reflect padding at the chunk
 // edges and zero padding beyond the chunk's valid length applied on the way in), two real frames share one 400-point complex
 // FFT (radix 4,4,5,5 Stockham in shared memory, wxb_fft400.h), |X|^2 goes back to shared memory and the sparse (banded) mel
@@ -16,7 +16,9 @@
 
 #define LM_FRAMES 16
 #define LM_PAIRS 8
-#define LM_THREADS 160
+#ifndef LM_THREADS
+#define LM_THREADS 320  // 10 warps per CTA, 3 CTAs per SM (shared memory): the kernel is latency-bound, 5-warp CTAs issued 1.2 instr/clk/SM
+#endif
 #define LM_HOP 160
 #define LM_NFFT 400
 #define LM_NBIN 201
@@ -38,7 +40,7 @@ struct LmSmem {
   cpx bufB[LM_PAIRS * LM_NFFT];
   float coef[LM_COEF_FLOATS];
   int2 band[128];
-  float red[8];
+  float red[16];
 };
 
 // band[m] = (first non-zero bin, number of bins up to the last non-zero) of filter row m;
@@ -103,9 +105,7 @@ logmel_kernel(const float* __restrict__ audio, const long long* __restrict__ chu
   __syncthreads();
 
   // pass 1 (radix 4, Ns = 1): window + pack two frames, no twiddles
-#pragma unroll
-  for (int r = 0; r < (LM_PAIRS * 100) / LM_THREADS; ++r) {
-    const int b = tid + LM_THREADS * r;
+  for (int b = tid; b < LM_PAIRS * 100; b += LM_THREADS) {
     const int p = b / 100, i = b - p * 100;
     const float* fa = sm.samp + (2 * p) * LM_HOP;
     const float* fb = fa + LM_HOP;
@@ -123,25 +123,19 @@ logmel_kernel(const float* __restrict__ audio, const long long* __restrict__ chu
   }
   __syncthreads();
   // pass 2 (radix 4, Ns = 4): B -> A
-#pragma unroll
-  for (int r = 0; r < (LM_PAIRS * 100) / LM_THREADS; ++r) {
-    const int b = tid + LM_THREADS * r;
+  for (int b = tid; b < LM_PAIRS * 100; b += LM_THREADS) {
     const int p = b / 100, i = b - p * 100;
     fft400_butterfly<4, 4>(sm.bufB + p * LM_NFFT, sm.bufA + p * LM_NFFT, sm.tw, i);
   }
   __syncthreads();
   // pass 3 (radix 5, Ns = 16): A -> B
-#pragma unroll
-  for (int r = 0; r < (LM_PAIRS * 80) / LM_THREADS; ++r) {
-    const int b = tid + LM_THREADS * r;
+  for (int b = tid; b < LM_PAIRS * 80; b += LM_THREADS) {
     const int p = b / 80, i = b - p * 80;
     fft400_butterfly<5, 16>(sm.bufA + p * LM_NFFT, sm.bufB + p * LM_NFFT, sm.tw, i);
   }
   __syncthreads();
   // pass 4 (radix 5, Ns = 80): B -> A
-#pragma unroll
-  for (int r = 0; r < (LM_PAIRS * 80) / LM_THREADS; ++r) {
-    const int b = tid + LM_THREADS * r;
+  for (int b = tid; b < LM_PAIRS * 80; b += LM_THREADS) {
     const int p = b / 80, i = b - p * 80;
     fft400_butterfly<5, 80>(sm.bufB + p * LM_NFFT, sm.bufA + p * LM_NFFT, sm.tw, i);
   }
