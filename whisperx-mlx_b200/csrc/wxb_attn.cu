@@ -11,6 +11,14 @@
 // (P stays within bf16 / fp32 range), so the O_t rescale (tcgen05.ld, multiply, tcgen05.st) is rare after the first
 // tiles and the softmax threads touch O only once more, for the final 1 / sum.
 // Warp roles: 0..3 softmax A, 4..7 softmax B, 8 = TMA producer, 9 = MMA issuer, 10 = TMEM allocator.
+//
+// Measured and not kept in round 2 (same shape, A/B inside one gpurun call; git history has both kernels):
+//   * S read from tensor memory ONCE per key tile (offset fixed by the first tile's exact row maximum, growth of the maximum
+//     detected on the fly, tile redone on the rare overflow): parity-clean, 1.233 ms vs 1.160 ms - tensor-memory read
+//     bandwidth is not the limiter, the extra max tracking in the exp pass costs more than the second tcgen05.ld;
+//   * two threads per query row (16 softmax warps, half-row maxima / sums exchanged through shared memory behind named
+//     barriers; 96 registers per thread because 18 warps put 5 on one scheduler): parity-clean, 1.252 ms vs 1.159 ms;
+//   * other FMA-pipe / MUFU splits of the exponentials (ATTN_POLY): flat between a quarter and a half of the pairs.
 #include "wxb_common.cuh"
 #include "wxb_tc.cuh"
 #include <math.h>
@@ -37,6 +45,12 @@ constexpr int TM_S = 0, TM_O = 256, TM_P = 384;  // TMEM columns: S_A, S_B at 0 
 #ifndef WXB_ATTN_P_TMEM
 #define WXB_ATTN_P_TMEM 1
 #endif
+#ifndef WXB_ATTN_POLY
+#define WXB_ATTN_POLY 2
+#endif
+// which pairs of a row's exponentials run on the FMA pipe instead of MUFU.EX2: 0 = none, 1 = every 4th pair, 2 = every other pair,
+// 3 = three of four pairs (measured, 60 x 20 heads, T = 1500: 1.250 / 1.153 / 1.160 / 1.231 ms per layer)
+constexpr int ATTN_POLY = WXB_ATTN_POLY;
 constexpr float RESCALE_LOG2 = 8.f;           // move the softmax offset only when the row max grew by more than 2^8
 
 struct AttnTcParams {
@@ -115,7 +129,7 @@ __device__ __forceinline__ float exp_block64(const uint32_t* sv, int col0, int v
   for (int i = 0; i < 64; i += 2) {
     const uint64_t x2 = ffma2(pack2(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), sl2, noff2);
     float p0, p1;
-    if ((i >> 1) & 1) {
+    if (ATTN_POLY == 2 ? ((i >> 1) & 1) != 0 : ATTN_POLY == 1 ? ((i >> 1) & 3) == 3 : ATTN_POLY == 3 ? ((i >> 1) & 3) != 0 : false) {
       float x0, x1;
       unpack2(x2, x0, x1);
       const uint64_t xc = pack2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));

@@ -224,8 +224,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t acc_phase = 0;
     for (int tile = first; tile < num_tiles; tile += step) {
       const int m_blk = PAIR ? 2 * (tile % num_mp) + rank : tile % num_mp, n_blk = tile / num_mp;
-      mbar_wait(tfull_bar + acc, acc_phase);
-      tc_fence_after();
       const int r = m_blk * BM + ew * 32 + lane;  // GEMM row of this thread
       bool row_ok = r < p.M;
       long long out_row = r;
@@ -239,6 +237,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const float* res_row = nullptr;
       if (p.res_mode == 1) res_row = p.residual + out_row * p.ldr;
       else if (p.res_mode == 2) res_row = p.residual + (long long)t_in_group * p.ldr;
+      // the residual values this thread will add (CHUNKS x 128 B of its row) are requested into L2 now, while the tile's
+      // products are still being accumulated: the epilogue's loads then find them on chip instead of waiting on HBM (the
+      // out-projection, K = d, is otherwise paced by its residual read: 36 % tensor-pipe activity before)
+      if (res_row && row_ok) {
+        const float* pf = res_row + n_blk * BN + half * CHUNKS * 32;
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c)
+          if (n_blk * BN + (half * CHUNKS + c) * 32 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + c * 32));
+      }
+      mbar_wait(tfull_bar + acc, acc_phase);
+      tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN + half * CHUNKS * 32);
       uint32_t vn[32];
       tc_ld_32x32(taddr0, vn);
