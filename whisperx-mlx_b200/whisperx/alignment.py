@@ -234,32 +234,50 @@ def merge_words(segments, separator="|"):
 # ------------------------------------------------------------------------------------------------
 # align()
 # ------------------------------------------------------------------------------------------------
+_PUNKT = None  # (PunktParameters, PunktSentenceTokenizer) once imported, False if nltk is absent
+
+
 def _sentence_spans(text: str):
     """Punkt sentence spans with the reference's abbreviation list (alignment.py:190-194).  nltk is an
     optional dependency here: without it the whole text is one sentence (documented in DESIGN.md)."""
-    try:
-        from nltk.tokenize.punkt import PunktParameters, PunktSentenceTokenizer
-    except ImportError:
+    global _PUNKT
+    if _PUNKT is None:
+        try:
+            from nltk.tokenize.punkt import PunktParameters, PunktSentenceTokenizer
+            _PUNKT = (PunktParameters, PunktSentenceTokenizer)
+        except ImportError:
+            _PUNKT = False
+    if not _PUNKT:
         return [(0, len(text))]
-    params = PunktParameters()
+    params = _PUNKT[0]()
     params.abbrev_types = set(PUNKT_ABBREVIATIONS)
-    return list(PunktSentenceTokenizer(params).span_tokenize(text))
+    return list(_PUNKT[1](params).span_tokenize(text))
 
 
 def _prepare_segment(text: str, dictionary: dict, spaced: bool):
-    """Character cleaning of one transcript segment (alignment.py:151-201)."""
+    """Character cleaning of one transcript segment (alignment.py:151-201): leading / trailing whitespace is skipped, every
+    other character is lower-cased (spaces become "|" in spaced languages) and replaced by the wildcard "*" if the align
+    model's dictionary does not know it."""
     lead = len(text) - len(text.lstrip())
     trail = len(text) - len(text.rstrip())
     last_kept = len(text) - trail - 1
-    clean_char, clean_cdx = [], []
-    for cdx, ch in enumerate(text):
-        if cdx < lead or cdx > last_kept:
-            continue
-        c = ch.lower()
+    if text.isascii():
+        # lower() and the space replacement are 1:1 on ASCII: whole-string operations instead of a per-character loop
+        body = text[lead:last_kept + 1].lower()
         if spaced:
-            c = c.replace(" ", "|")
-        clean_char.append(c if c in dictionary else "*")
-        clean_cdx.append(cdx)
+            body = body.replace(" ", "|")
+        clean_char = [c if c in dictionary else "*" for c in body]
+        clean_cdx = list(range(lead, last_kept + 1))
+    else:
+        clean_char, clean_cdx = [], []
+        for cdx, ch in enumerate(text):
+            if cdx < lead or cdx > last_kept:
+                continue
+            c = ch.lower()
+            if spaced:
+                c = c.replace(" ", "|")
+            clean_char.append(c if c in dictionary else "*")
+            clean_cdx.append(cdx)
     words = text.split(" ") if spaced else text
     return {"clean_char": clean_char, "clean_cdx": clean_cdx, "clean_wdx": list(range(len(words))),
             "sentence_spans": _sentence_spans(text)}
