@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define WXB_ABI_VERSION 2
+#define WXB_ABI_VERSION 3
 
 typedef struct wxb_ctx wxb_ctx;
 
@@ -233,6 +233,36 @@ int wxb_w2v_frames(int n_samples);
 int wxb_w2v_emissions(wxb_ctx* ctx, const float* audio_dev, const int64_t* seg_off_host,
                       const int32_t* seg_len_host, int n_seg, float* emis_out_dev,
                       const int32_t* t_off_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Word timing from the decoder's cross-attention — replaces the numeric core of
+ *     mlx_whisper_optimized_final.py:37-125 (per-step collection of the cross-attention QK of every layer) and :128-253
+ *     extract_words_with_dtw (alignment-head mean, softmax(10 x), median filter 7 (median_filter_fix.py:6-22), per-token
+ *     normalisation, mlx_whisper.timing.dtw = OpenAI whisper/timing.py dtw_cpu + backtrace).  Word grouping stays on the host.
+ * ---------------------------------------------------------------------------------------- */
+/* Select the (layer, head) pairs (layer_head_host int32 [n_heads][2], model.alignment_heads) whose scaled cross-attention
+ * queries every later wxb_decode_greedy / wxb_decoder_logits call logs on the device (64 floats per head and position);
+ * n_heads = 0 switches the logging off.  At most 127 heads. */
+int wxb_decode_collect_heads(wxb_ctx* ctx, const int32_t* layer_head_host, int n_heads);
+
+/* Pre-softmax cross-attention scores of the LAST decode, averaged over the selected heads: for sequence b, rows
+ * s = 0 .. n_rows_host[b]-1 are the query positions pos0 + s (pos0 = prompt_len - 1: the forward that predicts sampled token s,
+ * mlx_whisper_optimized_final.py:160-176).  qk_out_dev f32 [sum n_rows, n_audio_ctx], sequences back to back.  Needs the
+ * cross-K cache of that decode to be still resident (call before the next decode). */
+int wxb_dtw_scores(wxb_ctx* ctx, int B, int pos0, const int32_t* n_rows_host, float* qk_out_dev, void* stream);
+
+/* rows x T scores -> the DTW cost matrix: cost = -normalise(medfilt(softmax(temperature x), width)) per row
+ * (mlx_whisper_optimized_final.py:182-199; the reference uses temperature 10, width 7).  T <= 1536, odd width <= 9. */
+int wxb_dtw_cost(wxb_ctx* ctx, const float* qk_dev, int64_t rows, int T, float temperature, int medfilt_width,
+                 float* cost_out_dev, void* stream);
+
+/* dtw(x) with x[i, j] = cost[row j of sequence b][frame i] for every sequence (n_rows_host[b] <= 448 token rows of T frames,
+ * back to back in cost_dev): path_frames_dev / path_tokens_dev int32 [B, wxb_dtw_path_capacity(T)] receive the path from
+ * (0, 0) to (T-1, n_rows-1) (row 0 / row 1 of the reference's result), path_len_dev int32 [B] its length (0 for n_rows = 0).
+ * Bit-exact against the CPU algorithm for a given cost matrix (same additions, same tie rules). */
+int wxb_dtw_path(wxb_ctx* ctx, const float* cost_dev, int B, const int32_t* n_rows_host, int T, int32_t* path_frames_dev,
+                 int32_t* path_tokens_dev, int32_t* path_len_dev, void* stream);
+int wxb_dtw_path_capacity(int T);
 
 /* Stand-alone bf16 GEMM used by the encoder (exposed for parity tests and roofline timing):
  * D[M,N] = A[M,K] * W[N,K]^T (+bias[N]) (GELU) ; A,W bf16 row-major, D bf16 or f32.

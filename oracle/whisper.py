@@ -93,10 +93,13 @@ class DecoderCache:
         self.pos = 0
 
 
-def decoder_forward(w, dims, tokens: torch.Tensor, cache: DecoderCache, positions=None) -> torch.Tensor:
+def decoder_forward(w, dims, tokens: torch.Tensor, cache: DecoderCache, positions=None, cross_qk=None) -> torch.Tensor:
     """tokens int64 [B, n] appended at positions cache.pos.. ; returns f32 logits [B, n, V]
     (tied output head, HF modeling_whisper.py:971).  `positions` (indices into the n new tokens) limits the vocabulary
-    projection to those positions: logits [B, len(positions), V]."""
+    projection to those positions: logits [B, len(positions), V].  `cross_qk` = dict(heads=[(layer, head), ...], out=[]):
+    the pre-softmax cross-attention scores q k^T / 8 of those heads are appended to out as [B, n_heads, n, 1500] (what the
+    reference collects per forward, /root/reference/mlx_whisper_optimized_final.py:74-96)."""
+    qk_here = {}
     B, n = tokens.shape
     pos0 = cache.pos
     x = w["decoder.token_embedding.weight"][tokens] + w["decoder.positional_embedding"][pos0:pos0 + n][None]
@@ -110,11 +113,21 @@ def decoder_forward(w, dims, tokens: torch.Tensor, cache: DecoderCache, position
                  causal_offset=pos0)
         x = x + _lin(a, w, p + ".attn.out")
         h = _ln(x, w[p + ".cross_attn_ln.weight"], w[p + ".cross_attn_ln.bias"])
+        if cross_qk is not None and any(l == i for l, _ in cross_qk["heads"]):
+            dh = x.shape[-1] // dims["n_text_head"]
+            qh = _lin(h, w, p + ".cross_attn.query").view(B, n, dims["n_text_head"], dh).transpose(1, 2)
+            kh = cache.cross_k[i].view(B, -1, dims["n_text_head"], dh).transpose(1, 2)
+            s_all = (qh @ kh.transpose(-1, -2)) * (dh ** -0.5)
+            for l, hd in cross_qk["heads"]:
+                if l == i:
+                    qk_here[(l, hd)] = s_all[:, hd]
         a = _mha(_lin(h, w, p + ".cross_attn.query"), cache.cross_k[i], cache.cross_v[i], dims["n_text_head"])
         x = x + _lin(a, w, p + ".cross_attn.out")
         h = _ln(x, w[p + ".mlp_ln.weight"], w[p + ".mlp_ln.bias"])
         x = x + _lin(F.gelu(_lin(h, w, p + ".mlp.0")), w, p + ".mlp.2")
     cache.pos += n
+    if cross_qk is not None:
+        cross_qk["out"].append(torch.stack([qk_here[(l, hd)] for l, hd in cross_qk["heads"]], 1))
     if positions is not None:
         x = x[:, list(positions)]
     x = _ln(x, w["decoder.ln.weight"], w["decoder.ln.bias"])

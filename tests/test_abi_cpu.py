@@ -24,7 +24,7 @@ def test_header_symbols_exported():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/wxb200.h but not exported"
     assert set(names) == set(_native.EXPORTED_SYMBOLS)
-    assert lib.wxb_abi_version() == 2
+    assert lib.wxb_abi_version() == 3
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful without a GPU")

@@ -53,6 +53,11 @@ struct wxb_ctx {
   const void* dec_layers_model = nullptr;      // the model whose DecLayerW table is resident in "dec.layers"
   wxb_dec_maps_key dec_maps_key;               // identity of the tensor-map table resident in "dec.maps"
   std::map<std::string, std::vector<unsigned char>> tmap_cache;  // encoded CUtensorMaps keyed by (base, shape, box)
+  // word timing from cross-attention (wxb_dtw.cu): (layer, head) pairs whose cross-attention queries the decode kernel logs
+  std::vector<int> align_heads;     // flattened pairs; empty = logging off
+  bool align_heads_dirty = false;   // the device tables "dec.qhead" / "dec.qheads" are stale
+  bool qlog_valid = false;          // "dec.qlog" holds the queries of the last decode (of qlog_B0 sequences, positions < qlog_pos)
+  int qlog_B0 = 0, qlog_pos = 0;
 };
 
 constexpr size_t WXB_MAX_DEC_TIMINGS = 4096;

@@ -202,6 +202,11 @@ struct MkParams {
   MkGemv g_qkv, g_dd, g_fc1, g_fc2, g_logits;
   SampleParams sp;
   float scale;
+  // cross-attention queries of the alignment heads, kept for the DTW word timing (wxb_dtw.cu): qlog f32 [B0][TX][qA][64]
+  // (scaled q of head qhead^-1(a) at every decoded position), qhead int8 [L * H] = index a of (layer, head) or -1
+  float* qlog;
+  const signed char* qhead;
+  int qA;
 };
 
 // mbarriers + ring cursors of the persistent kernel.  The barriers live in one shared array (fixed slots sized for
@@ -775,7 +780,7 @@ __device__ __forceinline__ uint32_t split_pack(float x, float y, int sel) {
 // partials of the cq GEMV) of the next items, every consumer warp sums them for itself, deposits its (m, l, O) state of
 // a finished item in a double-buffered shared-memory slot and moves straight on; consumer warp (item % 7) merges the
 // 7 states once all have arrived (mbarrier) and writes the output.
-__device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, int xq, const float* __restrict__ cq_b, uint8_t* ring,
+__device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, int xq, int pos, const float* __restrict__ cq_b, uint8_t* ring,
                                                  float* scratch, MkSync& sy) {
   constexpr uint32_t STAGE = 2 * XA_HALF;
   float* sst = scratch;                                                                          // [2 item parities][7 warps][66]: m, l, O[64]
@@ -877,6 +882,15 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, int x
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(sy.mb(MB_Q_FREE + ipar));
+      if (p.qlog != nullptr && cw == 0 && x.piece <= 0) {
+        // an alignment head: the scaled query of this position is what the word-timing DTW multiplies with the cross K later
+        const int a = p.qhead[l * H + h];
+        if (a >= 0) {
+          float* ql = p.qlog + (((size_t)s_rows[b] * p.TX + pos) * p.qA + a) * 64;
+          ql[lane] = qn0;
+          ql[lane + 32] = qn1;
+        }
+      }
       // B fragments of q: lane (g, t) holds elements 16 j + 2 t + {0, 1} and + {8, 9}; column g = 0 hi part, g = 1 lo part
       uint32_t qb[4][2];
 #pragma unroll
@@ -1341,7 +1355,7 @@ __device__ __forceinline__ void run_op(const MkParams& p, const DecLayerW* s_lay
   } else if (kind == PH_SELF) {
     if (!(stub & 4) && !WXB_SKIP(p.skip, 4)) self_attn_phase(p, l, w.qkv_b, pos, ring, scratch, sy);
   } else if (kind == PH_CROSS) {
-    if (!(stub & 1) && !WXB_SKIP(p.skip, 1)) cross_attn_phase(p, l, xq, w.cq_b, ring, scratch, sy);
+    if (!(stub & 1) && !WXB_SKIP(p.skip, 1)) cross_attn_phase(p, l, xq, pos, w.cq_b, ring, scratch, sy);
   } else {
     if (!(stub & 16)) sample_phase(p.sp, p.B, pos, p.mode == 2, red, red_i, sy);
   }
@@ -1453,6 +1467,9 @@ struct DecBuffers {
   float *x, *logits, *part, *apart, *sum_lp;
   __nv_bfloat16 *att, *xn, *hid, *self_kv, *cross_kv;
   int *ticket, *d_pos, *tokens, *done, *rows, *ts_last;
+  float* qlog;               // alignment-head query log (nullptr = off), see MkParams::qlog
+  const signed char* qhead;
+  int qA;
   unsigned* bar;
   const DecLayerW* layers;
   const CUtensorMap* maps;
@@ -1551,6 +1568,32 @@ int alloc_buffers(wxb_ctx* ctx, int B, int tok_stride, DecBuffers* o) {
     ctx->dec_layers_model = ctx->model;
   }
   o->layers = layers;
+  // alignment-head query log for the DTW word timing (wxb_decode_collect_heads)
+  o->qlog = nullptr; o->qhead = nullptr; o->qA = 0;
+  ctx->qlog_valid = false;
+  if (!ctx->align_heads.empty()) {
+    const int A = (int)ctx->align_heads.size() / 2;
+    signed char* qh = (signed char*)wxb_named(ctx, "dec.qhead", (size_t)MAX_LAYERS * 64);
+    int* qhs = (int*)wxb_named(ctx, "dec.qheads", (size_t)128 * 2 * 4);
+    o->qlog = (float*)wxb_named(ctx, "dec.qlog", (size_t)B * D.n_text_ctx * A * 64 * 4);
+    if (!qh || !qhs || !o->qlog) return WXB_ERR_CUDA;
+    if (H > 64) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: alignment-head logging takes at most 64 heads per layer");
+    if (ctx->align_heads_dirty) {
+      std::vector<signed char> h((size_t)MAX_LAYERS * 64, (signed char)-1);
+      for (int a = 0; a < A; ++a) {
+        const int l = ctx->align_heads[2 * a], hd = ctx->align_heads[2 * a + 1];
+        if (l < 0 || l >= L || hd < 0 || hd >= H)
+          return wxb_fail(ctx, WXB_ERR_INVALID, "alignment head (%d, %d) outside the decoder's %d layers x %d heads", l, hd, L, H);
+        h[(size_t)l * H + hd] = (signed char)a;
+      }
+      WXB_CUDA(ctx, cudaDeviceSynchronize());  // a previous decode may still be reading the old tables
+      WXB_CUDA(ctx, cudaMemcpy(qh, h.data(), h.size(), cudaMemcpyHostToDevice));
+      WXB_CUDA(ctx, cudaMemcpy(qhs, ctx->align_heads.data(), ctx->align_heads.size() * 4, cudaMemcpyHostToDevice));
+      ctx->align_heads_dirty = false;
+    }
+    o->qhead = qh; o->qA = A;
+    ctx->qlog_B0 = B; ctx->qlog_pos = 0;
+  }
   // tensor maps (128-byte swizzle, 64-element boxes): weights [N, K] in 128-row boxes, activations [B, K] in boxes of
   // 16 MT rows (one map per batch-tile count MT = 1 .. 4: a launch over fewer live rows uses the narrower box); rows >= B
   // are zero-filled by the TMA unit
@@ -1617,7 +1660,10 @@ int launch_steps(wxb_ctx* ctx, const DecBuffers& buf, int mode, int n_steps, con
   const wxb_dims& D = ctx->model->dims;
   const int d = D.n_text_state, B = n_live;
   const int Bp = (B + 15) & ~15, MT = Bp / 16;
-  const int G = ctx->sm_count;
+  int G = ctx->sm_count;
+#ifdef WXB_PROBE
+  if (const char* e = getenv("WXB_DEC_GRID")) { const int g = atoi(e); if (g > 0 && g < G) G = g; }  // timing probe: narrower grid
+#endif
   MkParams p = {};
   p.B = B; p.B0 = buf.B; p.rows = rows_dev;
   p.d = d; p.H = D.n_text_head; p.L = D.n_text_layer; p.V = D.n_vocab; p.TX = D.n_text_ctx;
@@ -1633,6 +1679,8 @@ int launch_steps(wxb_ctx* ctx, const DecBuffers& buf, int mode, int n_steps, con
   p.self_kv = buf.self_kv; p.cross_kv = buf.cross_kv;
   p.logits = logits_out; p.ldl = ldl;
   p.apart = buf.apart; p.ticket = buf.ticket; p.bar = buf.bar;
+  p.qlog = buf.qlog; p.qhead = buf.qhead; p.qA = buf.qA;
+  if (buf.qlog) { ctx->qlog_pos += n_steps; ctx->qlog_valid = true; }
   if (dec_prof_enabled()) {
     p.prof = (unsigned long long*)wxb_named(ctx, "dec.prof", PROF_SLOTS * 8);
     if ((size_t)n_steps * (11 * p.L + 4) > PROF_SLOTS) p.prof = nullptr;
@@ -1708,6 +1756,8 @@ int dump_prof(wxb_ctx* ctx) {
 void wxb_decoder_reset(wxb_ctx* ctx) {
   ctx->dec_layers_model = nullptr;
   ctx->dec_maps_key = wxb_dec_maps_key();
+  ctx->align_heads_dirty = !ctx->align_heads.empty();  // re-validated against the new model's layers x heads
+  ctx->qlog_valid = false;
 }
 
 extern "C" int wxb_decode_greedy(wxb_ctx* ctx, const void* enc_out_dev, int B, const int32_t* prompt_host, int prompt_len,

@@ -109,7 +109,17 @@ def load_library(path: Optional[str] = None):
         lib.wxb_gemm_bf16.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
         lib.wxb_encoder_attention.restype = i32
         lib.wxb_encoder_attention.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
-        if lib.wxb_abi_version() != 2:
+        lib.wxb_decode_collect_heads.restype = i32
+        lib.wxb_decode_collect_heads.argtypes = [vp, vp, i32]
+        lib.wxb_dtw_scores.restype = i32
+        lib.wxb_dtw_scores.argtypes = [vp, i32, i32, vp, vp, vp]
+        lib.wxb_dtw_cost.restype = i32
+        lib.wxb_dtw_cost.argtypes = [vp, vp, i64, i32, C.c_float, i32, vp, vp]
+        lib.wxb_dtw_path.restype = i32
+        lib.wxb_dtw_path.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, vp]
+        lib.wxb_dtw_path_capacity.restype = i32
+        lib.wxb_dtw_path_capacity.argtypes = [i32]
+        if lib.wxb_abi_version() != 3:
             raise WxbError("libwxb200.so ABI version mismatch")
         lib._wxb_path = os.path.abspath(p)
         if path is None:
@@ -121,7 +131,8 @@ EXPORTED_SYMBOLS = (
     "wxb_abi_version", "wxb_create", "wxb_destroy", "wxb_last_error", "wxb_launch_count", "wxb_logmel",
     "wxb_ctc_align", "wxb_log_softmax_rows", "wxb_set_model", "wxb_encode", "wxb_decode_greedy",
     "wxb_decoder_logits", "wxb_gemm_bf16", "wxb_decode_stats", "wxb_encoder_attention", "wxb_decoder_sample",
-    "wxb_logmel_features", "wxb_set_align_model", "wxb_w2v_frames", "wxb_w2v_emissions", "wxb_debug_set", "wxb_debug_copy")
+    "wxb_logmel_features", "wxb_set_align_model", "wxb_w2v_frames", "wxb_w2v_emissions", "wxb_debug_set", "wxb_debug_copy",
+    "wxb_decode_collect_heads", "wxb_dtw_scores", "wxb_dtw_cost", "wxb_dtw_path", "wxb_dtw_path_capacity")
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -374,6 +385,43 @@ class Context:
         out = torch.empty((B, n, dims["n_vocab"]), dtype=torch.float32, device=self.device)
         self._check(self.lib.wxb_decoder_logits(self.h, _ptr(enc_out), B, _np_ptr(tokens), n, _ptr(out), self._stream()))
         return out
+
+    # ---- word timing from cross-attention (wxb_dtw.cu) -----------------------------------------------------------------
+    def collect_alignment_heads(self, heads):
+        """(layer, head) pairs whose cross-attention queries later decodes log on the device; None / [] = off."""
+        h = np.ascontiguousarray(np.asarray(heads if heads is not None else [], dtype=np.int32).reshape(-1, 2))
+        self._check(self.lib.wxb_decode_collect_heads(self.h, _np_ptr(h) if len(h) else None, len(h)))
+
+    def dtw_scores(self, n_rows: np.ndarray, pos0: int, n_frames: int = 1500) -> torch.Tensor:
+        """Mean-over-alignment-heads pre-softmax cross-attention scores of the last decode: f32 [sum n_rows, n_frames]."""
+        n_rows = np.ascontiguousarray(n_rows, dtype=np.int32)
+        out = torch.empty((int(n_rows.sum()), n_frames), dtype=torch.float32, device=self.device)
+        self._check(self.lib.wxb_dtw_scores(self.h, len(n_rows), int(pos0), _np_ptr(n_rows), _ptr(out), self._stream()))
+        return out
+
+    def dtw_cost(self, qk: torch.Tensor, temperature: float = 10.0, medfilt_width: int = 7) -> torch.Tensor:
+        assert qk.dtype == torch.float32 and qk.is_contiguous() and qk.dim() == 2
+        out = torch.empty_like(qk)
+        self._check(self.lib.wxb_dtw_cost(self.h, _ptr(qk), qk.shape[0], qk.shape[1], float(temperature), int(medfilt_width),
+                                          _ptr(out), self._stream()))
+        return out
+
+    def dtw_path(self, cost: torch.Tensor, n_rows: np.ndarray):
+        """cost f32 [sum n_rows, T] (token rows of every sequence back to back) -> list of int32 arrays [2, P_b]
+        (row 0 frame indices, row 1 token indices: the reference's dtw(-w.T) result)."""
+        assert cost.dtype == torch.float32 and cost.is_contiguous() and cost.dim() == 2
+        n_rows = np.ascontiguousarray(n_rows, dtype=np.int32)
+        assert int(n_rows.sum()) == cost.shape[0]
+        B, T = len(n_rows), cost.shape[1]
+        cap = self.lib.wxb_dtw_path_capacity(T)
+        pf = torch.empty((B, cap), dtype=torch.int32, device=self.device)
+        pt = torch.empty((B, cap), dtype=torch.int32, device=self.device)
+        pl = torch.empty((B,), dtype=torch.int32, device=self.device)
+        self._check(self.lib.wxb_dtw_path(self.h, _ptr(cost), B, _np_ptr(n_rows), T, _ptr(pf), _ptr(pt), _ptr(pl), self._stream()))
+        pl_h = pl.cpu().numpy()
+        n_max = int(pl_h.max()) if B else 0
+        pf_h, pt_h = pf[:, :n_max].cpu().numpy(), pt[:, :n_max].cpu().numpy()
+        return [np.stack([pf_h[b, :pl_h[b]], pt_h[b, :pl_h[b]]]) for b in range(B)]
 
     def gemm_bf16(self, A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None, gelu: bool = False,
                   out_f32: bool = False) -> torch.Tensor:

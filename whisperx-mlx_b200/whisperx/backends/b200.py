@@ -42,9 +42,9 @@ class B200WhisperBackend(WhisperBackend):
         self.language = language
         self.task = task or "transcribe"
         self.options = dict(suppress_blank=True, suppress_tokens=[], sample_len=self.dims["n_text_ctx"] // 2,
-                            without_timestamps=True)
+                            without_timestamps=True, dtw_word_timestamps=False, alignment_heads=None)
         if asr_options:
-            for k in ("suppress_blank", "suppress_tokens", "sample_len", "without_timestamps"):
+            for k in ("suppress_blank", "suppress_tokens", "sample_len", "without_timestamps", "dtw_word_timestamps", "alignment_heads"):
                 if k in asr_options and asr_options[k] is not None:
                     self.options[k] = asr_options[k]
         if list(self.options["suppress_tokens"]) == [-1]:
@@ -147,11 +147,19 @@ class B200WhisperBackend(WhisperBackend):
         total = (addr - start) // 4
         return np.lib.stride_tricks.as_strided(first, shape=(total,), strides=(4,))  # read below, never written
 
+    def _alignment_heads(self):
+        from ..word_timing import alignment_heads
+        return self.options["alignment_heads"] or alignment_heads(self.model_name, self.dims["n_text_layer"], self.dims["n_text_head"])
+
     def transcribe_device(self, audio_dev: torch.Tensor, offs: np.ndarray, lens: np.ndarray, batch_size: int,
-                          language: str, task: str):
+                          language: str, task: str, dtw_words: bool = False, chunk_starts=None):
         """mel -> encode -> greedy decode for chunks already resident in HBM.  Returns device tensors
-        (tokens [n, sample_len], n_tokens, sum_logprob, no_speech_prob)."""
+        (tokens [n, sample_len], n_tokens, sum_logprob, no_speech_prob).  With dtw_words the decode kernel logs the
+        alignment heads' cross-attention queries and every batch is followed by the DTW word timing (word_timing.py) while
+        its cross-K cache is still resident: the result gains "words" (one list per chunk, times offset by chunk_starts)."""
         self._bind()
+        self.ctx.collect_alignment_heads(self._alignment_heads() if dtw_words else None)
+        words: List[list] = []
         without_ts = self.options["without_timestamps"]
         prompt = self.tokenizer.prompt(language, task, without_ts)
         n = len(offs)
@@ -173,12 +181,25 @@ class B200WhisperBackend(WhisperBackend):
                                            no_timestamps=self.specials["no_timestamps"], max_initial_timestamp_index=50))
             for k in out:
                 out[k].append(r[k])
-        return {k: torch.cat(v, 0) for k, v in out.items()}
+            if dtw_words:
+                from ..word_timing import dtw_word_timestamps
+                toks, n_tok = r["tokens"].cpu().numpy(), r["n_tokens"].cpu().numpy()
+                words += dtw_word_timestamps(self.ctx, [toks[k, : n_tok[k]] for k in range(j - i)], self.specials["eot"], len(prompt),
+                                             lambda t: self.tokenizer.decode_piece(t),
+                                             offsets=None if chunk_starts is None else chunk_starts[i:j])
+        res = {k: torch.cat(v, 0) for k, v in out.items()}
+        if dtw_words:
+            res["words"] = words
+        return res
 
     # ------------------------------------------------------------------ public API
     def transcribe_batch(self, segments: List[Dict[str, Any]], batch_size: int = 8, align_words: bool = False,
                          print_progress: bool = False, combined_progress: bool = False, verbose: bool = False,
-                         language: Optional[str] = None, task: Optional[str] = None, **kwargs) -> Dict[str, Any]:
+                         language: Optional[str] = None, task: Optional[str] = None, dtw_words: Optional[bool] = None,
+                         **kwargs) -> Dict[str, Any]:
+        """`dtw_words` (default: asr_options["dtw_word_timestamps"]) adds "words" to every segment from the decoder's own
+        cross-attention (the reference's single-stage word timing, mlx_whisper_optimized_final.py) — no alignment model."""
+        dtw_words = bool(self.options["dtw_word_timestamps"] if dtw_words is None else dtw_words)
         segs = [s for s in segments if s.get("audio") is not None and len(s["audio"]) > 0]
         language = language or self.language
         if language is None:
@@ -187,7 +208,8 @@ class B200WhisperBackend(WhisperBackend):
         result_segments: List[Dict[str, Any]] = []
         if segs:
             audio_dev, offs, lens = self.upload_chunks([s["audio"] for s in segs])
-            r = self.transcribe_device(audio_dev, offs, lens, max(1, int(batch_size or 8)), language, task)
+            r = self.transcribe_device(audio_dev, offs, lens, max(1, int(batch_size or 8)), language, task, dtw_words=dtw_words,
+                                       chunk_starts=[float(s["start"]) for s in segs])
             tokens = r["tokens"].cpu().numpy()          # D2H of the step's result
             n_tok = r["n_tokens"].cpu().numpy()
             sum_lp = r["sum_logprob"].cpu().numpy()
@@ -202,6 +224,8 @@ class B200WhisperBackend(WhisperBackend):
                     continue
                 item = {"text": text, "start": round(float(seg["start"]), 3), "end": round(float(seg["end"]), 3),
                         "tokens": ids, "avg_logprob": float(sum_lp[k]) / (len(ids) + 1), "no_speech_prob": float(nsp[k])}
+                if dtw_words:
+                    item["words"] = r["words"][k]
                 if verbose:
                     print(f"[{item['start']:.3f} --> {item['end']:.3f}] {text}")
                 result_segments.append(item)

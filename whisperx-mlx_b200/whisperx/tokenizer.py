@@ -52,6 +52,13 @@ class Tokenizer:
             p.append(self.no_timestamps)
         return p
 
+    def decode_piece(self, token: int) -> str:
+        """Text of ONE token as it appears inside running text (a leading space marks a word start): what the DTW word
+        grouping looks at (mlx_whisper_optimized_final.py:205,213).  Every synthetic pseudo-word is a word of its own."""
+        if self._decode_fn is not None:
+            return self._decode_fn([int(token)])
+        return " " + _pseudo_word(int(token)) if 0 <= int(token) < self.eot else ""
+
     def decode(self, tokens: Iterable[int]) -> str:
         toks = [int(t) for t in tokens if 0 <= int(t) < self.eot]
         if self._decode_fn is not None:
