@@ -264,6 +264,42 @@ int wxb_dtw_path(wxb_ctx* ctx, const float* cost_dev, int B, const int32_t* n_ro
                  int32_t* path_tokens_dev, int32_t* path_len_dev, void* stream);
 int wxb_dtw_path_capacity(int T);
 
+/* ------------------------------------------------------------------------------------------
+ * VAD post-processing and chunking — replaces whisperx/vads/pyannote.py:134-216 Binarize.__call__ (hysteresis
+ *     thresholding of frame scores + the WhisperX min-cut at max_duration = chunk_size), :282-301 Pyannote.merge_chunks,
+ *     whisperx/vads/vad.py:20-53 Vad.merge_chunks and the chunk slicing of whisperx/asr.py:70-73, for frame scores that are
+ *     already in HBM.  Region / chunk boundaries are IEEE doubles bit-identical to the reference's Python floats.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  double frame_duration; /* pyannote SlidingWindow of the score track: frame i = [start + i step, + duration), time = its middle */
+  double frame_step;
+  double frame_start;
+  double chunk_size;     /* seconds: max_duration of the min-cut and the merge limit */
+  float onset;           /* a region opens when score > onset (0 < onset < 1) */
+  float offset;          /* ... and closes when score < offset; <= 0 = use onset (`offset or onset`) */
+} wxb_vad_params;
+
+/* scores_dev f32: the score tracks of n_rec recordings back to back, recording r = [score_off_host[r], score_off_host[r+1]);
+ * n_samples_host int64[n_rec] = samples of each recording (chunk slices are clipped to it like a Python slice).
+ * Outputs (device), per recording r:
+ *   regions_dev f64 [n_rec, max_regions, 2]   speech regions (start, end) in timeline order, n_regions_dev int32[n_rec]
+ *   chunks_dev  f64 [n_rec, max_chunks, 2]    merged chunks (start, end),                     n_chunks_dev  int32[n_rec]
+ *   chunk_first_dev int32 [n_rec, max_chunks + 1]  chunk k holds regions chunk_first[k] .. chunk_first[k+1]-1 ("segments")
+ *   chunk_off_dev int64 / chunk_len_dev int32 [n_rec, max_chunks]  int(start * 16000) and the slice length, clipped to the
+ *                 recording and to 480000 samples: the table wxb_logmel / wxb_logmel_features take
+ * A count larger than its capacity means the arrays were truncated (call again with larger capacities). */
+int wxb_vad_chunks(wxb_ctx* ctx, const float* scores_dev, const int64_t* score_off_host, const int64_t* n_samples_host,
+                   int n_rec, const wxb_vad_params* prm, int max_regions, int max_chunks, double* regions_dev,
+                   int32_t* n_regions_dev, double* chunks_dev, int32_t* chunk_first_dev, int32_t* n_chunks_dev,
+                   int64_t* chunk_off_dev, int32_t* chunk_len_dev, void* stream);
+
+/* Stand-in frame scorer (NOT in the reference: Silero comes from torch.hub and the pyannote checkpoint is not in the tree, so no
+ * VAD model exists offline): score[i] = sigmoid((10 log10(mean x^2 over samples [160 i, 160 i + 400)) + 1e-10) - floor_db) /
+ * width_db), wxb_vad_energy_frames(n_samples) = ceil(n_samples / 160) scores; frame clock duration 0.025, step 0.010, start 0. */
+int wxb_vad_energy_scores(wxb_ctx* ctx, const float* audio_dev, int64_t n_samples, float floor_db, float width_db,
+                          float* scores_out_dev, void* stream);
+int64_t wxb_vad_energy_frames(int64_t n_samples);
+
 /* Stand-alone bf16 GEMM used by the encoder (exposed for parity tests and roofline timing):
  * D[M,N] = A[M,K] * W[N,K]^T (+bias[N]) (GELU) ; A,W bf16 row-major, D bf16 or f32.
  * flags: bit0 = GELU, bit1 = output f32. */

@@ -41,6 +41,11 @@ class W2vDims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("conv_dim", "embed_dim", "n_heads", "n_layers", "ff_dim", "pos_kernel", "pos_groups", "n_out")]
 
 
+class VadParams(C.Structure):
+    _fields_ = [("frame_duration", C.c_double), ("frame_step", C.c_double), ("frame_start", C.c_double), ("chunk_size", C.c_double),
+                ("onset", C.c_float), ("offset", C.c_float)]
+
+
 class DecodeOpts(C.Structure):
     _fields_ = [("eot", C.c_int32), ("no_speech", C.c_int32), ("sample_len", C.c_int32),
                 ("suppress_blank", C.c_int32), ("blank_token", C.c_int32), ("n_suppress", C.c_int32),
@@ -119,6 +124,12 @@ def load_library(path: Optional[str] = None):
         lib.wxb_dtw_path.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, vp]
         lib.wxb_dtw_path_capacity.restype = i32
         lib.wxb_dtw_path_capacity.argtypes = [i32]
+        lib.wxb_vad_chunks.restype = i32
+        lib.wxb_vad_chunks.argtypes = [vp, vp, vp, vp, i32, C.POINTER(VadParams), i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+        lib.wxb_vad_energy_scores.restype = i32
+        lib.wxb_vad_energy_scores.argtypes = [vp, vp, i64, C.c_float, C.c_float, vp, vp]
+        lib.wxb_vad_energy_frames.restype = i64
+        lib.wxb_vad_energy_frames.argtypes = [i64]
         if lib.wxb_abi_version() != 3:
             raise WxbError("libwxb200.so ABI version mismatch")
         lib._wxb_path = os.path.abspath(p)
@@ -132,7 +143,7 @@ EXPORTED_SYMBOLS = (
     "wxb_ctc_align", "wxb_log_softmax_rows", "wxb_set_model", "wxb_encode", "wxb_decode_greedy",
     "wxb_decoder_logits", "wxb_gemm_bf16", "wxb_decode_stats", "wxb_encoder_attention", "wxb_decoder_sample",
     "wxb_logmel_features", "wxb_set_align_model", "wxb_w2v_frames", "wxb_w2v_emissions", "wxb_debug_set", "wxb_debug_copy",
-    "wxb_decode_collect_heads", "wxb_dtw_scores", "wxb_dtw_cost", "wxb_dtw_path", "wxb_dtw_path_capacity")
+    "wxb_vad_chunks", "wxb_vad_energy_scores", "wxb_vad_energy_frames", "wxb_decode_collect_heads", "wxb_dtw_scores", "wxb_dtw_cost", "wxb_dtw_path", "wxb_dtw_path_capacity")
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -422,6 +433,56 @@ class Context:
         n_max = int(pl_h.max()) if B else 0
         pf_h, pt_h = pf[:, :n_max].cpu().numpy(), pt[:, :n_max].cpu().numpy()
         return [np.stack([pf_h[b, :pl_h[b]], pt_h[b, :pl_h[b]]]) for b in range(B)]
+
+    # ---- VAD post-processing and chunking (wxb_vad.cu) ------------------------------------------------------------------
+    def vad_energy_scores(self, audio_dev: torch.Tensor, floor_db: float = -50.0, width_db: float = 6.0) -> torch.Tensor:
+        assert audio_dev.is_cuda and audio_dev.dtype == torch.float32 and audio_dev.is_contiguous() and audio_dev.dim() == 1
+        out = torch.empty((int(self.lib.wxb_vad_energy_frames(audio_dev.numel())),), dtype=torch.float32, device=self.device)
+        self._check(self.lib.wxb_vad_energy_scores(self.h, _ptr(audio_dev), audio_dev.numel(), float(floor_db), float(width_db),
+                                                   _ptr(out), self._stream()))
+        return out
+
+    def vad_chunks(self, scores_dev: torch.Tensor, score_off: np.ndarray, n_samples: np.ndarray, chunk_size: float, onset: float = 0.5,
+                   offset: Optional[float] = None, frame_duration: float = 0.0619375, frame_step: float = 0.016875,
+                   frame_start: float = 0.0, max_regions: int = 0, max_chunks: int = 0):
+        """Binarize + merge_chunks for the score tracks of len(score_off) - 1 recordings.  Returns per recording
+        dict(regions f64 [n, 2], chunks f64 [m, 2], chunk_first int32 [m + 1], chunk_off int64 [m], chunk_len int32 [m]) with the
+        chunk_off / chunk_len tables also left on the device under "chunk_off_dev" / "chunk_len_dev"."""
+        assert scores_dev.is_cuda and scores_dev.dtype == torch.float32 and scores_dev.is_contiguous()
+        off = np.ascontiguousarray(score_off, dtype=np.int64)
+        ns = np.ascontiguousarray(n_samples, dtype=np.int64)
+        n_rec = len(off) - 1
+        longest = int(np.diff(off).max()) if n_rec else 0
+        prm = VadParams(float(frame_duration), float(frame_step), float(frame_start), float(chunk_size), float(onset),
+                        float(offset) if offset else 0.0)
+        max_regions = int(max_regions) or max(16, longest // 2 + 2)  # a region needs at least two frames
+        max_chunks = int(max_chunks) or max_regions
+        dev = self.device
+        regions = torch.empty((n_rec, max_regions, 2), dtype=torch.float64, device=dev)
+        chunks = torch.empty((n_rec, max_chunks, 2), dtype=torch.float64, device=dev)
+        first = torch.empty((n_rec, max_chunks + 1), dtype=torch.int32, device=dev)
+        n_reg = torch.empty((n_rec,), dtype=torch.int32, device=dev)
+        n_ch = torch.empty((n_rec,), dtype=torch.int32, device=dev)
+        c_off = torch.empty((n_rec, max_chunks), dtype=torch.int64, device=dev)
+        c_len = torch.empty((n_rec, max_chunks), dtype=torch.int32, device=dev)
+        self._check(self.lib.wxb_vad_chunks(self.h, _ptr(scores_dev), _np_ptr(off), _np_ptr(ns), n_rec, C.byref(prm), max_regions,
+                                            max_chunks, _ptr(regions), _ptr(n_reg), _ptr(chunks), _ptr(first), _ptr(n_ch),
+                                            _ptr(c_off), _ptr(c_len), self._stream()))
+        n_reg_h, n_ch_h = n_reg.cpu().numpy(), n_ch.cpu().numpy()
+        if (n_reg_h > max_regions).any() or (n_ch_h > max_chunks).any():
+            raise WxbError(f"vad_chunks: {int(n_reg_h.max())} regions / {int(n_ch_h.max())} chunks exceed the capacities "
+                           f"({max_regions}, {max_chunks})")
+        mr, mc = int(n_reg_h.max()) if n_rec else 0, int(n_ch_h.max()) if n_rec else 0
+        regions_h, chunks_h = regions[:, :mr].cpu().numpy(), chunks[:, :mc].cpu().numpy()
+        first_h, off_h, len_h = first[:, :mc + 1].cpu().numpy(), c_off[:, :mc].cpu().numpy(), c_len[:, :mc].cpu().numpy()
+        out = []
+        for r in range(n_rec):
+            m = int(n_ch_h[r])
+            fr = first_h[r, :m + 1].copy()
+            fr[m] = n_reg_h[r]
+            out.append(dict(regions=regions_h[r, :n_reg_h[r]], chunks=chunks_h[r, :m], chunk_first=fr, chunk_off=off_h[r, :m],
+                            chunk_len=len_h[r, :m], chunk_off_dev=c_off[r, :m], chunk_len_dev=c_len[r, :m]))
+        return out
 
     def gemm_bf16(self, A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None, gelu: bool = False,
                   out_f32: bool = False) -> torch.Tensor:

@@ -59,9 +59,10 @@ def load_model(whisper_arch: str, device: str = "cuda", device_index: int = 0, c
     """whisperx.load_model(name, backend="b200").  `backend` accepts "auto" | "b200" | "cuda_b200";
     the reference's MLX backend names are rejected (this package ships the CUDA backend only).
 
-    VAD is upstream of the hot path and not part of this build: `vad_method` is "uniform" (fixed
-    chunk_size cuts, the benchmark's synthetic VAD), None / "none" (no cutting), or pass a ready
-    `vad_model` object (callable returning speech regions, with the reference's merge_chunks)."""
+    `vad_method`: "uniform" (fixed chunk_size cuts, the benchmark's synthetic VAD), "energy" (log-energy frame scores +
+    Binarize + merge_chunks on the GPU, vads/gpu.py), None / "none" (no cutting), or pass a ready `vad_model` object
+    (callable returning speech regions or device frame scores, with the reference's merge_chunks; vads.GpuVad wraps any
+    frame scorer).  The reference's Silero / pyannote checkpoints need network access and are not bundled."""
     if backend not in ("auto", "b200", "cuda_b200"):
         raise ValueError(f"backend '{backend}' is not available in the B200 build (use backend='b200')")
     from .backends.b200 import B200WhisperBackend
@@ -76,6 +77,12 @@ def load_model(whisper_arch: str, device: str = "cuda", device_index: int = 0, c
             vad_model = None
         elif vad_method == "uniform":
             vad_model = "uniform"
+        elif vad_method == "energy":
+            # frame scores, Binarize (hysteresis + min-cut) and merge_chunks on the GPU (vads/gpu.py); the scorer is a log-energy
+            # stand-in for the reference's Silero / pyannote models, whose checkpoints need network access
+            from .vads.gpu import EnergyVad
+            vad_model = EnergyVad(vad_onset=opts["vad_onset"], vad_offset=opts["vad_offset"], chunk_size=opts["chunk_size"],
+                                  device_index=device_index)
         else:
             raise RuntimeError(f"vad_method='{vad_method}' needs a VAD model that is outside this build's hot-path scope; "
                                "pass vad_model=<object> or use vad_method='uniform' / None")
