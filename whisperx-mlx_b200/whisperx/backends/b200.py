@@ -47,14 +47,27 @@ class B200WhisperBackend(WhisperBackend):
             for k in ("suppress_blank", "suppress_tokens", "sample_len", "without_timestamps", "dtw_word_timestamps", "alignment_heads"):
                 if k in asr_options and asr_options[k] is not None:
                     self.options[k] = asr_options[k]
-        if list(self.options["suppress_tokens"]) == [-1]:
-            # "-1" = the tokenizer's non-speech symbol set (the reference's default): it is a property of a real vocabulary file
-            warnings.warn("suppress_tokens=[-1] (the tokenizer's non-speech set) needs a real vocabulary; no token is suppressed "
-                          "- pass explicit ids to suppress")
-            self.options["suppress_tokens"] = []
         self.options["without_timestamps"] = bool(self.options["without_timestamps"])
         self.specials = bw.special_tokens(self.dims)
-        self.tokenizer = tokenizer or Tokenizer(self.specials, self.dims["n_vocab"])
+        vocab = kwargs.get("vocab")  # path of multilingual.tiktoken / vocab.json
+        self.tokenizer = tokenizer or (Tokenizer.from_file(vocab, self.specials, self.dims["n_vocab"]) if vocab
+                                       else Tokenizer(self.specials, self.dims["n_vocab"]))
+        if -1 in list(self.options["suppress_tokens"]):
+            # "-1" = the tokenizer's non-speech symbol set + the special tokens that must never be sampled (the reference's default)
+            rest = [t for t in self.options["suppress_tokens"] if t >= 0]
+            if self.tokenizer.ranks is not None:
+                sp = self.specials
+                # OpenAI decoding.py _get_suppress_tokens: + transcribe, translate, sot, startoflm, startofprev, nospeech
+                extra = [sp["transcribe"], sp["translate"], sp["sot"], sp["transcribe"] + 1, sp["transcribe"] + 2, sp["no_speech"]]
+                self.options["suppress_tokens"] = sorted(set(rest) | set(self.tokenizer.non_speech_tokens()) | set(extra))
+            else:
+                warnings.warn("suppress_tokens=[-1] (the tokenizer's non-speech set) needs a real vocabulary (vocab=<multilingual.tiktoken | "
+                              "vocab.json>); no symbol token is suppressed")
+                self.options["suppress_tokens"] = rest
+        if self.tokenizer.ranks is not None:
+            self.specials["blank"] = self.tokenizer.encode(" ")[0]  # SuppressBlank: encode(" ")
+        if weights is None and download_root and os.path.isdir(os.path.join(download_root, model)):
+            weights = os.path.join(download_root, model)  # a local copy of the checkpoint, as `download_root` holds in the reference
         self.kernel_weights = self._load_weights(weights, seed)
         bw.validate_kernel_weights(self.kernel_weights, self.dims)
         self._bind()
@@ -68,11 +81,15 @@ class B200WhisperBackend(WhisperBackend):
             warnings.warn(f"no checkpoint given for '{self.model_name}': using seeded random-init weights "
                           "(pass weights=<state dict or path> for a trained model)")
             return bw.random_kernel_weights_on_device(self.dims, self.device, seed=seed)
-        if isinstance(weights, str):
-            sd = torch.load(weights, map_location="cpu")
-            weights = sd.get("model_state_dict", sd)
+        if isinstance(weights, (str, os.PathLike)):
+            weights = bw.load_checkpoint(os.fspath(weights))  # HF safetensors dir / file, OpenAI .pt, mlx-community weights.npz
         if any(k.startswith("model.encoder.") for k in weights):
             weights = bw.from_hf_state_dict(weights)
+        if "encoder.conv1.weight" in weights:
+            got = bw.infer_dims(weights)
+            if got != self.dims:
+                diff = {k: (got[k], self.dims[k]) for k in got if got[k] != self.dims[k]}
+                raise ValueError(f"checkpoint does not match the '{self.model_name}' architecture: (checkpoint, expected) = {diff}")
         if "enc.conv1.w" in weights:  # already in kernel layout: cast to the dtypes the kernels read
             exp = bw.expected_kernel_tensors(self.dims)
             return {k: v.to(device=self.device, dtype=exp[k][1] if k in exp else v.dtype).contiguous() for k, v in weights.items()}

@@ -129,6 +129,71 @@ def from_hf_state_dict(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     return out
 
 
+def infer_dims(w: Dict[str, torch.Tensor]) -> Dict[str, int]:
+    """ModelDimensions from the shapes of an OpenAI-named state dict (what a checkpoint's config would say)."""
+    def n_blocks(prefix):
+        return 1 + max(int(k.split(".")[2]) for k in w if k.startswith(prefix + ".blocks."))
+    n_mels = int(w["encoder.conv1.weight"].shape[1])
+    ad = int(w["encoder.conv1.weight"].shape[0])
+    n_vocab, td = (int(v) for v in w["decoder.token_embedding.weight"].shape)
+    return dict(n_mels=n_mels, n_audio_ctx=int(w["encoder.positional_embedding"].shape[0]), n_audio_state=ad, n_audio_head=ad // 64,
+                n_audio_layer=n_blocks("encoder"), n_vocab=n_vocab, n_text_ctx=int(w["decoder.positional_embedding"].shape[0]),
+                n_text_state=td, n_text_head=td // 64, n_text_layer=n_blocks("decoder"))
+
+
+def _from_mlx_npz(path: str) -> Dict[str, torch.Tensor]:
+    """mlx-community `weights.npz` (what the reference's backends load, mlx_lightning.py:73): OpenAI names, fp16, Conv1d kernels
+    stored [out, k, in] (MLX layout) instead of [out, in, k]."""
+    import numpy as np
+    out = {}
+    with np.load(path) as z:
+        for k in z.files:
+            t = torch.from_numpy(np.asarray(z[k]).astype(np.float32))
+            if k in ("encoder.conv1.weight", "encoder.conv2.weight") and t.shape[1] == 3:
+                t = t.permute(0, 2, 1).contiguous()
+            out[k] = t
+    return out
+
+
+def load_checkpoint(path: str) -> Dict[str, torch.Tensor]:
+    """A checkpoint on disk -> OpenAI-named fp32 state dict.  Accepted: a Hugging Face directory (model.safetensors, sharded
+    model.safetensors.index.json, or pytorch_model.bin), a single .safetensors file, an OpenAI .pt ({"dims", "model_state_dict"}),
+    an mlx-community directory / weights.npz, or a torch file holding a plain state dict."""
+    import json
+    import os
+    if os.path.isdir(path):
+        for name in ("model.safetensors", "model.safetensors.index.json", "weights.safetensors", "weights.npz", "pytorch_model.bin"):
+            f = os.path.join(path, name)
+            if os.path.exists(f):
+                return load_checkpoint(f)
+        raise FileNotFoundError(f"no model.safetensors / weights.npz / pytorch_model.bin under {path}")
+    if not os.path.exists(path):
+        raise FileNotFoundError(path)
+    if path.endswith(".index.json"):
+        from safetensors.torch import load_file
+        with open(path) as fh:
+            shards = sorted(set(json.load(fh)["weight_map"].values()))
+        sd = {}
+        for shard in shards:
+            sd.update(load_file(os.path.join(os.path.dirname(path), shard)))
+    elif path.endswith(".safetensors"):
+        from safetensors.torch import load_file
+        sd = load_file(path)
+    elif path.endswith(".npz"):
+        sd = _from_mlx_npz(path)
+    else:
+        sd = torch.load(path, map_location="cpu", weights_only=True)
+        sd = sd.get("model_state_dict", sd)
+    if any(k.startswith("model.encoder.") for k in sd):
+        return from_hf_state_dict(sd)
+    if "encoder.conv1.weight" not in sd or "decoder.token_embedding.weight" not in sd:
+        raise ValueError(f"{path}: not a Whisper checkpoint (neither transformers nor OpenAI / MLX parameter names)")
+    sd = {k: v.detach().float() for k, v in sd.items()}
+    if "encoder.positional_embedding" not in sd:  # HF / MLX exports may leave the fixed sinusoid table out
+        sd["encoder.positional_embedding"] = _sinusoids(1500, int(sd["encoder.conv1.weight"].shape[0]))
+    return sd
+
+
 def round_to_bf16(w: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
     """What the kernels see, as fp32: every >=2-D matrix rounded to bf16 (biases / LN / positions of
     the ENCODER stay fp32; the decoder's positional table is bf16 like its embedding)."""
