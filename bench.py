@@ -292,6 +292,68 @@ def timed(job, dist, world, steps, warmup, flush, sampler=None):
                 dec_ms=steps_ms / steps, n_dec=n_dec / steps, stage_ms=stage_ms, clocks=clock_info)
 
 
+def side_paths(job, audio, flush, steps):
+    """Device time of the two side paths of SURVEY 8(f) on the headline job, CUDA events on the launching stream:
+    dtw_words  the decode with the alignment heads' queries logged, then scores + cost rows + DTW paths for every sequence
+               (224 token rows x 1500 frames each), and the host grouping of the words;
+    vad        log-energy frame scores of the 30-minute recording + Binarize / merge_chunks in one kernel."""
+    from whisperx.word_timing import dtw_word_timestamps
+    ctx, be = job.ctx, job.be
+
+    def ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    n = min(job.n_mine, job.batch_size)
+    heads = be._alignment_heads()
+    ctx.logmel_features(job.audio_dev, job.offs[:n], job.lens[:n], job.dims["n_mels"], be._filters)
+    enc = ctx.encode(None, n_chunks=n)
+    dec_ms, dtw_ms, host_ms, n_words = [], [], [], 0
+    for it in range(steps + 1):
+        flush.zero_()
+        ctx.collect_alignment_heads(heads)
+        e0 = ev()
+        r = ctx.decode_greedy(enc, job.prompt, be.specials["eot"], no_speech=be.specials["no_speech"], sample_len=job.sample_len,
+                              suppress_blank=True, blank_token=be.specials["blank"])
+        e1 = ev()
+        n_rows = np.full(n, job.sample_len, dtype=np.int32)
+        qk = ctx.dtw_scores(n_rows, len(job.prompt) - 1)
+        cost = ctx.dtw_cost(qk)
+        e2 = ev()
+        paths = ctx.dtw_path(cost, n_rows)   # includes the D2H of the paths
+        e3 = ev()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        toks = r["tokens"].cpu().numpy()
+        words = dtw_word_timestamps(ctx, [toks[k] for k in range(n)], be.specials["eot"], len(job.prompt), be.tokenizer.decode_piece)
+        t1 = time.perf_counter()
+        if it:  # first pass = warm-up
+            dec_ms.append(e0.elapsed_time(e1)); dtw_ms.append(e1.elapsed_time(e3)); host_ms.append((t1 - t0) * 1e3)
+            n_words = sum(len(w) for w in words)
+    ctx.collect_alignment_heads(None)
+    dtw = {"config": f"{n} sequences x {job.sample_len} token rows x 1500 frames, {len(heads)} alignment heads ({be.model_name})",
+           "decode_with_query_log_ms": float(np.mean(dec_ms)), "scores_cost_path_ms": float(np.mean(dtw_ms)),
+           "through_host_api_ms": float(np.mean(host_ms)), "words": n_words,
+           "note": "through_host_api_ms = word_timing.dtw_word_timestamps (3 launches + path D2H + word grouping on the host)"}
+    wav = torch.from_numpy(audio).to(ctx.device)
+    vad_ms = []
+    for it in range(steps + 1):
+        flush.zero_()
+        e0 = ev()
+        sc = ctx.vad_energy_scores(wav)
+        (res,) = ctx.vad_chunks(sc, np.array([0, sc.numel()]), np.array([wav.numel()]), 30.0, onset=0.5, offset=0.363,
+                                frame_duration=0.025, frame_step=0.010)
+        e1 = ev()
+        torch.cuda.synchronize()
+        if it:
+            vad_ms.append(e0.elapsed_time(e1))
+    vad = {"config": f"{len(audio) / SR / 60:g} min recording: log-energy frame scores ({sc.numel()} frames) + Binarize / merge_chunks kernel",
+           "ms": float(np.mean(vad_ms)), "chunks": int(len(res["chunks"])), "regions": int(len(res["regions"])),
+           "GB/s_audio_read": wav.numel() * 4 / (float(np.mean(vad_ms)) * 1e-3) / 1e9}
+    return dtw, vad
+
+
 def decode_roofline(job, r, P, n_rows):
     """Algorithmic bytes of the decode steps this rank ran / their device time."""
     prompt_len = len(job.prompt)
@@ -433,6 +495,8 @@ def main():
                                 "encoder_ms": r8["stage_ms"]["encoder"],
                                 "encoder_TFLOP/s": flops_encoder(dims) * 8 / (r8["stage_ms"]["encoder"] * 1e-3) / 1e12}
             del b8
+            # SURVEY 8 f-2 / f-3 on the headline job (N = 1): word timing from the decoder's cross-attention, VAD chunking
+            extras["dtw_words"], extras["vad"] = side_paths(job, audio, flush, args.steps)
         # BASELINE config 4: large-v3-turbo, the same 30-minute job sharded over the ranks
         tj = Job(args, "large-v3-turbo", local, rank, world, audio, segments, True, args.batch_size, None)
         tr = timed(tj, dist, world, args.steps, 2, flush)

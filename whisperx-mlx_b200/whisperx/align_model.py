@@ -185,13 +185,27 @@ class Wav2Vec2B200:
         if self._staging_done is not None:
             self._staging_done.synchronize()
         hv = self._staging.numpy()
-        for w, o, l in zip(waves, offs, lens):
-            n = len(w)
-            hv[o:o + n] = np.asarray(w, dtype=np.float32)
-            if n < l:
-                hv[o + n:o + l] = 0.0
         dev = torch.empty(max(total, 1), dtype=torch.float32, device=self.device)
-        dev[:total].copy_(self._staging[:total], non_blocking=True)
+        # Groups of segments: host copy into the pinned buffer, then an asynchronous H2D of that range, so the PCIe transfer of
+        # one group runs under the host copy of the next; segments that are back-to-back views of one float32 array (what
+        # align() cuts from a recording) are copied as one range with torch's multi-threaded copy (as the ASR backend does).
+        from .backends.b200 import B200WhisperBackend
+        n_seg, group = len(waves), 12
+        for g0 in range(0, n_seg, group):
+            g1 = min(n_seg, g0 + group)
+            a, b = int(offs[g0]), int(offs[g1 - 1] + lens[g1 - 1])
+            same_len = all(len(w) == int(l) for w, l in zip(waves[g0:g1], lens[g0:g1]))
+            run = B200WhisperBackend._contiguous_run(waves[g0:g1], lens[g0:g1]) if same_len else None
+            if run is not None:
+                self._staging[a:b].copy_(torch.from_numpy(run))
+            else:
+                for w, o, l in zip(waves[g0:g1], offs[g0:g1], lens[g0:g1]):
+                    n = len(w)
+                    hv[o:o + n] = np.asarray(w, dtype=np.float32)
+                    if n < l:
+                        hv[o + n:o + l] = 0.0
+            if b > a:
+                dev[a:b].copy_(self._staging[a:b], non_blocking=True)
         self._staging_done = torch.cuda.Event()
         self._staging_done.record()
         self.last_stats["h2d_bytes"] = total * 4

@@ -546,10 +546,27 @@ def _merge_runs(path_tok: np.ndarray, path_prob: np.ndarray):
     T = len(path_tok)
     if T == 0:
         return [], [], []
-    cut = (np.flatnonzero(path_tok[1:] != path_tok[:-1]) + 1).tolist()
-    lo, hi = [0] + cut, cut + [T]
-    prob = path_prob.astype(np.float64).tolist()
-    return lo, hi, [sum(prob[a:b]) / (b - a) for a, b in zip(lo, hi)]
+    cut = np.flatnonzero(path_tok[1:] != path_tok[:-1]) + 1
+    first = np.concatenate([[0], cut])
+    lo, hi = first.tolist(), cut.tolist() + [T]
+    length = np.diff(np.concatenate([first, [T]]))
+    # The probabilities are float32 values: a double sum of a few of them is EXACT (no rounding at all, hence independent of
+    # the summation order and of Python's compensated sum) whenever the binary exponents inside the run span less than
+    # 53 - 24 - log2(length) bits.  Those runs are summed with one reduceat; the rest (a run mixing ~1 and ~1e-9) take
+    # Python's own sum(), which is what the reference's merge_repeats evaluates.
+    p64 = path_prob.astype(np.float64)
+    _, ex = np.frexp(p64)
+    ex = np.where(p64 == 0.0, 10000, ex)  # zeros constrain nothing
+    e_min = np.minimum.reduceat(ex, first)
+    e_max = np.maximum.reduceat(np.where(p64 == 0.0, -10000, ex), first)
+    exact = (e_max - e_min <= 24) & (length <= 16)
+    sums = np.add.reduceat(p64, first)
+    mean = (sums / length).tolist()
+    if not exact.all():
+        prob = p64.tolist()
+        for k in np.flatnonzero(~exact).tolist():
+            mean[k] = sum(prob[lo[k]:hi[k]]) / (hi[k] - lo[k])
+    return lo, hi, mean
 
 
 def _merge_repeats_arrays(path_tok: np.ndarray, path_prob: np.ndarray, transcript: str) -> List[Segment]:

@@ -21,7 +21,17 @@ LANGUAGE_CODES = ("en zh de es ru ko fr ja pt tr pl ca nl ar sv it id hi fi vi h
                   "ka be tg sd gu am yi lo uz fo ht ps tk nn mt sa lb my bo tl mg as tt haw ln ha ba jw su yue").split()
 
 
+_PSEUDO_CACHE: Dict[int, str] = {}
+
+
 def _pseudo_word(i: int) -> str:
+    w = _PSEUDO_CACHE.get(i)
+    if w is None:
+        w = _PSEUDO_CACHE[i] = _pseudo_word_uncached(i)
+    return w
+
+
+def _pseudo_word_uncached(i: int) -> str:
     s = ""
     i += 26  # at least two letters
     while i > 0:
