@@ -423,6 +423,7 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     r = timed(job, dist, world, args.steps, args.warmup, flush, sampler)
     value = audio_s / (r["ms_step"] / 1e3)
+    w2v_stats = dict(getattr(align_bundle[0], "last_stats", {})) if align_bundle is not None else {}  # of THIS job (later jobs overwrite them)
 
     # ---- e2e: the public API with host buffers; chunks sharded, results gathered on rank 0 inside the timed region -------
     e2e = None
@@ -538,7 +539,7 @@ def main():
         "cross_kv_gemm": {"ms": r["cross_ms"], "TFLOP/s": ckv_flops / (r["cross_ms"] * 1e-3) / 1e12},
         "decode_steps": {"ms": r["dec_ms"], "steps": dr["steps"], "GB/s": dr["achieved"]}}
     if align_bundle is not None:
-        st = getattr(align_bundle[0], "last_stats", {})
+        st = w2v_stats
         stages["wav2vec2"] = {"ms": sm["w2v"], "TFLOP/s": st.get("flops", 0) / max(sm["w2v"] * 1e-3, 1e-9) / 1e12, "frames": st.get("frames")}
         stages["ctc"] = {"ms": sm["ctc"]}
     roofline = {"bound": "hbm", "kernel": "dec_step_kernel (persistent cooperative kernel: %d operators per decode step separated by grid "

@@ -517,9 +517,10 @@ __device__ __forceinline__ void att_consume(const uint4* kv, uint4* vv, int kb, 
 
 // Causal self-attention.  A (sequence, head) unit is finished by one warp: it completes the QKV GEMV for its head
 // (sum of split-K partials + bias), appends the new K/V row to the cache, and attends over cached keys plus the new one
-// (taken from registers, rounded to bf16 like its cached copy).  Units that do not fill a whole round of warps
-// (B H = 1200 on 1184 warps at batch 60) are NOT given a second round of their own: the 8 warps of a CTA share such
-// a unit, each attending over an eighth of the cached keys, and merge their states through shared memory.
+// (taken from registers, rounded to bf16 like its cached copy).  Units that do not fill a whole round of warps are NOT given
+// a second round of their own: all warps of a CTA share such a unit, each attending over its share of the cached keys, and
+// merge their states through shared memory.  With few units (small batches) EVERY unit is shared by W warps (sa_share): the
+// phase is a latency chain over the cached keys, and 160 units on 1776 warps would leave 91 % of them idle.
 struct SelfUnit {
   float q8[8];   // scaled q, dims 8 c8 .. 8 c8 + 7
   uint4 kq, vq;  // the new key / value row (bf16), same dims
@@ -664,6 +665,22 @@ __device__ __forceinline__ void self_unit_store(const MkParams& p, int b, int h,
   *reinterpret_cast<uint4*>(p.att + (size_t)b * p.d + h * 64 + c8 * 8) = pk;
 }
 
+// warps of a CTA that share one unit in the shared round of the self-attention phase: all of them when only the remainder units of a
+// large batch are shared, else the largest divisor of the warp count that fits every unit into that one round
+#ifndef WXB_SA_MIN_SHARE
+#define WXB_SA_MIN_SHARE 2
+#endif
+constexpr int SA_MIN_SHARE = WXB_SA_MIN_SHARE;  // fewest warps per unit for which sharing every unit pays (A/B knob; MK_WARPS + 1 = never)
+__device__ __forceinline__ int sa_share(int n_units, int n_warps) {
+  int W = MK_WARPS;
+  if (n_units * SA_MIN_SHARE <= n_warps) {
+#pragma unroll
+    for (int c = SA_MIN_SHARE; c <= MK_WARPS; ++c)
+      if (MK_WARPS % c == 0 && n_units * c <= n_warps) W = c;
+  }
+  return W;
+}
+
 __device__ __forceinline__ void self_attn_phase(const MkParams& p, int l, const float* __restrict__ qkv_b, int pos, uint8_t* ring,
                                                 float* scratch, const MkSync& sy) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, slot = lane >> 3, c8 = lane & 7;
@@ -672,31 +689,47 @@ __device__ __forceinline__ void self_attn_phase(const MkParams& p, int l, const 
   __nv_bfloat16* sk = p.self_kv + (size_t)l * 2 * p.B0 * H * TX * 64;
   __nv_bfloat16* sv = sk + (size_t)p.B0 * H * TX * 64;
   const int n_units = B * H, n_warps = sy.nc * MK_WARPS;
-  int n_solo = n_units;  // units [0, n_solo) get a warp each; units [n_solo, n_units) a CTA each
+  // Work items of a warp: its solo units (one warp per unit, whole rounds of n_warps units), then one SHARED round in which W warps
+  // of a CTA finish one unit together, each attending over 1 / W of the cached keys, states merged through shared memory:
+  //   many units (batch 60: 1200 units on 1776 warps)  the n_units % n_warps units that would need a second round of their own
+  //                                                    are shared by all warps of a CTA (W = MK_WARPS);
+  //   few units (small batches: strong scaling over several GPUs, BASELINE config 3)  the phase is a latency chain over the cached
+  //                                                    keys, so EVERY unit is shared by W warps, W = the largest divisor of the warp
+  //                                                    count that fits all units into the one shared round.
+  int n_solo = n_units;  // units [0, n_solo) get a warp each; units [n_solo, n_units) are shared by W warps of a CTA
   const int left = n_units % n_warps;
   if (left > 0 && left <= sy.nc && n_units > n_warps) n_solo = n_units - left;
-  // work items of this warp: its solo units, then (CTAs with a shared unit) an eighth of that unit's cached keys
+  if (n_units * SA_MIN_SHARE <= n_warps) n_solo = 0;
+  // work items of this warp: its solo units, then (CTAs with a shared unit) its share of a shared unit's cached keys
   const int n_rounds = (n_solo + n_warps - 1) / n_warps;
-  const bool shared_unit = n_solo + sy.cta < n_units;  // CTA-uniform
+  const bool shared_unit = n_solo + sy.cta < n_units;  // CTA-uniform: warp group 0 of this CTA has a shared unit
   for (int round = 0; round < n_rounds + (shared_unit ? 1 : 0); ++round) {
     const bool coop = round == n_rounds;
-    const int u0 = coop ? n_solo + sy.cta : round * n_warps + sy.cta * MK_WARPS + warp;
+    // The sharing factor W and this warp's share are derived twice (before and after the key loop, the second time from an
+    // opaque copy of n_units so that the compiler does not keep them live across it): the persistent kernel has no register
+    // to spare (DESIGN.md "Stack frames").
+    int u0 = round * n_warps + sy.cta * MK_WARPS + warp, k0 = 0, k1 = pos;
+    bool first = true;
+    if (coop) {
+      const int W = sa_share(n_units, n_warps), wi = warp % W;
+      // a warp group past the last unit repeats the last unit (identical values to identical addresses) so that the shared
+      // round stays free of divergent paths around its block barriers
+      u0 = min(n_units - 1, n_solo + (warp / W) * sy.nc + sy.cta);
+      const int per = (pos + W - 1) / W;  // cached keys per warp
+      k0 = min(pos, wi * per);
+      k1 = min(pos, k0 + per);
+      first = wi == 0;
+    }
     if (u0 >= (coop ? n_units : n_solo)) continue;
     const int b = u0 / H, h = u0 - b * H;
     const SelfUnit u = self_unit_qkv(p, qkv_b, b, h, slot, c8);
     const size_t slab = ((size_t)s_rows[b] * H + h) * TX * 64;
-    if (slot == 0 && (!coop || warp == 0)) {
+    if (slot == 0 && first) {
       *reinterpret_cast<uint4*>(sk + slab + (size_t)pos * 64 + c8 * 8) = u.kq;
       *reinterpret_cast<uint4*>(sv + slab + (size_t)pos * 64 + c8 * 8) = u.vq;
     }
-    int k0 = 0, k1 = pos;
-    if (coop) {
-      const int per = (pos + MK_WARPS - 1) / MK_WARPS;  // cached keys per warp
-      k0 = min(pos, warp * per);
-      k1 = min(pos, k0 + per);
-    }
     float m, lsum, acc[8];
-    self_unit_attend(u, sk + slab, sv + slab, k0, k1, !coop || warp == 0, slot, c8, stage, m, lsum, acc);
+    self_unit_attend(u, sk + slab, sv + slab, k0, k1, first, slot, c8, stage, m, lsum, acc);
     if (!coop) {
       if (slot == 0) self_unit_store(p, b, h, c8, lsum, acc);
     } else {
@@ -707,20 +740,26 @@ __device__ __forceinline__ void self_attn_phase(const MkParams& p, int l, const 
         for (int j = 0; j < 8; ++j) st[2 + c8 * 8 + j] = acc[j];
       }
       __syncthreads();
-      if (warp == 0 && slot == 0) {
+      int nu = n_units;
+      asm volatile("" : "+r"(nu));
+      const int W = sa_share(nu, n_warps);
+      if ((threadIdx.x >> 5) % W == 0 && slot == 0) {  // the group's first warp merges the W states that start at its own slot
         float M = -INFINITY;
 #pragma unroll
-        for (int w = 0; w < MK_WARPS; ++w) M = fmaxf(M, scratch[w * 66]);
+        for (int w = 0; w < MK_WARPS; ++w)
+          if (w < W) M = fmaxf(M, st[w * 66]);
         float L = 0.f, o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = 0.f;
 #pragma unroll
         for (int w = 0; w < MK_WARPS; ++w) {
-          const float mw = scratch[w * 66];
-          const float wt = (mw > -INFINITY) ? __expf(mw - M) : 0.f;
-          L += wt * scratch[w * 66 + 1];
+          if (w < W) {
+            const float mw = st[w * 66];
+            const float wt = (mw > -INFINITY) ? __expf(mw - M) : 0.f;
+            L += wt * st[w * 66 + 1];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] += wt * scratch[w * 66 + 2 + c8 * 8 + j];
+            for (int j = 0; j < 8; ++j) o[j] += wt * st[w * 66 + 2 + c8 * 8 + j];
+          }
         }
         self_unit_store(p, b, h, c8, L, o);
       }
@@ -745,12 +784,18 @@ __device__ __forceinline__ void self_attn_phase(const MkParams& p, int l, const 
 struct XaItem {
   int slab, k0, k1, piece, lj;
 };
-__device__ __forceinline__ XaItem xa_item(int it, int cta, int qw, int G, int P, int plen) {
+// Item `it` of CTA `cta`'s work list: its qw whole slabs, then its np = n_items - qw remainder pieces.  (Measured A/B, -DWXB_XA_PIECES_FIRST:
+// with the pieces at the FRONT of the list their publish / ticket / merge round trips stall the merging consumer warp and with it the
+// 4-stage ring while the stream should be running: 82.5 vs 77.4 us per phase at batch 60, 55.8 vs 45.6 at batch 30.)
+__device__ __forceinline__ XaItem xa_item(int it, int cta, int qw, int G, int P, int plen, int np) {
   XaItem x;
-  if (it < qw) {
-    x.slab = it * G + cta; x.k0 = 0; x.k1 = T_AUDIO; x.piece = -1; x.lj = 0;
+#ifndef WXB_XA_PIECES_FIRST
+  it = (it < qw) ? np + it : it - qw;  // position in the list -> (pieces 0 .. np-1, whole slabs np ..) numbering used below
+#endif
+  if (it >= np) {
+    x.slab = (it - np) * G + cta; x.k0 = 0; x.k1 = T_AUDIO; x.piece = -1; x.lj = 0;
   } else {
-    const int pc = (it - qw) * G + cta;
+    const int pc = it * G + cta;
     x.lj = pc / P; x.piece = pc - x.lj * P;
     x.slab = qw * G + x.lj; x.k0 = x.piece * plen; x.k1 = min(T_AUDIO, x.k0 + plen);
   }
@@ -761,8 +806,13 @@ __device__ __forceinline__ XaItem xa_item(int it, int cta, int qw, int G, int P,
 // per-phase counts: they are recomputed at the start of a phase instead of living in registers across all the others.
 __device__ __forceinline__ uint32_t xa_stage_count(int cta, int qw, int G, int P, int plen, int n_items) {
   uint32_t n_st = (uint32_t)qw * ((T_AUDIO + XA_KEYS - 1) / XA_KEYS);
-  for (int it = qw; it < n_items; ++it) {
-    const XaItem x = xa_item(it, cta, qw, G, P, plen);
+  for (int k = 0; k < n_items - qw; ++k) {
+#ifdef WXB_XA_PIECES_FIRST
+    const int it = k;
+#else
+    const int it = qw + k;  // the pieces sit behind the whole slabs
+#endif
+    const XaItem x = xa_item(it, cta, qw, G, P, plen, n_items - qw);
     n_st += (uint32_t)((x.k1 - x.k0 + XA_KEYS - 1) / XA_KEYS);
   }
   return n_st;
@@ -811,11 +861,11 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, int x
     XaItem x = {};
     int oslab = 0;  // K/V slab of the item's ORIGINAL row
     auto orig_slab = [&](int slab) { const int b = slab / H; return s_rows[b] * H + (slab - b * H); };
-    if (n_items > 0) { x = xa_item(0, cta, qw, G, P, plen); kk = x.k0; oslab = orig_slab(x.slab); }
+    if (n_items > 0) { x = xa_item(0, cta, qw, G, P, plen, n_items - qw); kk = x.k0; oslab = orig_slab(x.slab); }
     uint32_t issued = xa_count0;
     auto stage_q = [&](int qi) {
       // raw q rows of item qi (row gk = bias, rows 0 .. gk-1 = split-K partials of the cq GEMV), 2 rows per pass
-      const XaItem xq = xa_item(qi, cta, qw, G, P, plen);
+      const XaItem xq = xa_item(qi, cta, qw, G, P, plen, n_items - qw);
       const uint32_t gi = xa_items0 + (uint32_t)qi, qpar = gi & 1;
       mbar_wait(sy.mb(MB_Q_FREE + qpar), ((gi >> 1) & 1) ^ 1);  // the consumers have used the rows of item gi - 2
       float* dst = qraw + qpar * (QRAW_ROWS * 64);
@@ -853,7 +903,7 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, int x
       kk += XA_KEYS;
       if (kk >= x.k1) {
         ++it;
-        if (it < n_items) { x = xa_item(it, cta, qw, G, P, plen); kk = x.k0; oslab = orig_slab(x.slab); }
+        if (it < n_items) { x = xa_item(it, cta, qw, G, P, plen, n_items - qw); kk = x.k0; oslab = orig_slab(x.slab); }
       }
     }
     sy.pre = 0;
@@ -866,7 +916,7 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, int x
     const int sw = lane & 7;
     uint32_t consumed = xa_count0;
     for (int it = 0; it < n_items; ++it) {
-      const XaItem x = xa_item(it, cta, qw, G, P, plen);
+      const XaItem x = xa_item(it, cta, qw, G, P, plen, n_items - qw);
       const int b = x.slab / H, h = x.slab - b * H;
       const uint32_t gi = xa_items0 + (uint32_t)it;  // items since kernel start: parity and phase of the double-buffered slots
       const uint32_t ipar = gi & 1, iph = (gi >> 1) & 1;
@@ -1044,14 +1094,30 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, int x
           last = __shfl_sync(0xffffffffu, last, 0);
           if (last) {
             __threadfence();
+            // the P piece states: maxima spread over the lanes, then groups of four pieces with all 16 loads of a group in
+            // flight at once (one L2 round trip per group instead of one per piece; same summation order as a piece-by-piece loop)
             float MM = -INFINITY;
-            for (int s2 = 0; s2 < P; ++s2) MM = fmaxf(MM, __ldcg(part + s2 * 66));
+            for (int s2 = lane; s2 < P; s2 += 32) MM = fmaxf(MM, __ldcg(part + s2 * 66));
+            MM = warp_max(MM);
             float LL = 0.f, O0 = 0.f, O1 = 0.f;
-            for (int s2 = 0; s2 < P; ++s2) {
-              const float w = __expf(__ldcg(part + s2 * 66) - MM);
-              LL += w * __ldcg(part + s2 * 66 + 1);
-              O0 += w * __ldcg(part + s2 * 66 + 2 + lane);
-              O1 += w * __ldcg(part + s2 * 66 + 2 + lane + 32);
+            for (int s0 = 0; s0 < P; s0 += 4) {
+              float mv[4], lv[4], a0[4], a1[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const bool in = s0 + u < P;
+                const float* ps = part + (in ? s0 + u : s0) * 66;
+                mv[u] = in ? __ldcg(ps) : -INFINITY;
+                lv[u] = __ldcg(ps + 1);
+                a0[u] = __ldcg(ps + 2 + lane);
+                a1[u] = __ldcg(ps + 2 + lane + 32);
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float w = __expf(mv[u] - MM);  // a slot past P: exp(-inf) = 0
+                LL += w * lv[u];
+                O0 += w * a0[u];
+                O1 += w * a1[u];
+              }
             }
             out[lane] = __float2bfloat16_rn(O0 / LL);
             out[lane + 32] = __float2bfloat16_rn(O1 / LL);
@@ -1304,7 +1370,7 @@ __device__ __forceinline__ void pre_issue(const MkParams& p, int l, int k, int x
     const uint32_t xa_count0 = (uint32_t)xq * xa_stage_count(cta, qw, G, P, plen, n_items);
     int it = 0, n = 0;
     while (it < n_items && n < XA_NST) {
-      const XaItem x = xa_item(it, cta, qw, G, P, plen);
+      const XaItem x = xa_item(it, cta, qw, G, P, plen, n_items - qw);
       const int xb = x.slab / p.H, oslab = s_rows[xb] * p.H + (x.slab - xb * p.H);
       for (int kk = x.k0; kk < x.k1 && n < XA_NST; kk += XA_KEYS, ++n) {
         if (!issue) continue;
