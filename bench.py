@@ -184,6 +184,10 @@ class Job:
                                         vad_method="uniform", batch_size=batch_size, align_model=align_bundle)
         self.be = self.pipe.backend
         self.ctx, self.dims = self.be.ctx, self.be.dims
+        if args.dec_groups:            # A/B aids of the decoder's sequence-group schedule (results do not depend on them)
+            self.ctx.debug_set("dec_groups", args.dec_groups)
+        if args.dec_group_delay_ns >= 0:
+            self.ctx.debug_set("dec_group_delay_ns", args.dec_group_delay_ns)
         if args.sample_len > 0:
             self.be.options["sample_len"] = args.sample_len
         self.sample_len = int(self.be.options["sample_len"])
@@ -383,6 +387,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the batch8 / turbo / weak sub-records")
     ap.add_argument("--no-align", action="store_true", help="leave the wav2vec2 + CTC alignment leg out (profiling only)")
+    ap.add_argument("--dec-groups", type=int, default=0, help="A/B aid: sequence groups per decode call (0 = the library's choice)")
+    ap.add_argument("--dec-group-delay-ns", type=int, default=-1, help="A/B aid: start offset between the sequence groups (-1 = default)")
     ap.add_argument("--allow-env", action="store_true", help="run although WXB_* variables are set (A/B runs, not a bench value)")
     args = ap.parse_args()
     env_seen = env_guard(args.allow_env)
@@ -577,7 +583,9 @@ def main():
                                    f"dealt to {world} GPU(s) (LPT queues, {n_mine} chunks on rank 0), batch {min(args.batch_size, n_mine)}, log-mel + "
                                    f"encoder + greedy decode ({job.sample_len} positions) + {align_note}",
                        "batch_size": args.batch_size, "parallelism": f"{world} x 1 GPU, chunk-sharded, host gather only (no collective)",
-                       "l2": "256 MB flush buffer written before every step", "library": lib_path, "env": env_seen},
+                       "l2": "256 MB flush buffer written before every step", "library": lib_path, "env": env_seen,
+                       **({"dec_groups": args.dec_groups} if args.dec_groups else {}),
+                       **({"dec_group_delay_ns": args.dec_group_delay_ns} if args.dec_group_delay_ns >= 0 else {})},
             "clocks": r["clocks"], "e2e": e2e, "gpu_launches": int(r["launches"]), "roofline": roofline, "cpu_baseline": cpu_baseline}
     line.update(extras)
     print(json.dumps(line), flush=True)

@@ -87,6 +87,11 @@ void wxb_destroy(wxb_ctx* ctx) {
   wxb_model_free(ctx);
   wxb_align_model_free(ctx);
   wxb_dec_timings_clear(ctx);
+  for (int i = 0; i < WXB_MAX_DEC_GROUPS - 1; ++i) {
+    if (ctx->dec_side[i]) cudaStreamDestroy(ctx->dec_side[i]);
+    if (ctx->dec_join[i]) cudaEventDestroy(ctx->dec_join[i]);
+  }
+  if (ctx->dec_fork) cudaEventDestroy(ctx->dec_fork);
   wxb_buf* bufs[] = {&ctx->ws_ctc_trellis, &ctx->ws_ctc_hist, &ctx->ws_ctc_meta, &ctx->ws_mel_max,
                      &ctx->ws_mel_band};
   for (wxb_buf* b : bufs)
@@ -103,6 +108,16 @@ int64_t wxb_launch_count(const wxb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int wxb_debug_set(wxb_ctx* ctx, const char* key, int value) {
   if (!ctx || !key) return WXB_ERR_INVALID;
   if (std::string(key) == "w2v_stop") { ctx->w2v_stop = value; return WXB_OK; }
+  if (std::string(key) == "dec_groups") {  // A/B aid: sequence groups per decode call (0 = automatic); results do not depend on it
+    if (value < 0 || value > WXB_MAX_DEC_GROUPS) return wxb_fail(ctx, WXB_ERR_INVALID, "dec_groups: 0 .. %d", WXB_MAX_DEC_GROUPS);
+    ctx->dec_groups_override = value;
+    return WXB_OK;
+  }
+  if (std::string(key) == "dec_group_delay_ns") {  // A/B aid: start offset between the sequence groups' kernel instances
+    if (value < 0 || value > 10000000) return wxb_fail(ctx, WXB_ERR_INVALID, "dec_group_delay_ns: 0 .. 10000000");
+    ctx->dec_group_delay_ns = value;
+    return WXB_OK;
+  }
   return wxb_fail(ctx, WXB_ERR_INVALID, "wxb_debug_set: unknown key '%s'", key);
 }
 

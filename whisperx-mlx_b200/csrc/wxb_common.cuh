@@ -27,7 +27,10 @@ struct wxb_dec_maps_key {
   const void* model = nullptr;
   const void *xn = nullptr, *att = nullptr, *hid = nullptr, *ckv = nullptr;
   int B = 0;
+  int groups = 0;  // sequence groups the activation maps were laid out for
 };
+
+constexpr int WXB_MAX_DEC_GROUPS = 4;  // sequence groups (concurrent instances of the decode kernel) per call
 
 struct wxb_ctx {
   int device = 0;
@@ -47,6 +50,11 @@ struct wxb_ctx {
   // reset, by wxb_destroy, and capped at WXB_MAX_DEC_TIMINGS so a serving process cannot grow without bound)
   bool dec_timing_on = false;
   std::vector<wxb_dec_timing> dec_timings;  // one entry per timed wxb_decode_greedy call since the last reset
+  // sequence groups 1.. of a decode call run on side streams forked from / joined to the caller's stream (created on first use)
+  cudaStream_t dec_side[WXB_MAX_DEC_GROUPS - 1] = {};
+  cudaEvent_t dec_fork = nullptr, dec_join[WXB_MAX_DEC_GROUPS - 1] = {};
+  int dec_groups_override = 0;  // wxb_debug_set "dec_groups": 0 = automatic
+  int dec_group_delay_ns = 110000;  // group g of G starts g / G of this (about one layer of a group) late: wxb_debug_set "dec_group_delay_ns"
   bool lm_tables_ready = false;  // log-mel window/twiddle tables uploaded to this device
   // per-device state that must not be process-global (a process may hold one ctx per GPU):
   std::map<const void*, int> func_smem;        // kernels whose MaxDynamicSharedMemorySize attribute was raised on this device

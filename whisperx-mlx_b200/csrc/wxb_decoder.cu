@@ -58,6 +58,12 @@ constexpr int T_AUDIO = 1500;
 #endif
 constexpr int MK_THREADS = WXB_MK_THREADS;  // 12 warps: 11 cross-attention consumer warps, one self-attention round at 1200 units
 constexpr int MK_WARPS = MK_THREADS / 32;
+// 6-warp CTAs are built so that TWO kernel instances share every SM (launch bounds, shared-memory plan): the batch is cut into
+// sequence groups, one kernel instance per group on its own stream, and one group's latency-bound operator chain runs under the
+// other group's cross-K/V stream (launch_groups).  The hardware co-schedules CTAs of several launches that allocate tensor memory on
+// one SM as long as their columns fit (tools/probe/coresident_probe.cu) although the occupancy API reports 1 CTA per SM.
+constexpr int MK_CTAS_PER_SM = MK_WARPS <= 6 ? 2 : 1;
+constexpr int GV_MAX_MT = MK_CTAS_PER_SM == 2 ? 2 : 4;  // m16 batch tiles of one kernel instance (rows per instance <= 16 GV_MAX_MT)
 constexpr int LN_V4 = 2;    // LayerNorm phase: float4 groups per thread, d <= 4 * 2 * 256
 constexpr int GK_MAX = 10;  // largest split-K factor a GEMV plan may use
 constexpr int MAX_LAYERS = 32;
@@ -78,7 +84,7 @@ constexpr int GV_A_BYTES = GV_ROWS * GV_BK * 2;
 constexpr int XA_CW = MK_WARPS - 1;          // cross-attention consumer warps (hardware warps 1 ..); warp 0 produces
 constexpr int XA_KEYS = 16 * XA_CW;          // keys per stage: one m16 tile per consumer warp
 constexpr int XA_HALF = XA_KEYS * 128;       // bytes of K (or V) per stage
-constexpr int XA_TAIL = MK_WARPS == 8 ? 48 : 96;  // rows of the short TMA box used when at most this many keys of an item remain (1500 = 8 x 176 + 92)
+constexpr int XA_TAIL = MK_WARPS == 8 ? 48 : MK_WARPS == 6 ? 64 : 96;  // rows of the short TMA box used when at most this many keys of an item remain (1500 = 8 x 176 + 92 = 18 x 80 + 60)
 constexpr int SST_BYTES = (2 * XA_CW * 66 * 4 + 127) & ~127;  // [2 item parities][XA_CW warps][66] floats, padded
 constexpr int QRAW_ROWS = GK_MAX + 1;                     // bias row + up to GK_MAX split-K partial rows of q
 constexpr int QRAW_BYTES = 2 * QRAW_ROWS * 64 * 4;        // two items in flight
@@ -88,7 +94,7 @@ constexpr int XA_NST = MK_WARPS == 8 ? 6 : MK_WARPS == 10 ? 5 : 4;  // K/V ring 
 #define WXB_XA_NS 1
 #endif
 constexpr int XA_NS = WXB_XA_NS;             // K/V stages per consumer iteration
-constexpr int GV_NST = 6;                    // GEMV ring depth
+constexpr int GV_NST = MK_CTAS_PER_SM == 2 ? 4 : 6;  // GEMV ring depth
 #ifndef WXB_GV_NACC
 #define WXB_GV_NACC 1
 #endif
@@ -101,7 +107,8 @@ constexpr int GV_TMEM_COLS = 64 * GV_NACC < 32 ? 32 : 64 * GV_NACC;
 static_assert(GV_NACC == 1 || GV_NACC == 2 || GV_NACC == 4, "GV_NACC");
 constexpr int RING_BYTES = XA_NST * 2 * XA_HALF;
 constexpr size_t MK_SMEM = RING_BYTES + SCRATCH_BYTES + 1024;
-static_assert(GV_NST * (GV_A_BYTES + 64 * GV_BK * 2) <= RING_BYTES, "GEMV ring must fit the shared region");
+static_assert(GV_NST * (GV_A_BYTES + 16 * GV_MAX_MT * GV_BK * 2) <= RING_BYTES, "GEMV ring must fit the shared region");
+static_assert(MK_CTAS_PER_SM * (MK_SMEM + 10 * 1024) <= 228 * 1024, "shared memory of the CTAs that share an SM (dynamic + ~9 KB static + 1 KB reserved each)");
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -179,6 +186,7 @@ struct MkParams {
   const int* rows;        // [B] original row of compact row i (identity while every row is live)
   int mode;     // 0: no logits (forced prompt token); 1: logits; 2: logits + sampling
   int n_steps;  // consecutive positions decoded by this launch (> 1 only in mode 2)
+  unsigned delay_ns;  // sequence group g > 0: the instance idles this long first, so that the groups' cross-attention phases interleave
   int skip;     // profiling aid (WXB_DEC_SKIP): 1 cross-attention, 2 GEMV, 4 self-attention, 8 LayerNorm, 16 cross math, 32 cross merge,
                 //   64 every CTA streams the same 4 K/V slabs (all L2 hits)
   const DecLayerW* layers;  // device array [L]
@@ -1436,7 +1444,7 @@ __device__ __forceinline__ int ops_per_step(const MkParams& p) {
 // (Running several CTAs per SM so that one sequence group's chain hides under another group's K/V stream was tried
 // and measured slower; see DESIGN.md.  A kernel that allocates tensor memory is pinned to one CTA per SM anyway.)
 template <int MT>
-__global__ void __launch_bounds__(MK_THREADS, 1) dec_step_kernel(const __grid_constant__ MkParams p) {
+__global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) dec_step_kernel(const __grid_constant__ MkParams p) {
   extern __shared__ uint8_t mk_smem_raw[];
   uint8_t* ring = mk_smem_raw + ((1024u - (smem_u32(mk_smem_raw) & 1023u)) & 1023u);  // 1024-byte aligned (swizzle atoms)
   float* scratch = reinterpret_cast<float*>(ring + RING_BYTES);
@@ -1469,6 +1477,22 @@ __global__ void __launch_bounds__(MK_THREADS, 1) dec_step_kernel(const __grid_co
   tc_fence_after();
   sy.tmem = tmem_slot;
 
+  if (p.delay_ns) {  // CTA-uniform
+    if (threadIdx.x == 0) {
+      unsigned long long t0, t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      do { __nanosleep(500); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); } while (t1 - t0 < (unsigned long long)p.delay_ns);
+    }
+    __syncthreads();
+  }
+  if (p.prof && sy.cta == 0 && threadIdx.x == 0) {  // tracing aid: where and when this instance's CTA 0 started
+    unsigned smid;
+    unsigned long long t;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.prof[(1 << 16) - 1] = smid;
+    p.prof[(1 << 16) - 2] = t;
+  }
   unsigned bar_target = 0;
   const int pos0 = *p.d_pos;  // written only after the last barrier of this launch
   const int n_ph = ops_per_step(p);
@@ -1527,7 +1551,23 @@ __global__ void dec_finalize_kernel(const int* __restrict__ tokens, int stride, 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-constexpr size_t PART_FLOATS = (size_t)4 << 20;  // 16 MB of fp32 split-K partials per group
+constexpr size_t PART_FLOATS = (size_t)4 << 20;  // 16 MB of fp32 split-K partials, shared out between the sequence groups
+// Sequence groups.  The activation buffers hold MAX_GROUP rows cut into LAYOUT_GROUPS fixed regions; group g of a launch works in
+// region g (compact rows of the group from the region's first row), with its own split-K partials, piece states, tickets, grid
+// barrier counter, position counter, row list and activation tensor maps.  K/V caches, tokens and per-row outputs are indexed
+// by the ORIGINAL row and shared.
+constexpr int LAYOUT_GROUPS = MK_CTAS_PER_SM;
+constexpr int GROUP_ROWS = MAX_GROUP / LAYOUT_GROUPS;  // rows of a region = 16 GV_MAX_MT
+static_assert(GROUP_ROWS == 16 * GV_MAX_MT && LAYOUT_GROUPS <= WXB_MAX_DEC_GROUPS, "sequence-group layout");
+constexpr size_t GROUP_PART_FLOATS = PART_FLOATS / LAYOUT_GROUPS;
+constexpr int GROUP_PIECES = 1024, GROUP_TICKETS = 512;
+#ifndef WXB_DEC_GROUP_MIN
+#define WXB_DEC_GROUP_MIN 8
+#endif
+constexpr int DEC_GROUP_MIN_ROWS = WXB_DEC_GROUP_MIN;  // fewest rows per group for which a second group is started
+#ifndef WXB_DEC_GROUP_DELAY_NS
+#define WXB_DEC_GROUP_DELAY_NS 55000
+#endif
 
 struct DecBuffers {
   float *x, *logits, *part, *apart, *sum_lp;
@@ -1538,7 +1578,8 @@ struct DecBuffers {
   int qA;
   unsigned* bar;
   const DecLayerW* layers;
-  const CUtensorMap* maps;
+  const CUtensorMap* maps;  // LAYOUT_GROUPS tables of n_maps entries
+  size_t n_maps;
   int B, tok_stride;
   long long ldl;  // row stride of `logits` (n_vocab rounded up to 4 floats: 16-byte aligned rows)
 };
@@ -1567,14 +1608,16 @@ bool dec_prof_enabled() {
   }
   return v == 1;
 }
-constexpr size_t PROF_SLOTS = 1 << 16;
-struct ProfLast { int mode = 0, n_steps = 0, L = 0; bool nsp = false; unsigned long long* dev = nullptr; } g_prof_last;
+constexpr size_t PROF_SLOTS = 1 << 16;  // the kernel keeps its start record in the last two slots
+static_assert(PROF_SLOTS == (1 << 16), "dec_step_kernel writes prof[(1 << 16) - 1 / - 2]");
+struct ProfLast { int mode = 0, n_steps = 0, L = 0, groups = 1; bool nsp = false; unsigned long long* dev = nullptr; } g_prof_last;
 
 // Pick the split-K factor for y[B, N] = act[B, K] W[N, K]^T on G CTAs (tiles of 128 weight rows x K / gk).
 // Cost model in microseconds: a CTA pulls its weight tile at ~60 KB/us and its activation slice from L2 at
 // ~80 KB/us, every wave of tiles pays ~1 us of pipeline latency, and split-K partials are written once and
 // read once through L2 (~10 MB/us chip-wide).
 MkGemv plan_gemv(int N, int K, int B, int Bp, int G, bool full_k) {
+  // (B = live rows of ONE sequence group; its partials live in GROUP_PART_FLOATS floats)
   MkGemv best = {N, K, 0, 0};
   double best_cost = 1e30;
   for (int gk = 1; gk <= K / GV_BK && gk <= GK_MAX; ++gk) {
@@ -1582,7 +1625,7 @@ MkGemv plan_gemv(int N, int K, int B, int Bp, int G, bool full_k) {
     if (K % gk) continue;
     const int Ks = K / gk;
     if (Ks % GV_BK) continue;
-    if ((size_t)gk * B * N > PART_FLOATS) continue;
+    if ((size_t)gk * B * N > GROUP_PART_FLOATS) continue;
     const int tiles = ceil_div(N, GV_ROWS) * gk;
     const int waves = ceil_div(tiles, G);
     const double cost = waves * ((double)GV_ROWS * Ks * 2 / 60e3 + (double)Bp * Ks * 2 / 80e3 + 1.0) +
@@ -1603,19 +1646,19 @@ int alloc_buffers(wxb_ctx* ctx, int B, int tok_stride, DecBuffers* o) {
   if (L > MAX_LAYERS) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: %d layers > %d", L, MAX_LAYERS);
   if (d > 4 * LN_V4 * MK_THREADS || d % 64)
     return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: n_text_state=%d unsupported (multiple of 64, <= %d)", d, 4 * LN_V4 * MK_THREADS);
-  o->x = (float*)wxb_named(ctx, nm("dec.x").c_str(), (size_t)B * d * 4);
-  o->att = (__nv_bfloat16*)wxb_named(ctx, nm("dec.att").c_str(), (size_t)B * d * 2);
-  o->xn = (__nv_bfloat16*)wxb_named(ctx, nm("dec.xn").c_str(), (size_t)B * d * 2);
+  o->x = (float*)wxb_named(ctx, nm("dec.x").c_str(), (size_t)MAX_GROUP * d * 4);
+  o->att = (__nv_bfloat16*)wxb_named(ctx, nm("dec.att").c_str(), (size_t)MAX_GROUP * d * 2);
+  o->xn = (__nv_bfloat16*)wxb_named(ctx, nm("dec.xn").c_str(), (size_t)MAX_GROUP * d * 2);
   o->part = (float*)wxb_named(ctx, nm("dec.part").c_str(), PART_FLOATS * 4);
-  o->hid = (__nv_bfloat16*)wxb_named(ctx, nm("dec.hid").c_str(), (size_t)B * 4 * d * 2);
-  o->logits = (float*)wxb_named(ctx, nm("dec.logits").c_str(), (size_t)B * o->ldl * 4);
-  o->apart = (float*)wxb_named(ctx, nm("dec.apart").c_str(), (size_t)2 * 1024 * 66 * 4);
+  o->hid = (__nv_bfloat16*)wxb_named(ctx, nm("dec.hid").c_str(), (size_t)MAX_GROUP * 4 * d * 2);
+  o->logits = (float*)wxb_named(ctx, nm("dec.logits").c_str(), (size_t)MAX_GROUP * o->ldl * 4);
+  o->apart = (float*)wxb_named(ctx, nm("dec.apart").c_str(), (size_t)LAYOUT_GROUPS * GROUP_PIECES * 66 * 4);
   o->sum_lp = (float*)wxb_named(ctx, nm("dec.sum_lp").c_str(), (size_t)B * 4);
   o->self_kv = (__nv_bfloat16*)wxb_named(ctx, nm("dec.self_kv").c_str(), (size_t)L * 2 * B * H * D.n_text_ctx * 64 * 2);
   o->cross_kv = (__nv_bfloat16*)wxb_named(ctx, nm("dec.cross_kv").c_str(), (size_t)L * 2 * B * H * T_AUDIO * 64 * 2);
-  o->ticket = (int*)wxb_named(ctx, nm("dec.ticket").c_str(), (size_t)1024 * 4, true);
-  o->d_pos = (int*)wxb_named(ctx, nm("dec.pos").c_str(), 64);
-  o->bar = (unsigned*)wxb_named(ctx, "dec.bar", 128, true);  // grid-barrier counter, zeroed before every launch
+  o->ticket = (int*)wxb_named(ctx, nm("dec.ticket").c_str(), (size_t)LAYOUT_GROUPS * GROUP_TICKETS * 4, true);
+  o->d_pos = (int*)wxb_named(ctx, nm("dec.pos").c_str(), 64 * WXB_MAX_DEC_GROUPS);            // one 64-byte slot per group
+  o->bar = (unsigned*)wxb_named(ctx, "dec.bar", 128 * WXB_MAX_DEC_GROUPS, true);  // grid-barrier counters (128 bytes apart), zeroed before every launch
   o->tokens = (int*)wxb_named(ctx, nm("dec.tokens").c_str(), (size_t)B * tok_stride * 4);
   o->done = (int*)wxb_named(ctx, nm("dec.done").c_str(), (size_t)B * 4);
   o->rows = (int*)wxb_named(ctx, "dec.rows", (size_t)2 * MAX_GROUP * 4);  // two row lists: a launch may still read the other one
@@ -1664,11 +1707,13 @@ int alloc_buffers(wxb_ctx* ctx, int B, int tok_stride, DecBuffers* o) {
   // 16 MT rows (one map per batch-tile count MT = 1 .. 4: a launch over fewer live rows uses the narrower box); rows >= B
   // are zero-filled by the TMA unit
   const size_t n_maps = (size_t)TM_PER_LAYER * L + TM_TAIL_COUNT;
-  CUtensorMap* maps = (CUtensorMap*)wxb_named(ctx, nm("dec.maps").c_str(), n_maps * sizeof(CUtensorMap));
+  CUtensorMap* maps = (CUtensorMap*)wxb_named(ctx, nm("dec.maps").c_str(), LAYOUT_GROUPS * n_maps * sizeof(CUtensorMap));
   if (!maps) return WXB_ERR_CUDA;
+  o->n_maps = n_maps;
   wxb_dec_maps_key& key = ctx->dec_maps_key;
-  if (key.model != (const void*)ctx->model || key.xn != o->xn || key.att != o->att || key.hid != o->hid || key.ckv != o->cross_kv || key.B != B) {
-    std::vector<CUtensorMap> h(n_maps);
+  if (key.model != (const void*)ctx->model || key.xn != o->xn || key.att != o->att || key.hid != o->hid || key.ckv != o->cross_kv || key.B != B ||
+      key.groups != LAYOUT_GROUPS) {
+    std::vector<CUtensorMap> h(LAYOUT_GROUPS * n_maps);
     int rc;
     for (int l = 0; l < L; ++l) {
       DecLayerW w;
@@ -1684,18 +1729,31 @@ int alloc_buffers(wxb_ctx* ctx, int B, int tok_stride, DecBuffers* o) {
     if (!emb) return WXB_ERR_STATE;
     CUtensorMap* am = &h[(size_t)TM_PER_LAYER * L];
     if ((rc = wxb_make_tmap_bf16(ctx, am + TM_EMB, emb, (uint64_t)d, (uint64_t)V, (uint64_t)d * 2, GV_BK, GV_ROWS)) != WXB_OK) return rc;
-    for (int mt = 1; mt <= 4; ++mt) {
+    for (int mt = 1; mt <= GV_MAX_MT; ++mt) {  // region 0; the other regions' activation maps are made below
       CUtensorMap* a3 = am + TM_ACT + (mt - 1) * 3;
-      if ((rc = wxb_make_tmap_bf16(ctx, a3 + 0, o->xn, (uint64_t)d, (uint64_t)B, (uint64_t)d * 2, GV_BK, 16 * mt)) != WXB_OK) return rc;
-      if ((rc = wxb_make_tmap_bf16(ctx, a3 + 1, o->att, (uint64_t)d, (uint64_t)B, (uint64_t)d * 2, GV_BK, 16 * mt)) != WXB_OK) return rc;
-      if ((rc = wxb_make_tmap_bf16(ctx, a3 + 2, o->hid, (uint64_t)4 * d, (uint64_t)B, (uint64_t)4 * d * 2, GV_BK, 16 * mt)) != WXB_OK) return rc;
+      if ((rc = wxb_make_tmap_bf16(ctx, a3 + 0, o->xn, (uint64_t)d, (uint64_t)GROUP_ROWS, (uint64_t)d * 2, GV_BK, 16 * mt)) != WXB_OK) return rc;
+      if ((rc = wxb_make_tmap_bf16(ctx, a3 + 1, o->att, (uint64_t)d, (uint64_t)GROUP_ROWS, (uint64_t)d * 2, GV_BK, 16 * mt)) != WXB_OK) return rc;
+      if ((rc = wxb_make_tmap_bf16(ctx, a3 + 2, o->hid, (uint64_t)4 * d, (uint64_t)GROUP_ROWS, (uint64_t)4 * d * 2, GV_BK, 16 * mt)) != WXB_OK) return rc;
     }
     // cross K/V of all layers as one [rows, 64] tensor read in full-stage boxes (shorter boxes at the end of an item)
     if ((rc = wxb_make_tmap_bf16(ctx, am + TM_KV, o->cross_kv, 64, (uint64_t)L * 2 * B * H * T_AUDIO, 128, 64, XA_KEYS)) != WXB_OK) return rc;
     if ((rc = wxb_make_tmap_bf16(ctx, am + TM_KV + 1, o->cross_kv, 64, (uint64_t)L * 2 * B * H * T_AUDIO, 128, 64, XA_TAIL)) != WXB_OK) return rc;
+    // the tables of regions 1 ..: the same weight / K/V maps, activation maps over the region's rows (rows past the region are
+    // zero-filled by the TMA unit; rows past a launch's live rows hold stale values whose products are never stored)
+    for (int g = 1; g < LAYOUT_GROUPS; ++g) {
+      for (size_t i = 0; i < n_maps; ++i) h[g * n_maps + i] = h[i];
+      CUtensorMap* amg = &h[g * n_maps + (size_t)TM_PER_LAYER * L];
+      const size_t r0 = (size_t)g * GROUP_ROWS;
+      for (int mt = 1; mt <= GV_MAX_MT; ++mt) {
+        CUtensorMap* a3 = amg + TM_ACT + (mt - 1) * 3;
+        if ((rc = wxb_make_tmap_bf16(ctx, a3 + 0, o->xn + r0 * d, (uint64_t)d, (uint64_t)GROUP_ROWS, (uint64_t)d * 2, GV_BK, 16 * mt)) != WXB_OK) return rc;
+        if ((rc = wxb_make_tmap_bf16(ctx, a3 + 1, o->att + r0 * d, (uint64_t)d, (uint64_t)GROUP_ROWS, (uint64_t)d * 2, GV_BK, 16 * mt)) != WXB_OK) return rc;
+        if ((rc = wxb_make_tmap_bf16(ctx, a3 + 2, o->hid + r0 * 4 * d, (uint64_t)4 * d, (uint64_t)GROUP_ROWS, (uint64_t)4 * d * 2, GV_BK, 16 * mt)) != WXB_OK) return rc;
+      }
+    }
     WXB_CUDA(ctx, cudaDeviceSynchronize());  // a previous decode may still be reading the old table
-    WXB_CUDA(ctx, cudaMemcpy(maps, h.data(), n_maps * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
-    key.model = ctx->model; key.xn = o->xn; key.att = o->att; key.hid = o->hid; key.ckv = o->cross_kv; key.B = B;
+    WXB_CUDA(ctx, cudaMemcpy(maps, h.data(), LAYOUT_GROUPS * n_maps * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    key.model = ctx->model; key.xn = o->xn; key.att = o->att; key.hid = o->hid; key.ckv = o->cross_kv; key.B = B; key.groups = LAYOUT_GROUPS;
   }
   o->maps = maps;
   return WXB_OK;
@@ -1719,39 +1777,70 @@ int cross_kv_precompute(wxb_ctx* ctx, const __nv_bfloat16* enc_out, const DecBuf
   return WXB_OK;
 }
 
-// Launch the persistent step kernel: n_steps consecutive positions starting at *d_pos, over the n_live rows listed in
-// rows_dev (original row numbers; nullptr = all buf.B rows).
-int launch_steps(wxb_ctx* ctx, const DecBuffers& buf, int mode, int n_steps, const SampleParams& sp, float* logits_out,
-                 long long ldl, int n_live, const int* rows_dev, cudaStream_t st) {
+// Sequence groups of a launch over n_live rows: group g takes rows [lo[g], lo[g + 1]) of the live list.
+struct GroupSplit {
+  int G;
+  int lo[WXB_MAX_DEC_GROUPS + 1];
+};
+int split_groups(wxb_ctx* ctx, int n_live, GroupSplit* gs) {
+  int G = (LAYOUT_GROUPS >= 2 && n_live >= 2 * DEC_GROUP_MIN_ROWS) ? 2 : 1;
+  if (ctx->dec_groups_override > 0) G = ctx->dec_groups_override;
+  G = std::max(1, std::min(std::min(G, LAYOUT_GROUPS), n_live));
+  while (G < LAYOUT_GROUPS && ceil_div(n_live, G) > GROUP_ROWS) ++G;
+  if (ceil_div(n_live, G) > GROUP_ROWS)
+    return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: %d rows do not fit %d sequence group(s) of %d rows", n_live, G, GROUP_ROWS);
+  gs->G = G;
+  for (int g = 0; g <= G; ++g) gs->lo[g] = (int)((long long)n_live * g / G);
+  return WXB_OK;
+}
+
+// The row lists of a launch: group g's live rows (original row numbers) at rows_base + g * GROUP_ROWS.
+int upload_rows(wxb_ctx* ctx, const GroupSplit& gs, const int* live_host, int* rows_base, cudaStream_t st) {
+  for (int g = 0; g < gs.G; ++g)
+    WXB_CUDA(ctx, cudaMemcpyAsync(rows_base + g * GROUP_ROWS, live_host + gs.lo[g], (size_t)(gs.lo[g + 1] - gs.lo[g]) * 4,
+                                  cudaMemcpyHostToDevice, st));
+  return WXB_OK;
+}
+
+// Launch the persistent step kernel for ONE sequence group: n_steps consecutive positions starting at *d_pos, over the B live
+// rows listed in rows_dev (original row numbers), in activation region `region`.
+int launch_group(wxb_ctx* ctx, const DecBuffers& buf, int region, int mode, int n_steps, const SampleParams& sp, float* logits_out,
+                 long long ldl, int B, const int* rows_dev, unsigned delay_ns, cudaStream_t st) {
   const wxb_dims& D = ctx->model->dims;
-  const int d = D.n_text_state, B = n_live;
+  const int d = D.n_text_state;
   const int Bp = (B + 15) & ~15, MT = Bp / 16;
   int G = ctx->sm_count;
 #ifdef WXB_PROBE
   if (const char* e = getenv("WXB_DEC_GRID")) { const int g = atoi(e); if (g > 0 && g < G) G = g; }  // timing probe: narrower grid
 #endif
+  const size_t r0 = (size_t)region * GROUP_ROWS;
   MkParams p = {};
   p.B = B; p.B0 = buf.B; p.rows = rows_dev;
   p.d = d; p.H = D.n_text_head; p.L = D.n_text_layer; p.V = D.n_vocab; p.TX = D.n_text_ctx;
-  p.mode = mode; p.n_steps = n_steps; p.skip = dec_skip_mask();
-  p.layers = buf.layers; p.maps = buf.maps;
+  p.mode = mode; p.n_steps = n_steps; p.skip = dec_skip_mask(); p.delay_ns = delay_ns;
+  p.layers = buf.layers; p.maps = buf.maps + (size_t)region * buf.n_maps;
   p.emb = (const __nv_bfloat16*)wxb_weight(ctx, "dec.emb");
   p.pos_emb = (const float*)wxb_weight(ctx, "dec.pos");
   p.lnf_w = (const float*)wxb_weight(ctx, "dec.ln.w");
   p.lnf_b = (const float*)wxb_weight(ctx, "dec.ln.b");
   if (!p.emb || !p.pos_emb || !p.lnf_w || !p.lnf_b) return WXB_ERR_STATE;
-  p.tokens = buf.tokens; p.tok_stride = buf.tok_stride; p.d_pos = buf.d_pos;
-  p.x = buf.x; p.xn = buf.xn; p.att = buf.att; p.hid = buf.hid; p.part = buf.part;
+  p.tokens = buf.tokens; p.tok_stride = buf.tok_stride; p.d_pos = buf.d_pos + 16 * region;
+  p.x = buf.x + r0 * d; p.xn = buf.xn + r0 * d; p.att = buf.att + r0 * d; p.hid = buf.hid + r0 * 4 * d;
+  p.part = buf.part + (size_t)region * GROUP_PART_FLOATS;
   p.self_kv = buf.self_kv; p.cross_kv = buf.cross_kv;
   p.logits = logits_out; p.ldl = ldl;
-  p.apart = buf.apart; p.ticket = buf.ticket; p.bar = buf.bar;
+  p.apart = buf.apart + (size_t)region * GROUP_PIECES * 66; p.ticket = buf.ticket + region * GROUP_TICKETS; p.bar = buf.bar + 32 * region;
   p.qlog = buf.qlog; p.qhead = buf.qhead; p.qA = buf.qA;
-  if (buf.qlog) { ctx->qlog_pos += n_steps; ctx->qlog_valid = true; }
   if (dec_prof_enabled()) {
-    p.prof = (unsigned long long*)wxb_named(ctx, "dec.prof", PROF_SLOTS * 8);
-    if ((size_t)n_steps * (11 * p.L + 4) > PROF_SLOTS) p.prof = nullptr;
-    g_prof_last.mode = mode; g_prof_last.n_steps = n_steps; g_prof_last.L = p.L; g_prof_last.nsp = sp.nsp_out != nullptr;
-    g_prof_last.dev = p.prof;
+    unsigned long long* base = (unsigned long long*)wxb_named(ctx, "dec.prof", LAYOUT_GROUPS * PROF_SLOTS * 8);
+    p.prof = base ? base + (size_t)region * PROF_SLOTS : nullptr;
+    if ((size_t)n_steps * (11 * p.L + 4) + 2 > PROF_SLOTS) p.prof = nullptr;
+    if (region == 0) {
+      g_prof_last.mode = mode; g_prof_last.n_steps = n_steps; g_prof_last.L = p.L; g_prof_last.nsp = sp.nsp_out != nullptr;
+      g_prof_last.dev = p.prof; g_prof_last.groups = 1;
+    } else {
+      g_prof_last.groups = region + 1;
+    }
   }
   p.g_qkv = plan_gemv(3 * d, d, B, Bp, G, false);
   p.g_dd = plan_gemv(d, d, B, Bp, G, false);
@@ -1761,16 +1850,20 @@ int launch_steps(wxb_ctx* ctx, const DecBuffers& buf, int mode, int n_steps, con
   if (!p.g_qkv.gk || !p.g_dd.gk || !p.g_fc1.gk || !p.g_fc2.gk || !p.g_logits.gk)
     return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: no GEMV tiling fits (d=%d, batch %d)", d, B);
   p.sp = sp;
+  if (p.sp.logits) p.sp.logits += r0 * (size_t)p.sp.ldl;  // the sampling phase reads the group's rows of the scratch logits
   p.scale = 1.0f / sqrtf(64.f);
-  void (*kern)(const MkParams) = MT == 1 ? dec_step_kernel<1> : MT == 2 ? dec_step_kernel<2> : MT == 3 ? dec_step_kernel<3> : dec_step_kernel<4>;
+  if (MT > GV_MAX_MT) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: %d rows in one sequence group (at most %d)", B, 16 * GV_MAX_MT);
+  void (*kern)(const MkParams) = MT == 1 ? dec_step_kernel<1> : dec_step_kernel<2>;
+  if (GV_MAX_MT > 2 && MT > 2) kern = MT == 3 ? dec_step_kernel<GV_MAX_MT < 3 ? 1 : 3> : dec_step_kernel<GV_MAX_MT < 4 ? 1 : 4>;
   if (ctx->func_smem.find(reinterpret_cast<const void*>(kern)) == ctx->func_smem.end()) {
     int rc = wxb_func_smem(ctx, kern, (int)MK_SMEM);
     if (rc != WXB_OK) return rc;
+    if (MK_CTAS_PER_SM > 1)  // two instances share an SM: leave the whole configurable array to shared memory
+      WXB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 0;
     WXB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MK_THREADS, MK_SMEM));
     if (per_sm < 1) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: persistent step kernel does not fit an SM");
   }
-  WXB_CUDA(ctx, cudaMemsetAsync(buf.bar, 0, 4, st));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(G);
   cfg.blockDim = dim3(MK_THREADS);
@@ -1780,10 +1873,50 @@ int launch_steps(wxb_ctx* ctx, const DecBuffers& buf, int mode, int n_steps, con
   attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident: the grid barrier cannot deadlock
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
+#ifdef WXB_DEC_NO_COOP
+  cfg.numAttrs = 0;
+#else
   cfg.numAttrs = 1;
+#endif
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
   ctx->launches++;
   if (e != cudaSuccess) return wxb_fail(ctx, WXB_ERR_CUDA, "decoder step launch failed: %s", cudaGetErrorString(e));
+  return WXB_OK;
+}
+
+// One launch round: every sequence group of the split runs n_steps positions, group 0 on the caller's stream, the others on side
+// streams forked from it and joined back, so that the caller's stream order covers all of them.  rows_base: the row lists written
+// by upload_rows.  by_row: logits_out is indexed by the ORIGINAL row (teacher-forced logits with all rows live); otherwise it is the
+// scratch indexed by region row.
+int launch_groups(wxb_ctx* ctx, const DecBuffers& buf, const GroupSplit& gs, int mode, int n_steps, const SampleParams& sp,
+                  float* logits_out, long long ldl, bool by_row, const int* rows_base, cudaStream_t st) {
+  WXB_CUDA(ctx, cudaMemsetAsync(buf.bar, 0, 128 * WXB_MAX_DEC_GROUPS, st));
+  if (buf.qlog) { ctx->qlog_pos += n_steps; ctx->qlog_valid = true; }
+  if (gs.G > 1) {
+    if (!ctx->dec_fork) WXB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->dec_fork, cudaEventDisableTiming));
+    WXB_CUDA(ctx, cudaEventRecord(ctx->dec_fork, st));
+  }
+  int rc;
+  for (int g = 0; g < gs.G; ++g) {
+    cudaStream_t sg = st;
+    if (g > 0) {
+      if (!ctx->dec_side[g - 1]) {
+        WXB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->dec_side[g - 1], cudaStreamNonBlocking));
+        WXB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->dec_join[g - 1], cudaEventDisableTiming));
+      }
+      sg = ctx->dec_side[g - 1];
+      WXB_CUDA(ctx, cudaStreamWaitEvent(sg, ctx->dec_fork, 0));
+    }
+    const size_t lrow = by_row ? (size_t)gs.lo[g] : (size_t)g * GROUP_ROWS;
+    const unsigned delay = (unsigned)((long long)ctx->dec_group_delay_ns * g / gs.G);
+    if ((rc = launch_group(ctx, buf, g, mode, n_steps, sp, logits_out + lrow * (size_t)ldl, ldl, gs.lo[g + 1] - gs.lo[g],
+                           rows_base + g * GROUP_ROWS, delay, sg)) != WXB_OK)
+      return rc;
+    if (g > 0) {
+      WXB_CUDA(ctx, cudaEventRecord(ctx->dec_join[g - 1], sg));
+      WXB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->dec_join[g - 1], 0));
+    }
+  }
   return WXB_OK;
 }
 
@@ -1814,6 +1947,27 @@ int dump_prof(wxb_ctx* ctx) {
   static const char* tn[4] = {"lnf", "logits", "sample", "x"};
   for (int i = 11; i < 15; ++i) if (cnt[i]) fprintf(stderr, " %s %.2f", tn[i - 11], sum[i] / cnt[i]);
   fprintf(stderr, " | step %.1f us\n", (double)(t[n - 1] - t[0]) * 1e-3 / P.n_steps);
+  for (int g = 1; g < P.groups; ++g) {
+    // the other sequence groups' instances: how far behind group 0 they pass the same barriers, and where their CTA 0 ran
+    std::vector<unsigned long long> u(n);
+    unsigned long long meta[2][2];
+    WXB_CUDA(ctx, cudaMemcpy(u.data(), P.dev + (size_t)g * PROF_SLOTS, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    WXB_CUDA(ctx, cudaMemcpy(meta[0], P.dev + PROF_SLOTS - 2, 16, cudaMemcpyDeviceToHost));
+    WXB_CUDA(ctx, cudaMemcpy(meta[1], P.dev + (size_t)g * PROF_SLOTS + PROF_SLOTS - 2, 16, cudaMemcpyDeviceToHost));
+    double lag_cross_in = 0, lag_cross_out = 0;
+    long c = 0;
+    for (int s = 0; s < P.n_steps; ++s)
+      for (int l = 0; l < P.L; ++l) {
+        const int k = s * per_step + l * 11 + 5;  // barrier after cq = start of the cross-attention phase
+        if (k + 1 >= n) continue;
+        lag_cross_in += (double)((long long)(u[k] - t[k])) * 1e-3;
+        lag_cross_out += (double)((long long)(u[k + 1] - t[k + 1])) * 1e-3;
+        ++c;
+      }
+    fprintf(stderr, "[wxb dec prof] group %d: CTA 0 on SM %llu (group 0: SM %llu), started %.1f us after group 0, enters / leaves cross-attention %.1f / %.1f us after group 0, ends %.1f us after\n",
+            g, meta[1][1], meta[0][1], (double)((long long)(meta[1][0] - meta[0][0])) * 1e-3, c ? lag_cross_in / c : 0.0,
+            c ? lag_cross_out / c : 0.0, (double)((long long)(u[n - 1] - t[n - 1])) * 1e-3);
+  }
   return WXB_OK;
 }
 
@@ -1868,7 +2022,8 @@ extern "C" int wxb_decode_greedy(wxb_ctx* ctx, const void* enc_out_dev, int B, c
   for (int b = 0; b < B; ++b)
     for (int i = 0; i < prompt_len; ++i) init[(size_t)b * stride + i] = prompt_host[i];
   WXB_CUDA(ctx, cudaMemcpyAsync(buf.tokens, init.data(), (size_t)B * stride * 4, cudaMemcpyHostToDevice, st));
-  WXB_CUDA(ctx, cudaMemsetAsync(buf.d_pos, 0, 4, st));
+  int pos_host[16 * WXB_MAX_DEC_GROUPS] = {};  // one 64-byte slot per region
+  WXB_CUDA(ctx, cudaMemsetAsync(buf.d_pos, 0, 64 * WXB_MAX_DEC_GROUPS, st));
   WXB_CUDA(ctx, cudaMemsetAsync(buf.done, 0, (size_t)B * 4, st));
   WXB_CUDA(ctx, cudaMemsetAsync(buf.sum_lp, 0, (size_t)B * 4, st));
   WXB_CUDA(ctx, cudaMemsetAsync(buf.ts_last, 0xff, (size_t)MAX_GROUP * 4, st));  // -1: no timestamp sampled yet
@@ -1884,28 +2039,32 @@ extern "C" int wxb_decode_greedy(wxb_ctx* ctx, const void* enc_out_dev, int B, c
   if (tm) WXB_CUDA(ctx, cudaEventRecord(tm->e1, st));
 
   const bool want_nsp = (opts->no_speech >= 0 && no_speech_prob_dev);
+  std::vector<int> done_host(B), live(B);
+  for (int b = 0; b < B; ++b) live[b] = b;
+  int n_live = B, n_sampled = 0, flip = 0;
+  GroupSplit gs;
+  if ((rc = split_groups(ctx, n_live, &gs)) != WXB_OK) return rc;
+  int* rows_dev = buf.rows;
+  if ((rc = upload_rows(ctx, gs, live.data(), rows_dev, st)) != WXB_OK) return rc;
   // prompt positions 0 .. prompt_len-2 (forced tokens); logits only at position 0 for no_speech_prob
   for (int pos = 0; pos < prompt_len - 1; ++pos) {
     SampleParams s1 = sp;
     const bool nsp = (pos == 0 && want_nsp);
     if (nsp) s1.nsp_out = no_speech_prob_dev;
-    if ((rc = launch_steps(ctx, buf, nsp ? 1 : 0, 1, s1, buf.logits, buf.ldl, B, nullptr, st)) != WXB_OK) return rc;
+    if ((rc = launch_groups(ctx, buf, gs, nsp ? 1 : 0, 1, s1, buf.logits, buf.ldl, false, rows_dev, st)) != WXB_OK) return rc;
   }
   // Sampling loop.  Every `check_every` positions the host reads the EOT flags (mlx_whisper_batch_decoder.py:357) and the
   // next launch runs over the rows that are still live (:37-100: finished sequences leave the batch; their K/V slabs are
-  // no longer streamed and their GEMV / LayerNorm / attention work disappears).
+  // no longer streamed and their GEMV / LayerNorm / attention work disappears); the live rows are dealt to the sequence
+  // groups anew.
   const int check_every = opts->check_every > 0 ? opts->check_every : 16;
-  std::vector<int> done_host(B), live(B);
-  for (int b = 0; b < B; ++b) live[b] = b;
-  int n_live = B, n_sampled = 0, flip = 0;
-  const int* rows_dev = nullptr;  // identity
   while (n_sampled < sample_len) {
     // a single-token prompt makes the SOT position the first sampling position: that step also emits no_speech_prob
     const bool nsp_now = (n_sampled == 0 && prompt_len == 1 && want_nsp);
     const int n = nsp_now ? 1 : std::min(check_every, sample_len - n_sampled);
     SampleParams s1 = sp;
     if (nsp_now) s1.nsp_out = no_speech_prob_dev;
-    if ((rc = launch_steps(ctx, buf, 2, n, s1, buf.logits, buf.ldl, n_live, rows_dev, st)) != WXB_OK) return rc;
+    if ((rc = launch_groups(ctx, buf, gs, 2, n, s1, buf.logits, buf.ldl, false, rows_dev, st)) != WXB_OK) return rc;
     n_sampled += n;
     if (n_sampled < sample_len && !nsp_now) {
       WXB_CUDA(ctx, cudaMemcpyAsync(done_host.data(), buf.done, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
@@ -1916,10 +2075,14 @@ extern "C" int wxb_decode_greedy(wxb_ctx* ctx, const void* enc_out_dev, int B, c
       if (m == 0) break;  // every row has emitted EOT
       if (m < n_live && !opts->no_compaction) {
         n_live = m;
-        int* dst = buf.rows + (flip ? MAX_GROUP : 0);
+        // the position counter of every region a later split may use: all groups have advanced to the same position
+        const int pos_now = prompt_len - 1 + n_sampled;
+        for (int g = 0; g < LAYOUT_GROUPS; ++g) pos_host[16 * g] = pos_now;
+        WXB_CUDA(ctx, cudaMemcpyAsync(buf.d_pos, pos_host, sizeof(pos_host), cudaMemcpyHostToDevice, st));
+        if ((rc = split_groups(ctx, n_live, &gs)) != WXB_OK) return rc;
         flip ^= 1;
-        WXB_CUDA(ctx, cudaMemcpyAsync(dst, live.data(), (size_t)n_live * 4, cudaMemcpyHostToDevice, st));
-        rows_dev = dst;
+        rows_dev = buf.rows + (flip ? MAX_GROUP : 0);
+        if ((rc = upload_rows(ctx, gs, live.data(), rows_dev, st)) != WXB_OK) return rc;
       }
     }
   }
@@ -1992,10 +2155,16 @@ extern "C" int wxb_decoder_logits(wxb_ctx* ctx, const void* enc_out_dev, int B, 
   int rc;
   if ((rc = alloc_buffers(ctx, B, n_tok, &buf)) != WXB_OK) return rc;
   WXB_CUDA(ctx, cudaMemcpyAsync(buf.tokens, tokens_host, (size_t)B * n_tok * 4, cudaMemcpyHostToDevice, st));
-  WXB_CUDA(ctx, cudaMemsetAsync(buf.d_pos, 0, 4, st));
+  WXB_CUDA(ctx, cudaMemsetAsync(buf.d_pos, 0, 64 * WXB_MAX_DEC_GROUPS, st));
   if ((rc = cross_kv_precompute(ctx, (const __nv_bfloat16*)enc_out_dev, buf, st)) != WXB_OK) return rc;
+  std::vector<int> live(B);
+  for (int b = 0; b < B; ++b) live[b] = b;
+  GroupSplit gs;
+  if ((rc = split_groups(ctx, B, &gs)) != WXB_OK) return rc;
+  if ((rc = upload_rows(ctx, gs, live.data(), buf.rows, st)) != WXB_OK) return rc;
+  WXB_CUDA(ctx, cudaStreamSynchronize(st));  // `live` is pageable host memory
   SampleParams sp = {};
   for (int pos = 0; pos < n_tok; ++pos)
-    if ((rc = launch_steps(ctx, buf, 1, 1, sp, logits_out_dev + (size_t)pos * D.n_vocab, (long long)n_tok * D.n_vocab, B, nullptr, st)) != WXB_OK) return rc;
+    if ((rc = launch_groups(ctx, buf, gs, 1, 1, sp, logits_out_dev + (size_t)pos * D.n_vocab, (long long)n_tok * D.n_vocab, true, buf.rows, st)) != WXB_OK) return rc;
   return WXB_OK;
 }
