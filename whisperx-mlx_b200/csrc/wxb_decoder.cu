@@ -37,6 +37,7 @@
 #include "wxb_model.cuh"
 #include "wxb_tc.cuh"
 #include <math.h>
+#include <type_traits>
 #include <stdlib.h>
 #include <string.h>
 
@@ -90,10 +91,6 @@ constexpr int QRAW_ROWS = GK_MAX + 1;                     // bias row + up to GK
 constexpr int QRAW_BYTES = 2 * QRAW_ROWS * 64 * 4;        // two items in flight
 constexpr int SCRATCH_BYTES = SST_BYTES + QRAW_BYTES;     // attention scratch behind the ring
 constexpr int XA_NST = MK_WARPS == 8 ? 6 : MK_WARPS == 10 ? 5 : 4;  // K/V ring depth (stages of 2 x 16 XA_CW keys x 128 B)
-#ifndef WXB_XA_NS
-#define WXB_XA_NS 1
-#endif
-constexpr int XA_NS = WXB_XA_NS;             // K/V stages per consumer iteration
 constexpr int GV_NST = MK_CTAS_PER_SM == 2 ? 4 : 6;  // GEMV ring depth
 #ifndef WXB_GV_NACC
 #define WXB_GV_NACC 1
@@ -111,6 +108,11 @@ static_assert(GV_NST * (GV_A_BYTES + 16 * GV_MAX_MT * GV_BK * 2) <= RING_BYTES, 
 static_assert(MK_CTAS_PER_SM * (MK_SMEM + 10 * 1024) <= 228 * 1024, "shared memory of the CTAs that share an SM (dynamic + ~9 KB static + 1 KB reserved each)");
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float ex2_approx(float x) {  // 2^x, -inf -> 0, no range fix-up (arguments are <= XA_LAZY)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -123,10 +125,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // operator that does not depend on this one (requesting its weight / K/V tiles), so that HBM latency is spent
 // while the barrier completes.  With `prof` set, CTA 0 records the global timer at every barrier exit.
 template <class Pre>
-__device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& target, int nc, int cta, unsigned long long* prof, Pre pre) {
+__device__ __forceinline__ void grid_sync(unsigned* bar, const unsigned index, int nc, int cta, unsigned long long* prof, Pre pre) {
+  // index: number of this barrier within the launch (1 ..); the counter has reached index * nc once every CTA has arrived.  The
+  // target is derived from the schedule position instead of being carried in a register through every phase.
   __syncthreads();
   if (threadIdx.x == 0) {
-    target += (unsigned)nc;
+    const unsigned target = index * (unsigned)nc;
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
     unsigned v;
     unsigned spins = 0;
@@ -138,7 +142,7 @@ __device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& target, int n
     if (prof && cta == 0) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      prof[target / (unsigned)nc - 1u] = t;  // barrier index within the launch
+      prof[index - 1u] = t;  // barrier index within the launch
     }
   } else if (threadIdx.x == 32) {
     pre();
@@ -225,13 +229,15 @@ enum {
   MB_GV_FULL = 0,    // [6] TMA -> MMA
   MB_GV_EMPTY = 6,   // [6] MMA (tcgen05.commit / 8 warp arrivals) -> TMA
   MB_ACC_FULL = 12,  // [1] MMA -> epilogue
-  MB_XA_FULL = 13,   // [6] TMA -> attention warps
-  MB_XA_EMPTY = 19,  // [6] 7 consumer-warp arrivals -> producer
-  MB_ST_FULL = 25,   // [2] 7 warp states of an item deposited -> merging warp
-  MB_ST_FREE = 27,   // [2] merging warp -> writers of the item after next
-  MB_Q_FULL = 29,    // [2] raw q rows of an item landed (cp.async arrive-on of the 32 producer lanes)
-  MB_Q_FREE = 31,    // [2] 7 consumer warps have built their q fragments
-  MB_COUNT = 33
+  MB_XK_FULL = 13,   // [6] TMA -> attention warps: the K half of a stage has landed
+  MB_XK_EMPTY = 19,  // [6] consumer-warp arrivals -> producer: the K half has been read
+  MB_XV_FULL = 25,   // [6] the V half of a stage (read one iteration later than its K half, released on its own)
+  MB_XV_EMPTY = 31,  // [6]
+  MB_ST_FULL = 37,   // [2] warp states of an item deposited -> merging warp
+  MB_ST_FREE = 39,   // [2] merging warp -> writers of the item after next
+  MB_Q_FULL = 41,    // [2] raw q rows of an item landed (cp.async arrive-on of the 32 producer lanes)
+  MB_Q_FREE = 43,    // [2] consumer warps have built their q fragments
+  MB_COUNT = 45
 };
 struct MkSync {
   uint32_t bars;       // shared-memory address of the barrier array
@@ -716,7 +722,9 @@ __device__ __forceinline__ void self_attn_phase(const MkParams& p, int l, const 
     // The sharing factor W and this warp's share are derived twice (before and after the key loop, the second time from an
     // opaque copy of n_units so that the compiler does not keep them live across it): the persistent kernel has no register
     // to spare (DESIGN.md "Stack frames").
-    int u0 = round * n_warps + sy.cta * MK_WARPS + warp, k0 = 0, k1 = pos;
+    // solo units are dealt round-robin over the CTAs (unit u of a round: CTA u % nc, warp u / nc): 1200 units occupy 8 - 9 warps
+    // of EVERY SM instead of all 12 warps of the first 100, so the latency-bound key loops run on all SMs' load paths
+    int u0 = round * n_warps + warp * sy.nc + sy.cta, k0 = 0, k1 = pos;
     bool first = true;
     if (coop) {
       const int W = sa_share(n_units, n_warps), wi = warp % W;
@@ -892,19 +900,17 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, int x
       if (kk == x.k0) stage_q(it);  // first stage of an item: its raw q rows
       if (lane == 0 && (int)(issued - xa_count0) >= sy.pre) {  // the first sy.pre stages were requested before the barrier wait
         const uint32_t sl = issued % XA_NST, par = (issued / XA_NST) & 1;
-        mbar_wait(sy.mb(MB_XA_EMPTY + sl), par ^ 1);
         const bool tail = (x.k1 - kk <= XA_TAIL);  // keys past the item (or the tensor: zero-filled) are masked by the consumer
         const CUtensorMap* m = tail ? kvmap + 1 : kvmap;
         uint8_t* dst = ring + (size_t)sl * STAGE;
-        mbar_arrive_expect_tx(sy.mb(MB_XA_FULL + sl), tail ? 2 * XA_TAIL * 128 : STAGE);
         const int slab_ld = WXB_SKIP(skip, 64) ? (oslab & 3) : oslab;  // probe: every CTA streams the same 4 slabs (all L2 hits)
-        if (WXB_SKIP(skip, 64)) {
-          tma_load_2d(dst, m, sy.mb(MB_XA_FULL + sl), 0, krow0 + slab_ld * T_AUDIO + kk);
-          tma_load_2d(dst + XA_HALF, m, sy.mb(MB_XA_FULL + sl), 0, vrow0 + slab_ld * T_AUDIO + kk);
-        } else {
-        tma_load_2d_hint(dst, m, sy.mb(MB_XA_FULL + sl), 0, krow0 + oslab * T_AUDIO + kk, L2_EVICT_FIRST);
-        tma_load_2d_hint(dst + XA_HALF, m, sy.mb(MB_XA_FULL + sl), 0, vrow0 + oslab * T_AUDIO + kk, L2_EVICT_FIRST);
-        }
+        const uint32_t half_tx = tail ? XA_TAIL * 128 : XA_HALF;
+        mbar_wait(sy.mb(MB_XK_EMPTY + sl), par ^ 1);
+        mbar_arrive_expect_tx(sy.mb(MB_XK_FULL + sl), half_tx);
+        tma_load_2d_hint(dst, m, sy.mb(MB_XK_FULL + sl), 0, krow0 + slab_ld * T_AUDIO + kk, L2_EVICT_FIRST);
+        mbar_wait(sy.mb(MB_XV_EMPTY + sl), par ^ 1);
+        mbar_arrive_expect_tx(sy.mb(MB_XV_FULL + sl), half_tx);
+        tma_load_2d_hint(dst + XA_HALF, m, sy.mb(MB_XV_FULL + sl), 0, vrow0 + slab_ld * T_AUDIO + kk, L2_EVICT_FIRST);
       }
       __syncwarp();
       ++issued;
@@ -919,18 +925,25 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, int x
     // ------------------------------- consumer warps -------------------------------
     const int cw = warp - 1;
     // ldmatrix lane addressing inside a 112-row x 128-byte swizzled tile (chunk' = chunk ^ (row & 7)); this warp's rows 16 cw ..
-    const int rowA = cw * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, chA = lane >> 4;         // K (non-transposed): chunk 2 j + chA
-    const int rowV = cw * 16 + (lane & 7) + ((lane >> 4) & 1) * 8, chV = (lane >> 3) & 1;   // V (transposed): chunk 2 mt + chV
+    // K (non-transposed): row 16 cw + (lane & 7) + 8 ((lane >> 3) & 1), 16-byte chunk 2 j + (lane >> 4); V (transposed): row
+    // 16 cw + (lane & 7) + 8 ((lane >> 4) & 1), chunk 2 mt + ((lane >> 3) & 1).  With sw = lane & 7 the swizzled chunk is
+    // (2 j + c) ^ sw = ((j ^ (sw >> 1)) << 1) | (c ^ (sw & 1)): the lane's byte offset for j = 0 is kept, fragment j is at
+    // (stage base + offset) ^ (j << 5) (stage bases are multiples of 1024, so bits 4 .. 6 come from the chunk alone).
     const int sw = lane & 7;
+    const uint32_t laneK = (uint32_t)((cw * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * 128 + ((((lane >> 4) & 1) ^ sw) << 4));
+    const uint32_t laneV = (uint32_t)((cw * 16 + (lane & 7) + ((lane >> 4) & 1) * 8) * 128 + ((((lane >> 3) & 1) ^ sw) << 4));
     uint32_t consumed = xa_count0;
     for (int it = 0; it < n_items; ++it) {
+      float qn0, qn1;
+      int xk0, xk1;  // key range of the item
+      {
       const XaItem x = xa_item(it, cta, qw, G, P, plen, n_items - qw);
+      xk0 = x.k0; xk1 = x.k1;
       const int b = x.slab / H, h = x.slab - b * H;
       const uint32_t gi = xa_items0 + (uint32_t)it;  // items since kernel start: parity and phase of the double-buffered slots
       const uint32_t ipar = gi & 1, iph = (gi >> 1) & 1;
       // scaled q = (bias + split-K partials in slice order) * scale; lane holds dims lane and lane + 32
       mbar_wait(sy.mb(MB_Q_FULL + ipar), iph);
-      float qn0, qn1;
       {
         const float* qr = qraw + ipar * (QRAW_ROWS * 64);
         float a0 = qr[gk * 64 + lane], a1 = qr[gk * 64 + lane + 32];
@@ -949,11 +962,13 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, int x
           ql[lane + 32] = qn1;
         }
       }
-      // B fragments of q: lane (g, t) holds elements 16 j + 2 t + {0, 1} and + {8, 9}; column g = 0 hi part, g = 1 lo part
+      }
+      // B fragments of q: lane (g, t) holds elements 16 j + 2 t + {0, 1} and + {8, 9}; column g = 0 hi part, g = 1 lo part.
+      // The scores are kept in the base-2 domain (q carries log2 e), so a probability is one ex2 of a difference.
       uint32_t qb[4][2];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float src = (j < 2) ? qn0 : qn1;
+        const float src = ((j < 2) ? qn0 : qn1) * 1.4426950408889634f;
         const int e = (16 * j + 2 * t) & 31;
         const float v0 = __shfl_sync(0xffffffffu, src, e), v1 = __shfl_sync(0xffffffffu, src, e + 1);
         const float v8 = __shfl_sync(0xffffffffu, src, e + 8), v9 = __shfl_sync(0xffffffffu, src, e + 9);
@@ -963,90 +978,118 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, int x
       float m = -INFINITY, lsum = 0.f, o[4][4];
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt) o[mt][0] = o[mt][1] = o[mt][2] = o[mt][3] = 0.f;
-      // XA_NS stages per iteration: the QK products, shuffles and exponentials of the stages overlap instead of forming
-      // one dependent chain per stage (the consumer math, not the K/V stream, bounds the phase once K/V hit L2).  K
-      // fragments of all stages are read first; the V fragments of a stage are read right before its PV products (and
-      // only then is the slot released), which keeps the register peak at one stage of V.
-      int kk = x.k0;
-      while (kk < x.k1) {
-        const int ns = (XA_NS == 2 && kk + XA_KEYS < x.k1) ? 2 : 1;  // warp-uniform
-        uint32_t ka[XA_NS][4][4];
-        uint32_t vb[XA_NS], slv[XA_NS];
-        bool act[XA_NS];
+      // Two K/V stages per iteration (one for an odd last stage): the consumer is bound by the dependent-issue latency of ONE warp
+      // per scheduler (ldmatrix -> HMMA -> vote -> ex2 -> shuffles -> pack -> HMMA), so the chains of two 16-key blocks are
+      // interleaved instruction by instruction and the barrier waits, vote and loop bookkeeping are shared.  The K half of a stage
+      // is released as soon as its fragments are in registers, the V half after its own ldmatrix (separate barriers): a warp
+      // holds shared memory only for the duration of an ldmatrix, so the ring stays full although two stages are consumed at a time.
+      // Scores / probabilities live in the t = 0 lane of every quad (B columns 2 .. 7 are zero: the other lanes compute 0 and are
+      // masked out of the votes and reductions; the P fragment is gathered from the t = 0 lanes).
+      // The running offset m is only moved when a score exceeds it by more than 2^XA_LAZY (warp vote): most iterations need no
+      // max reduction and no rescale at all; probabilities are then at most 2^XA_LAZY.
+      constexpr float XA_LAZY = 8.f;
+      const uint32_t ring_a = smem_u32(ring);
+      int kk = xk0;
+      auto stages = [&](auto ns_tag) {
+        constexpr int NS = decltype(ns_tag)::value;
+        uint32_t sl[NS];
+        float c[NS][4];
+        // Blocks past the item's end (last stage only) may lie outside the short TMA box: what is read there are stale bf16 values
+        // of earlier stages / operators (the ring is zeroed when the kernel starts, so never uninitialised bits): their scores are
+        // masked and 0 x finite adds nothing to O.
+        {
+          uint32_t ka[NS][4][4];
 #pragma unroll
-        for (int n = 0; n < XA_NS; ++n) {
-          act[n] = false;
-          if (n < ns) {
-            const uint32_t sl = consumed % XA_NST, par = (consumed / XA_NST) & 1;
-            act[n] = kk + n * XA_KEYS + cw * 16 < x.k1;  // warp-uniform: this warp's 16 keys hold at least one key of the item
-            mbar_wait(sy.mb(MB_XA_FULL + sl), par);
-            const uint32_t kbase = smem_u32(ring + (size_t)sl * STAGE);
-            vb[n] = kbase + XA_HALF; slv[n] = sl;
-            if (act[n]) {
+          for (int n = 0; n < NS; ++n) {
+            const uint32_t cn = consumed + (uint32_t)n;
+            sl[n] = cn % XA_NST;
+            mbar_wait(sy.mb(MB_XK_FULL + sl[n]), (cn / XA_NST) & 1);
+            const uint32_t a0 = ring_a + sl[n] * STAGE + laneK;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) ldsm_x4(ka[n][j], kbase + rowA * 128 + (((2 * j + chA) ^ sw) << 4));
-            }
-            ++consumed;
+            for (int j = 0; j < 4; ++j) ldsm_x4(ka[n][j], a0 ^ (uint32_t)(j << 5));
+          }
+          __syncwarp();
+          if (lane == 0) {
+#pragma unroll
+            for (int n = 0; n < NS; ++n) mbar_arrive(sy.mb(MB_XK_EMPTY + sl[n]));  // this warp holds its K fragments
+          }
+#pragma unroll
+          for (int n = 0; n < NS; ++n) c[n][0] = c[n][1] = c[n][2] = c[n][3] = 0.f;
+          if (!WXB_SKIP(skip, 16)) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int n = 0; n < NS; ++n) mma_16816(c[n], ka[n][j], qb[j][0], qb[j][1]);
           }
         }
-        // scores of the stages (two accumulators per stage), one max reduction for all of them
-        float sc[XA_NS][2];
+        // V fragments: requested before the softmax arithmetic so that their latency is covered by it
+        uint32_t va[NS][4][4];
 #pragma unroll
-        for (int n = 0; n < XA_NS; ++n) {
-          sc[n][0] = sc[n][1] = -INFINITY;
-          if (n < ns && act[n] && !WXB_SKIP(skip, 16)) {
-            float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
-            mma_16816(c0, ka[n][0], qb[0][0], qb[0][1]);
-            mma_16816(c1, ka[n][1], qb[1][0], qb[1][1]);
-            mma_16816(c0, ka[n][2], qb[2][0], qb[2][1]);
-            mma_16816(c1, ka[n][3], qb[3][0], qb[3][1]);
-            const int key0 = kk + n * XA_KEYS + cw * 16 + g;
-            const float s0 = __shfl_sync(0xffffffffu, (c0[0] + c0[1]) + (c1[0] + c1[1]), lane & ~3);
-            const float s1 = __shfl_sync(0xffffffffu, (c0[2] + c0[3]) + (c1[2] + c1[3]), lane & ~3);
-            sc[n][0] = (key0 < x.k1) ? s0 : -INFINITY;
-            sc[n][1] = (key0 + 8 < x.k1) ? s1 : -INFINITY;
-          }
+        for (int n = 0; n < NS; ++n) {
+          mbar_wait(sy.mb(MB_XV_FULL + sl[n]), ((consumed + (uint32_t)n) / XA_NST) & 1);
+          const uint32_t a1 = ring_a + sl[n] * STAGE + XA_HALF + laneV;
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) ldsm_x4_t(va[n][mt], a1 ^ (uint32_t)(mt << 5));
         }
-        float mx = fmaxf(sc[0][0], sc[0][1]);
+        __syncwarp();
+        if (lane == 0) {
 #pragma unroll
-        for (int n = 1; n < XA_NS; ++n) mx = fmaxf(mx, fmaxf(sc[n][0], sc[n][1]));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
-        const float mn = fmaxf(m, mx);
-        if (mn > m) {  // warp-uniform
-          const float alpha = __expf(m - mn);  // m = -inf -> 0
+          for (int n = 0; n < NS; ++n) mbar_arrive(sy.mb(MB_XV_EMPTY + sl[n]));  // this warp is done with the stages
+        }
+        // scores of this warp's keys 16 cw + g (s0) and + 8 (s1) of every stage; keys past the item are masked
+        float s0[NS], s1[NS];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int n = 0; n < NS; ++n) {
+          const int lim = xk1 - (kk + n * XA_KEYS + cw * 16);  // valid keys of this warp's block (<= 0: none)
+          const bool mine = (t == 0) && !WXB_SKIP(skip, 16);
+          s0[n] = (mine && g < lim) ? c[n][0] + c[n][1] : -INFINITY;
+          s1[n] = (mine && g + 8 < lim) ? c[n][2] + c[n][3] : -INFINITY;
+          mx = fmaxf(mx, fmaxf(s0[n], s1[n]));
+        }
+        if (__any_sync(0xffffffffu, mx > m + XA_LAZY)) {  // m = -inf: any finite score
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+          mx = __shfl_sync(0xffffffffu, mx, 0);
+          const float alpha = exp2f(m - mx);  // m = -inf -> 0
           lsum *= alpha;
 #pragma unroll
           for (int mt = 0; mt < 4; ++mt) { o[mt][0] *= alpha; o[mt][1] *= alpha; o[mt][2] *= alpha; o[mt][3] *= alpha; }
-          m = mn;
+          m = mx;
         }
+        if (m > -INFINITY) {  // warp-uniform; false only while every key seen so far was masked
+          uint32_t pb[NS][2];
 #pragma unroll
-        for (int n = 0; n < XA_NS; ++n) {
-          if (n < ns) {
-            const bool live = act[n] && m > -INFINITY && !WXB_SKIP(skip, 16);
-            uint32_t va[4][4];
-            if (live) {
+          for (int n = 0; n < NS; ++n) {
+            const float p0 = ex2_approx(s0[n] - m), p1 = ex2_approx(s1[n] - m);  // -inf -> 0
+            lsum += p0 + p1;  // meaningful in the t = 0 lanes
+            // B fragment of p: lane (g, t) needs keys 2t, 2t+1 (b0) and 2t+8, 2t+9 (b1): the t = 0 lanes of quads 2t and 2t+1
+            const float x0 = __shfl_sync(0xffffffffu, p0, 8 * t), x1 = __shfl_sync(0xffffffffu, p0, 8 * t + 4);
+            const float y0 = __shfl_sync(0xffffffffu, p1, 8 * t), y1 = __shfl_sync(0xffffffffu, p1, 8 * t + 4);
+            pb[n][0] = split_pack(x0, x1, g);
+            pb[n][1] = split_pack(y0, y1, g);
+          }
+          if (!WXB_SKIP(skip, 128)) {
 #pragma unroll
-              for (int mt = 0; mt < 4; ++mt) ldsm_x4_t(va[mt], vb[n] + rowV * 128 + (((2 * mt + chV) ^ sw) << 4));
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(sy.mb(MB_XA_EMPTY + slv[n]));  // this warp is done reading the stage
-            if (live) {
-              const float p0 = __expf(sc[n][0] - m), p1 = __expf(sc[n][1] - m);  // -inf -> 0
-              lsum += p0 + p1;  // per-quad partial sum (identical in the 4 lanes of a quad)
-              // B fragment of p: lane (g, t) needs keys 2t, 2t+1 (b0) and 2t+8, 2t+9 (b1): quads 2t and 2t+1
-              const float x0 = __shfl_sync(0xffffffffu, p0, 8 * t), x1 = __shfl_sync(0xffffffffu, p0, 8 * t + 4);
-              const float y0 = __shfl_sync(0xffffffffu, p1, 8 * t), y1 = __shfl_sync(0xffffffffu, p1, 8 * t + 4);
-              const uint32_t pb0 = split_pack(x0, x1, g), pb1 = split_pack(y0, y1, g);
+          for (int n = 0; n < NS; ++n)
 #pragma unroll
-              for (int mt = 0; mt < 4; ++mt) mma_16816(o[mt], va[mt], pb0, pb1);
-            }
+            for (int mt = 0; mt < 4; ++mt) mma_16816(o[mt], va[n][mt], pb[n][0], pb[n][1]);
           }
         }
-        kk += ns * XA_KEYS;
-      }
-      // ---- deposit this warp's state; consumer warp (item % 7) merges the 7 states and writes the output ----
+        consumed += NS;
+        kk += NS * XA_KEYS;
+      };
+      while (kk + XA_KEYS < xk1) stages(std::integral_constant<int, 2>{});
+      if (kk < xk1) stages(std::integral_constant<int, 1>{});
+      // ---- deposit this warp's state; consumer warp (item % XA_CW) merges the states and writes the output ----
+      // (the item's coordinates are derived again from an opaque copy of its index: nothing but the softmax state is carried
+      // through the key loop in registers, see DESIGN.md "Stack frames")
+      int it2 = it;
+      asm volatile("" : "+r"(it2));
+      const XaItem x = xa_item(it2, cta, qw, G, P, plen, n_items - qw);
+      const int b = x.slab / H, h = x.slab - b * H;
+      const uint32_t gi = xa_items0 + (uint32_t)it2, ipar = gi & 1, iph = (gi >> 1) & 1;
       lsum += __shfl_xor_sync(0xffffffffu, lsum, 4);
       lsum += __shfl_xor_sync(0xffffffffu, lsum, 8);
       lsum += __shfl_xor_sync(0xffffffffu, lsum, 16);
@@ -1073,7 +1116,7 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, int x
         float Ls = 0.f, o0 = 0.f, o1 = 0.f;  // dims lane and lane + 32
 #pragma unroll
         for (int i = 0; i < XA_CW; ++i) {
-          const float w = __expf(st[i * 66] - M);  // a warp that saw no key of the item: m = -inf -> 0
+          const float w = exp2f(st[i * 66] - M);  // (offsets are base-2) a warp that saw no key of the item: m = -inf -> 0
           Ls += w * st[i * 66 + 1];
           o0 += w * st[i * 66 + 2 + lane];
           o1 += w * st[i * 66 + 2 + lane + 32];
@@ -1121,7 +1164,7 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, int x
               }
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
-                const float w = __expf(mv[u] - MM);  // a slot past P: exp(-inf) = 0
+                const float w = exp2f(mv[u] - MM);  // a slot past P: 2^-inf = 0
                 LL += w * lv[u];
                 O0 += w * a0[u];
                 O1 += w * a1[u];
@@ -1383,13 +1426,16 @@ __device__ __forceinline__ void pre_issue(const MkParams& p, int l, int k, int x
       for (int kk = x.k0; kk < x.k1 && n < XA_NST; kk += XA_KEYS, ++n) {
         if (!issue) continue;
         const uint32_t c = xa_count0 + (uint32_t)n, sl = c % XA_NST, par = (c / XA_NST) & 1;
-        mbar_wait(sy.mb(MB_XA_EMPTY + sl), par ^ 1);
         const bool tail = (x.k1 - kk <= XA_TAIL);
         const CUtensorMap* m = tail ? kvmap + 1 : kvmap;
         uint8_t* dst = ring + (size_t)sl * STAGE;
-        mbar_arrive_expect_tx(sy.mb(MB_XA_FULL + sl), tail ? 2 * XA_TAIL * 128 : STAGE);
-        tma_load_2d_hint(dst, m, sy.mb(MB_XA_FULL + sl), 0, krow0 + oslab * T_AUDIO + kk, L2_EVICT_FIRST);
-        tma_load_2d_hint(dst + XA_HALF, m, sy.mb(MB_XA_FULL + sl), 0, vrow0 + oslab * T_AUDIO + kk, L2_EVICT_FIRST);
+        const uint32_t half_tx = tail ? XA_TAIL * 128 : XA_HALF;
+        mbar_wait(sy.mb(MB_XK_EMPTY + sl), par ^ 1);
+        mbar_arrive_expect_tx(sy.mb(MB_XK_FULL + sl), half_tx);
+        tma_load_2d_hint(dst, m, sy.mb(MB_XK_FULL + sl), 0, krow0 + oslab * T_AUDIO + kk, L2_EVICT_FIRST);
+        mbar_wait(sy.mb(MB_XV_EMPTY + sl), par ^ 1);
+        mbar_arrive_expect_tx(sy.mb(MB_XV_FULL + sl), half_tx);
+        tma_load_2d_hint(dst + XA_HALF, m, sy.mb(MB_XV_FULL + sl), 0, vrow0 + oslab * T_AUDIO + kk, L2_EVICT_FIRST);
       }
       ++it;
     }
@@ -1456,6 +1502,9 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) dec_step_kernel(co
   for (int i = threadIdx.x; i < p.L * (int)(sizeof(DecLayerW) / 8); i += MK_THREADS)
     reinterpret_cast<unsigned long long*>(s_layers)[i] = reinterpret_cast<const unsigned long long*>(p.layers)[i];
   for (int i = threadIdx.x; i < p.B; i += MK_THREADS) s_rows[i] = p.rows ? p.rows[i] : i;
+  // the cross-attention consumers may read ring rows that no TMA box of the current stage has written (cross_attn_phase): such
+  // rows must never hold uninitialised bits
+  for (int i = threadIdx.x; i < RING_BYTES / 16; i += MK_THREADS) reinterpret_cast<uint4*>(ring)[i] = make_uint4(0u, 0u, 0u, 0u);
   const int warp = threadIdx.x >> 5;
   MkSync sy;
   sy.bars = smem_u32(bars);
@@ -1464,7 +1513,10 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) dec_step_kernel(co
   if (threadIdx.x == 0) {
     for (int i = 0; i < GV_NST; ++i) { mbar_init(sy.mb(MB_GV_FULL + i), 1); mbar_init(sy.mb(MB_GV_EMPTY + i), 1); }
     mbar_init(sy.mb(MB_ACC_FULL), 1);
-    for (int i = 0; i < XA_NST; ++i) { mbar_init(sy.mb(MB_XA_FULL + i), 1); mbar_init(sy.mb(MB_XA_EMPTY + i), XA_CW); }
+    for (int i = 0; i < XA_NST; ++i) {
+      mbar_init(sy.mb(MB_XK_FULL + i), 1); mbar_init(sy.mb(MB_XK_EMPTY + i), XA_CW);
+      mbar_init(sy.mb(MB_XV_FULL + i), 1); mbar_init(sy.mb(MB_XV_EMPTY + i), XA_CW);
+    }
     for (int i = 0; i < 2; ++i) {
       mbar_init(sy.mb(MB_ST_FULL + i), XA_CW); mbar_init(sy.mb(MB_ST_FREE + i), 1);
       mbar_init(sy.mb(MB_Q_FULL + i), 32); mbar_init(sy.mb(MB_Q_FREE + i), XA_CW);
@@ -1493,7 +1545,6 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) dec_step_kernel(co
     p.prof[(1 << 16) - 1] = smid;
     p.prof[(1 << 16) - 2] = t;
   }
-  unsigned bar_target = 0;
   const int pos0 = *p.d_pos;  // written only after the last barrier of this launch
   const int n_ph = ops_per_step(p);
   for (int s = 0; s < p.n_steps; ++s) {
@@ -1508,7 +1559,7 @@ __global__ void __launch_bounds__(MK_THREADS, MK_CTAS_PER_SM) dec_step_kernel(co
         int l2 = ph2 / 11, k2 = ph2 - 11 * l2;
         if (l2 >= p.L) { k2 = 11 + (ph2 - 11 * p.L); l2 = p.L - 1; }
         const int xq2 = (ph + 1 < n_ph ? s : s + 1) * p.L + l2;  // cross-attention phases completed before operator (l2, k2)
-        grid_sync(p.bar, bar_target, sy.nc, sy.cta, p.prof, [&]() { pre_issue<MT>(p, l2, k2, xq2, ring, sy, true); });
+        grid_sync(p.bar, (unsigned)(s * n_ph + ph + 1), sy.nc, sy.cta, p.prof, [&]() { pre_issue<MT>(p, l2, k2, xq2, ring, sy, true); });
         if (warp == 0) pre_issue<MT>(p, l2, k2, xq2, ring, sy, false);  // the producer warp only needs the count
       }
     }
