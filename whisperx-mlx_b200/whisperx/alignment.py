@@ -294,6 +294,16 @@ def _emissions_for(model, model_type: str, wave: torch.Tensor, lengths, device):
     return logits[0]
 
 
+def _pinned(ctx, name: str, n: int, dtype) -> torch.Tensor:
+    """Pinned host buffers kept on the Context between align() calls (cudaHostAlloc per call costs more than the copies)."""
+    cache = ctx.__dict__.setdefault("_align_pinned", {})
+    t = cache.get(name)
+    if t is None or t.numel() < n or t.dtype != dtype:
+        t = torch.empty(max(n, 1024), dtype=dtype).pin_memory()
+        cache[name] = t
+    return t
+
+
 def align(
     transcript: Iterable[SingleSegment],
     model: torch.nn.Module,
@@ -374,49 +384,88 @@ def align(
         tok_parts.append(np.asarray(tokens, dtype=np.int32))
         jobs.append((sdx, text_clean, tokens, logits.shape[0], wave.size(0)))
 
-    results = {}
-    if jobs:
-        if native:
-            if model.ctx is not ctx:
-                raise RuntimeError("the alignment model lives on another GPU than `device`")
-            emis, _ = model.emissions(native_waves)  # pinned upload -> batched wav2vec2 forward (csrc/wxb_w2v.cu) -> [sum T, V]
-        else:
-            emis = torch.cat(emis_parts, 0).contiguous()
-        ctx.log_softmax_rows_(emis)  # alignment.py:258
-        t_off = np.concatenate([[0], np.cumsum([j[3] for j in jobs])]).astype(np.int32)
-        n_off = np.concatenate([[0], np.cumsum([len(t) for t in tok_parts])]).astype(np.int32)
-        tok_dev = torch.from_numpy(np.concatenate(tok_parts)).to(ctx.device)
-        res = ctx.ctc_align(emis, t_off, tok_dev, n_off, blank_id, CTC_BEAM2)
-        status = res["status"].cpu().numpy()
-        path_tok = res["path_tok"].cpu().numpy()
-        path_prob = torch.exp(res["path_lp"].cpu()).numpy()
-        if native:
-            model.last_stats["d2h_bytes"] = int(status.nbytes + path_tok.nbytes + path_prob.nbytes)
-        for k, job in enumerate(jobs):
-            a, b = int(t_off[k]), int(t_off[k + 1])
-            results[job[0]] = (int(status[k]), path_tok[a:b], path_prob[a:b], job)
+    # ---- pass 2: K4 on the GPU, host assembly of the dicts ------------------------------------
+    # The jobs run as a short pipeline of groups: while the GPU does the wav2vec2 forward + log-softmax + K4 of group i + 1, the
+    # host assembles the char / word / sentence dicts of group i (path read-back through pinned buffers and an event, no
+    # blocking copy in between).  One group when there are few segments or a torch model produced the emissions.
+    assembled = {}   # sdx -> list of aligned segments
+    failed = {}      # sdx -> message
+    n_groups = min(4, max(1, len(jobs) // 15)) if native else 1
+    bounds = [len(jobs) * g // n_groups for g in range(n_groups + 1)]
+    d2h_bytes = 0
 
-    # ---- pass 2: host assembly --------------------------------------------------------------
+    def launch(g, a, b):
+        toks = np.concatenate(tok_parts[a:b]) if b > a else np.zeros(0, np.int32)
+        t_off = np.concatenate([[0], np.cumsum([j[3] for j in jobs[a:b]])]).astype(np.int32)
+        n_off = np.concatenate([[0], np.cumsum([len(t) for t in tok_parts[a:b]])]).astype(np.int32)
+        sum_t = int(t_off[-1])
+        pin = _pinned(ctx, "tok%d" % (g % 2), max(len(toks), 1), torch.int32)
+        pin[: len(toks)].copy_(torch.from_numpy(toks))
+        tok_dev = torch.empty(max(len(toks), 1), dtype=torch.int32, device=ctx.device)
+        tok_dev[: len(toks)].copy_(pin[: len(toks)], non_blocking=True)  # before the forward: nothing below waits for the stream
+        if native:
+            emis, _ = model.emissions(native_waves[a:b])  # pinned upload -> batched wav2vec2 forward (csrc/wxb_w2v.cu) -> [sum T, V]
+        else:
+            emis = torch.cat(emis_parts[a:b], 0).contiguous()
+        ctx.log_softmax_rows_(emis)  # alignment.py:258
+        res = ctx.ctc_align(emis, t_off, tok_dev[: len(toks)], n_off, blank_id, CTC_BEAM2)
+        slot = g % 2  # two sets of read-back buffers: group g + 1 is launched before group g is read
+        h_status = _pinned(ctx, "status%d" % slot, b - a, torch.int32)
+        h_tok = _pinned(ctx, "ptok%d" % slot, max(sum_t, 1), torch.int32)
+        h_lp = _pinned(ctx, "plp%d" % slot, max(sum_t, 1), torch.float32)
+        h_status[: b - a].copy_(res["status"], non_blocking=True)
+        h_tok[:sum_t].copy_(res["path_tok"], non_blocking=True)
+        h_lp[:sum_t].copy_(res["path_lp"], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return (a, b, t_off, sum_t, h_status, h_tok, h_lp, ev, (emis, tok_dev, res))
+
+    def finish(h):
+        nonlocal d2h_bytes
+        a, b, t_off, sum_t, h_status, h_tok, h_lp, ev, _keep = h
+        ev.synchronize()
+        status = h_status[: b - a].numpy()
+        path_tok = h_tok[:sum_t].numpy()
+        path_prob = torch.exp(h_lp[:sum_t]).numpy()
+        d2h_bytes += int(status.nbytes + path_tok.nbytes + path_prob.nbytes)
+        for k in range(a, b):
+            sdx, text_clean, _tokens, T, n_channels = jobs[k]
+            seg = transcript[sdx]
+            t1, t2, text = seg["start"], seg["end"], seg["text"]
+            if int(status[k - a]) != 0:
+                failed[sdx] = "backtrack failed, resorting to original..."
+                continue
+            f0, f1 = int(t_off[k - a]), int(t_off[k - a + 1])
+            runs = _merge_runs(path_tok[f0:f1], path_prob[f0:f1])
+            ratio = (t2 - t1) * n_channels / (T - 1)
+            assembled[sdx] = _assemble(text, prepared[sdx], runs, ratio, t1, spaced, interpolate_method, return_char_alignments)
+
+    pending = None
+    for g in range(n_groups):
+        if bounds[g + 1] == bounds[g]:
+            continue
+        if native and model.ctx is not ctx:
+            raise RuntimeError("the alignment model lives on another GPU than `device`")
+        h = launch(g, bounds[g], bounds[g + 1])
+        if pending is not None:
+            finish(pending)
+        pending = h
+    if pending is not None:
+        finish(pending)
+    if native and jobs:
+        model.last_stats["d2h_bytes"] = d2h_bytes
+
     aligned_segments: List[SingleAlignedSegment] = []
     for sdx, seg in enumerate(transcript):
         t1, t2, text = seg["start"], seg["end"], seg["text"]
+        if sdx in assembled:
+            aligned_segments += assembled[sdx]
+            continue
         plain: SingleAlignedSegment = {"start": t1, "end": t2, "text": text, "words": [], "chars": None}
         if return_char_alignments:
             plain["chars"] = []
-        if sdx in skip_reason:
-            print(f'Failed to align segment ("{text}"): {skip_reason[sdx]}')
-            aligned_segments.append(plain)
-            continue
-        status, ptok, pprob, job = results[sdx]
-        if status != 0:
-            print(f'Failed to align segment ("{text}"): backtrack failed, resorting to original...')
-            aligned_segments.append(plain)
-            continue
-        _, text_clean, _tokens, T, n_channels = job
-        runs = _merge_runs(ptok, pprob)
-        ratio = (t2 - t1) * n_channels / (T - 1)
-        aligned_segments += _assemble(text, prepared[sdx], runs, ratio, t1, spaced,
-                                      interpolate_method, return_char_alignments)
+        print(f'Failed to align segment ("{text}"): {skip_reason.get(sdx) or failed.get(sdx)}')
+        aligned_segments.append(plain)
 
     word_segments: List[SingleWordSegment] = []
     for seg in aligned_segments:
