@@ -482,51 +482,64 @@ __device__ __forceinline__ void gemv_phase(const MkParams& p, const MkGemv& g, c
 // One call consumes 4 keys per slot: key(u) = kb + u * KSTRIDE + slot, masked by key < k1.
 // ---------------------------------------------------------------------------------------------
 template <int KSTRIDE>
-__device__ __forceinline__ void att_consume(const uint4* kv, uint4* vv, int kb, int slot, int k1, const float* qr, float& m,
+__device__ __forceinline__ void att_consume(const uint4* kv, const uint4* vv, int kb, int slot, int k1, const float* qr, float& m,
                                             float& l, float* acc) {
+  // Branch-free: the four keys' dot-product chains (8 FMA + 3 shuffles each) and their P V updates are independent instruction
+  // streams that the scheduler can interleave; a branch per key would serialise them.  Keys at or past k1 were not loaded: their
+  // staging slots hold stale but finite bf16 values (the staging region is zeroed when the kernel starts), their scores are
+  // masked to -inf and 0 x finite adds nothing.
   float sc4[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&kv[u]);
+    float s0 = 0.f, s1 = 0.f;  // two partial chains per key
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(h2[j]);
+      s0 = fmaf(qr[2 * j], f.x, s0);
+      s1 = fmaf(qr[2 * j + 1], f.y, s1);
+    }
+    sc4[u] = s0 + s1;
+  }
+#pragma unroll
+  for (int o = 1; o <= 4; o <<= 1) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) sc4[u] += __shfl_xor_sync(0xffffffffu, sc4[u], o);
+  }
   float mx = -INFINITY;
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
-    const int key = kb + u * KSTRIDE + slot;
-    float sdot = 0.f;
-    if (key < k1) {
-      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&kv[u]);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __bfloat1622float2(h2[j]);
-        sdot = fmaf(qr[2 * j], f.x, sdot);
-        sdot = fmaf(qr[2 * j + 1], f.y, sdot);
-      }
-    } else {
-      vv[u] = make_uint4(0u, 0u, 0u, 0u);  // never loaded: 0 * garbage must not make NaN
-    }
-    sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
-    sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
-    sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
-    sc4[u] = (key < k1) ? sdot : -INFINITY;
+    sc4[u] = (kb + u * KSTRIDE + slot < k1) ? sc4[u] : -INFINITY;
     mx = fmaxf(mx, sc4[u]);
   }
-  if (mx > -INFINITY) {  // uniform within the 8-lane slot
-    const float mn = fmaxf(m, mx);
-    const float alpha = __expf(m - mn);  // m = -inf -> 0
-    m = mn;
-    l *= alpha;
+  const float mn = fmaxf(m, mx);
+  const float alpha = (m > -INFINITY) ? __expf(m - mn) : 0.f;  // nothing accumulated yet: l = acc = 0 anyway
+  m = mn;
+  l *= alpha;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] *= alpha;
+  for (int j = 0; j < 8; ++j) acc[j] *= alpha;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float pr = __expf(sc4[u] - mn);  // -inf -> 0
-      l += pr;
-      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&vv[u]);
+  for (int u = 0; u < 4; ++u) {
+    const float pr = (sc4[u] > -INFINITY) ? __expf(sc4[u] - mn) : 0.f;  // mn = -inf only while every key so far was masked
+    l += pr;
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&vv[u]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __bfloat1622float2(h2[j]);
-        acc[2 * j] = fmaf(pr, f.x, acc[2 * j]);
-        acc[2 * j + 1] = fmaf(pr, f.y, acc[2 * j + 1]);
-      }
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(h2[j]);
+      acc[2 * j] = fmaf(pr, f.x, acc[2 * j]);
+      acc[2 * j + 1] = fmaf(pr, f.y, acc[2 * j + 1]);
     }
   }
+}
+
+// 16-byte asynchronous copy / shared-memory load at a compile-time offset from a base (the offset is an immediate of the instruction)
+template <int DST_OFF, int SRC_OFF>
+__device__ __forceinline__ void cp_async16(uint32_t dst, const char* src) {
+  asm volatile("cp.async.cg.shared.global [%0+%2], [%1+%3], 16;" ::"r"(dst), "l"(src), "n"(DST_OFF), "n"(SRC_OFF) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ void lds128(uint32_t addr, uint4& v) {
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+%5];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr), "n"(OFF));
 }
 
 // Causal self-attention.  A (sequence, head) unit is finished by one warp: it completes the QKV GEMV for its head
@@ -584,9 +597,14 @@ __device__ __forceinline__ SelfUnit self_unit_qkv(const MkParams& p, const float
 }
 // online-softmax state of one warp over the cached keys [k_begin, k_end) (and the new key if with_new), merged over
 // the warp's 4 key slots: on return every lane holds m, l and the 8 output dims of its c8
-constexpr int SA_AHEAD = MK_WARPS == 8 ? 4 : MK_WARPS == 10 ? 3 : 2;  // chunks of 16 keys requested ahead of the one being consumed
+#ifndef WXB_SA_AHEAD
+#define WXB_SA_AHEAD (MK_WARPS == 8 ? 4 : MK_WARPS == 10 ? 3 : 2)
+#endif
+constexpr int SA_AHEAD = WXB_SA_AHEAD;  // chunks of 16 keys requested ahead of the one being consumed
 constexpr int SA_RING = SA_AHEAD + 1;  // 4 KB chunk slots per warp
+#ifndef WXB_SA_EXPERIMENT
 static_assert(MK_WARPS * SA_RING * 4096 <= RING_BYTES, "self-attention staging must fit the TMA ring region");
+#endif
 __device__ __forceinline__ void self_unit_attend(const SelfUnit& u, const __nv_bfloat16* Kb, const __nv_bfloat16* Vb, int k_begin, int k_end,
                                                  bool with_new, int slot, int c8, uint32_t stage, float& m, float& lsum, float* acc) {
   m = -INFINITY; lsum = 0.f;
@@ -622,18 +640,19 @@ __device__ __forceinline__ void self_unit_attend(const SelfUnit& u, const __nv_b
   const int n = k_end;
   const int nch = (n > k_begin) ? (n - k_begin + 15) >> 4 : 0;
   const uint32_t lane_off = (uint32_t)((slot * 8 + c8) * 16);  // inside a 512-byte row group (4 keys x 128 B)
+  // this lane's piece of key k_begin + slot; chunk c, key group i is 2048 c + 512 i bytes further (rows are 128 bytes)
+  const char* kp0 = reinterpret_cast<const char*>(Kb + (size_t)(k_begin + slot) * 64 + c8 * 8);
+  const char* vp0 = reinterpret_cast<const char*>(Vb + (size_t)(k_begin + slot) * 64 + c8 * 8);
   auto issue = [&](int c) {  // chunk c: keys k_begin + 16 c + 4 i + slot; K pieces at [c % SA_RING][i], V pieces 2 KB behind
     if (c < nch) {
-      const int kb = k_begin + (c << 4);
       const uint32_t dst = stage + (uint32_t)((c % SA_RING) * 4096) + lane_off;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int key = kb + i * 4 + slot;
-        if (key < n) {
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 512), "l"(Kb + (size_t)key * 64 + c8 * 8) : "memory");
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 2048 + i * 512), "l"(Vb + (size_t)key * 64 + c8 * 8) : "memory");
-        }
-      }
+      const char* kp = kp0 + (size_t)c * 2048;
+      const char* vp = vp0 + (size_t)c * 2048;
+      const int left = n - k_begin - (c << 4) - slot;  // this lane's keys of the chunk: i with 4 i < left
+      if (0 < left) { cp_async16<0, 0>(dst, kp); cp_async16<2048, 0>(dst, vp); }
+      if (4 < left) { cp_async16<512, 512>(dst, kp); cp_async16<2048 + 512, 512>(dst, vp); }
+      if (8 < left) { cp_async16<1024, 1024>(dst, kp); cp_async16<2048 + 1024, 1024>(dst, vp); }
+      if (12 < left) { cp_async16<1536, 1536>(dst, kp); cp_async16<2048 + 1536, 1536>(dst, vp); }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");  // one group per chunk index, empty or not: the wait below counts groups
   };
@@ -644,11 +663,8 @@ __device__ __forceinline__ void self_unit_attend(const SelfUnit& u, const __nv_b
     asm volatile("cp.async.wait_group %0;" ::"n"(SA_AHEAD) : "memory");  // chunk c has landed
     const uint32_t src = stage + (uint32_t)((c % SA_RING) * 4096) + lane_off;
     uint4 kA[4], vA[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(kA[i].x), "=r"(kA[i].y), "=r"(kA[i].z), "=r"(kA[i].w) : "r"(src + i * 512));
-      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(vA[i].x), "=r"(vA[i].y), "=r"(vA[i].z), "=r"(vA[i].w) : "r"(src + 2048 + i * 512));
-    }
+    lds128<0>(src, kA[0]); lds128<512>(src, kA[1]); lds128<1024>(src, kA[2]); lds128<1536>(src, kA[3]);
+    lds128<2048>(src, vA[0]); lds128<2048 + 512>(src, vA[1]); lds128<2048 + 1024>(src, vA[2]); lds128<2048 + 1536>(src, vA[3]);
     att_consume<4>(kA, vA, k_begin + (c << 4), slot, n, u.q8, m, lsum, acc);
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");

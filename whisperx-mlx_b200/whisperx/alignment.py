@@ -393,8 +393,11 @@ def align(
     n_groups = min(4, max(1, len(jobs) // 15)) if native else 1
     bounds = [len(jobs) * g // n_groups for g in range(n_groups + 1)]
     d2h_bytes = 0
+    h2d_bytes = 0
+    stats_sum = {"flops": 0.0, "frames": 0, "segments": 0}
 
     def launch(g, a, b):
+        nonlocal h2d_bytes
         toks = np.concatenate(tok_parts[a:b]) if b > a else np.zeros(0, np.int32)
         t_off = np.concatenate([[0], np.cumsum([j[3] for j in jobs[a:b]])]).astype(np.int32)
         n_off = np.concatenate([[0], np.cumsum([len(t) for t in tok_parts[a:b]])]).astype(np.int32)
@@ -405,6 +408,9 @@ def align(
         tok_dev[: len(toks)].copy_(pin[: len(toks)], non_blocking=True)  # before the forward: nothing below waits for the stream
         if native:
             emis, _ = model.emissions(native_waves[a:b])  # pinned upload -> batched wav2vec2 forward (csrc/wxb_w2v.cu) -> [sum T, V]
+            h2d_bytes += int(model.last_stats.get("h2d_bytes", 0)) + int(toks.nbytes)
+            for k2 in stats_sum:
+                stats_sum[k2] += model.last_stats.get(k2, 0)
         else:
             emis = torch.cat(emis_parts[a:b], 0).contiguous()
         ctx.log_softmax_rows_(emis)  # alignment.py:258
@@ -452,8 +458,8 @@ def align(
         pending = h
     if pending is not None:
         finish(pending)
-    if native and jobs:
-        model.last_stats["d2h_bytes"] = d2h_bytes
+    if native and jobs:  # totals of this align() call (the groups' forwards each wrote their own)
+        model.last_stats.update(d2h_bytes=d2h_bytes, h2d_bytes=h2d_bytes, **stats_sum)
 
     aligned_segments: List[SingleAlignedSegment] = []
     for sdx, seg in enumerate(transcript):
