@@ -188,6 +188,8 @@ class Job:
             self.ctx.debug_set("dec_groups", args.dec_groups)
         if args.dec_group_delay_ns >= 0:
             self.ctx.debug_set("dec_group_delay_ns", args.dec_group_delay_ns)
+        if args.enc_group >= 0:        # A/B aid: chunks per group of the encoder's layer stack (results do not depend on it)
+            self.ctx.debug_set("enc_group", args.enc_group)
         if args.sample_len > 0:
             self.be.options["sample_len"] = args.sample_len
         self.sample_len = int(self.be.options["sample_len"])
@@ -385,9 +387,10 @@ def main():
     ap.add_argument("--sample-len", type=int, default=0, help="override the number of sampled positions (profiling only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the batch8 / turbo / weak sub-records")
+    ap.add_argument("--no-extras", action="store_true", help="skip the batch8 / ragged / turbo / weak sub-records")
     ap.add_argument("--no-align", action="store_true", help="leave the wav2vec2 + CTC alignment leg out (profiling only)")
     ap.add_argument("--dec-groups", type=int, default=0, help="A/B aid: sequence groups per decode call (0 = the library's choice)")
+    ap.add_argument("--enc-group", type=int, default=-1, help="A/B aid: chunks per group of the encoder's layer stack (-1 = the library's default, 0 = whole batch)")
     ap.add_argument("--dec-group-delay-ns", type=int, default=-1, help="A/B aid: start offset between the sequence groups (-1 = default)")
     ap.add_argument("--allow-env", action="store_true", help="run although WXB_* variables are set (A/B runs, not a bench value)")
     args = ap.parse_args()
@@ -504,6 +507,19 @@ def main():
             del b8
             # SURVEY 8 f-2 / f-3 on the headline job (N = 1): word timing from the decoder's cross-attention, VAD chunking
             extras["dtw_words"], extras["vad"] = side_paths(job, audio, flush, args.steps)
+        # the same recording cut into ragged VAD chunks, durations ~ U(5, 30) s (about 100 chunks), LPT-dealt to the
+        # ranks; every rank walks its queue in batches of `batch_size` (chunks are padded to 30 s by the log-mel, as in the reference)
+        rseg = synthetic_vad_cuts(audio_s, "ragged", chunk_size=CHUNK_S)
+        rj = Job(args, args.model, local, rank, world, audio, rseg, True, args.batch_size, align_bundle)
+        rr = timed(rj, dist, world, max(1, min(args.steps, 2)), 1, flush)
+        drr = decode_roofline(rj, rr, P, rj.n_mine)
+        extras["ragged"] = {"config": f"whisper-{args.model}, the same {args.minutes:g} min cut into {len(rseg)} ragged VAD chunks (U(5, 30) s, seed 1234) "
+                                      f"sharded over {world} GPU(s), batches of {args.batch_size}; {rj.n_mine} chunks on rank 0",
+                            "value": audio_s / (rr["ms_step"] / 1e3), "unit": "x realtime", "ms_per_step": rr["ms_step"],
+                            "decode_rank0": {"ms_per_step": drr["ms_per_step"], "GB/s": drr["achieved"], "frac_hbm": drr["frac"],
+                                             "rows_per_call": drr["rows_per_call"]},
+                            "note": "random-init weights never emit EOT, so every chunk decodes all sampled positions whatever its duration"}
+        del rj
         # BASELINE config 4: large-v3-turbo, the same 30-minute job sharded over the ranks
         tj = Job(args, "large-v3-turbo", local, rank, world, audio, segments, True, args.batch_size, None)
         tr = timed(tj, dist, world, args.steps, 2, flush)
@@ -585,7 +601,8 @@ def main():
                        "batch_size": args.batch_size, "parallelism": f"{world} x 1 GPU, chunk-sharded, host gather only (no collective)",
                        "l2": "256 MB flush buffer written before every step", "library": lib_path, "env": env_seen,
                        **({"dec_groups": args.dec_groups} if args.dec_groups else {}),
-                       **({"dec_group_delay_ns": args.dec_group_delay_ns} if args.dec_group_delay_ns >= 0 else {})},
+                       **({"dec_group_delay_ns": args.dec_group_delay_ns} if args.dec_group_delay_ns >= 0 else {}),
+                       **({"enc_group": args.enc_group} if args.enc_group >= 0 else {})},
             "clocks": r["clocks"], "e2e": e2e, "gpu_launches": int(r["launches"]), "roofline": roofline, "cpu_baseline": cpu_baseline}
     line.update(extras)
     print(json.dumps(line), flush=True)

@@ -69,6 +69,27 @@ def test_encoder_vs_oracle(wxb_ctx, cfg):
     assert float(err.mean()) <= 0.006 * max(1.0, scale)
 
 
+def test_encoder_chunk_groups_bit_identical(wxb_ctx):
+    """The layer stack over groups of chunks (wxb_encoder.cu: chunk groups, `enc_group`) returns the same bits as the whole
+    batch at once: group sizes 1, 2 (ragged last group of 1) and 4 on a 5-chunk batch."""
+    from whisperx.backends import b200_weights as bw
+    from fake_ctc_model import synthetic_speech
+    import whisperx.audio as wa
+
+    dims = _tiny_dims(80, 128, 2, 2)
+    wxb_ctx.set_model(dims, bw.to_kernel_layout(bw.init_random_weights(dims, seed=4, std=0.05), dims, "cuda"))
+    chunks = [synthetic_speech(30.0 if i % 2 == 0 else 7.0 + i, seed=40 + i) for i in range(5)]
+    mel = wa.log_mel_chunks(chunks, 80)
+    try:
+        wxb_ctx.debug_set("enc_group", 0)
+        whole = wxb_ctx.encode(mel).clone()
+        for g in (1, 2, 4):
+            wxb_ctx.debug_set("enc_group", g)
+            assert torch.equal(wxb_ctx.encode(mel), whole), f"enc_group={g}"
+    finally:
+        wxb_ctx.debug_set("enc_group", -1)
+
+
 @pytest.mark.parametrize("B,T,H", [(1, 1500, 2), (2, 1500, 6), (3, 700, 3), (1, 128, 1), (2, 129, 2)])
 def test_encoder_attention_vs_torch(wxb_ctx, B, T, H):
     """Stand-alone self-attention vs torch fp32 SDPA on the same bf16 inputs.  P is rounded to bf16 before the PV

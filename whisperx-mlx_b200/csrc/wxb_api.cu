@@ -108,6 +108,11 @@ int64_t wxb_launch_count(const wxb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int wxb_debug_set(wxb_ctx* ctx, const char* key, int value) {
   if (!ctx || !key) return WXB_ERR_INVALID;
   if (std::string(key) == "w2v_stop") { ctx->w2v_stop = value; return WXB_OK; }
+  if (std::string(key) == "enc_group") {  // chunks per group of the encoder's layer stack (0 = whole batch, -1 = the library's default); results do not depend on it
+    if (value < -1) return wxb_fail(ctx, WXB_ERR_INVALID, "enc_group: >= -1");
+    ctx->enc_group = value;
+    return WXB_OK;
+  }
   if (std::string(key) == "dec_groups") {  // A/B aid: sequence groups per decode call (0 = automatic); results do not depend on it
     if (value < 0 || value > WXB_MAX_DEC_GROUPS) return wxb_fail(ctx, WXB_ERR_INVALID, "dec_groups: 0 .. %d", WXB_MAX_DEC_GROUPS);
     ctx->dec_groups_override = value;

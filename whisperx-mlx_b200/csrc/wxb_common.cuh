@@ -44,6 +44,7 @@ struct wxb_ctx {
   wxb_model* align_model = nullptr;  // wav2vec2 CTC model (wxb_set_align_model), same borrowed-pointer table
   wxb_w2v_dims align_dims = {};
   int melT_chunks = 0, melT_mels = 0;  // "enc.melT" holds the log-mel of this many chunks (wxb_logmel_features), 0 = nothing
+  int enc_group = -1;  // encoder layer stack over groups of this many chunks (0 = the whole batch at once, -1 = default): wxb_debug_set "enc_group"
   int w2v_stop = -1;  // bring-up aid (wxb_debug_set "w2v_stop"): return from the forward after this stage, -1 = run everything
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled (driver entry point), lazily resolved
   // decode timing is opt-in: wxb_decode_stats(reset = 1) switches it on; entries are owned by the ctx (freed by the next

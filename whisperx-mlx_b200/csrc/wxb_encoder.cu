@@ -129,6 +129,9 @@ int wxb_launch_layernorm(wxb_ctx* ctx, const float* x, const float* w, const flo
   return launch_layernorm(ctx, x, w, b, y, rows, d, st);
 }
 
+#ifndef WXB_ENC_GROUP
+#define WXB_ENC_GROUP 0  // default chunk-group size of the layer stack (0 = whole batch)
+#endif
 int wxb_encode_impl(wxb_ctx* ctx, const float* mel_dev, int B, __nv_bfloat16* enc_out, cudaStream_t st) {
   if (!ctx->model) return wxb_fail(ctx, WXB_ERR_STATE, "wxb_encode: no model set");
   const wxb_dims& D = ctx->model->dims;
@@ -137,11 +140,17 @@ int wxb_encode_impl(wxb_ctx* ctx, const float* mel_dev, int B, __nv_bfloat16* en
   const long long rows1 = (long long)B * G1 + 2;
   __nv_bfloat16* melT = (__nv_bfloat16*)wxb_named(ctx, "enc.melT", rows1 * nm * 2);
   __nv_bfloat16* h1 = (__nv_bfloat16*)wxb_named(ctx, "enc.h1", rows1 * d * 2);
+  // Chunk groups: the conv stem runs over the whole batch, the layer stack over groups of Bs chunks one after the other, so
+  // that what one kernel writes (xn, qkv, att, hid of a group) is still L2-resident when the next kernel reads it.  Results do
+  // not depend on the grouping (every row's arithmetic is the same).
+  const int eg = ctx->enc_group >= 0 ? ctx->enc_group : WXB_ENC_GROUP;
+  const int Bs = (eg > 0 && eg < B) ? eg : B;
+  const long long Mg = (long long)Bs * T_AUDIO;
   float* x = (float*)wxb_named(ctx, "enc.x", M * d * 4);
-  __nv_bfloat16* xn = (__nv_bfloat16*)wxb_named(ctx, "enc.xn", M * d * 2);
-  __nv_bfloat16* qkv = (__nv_bfloat16*)wxb_named(ctx, "enc.qkv", M * 3 * d * 2);
-  __nv_bfloat16* att = (__nv_bfloat16*)wxb_named(ctx, "enc.att", M * d * 2);
-  __nv_bfloat16* hid = (__nv_bfloat16*)wxb_named(ctx, "enc.hid", M * 4 * d * 2);
+  __nv_bfloat16* xn = (__nv_bfloat16*)wxb_named(ctx, "enc.xn", Mg * d * 2);
+  __nv_bfloat16* qkv = (__nv_bfloat16*)wxb_named(ctx, "enc.qkv", Mg * 3 * d * 2);
+  __nv_bfloat16* att = (__nv_bfloat16*)wxb_named(ctx, "enc.att", Mg * d * 2);
+  __nv_bfloat16* hid = (__nv_bfloat16*)wxb_named(ctx, "enc.hid", Mg * 4 * d * 2);
   if (!melT || !h1 || !x || !xn || !qkv || !att || !hid) return WXB_ERR_CUDA;
 
   const __nv_bfloat16* c1w = (const __nv_bfloat16*)wxb_weight(ctx, "enc.conv1.w");
@@ -178,38 +187,44 @@ int wxb_encode_impl(wxb_ctx* ctx, const float* mel_dev, int B, __nv_bfloat16* en
     a.g_in = T_AUDIO + 1; a.g_valid = T_AUDIO; a.g_out = T_AUDIO; a.out_off = 0;
     if ((rc = wxb_gemm_launch(ctx, a, st)) != WXB_OK) return rc;
   }
-  for (int l = 0; l < D.n_audio_layer; ++l) {
-    EncLayerW w;
-    if ((rc = wxb_enc_layer(ctx, l, &w)) != WXB_OK) return rc;
-    if ((rc = launch_layernorm(ctx, x, w.ln1_w, w.ln1_b, xn, M, d, st)) != WXB_OK) return rc;
-    {
-      GemmArgs a;
-      a.A = xn; a.lda = d; a.M = (int)M; a.W = w.qkv_w; a.N = 3 * d; a.K = d; a.bias = w.qkv_b;
-      a.out = qkv; a.ldo = 3 * d;
-      if ((rc = wxb_gemm_launch(ctx, a, st)) != WXB_OK) return rc;
+  for (int b0 = 0; b0 < B; b0 += Bs) {
+    const int nb = (B - b0 < Bs) ? B - b0 : Bs;
+    const long long Mb = (long long)nb * T_AUDIO;
+    float* xg = x + (size_t)b0 * T_AUDIO * d;
+    for (int l = 0; l < D.n_audio_layer; ++l) {
+      EncLayerW w;
+      if ((rc = wxb_enc_layer(ctx, l, &w)) != WXB_OK) return rc;
+      if ((rc = launch_layernorm(ctx, xg, w.ln1_w, w.ln1_b, xn, Mb, d, st)) != WXB_OK) return rc;
+      {
+        GemmArgs a;
+        a.A = xn; a.lda = d; a.M = (int)Mb; a.W = w.qkv_w; a.N = 3 * d; a.K = d; a.bias = w.qkv_b;
+        a.out = qkv; a.ldo = 3 * d;
+        if ((rc = wxb_gemm_launch(ctx, a, st)) != WXB_OK) return rc;
+      }
+      if ((rc = wxb_attention_tc(ctx, qkv, att, nb, T_AUDIO, d, H, nullptr, st)) != WXB_OK) return rc;
+      {
+        GemmArgs a;
+        a.A = att; a.lda = d; a.M = (int)Mb; a.W = w.out_w; a.N = d; a.K = d; a.bias = w.out_b;
+        a.residual = xg; a.res_mode = 1; a.ldr = d; a.out = xg; a.out_f32 = 1; a.ldo = d;
+        if ((rc = wxb_gemm_launch(ctx, a, st)) != WXB_OK) return rc;
+      }
+      if ((rc = launch_layernorm(ctx, xg, w.ln2_w, w.ln2_b, xn, Mb, d, st)) != WXB_OK) return rc;
+      {
+        GemmArgs a;
+        a.A = xn; a.lda = d; a.M = (int)Mb; a.W = w.fc1_w; a.N = 4 * d; a.K = d; a.bias = w.fc1_b; a.gelu = 1;
+        a.out = hid; a.ldo = 4 * d;
+        if ((rc = wxb_gemm_launch(ctx, a, st)) != WXB_OK) return rc;
+      }
+      {
+        GemmArgs a;
+        a.A = hid; a.lda = 4 * d; a.M = (int)Mb; a.W = w.fc2_w; a.N = d; a.K = 4 * d; a.bias = w.fc2_b;
+        a.residual = xg; a.res_mode = 1; a.ldr = d; a.out = xg; a.out_f32 = 1; a.ldo = d;
+        if ((rc = wxb_gemm_launch(ctx, a, st)) != WXB_OK) return rc;
+      }
     }
-    if ((rc = wxb_attention_tc(ctx, qkv, att, B, T_AUDIO, d, H, nullptr, st)) != WXB_OK) return rc;
-    {
-      GemmArgs a;
-      a.A = att; a.lda = d; a.M = (int)M; a.W = w.out_w; a.N = d; a.K = d; a.bias = w.out_b;
-      a.residual = x; a.res_mode = 1; a.ldr = d; a.out = x; a.out_f32 = 1; a.ldo = d;
-      if ((rc = wxb_gemm_launch(ctx, a, st)) != WXB_OK) return rc;
-    }
-    if ((rc = launch_layernorm(ctx, x, w.ln2_w, w.ln2_b, xn, M, d, st)) != WXB_OK) return rc;
-    {
-      GemmArgs a;
-      a.A = xn; a.lda = d; a.M = (int)M; a.W = w.fc1_w; a.N = 4 * d; a.K = d; a.bias = w.fc1_b; a.gelu = 1;
-      a.out = hid; a.ldo = 4 * d;
-      if ((rc = wxb_gemm_launch(ctx, a, st)) != WXB_OK) return rc;
-    }
-    {
-      GemmArgs a;
-      a.A = hid; a.lda = 4 * d; a.M = (int)M; a.W = w.fc2_w; a.N = d; a.K = 4 * d; a.bias = w.fc2_b;
-      a.residual = x; a.res_mode = 1; a.ldr = d; a.out = x; a.out_f32 = 1; a.ldo = d;
-      if ((rc = wxb_gemm_launch(ctx, a, st)) != WXB_OK) return rc;
-    }
+    if ((rc = launch_layernorm(ctx, xg, lnp_w, lnp_b, enc_out + (size_t)b0 * T_AUDIO * d, Mb, d, st)) != WXB_OK) return rc;
   }
-  return launch_layernorm(ctx, x, lnp_w, lnp_b, enc_out, M, d, st);
+  return WXB_OK;
 }
 
 extern "C" int wxb_encoder_attention(wxb_ctx* ctx, const void* qkv_dev, void* out_dev, int B, int T, int d, int H, void* stream) {
