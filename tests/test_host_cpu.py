@@ -175,6 +175,27 @@ def test_align_assembly_numpy_path_equals_pandas_path():
             assert a == b, (case, a, b)
             n_checked += 1
     assert n_checked == 120
+    # long words (8+ characters take ndarray.sum's pairwise order), scores that are multiples of 0.001 (word means then sit ON
+    # the rounding boundaries of round(., 3) all the time), double spaces, numpy-array runs as _merge_runs returns them
+    for case in range(120):
+        n_words = int(rng.randint(1, 40))
+        words = ["".join(rng.choice(list(letters + "4"), size=int(rng.randint(1, 20)))) for _ in range(n_words)]
+        text = (" " if case % 3 == 0 else "") + (" " if case % 4 else "  ").join(words) + ("  " if case % 5 == 0 else "")
+        prep = al._prepare_segment(text, {c: i for i, c in enumerate("-|" + letters)}, True)
+        if case % 2:
+            prep["clean_cdx"] = [c for c, ch in zip(prep["clean_cdx"], prep["clean_char"]) if ch != "*"]
+        t = 0
+        segs = []
+        for _ in prep["clean_cdx"]:
+            dur = int(rng.randint(1, 9))
+            segs.append(al.Segment("x", t, t + dur, float(np.round(rng.rand(), 3)) if case % 2 else float(rng.rand())))
+            t += dur + int(rng.randint(0, 3))
+        runs = (np.array([g.start for g in segs]), np.array([g.end for g in segs]), np.array([g.score for g in segs]))
+        t1 = float(rng.uniform(0, 1800))
+        for chars in (False, True):
+            a = al._assemble(text, prep, runs, 0.020013342228152101, t1, True, "nearest", chars)
+            b = al._assemble_pandas(text, prep, segs, 0.020013342228152101, t1, True, "nearest", chars)
+            assert a == b, (case, a, b)
     # run-length merge straight from the per-frame arrays == the reference's merge over Point objects
     for T in (1, 7, 300):
         tok = np.sort(rng.randint(0, 40, size=T)).astype(np.int32)

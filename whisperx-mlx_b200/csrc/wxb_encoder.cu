@@ -130,7 +130,9 @@ int wxb_launch_layernorm(wxb_ctx* ctx, const float* x, const float* w, const flo
 }
 
 #ifndef WXB_ENC_GROUP
-#define WXB_ENC_GROUP 0  // default chunk-group size of the layer stack (0 = whole batch)
+// default chunk-group size of the layer stack (0 = whole batch).  Measured on the 60-chunk large-v3 job (tools/ab_enc_group.sh, one
+// gpurun call): whole batch 170.5 ms, groups of 6 / 8 / 10 169.3-170.3, 12 / 15 166.4, 20 168.0, 30 170.2 ms.
+#define WXB_ENC_GROUP 15
 #endif
 int wxb_encode_impl(wxb_ctx* ctx, const float* mel_dev, int B, __nv_bfloat16* enc_out, cudaStream_t st) {
   if (!ctx->model) return wxb_fail(ctx, WXB_ERR_STATE, "wxb_encode: no model set");

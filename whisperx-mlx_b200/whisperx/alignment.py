@@ -489,6 +489,7 @@ def _assemble(text, prep, runs, ratio, t1, spaced, interpolate_method, return_ch
         runs = ([g.start for g in runs], [g.end for g in runs], [g.score for g in runs])
     if len(spans) == 1:
         return _assemble_single_sentence(text, prep, runs, ratio, t1, spaced, return_char_alignments)
+    runs = tuple(np.asarray(r).tolist() for r in runs)  # plain Python ints / floats, as merge_repeats produces them
     char_segments = [Segment("", a, b, v) for a, b, v in zip(*runs)]  # the pandas path only reads start / end / score
     return _assemble_pandas(text, prep, char_segments, ratio, t1, spaced, interpolate_method, return_char_alignments)
 
@@ -539,39 +540,65 @@ def _assemble_single_sentence(text, prep, runs, ratio, t1, spaced, return_char_a
     sc_m = np.where(sp, np.nan, score[sel])
     w_start = np.fmin.reduceat(st_m, first)
     w_end = np.fmax.reduceat(en_m, first)
-    n_ns = np.add.reduceat((~sp).astype(np.int64), first).tolist()   # non-space characters per word
+    n_ns = np.add.reduceat((~sp).astype(np.int64), first)   # non-space characters per word
     # score: pandas' nanmean = ONE ndarray.sum over the word's non-space characters with NaNs counted as 0, divided by the
-    # number of non-NaN values.  ndarray.sum's association is its own (neither left-to-right nor reduceat's); the orders
-    # differ by an ulp, which matters only when the mean sits on a rounding boundary of round(., 3): those words (and only
-    # those) are re-summed with ndarray.sum itself on the compacted array.
+    # number of non-NaN values, then round(., 3).  The sum must associate exactly as ndarray.sum does, or a mean that sits on a
+    # rounding boundary of round(., 3) (every other two-letter word: scores are multiples of 0.001) rounds the other way:
+    #   * fewer than 8 addends: ndarray.sum adds left to right.  All such words are summed at once, column by column over a
+    #     [words, 7] gather of the compacted scores (trailing zeros are exact);
+    #   * 8 or more: ndarray.sum is pairwise with its own blocking.  reduceat's order differs from it by an ulp at most, which
+    #     matters only on a rounding boundary: those words (and only those) are re-summed with ndarray.sum itself.
     sc_ns = score[sel][~sp]
     ok_ns = ~np.isnan(sc_ns)
     z_ns = np.where(ok_ns, sc_ns, 0.0)
-    ok_cum = np.concatenate([[0], np.cumsum(ok_ns)]).tolist()
-    ok_m = ~np.isnan(sc_m)
+    j1 = np.cumsum(n_ns)
+    j0 = j1 - n_ns                                             # word k owns z_ns[j0[k]:j1[k]]
+    ok_cum = np.concatenate([[0], np.cumsum(ok_ns)])
+    cnt = ok_cum[j1] - ok_cum[j0]                              # non-NaN scores per word
+    zp = np.concatenate([z_ns, np.zeros(7)])
+    col = np.arange(7)
+    vals = np.where(col[None, :] < n_ns[:, None], zp[j0[:, None] + col[None, :]], 0.0)
+    acc = vals[:, 0].copy()
+    for c in range(1, 7):
+        acc += vals[:, c]
     with np.errstate(invalid="ignore", divide="ignore"):
-        mean_fast = np.add.reduceat(np.where(ok_m, sc_m, 0.0), first) / np.add.reduceat(ok_m.astype(np.int64), first)
-        y = mean_fast * 1000.0
-        on_boundary = (np.abs(y - np.floor(y) - 0.5) < 1e-6).tolist()
-    score_fast = np.round(mean_fast, 3)
-    bounds = first.tolist() + [hi + 1 - lo]
-    has_s, has_e = (~np.isnan(w_start)).tolist(), (~np.isnan(w_end)).tolist()
-    j = 0  # cursor into the compacted (non-space) arrays
-    for k in range(len(first)):
-        c, e = lo + bounds[k], lo + bounds[k + 1]
-        j0, j = j, j + n_ns[k]
-        wtext = text[c:e].strip()
-        if not wtext:
-            continue
-        entry = {"word": wtext}
-        if has_s[k]:
-            entry["start"] = w_start[k]
-        if has_e[k]:
-            entry["end"] = w_end[k]
-        cnt = ok_cum[j] - ok_cum[j0]
-        if cnt:
-            entry["score"] = np.round(z_ns[j0:j].sum() / cnt, 3) if on_boundary[k] else score_fast[k]
-        words.append(entry)
+        w_score = np.round(acc / cnt, 3)
+        big = np.flatnonzero((n_ns >= 8) & (cnt > 0))
+        if big.size:
+            ok_m = ~np.isnan(sc_m)
+            mean_fast = np.add.reduceat(np.where(ok_m, sc_m, 0.0), first)[big] / cnt[big]
+            y = mean_fast * 1000.0
+            w_score[big] = np.round(mean_fast, 3)
+            for k in big[np.abs(y - np.floor(y) - 0.5) < 1e-6].tolist():
+                w_score[k] = np.round(z_ns[j0[k]:j1[k]].sum() / cnt[k], 3)
+    wtexts = None
+    if spaced:
+        # a group = a space and the characters up to the next space: the pieces of str.split(" "), minus the empty piece in
+        # front of a leading space
+        pieces = text[lo:hi + 1].split(" ")
+        if sp[0]:
+            del pieces[0]
+        if len(pieces) == len(first):
+            wtexts = [p.strip() for p in pieces]
+    if wtexts is None:
+        bounds = (first + lo).tolist() + [hi + 1]
+        wtexts = [text[c:e].strip() for c, e in zip(bounds[:-1], bounds[1:])]
+    full = (~np.isnan(w_start)) & (~np.isnan(w_end)) & (cnt > 0)
+    if full.all():  # the usual case: every word has its times and a score
+        words = [{"word": t, "start": a, "end": b, "score": c} for t, a, b, c in zip(wtexts, w_start, w_end, w_score) if t]
+    else:
+        has_s, has_e, has_c = (~np.isnan(w_start)).tolist(), (~np.isnan(w_end)).tolist(), (cnt > 0).tolist()
+        for k, wtext in enumerate(wtexts):
+            if not wtext:
+                continue
+            entry = {"word": wtext}
+            if has_s[k]:
+                entry["start"] = w_start[k]
+            if has_e[k]:
+                entry["end"] = w_end[k]
+            if has_c[k]:
+                entry["score"] = w_score[k]
+            words.append(entry)
     ns = np.flatnonzero(~sp) + lo
     sent_start = np.fmin.reduce(start[sel]) if hi >= lo else np.nan
     sent_end = np.fmax.reduce(end[ns]) if ns.size else np.nan
@@ -603,8 +630,8 @@ def _merge_runs(path_tok: np.ndarray, path_prob: np.ndarray):
         return [], [], []
     cut = np.flatnonzero(path_tok[1:] != path_tok[:-1]) + 1
     first = np.concatenate([[0], cut])
-    lo, hi = first.tolist(), cut.tolist() + [T]
-    length = np.diff(np.concatenate([first, [T]]))
+    hi_arr = np.concatenate([cut, [T]])
+    length = hi_arr - first
     # The probabilities are float32 values: a double sum of a few of them is EXACT (no rounding at all, hence independent of
     # the summation order and of Python's compensated sum) whenever the binary exponents inside the run span less than
     # 53 - 24 - log2(length) bits.  Those runs are summed with one reduceat; the rest (a run mixing ~1 and ~1e-9) take
@@ -616,16 +643,17 @@ def _merge_runs(path_tok: np.ndarray, path_prob: np.ndarray):
     e_max = np.maximum.reduceat(np.where(p64 == 0.0, -10000, ex), first)
     exact = (e_max - e_min <= 24) & (length <= 16)
     sums = np.add.reduceat(p64, first)
-    mean = (sums / length).tolist()
+    mean = sums / length
     if not exact.all():
         prob = p64.tolist()
+        lo, hi = first.tolist(), hi_arr.tolist()
         for k in np.flatnonzero(~exact).tolist():
             mean[k] = sum(prob[lo[k]:hi[k]]) / (hi[k] - lo[k])
-    return lo, hi, mean
+    return first, hi_arr, mean
 
 
 def _merge_repeats_arrays(path_tok: np.ndarray, path_prob: np.ndarray, transcript: str) -> List[Segment]:
-    lo, hi, sc = _merge_runs(path_tok, path_prob)
+    lo, hi, sc = (np.asarray(r).tolist() for r in _merge_runs(path_tok, path_prob))
     tok = path_tok.tolist()
     return [Segment(transcript[tok[a]], a, b, v) for a, b, v in zip(lo, hi, sc)]
 
