@@ -129,6 +129,55 @@ def test_ctc_many_ragged_segments_one_launch(wxb_ctx):
             assert np.allclose(np.exp(plp[a:b]), [p.score for p in ref], rtol=1e-6), (fn, i)
 
 
+@pytest.mark.parametrize("nmax", [200, 256, 257, 512, 513, 1040, 1088, 1089, 1300])
+def test_ctc_every_recurrence_variant_bit_exact(wxb_ctx, nmax):
+    """The launch picks the trellis recurrence by its longest segment: the row in registers with 8 / 16 / 34 columns per lane
+    (N <= 256 / 512 / 1088), shared-memory rows beyond.  Each variant, at its boundaries, with shorter segments (lanes without
+    columns, N = 1, N = 33) and wildcards in the same launch: trellis bits, path indices and probabilities vs the oracle."""
+    from whisperx._native import CTC_BACKTRACK, CTC_BEAM2
+    rng = np.random.RandomState(nmax)
+    V, blank = 29, 0
+    shapes = [(1499, nmax), (1499, max(1, nmax // 3)), (400, 33), (300, 1), (1499, nmax - 1)]
+    ems, toks = [], []
+    for i, (T, N) in enumerate(shapes):
+        g = torch.Generator().manual_seed(nmax + i)
+        ems.append(torch.log_softmax(torch.randn(T, V, generator=g) / (0.3 if i % 2 else 1.0), -1).numpy())
+        t = rng.randint(1, V, size=N)
+        if i != 4:
+            t[rng.rand(N) < 0.05] = -1
+        toks.append(t.astype(np.int32))
+    e = torch.from_numpy(np.concatenate(ems)).cuda()
+    tk = torch.from_numpy(np.concatenate(toks)).cuda()
+    t_off = np.concatenate([[0], np.cumsum([s[0] for s in shapes])])
+    n_off = np.concatenate([[0], np.cumsum([s[1] for s in shapes])])
+    trs = [octc.get_trellis(ems[i], toks[i].tolist(), blank) for i in range(len(shapes))]
+    for mode in (CTC_BACKTRACK, CTC_BEAM2):
+        r = wxb_ctx.ctc_align(e, t_off, tk, n_off, blank, mode, want_trellis=True)
+        status = r["status"].cpu().numpy()
+        ptok = r["path_tok"].cpu().numpy()
+        plp = r["path_lp"].cpu().numpy()
+        trg = r["trellis"].cpu().numpy()
+        o = 0
+        for i, (T, N) in enumerate(shapes):
+            got = trg[o:o + T * N].reshape(T, N)
+            o += T * N
+            assert np.array_equal(got.view(np.uint32), np.asarray(trs[i], dtype=np.float32).view(np.uint32)), (nmax, mode, i)
+            if mode == CTC_BACKTRACK:
+                try:
+                    ref = octc.backtrack(trs[i], ems[i], toks[i].tolist(), blank)
+                except AssertionError:
+                    ref = None
+            else:
+                ref = octc.backtrack_beam(trs[i], ems[i], toks[i].tolist(), blank, beam_width=2)
+            if ref is None:
+                assert status[i] == 1, (nmax, mode, i)
+                continue
+            assert status[i] == 0, (nmax, mode, i)
+            a, b = t_off[i], t_off[i + 1]
+            assert ptok[a:b].tolist() == [p.token_index for p in ref], (nmax, mode, i)
+            assert np.allclose(np.exp(plp[a:b]), [p.score for p in ref], rtol=1e-6), (nmax, mode, i)
+
+
 def test_log_softmax_rows(wxb_ctx):
     x = torch.randn(1499, 29, generator=torch.Generator().manual_seed(0)) * 4
     got = wxb_ctx.log_softmax_rows_(x.clone().cuda()).cpu()

@@ -46,6 +46,43 @@ def step():
 for _ in range(2):
     step()
 sections.clear()
+
+# ---- pass 1, WITHOUT a profiler (cProfile inflates the Python-heavy host parts several times over): wall-clock sums of a few
+# coarse functions, wrapped in place
+import whisperx.alignment as _al  # noqa: E402
+
+
+def _wrap(obj, name, key):
+    f = getattr(obj, name)
+
+    def g(*a, **k):
+        t0 = time.perf_counter()
+        try:
+            return f(*a, **k)
+        finally:
+            sections.setdefault(key, []).append(time.perf_counter() - t0)
+    setattr(obj, name, g)
+    return f
+
+
+be = pipe.backend
+saved = [(be, "upload_chunks", _wrap(be, "upload_chunks", "  transcribe: upload_chunks (pinned copy + H2D enqueue)")),
+         (be, "transcribe_device", _wrap(be, "transcribe_device", "  transcribe: transcribe_device (mel + encoder + decode, blocks in the EOT polls)")),
+         (be.tokenizer, "decode", _wrap(be.tokenizer, "decode", "  transcribe: tokenizer.decode (sum over segments)")),
+         (be, "transcribe_batch", _wrap(be, "transcribe_batch", "transcribe_batch")),
+         (_al, "_prepare_segment", _wrap(_al, "_prepare_segment", "  align: _prepare_segment (sum)")),
+         (_al, "_assemble", _wrap(_al, "_assemble", "  align: _assemble (sum)")),
+         (_al, "_merge_runs", _wrap(_al, "_merge_runs", "  align: _merge_runs (sum)")),
+         (bundle[0], "emissions", _wrap(bundle[0], "emissions", "  align: model.emissions (upload + forward enqueue, sum over groups)"))]
+for _ in range(steps):
+    step()
+n = steps
+print("un-profiled pass, ms per step:")
+for k, v in sections.items():
+    print("  %-90s %8.1f" % (k, 1e3 * sum(v) / n))
+for obj, name, f in saved:
+    setattr(obj, name, f)
+sections.clear()
 pr = cProfile.Profile()
 pr.enable()
 for _ in range(steps):

@@ -35,6 +35,19 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
+// nanmax (torch.maximum: the first NaN operand wins, else the larger) as selects: no branch for the compiler to build blocks from
+__device__ __forceinline__ float nanmax_sel(float a, float b) {
+  float r;
+  asm("{\n\t.reg .pred p, q;\n\t.reg .f32 m;\n\t"
+      "max.f32 m, %1, %2;\n\t"
+      "setp.nan.f32 q, %2, %2;\n\t"
+      "selp.f32 m, %2, m, q;\n\t"
+      "setp.nan.f32 p, %1, %1;\n\t"
+      "selp.f32 %0, %1, m, p;\n\t}"
+      : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+
 // max over v != blank of row[v]  (warp-uniform result)
 __device__ __forceinline__ float wild_max_global(const float* row, int V, int blank, int lane) {
   float m = -INFINITY;
@@ -43,7 +56,15 @@ __device__ __forceinline__ float wild_max_global(const float* row, int V, int bl
   return warp_max(m);
 }
 
-template <int WMAX>  // beam arrays sized (and loops unrolled) for widths <= WMAX: 2 keeps align()'s walk in registers
+// WMAX: beam arrays sized (and loops unrolled) for widths <= WMAX: 2 keeps align()'s walk in registers.
+// KREG > 0: every segment of the launch has N <= 32 KREG tokens and the trellis recurrence keeps the current row in REGISTERS:
+// lane l owns columns l, l + 32, .. (a warp's store of one register is 128 contiguous bytes of the trellis row), the left
+// neighbour's value arrives by one rotate-shuffle per column, the emission offset of every column's token is a register too,
+// and a step is KREG independent {SHFL, LDS, 2 FADD, max, STG} groups with no shared-memory row, no per-column branch and no
+// store -> load ordering.  (Consecutive columns per lane need one shuffle per STEP, but then every store instruction touches 32
+// different sectors: measured 3.44 ms vs 4.55 ms for the shared-memory rows at N = 1040, store-transaction bound.)
+// KREG = 0 is the general path (rows ping-pong in shared memory, any N that fits).  Same adds, same max per cell: same bits.
+template <int WMAX, int KREG>
 __global__ void __launch_bounds__(CTC_WARPS * 32)
 ctc_align_kernel(const float* __restrict__ emis, const int* __restrict__ tok,
                  const CtcSeg* __restrict__ segs, int n_seg, int V, int Vpad, int blank, int mode,
@@ -88,6 +109,74 @@ ctc_align_kernel(const float* __restrict__ emis, const int* __restrict__ tok,
   int inf_start = (N == 1) ? 0 : (T - N + 1);
   if (inf_start < 0) inf_start = 0;
 
+  if (KREG > 0) {
+    __syncwarp();  // stok is complete
+    constexpr int KR = KREG > 0 ? KREG : 1;
+    const int kl = (N - lane + 31) >> 5;  // this lane's columns lane + 32 k, k < kl, exist
+    float cur[KR];
+    int toff[KR];  // byte offset of the column's emission inside a ring row; wildcards read the spare slot V (the step's wc)
+#pragma unroll
+    for (int k = 0; k < KR; ++k) {
+      const int j = lane + 32 * k;
+      const int tkn = (j < N) ? stok[j] : 0;
+      toff[k] = 4 * (tkn < 0 ? V : tkn);
+      cur[k] = (j == 0) ? ((0 >= inf_start) ? INFINITY : 0.f) : -INFINITY;
+      if (k < kl) TR[j] = cur[k];
+    }
+    for (int r = 0; r < CTC_PD; ++r) {
+      if (r < T)
+        for (int v = lane; v < V; v += 32) cp_async4(ering + (r % CTC_RING) * Vpad + v, E + (size_t)r * V + v);
+      cp_async_commit();
+    }
+    double acc = 0.0;  // lane 0 only: fp64 accumulator of the blank column (torch CPU cumsum)
+    for (int t = 0; t < T - 1; ++t) {
+      {
+        const int r = t + CTC_PD;
+        if (r < T)
+          for (int v = lane; v < V; v += 32) cp_async4(ering + (r % CTC_RING) * Vpad + v, E + (size_t)r * V + v);
+        cp_async_commit();
+      }
+      cp_async_wait<CTC_PD - 1>();  // rows <= t+1 have landed
+      __syncwarp();
+      float* er = ering + (t % CTC_RING) * Vpad;
+      const float* er1 = ering + ((t + 1) % CTC_RING) * Vpad;
+      const float eb = er[blank];
+      if (has_wild) {
+        float wc = -INFINITY;
+        for (int v = lane; v < V; v += 32)
+          if (v != blank) wc = fmaxf(wc, er[v]);
+        wc = warp_max(wc);
+        if (lane == 0) er[V] = wc;  // spare slot behind the V labels (Vpad > V)
+        __syncwarp();
+      }
+      float c0 = 0.f;
+      if (lane == 0) {
+        acc += (double)er1[blank];
+        c0 = (t + 1 >= inf_start) ? INFINITY : (float)acc;
+      }
+      float* trow = TR + (size_t)(t + 1) * N + lane;
+      const char* erb = reinterpret_cast<const char*>(er);
+      const int src = (lane + 31) & 31;  // rotate: lane l reads lane l - 1, lane 0 reads lane 31
+      // column j - 1 of the current row: lane l - 1's cur[k]; for lane 0 it is lane 31's cur[k - 1].  All rotates first, then a
+      // branch-free body (nanmax_sel, predicated stores): one basic block, so the scheduler overlaps the columns' LDS / FADD
+      // chains.  With a shuffle or a branch inside every column's code each column was its own block: ~125 cycles apiece.
+      float rot[KR];
+#pragma unroll
+      for (int k = 0; k < KR; ++k) rot[k] = __shfl_sync(0xffffffffu, cur[k], src);
+#pragma unroll
+      for (int k = 0; k < KR; ++k) {
+        const float left = (lane == 0) ? rot[k > 0 ? k - 1 : 0] : rot[k];
+        const float w = *reinterpret_cast<const float*>(erb + toff[k]);
+        float nv = nanmax_sel(__fadd_rn(cur[k], eb), __fadd_rn(left, w));
+        if (k == 0) nv = (lane == 0) ? c0 : nv;
+        cur[k] = nv;
+        if (k < kl) trow[32 * k] = nv;
+      }
+      __syncwarp();  // every lane is done with ring row t before a later cp.async lands on its slot
+    }
+    cp_async_wait<0>();
+    __syncwarp();
+  } else {
   float* prev = rowA;
   float* next = rowB;
   for (int j = lane; j < N; j += 32) {
@@ -146,6 +235,7 @@ ctc_align_kernel(const float* __restrict__ emis, const int* __restrict__ tok,
   }
   cp_async_wait<0>();
   __syncwarp();
+  }
   if (mode == WXB_CTC_TRELLIS_ONLY) {
     if (lane == 0) status[seg_id] = 0;
     return;
@@ -168,10 +258,11 @@ ctc_align_kernel(const float* __restrict__ emis, const int* __restrict__ tok,
       const float* erow = E + (size_t)(t - 1) * V;
       const float p_stay = __ldg(erow + blank);
       const int tkn = stok[j];
-      const float p_change = (tkn < 0) ? wild_max_global(erow, V, blank, lane) : __ldg(erow + tkn);
       const float* trow = TR + (size_t)(t - 1) * N;
-      const float stayed = __fadd_rn(trow[j], p_stay);
-      const float changed = __fadd_rn(trow[j - 1], p_change);
+      const float tr_j = trow[j], tr_j1 = trow[j - 1];  // requested together with the emissions: one round trip per step
+      const float p_change = (tkn < 0) ? wild_max_global(erow, V, blank, lane) : __ldg(erow + tkn);
+      const float stayed = __fadd_rn(tr_j, p_stay);
+      const float changed = __fadd_rn(tr_j1, p_change);
       t -= 1;
       const bool ch = changed > stayed;
       if (ch) j -= 1;
@@ -212,17 +303,30 @@ ctc_align_kernel(const float* __restrict__ emis, const int* __restrict__ tok,
       const float* erow = E + (size_t)(t - 1) * V;
       const float* trow = TR + (size_t)(t - 1) * N;
       const float p_stay = __ldg(erow + blank);
+      // Everything a step reads depends only on the beams' positions: the predecessor cells of every beam and the emission
+      // of its token are requested together (one L2 round trip per step).  Read one after the other behind the isinf tests,
+      // they were three dependent round trips per beam, ~5000 cycles per step.
+      float ss[WMAX], sc[WMAX], pc[WMAX];
+#pragma unroll
+      for (int i = 0; i < WMAX; ++i) {
+        if (i < nb) {
+          const int j = bj[i];
+          const int tkn = stok[j];
+          ss[i] = trow[j];
+          sc[i] = trow[j > 0 ? j - 1 : 0];
+          pc[i] = __ldg(erow + (tkn < 0 ? blank : tkn));
+        }
+      }
 #pragma unroll
       for (int i = 0; i < WMAX; ++i) {
         if (i >= nb) break;
         const int j = bj[i];
-        const float stay_score = trow[j];
+        const float stay_score = ss[i];
         if (!isinf(stay_score)) { cj[nc] = j; cs[nc] = stay_score; cp[nc] = i; cl[nc] = p_stay; nc++; }
         if (j > 0) {
-          const float change_score = trow[j - 1];
+          const float change_score = sc[i];
           if (!isinf(change_score)) {
-            const int tkn = stok[j];
-            const float p_change = (tkn < 0) ? wild_max_global(erow, V, blank, lane) : __ldg(erow + tkn);
+            const float p_change = (stok[j] < 0) ? wild_max_global(erow, V, blank, lane) : pc[i];
             cj[nc] = j - 1; cs[nc] = change_score; cp[nc] = i; cl[nc] = p_change; nc++;
           }
         }
@@ -332,7 +436,7 @@ int wxb_ctc_align(wxb_ctx* ctx, const float* emis_dev, const int32_t* t_off_host
   }
   const long long sumT = t_off_host[n_seg];
   const int nmax_pad = (nmax + 31) & ~31;
-  const int Vpad = (V + 3) & ~3;
+  const int Vpad = (V + 1 + 3) & ~3;  // ring row stride: the V labels + a spare slot for the step's wildcard emission
   // shared memory per warp: token ids + two trellis rows + the emission ring; large vocabularies (the ja / zh align models
   // have 2-3.5 k labels) get fewer warps per block instead of an error
   const size_t per_warp = (size_t)nmax_pad * 12 + (size_t)CTC_RING * Vpad * 4;
@@ -351,7 +455,14 @@ int wxb_ctc_align(wxb_ctx* ctx, const float* emis_dev, const int32_t* t_off_host
   WXB_CUDA(ctx, cudaMemcpyAsync(ctx->ws_ctc_meta.p, segs.data(), sizeof(CtcSeg) * n_seg, cudaMemcpyHostToDevice, st));
   // the pageable source buffer `segs` dies at return: the copy above is staged synchronously by
   // the runtime for pageable memory, so this is safe.
-  auto kern = beam_w <= 2 ? ctc_align_kernel<2> : ctc_align_kernel<CTC_WMAX>;
+  // register-resident recurrence when every segment fits 32 KREG columns (KREG in {8, 16, 34}), shared-memory rows otherwise
+  const int kreg = nmax <= 256 ? 8 : nmax <= 512 ? 16 : nmax <= 1088 ? 34 : 0;
+  auto kern = beam_w <= 2 ? (kreg == 8 ? ctc_align_kernel<2, 8> : kreg == 16 ? ctc_align_kernel<2, 16> : kreg == 34 ? ctc_align_kernel<2, 34> : ctc_align_kernel<2, 0>)
+                          : (kreg == 8 ? ctc_align_kernel<CTC_WMAX, 8> : kreg == 16 ? ctc_align_kernel<CTC_WMAX, 16>
+                             : kreg == 34 ? ctc_align_kernel<CTC_WMAX, 34> : ctc_align_kernel<CTC_WMAX, 0>);
+#ifdef WXB_PROBE
+  if (getenv("WXB_CTC_SMEM_ROWS")) kern = beam_w <= 2 ? ctc_align_kernel<2, 0> : ctc_align_kernel<CTC_WMAX, 0>;  // A/B: the general path
+#endif
   if ((rc = wxb_func_smem(ctx, kern, (int)smem)) != WXB_OK) return rc;
   const int grid = ceil_div(n_seg, wpb);
   kern<<<grid, wpb * 32, smem, st>>>(
