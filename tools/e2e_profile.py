@@ -65,6 +65,8 @@ def _wrap(obj, name, key):
     return f
 
 
+if os.environ.get("E2E_GROUPS"):  # A/B of align()'s pipeline depth: "groups,min_segments"
+    _al.PIPELINE_GROUPS, _al.PIPELINE_MIN_SEGMENTS = (int(v) for v in os.environ["E2E_GROUPS"].split(","))
 be = pipe.backend
 saved = [(be, "upload_chunks", _wrap(be, "upload_chunks", "  transcribe: upload_chunks (pinned copy + H2D enqueue)")),
          (be, "transcribe_device", _wrap(be, "transcribe_device", "  transcribe: transcribe_device (mel + encoder + decode, blocks in the EOT polls)")),
@@ -82,6 +84,13 @@ for k, v in sections.items():
     print("  %-90s %8.1f" % (k, 1e3 * sum(v) / n))
 for obj, name, f in saved:
     setattr(obj, name, f)
+# timeline of one align() call (whisperx.alignment.TRACE)
+_al.TRACE = []
+step()
+tr, _al.TRACE = _al.TRACE, None
+print("align() timeline of one step, ms since its start:")
+for label, t in tr:
+    print("  %8.2f  %s" % (1e3 * (t - tr[0][1]), label))
 sections.clear()
 pr = cProfile.Profile()
 pr.enable()

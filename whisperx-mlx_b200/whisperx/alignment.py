@@ -304,6 +304,19 @@ def _pinned(ctx, name: str, n: int, dtype) -> torch.Tensor:
     return t
 
 
+# align() runs its segments as a pipeline of at most this many groups of at least this many segments (GPU: forward + K4 of one
+# group while the host assembles the previous one)
+PIPELINE_GROUPS = 2     # measured on 60 x 30 s segments (tools/e2e_profile.py, E2E_GROUPS): 1 group 85.7 ms, 2: 78.3, 3: 81.3, 4: 87.6, 6: 99.1
+PIPELINE_MIN_SEGMENTS = 15  # per group: below this one batched forward is the better deal
+TRACE = None  # tools/e2e_profile.py sets this to a list: align() then appends (label, perf_counter()) at its pipeline points
+
+
+def _mark(label: str):
+    if TRACE is not None:
+        import time
+        TRACE.append((label, time.perf_counter()))
+
+
 def align(
     transcript: Iterable[SingleSegment],
     model: torch.nn.Module,
@@ -320,6 +333,7 @@ def align(
     builds the same char / word / sentence dicts."""
     from ._native import CTC_BEAM2
 
+    _mark("start")
     if not torch.is_tensor(audio):
         if isinstance(audio, str):
             audio = load_audio(audio)
@@ -348,6 +362,7 @@ def align(
         if ch == "[pad]" or ch == "<pad>":
             blank_id = code
 
+    _mark("segments prepared")
     # ---- pass 1: emissions of every alignable segment, kept on the device ------------------
     jobs = []  # (sdx, text_clean, tokens, T)
     emis_parts, tok_parts = [], []
@@ -390,14 +405,20 @@ def align(
     # blocking copy in between).  One group when there are few segments or a torch model produced the emissions.
     assembled = {}   # sdx -> list of aligned segments
     failed = {}      # sdx -> message
-    n_groups = min(4, max(1, len(jobs) // 15)) if native else 1
-    bounds = [len(jobs) * g // n_groups for g in range(n_groups + 1)]
+    n_groups = min(PIPELINE_GROUPS, max(1, len(jobs) // PIPELINE_MIN_SEGMENTS)) if native else 1
+    if n_groups == 2:
+        # two groups, the first twice the size of the second: the host work left over when the GPU is done is the assembly of
+        # the LAST group only, and a small batch costs the forward little once it is a third of the job
+        bounds = [0, (2 * len(jobs) + 2) // 3, len(jobs)]
+    else:
+        bounds = [len(jobs) * g // n_groups for g in range(n_groups + 1)]
     d2h_bytes = 0
     h2d_bytes = 0
     stats_sum = {"flops": 0.0, "frames": 0, "segments": 0}
 
     def launch(g, a, b):
         nonlocal h2d_bytes
+        _mark("launch %d: begin" % g)
         toks = np.concatenate(tok_parts[a:b]) if b > a else np.zeros(0, np.int32)
         t_off = np.concatenate([[0], np.cumsum([j[3] for j in jobs[a:b]])]).astype(np.int32)
         n_off = np.concatenate([[0], np.cumsum([len(t) for t in tok_parts[a:b]])]).astype(np.int32)
@@ -424,12 +445,15 @@ def align(
         h_lp[:sum_t].copy_(res["path_lp"], non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
+        _mark("launch %d: enqueued" % g)
         return (a, b, t_off, sum_t, h_status, h_tok, h_lp, ev, (emis, tok_dev, res))
 
     def finish(h):
         nonlocal d2h_bytes
         a, b, t_off, sum_t, h_status, h_tok, h_lp, ev, _keep = h
+        _mark("finish: wait for the GPU")
         ev.synchronize()
+        _mark("finish: paths on the host")
         status = h_status[: b - a].numpy()
         path_tok = h_tok[:sum_t].numpy()
         path_prob = torch.exp(h_lp[:sum_t]).numpy()
@@ -446,6 +470,7 @@ def align(
             ratio = (t2 - t1) * n_channels / (T - 1)
             assembled[sdx] = _assemble(text, prepared[sdx], runs, ratio, t1, spaced, interpolate_method, return_char_alignments)
 
+    _mark("tokens / waves listed")
     pending = None
     for g in range(n_groups):
         if bounds[g + 1] == bounds[g]:
@@ -458,6 +483,7 @@ def align(
         pending = h
     if pending is not None:
         finish(pending)
+    _mark("all groups assembled")
     if native and jobs:  # totals of this align() call (the groups' forwards each wrote their own)
         model.last_stats.update(d2h_bytes=d2h_bytes, h2d_bytes=h2d_bytes, **stats_sum)
 
@@ -476,6 +502,7 @@ def align(
     word_segments: List[SingleWordSegment] = []
     for seg in aligned_segments:
         word_segments += seg["words"]
+    _mark("end")
     return {"segments": aligned_segments, "word_segments": word_segments}
 
 
