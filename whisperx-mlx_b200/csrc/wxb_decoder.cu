@@ -177,6 +177,10 @@ struct SampleParams {
   int no_timestamps;   // <|notimestamps|> id, suppressed when the rules are on
   int max_initial_ts;  // max_initial_timestamp_index (50), < 0 = unlimited
   int* ts_last;        // [B] last sampled timestamp token of each row, -1 = none yet
+  // rows shared by several CTAs (persistent kernel only; nullptr = one CTA per row): slice statistics [B][R][8] and a
+  // zero-initialised, self-cleaning arrival counter per row
+  float* part_stats;
+  int* part_ticket;
 };
 
 // tensor-map table (device array): per layer {qkv, out, cq, cout, fc1, fc2} weight maps, then emb, xn, att, hid, cross K/V
@@ -1248,7 +1252,14 @@ __device__ __forceinline__ void sample_phase(const SampleParams& p, int B, int p
   const int tid = threadIdx.x;
   constexpr int U = 2;  // float4 loads in flight per thread (3 or more cost the persistent kernel a stack frame)
   const int V4 = (p.V + 3) >> 2;  // the padding elements of the last group are masked by index
-  for (int b = sy.cta; b < B; b += sy.nc) {
+  // A row is scanned by R CTAs, each over its own slice of the vocabulary (the scan is a latency-bound loop of L2 round trips:
+  // 17 iterations for one CTA at V = 51866, whatever the batch; with 8 rows on 148 CTAs R = 18 and it is one).  Slice statistics
+  // go through `part_stats`, the last CTA to arrive at the row's counter merges them (slice order) and samples.  The first step
+  // (no_speech_prob needs the unfiltered row) and the stand-alone sampling kernel keep one CTA per row.
+  const int R = (p.part_stats && do_sample && !p.nsp_out) ? max(1, sy.nc / B) : 1;
+  for (int unit = sy.cta; unit < B * R; unit += sy.nc) {
+    const int b = unit / R, part = unit - b * R;
+    const int g0 = (int)((long long)V4 * part / R), g1 = (int)((long long)V4 * (part + 1) / R);  // float4 groups of this slice
     float* x = p.logits + (size_t)b * p.ldl;
     const float4* x4 = reinterpret_cast<const float4*>(x);
     const int ob = s_rows[b];
@@ -1272,20 +1283,22 @@ __device__ __forceinline__ void sample_phase(const SampleParams& p, int B, int p
     }
     if (!do_sample) continue;
     __syncthreads();
+    // static filters, applied in place by the CTA whose slice holds the id (no CTA reads another slice)
+    const int e0 = 4 * g0, e1 = min(4 * g1, p.V);
     for (int i = tid; i < p.n_suppress; i += MK_THREADS) {
       const int id = p.suppress[i];
-      if (id >= 0 && id < p.V) x[id] = -INFINITY;
+      if (id >= e0 && id < e1) x[id] = -INFINITY;
     }
     if (p.suppress_blank && pos == p.prompt_len - 1 && tid == 0) {
-      if (p.blank_token >= 0 && p.blank_token < p.V) x[p.blank_token] = -INFINITY;
-      x[p.eot] = -INFINITY;
+      if (p.blank_token >= e0 && p.blank_token < e1) x[p.blank_token] = -INFINITY;
+      if (p.eot >= e0 && p.eot < e1) x[p.eot] = -INFINITY;
     }
     // range rules of this row: ids < lo_text are masked, timestamps in [ts_begin, ts_lo) and ids > ts_hi are masked
     int lo_text = 0, ts_lo = p.V, ts_hi = p.V - 1, tsb = p.V;
     const int* row_tok = p.tokens + (size_t)ob * p.stride;
     if (p.ts_rules) {
       tsb = p.ts_begin; ts_lo = tsb;
-      if (tid == 0 && p.no_timestamps >= 0 && p.no_timestamps < p.V) x[p.no_timestamps] = -INFINITY;
+      if (tid == 0 && p.no_timestamps >= e0 && p.no_timestamps < e1) x[p.no_timestamps] = -INFINITY;
       const int n_seq = pos + 1 - p.prompt_len;  // sampled tokens so far
       const bool last_ts = n_seq >= 1 && __ldcg(row_tok + pos) >= tsb;
       const bool pen_ts = n_seq < 2 || __ldcg(row_tok + pos - 1) >= tsb;
@@ -1306,11 +1319,11 @@ __device__ __forceinline__ void sample_phase(const SampleParams& p, int B, int p
     __syncthreads();
     RowStat tx = {-INFINITY, 0x7fffffff, 0.f}, tt = {-INFINITY, 0x7fffffff, 0.f};  // ids below / from ts_begin
     if (!p.ts_rules) {
-      // no range rule: one running (max, argmax, sum) over the whole row
-      for (int i0 = tid; i0 < V4; i0 += MK_THREADS * U) {
+      // no range rule: one running (max, argmax, sum) over the slice
+      for (int i0 = g0 + tid; i0 < g1; i0 += MK_THREADS * U) {
         float4 t[U];
 #pragma unroll
-        for (int j = 0; j < U; ++j) { const int i = i0 + MK_THREADS * j; t[j] = i < V4 ? __ldcg(x4 + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY); }
+        for (int j = 0; j < U; ++j) { const int i = i0 + MK_THREADS * j; t[j] = i < g1 ? __ldcg(x4 + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY); }
 #pragma unroll
         for (int j = 0; j < U; ++j) {
           const int i = 4 * (i0 + MK_THREADS * j);  // increasing within the thread: strict > keeps the first maximum
@@ -1321,10 +1334,10 @@ __device__ __forceinline__ void sample_phase(const SampleParams& p, int B, int p
         }
       }
     } else {
-      for (int i0 = tid; i0 < V4; i0 += MK_THREADS * U) {
+      for (int i0 = g0 + tid; i0 < g1; i0 += MK_THREADS * U) {
         float4 t[U];
 #pragma unroll
-        for (int j = 0; j < U; ++j) { const int i = i0 + MK_THREADS * j; t[j] = i < V4 ? __ldcg(x4 + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY); }
+        for (int j = 0; j < U; ++j) { const int i = i0 + MK_THREADS * j; t[j] = i < g1 ? __ldcg(x4 + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY); }
 #pragma unroll
         for (int j = 0; j < U; ++j) {
           const int i = 4 * (i0 + MK_THREADS * j);
@@ -1344,27 +1357,48 @@ __device__ __forceinline__ void sample_phase(const SampleParams& p, int B, int p
     stat_block(tx, red, red_i, red_s);
     if (p.ts_rules) stat_block(tt, red, red_i, red_s);
     if (tid == 0) {
-      float best = tx.m, ssum = tx.s;
-      int bi = tx.i;
-      if (p.ts_rules && tt.m > -INFINITY) {
-        // logsumexp over timestamps vs the best text logprob (the common normaliser cancels): timestamps win -> only they remain
-        const bool ts_only = !(tx.m > -INFINITY) || (tt.m + __logf(tt.s) > tx.m);
-        if (ts_only) { best = tt.m; bi = tt.i; ssum = tt.s; }
-        else {
-          RowStat all = tx;
-          stat_merge(all, tt.m, tt.i, tt.s);
-          best = all.m; bi = all.i; ssum = all.s;
+      bool mine = true;  // this CTA samples the row
+      if (R > 1) {
+        float* ps = p.part_stats + (size_t)(b * R + part) * 8;
+        ps[0] = tx.m; ps[1] = __int_as_float(tx.i); ps[2] = tx.s;
+        ps[3] = tt.m; ps[4] = __int_as_float(tt.i); ps[5] = tt.s;
+        __threadfence();
+        mine = atomicAdd(p.part_ticket + b, 1) == R - 1;
+        if (mine) {
+          __threadfence();
+          p.part_ticket[b] = 0;  // self-cleaning
+          tx = {-INFINITY, 0x7fffffff, 0.f}; tt = {-INFINITY, 0x7fffffff, 0.f};
+          for (int r = 0; r < R; ++r) {
+            const float* q = p.part_stats + (size_t)(b * R + r) * 8;
+            stat_merge(tx, __ldcg(q), __float_as_int(__ldcg(q + 1)), __ldcg(q + 2));
+            if (p.ts_rules) stat_merge(tt, __ldcg(q + 3), __float_as_int(__ldcg(q + 4)), __ldcg(q + 5));
+          }
         }
       }
-      const float logprob = -logf(ssum);  // x[bi] - (best + log(sum)) with x[bi] == best
-      int* row = p.tokens + (size_t)ob * p.stride;
-      const int last = __ldcg(row + pos);
-      const bool was_eot = (last == p.eot) && (pos >= p.prompt_len);  // prompt tokens never latch
-      if (!was_eot) p.sum_logprob[ob] += logprob;
-      const int next = was_eot ? p.eot : bi;
-      row[pos + 1] = next;
-      if (next == p.eot) p.done[ob] = 1;
-      if (p.ts_rules && next >= p.ts_begin) p.ts_last[ob] = next;
+      if (mine) {
+        float best = tx.m, ssum = tx.s;
+        int bi = tx.i;
+        if (p.ts_rules && tt.m > -INFINITY) {
+          // logsumexp over timestamps vs the best text logprob (the common normaliser cancels): timestamps win -> only they remain
+          const bool ts_only = !(tx.m > -INFINITY) || (tt.m + __logf(tt.s) > tx.m);
+          if (ts_only) { best = tt.m; bi = tt.i; ssum = tt.s; }
+          else {
+            RowStat all = tx;
+            stat_merge(all, tt.m, tt.i, tt.s);
+            best = all.m; bi = all.i; ssum = all.s;
+          }
+        }
+        const float logprob = -logf(ssum);  // x[bi] - (best + log(sum)) with x[bi] == best
+        int* row = p.tokens + (size_t)ob * p.stride;
+        const int last = __ldcg(row + pos);
+        const bool was_eot = (last == p.eot) && (pos >= p.prompt_len);  // prompt tokens never latch
+        if (!was_eot) p.sum_logprob[ob] += logprob;
+        const int next = was_eot ? p.eot : bi;
+        row[pos + 1] = next;
+        if (next == p.eot) p.done[ob] = 1;
+        if (p.ts_rules && next >= p.ts_begin) p.ts_last[ob] = next;
+        (void)best;
+      }
     }
     __syncthreads();
   }
@@ -1918,6 +1952,8 @@ int launch_group(wxb_ctx* ctx, const DecBuffers& buf, int region, int mode, int 
     return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: no GEMV tiling fits (d=%d, batch %d)", d, B);
   p.sp = sp;
   if (p.sp.logits) p.sp.logits += r0 * (size_t)p.sp.ldl;  // the sampling phase reads the group's rows of the scratch logits
+  p.sp.part_stats = p.apart;    // idle outside the cross-attention phases (<= 148 slices x 8 floats of the 1024 x 66)
+  p.sp.part_ticket = p.ticket;  // all zero outside the cross-attention phases
   p.scale = 1.0f / sqrtf(64.f);
   if (MT > GV_MAX_MT) return wxb_fail(ctx, WXB_ERR_UNSUPPORTED, "decoder: %d rows in one sequence group (at most %d)", B, 16 * GV_MAX_MT);
   void (*kern)(const MkParams) = MT == 1 ? dec_step_kernel<1> : dec_step_kernel<2>;
