@@ -90,6 +90,10 @@ constexpr int SST_BYTES = (2 * XA_CW * 66 * 4 + 127) & ~127;  // [2 item paritie
 constexpr int QRAW_ROWS = GK_MAX + 1;                     // bias row + up to GK_MAX split-K partial rows of q
 constexpr int QRAW_BYTES = 2 * QRAW_ROWS * 64 * 4;        // two items in flight
 constexpr int SCRATCH_BYTES = SST_BYTES + QRAW_BYTES;     // attention scratch behind the ring
+#ifndef WXB_XA_MG
+#define WXB_XA_MG 16
+#endif
+constexpr int XA_MG = WXB_XA_MG;  // piece states merged per L2 round trip
 constexpr int XA_NST = MK_WARPS == 8 ? 6 : MK_WARPS == 10 ? 5 : 4;  // K/V ring depth (stages of 2 x 16 XA_CW keys x 128 B)
 constexpr int GV_NST = MK_CTAS_PER_SM == 2 ? 4 : 6;  // GEMV ring depth
 #ifndef WXB_GV_NACC
@@ -1165,16 +1169,15 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, int x
           last = __shfl_sync(0xffffffffu, last, 0);
           if (last) {
             __threadfence();
-            // the P piece states: maxima spread over the lanes, then groups of four pieces with all 16 loads of a group in
-            // flight at once (one L2 round trip per group instead of one per piece; same summation order as a piece-by-piece loop)
-            float MM = -INFINITY;
-            for (int s2 = lane; s2 < P; s2 += 32) MM = fmaxf(MM, __ldcg(part + s2 * 66));
-            MM = warp_max(MM);
-            float LL = 0.f, O0 = 0.f, O1 = 0.f;
-            for (int s0 = 0; s0 < P; s0 += 4) {
-              float mv[4], lv[4], a0[4], a1[4];
+            // the P piece states in groups of XA_MG pieces, every load of a group in flight at once and the running offset
+            // carried across groups: ONE L2 round trip per group (P <= XA_MG: one in all).  A separate pass over the maxima
+            // plus groups of four were 4-5 dependent round trips at the very end of the phase: 4.4 us (batch 60) to 5.1 us
+            // (batch 8) of every layer (tools/xa_fixed_probe.sh).
+            float MM = -INFINITY, LL = 0.f, O0 = 0.f, O1 = 0.f;
+            for (int s0 = 0; s0 < P; s0 += XA_MG) {
+              float mv[XA_MG], lv[XA_MG], a0[XA_MG], a1[XA_MG];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
+              for (int u = 0; u < XA_MG; ++u) {
                 const bool in = s0 + u < P;
                 const float* ps = part + (in ? s0 + u : s0) * 66;
                 mv[u] = in ? __ldcg(ps) : -INFINITY;
@@ -1182,9 +1185,16 @@ __device__ __forceinline__ void cross_attn_phase(const MkParams& p, int l, int x
                 a0[u] = __ldcg(ps + 2 + lane);
                 a1[u] = __ldcg(ps + 2 + lane + 32);
               }
+              float gm = mv[0];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const float w = exp2f(mv[u] - MM);  // a slot past P: 2^-inf = 0
+              for (int u = 1; u < XA_MG; ++u) gm = fmaxf(gm, mv[u]);
+              const float Mn = fmaxf(MM, gm);
+              const float sc = (Mn == MM) ? 1.f : exp2f(MM - Mn);  // first group: 2^-inf = 0 on zeros
+              LL *= sc; O0 *= sc; O1 *= sc;
+              MM = Mn;
+#pragma unroll
+              for (int u = 0; u < XA_MG; ++u) {
+                const float w = (mv[u] > -INFINITY) ? exp2f(mv[u] - MM) : 0.f;  // a slot past P
                 LL += w * lv[u];
                 O0 += w * a0[u];
                 O1 += w * a1[u];
