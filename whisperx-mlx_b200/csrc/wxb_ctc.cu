@@ -296,9 +296,14 @@ ctc_align_kernel(const float* __restrict__ emis, const int* __restrict__ tok,
   const float lp0 = E[(size_t)t * V + blank];
   int K = 0;
   while (nb > 0 && bj[0] > 0) {
-    int cj[2 * WMAX], cp[2 * WMAX];
+    // Candidates sit in FIXED slots (2 i = beam i stays, 2 i + 1 = beam i changes) with a validity mask, so every array index
+    // below is a compile-time constant and the step's state lives in registers; compacting them with a running count put the
+    // four arrays in local memory.  Slot order = the reference's generation order, which is what the stable sort keeps on ties.
+    int cj[2 * WMAX];
     float cs[2 * WMAX], cl[2 * WMAX];
-    int nc = 0;
+    unsigned valid = 0u;
+#pragma unroll
+    for (int i = 0; i < 2 * WMAX; ++i) { cj[i] = 0; cs[i] = 0.f; cl[i] = 0.f; }
     if (t > 0) {
       const float* erow = E + (size_t)(t - 1) * V;
       const float* trow = TR + (size_t)(t - 1) * N;
@@ -319,37 +324,35 @@ ctc_align_kernel(const float* __restrict__ emis, const int* __restrict__ tok,
       }
 #pragma unroll
       for (int i = 0; i < WMAX; ++i) {
-        if (i >= nb) break;
-        const int j = bj[i];
-        const float stay_score = ss[i];
-        if (!isinf(stay_score)) { cj[nc] = j; cs[nc] = stay_score; cp[nc] = i; cl[nc] = p_stay; nc++; }
-        if (j > 0) {
-          const float change_score = sc[i];
-          if (!isinf(change_score)) {
+        if (i < nb) {
+          const int j = bj[i];
+          if (!isinf(ss[i])) { cj[2 * i] = j; cs[2 * i] = ss[i]; cl[2 * i] = p_stay; valid |= 1u << (2 * i); }
+          if (j > 0 && !isinf(sc[i])) {
             const float p_change = (stok[j] < 0) ? wild_max_global(erow, V, blank, lane) : pc[i];
-            cj[nc] = j - 1; cs[nc] = change_score; cp[nc] = i; cl[nc] = p_change; nc++;
+            cj[2 * i + 1] = j - 1; cs[2 * i + 1] = sc[i]; cl[2 * i + 1] = p_change; valid |= 1u << (2 * i + 1);
           }
         }
       }
     }
     // stable descending top-W: repeatedly take the first not-yet-taken candidate with the largest score
+    const int nc = __popc(valid);
     nb = nc < W ? nc : W;
     t -= 1;
     K += 1;
-    unsigned taken = 0u;
 #pragma unroll
     for (int s2 = 0; s2 < WMAX; ++s2) {
-      if (s2 >= nb) break;
-      int best = -1;
-      float best_s = 0.f;
-      int best_j = 0, best_p = 0;
-      float best_l = 0.f;
+      if (s2 < nb) {
+        int best = -1;
+        float best_s = 0.f;
+        int best_j = 0;
+        float best_l = 0.f;
 #pragma unroll
-      for (int i = 0; i < 2 * WMAX; ++i)
-        if (i < nc && !((taken >> i) & 1u) && (best < 0 || cs[i] > best_s)) { best = i; best_s = cs[i]; best_j = cj[i]; best_p = cp[i]; best_l = cl[i]; }
-      taken |= 1u << best;
-      bj[s2] = best_j;
-      if (lane == 0) H[(size_t)K * W + s2] = make_int2(best_j | (best_p << 28), __float_as_int(best_l));
+        for (int i = 0; i < 2 * WMAX; ++i)
+          if (((valid >> i) & 1u) && (best < 0 || cs[i] > best_s)) { best = i; best_s = cs[i]; best_j = cj[i]; best_l = cl[i]; }
+        valid &= ~(1u << best);
+        bj[s2] = best_j;
+        if (lane == 0) H[(size_t)K * W + s2] = make_int2(best_j | ((best >> 1) << 28), __float_as_int(best_l));
+      }
     }
   }
   if (nb == 0) {
