@@ -132,6 +132,17 @@ def decode_bytes_per_step(dims, B, t_mean):
     return weights, cross, selfkv
 
 
+def workload_config(model_name, minutes, n_chunks, world, n_mine, batch_size, sample_len, align_note):
+    """The job both arms are measured on, in words (the reference arm times a bounded sample of it on the host cores)."""
+    return {"workload": f"whisper-{model_name} (random-init), ONE {minutes:g} min synthetic recording = {n_chunks} x 30 s VAD chunks "
+                        f"dealt to {world} GPU(s) (LPT queues, {n_mine} chunks on rank 0), batch {min(batch_size, n_mine)}, log-mel + "
+                        f"encoder + greedy decode ({sample_len} positions) + {align_note}",
+            "batch_size": batch_size, "parallelism": f"{world} x 1 GPU, chunk-sharded, host gather only (no collective)"}
+
+
+ALIGN_NOTE = "wav2vec2-base forward (own kernels, random-init) + CTC beam-2 alignment"
+
+
 # --------------------------------------------------------------------------------------------------
 def run_reference(args):
     """The reference's CPU implementation of the path (oracle port), all host threads, bounded sample per step."""
@@ -149,6 +160,8 @@ def run_reference(args):
     emis, toks = align_inputs(n_chunks, 1234)
     n = args.cpu_chunks
     chunks = [audio[i * 480000:(i + 1) * 480000] for i in range(n)]
+    world = max(1, int(os.environ.get("WORLD_SIZE", str(args.gpus))))
+    n_mine = -(-n_chunks // world)  # the LPT deal of equal chunks gives rank 0 the ceiling
     prompt = [sp["sot"], sp["sot"] + 1, sp["transcribe"], sp["no_timestamps"]]
     times = []
     for it in range(args.warmup + args.steps):
@@ -164,8 +177,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "large-v3 RTFx (audio s / wall s)", "value": value, "unit": "x realtime",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"whisper-{args.model}, {args.minutes:g} min synthetic audio, 30 s VAD chunks (bounded sample per step)",
-                       "parallelism": "cpu"},
+            "config": {**workload_config(args.model, args.minutes, n_chunks, world, n_mine, args.batch_size, dims["n_text_ctx"] // 2, ALIGN_NOTE),
+                       "arm": "the same job's hot path on the host cores (oracle port), a bounded sample per step: " + sample +
+                              "; the wav2vec2 forward is not in the CPU sample"},
             "cpu_baseline": {"value": value, "unit": "x realtime", "cores": torch.get_num_threads(), "kind": "port", "sample": sample,
                              "stage_seconds": parts},
             "e2e": {"value": value, "unit": "x realtime", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -590,15 +604,12 @@ def main():
                                   "the wav2vec2 forward is not in the CPU sample)",
                         "seconds": sec, "stage_seconds": parts}
 
-    align_note = ("wav2vec2-base forward (own kernels, random-init) + CTC beam-2 alignment" if align_bundle is not None
+    align_note = (ALIGN_NOTE if align_bundle is not None
                   else "no alignment leg (--no-align)")
     line = {"metric": "large-v3 RTFx (audio s / wall s)", "value": value, "unit": "x realtime", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": r["ms_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"whisper-{be.model_name} (random-init), ONE {args.minutes:g} min synthetic recording = {n_chunks} x 30 s VAD chunks "
-                                   f"dealt to {world} GPU(s) (LPT queues, {n_mine} chunks on rank 0), batch {min(args.batch_size, n_mine)}, log-mel + "
-                                   f"encoder + greedy decode ({job.sample_len} positions) + {align_note}",
-                       "batch_size": args.batch_size, "parallelism": f"{world} x 1 GPU, chunk-sharded, host gather only (no collective)",
+            "config": {**workload_config(be.model_name, args.minutes, n_chunks, world, n_mine, args.batch_size, job.sample_len, align_note),
                        "l2": "256 MB flush buffer written before every step", "library": lib_path, "env": env_seen,
                        **({"dec_groups": args.dec_groups} if args.dec_groups else {}),
                        **({"dec_group_delay_ns": args.dec_group_delay_ns} if args.dec_group_delay_ns >= 0 else {}),
