@@ -39,9 +39,18 @@ def gather_results(local: Dict, rank: int, world_size: int, dst: int = 0):
     merged.sort(key=lambda s: (s["start"], s["end"]))
     out = {"segments": merged, "language": bucket[0].get("language", "en")}
     if any("word_segments" in r for r in bucket):
-        words = [w for r in bucket for w in r.get("word_segments", [])]
-        out["word_segments"] = sorted(words, key=lambda w: (w.get("start", float("inf"))))
+        out["word_segments"] = _merge_words(bucket, merged)
     return out
+
+
+def _merge_words(bucket, merged) -> List[Dict]:
+    """"word_segments" of the gathered result.  align() builds it by concatenating the segments' "words" in segment order
+    (alignment.py:375-378); when every rank's list is exactly that, the same concatenation over the merged (start-sorted)
+    segments is the single-process answer and needs no sort of the words.  Lists built any other way are merged by start time."""
+    if all(len(r.get("word_segments", [])) == sum(len(s.get("words") or ()) for s in r["segments"]) for r in bucket):
+        return [w for s in merged for w in (s.get("words") or ())]
+    words = [w for r in bucket for w in r.get("word_segments", [])]
+    return sorted(words, key=lambda w: (w.get("start", float("inf"))))
 
 
 def plain_numbers(result: Dict) -> Dict:
@@ -97,6 +106,5 @@ def transcribe_sharded(pipeline, audio, rank: int, world_size: int, batch_size: 
     merged.sort(key=lambda s: (s["start"], s["end"]))
     out = {"segments": merged, "language": bucket[0].get("language", "en")}
     if any("word_segments" in r for r in bucket):
-        words = [w for r in bucket for w in r.get("word_segments", [])]
-        out["word_segments"] = sorted(words, key=lambda w: (w.get("start", float("inf"))))
+        out["word_segments"] = _merge_words(bucket, merged)
     return out
