@@ -364,6 +364,10 @@ def align(
 
     _mark("segments prepared")
     # ---- pass 1: emissions of every alignable segment, kept on the device ------------------
+    ascii_lut = np.full(128, -1, dtype=np.int32)  # dictionary code of every single ASCII character (-1 = wildcard)
+    for ch, code in dictionary.items():
+        if len(ch) == 1 and ord(ch) < 128:
+            ascii_lut[ord(ch)] = code
     jobs = []  # (sdx, text_clean, tokens, T)
     emis_parts, tok_parts = [], []
     skip_reason = {}
@@ -378,7 +382,10 @@ def align(
             skip_reason[sdx] = "original start time longer than audio duration, skipping..."
             continue
         text_clean = "".join(prepared[sdx]["clean_char"])
-        tokens = [dictionary.get(c, -1) for c in text_clean]
+        if text_clean.isascii():  # one table look-up per segment instead of a dict look-up per character
+            tokens = ascii_lut[np.frombuffer(text_clean.encode("ascii"), dtype=np.uint8)]
+        else:
+            tokens = [dictionary.get(c, -1) for c in text_clean]
         f1, f2 = int(t1 * SAMPLE_RATE), int(t2 * SAMPLE_RATE)
         wave = audio[:, f1:f2]
         if native:
